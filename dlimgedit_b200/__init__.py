@@ -1,0 +1,383 @@
+"""dlimgedit_b200 -- Python mirror of dlimgedit's public C++ façade for the segmentation hot path
+(reference src/include/dlimgedit/dlimgedit.hpp:16-193), bound with ctypes to the C ABI of the
+B200-native engine (include/dlimg_b200.h -> dlimgedit_b200/libdlimgedit.so).
+
+The classes keep the reference's names, argument meaning and error behaviour (dlimg::Exception ->
+`dlimgedit_b200.Exception`).  There is NO CPU / PyTorch fallback: importing works without the built
+library (so CPU-only tooling can import the package), but every call fails loudly if
+libdlimgedit.so is missing or no Blackwell GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdlimgedit.so")
+WEIGHT_FILE_NAME = "mobile_sam_b200.bin"
+
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_i32p = ctypes.POINTER(ctypes.c_int)
+
+
+class Exception(RuntimeError):  # noqa: A001 - mirrors dlimg::Exception (dlimgedit.hpp:184)
+    pass
+
+
+class Channels(enum.IntEnum):  # dlimgedit.hpp:29
+    mask = 1
+    rgb = 3
+    rgba = 4
+    bgra = 5
+    argb = 6
+
+
+def count(c: Channels) -> int:  # dlimgedit.impl.hpp:15
+    return 4 if int(c) > 4 else int(c)
+
+
+class Backend(enum.IntEnum):  # dlimgedit.hpp:88
+    cpu = 0
+    gpu = 1
+
+
+@dataclass
+class Extent:
+    width: int = 0
+    height: int = 0
+
+
+@dataclass
+class Point:  # dlimgedit.hpp:119
+    x: int = 0
+    y: int = 0
+
+
+@dataclass
+class Region:  # dlimgedit.hpp:125-134
+    top_left: Point
+    bottom_right: Point
+
+    @staticmethod
+    def from_origin(origin: Point, extent: Extent) -> "Region":
+        return Region(origin, Point(origin.x + extent.width, origin.y + extent.height))
+
+
+# ---- C structures (include/dlimg_b200.h) -------------------------------------------------------
+class _ImageView(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("channels", ctypes.c_int),
+                ("stride", ctypes.c_int), ("pixels", ctypes.c_void_p)]
+
+
+class _Options(ctypes.Structure):
+    _fields_ = [("backend", ctypes.c_int), ("model_directory", ctypes.c_char_p)]
+
+
+class _Prompt(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("x0", ctypes.c_int), ("y0", ctypes.c_int), ("x1", ctypes.c_int),
+                ("y1", ctypes.c_int)]
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [("kernel_launches", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
+
+
+_R = ctypes.c_int  # dlimg_Result
+_H = ctypes.c_void_p  # opaque handles
+_F = ctypes.CFUNCTYPE
+
+
+class _Api(ctypes.Structure):  # 13 slots, order of dlimgedit.h:44-68
+    _fields_ = [
+        ("is_backend_supported", _F(ctypes.c_int, ctypes.c_int)),
+        ("create_environment", _F(_R, ctypes.POINTER(_H), ctypes.POINTER(_Options))),
+        ("destroy_environment", _F(None, _H)),
+        ("process_image_for_segmentation", _F(_R, ctypes.POINTER(_H), ctypes.POINTER(_ImageView), _H)),
+        ("get_segmentation_mask", _F(_R, _H, c_i32p, c_i32p, ctypes.POINTER(ctypes.c_void_p), c_f32p)),
+        ("get_segmentation_extent", _F(None, _H, c_i32p)),
+        ("destroy_segmentation", _F(None, _H)),
+        ("segment_objects", _F(_R, ctypes.POINTER(_ImageView), ctypes.c_void_p, _H)),
+        ("load_image", _F(_R, ctypes.c_char_p, c_i32p, c_i32p, ctypes.POINTER(ctypes.c_void_p))),
+        ("save_image", _F(_R, ctypes.POINTER(_ImageView), ctypes.c_char_p)),
+        ("create_image", _F(ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int)),
+        ("destroy_image", _F(None, ctypes.c_void_p)),
+        ("last_error", _F(ctypes.c_char_p)),
+    ]
+
+
+class _Ext(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("abi_version", ctypes.c_uint32),
+        ("set_stream", _F(_R, _H, ctypes.c_void_p)),
+        ("synchronize", _F(_R, _H)),
+        ("get_stats", _F(_R, _H, ctypes.POINTER(_Stats))),
+        ("process_batch", _F(_R, _H, ctypes.POINTER(_ImageView), ctypes.c_int, ctypes.c_int, ctypes.POINTER(_H))),
+        ("compute_masks_batch", _F(_R, _H, ctypes.POINTER(_H), ctypes.POINTER(_Prompt), ctypes.c_int, ctypes.c_int,
+                                   ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int)),
+        ("get_embedding", _F(_R, _H, c_f32p)),
+        ("get_low_res_logits", _F(_R, _H, ctypes.POINTER(_Prompt), c_f32p, c_f32p)),
+        ("resize_longest_side", _F(_R, _H, ctypes.POINTER(_ImageView), ctypes.c_int, ctypes.c_void_p, c_i32p)),
+        ("image_tensor", _F(_R, _H, ctypes.POINTER(_ImageView), ctypes.c_void_p)),
+        ("mask_postprocess", _F(_R, _H, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p)),
+        ("threshold_mask", _F(_R, _H, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                              ctypes.c_void_p)),
+    ]
+
+
+class _Debug(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("gemm", _F(_R, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                    ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                    ctypes.c_int, ctypes.c_void_p)),
+        ("encode_tap", _F(_R, _H, ctypes.POINTER(_ImageView), ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p,
+                          ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t))),
+        ("resize_plan", _F(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i32p, c_f32p)),
+        ("srgb_tables", _F(None, c_f32p, c_f32p)),
+    ]
+
+
+EXPORTED_SYMBOLS = ("dlimg_init", "dlimg_b200_ext_init", "dlimg_b200_debug_init")
+
+_lib = None
+_api: Optional[_Api] = None
+_ext: Optional[_Ext] = None
+_dbg: Optional[_Debug] = None
+
+
+def load_library():
+    """dlopen libdlimgedit.so and resolve the tables (the dynamic-loading route of dlimgedit.hpp:178-181)."""
+    global _lib, _api, _ext, _dbg
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Exception(f"{LIB_PATH} is missing: build it with `python -m dlimgedit_b200._build` "
+                            "(there is no CPU or PyTorch fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.dlimg_init.restype = ctypes.POINTER(_Api)
+        lib.dlimg_b200_ext_init.restype = ctypes.POINTER(_Ext)
+        lib.dlimg_b200_debug_init.restype = ctypes.POINTER(_Debug)
+        _api = lib.dlimg_init().contents
+        _ext = lib.dlimg_b200_ext_init().contents
+        _dbg = lib.dlimg_b200_debug_init().contents
+        assert _ext.struct_size == ctypes.sizeof(_Ext), "dlimg_b200_Ext layout mismatch"
+        assert _dbg.struct_size == ctypes.sizeof(_Debug), "dlimg_b200_Debug layout mismatch"
+        _lib = lib
+    return _lib
+
+
+def api() -> _Api:
+    load_library()
+    return _api
+
+
+def ext() -> _Ext:
+    load_library()
+    return _ext
+
+
+def debug() -> _Debug:
+    load_library()
+    return _dbg
+
+
+def _check(result: int):
+    if result != 0:
+        raise Exception(api().last_error().decode(errors="replace"))
+
+
+# ---- façade ------------------------------------------------------------------------------------
+class ImageView:
+    """Read-only view of pixels (dlimgedit.hpp:36-45).  `pixels` is a numpy uint8 array (host) or an
+    integer device address when `device=True`; `stride` is in bytes (default width * count(channels))."""
+
+    def __init__(self, pixels, extent: Extent = None, channels: Channels = Channels.rgba, stride: int = 0,
+                 device: bool = False):
+        self.device = device
+        self.channels = Channels(channels)
+        if device:
+            assert extent is not None
+            self._addr = int(pixels)
+            self._keep = None
+        else:
+            arr = np.asarray(pixels)
+            assert arr.dtype == np.uint8
+            if extent is None:
+                extent = Extent(arr.shape[1], arr.shape[0])
+            if not stride and arr.ndim >= 2:
+                arr = np.ascontiguousarray(arr)
+            self._keep = arr
+            self._addr = arr.ctypes.data
+        self.extent = extent
+        self.stride = stride or extent.width * count(self.channels)
+
+    def to_c(self) -> _ImageView:
+        return _ImageView(self.extent.width, self.extent.height, int(self.channels), self.stride, self._addr)
+
+
+class Options:  # dlimgedit.hpp:91-96
+    def __init__(self, backend: Backend = Backend.cpu, model_directory: str = "models"):
+        self.backend = backend
+        self.model_directory = model_directory
+
+
+class Environment:
+    """dlimgedit.hpp:102-113.  Models are loaded on first use; must outlive its Segmentations."""
+
+    @staticmethod
+    def is_supported(backend: Backend) -> bool:
+        return api().is_backend_supported(int(backend)) != 0
+
+    def __init__(self, options: Options = None):
+        options = options or Options()
+        self._h = _H()
+        self._dir = options.model_directory.encode()
+        opts = _Options(int(options.backend), self._dir)
+        _check(api().create_environment(ctypes.byref(self._h), ctypes.byref(opts)))
+
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            api().destroy_environment(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except BaseException:
+            pass
+
+    # -- additive extension -----------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        _check(ext().set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        _check(ext().synchronize(self._h))
+
+    def stats(self) -> dict:
+        s = _Stats()
+        _check(ext().get_stats(self._h, ctypes.byref(s)))
+        return {"kernel_launches": s.kernel_launches, "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes}
+
+    def process_batch(self, views: Sequence[ImageView]) -> List["Segmentation"]:
+        n = len(views)
+        on_device = views[0].device
+        assert all(v.device == on_device for v in views)
+        arr = (_ImageView * n)(*[v.to_c() for v in views])
+        out = (_H * n)()
+        r = ext().process_batch(self._h, arr, n, int(on_device), out)
+        segs = [Segmentation._wrap(out[i], self) for i in range(n) if out[i]]
+        _check(r)
+        return segs
+
+    def compute_masks_batch(self, segs: Sequence["Segmentation"], prompts: Sequence, multi: bool = False,
+                            masks_out: Sequence[int] = None, ious_out: int = 0):
+        """Host mode (masks_out None): returns (list of uint8 arrays (n, H, W), float32 array (count, n)).
+        Device mode: masks_out = device addresses (one per prompt, n*W*H bytes), ious_out = device address."""
+        cnt = len(prompts)
+        n = 3 if multi else 1
+        harr = (_H * cnt)(*[s._h for s in segs])
+        parr = (_Prompt * cnt)(*[_to_prompt(p) for p in prompts])
+        if masks_out is None:
+            outs = [np.empty((n, s.extent().height, s.extent().width), np.uint8) for s in segs]
+            ptrs = (ctypes.c_void_p * cnt)(*[o.ctypes.data for o in outs])
+            ious = np.zeros((cnt, n), np.float32)
+            _check(ext().compute_masks_batch(self._h, harr, parr, cnt, int(multi), ptrs,
+                                             ctypes.c_void_p(ious.ctypes.data), 0))
+            return outs, ious
+        ptrs = (ctypes.c_void_p * cnt)(*[int(a) for a in masks_out])
+        _check(ext().compute_masks_batch(self._h, harr, parr, cnt, int(multi), ptrs, ctypes.c_void_p(ious_out), 1))
+        return None
+
+
+def _to_prompt(p) -> _Prompt:
+    if isinstance(p, Point):
+        return _Prompt(0, p.x, p.y, 0, 0)
+    if isinstance(p, Region):
+        return _Prompt(1, p.top_left.x, p.top_left.y, p.bottom_right.x, p.bottom_right.y)
+    raise TypeError("prompt must be Point or Region")
+
+
+class Segmentation:
+    """dlimgedit.hpp:138-168: an image embedding that can be queried for masks."""
+
+    def __init__(self):
+        self._h = None
+        self._env = None
+
+    @staticmethod
+    def _wrap(h, env) -> "Segmentation":
+        s = Segmentation()
+        s._h = _H(h)
+        s._env = env
+        return s
+
+    @staticmethod
+    def process(img: ImageView, env: Environment) -> "Segmentation":
+        assert not img.device, "Segmentation.process takes host pixels (use Environment.process_batch for device data)"
+        h = _H()
+        view = img.to_c()
+        r = api().process_image_for_segmentation(ctypes.byref(h), ctypes.byref(view), env.handle())
+        seg = Segmentation._wrap(h.value, env) if h else None  # the handle is owned even when the call failed
+        _check(r)
+        return seg
+
+    def extent(self) -> Extent:
+        e = (ctypes.c_int * 2)()
+        api().get_segmentation_extent(self._h, e)
+        return Extent(e[0], e[1])
+
+    def _mask_call(self, point, region, n_masks):
+        e = self.extent()
+        masks = [np.empty((e.height, e.width), np.uint8) for _ in range(n_masks)]
+        ptrs = (ctypes.c_void_p * 3)(*[m.ctypes.data for m in masks] + [None] * (3 - n_masks))
+        ious = (ctypes.c_float * 3)(0.0, 0.0, 0.0)
+        pt = (ctypes.c_int * 2)(point.x, point.y) if point is not None else None
+        rg = (ctypes.c_int * 4)(region.top_left.x, region.top_left.y, region.bottom_right.x,
+                                region.bottom_right.y) if region is not None else None
+        _check(api().get_segmentation_mask(self._h, pt, rg, ptrs, ious))
+        return masks, [ious[i] for i in range(3)]
+
+    def compute_mask(self, prompt) -> np.ndarray:
+        """Point -> best mask; Region -> mask of the largest object in the box.  uint8 (H, W), 0 / 255."""
+        if isinstance(prompt, Point):
+            return self._mask_call(prompt, None, 1)[0][0]
+        if isinstance(prompt, Region):
+            return self._mask_call(None, prompt, 1)[0][0]
+        raise TypeError("prompt must be Point or Region")
+
+    def compute_masks(self, point: Point) -> List[Tuple[np.ndarray, float]]:
+        masks, ious = self._mask_call(point, None, 3)
+        return list(zip(masks, ious))
+
+    # -- additive extension -----------------------------------------------------------------------
+    def embedding(self) -> np.ndarray:
+        out = np.empty((1, 256, 64, 64), np.float32)
+        _check(ext().get_embedding(self._h, out.ctypes.data_as(c_f32p)))
+        return out
+
+    def low_res_logits(self, prompt) -> Tuple[np.ndarray, np.ndarray]:
+        logits = np.empty((4, 256, 256), np.float32)
+        iou = np.empty((4,), np.float32)
+        p = _to_prompt(prompt)
+        _check(ext().get_low_res_logits(self._h, ctypes.byref(p), logits.ctypes.data_as(c_f32p), iou.ctypes.data_as(c_f32p)))
+        return logits, iou
+
+    def close(self):
+        if getattr(self, "_h", None):
+            api().destroy_segmentation(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except BaseException:
+            pass

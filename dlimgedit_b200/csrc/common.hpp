@@ -1,0 +1,78 @@
+// common.hpp -- error handling, small utilities shared by host and device translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace dlimg {
+
+// Mirrors dlimg::Exception of the reference façade (dlimgedit.hpp:184-191): everything thrown inside
+// the library derives from std::exception and is mapped to dlimg_error at the C boundary.
+class Error : public std::runtime_error {
+  public:
+    explicit Error(std::string const& msg) : std::runtime_error(msg) {}
+};
+
+[[noreturn]] inline void fail(std::string const& msg) { throw Error(msg); }
+
+// Same contract as the reference's ASSERT (assert.hpp:17-28): report on stderr and throw.
+#define DLIMG_ASSERT(cond)                                                                           \
+    do {                                                                                             \
+        if (!(cond)) {                                                                               \
+            std::fprintf(stderr, "Assertion failed at %s:%d: %s\n", __FILE__, __LINE__, #cond);      \
+            throw ::dlimg::Error(std::string("Assertion failed: ") + #cond);                         \
+        }                                                                                            \
+    } while (0)
+
+#define CUDA_CHECK(expr)                                                                             \
+    do {                                                                                             \
+        cudaError_t err__ = (expr);                                                                  \
+        if (err__ != cudaSuccess) {                                                                  \
+            throw ::dlimg::Error(std::string("CUDA error ") + cudaGetErrorName(err__) + " (" +       \
+                                 cudaGetErrorString(err__) + ") at " + __FILE__ + ":" +              \
+                                 std::to_string(__LINE__) + ": " #expr);                             \
+        }                                                                                            \
+    } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up64(int64_t a, int64_t b) { return ceil_div64(a, b) * b; }
+
+// Channels enum values carried in dlimg_ImageView::channels (reference dlimgedit.hpp:29).
+enum : int { CH_MASK = 1, CH_RGB = 3, CH_RGBA = 4, CH_BGRA = 5, CH_ARGB = 6 };
+inline int bytes_per_pixel(int channels) { return channels > 4 ? 4 : channels; } // impl.hpp:15
+inline bool valid_channels(int c) { return c == 1 || c == 3 || c == 4 || c == 5 || c == 6; }
+
+// Source byte offsets of R, G, B inside a pixel (reference segmentation.cpp:82-95).
+inline void channel_map(int channels, int cmap[3]) {
+    cmap[0] = 0; cmap[1] = 1; cmap[2] = 2;
+    if (channels == CH_MASK) { cmap[0] = cmap[1] = cmap[2] = 0; }
+    else if (channels == CH_BGRA) { cmap[0] = 2; cmap[1] = 1; cmap[2] = 0; }
+    else if (channels == CH_ARGB) { cmap[0] = 1; cmap[1] = 2; cmap[2] = 3; }
+}
+
+constexpr int kImageSize = 1024;   // reference segmentation.cpp:17
+constexpr int kEmbedDim = 256;     // image embedding channels
+constexpr int kEmbedRes = 64;      // image embedding spatial size
+constexpr int kLowRes = 256;       // low-resolution mask size
+
+} // namespace dlimg
+
+#include <atomic>
+namespace dlimg {
+// Process-wide tally of kernels launched by this library (reported through dlimg_b200_Ext::get_stats).
+extern std::atomic<uint64_t> g_kernel_launches;
+extern std::atomic<uint64_t> g_h2d_bytes;
+extern std::atomic<uint64_t> g_d2h_bytes;
+inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+// Launch-configuration errors surface immediately; execution errors at the next synchronising call.
+#define KERNEL_CHECK()                                                                               \
+    do {                                                                                             \
+        ::dlimg::count_launch();                                                                     \
+        CUDA_CHECK(cudaGetLastError());                                                              \
+    } while (0)
+} // namespace dlimg

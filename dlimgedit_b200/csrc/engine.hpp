@@ -1,0 +1,131 @@
+// engine.hpp -- host-side objects behind the C ABI: EnvironmentImpl (device context, weights, workspaces)
+// and SegmentationImpl (one encoded image).  They take the place of the reference's EnvironmentImpl
+// (environment.hpp:20-42), Session (session.hpp:32-57) and SegmentationImpl (segmentation.hpp:47-62).
+#pragma once
+
+#include "../../include/dlimg_b200.h"
+#include "common.hpp"
+#include "kernels/prepost_kernels.cuh"
+#include "model.hpp"
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace dlimg {
+
+class SegmentationImpl;
+
+struct DeviceAxisPlan {
+    DeviceBuffer<int> first;
+    DeviceBuffer<float> weights;
+    int taps = 0;
+};
+
+// Page-locked host arena for small parameter uploads (prompt coordinates, descriptors, pointer tables).
+class PinnedArena {
+  public:
+    explicit PinnedArena(size_t bytes);
+    ~PinnedArena();
+    // Returns `bytes` of pinned memory; when the arena wraps it first waits for `stream` so that earlier
+    // asynchronous copies out of the arena have completed.
+    void* take(size_t bytes, cudaStream_t stream);
+
+  private:
+    uint8_t* base_ = nullptr;
+    size_t cap_ = 0, off_ = 0;
+};
+
+class EnvironmentImpl {
+  public:
+    explicit EnvironmentImpl(dlimg_Options const& opts);
+    ~EnvironmentImpl();
+
+    static bool is_supported(dlimg_Backend backend);
+    static int device_ordinal();  // $DLIMG_B200_DEVICE or 0
+
+    SamModel& model();  // loaded on first use (reference lazy.hpp:10-13)
+    cudaStream_t stream() const { return user_stream_ ? user_stream_ : own_stream_; }
+    void set_stream(cudaStream_t s) { user_stream_ = s; }
+    void bind_device() const;
+
+    // Encodes `count` images (host or device pixels) and fills `out` with new handles.
+    void process_batch(dlimg_ImageView const* views, int count, bool on_device, SegmentationImpl** out);
+    // Prompts -> masks.  See dlimg_b200_Ext::compute_masks_batch.
+    void compute_masks_batch(SegmentationImpl* const* segs, dlimg_b200_Prompt const* prompts, int count, bool multi,
+                             uint8_t* const* masks_out, float* ious_out, bool on_device);
+    void low_res_logits(SegmentationImpl& seg, dlimg_b200_Prompt const& prompt, float* logits_host, float* iou_host);
+
+    // Stand-alone stages (device pointers)
+    void resize_longest_side(dlimg_ImageView const& dev_view, int max_side, uint8_t* dev_out, int* out_extent);
+    void image_tensor(dlimg_ImageView const& dev_view, float* dev_out);
+    void mask_postprocess(float const* dev_low_res, int count, int w, int h, uint8_t* dev_out);
+    void threshold_mask(float const* dev_logits, int th, int tw, int w, int h, uint8_t* dev_out);
+
+    // debug: encode one device-resident image and copy a named activation (see model.cu tap names)
+    size_t encode_tap(dlimg_ImageView const* dev_views, int count, char const* tap_name, float* dev_out, size_t capacity);
+
+    std::mutex& mutex() { return mutex_; }
+    int max_batch() const { return max_batch_; }
+    int max_prompts() const { return max_prompts_; }
+
+  private:
+    friend class SegmentationImpl;
+    EncoderWorkspace& encoder_ws();
+    DecoderWorkspace& decoder_ws();
+    prepost::ResizeDeviceTables resize_tables(int in_w, int in_h, int out_w, int out_h);
+    DeviceAxisPlan const& axis_plan(int in_size, int out_size);
+    void encode_chunk(enc::ImageDesc const* host_descs, int batch, prepost::LongestSide const& size, int channels,
+                      float* emb_out, Tap* tap);
+    uint8_t* prepare_input(dlimg_ImageView const& view, bool on_device, prepost::LongestSide const& size, int slot,
+                           enc::ImageDesc& desc);
+
+    int device_ = 0;
+    int num_sms_ = 148;
+    std::string model_dir_;
+    std::mutex mutex_;       // serialises GPU submission per environment (Environment is thread-safe)
+    std::once_flag model_once_;
+    std::unique_ptr<SamModel> model_;
+    cudaStream_t own_stream_ = nullptr;
+    cudaStream_t user_stream_ = nullptr;
+    int max_batch_ = 8;
+    int max_prompts_ = 32;
+    std::unique_ptr<EncoderWorkspace> enc_ws_;
+    std::unique_ptr<DecoderWorkspace> dec_ws_;
+    std::unique_ptr<PinnedArena> pinned_;
+    DeviceBuffer<uint8_t> input_px_;      // uploaded originals, max_batch slots
+    DeviceBuffer<uint8_t> resized_px_;    // resized images (<= 1024 x 1024 x 4 each), max_batch slots
+    DeviceBuffer<float> resize_scratch_;  // horizontal-pass intermediate
+    size_t input_slot_bytes_ = 0;
+    DeviceBuffer<enc::ImageDesc> descs_;
+    DeviceBuffer<float> srgb_decode_, srgb_threshold_;
+    std::map<std::pair<int, int>, DeviceAxisPlan> plans_;
+    DeviceBuffer<uint8_t> mask_out_;       // device staging for host-destined masks
+    DeviceBuffer<uint8_t*> plane_ptrs_;
+};
+
+class SegmentationImpl {
+  public:
+    explicit SegmentationImpl(EnvironmentImpl& env) : env_(env) {}
+
+    void process(dlimg_ImageView const& view);  // reference segmentation.cpp:121-129
+    void compute_mask(int const* point, int const* region, uint8_t** out_masks, float* out_accuracy);  // :131-174
+    void embedding_nchw(float* out_host);
+
+    int width() const { return size_.orig_w; }
+    int height() const { return size_.orig_h; }
+    bool encoded() const { return emb_ != nullptr; }
+    EnvironmentImpl& environment() { return env_; }
+
+  private:
+    friend class EnvironmentImpl;
+    EnvironmentImpl& env_;
+    prepost::LongestSide size_;
+    std::shared_ptr<DeviceBuffer<float>> emb_store_;  // shared by the images of one encoder chunk
+    float* emb_ = nullptr;                            // (4096, 256) fp32 token-major
+    EmbeddingCache cache_;
+};
+
+}  // namespace dlimg

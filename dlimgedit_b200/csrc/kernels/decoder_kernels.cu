@@ -1,0 +1,511 @@
+// decoder_kernels.cu -- see decoder_kernels.cuh.
+#include "decoder_kernels.cuh"
+
+namespace dlimg {
+namespace dec {
+
+namespace {
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// random-Fourier positional encoding of a point in [0,1]^2 (SAM PositionEmbeddingRandom._pe_encoding)
+__device__ __forceinline__ float pe_feature(float cx, float cy, float const* __restrict__ G, int j) {
+    int const jj = j & 127;
+    float const x = 2.0f * cx - 1.0f, y = 2.0f * cy - 1.0f;
+    float v = fmaf(y, G[128 + jj], x * G[jj]);
+    v *= 6.283185307179586f;
+    return j < 128 ? sinf(v) : cosf(v);
+}
+
+__global__ void __launch_bounds__(256) prompt_tokens_kernel(float const* __restrict__ coords, float const* __restrict__ labels,
+                                                            PromptParams pp, float* __restrict__ tokens) {
+    int const p = blockIdx.x, j = threadIdx.x;
+    float* out = tokens + (size_t)p * kTokens * kDim;
+    out[j] = pp.iou_token[j];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) out[(1 + m) * kDim + j] = pp.mask_tokens[m * kDim + j];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float const cx = (coords[(p * 2 + i) * 2 + 0] + 0.5f) / 1024.0f;
+        float const cy = (coords[(p * 2 + i) * 2 + 1] + 0.5f) / 1024.0f;
+        float const lab = labels[p * 2 + i];
+        float v = pe_feature(cx, cy, pp.gaussian, j);
+        v = v * (lab != -1.0f ? 1.0f : 0.0f);
+        v = v + pp.not_a_point[j] * (lab == -1.0f ? 1.0f : 0.0f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v = v + pp.point_embed[e * kDim + j] * (lab == (float)e ? 1.0f : 0.0f);
+        out[(5 + i) * kDim + j] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) dense_pe_kernel(float const* __restrict__ G, float* __restrict__ pos) {
+    int const tok = blockIdx.x, j = threadIdx.x;
+    int const iy = tok / kEmbedRes, ix = tok % kEmbedRes;
+    float const cx = ((float)ix + 0.5f) / (float)kEmbedRes, cy = ((float)iy + 0.5f) / (float)kEmbedRes;
+    pos[(size_t)tok * kDim + j] = pe_feature(cx, cy, G, j);
+}
+
+__global__ void embed_prepare_kernel(float const* __restrict__ emb, float const* __restrict__ no_mask,
+                                     float const* __restrict__ pos, int64_t total4, float* __restrict__ keys0,
+                                     float* __restrict__ kpe0) {
+    int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total4) return;
+    int const c4 = (int)(t % (kDim / 4));
+    int64_t const row = t / (kDim / 4);
+    float4 const e = reinterpret_cast<float4 const*>(emb)[t];
+    float4 const n = reinterpret_cast<float4 const*>(no_mask)[c4];
+    float4 const q = reinterpret_cast<float4 const*>(pos)[(row % kImgTokens) * (kDim / 4) + c4];
+    float4 const k = make_float4(e.x + n.x, e.y + n.y, e.z + n.z, e.w + n.w);
+    reinterpret_cast<float4*>(keys0)[t] = k;
+    reinterpret_cast<float4*>(kpe0)[t] = make_float4(k.x + q.x, k.y + q.y, k.z + q.z, k.w + q.w);
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kLinRows = 8;   // rows per block
+constexpr int kLinWarps = 8;
+constexpr int kLinColsPerBlock = 64;
+
+__global__ void __launch_bounds__(kLinWarps * 32) linear_small_kernel(float const* __restrict__ x, int64_t x_stride,
+                                                                      float const* __restrict__ x2, int64_t x2_stride,
+                                                                      int rows, int K, float const* __restrict__ W,
+                                                                      float const* __restrict__ b, int N, int relu,
+                                                                      float* __restrict__ y, int64_t y_stride) {
+    extern __shared__ float xs[];  // [kLinRows][K]
+    int const r0 = blockIdx.x * kLinRows;
+    for (int i = threadIdx.x; i < kLinRows * K; i += blockDim.x) {
+        int const r = i / K, k = i % K;
+        float v = 0.f;
+        if (r0 + r < rows) {
+            v = x[(int64_t)(r0 + r) * x_stride + k];
+            if (x2) v += x2[(int64_t)(r0 + r) * x2_stride + k];
+        }
+        xs[i] = v;
+    }
+    __syncthreads();
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int const n_end = min(N, (int)(blockIdx.y + 1) * kLinColsPerBlock);
+    for (int n = blockIdx.y * kLinColsPerBlock + warp; n < n_end; n += kLinWarps) {
+        float acc[kLinRows];
+#pragma unroll
+        for (int r = 0; r < kLinRows; ++r) acc[r] = 0.f;
+        float const* w = W + (int64_t)n * K;
+        for (int k = lane; k < K; k += 32) {
+            float const wv = __ldg(w + k);
+#pragma unroll
+            for (int r = 0; r < kLinRows; ++r) acc[r] = fmaf(xs[r * K + k], wv, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kLinRows; ++r) acc[r] = warp_sum(acc[r]);
+        if (lane < kLinRows && r0 + lane < rows) {
+            float v = 0.f;
+#pragma unroll
+            for (int r = 0; r < kLinRows; ++r) v = lane == r ? acc[r] : v;
+            if (b) v += b[n];
+            if (relu) v = fmaxf(v, 0.f);
+            y[(int64_t)(r0 + lane) * y_stride + n] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) token_self_attention_kernel(float const* __restrict__ q, float const* __restrict__ k,
+                                                                   float const* __restrict__ v, float* __restrict__ out) {
+    int const p = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    size_t const base = (size_t)p * kTokens * kDim + h * 32 + lane;
+    float kk[kTokens], vv[kTokens];
+#pragma unroll
+    for (int u = 0; u < kTokens; ++u) {
+        kk[u] = k[base + u * kDim];
+        vv[u] = v[base + u * kDim];
+    }
+    float const scale = 0.17677669529663687f;  // 1/sqrt(32)
+#pragma unroll
+    for (int t = 0; t < kTokens; ++t) {
+        float const qv = q[base + t * kDim];
+        float s[kTokens];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < kTokens; ++u) {
+            s[u] = warp_sum(qv * kk[u]) * scale;
+            mx = fmaxf(mx, s[u]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int u = 0; u < kTokens; ++u) {
+            s[u] = expf(s[u] - mx);
+            sum += s[u];
+        }
+        float o = 0.f;
+#pragma unroll
+        for (int u = 0; u < kTokens; ++u) o = fmaf(s[u] / sum, vv[u], o);
+        out[base + t * kDim] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kT2iThreads = 256;
+constexpr size_t kT2iSmem = sizeof(float) * ((size_t)kTokens * kImgTokens + kTokens * 16 + 8 * kTokens + kTokens + 2 * kTokens * 16);
+
+__global__ void __launch_bounds__(kT2iThreads) t2i_attention_kernel(float const* __restrict__ q, float const* __restrict__ K,
+                                                                    float const* __restrict__ V, int64_t kv_stride,
+                                                                    float* __restrict__ out) {
+    extern __shared__ float sm[];
+    float* S = sm;                                  // [7][4096]
+    float* qs = S + kTokens * kImgTokens;           // [7][16]
+    float* red = qs + kTokens * 16;                 // [8 warps][7]
+    float* stat = red + 8 * kTokens;                // [7]
+    float* part = stat + kTokens;                   // [2][7*16]
+    int const p = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
+    int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float const* Kp = K + (size_t)p * kv_stride + h * 16;
+    float const* Vp = V + (size_t)p * kv_stride + h * 16;
+    if (tid < kTokens * 16) qs[tid] = q[((size_t)p * kTokens + tid / 16) * 128 + h * 16 + (tid % 16)];
+    __syncthreads();
+    // phase A: scores + running max
+    float mx[kTokens];
+#pragma unroll
+    for (int t = 0; t < kTokens; ++t) mx[t] = -INFINITY;
+    for (int i = tid; i < kImgTokens; i += kT2iThreads) {
+        float kv[16];
+        float4 const* k4 = reinterpret_cast<float4 const*>(Kp + (size_t)i * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float4 const x = k4[c];
+            kv[4 * c] = x.x; kv[4 * c + 1] = x.y; kv[4 * c + 2] = x.z; kv[4 * c + 3] = x.w;
+        }
+#pragma unroll
+        for (int t = 0; t < kTokens; ++t) {
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) a = fmaf(qs[t * 16 + d], kv[d], a);
+            a *= 0.25f;  // 1/sqrt(16)
+            S[t * kImgTokens + i] = a;
+            mx[t] = fmaxf(mx[t], a);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kTokens; ++t) {
+        float const m = warp_max(mx[t]);
+        if (lane == 0) red[warp * kTokens + t] = m;
+    }
+    __syncthreads();
+    if (tid < kTokens) {
+        float m = red[tid];
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w * kTokens + tid]);
+        stat[tid] = m;
+    }
+    __syncthreads();
+    // phase B: exponentials + sums
+    float sum[kTokens];
+#pragma unroll
+    for (int t = 0; t < kTokens; ++t) sum[t] = 0.f;
+    for (int i = tid; i < kImgTokens; i += kT2iThreads) {
+#pragma unroll
+        for (int t = 0; t < kTokens; ++t) {
+            float const e = expf(S[t * kImgTokens + i] - stat[t]);
+            S[t * kImgTokens + i] = e;
+            sum[t] += e;
+        }
+    }
+    __syncthreads();  // everyone has read stat[] (max) before it is overwritten with the sums
+#pragma unroll
+    for (int t = 0; t < kTokens; ++t) {
+        float const v = warp_sum(sum[t]);
+        if (lane == 0) red[warp * kTokens + t] = v;
+    }
+    __syncthreads();
+    if (tid < kTokens) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w * kTokens + tid];
+        stat[tid] = v;
+    }
+    __syncthreads();
+    // phase C: out[t][d] = sum_i P[t][i] V[i][d] / sum[t]; two halves of the keys in parallel
+    if (tid < 2 * kTokens * 16) {
+        int const half = tid / (kTokens * 16), td = tid % (kTokens * 16);
+        int const t = td / 16, d = td % 16;
+        float a = 0.f;
+        int const i0 = half * (kImgTokens / 2);
+        float const* Srow = S + t * kImgTokens;
+#pragma unroll 4
+        for (int i = i0; i < i0 + kImgTokens / 2; ++i) a = fmaf(Srow[i], __ldg(Vp + (size_t)i * 128 + d), a);
+        part[half * kTokens * 16 + td] = a;
+    }
+    __syncthreads();
+    if (tid < kTokens * 16) {
+        int const t = tid / 16, d = tid % 16;
+        out[((size_t)p * kTokens + t) * 128 + h * 16 + d] = (part[tid] + part[kTokens * 16 + tid]) / stat[t];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) i2t_attention_kernel(float const* __restrict__ Q, int64_t q_stride,
+                                                            float const* __restrict__ kt, float const* __restrict__ vt,
+                                                            float* __restrict__ out) {
+    __shared__ float ks[kTokens * 128];
+    __shared__ float vs[kTokens * 128];
+    int const p = blockIdx.y;
+    for (int i = threadIdx.x; i < kTokens * 128; i += blockDim.x) {
+        ks[i] = kt[(size_t)p * kTokens * 128 + i];
+        vs[i] = vt[(size_t)p * kTokens * 128 + i];
+    }
+    __syncthreads();
+    int const idx = blockIdx.x * blockDim.x + threadIdx.x;  // (token, head)
+    int const i = idx >> 3, h = idx & 7;
+    float qv[16];
+    float4 const* q4 = reinterpret_cast<float4 const*>(Q + (size_t)p * q_stride + (size_t)i * 128 + h * 16);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float4 const x = q4[c];
+        qv[4 * c] = x.x; qv[4 * c + 1] = x.y; qv[4 * c + 2] = x.z; qv[4 * c + 3] = x.w;
+    }
+    float s[kTokens];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < kTokens; ++t) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) a = fmaf(qv[d], ks[t * 128 + h * 16 + d], a);
+        s[t] = a * 0.25f;
+        mx = fmaxf(mx, s[t]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < kTokens; ++t) {
+        s[t] = expf(s[t] - mx);
+        sum += s[t];
+    }
+    float const inv = 1.0f / sum;
+    float o[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int t = 0; t < kTokens; ++t) {
+        float const w = s[t] * inv;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o[d] = fmaf(w, vs[t * 128 + h * 16 + d], o[d]);
+    }
+    float4* o4 = reinterpret_cast<float4*>(out + ((size_t)p * kImgTokens + i) * 128 + h * 16);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o4[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// `res` and `out` may alias (in-place residual update), so neither is __restrict__.
+__global__ void __launch_bounds__(256) layernorm256_kernel(float const* x, float const* res, int64_t res_mod, int64_t rows,
+                                                           float const* __restrict__ gamma, float const* __restrict__ beta,
+                                                           float const* __restrict__ pos, int64_t pos_mod, float* out,
+                                                           float* out2) {
+    int64_t const row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int const lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float v[8];
+    {
+        float4 const a = reinterpret_cast<float4 const*>(x + row * kDim)[lane];
+        float4 const b = reinterpret_cast<float4 const*>(x + row * kDim)[32 + lane];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    if (res) {
+        float const* r = res + (row % res_mod) * kDim;
+        float4 const a = reinterpret_cast<float4 const*>(r)[lane];
+        float4 const b = reinterpret_cast<float4 const*>(r)[32 + lane];
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += v[i];
+    float const mean = warp_sum(sum) * (1.0f / kDim);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float const d = v[i] - mean;
+        var = fmaf(d, d, var);
+    }
+    float const rstd = rsqrtf(warp_sum(var) * (1.0f / kDim) + 1e-5f);
+    float y[8];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float4 const g = reinterpret_cast<float4 const*>(gamma)[half * 32 + lane];
+        float4 const bt = reinterpret_cast<float4 const*>(beta)[half * 32 + lane];
+        y[4 * half + 0] = (v[4 * half + 0] - mean) * rstd * g.x + bt.x;
+        y[4 * half + 1] = (v[4 * half + 1] - mean) * rstd * g.y + bt.y;
+        y[4 * half + 2] = (v[4 * half + 2] - mean) * rstd * g.z + bt.z;
+        y[4 * half + 3] = (v[4 * half + 3] - mean) * rstd * g.w + bt.w;
+        reinterpret_cast<float4*>(out + row * kDim)[half * 32 + lane] =
+            make_float4(y[4 * half], y[4 * half + 1], y[4 * half + 2], y[4 * half + 3]);
+    }
+    if (out2) {
+        float const* q = pos + (row % pos_mod) * kDim;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float4 const a = reinterpret_cast<float4 const*>(q)[half * 32 + lane];
+            reinterpret_cast<float4*>(out2 + row * kDim)[half * 32 + lane] =
+                make_float4(y[4 * half] + a.x, y[4 * half + 1] + a.y, y[4 * half + 2] + a.z, y[4 * half + 3] + a.w);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) layernorm64_gelu_kernel(float* __restrict__ x, int64_t rows,
+                                                               float const* __restrict__ gamma,
+                                                               float const* __restrict__ beta) {
+    int64_t const row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int const lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float2 v = reinterpret_cast<float2*>(x + row * 64)[lane];
+    float const mean = warp_sum(v.x + v.y) * (1.0f / 64.0f);
+    float const dx = v.x - mean, dy = v.y - mean;
+    float const rstd = rsqrtf(warp_sum(dx * dx + dy * dy) * (1.0f / 64.0f) + 1e-6f);
+    float2 const g = reinterpret_cast<float2 const*>(gamma)[lane];
+    float2 const b = reinterpret_cast<float2 const*>(beta)[lane];
+    v.x = gelu_erf(dx * rstd * g.x + b.x);
+    v.y = gelu_erf(dy * rstd * g.y + b.y);
+    reinterpret_cast<float2*>(x + row * 64)[lane] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_dot_kernel(float const* __restrict__ hyper, float const* __restrict__ up2,
+                                                       float* __restrict__ low) {
+    __shared__ float hs[4 * 32];
+    int const p = blockIdx.y;
+    if (threadIdx.x < 128) hs[threadIdx.x] = hyper[(size_t)p * 128 + threadIdx.x];
+    __syncthreads();
+    int const pix = blockIdx.x * blockDim.x + threadIdx.x;  // Y*256 + X
+    int const Y = pix >> 8, X = pix & 255;
+    int const y = Y >> 2, dy = (Y >> 1) & 1, ey = Y & 1;
+    int const x = X >> 2, dx = (X >> 1) & 1, ex = X & 1;
+    size_t const row = ((size_t)(y * 64 + x) * 4 + dy * 2 + dx);
+    float4 const* u4 = reinterpret_cast<float4 const*>(up2 + ((size_t)p * 16384 + row) * 128 + (ey * 2 + ex) * 32);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 const u = __ldg(u4 + c);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            float const* hm = hs + m * 32 + c * 4;
+            acc[m] = fmaf(u.x, hm[0], acc[m]);
+            acc[m] = fmaf(u.y, hm[1], acc[m]);
+            acc[m] = fmaf(u.z, hm[2], acc[m]);
+            acc[m] = fmaf(u.w, hm[3], acc[m]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) low[((size_t)p * 4 + m) * 65536 + pix] = acc[m];
+}
+
+__global__ void select_masks_kernel(float const* __restrict__ iou, int P, int multi, int* __restrict__ plane_index,
+                                    float* __restrict__ iou_out) {
+    int const p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float const* s = iou + p * 4;
+    if (multi) {
+        for (int i = 0; i < 3; ++i) {
+            plane_index[p * 3 + i] = p * 4 + 1 + i;
+            if (iou_out) iou_out[p * 3 + i] = s[1 + i];
+        }
+    } else {
+        // score = iou + (num_points - 2.5) * [1000, 0, 0, 0] with num_points == 2; first maximum wins
+        float best = s[0] + (2.0f - 2.5f) * 1000.0f;
+        int bi = 0;
+        for (int i = 1; i < 4; ++i) {
+            float const v = s[i] + (2.0f - 2.5f) * 0.0f;
+            if (v > best) { best = v; bi = i; }
+        }
+        plane_index[p] = p * 4 + bi;
+        if (iou_out) iou_out[p] = s[bi];
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+void prompt_tokens(cudaStream_t s, float const* coords, float const* labels, int P, PromptParams const& pp, float* tokens) {
+    prompt_tokens_kernel<<<P, 256, 0, s>>>(coords, labels, pp, tokens);
+    KERNEL_CHECK();
+}
+
+void dense_pe(cudaStream_t s, float const* gaussian, float* pos) {
+    dense_pe_kernel<<<kImgTokens, 256, 0, s>>>(gaussian, pos);
+    KERNEL_CHECK();
+}
+
+void embed_prepare(cudaStream_t s, float const* emb, float const* no_mask, float const* pos, int64_t rows, float* keys0,
+                   float* kpe0) {
+    int64_t const total4 = rows * (kDim / 4);
+    embed_prepare_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, s>>>(emb, no_mask, pos, total4, keys0, kpe0);
+    KERNEL_CHECK();
+}
+
+void linear_small(cudaStream_t s, float const* x, int64_t x_stride, float const* x2, int64_t x2_stride, int rows, int K,
+                  float const* W, float const* b, int N, bool relu, float* y, int64_t y_stride) {
+    DLIMG_ASSERT(K <= 2048);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinRows * 2048 * 4));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(rows, kLinRows), ceil_div(N, kLinColsPerBlock));
+    linear_small_kernel<<<grid, kLinWarps * 32, sizeof(float) * kLinRows * K, s>>>(x, x_stride, x2, x2_stride, rows, K, W, b,
+                                                                                  N, relu ? 1 : 0, y, y_stride);
+    KERNEL_CHECK();
+}
+
+void token_self_attention(cudaStream_t s, float const* q, float const* k, float const* v, int P, float* out) {
+    token_self_attention_kernel<<<P, 256, 0, s>>>(q, k, v, out);
+    KERNEL_CHECK();
+}
+
+void token_to_image_attention(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride, int P,
+                              float* out) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(t2i_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT2iSmem));
+        attr_set = true;
+    }
+    t2i_attention_kernel<<<P * kHeads, kT2iThreads, kT2iSmem, s>>>(q, K, V, kv_stride, out);
+    KERNEL_CHECK();
+}
+
+void image_to_token_attention(cudaStream_t s, float const* Q, int64_t q_stride, float const* kt, float const* vt, int P,
+                              float* out) {
+    dim3 grid(kImgTokens * kHeads / 256, P);
+    i2t_attention_kernel<<<grid, 256, 0, s>>>(Q, q_stride, kt, vt, out);
+    KERNEL_CHECK();
+}
+
+void layernorm256(cudaStream_t s, float const* x, float const* res, int64_t res_mod, int64_t rows, float const* gamma,
+                  float const* beta, float const* pos, int64_t pos_mod, float* out, float* out2) {
+    if (res_mod <= 0) res_mod = rows;
+    if (pos_mod <= 0) pos_mod = rows;
+    layernorm256_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, s>>>(x, res, res_mod, rows, gamma, beta, pos, pos_mod, out,
+                                                                     out2);
+    KERNEL_CHECK();
+}
+
+void layernorm64_gelu(cudaStream_t s, float* x, int64_t rows, float const* gamma, float const* beta) {
+    layernorm64_gelu_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, s>>>(x, rows, gamma, beta);
+    KERNEL_CHECK();
+}
+
+void mask_dot(cudaStream_t s, float const* hyper, float const* up2, int P, float* low) {
+    dim3 grid(65536 / 256, P);
+    mask_dot_kernel<<<grid, 256, 0, s>>>(hyper, up2, low);
+    KERNEL_CHECK();
+}
+
+void select_masks(cudaStream_t s, float const* iou, int P, int multi, int* plane_index, float* iou_out) {
+    select_masks_kernel<<<ceil_div(P, 128), 128, 0, s>>>(iou, P, multi, plane_index, iou_out);
+    KERNEL_CHECK();
+}
+
+}  // namespace dec
+}  // namespace dlimg

@@ -1,0 +1,384 @@
+// encoder_kernels.cu -- see encoder_kernels.cuh.
+#include "encoder_kernels.cuh"
+
+namespace dlimg {
+namespace enc {
+
+namespace {
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ void unpack8(uint4 const& v, float (&f)[8]) {
+    __nv_bfloat162 const* h = reinterpret_cast<__nv_bfloat162 const*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(float const (&f)[8]) {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Conv1Params {
+    int w, h, bpp;
+    int c0, c1, c2;  // byte offsets of R, G, B in a pixel
+};
+
+constexpr int kC1Tile = 16;
+constexpr int kC1In = 2 * kC1Tile + 1;  // 33
+
+__global__ void __launch_bounds__(256) conv1_preprocess_kernel(ImageDesc const* __restrict__ imgs, Conv1Params p,
+                                                               float const* __restrict__ weight,
+                                                               float const* __restrict__ bias, bf16* __restrict__ out) {
+    __shared__ float tile[kC1In * kC1In * 3];
+    __shared__ __align__(16) float wsm[27 * 32];
+    __shared__ float bsm[32];
+    int const tid = threadIdx.y * kC1Tile + threadIdx.x;
+    int const b = blockIdx.z;
+    ImageDesc const img = imgs[b];
+    int const oy0 = blockIdx.y * kC1Tile, ox0 = blockIdx.x * kC1Tile;
+    int const iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
+    for (int i = tid; i < 27 * 32; i += 256) wsm[i] = weight[i];
+    if (tid < 32) bsm[tid] = bias[tid];
+    // mean / std of the encoder graph's preamble
+    float const mean[3] = {123.675f, 116.28f, 103.53f};
+    float const sd[3] = {58.395f, 57.12f, 57.375f};
+    int const coff[3] = {p.c0, p.c1, p.c2};
+    for (int i = tid; i < kC1In * kC1In; i += 256) {
+        int const r = i / kC1In, c = i % kC1In;
+        int const iy = iy0 + r, ix = ix0 + c;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+            uint8_t const* px = img.pixels + (size_t)iy * img.stride + (size_t)ix * p.bpp;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) v[ch] = __fdiv_rn((float)px[coff[ch]] - mean[ch], sd[ch]);
+        }
+        tile[i * 3 + 0] = v[0];
+        tile[i * 3 + 1] = v[1];
+        tile[i * 3 + 2] = v[2];
+    }
+    __syncthreads();
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = bsm[i];
+    int const ty = threadIdx.y, tx = threadIdx.x;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            float const* src = tile + ((2 * ty + ky) * kC1In + 2 * tx + kx) * 3;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                float const v = src[ci];
+                float4 const* w4 = reinterpret_cast<float4 const*>(wsm + ((ky * 3 + kx) * 3 + ci) * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 const w = w4[q];
+                    acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+                }
+            }
+        }
+    }
+    int const oy = oy0 + ty, ox = ox0 + tx;
+    uint4* o = reinterpret_cast<uint4*>(out + (((size_t)b * 512 + oy) * 512 + ox) * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = gelu_erf(acc[8 * q + i]);
+        o[q] = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col3x3_kernel(bf16 const* __restrict__ in, int H, int W, int C8, int stride, int Ho, int Wo,
+                                 int64_t total, bf16* __restrict__ out) {
+    int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int const c8 = (int)(t % C8);
+    int64_t r = t / C8;
+    int const tap = (int)(r % 9);
+    r /= 9;  // output pixel index (b, oy, ox)
+    int const ox = (int)(r % Wo);
+    int64_t r2 = r / Wo;
+    int const oy = (int)(r2 % Ho);
+    int const b = (int)(r2 / Ho);
+    int const iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v = reinterpret_cast<uint4 const*>(in)[(((int64_t)b * H + iy) * W + ix) * C8 + c8];
+    reinterpret_cast<uint4*>(out)[t] = v;  // t == (r*9 + tap)*C8 + c8
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void dwconv3x3_kernel(bf16 const* __restrict__ in, int H, int W, int C8, int stride, int Ho, int Wo,
+                                 int64_t total, float const* __restrict__ weight, float const* __restrict__ bias,
+                                 int gelu, bf16* __restrict__ out) {
+    int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int const c8 = (int)(t % C8);
+    int64_t r = t / C8;
+    int const ox = (int)(r % Wo);
+    int64_t r2 = r / Wo;
+    int const oy = (int)(r2 % Ho);
+    int const b = (int)(r2 / Ho);
+    int const C = C8 * 8;
+    float acc[8];
+    {
+        float4 const* b4 = reinterpret_cast<float4 const*>(bias + c8 * 8);
+        float4 const b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+        acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        int const iy = oy * stride + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            int const ix = ox * stride + kx - 1;
+            if (ix < 0 || ix >= W) continue;
+            uint4 const v = __ldg(reinterpret_cast<uint4 const*>(in) + (((int64_t)b * H + iy) * W + ix) * C8 + c8);
+            float f[8];
+            unpack8(v, f);
+            float4 const* w4 = reinterpret_cast<float4 const*>(weight + (ky * 3 + kx) * C + c8 * 8);
+            float4 const w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+            acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+            acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+            acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+            acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+        }
+    }
+    if (gelu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = gelu_erf(acc[i]);
+    }
+    reinterpret_cast<uint4*>(out)[t] = pack8(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnMaxPairs = 5;  // C <= 320
+
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(bf16 const* __restrict__ in, int rows, int C,
+                                                             int const* __restrict__ src_row,
+                                                             float const* __restrict__ gamma,
+                                                             float const* __restrict__ beta, float eps,
+                                                             void* __restrict__ out, int out_f32) {
+    int const row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    int const lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    int const pairs = C >> 1;
+    int64_t src = row;
+    if (src_row) src = src_row[row];
+    float2 x[kLnMaxPairs];
+    float sum = 0.f;
+    if (src >= 0) {
+        __nv_bfloat162 const* p = reinterpret_cast<__nv_bfloat162 const*>(in + src * C);
+#pragma unroll
+        for (int i = 0; i < kLnMaxPairs; ++i) {
+            int const idx = lane + 32 * i;
+            x[i] = idx < pairs ? __bfloat1622float2(p[idx]) : make_float2(0.f, 0.f);
+            sum += x[i].x + x[i].y;
+        }
+    }
+    float rstd = 0.f, mean = 0.f;
+    if (src >= 0) {  // warp-uniform
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mean = sum / (float)C;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < kLnMaxPairs; ++i) {
+            int const idx = lane + 32 * i;
+            if (idx < pairs) {
+                float const a = x[i].x - mean, b = x[i].y - mean;
+                var += a * a + b * b;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        rstd = rsqrtf(var / (float)C + eps);
+    }
+#pragma unroll
+    for (int i = 0; i < kLnMaxPairs; ++i) {
+        int const idx = lane + 32 * i;
+        if (idx >= pairs) continue;
+        float2 const g = reinterpret_cast<float2 const*>(gamma)[idx];
+        float2 const bt = reinterpret_cast<float2 const*>(beta)[idx];
+        float2 y;
+        if (src >= 0) {
+            y.x = (x[i].x - mean) * rstd * g.x + bt.x;
+            y.y = (x[i].y - mean) * rstd * g.y + bt.y;
+        } else {
+            y = bt;  // LayerNorm of an all-zero padding token
+        }
+        if (out_f32) reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + (int64_t)row * C)[idx] = y;
+        else reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(out) + (int64_t)row * C)[idx] = __floats2bfloat162_rn(y.x, y.y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kAttnWarps = 8;
+constexpr int kAttnMaxJ = 7;  // n <= 224 keys
+
+__global__ void __launch_bounds__(kAttnWarps * 32) window_attention_kernel(bf16 const* __restrict__ qkv, int n, int heads,
+                                                                           float const* __restrict__ bias,
+                                                                           bf16* __restrict__ out) {
+    extern __shared__ float sm[];
+    float* Ks = sm;                       // [n][33]
+    float* Vs = Ks + n * 33;              // [n][32]
+    float* Qs = Vs + n * 32;              // [warps][32]
+    float* Ps = Qs + kAttnWarps * 32;     // [warps][n]
+    int const win = blockIdx.x / heads, h = blockIdx.x % heads;
+    int const ld = heads * 96, C = heads * 32;
+    int64_t const row0 = (int64_t)win * n;
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < n * 32; i += blockDim.x) {
+        int const j = i >> 5, d = i & 31;
+        bf16 const* base = qkv + (row0 + j) * ld + h * 96;
+        Ks[j * 33 + d] = __bfloat162float(base[32 + d]);
+        Vs[j * 32 + d] = __bfloat162float(base[64 + d]);
+    }
+    __syncthreads();
+    float const scale = 0.17677669529663687f;  // 32^-0.5
+    float const* bias_h = bias + (int64_t)h * n * n;
+    for (int i = warp; i < n; i += kAttnWarps) {
+        Qs[warp * 32 + lane] = __bfloat162float(qkv[(row0 + i) * ld + h * 96 + lane]);
+        __syncwarp();
+        float s[kAttnMaxJ];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < kAttnMaxJ; ++jj) {
+            int const j = jj * 32 + lane;
+            s[jj] = -INFINITY;
+            if (j < n) {
+                float a = 0.f;
+#pragma unroll
+                for (int d = 0; d < 32; ++d) a = fmaf(Qs[warp * 32 + d], Ks[j * 33 + d], a);
+                s[jj] = a * scale + __ldg(bias_h + (int64_t)i * n + j);
+            }
+            mx = fmaxf(mx, s[jj]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < kAttnMaxJ; ++jj) {
+            int const j = jj * 32 + lane;
+            float const e = j < n ? __expf(s[jj] - mx) : 0.f;
+            s[jj] = e;
+            sum += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        float const inv = 1.0f / sum;
+#pragma unroll
+        for (int jj = 0; jj < kAttnMaxJ; ++jj) {
+            int const j = jj * 32 + lane;
+            if (j < n) Ps[warp * n + j] = s[jj] * inv;
+        }
+        __syncwarp();
+        float o = 0.f;
+        for (int j = 0; j < n; ++j) o = fmaf(Ps[warp * n + j], Vs[j * 32 + lane], o);
+        out[(row0 + i) * C + h * 32 + lane] = __float2bfloat16_rn(o);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void tokens_to_nchw_kernel(float const* __restrict__ in, int tokens, int C, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    int const b = blockIdx.z;
+    int const t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    float const* src = in + (int64_t)b * tokens * C;
+    float* dst = out + (int64_t)b * tokens * C;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int const t = t0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (t < tokens && c < C) ? src[(int64_t)t * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int const c = c0 + i, t = t0 + threadIdx.x;
+        if (t < tokens && c < C) dst[(int64_t)c * tokens + t] = tile[threadIdx.x][i];
+    }
+}
+
+__global__ void bf16_to_f32_kernel(bf16 const* __restrict__ in, int64_t n, float* __restrict__ out) {
+    int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+void conv1_preprocess(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h, int channels,
+                      float const* weight, float const* bias, bf16* out) {
+    DLIMG_ASSERT(w >= 1 && h >= 1 && w <= kImageSize && h <= kImageSize);
+    int cmap[3];
+    channel_map(channels, cmap);
+    Conv1Params p{w, h, bytes_per_pixel(channels), cmap[0], cmap[1], cmap[2]};
+    dim3 grid(512 / kC1Tile, 512 / kC1Tile, batch), block(kC1Tile, kC1Tile);
+    conv1_preprocess_kernel<<<grid, block, 0, s>>>(imgs, p, weight, bias, out);
+    KERNEL_CHECK();
+}
+
+void im2col3x3(cudaStream_t s, bf16 const* in, int batch, int H, int W, int C, int stride, bf16* out) {
+    DLIMG_ASSERT(C % 8 == 0);
+    int const Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    int64_t const total = (int64_t)batch * Ho * Wo * 9 * (C / 8);
+    im2col3x3_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(in, H, W, C / 8, stride, Ho, Wo, total, out);
+    KERNEL_CHECK();
+}
+
+void dwconv3x3(cudaStream_t s, bf16 const* in, int batch, int H, int W, int C, int stride, float const* weight,
+               float const* bias, bool gelu, bf16* out) {
+    DLIMG_ASSERT(C % 8 == 0);
+    int const Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    int64_t const total = (int64_t)batch * Ho * Wo * (C / 8);
+    dwconv3x3_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(in, H, W, C / 8, stride, Ho, Wo, total, weight,
+                                                                      bias, gelu ? 1 : 0, out);
+    KERNEL_CHECK();
+}
+
+void layernorm_rows(cudaStream_t s, bf16 const* in, int rows, int C, int const* src_row, float const* gamma,
+                    float const* beta, float eps, void* out, bool out_f32) {
+    DLIMG_ASSERT(C % 2 == 0 && C <= kLnMaxPairs * 64);
+    layernorm_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(in, rows, C, src_row, gamma, beta, eps, out, out_f32 ? 1 : 0);
+    KERNEL_CHECK();
+}
+
+void window_attention(cudaStream_t s, bf16 const* qkv, int windows, int n, int heads, float const* bias, bf16* out) {
+    DLIMG_ASSERT(n <= kAttnMaxJ * 32);
+    size_t const smem = sizeof(float) * ((size_t)n * 33 + (size_t)n * 32 + kAttnWarps * 32 + (size_t)kAttnWarps * n);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    window_attention_kernel<<<windows * heads, kAttnWarps * 32, smem, s>>>(qkv, n, heads, bias, out);
+    KERNEL_CHECK();
+}
+
+void tokens_to_nchw(cudaStream_t s, float const* in, int batch, int tokens, int C, float* out) {
+    dim3 grid(ceil_div(tokens, 32), ceil_div(C, 32), batch), block(32, 8);
+    tokens_to_nchw_kernel<<<grid, block, 0, s>>>(in, tokens, C, out);
+    KERNEL_CHECK();
+}
+
+void bf16_to_f32(cudaStream_t s, bf16 const* in, int64_t n, float* out) {
+    bf16_to_f32_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(in, n, out);
+    KERNEL_CHECK();
+}
+
+}  // namespace enc
+}  // namespace dlimg

@@ -1,0 +1,51 @@
+// encoder_kernels.cuh -- non-GEMM kernels of the TinyViT encoder.  Activations are bf16, NHWC
+// ("token-major": row = pixel, contiguous channels), so every 1x1 conv / Linear is a plain K-major GEMM.
+#pragma once
+
+#include "../common.hpp"
+
+#include <cuda_bf16.h>
+
+namespace dlimg {
+namespace enc {
+
+using bf16 = __nv_bfloat16;
+
+// One input image as the preprocessing kernels see it (device memory).
+struct ImageDesc {
+    uint8_t const* pixels;  // device pointer, row-major u8
+    int stride;             // bytes per row
+    int _pad;
+};
+
+// Fused: channel-map + (x-mean)/std + zero-pad to 1024^2 (encoder graph preamble) +
+// PatchEmbed conv 3x3 s2 p1 (3->32, BN folded) + GELU.  Reads the u8 image once, writes bf16
+// (B, 512, 512, 32).  `w`,`h` is the valid (already <= 1024) extent; weight layout [27][32] (tap-major,
+// tap = (ky*3+kx)*3+ci), bias [32].
+void conv1_preprocess(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h, int channels,
+                      float const* weight, float const* bias, bf16* out);
+
+// im2col for 3x3 / pad 1 convolutions on NHWC bf16: out[(b,oy,ox)][(ky,kx,c)] (K = 9*C).
+void im2col3x3(cudaStream_t s, bf16 const* in, int batch, int H, int W, int C, int stride, bf16* out);
+
+// Depthwise 3x3 / pad 1, NHWC bf16, fp32 weights [9][C] + bias [C] (BN folded), optional GELU.
+void dwconv3x3(cudaStream_t s, bf16 const* in, int batch, int H, int W, int C, int stride, float const* weight,
+               float const* bias, bool gelu, bf16* out);
+
+// Row LayerNorm over C channels.  src_row (optional, length `rows`): gather index into `in`, -1 = the row
+// is window padding and the output is LN(0) = beta.  Output bf16 or fp32.
+void layernorm_rows(cudaStream_t s, bf16 const* in, int rows, int C, int const* src_row, float const* gamma,
+                    float const* beta, float eps, void* out, bool out_f32);
+
+// Windowed multi-head attention, head_dim 32.  qkv: (windows*n, heads*96) with per-head [q|k|v];
+// bias: (heads, n, n) fp32 (already gathered from attention_biases); out: (windows*n, heads*32).
+void window_attention(cudaStream_t s, bf16 const* qkv, int windows, int n, int heads, float const* bias, bf16* out);
+
+// (tokens, C) fp32 -> (C, tokens) fp32 per image: the reference's NCHW `image_embeddings` layout.
+void tokens_to_nchw(cudaStream_t s, float const* in, int batch, int tokens, int C, float* out);
+
+// bf16 -> fp32 copy (debug taps).
+void bf16_to_f32(cudaStream_t s, bf16 const* in, int64_t n, float* out);
+
+}  // namespace enc
+}  // namespace dlimg

@@ -1,0 +1,455 @@
+// gemm.cu -- tcgen05 / TMEM / TMA GEMM for sm_100a (see gemm.cuh for the contract).
+#include "gemm.cuh"
+
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+namespace dlimg {
+namespace gemm {
+
+namespace {
+
+constexpr int kAStageBytes = kBlockM * kKBytes;     // 16 KiB
+constexpr int kBStageBytes = kMaxBlockN * kKBytes;  // 32 KiB
+constexpr int kNumThreads = 192;
+constexpr int kTmemCols = 512;                      // two accumulator stages of up to 256 fp32 columns
+constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(void const* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, CUtensorMap const* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int kTF32>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if (kTF32) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows are 128 B apart, groups of 8 rows 1024 B
+// apart (SBO).  LBO is unused for swizzled K-major layouts (encoded as 1), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                   // leading byte offset (ignored)
+    d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset
+    d |= (uint64_t)1 << 46;                   // descriptor version
+    d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+struct EpiParams {
+    float const* bias;
+    void const* residual;
+    int const* row_map;
+    int act;
+    int out_f32;
+    int ldc;
+};
+
+// One 16-column slab of one accumulator row: bias -> residual -> activation -> store.
+__device__ __forceinline__ void epilogue_store16(uint32_t const (&r)[16], EpiParams const& ep, void* out, int64_t orow,
+                                                 int col) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    if (ep.bias) {
+        float4 const* b4 = reinterpret_cast<float4 const*>(ep.bias + col);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 b = __ldg(b4 + i);
+            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+    }
+    if (ep.out_f32) {
+        float* o = reinterpret_cast<float*>(out) + orow * ep.ldc + col;
+        if (ep.residual) {
+            float4 const* r4 = reinterpret_cast<float4 const*>(reinterpret_cast<float const*>(ep.residual) + orow * ep.ldc + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 x = r4[i];
+                v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+            }
+        }
+        if (ep.act == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+        } else if (ep.act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + orow * ep.ldc + col;
+        if (ep.residual) {
+            uint4 const* r4 = reinterpret_cast<uint4 const*>(reinterpret_cast<__nv_bfloat16 const*>(ep.residual) + orow * ep.ldc + col);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                uint4 x = r4[i];
+                __nv_bfloat162 const* h = reinterpret_cast<__nv_bfloat162 const*>(&x);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 f = __bfloat1622float2(h[j]);
+                    v[8 * i + 2 * j] += f.x;
+                    v[8 * i + 2 * j + 1] += f.y;
+                }
+            }
+        }
+        if (ep.act == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+        } else if (ep.act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            uint4 x;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+            o4[i] = x;
+        }
+    }
+}
+
+template <int kTF32>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
+               int K, int block_n, void* out, EpiParams ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint32_t const smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint32_t const a_base = smem_base;
+    uint32_t const b_base = smem_base + kStages * kAStageBytes;
+    uint32_t const bar_base = b_base + kStages * kBStageBytes;
+    // barrier slots (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+    uint32_t const tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    int const warp = threadIdx.x >> 5;
+    int const lane = threadIdx.x & 31;
+
+    int const elems_per_kb = kTF32 ? 32 : 64;
+    int const elem_bytes = kTF32 ? 4 : 2;
+    int const num_kb = (K + elems_per_kb - 1) / elems_per_kb;
+    int const n_tiles = N / block_n;
+    int const m_tiles = (M + kBlockM - 1) / kBlockM;
+    int const total_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t const tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t const tx_bytes = (uint32_t)(kAStageBytes + block_n * kKBytes);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int const m0 = (tile / n_tiles) * kBlockM;
+                int const n0 = (tile % n_tiles) * block_n;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), tx_bytes);
+                    tma_load_2d(a_base + stage * kAStageBytes, &tma_a, full_bar(stage), kb * elems_per_kb, m0);
+                    tma_load_2d(b_base + stage * kBStageBytes, &tma_b, full_bar(stage), kb * elems_per_kb, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B bf16 or tf32, both K-major, N = block_n, M = 128
+            uint32_t const fmt = kTF32 ? 2u : 1u;
+            uint32_t const idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) |
+                                   ((uint32_t)(kBlockM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+                int const acc = local & 1;
+                uint32_t const acc_phase = (uint32_t)(local >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                uint32_t const d_tmem = tmem_base + (uint32_t)(acc * kMaxBlockN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    int const valid_bytes = min(kKBytes, (K - kb * elems_per_kb) * elem_bytes);
+                    int const n_instr = (valid_bytes + 31) >> 5;
+                    uint64_t const adesc = make_smem_desc(a_base + stage * kAStageBytes);
+                    uint64_t const bdesc = make_smem_desc(b_base + stage * kBStageBytes);
+                    for (int k = 0; k < n_instr; ++k) {
+                        // advance 32 bytes of K inside the swizzle atom: +2 in the 16-byte address field
+                        tc_mma<kTF32>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                      (uint32_t)((kb | k) != 0));
+                    }
+                    tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ---------------- epilogue (4 warps; TMEM lane quarter = warp index mod 4) ----------------
+        int const quarter = warp & 3;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            int const acc = local & 1;
+            uint32_t const acc_phase = (uint32_t)(local >> 1) & 1u;
+            int const m0 = (tile / n_tiles) * kBlockM;
+            int const n0 = (tile % n_tiles) * block_n;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            int const row = m0 + quarter * 32 + lane;
+            int64_t orow = -1;
+            if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
+            uint32_t const taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN);
+            for (int c = 0; c < block_n; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + (uint32_t)c, r);
+                tmem_ld_wait();
+                if (orow >= 0) epilogue_store16(r, ep, out, orow, n0 + c);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+// ---- CUDA-core cross-check / small-M kernel -------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void gemm_simt_kernel(T const* __restrict__ A, int64_t lda, T const* __restrict__ B, int64_t ldb, int M, int N,
+                                 int K, void* out, EpiParams ep) {
+    // 32x32 output tile per block, 32x8 threads, each thread 4 rows; K tiled by 32 through shared memory
+    __shared__ float As[32][33];
+    __shared__ float Bs[32][33];
+    int const tx = threadIdx.x, ty = threadIdx.y;
+    int const m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int i = ty; i < 32; i += 8) {
+            int const m = m0 + i, n = n0 + i, k = k0 + tx;
+            As[i][tx] = (m < M && k < K) ? to_f32<T>(A[(int64_t)m * lda + k]) : 0.f;
+            Bs[i][tx] = (n < N && k < K) ? to_f32<T>(B[(int64_t)n * ldb + k]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            float const b = Bs[tx][k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += As[ty + 8 * i][k] * b;
+        }
+        __syncthreads();
+    }
+    int const n = n0 + tx;
+    if (n >= N) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int const m = m0 + ty + 8 * i;
+        if (m >= M) continue;
+        int64_t const orow = ep.row_map ? (int64_t)ep.row_map[m] : (int64_t)m;
+        if (orow < 0) continue;
+        float v = acc[i];
+        if (ep.bias) v += ep.bias[n];
+        int64_t const o = orow * ep.ldc + n;
+        if (ep.residual)
+            v += ep.out_f32 ? reinterpret_cast<float const*>(ep.residual)[o]
+                            : __bfloat162float(reinterpret_cast<__nv_bfloat16 const*>(ep.residual)[o]);
+        if (ep.act == ACT_GELU) v = gelu_erf(v);
+        else if (ep.act == ACT_RELU) v = fmaxf(v, 0.f);
+        if (ep.out_f32) reinterpret_cast<float*>(out)[o] = v;
+        else reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(v);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, cuuint64_t const*,
+                                   cuuint64_t const*, cuuint32_t const*, cuuint32_t const*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess) fail("cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+CUtensorMap make_map(Operand const& op, bool tf32, int box_rows) {
+    CUtensorMap map;
+    int const esz = tf32 ? 4 : 2;
+    int64_t const pitch = op.pitch ? op.pitch : op.cols;
+    DLIMG_ASSERT((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0);
+    DLIMG_ASSERT((pitch * esz) % 16 == 0);
+    cuuint64_t dims[2] = {(cuuint64_t)op.cols, (cuuint64_t)op.rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(pitch * esz)};
+    cuuint32_t box[2] = {(cuuint32_t)(kKBytes / esz), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_fn()(&map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                             const_cast<void*>(op.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return map;
+}
+
+EpiParams to_params(Epilogue const& e, int N) {
+    EpiParams p;
+    p.bias = e.bias;
+    p.residual = e.residual;
+    p.row_map = e.row_map;
+    p.act = e.act;
+    p.out_f32 = e.out_f32;
+    p.ldc = e.ldc ? e.ldc : N;
+    return p;
+}
+
+}  // namespace
+
+int pick_block_n(int N) {
+    for (int bn = kMaxBlockN; bn >= 16; bn -= 16)
+        if (N % bn == 0) return bn;
+    return 0;
+}
+
+void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, void* out, Epilogue const& epi,
+            int num_sms) {
+    int const M = (int)a.rows, N = (int)b.rows, K = (int)a.cols;
+    DLIMG_ASSERT(a.cols == b.cols);
+    DLIMG_ASSERT(M > 0 && N > 0 && K > 0);
+    int const block_n = pick_block_n(N);
+    if (block_n == 0) fail("GEMM: N must be a multiple of 16, got " + std::to_string(N));
+    EpiParams ep = to_params(epi, N);
+    DLIMG_ASSERT(ep.ldc % (ep.out_f32 ? 4 : 8) == 0);
+    CUtensorMap ma = make_map(a, tf32, kBlockM);
+    CUtensorMap mb = make_map(b, tf32, block_n);
+    int const tiles = ceil_div(M, kBlockM) * (N / block_n);
+    int const grid = tiles < num_sms ? tiles : num_sms;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    });
+    if (tf32) gemm_tc_kernel<1><<<grid, kNumThreads, kSmemBytes, stream>>>(ma, mb, M, N, K, block_n, out, ep);
+    else gemm_tc_kernel<0><<<grid, kNumThreads, kSmemBytes, stream>>>(ma, mb, M, N, K, block_n, out, ep);
+    KERNEL_CHECK();
+}
+
+void launch_simt(cudaStream_t stream, bool f32_operands, Operand const& a, Operand const& b, void* out,
+                 Epilogue const& epi) {
+    int const M = (int)a.rows, N = (int)b.rows, K = (int)a.cols;
+    DLIMG_ASSERT(a.cols == b.cols);
+    EpiParams ep = to_params(epi, N);
+    dim3 grid(ceil_div(N, 32), ceil_div(M, 32)), block(32, 8);
+    int64_t const lda = a.pitch ? a.pitch : a.cols, ldb = b.pitch ? b.pitch : b.cols;
+    if (f32_operands)
+        gemm_simt_kernel<float><<<grid, block, 0, stream>>>((float const*)a.ptr, lda, (float const*)b.ptr, ldb, M, N, K, out, ep);
+    else
+        gemm_simt_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((__nv_bfloat16 const*)a.ptr, lda,
+                                                                     (__nv_bfloat16 const*)b.ptr, ldb, M, N, K, out, ep);
+    KERNEL_CHECK();
+}
+
+}  // namespace gemm
+}  // namespace dlimg

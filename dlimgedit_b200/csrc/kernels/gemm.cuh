@@ -1,0 +1,58 @@
+// gemm.cuh -- the tensor-core workhorse: C[M,N] = epilogue(A[M,K] * B[N,K]^T).
+//
+// Both operands are K-major (activations: rows = tokens; weights: rows = output features, exactly the
+// nn.Linear / 1x1-conv layout).  The kernel is a persistent, warp-specialised sm_100a pipeline:
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128-byte swizzle, 4-stage mbarrier ring)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128, N=block_n, fp32 accumulators in TMEM,
+//                               two accumulator stages so the epilogue of tile i overlaps tile i+1)
+//   warps 2..5  epilogue       (tcgen05.ld -> bias / residual / activation -> bf16|fp32 global stores,
+//                               optional row scatter used for window un-partition)
+// Operand element type is bf16 (kind::f16) for the encoder or fp32-as-tf32 (kind::tf32) for the decoder;
+// the shared-memory geometry is identical in bytes (128 B of K per row per stage).
+#pragma once
+
+#include "../common.hpp"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace dlimg {
+namespace gemm {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+struct Epilogue {
+    float const* bias = nullptr;     // [N] fp32, or null
+    void const* residual = nullptr;  // same element type / pitch as the output, indexed by OUTPUT row
+    int const* row_map = nullptr;    // [M] -> output row (-1 = drop the row), or null for identity
+    int act = ACT_NONE;              // applied after bias and residual
+    int out_f32 = 0;                 // 0: bf16 output, 1: fp32 output
+    int ldc = 0;                     // output row pitch in elements (0 = N)
+};
+
+struct Operand {
+    void const* ptr = nullptr;
+    int64_t rows = 0;   // M for A, N for B
+    int64_t cols = 0;   // K
+    int64_t pitch = 0;  // row pitch in elements (0 = cols)
+};
+
+constexpr int kBlockM = 128;
+constexpr int kStages = 4;
+constexpr int kMaxBlockN = 256;
+constexpr int kKBytes = 128;  // bytes of K per row per stage == swizzle span
+
+// Picks the widest legal tile width (multiple of 16, <= 256) that divides N.
+int pick_block_n(int N);
+
+// Encodes the two tensor maps and launches.  tf32 != 0 selects fp32 operands with kind::tf32.
+void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, void* out, Epilogue const& epi,
+            int num_sms);
+
+// Plain CUDA-core GEMM with the same contract; used by tests to cross-check the tensor-core kernel and
+// for tiny problems (M < 64) where a 128-row tile would be mostly padding.
+void launch_simt(cudaStream_t stream, bool f32_operands, Operand const& a, Operand const& b, void* out,
+                 Epilogue const& epi);
+
+}  // namespace gemm
+}  // namespace dlimg

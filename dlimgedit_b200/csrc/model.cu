@@ -1,0 +1,557 @@
+// model.cu -- see model.hpp.
+#include "model.hpp"
+
+#include "kernels/gemm.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+
+namespace dlimg {
+
+// ---------------------------------------------------------------------------------------------
+// TinyViT-5M as configured for MobileSAM
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kDims[4] = {64, 128, 160, 320};
+constexpr int kDepths[4] = {2, 2, 6, 2};
+constexpr int kHeadsCfg[4] = {2, 4, 5, 10};
+constexpr int kWindows[4] = {7, 7, 14, 7};
+constexpr int kRes[4] = {256, 128, 64, 64};
+constexpr float kBnEps = 1e-5f;
+
+std::vector<bf16> to_bf16(std::vector<float> const& v) {
+    std::vector<bf16> o(v.size());
+    for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+    return o;
+}
+
+// Conv2d_BN folding: y = conv(x) * scale + shift, scale = gamma / sqrt(var + eps), shift = beta - mean * scale
+void bn_fold(WeightFile const& wf, std::string const& p, int c, std::vector<float>& scale, std::vector<float>& shift) {
+    auto const& g = wf.get(p + ".bn.weight", {c});
+    auto const& b = wf.get(p + ".bn.bias", {c});
+    auto const& m = wf.get(p + ".bn.running_mean", {c});
+    auto const& v = wf.get(p + ".bn.running_var", {c});
+    scale.resize((size_t)c);
+    shift.resize((size_t)c);
+    for (int i = 0; i < c; ++i) {
+        scale[(size_t)i] = g.data[(size_t)i] / std::sqrt(v.data[(size_t)i] + kBnEps);
+        shift[(size_t)i] = b.data[(size_t)i] - m.data[(size_t)i] * scale[(size_t)i];
+    }
+}
+
+// k x k Conv2d_BN (cout, cin, k, k) -> GEMM operand (cout, k*k*cin), K ordered (ky, kx, ci)
+Linear16 load_conv_bn(WeightFile const& wf, std::string const& p, int cout, int cin, int ks) {
+    auto const& w = wf.get(p + ".c.weight", {cout, cin, ks, ks});
+    std::vector<float> scale, shift;
+    bn_fold(wf, p, cout, scale, shift);
+    int const K = ks * ks * cin;
+    std::vector<float> o((size_t)cout * K);
+    for (int oc = 0; oc < cout; ++oc)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int t = 0; t < ks * ks; ++t)
+                o[(size_t)oc * K + (size_t)t * cin + ci] = w.data[((size_t)oc * cin + ci) * ks * ks + t] * scale[(size_t)oc];
+    Linear16 l;
+    l.n = cout;
+    l.k = K;
+    l.w.upload(to_bf16(o));
+    l.b.upload(shift);
+    return l;
+}
+
+DwConv load_dw_bn(WeightFile const& wf, std::string const& p, int c) {
+    auto const& w = wf.get(p + ".c.weight", {c, 1, 3, 3});
+    std::vector<float> scale, shift;
+    bn_fold(wf, p, c, scale, shift);
+    std::vector<float> o((size_t)9 * c);
+    for (int ch = 0; ch < c; ++ch)
+        for (int t = 0; t < 9; ++t) o[(size_t)t * c + ch] = w.data[(size_t)ch * 9 + t] * scale[(size_t)ch];
+    DwConv d;
+    d.c = c;
+    d.w.upload(o);
+    d.b.upload(shift);
+    return d;
+}
+
+Linear16 load_linear16(WeightFile const& wf, std::string const& p, int n, int k, bool bias = true) {
+    Linear16 l;
+    l.n = n;
+    l.k = k;
+    l.w.upload(to_bf16(wf.get(p + ".weight", {n, k}).data));
+    if (bias) l.b.upload(wf.get(p + ".bias", {n}).data);
+    return l;
+}
+
+Linear32 load_linear32(WeightFile const& wf, std::string const& p, int n, int k) {
+    Linear32 l;
+    l.n = n;
+    l.k = k;
+    l.w.upload(wf.get(p + ".weight", {n, k}).data);
+    l.b.upload(wf.get(p + ".bias", {n}).data);
+    return l;
+}
+
+Norm load_norm(WeightFile const& wf, std::string const& p, int c) {
+    Norm n;
+    n.g.upload(wf.get(p + ".weight", {c}).data);
+    n.b.upload(wf.get(p + ".bias", {c}).data);
+    return n;
+}
+
+AttnW load_attn(WeightFile const& wf, std::string const& p, int dim, int internal) {
+    AttnW a;
+    a.q = load_linear32(wf, p + ".q_proj", internal, dim);
+    a.k = load_linear32(wf, p + ".k_proj", internal, dim);
+    a.v = load_linear32(wf, p + ".v_proj", internal, dim);
+    a.o = load_linear32(wf, p + ".out_proj", dim, internal);
+    return a;
+}
+
+// attention_bias_idxs (a non-persistent buffer upstream): first-seen order of (|dy|, |dx|) offsets over
+// all ordered pairs of window positions -> dense (heads, n, n) bias table.
+std::vector<float> dense_attention_bias(HostTensor const& biases, int heads, int ws) {
+    int const n = ws * ws;
+    std::map<std::pair<int, int>, int> offsets;
+    std::vector<int> idx((size_t)n * n);
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            std::pair<int, int> const o{std::abs(a / ws - b / ws), std::abs(a % ws - b % ws)};
+            auto it = offsets.find(o);
+            if (it == offsets.end()) it = offsets.emplace(o, (int)offsets.size()).first;
+            idx[(size_t)a * n + b] = it->second;
+        }
+    int const n_off = (int)offsets.size();
+    DLIMG_ASSERT(biases.shape.size() == 2 && biases.dim(0) == heads && biases.dim(1) == n_off);
+    std::vector<float> dense((size_t)heads * n * n);
+    for (int h = 0; h < heads; ++h)
+        for (size_t i = 0; i < (size_t)n * n; ++i) dense[(size_t)h * n * n + i] = biases.data[(size_t)h * n_off + idx[i]];
+    return dense;
+}
+
+void tap_bf16(cudaStream_t s, Tap* tap, char const* name, bf16 const* p, size_t n) {
+    if (!tap || !tap->name || std::strcmp(tap->name, name) != 0) return;
+    if (n > tap->capacity) fail(std::string("tap buffer too small for ") + name);
+    enc::bf16_to_f32(s, p, (int64_t)n, tap->out);
+    tap->written = n;
+}
+
+}  // namespace
+
+StageCfg SamModel::stage(int i) { return StageCfg{kDims[i], kRes[i], kDepths[i], kHeadsCfg[i], kWindows[i]}; }
+
+// ---------------------------------------------------------------------------------------------
+SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_sms) {
+    WeightFile const wf = WeightFile::load(weight_path);
+    std::string const E = "image_encoder.";
+
+    // --- PatchEmbed
+    {
+        auto const& w = wf.get(E + "patch_embed.seq.0.c.weight", {32, 3, 3, 3});
+        std::vector<float> scale, shift;
+        bn_fold(wf, E + "patch_embed.seq.0", 32, scale, shift);
+        std::vector<float> o(27 * 32);
+        for (int oc = 0; oc < 32; ++oc)
+            for (int ci = 0; ci < 3; ++ci)
+                for (int t = 0; t < 9; ++t) o[(size_t)(t * 3 + ci) * 32 + oc] = w.data[((size_t)oc * 3 + ci) * 9 + t] * scale[(size_t)oc];
+        enc_.conv1_w.upload(o);
+        enc_.conv1_b.upload(shift);
+        enc_.conv2 = load_conv_bn(wf, E + "patch_embed.seq.2", 64, 32, 3);
+    }
+    // --- layer 0: MBConv x2
+    for (int i = 0; i < 2; ++i) {
+        std::string const p = E + "layers.0.blocks." + std::to_string(i);
+        enc_.mb[i].conv1 = load_conv_bn(wf, p + ".conv1", 256, 64, 1);
+        enc_.mb[i].conv2 = load_dw_bn(wf, p + ".conv2", 256);
+        enc_.mb[i].conv3 = load_conv_bn(wf, p + ".conv3", 64, 256, 1);
+    }
+    // --- PatchMerging 0..2
+    for (int i = 0; i < 3; ++i) {
+        std::string const p = E + "layers." + std::to_string(i) + ".downsample";
+        int const din = kDims[i], dout = kDims[i + 1];
+        enc_.merge[i].conv1 = load_conv_bn(wf, p + ".conv1", dout, din, 1);
+        enc_.merge[i].conv2 = load_dw_bn(wf, p + ".conv2", dout);
+        enc_.merge[i].conv3 = load_conv_bn(wf, p + ".conv3", dout, dout, 1);
+        enc_.merge[i].stride = (dout == 320 || dout == 448 || dout == 576) ? 1 : 2;
+    }
+    // --- TinyViT blocks
+    for (int st = 1; st <= 3; ++st) {
+        int const C = kDims[st], heads = kHeadsCfg[st], ws = kWindows[st];
+        for (int i = 0; i < kDepths[st]; ++i) {
+            std::string const p = E + "layers." + std::to_string(st) + ".blocks." + std::to_string(i);
+            BlockW b;
+            b.attn_norm = load_norm(wf, p + ".attn.norm", C);
+            b.qkv = load_linear16(wf, p + ".attn.qkv", 3 * C, C);
+            b.proj = load_linear16(wf, p + ".attn.proj", C, C);
+            b.attn_bias.upload(dense_attention_bias(wf.get(p + ".attn.attention_biases"), heads, ws));
+            b.local_conv = load_dw_bn(wf, p + ".local_conv", C);
+            b.mlp_norm = load_norm(wf, p + ".mlp.norm", C);
+            b.fc1 = load_linear16(wf, p + ".mlp.fc1", 4 * C, C);
+            b.fc2 = load_linear16(wf, p + ".mlp.fc2", C, 4 * C);
+            enc_.blocks[st - 1].push_back(std::move(b));
+        }
+    }
+    // --- neck
+    {
+        auto const& w1 = wf.get(E + "neck.0.weight", {256, 320, 1, 1});
+        enc_.neck1.n = 256;
+        enc_.neck1.k = 320;
+        enc_.neck1.w.upload(to_bf16(w1.data));
+        enc_.neck_ln1 = load_norm(wf, E + "neck.1", 256);
+        auto const& w2 = wf.get(E + "neck.2.weight", {256, 256, 3, 3});
+        std::vector<float> o((size_t)256 * 2304);
+        for (int oc = 0; oc < 256; ++oc)
+            for (int ci = 0; ci < 256; ++ci)
+                for (int t = 0; t < 9; ++t) o[(size_t)oc * 2304 + (size_t)t * 256 + ci] = w2.data[((size_t)oc * 256 + ci) * 9 + t];
+        enc_.neck2.n = 256;
+        enc_.neck2.k = 2304;
+        enc_.neck2.w.upload(to_bf16(o));
+        enc_.neck_ln2 = load_norm(wf, E + "neck.3", 256);
+    }
+
+    // --- prompt encoder + mask decoder (fp32)
+    std::string const P = "prompt_encoder.", D = "mask_decoder.";
+    dec_.gaussian.upload(wf.get(P + "pe_layer.positional_encoding_gaussian_matrix", {2, 128}).data);
+    {
+        std::vector<float> pe(4 * 256);
+        for (int i = 0; i < 4; ++i) {
+            auto const& t = wf.get(P + "point_embeddings." + std::to_string(i) + ".weight", {1, 256});
+            std::copy(t.data.begin(), t.data.end(), pe.begin() + i * 256);
+        }
+        dec_.point_embed.upload(pe);
+    }
+    dec_.not_a_point.upload(wf.get(P + "not_a_point_embed.weight", {1, 256}).data);
+    dec_.no_mask.upload(wf.get(P + "no_mask_embed.weight", {1, 256}).data);
+    dec_.iou_token.upload(wf.get(D + "iou_token.weight", {1, 256}).data);
+    dec_.mask_tokens.upload(wf.get(D + "mask_tokens.weight", {4, 256}).data);
+    for (int i = 0; i < 2; ++i) {
+        std::string const p = D + "transformer.layers." + std::to_string(i);
+        DecLayerW& l = dec_.layers[i];
+        l.self_attn = load_attn(wf, p + ".self_attn", 256, 256);
+        l.t2i = load_attn(wf, p + ".cross_attn_token_to_image", 256, 128);
+        l.i2t = load_attn(wf, p + ".cross_attn_image_to_token", 256, 128);
+        l.n1 = load_norm(wf, p + ".norm1", 256);
+        l.n2 = load_norm(wf, p + ".norm2", 256);
+        l.n3 = load_norm(wf, p + ".norm3", 256);
+        l.n4 = load_norm(wf, p + ".norm4", 256);
+        l.lin1 = load_linear32(wf, p + ".mlp.lin1", 2048, 256);
+        l.lin2 = load_linear32(wf, p + ".mlp.lin2", 256, 2048);
+    }
+    dec_.final_attn = load_attn(wf, D + "transformer.final_attn_token_to_image", 256, 128);
+    dec_.norm_final = load_norm(wf, D + "transformer.norm_final_attn", 256);
+    {
+        // ConvTranspose2d(256, 64, 2, 2): weight (cin, cout, 2, 2) -> GEMM operand ((dy,dx,co), ci)
+        auto const& w = wf.get(D + "output_upscaling.0.weight", {256, 64, 2, 2});
+        auto const& b = wf.get(D + "output_upscaling.0.bias", {64});
+        std::vector<float> o((size_t)256 * 256), bb(256);
+        for (int ci = 0; ci < 256; ++ci)
+            for (int co = 0; co < 64; ++co)
+                for (int t = 0; t < 4; ++t) o[((size_t)t * 64 + co) * 256 + ci] = w.data[((size_t)ci * 64 + co) * 4 + t];
+        for (int t = 0; t < 4; ++t)
+            for (int co = 0; co < 64; ++co) bb[(size_t)t * 64 + co] = b.data[(size_t)co];
+        dec_.up1.n = 256;
+        dec_.up1.k = 256;
+        dec_.up1.w.upload(o);
+        dec_.up1.b.upload(bb);
+        dec_.up_ln = load_norm(wf, D + "output_upscaling.1", 64);
+        auto const& w2 = wf.get(D + "output_upscaling.3.weight", {64, 32, 2, 2});
+        auto const& b2 = wf.get(D + "output_upscaling.3.bias", {32});
+        std::vector<float> o2((size_t)128 * 64), bb2(128);
+        for (int c1 = 0; c1 < 64; ++c1)
+            for (int c2 = 0; c2 < 32; ++c2)
+                for (int t = 0; t < 4; ++t) o2[((size_t)t * 32 + c2) * 64 + c1] = w2.data[((size_t)c1 * 32 + c2) * 4 + t];
+        for (int t = 0; t < 4; ++t)
+            for (int c2 = 0; c2 < 32; ++c2) bb2[(size_t)t * 32 + c2] = b2.data[(size_t)c2];
+        dec_.up2.n = 128;
+        dec_.up2.k = 64;
+        dec_.up2.w.upload(o2);
+        dec_.up2.b.upload(bb2);
+    }
+    for (int m = 0; m < 4; ++m) {
+        std::string const p = D + "output_hypernetworks_mlps." + std::to_string(m) + ".layers.";
+        dec_.hyper[m][0] = load_linear32(wf, p + "0", 256, 256);
+        dec_.hyper[m][1] = load_linear32(wf, p + "1", 256, 256);
+        dec_.hyper[m][2] = load_linear32(wf, p + "2", 32, 256);
+    }
+    dec_.iou[0] = load_linear32(wf, D + "iou_prediction_head.layers.0", 256, 256);
+    dec_.iou[1] = load_linear32(wf, D + "iou_prediction_head.layers.1", 256, 256);
+    dec_.iou[2] = load_linear32(wf, D + "iou_prediction_head.layers.2", 4, 256);
+
+    dec_.dense_pe.allocate((size_t)dec::kImgTokens * dec::kDim);
+    dec::dense_pe(nullptr, dec_.gaussian.get(), dec_.dense_pe.get());
+    CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+// ---------------------------------------------------------------------------------------------
+EncoderWorkspace::EncoderWorkspace(int mb) : max_batch(mb) {
+    size_t const B = (size_t)mb;
+    c1.allocate(B * 512 * 512 * 32);
+    col.allocate(B * 65536 * 288);
+    xa.allocate(B * 65536 * 64);
+    xb.allocate(B * 65536 * 64);
+    for (auto& b : big) b.allocate(B * 65536 * 256);
+    for (int st = 1; st <= 3; ++st) {
+        StageCfg const c = SamModel::stage(st);
+        int const pad = (c.ws - c.res % c.ws) % c.ws, pr = c.res + pad, nw = pr / c.ws, n = c.ws * c.ws;
+        win_rows[st - 1] = nw * nw * n;
+        std::vector<int> map(B * (size_t)win_rows[st - 1]);
+        size_t m = 0;
+        for (int b = 0; b < mb; ++b)
+            for (int wy = 0; wy < nw; ++wy)
+                for (int wx = 0; wx < nw; ++wx)
+                    for (int iy = 0; iy < c.ws; ++iy)
+                        for (int ix = 0; ix < c.ws; ++ix) {
+                            int const y = wy * c.ws + iy, x = wx * c.ws + ix;
+                            map[m++] = (y < c.res && x < c.res) ? (b * c.res + y) * c.res + x : -1;
+                        }
+        row_map[st - 1].upload(map);
+    }
+}
+
+DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
+    size_t const P = (size_t)mp;
+    coords.allocate(P * 4);
+    labels.allocate(P * 2);
+    for (auto* b : {&tok0, &queries, &tq, &tk, &tv, &ta, &tmp}) b->allocate(P * 7 * 256);
+    t128a.allocate(P * 7 * 128);
+    t128b.allocate(P * 7 * 128);
+    hid.allocate(P * 7 * 2048);
+    h1.allocate(P * 4 * 256);
+    h2.allocate(P * 4 * 256);
+    hyper.allocate(P * 4 * 32);
+    iou.allocate(P * 4);
+    for (auto* b : {&keys, &kpe, &big256}) b->allocate(P * 4096 * 256);
+    for (auto* b : {&Kp, &Vp, &Qp, &ao}) b->allocate(P * 4096 * 128);
+    up2.allocate(P * 16384 * 128);
+    low.allocate(P * 4 * 65536);
+    plane_index.allocate(P * 3);
+    iou_sel.allocate(P * 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+void SamModel::gemm16(cudaStream_t s, bf16 const* a, int64_t rows, Linear16 const& l, void* out, int act,
+                      bf16 const* residual, int const* row_map, bool out_f32) const {
+    gemm::Operand A{a, rows, l.k, l.k};
+    gemm::Operand B{l.w.get(), l.n, l.k, l.k};
+    gemm::Epilogue e;
+    e.bias = l.b.get();
+    e.residual = residual;
+    e.row_map = row_map;
+    e.act = act;
+    e.out_f32 = out_f32 ? 1 : 0;
+    e.ldc = l.n;
+    gemm::launch(s, false, A, B, out, e, num_sms_);
+}
+
+void SamModel::gemm32(cudaStream_t s, float const* a, int64_t rows, Linear32 const& l, float* out, int act) const {
+    gemm::Operand A{a, rows, l.k, l.k};
+    gemm::Operand B{l.w.get(), l.n, l.k, l.k};
+    gemm::Epilogue e;
+    e.bias = l.b.get();
+    e.act = act;
+    e.out_f32 = 1;
+    e.ldc = l.n;
+    gemm::launch(s, true, A, B, out, e, num_sms_);
+}
+
+void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const* images, int batch, int w, int h,
+                      int channels, float* emb_out, Tap* tap) const {
+    DLIMG_ASSERT(batch >= 1 && batch <= ws.max_batch);
+    int64_t const B = batch;
+    using gemm::ACT_GELU;
+    using gemm::ACT_NONE;
+
+    // PatchEmbed: fused preprocess + conv1 + GELU, then conv2 as im2col + GEMM
+    enc::conv1_preprocess(s, images, batch, w, h, channels, enc_.conv1_w.get(), enc_.conv1_b.get(), ws.c1.get());
+    tap_bf16(s, tap, "conv1", ws.c1.get(), (size_t)B * 512 * 512 * 32);
+    enc::im2col3x3(s, ws.c1.get(), batch, 512, 512, 32, 2, ws.col.get());
+    bf16* x = ws.xa.get();
+    bf16* y = ws.xb.get();
+    gemm16(s, ws.col.get(), B * 65536, enc_.conv2, x, ACT_NONE, nullptr, nullptr);
+    tap_bf16(s, tap, "patch_embed", x, (size_t)B * 65536 * 64);
+
+    // layer 0: MBConv x2 (1x1 expand + GELU, dw3x3 + GELU, 1x1 project + shortcut + GELU)
+    for (int i = 0; i < 2; ++i) {
+        MBConvW const& m = enc_.mb[i];
+        gemm16(s, x, B * 65536, m.conv1, ws.big[0].get(), ACT_GELU, nullptr, nullptr);
+        enc::dwconv3x3(s, ws.big[0].get(), batch, 256, 256, 256, 1, m.conv2.w.get(), m.conv2.b.get(), true, ws.big[1].get());
+        gemm16(s, ws.big[1].get(), B * 65536, m.conv3, y, ACT_GELU, x, nullptr);
+        std::swap(x, y);
+        tap_bf16(s, tap, i == 0 ? "mb0" : "mb1", x, (size_t)B * 65536 * 64);
+    }
+
+    auto merge = [&](MergeW const& m, int res, char const* name) {
+        int const out_res = m.stride == 2 ? res / 2 : res;
+        int const dout = m.conv1.n;
+        gemm16(s, x, B * res * res, m.conv1, ws.big[0].get(), ACT_GELU, nullptr, nullptr);
+        enc::dwconv3x3(s, ws.big[0].get(), batch, res, res, dout, m.stride, m.conv2.w.get(), m.conv2.b.get(), true,
+                       ws.big[1].get());
+        gemm16(s, ws.big[1].get(), B * out_res * out_res, m.conv3, y, ACT_NONE, nullptr, nullptr);
+        std::swap(x, y);
+        tap_bf16(s, tap, name, x, (size_t)B * out_res * out_res * dout);
+    };
+    merge(enc_.merge[0], 256, "layer0");
+
+    for (int st = 1; st <= 3; ++st) {
+        StageCfg const c = stage(st);
+        int const C = c.dim, L = c.res * c.res, n = c.ws * c.ws;
+        int64_t const wrows = B * ws.win_rows[st - 1];
+        int const windows = (int)(wrows / n);
+        int const* map = ws.row_map[st - 1].get();
+        for (int i = 0; i < c.depth; ++i) {
+            BlockW const& b = enc_.blocks[st - 1][(size_t)i];
+            std::string const tn = "s" + std::to_string(st) + "b" + std::to_string(i);
+            // attention branch: pad + partition + LN (gather), QKV, windowed attention, proj + un-partition + residual
+            enc::layernorm_rows(s, x, (int)wrows, C, map, b.attn_norm.g.get(), b.attn_norm.b.get(), 1e-5f, ws.big[0].get(), false);
+            tap_bf16(s, tap, (tn + ".ln").c_str(), ws.big[0].get(), (size_t)wrows * C);
+            gemm16(s, ws.big[0].get(), wrows, b.qkv, ws.big[1].get(), ACT_NONE, nullptr, nullptr);
+            tap_bf16(s, tap, (tn + ".qkv").c_str(), ws.big[1].get(), (size_t)wrows * 3 * C);
+            enc::window_attention(s, ws.big[1].get(), windows, n, c.heads, b.attn_bias.get(), ws.big[2].get());
+            tap_bf16(s, tap, (tn + ".att").c_str(), ws.big[2].get(), (size_t)wrows * C);
+            gemm16(s, ws.big[2].get(), wrows, b.proj, x, ACT_NONE, x, map);
+            tap_bf16(s, tap, (tn + ".proj").c_str(), x, (size_t)B * L * C);
+            // local depthwise conv (no activation, no residual)
+            enc::dwconv3x3(s, x, batch, c.res, c.res, C, 1, b.local_conv.w.get(), b.local_conv.b.get(), false, y);
+            tap_bf16(s, tap, (tn + ".lc").c_str(), y, (size_t)B * L * C);
+            // MLP branch
+            enc::layernorm_rows(s, y, (int)(B * L), C, nullptr, b.mlp_norm.g.get(), b.mlp_norm.b.get(), 1e-5f, ws.big[0].get(), false);
+            gemm16(s, ws.big[0].get(), B * L, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, nullptr);
+            gemm16(s, ws.big[1].get(), B * L, b.fc2, y, ACT_NONE, y, nullptr);
+            std::swap(x, y);
+            tap_bf16(s, tap, tn.c_str(), x, (size_t)B * L * C);
+        }
+        if (st < 3) merge(enc_.merge[st], c.res, st == 1 ? "layer1" : "layer2");
+    }
+    tap_bf16(s, tap, "layer3", x, (size_t)B * 4096 * 320);
+
+    // neck: 1x1 conv -> LayerNorm2d -> 3x3 conv -> LayerNorm2d (token-major, so LayerNorm2d is a row LayerNorm)
+    gemm16(s, x, B * 4096, enc_.neck1, ws.big[0].get(), ACT_NONE, nullptr, nullptr);
+    enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln1.g.get(), enc_.neck_ln1.b.get(), 1e-6f,
+                        ws.big[1].get(), false);
+    tap_bf16(s, tap, "neck1", ws.big[1].get(), (size_t)B * 4096 * 256);
+    enc::im2col3x3(s, ws.big[1].get(), batch, 64, 64, 256, 1, ws.col.get());
+    gemm16(s, ws.col.get(), B * 4096, enc_.neck2, ws.big[0].get(), ACT_NONE, nullptr, nullptr);
+    enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f,
+                        emb_out, true);
+    if (tap && tap->name && std::strcmp(tap->name, "neck") == 0) {
+        size_t const n = (size_t)B * 4096 * 256;
+        if (n > tap->capacity) fail("tap buffer too small for neck");
+        CUDA_CHECK(cudaMemcpyAsync(tap->out, emb_out, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        tap->written = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+void SamModel::prepare_embedding(cudaStream_t s, float const* emb, EmbeddingCache& c) const {
+    size_t const n256 = (size_t)dec::kImgTokens * 256, n128 = (size_t)dec::kImgTokens * 128;
+    if (!c.keys0) {
+        c.keys0.allocate(n256);
+        c.kpe0.allocate(n256);
+        c.K0.allocate(n128);
+        c.V0.allocate(n128);
+        c.Q0i.allocate(n128);
+    }
+    dec::embed_prepare(s, emb, dec_.no_mask.get(), dec_.dense_pe.get(), dec::kImgTokens, c.keys0.get(), c.kpe0.get());
+    DecLayerW const& l0 = dec_.layers[0];
+    gemm32(s, c.kpe0.get(), dec::kImgTokens, l0.t2i.k, c.K0.get(), gemm::ACT_NONE);
+    gemm32(s, c.keys0.get(), dec::kImgTokens, l0.t2i.v, c.V0.get(), gemm::ACT_NONE);
+    gemm32(s, c.kpe0.get(), dec::kImgTokens, l0.i2t.q, c.Q0i.get(), gemm::ACT_NONE);
+    c.ready = true;
+}
+
+void SamModel::lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, int rows, Linear32 const& l, bool relu,
+                   float* y, int64_t ys) const {
+    dec::linear_small(s, x, xs, x2, xs, rows, l.k, l.w.get(), l.b.get(), l.n, relu, y, ys);
+}
+
+// Token self-attention block of the two-way transformer: queries <- LN(queries? + out_proj(attn(q, k, v)))
+void SamModel::attn_tokens(cudaStream_t s, DecoderWorkspace& ws, AttnW const& a, bool with_pe, bool residual, Norm const& n,
+                           int P) const {
+    int const R = P * dec::kTokens;
+    float const* pe = with_pe ? ws.tok0.get() : nullptr;
+    lin(s, ws.queries.get(), 256, pe, R, a.q, false, ws.tq.get(), 256);
+    lin(s, ws.queries.get(), 256, pe, R, a.k, false, ws.tk.get(), 256);
+    lin(s, ws.queries.get(), 256, nullptr, R, a.v, false, ws.tv.get(), 256);
+    dec::token_self_attention(s, ws.tq.get(), ws.tk.get(), ws.tv.get(), P, ws.ta.get());
+    lin(s, ws.ta.get(), 256, nullptr, R, a.o, false, ws.tmp.get(), 256);
+    dec::layernorm256(s, ws.tmp.get(), residual ? ws.queries.get() : nullptr, 0, R, n.g.get(), n.b.get(), nullptr, 0,
+                      ws.queries.get(), nullptr);
+}
+
+void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, EmbeddingCache const& cache, int P) const {
+    DLIMG_ASSERT(P >= 1 && P <= ws.max_prompts);
+    DLIMG_ASSERT(cache.ready);
+    int const R = P * dec::kTokens;
+    int64_t const IR = (int64_t)P * dec::kImgTokens;  // image-side rows
+    int64_t const img_stride = (int64_t)dec::kImgTokens * 128;
+
+    dec::PromptParams pp{dec_.gaussian.get(), dec_.point_embed.get(), dec_.not_a_point.get(), dec_.iou_token.get(),
+                         dec_.mask_tokens.get()};
+    dec::prompt_tokens(s, ws.coords.get(), ws.labels.get(), P, pp, ws.tok0.get());
+    CUDA_CHECK(cudaMemcpyAsync(ws.queries.get(), ws.tok0.get(), sizeof(float) * (size_t)R * 256, cudaMemcpyDeviceToDevice, s));
+
+    float const* keys = cache.keys0.get();  // layer 0 reads the shared, prompt-independent tensors
+    float const* kpe = cache.kpe0.get();
+    for (int li = 0; li < 2; ++li) {
+        DecLayerW const& l = dec_.layers[li];
+        bool const first = li == 0;
+        // (1) token self-attention (layer 0: no positional encoding, output replaces the queries)
+        attn_tokens(s, ws, l.self_attn, !first, !first, l.n1, P);
+        // (2) tokens attend to the image
+        lin(s, ws.queries.get(), 256, ws.tok0.get(), R, l.t2i.q, false, ws.t128a.get(), 128);
+        if (first) {
+            dec::token_to_image_attention(s, ws.t128a.get(), cache.K0.get(), cache.V0.get(), 0, P, ws.t128b.get());
+        } else {
+            gemm32(s, kpe, IR, l.t2i.k, ws.Kp.get(), gemm::ACT_NONE);
+            gemm32(s, keys, IR, l.t2i.v, ws.Vp.get(), gemm::ACT_NONE);
+            dec::token_to_image_attention(s, ws.t128a.get(), ws.Kp.get(), ws.Vp.get(), img_stride, P, ws.t128b.get());
+        }
+        lin(s, ws.t128b.get(), 128, nullptr, R, l.t2i.o, false, ws.tmp.get(), 256);
+        dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, l.n2.g.get(), l.n2.b.get(), nullptr, 0, ws.queries.get(), nullptr);
+        // (3) token MLP
+        lin(s, ws.queries.get(), 256, nullptr, R, l.lin1, true, ws.hid.get(), 2048);
+        lin(s, ws.hid.get(), 2048, nullptr, R, l.lin2, false, ws.tmp.get(), 256);
+        dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, l.n3.g.get(), l.n3.b.get(), nullptr, 0, ws.queries.get(), nullptr);
+        // (4) image attends to the tokens; keys <- LN(keys + out_proj(attn)), and keys + pos for the next consumer
+        lin(s, ws.queries.get(), 256, ws.tok0.get(), R, l.i2t.k, false, ws.t128a.get(), 128);
+        lin(s, ws.queries.get(), 256, nullptr, R, l.i2t.v, false, ws.t128b.get(), 128);
+        if (first) {
+            dec::image_to_token_attention(s, cache.Q0i.get(), 0, ws.t128a.get(), ws.t128b.get(), P, ws.ao.get());
+        } else {
+            gemm32(s, kpe, IR, l.i2t.q, ws.Qp.get(), gemm::ACT_NONE);
+            dec::image_to_token_attention(s, ws.Qp.get(), img_stride, ws.t128a.get(), ws.t128b.get(), P, ws.ao.get());
+        }
+        gemm32(s, ws.ao.get(), IR, l.i2t.o, ws.big256.get(), gemm::ACT_NONE);
+        dec::layernorm256(s, ws.big256.get(), keys, first ? dec::kImgTokens : IR, IR, l.n4.g.get(), l.n4.b.get(),
+                          dec_.dense_pe.get(), dec::kImgTokens, ws.keys.get(), ws.kpe.get());
+        keys = ws.keys.get();
+        kpe = ws.kpe.get();
+    }
+    // final token -> image attention
+    lin(s, ws.queries.get(), 256, ws.tok0.get(), R, dec_.final_attn.q, false, ws.t128a.get(), 128);
+    gemm32(s, kpe, IR, dec_.final_attn.k, ws.Kp.get(), gemm::ACT_NONE);
+    gemm32(s, keys, IR, dec_.final_attn.v, ws.Vp.get(), gemm::ACT_NONE);
+    dec::token_to_image_attention(s, ws.t128a.get(), ws.Kp.get(), ws.Vp.get(), img_stride, P, ws.t128b.get());
+    lin(s, ws.t128b.get(), 128, nullptr, R, dec_.final_attn.o, false, ws.tmp.get(), 256);
+    dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, dec_.norm_final.g.get(), dec_.norm_final.b.get(), nullptr, 0,
+                      ws.queries.get(), nullptr);
+
+    // IoU head on the iou token, hypernetwork MLPs on the four mask tokens (row stride 7*256 selects the token)
+    int64_t const ts = (int64_t)dec::kTokens * 256;
+    lin(s, ws.queries.get(), ts, nullptr, P, dec_.iou[0], true, ws.h1.get(), 256);
+    lin(s, ws.h1.get(), 256, nullptr, P, dec_.iou[1], true, ws.h2.get(), 256);
+    lin(s, ws.h2.get(), 256, nullptr, P, dec_.iou[2], false, ws.iou.get(), 4);
+    for (int m = 0; m < 4; ++m) {
+        lin(s, ws.queries.get() + (1 + m) * 256, ts, nullptr, P, dec_.hyper[m][0], true, ws.h1.get(), 256);
+        lin(s, ws.h1.get(), 256, nullptr, P, dec_.hyper[m][1], true, ws.h2.get(), 256);
+        lin(s, ws.h2.get(), 256, nullptr, P, dec_.hyper[m][2], false, ws.hyper.get() + m * 32, 128);
+    }
+
+    // upscaling: two transposed 2x2/stride-2 convolutions as GEMMs in a blocked pixel layout
+    gemm32(s, keys, IR, dec_.up1, ws.big256.get(), gemm::ACT_NONE);
+    dec::layernorm64_gelu(s, ws.big256.get(), IR * 4, dec_.up_ln.g.get(), dec_.up_ln.b.get());
+    gemm32(s, ws.big256.get(), IR * 4, dec_.up2, ws.up2.get(), gemm::ACT_GELU);
+    dec::mask_dot(s, ws.hyper.get(), ws.up2.get(), P, ws.low.get());
+}
+
+}  // namespace dlimg

@@ -1,0 +1,189 @@
+// model.hpp -- MobileSAM on the device: weights (folded / re-laid-out at load), the TinyViT encoder
+// launch sequence and the batched prompt decoder.  Takes the place of the reference's
+// SegmentAnythingModel + three onnxruntime sessions (segmentation.hpp:17-32, session.cpp:57-136).
+#pragma once
+
+#include "common.hpp"
+#include "kernels/decoder_kernels.cuh"
+#include "kernels/encoder_kernels.cuh"
+#include "weights.hpp"
+
+#include <cuda_bf16.h>
+
+#include <string>
+#include <vector>
+
+namespace dlimg {
+
+using bf16 = __nv_bfloat16;
+
+template <typename T> class DeviceBuffer {
+  public:
+    DeviceBuffer() = default;
+    explicit DeviceBuffer(size_t n) { allocate(n); }
+    DeviceBuffer(DeviceBuffer const&) = delete;
+    DeviceBuffer& operator=(DeviceBuffer const&) = delete;
+    DeviceBuffer(DeviceBuffer&& o) noexcept : ptr_(o.ptr_), n_(o.n_) { o.ptr_ = nullptr; o.n_ = 0; }
+    DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
+        if (this != &o) { release(); ptr_ = o.ptr_; n_ = o.n_; o.ptr_ = nullptr; o.n_ = 0; }
+        return *this;
+    }
+    ~DeviceBuffer() { release(); }
+
+    void allocate(size_t n) {
+        release();
+        if (n) CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ptr_), n * sizeof(T)));
+        n_ = n;
+    }
+    void release() {
+        if (ptr_) cudaFree(ptr_);
+        ptr_ = nullptr;
+        n_ = 0;
+    }
+    void upload(std::vector<T> const& host) {
+        allocate(host.size());
+        if (!host.empty()) CUDA_CHECK(cudaMemcpy(ptr_, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    T* get() const { return ptr_; }
+    size_t size() const { return n_; }
+    explicit operator bool() const { return ptr_ != nullptr; }
+
+  private:
+    T* ptr_ = nullptr;
+    size_t n_ = 0;
+};
+
+// ---- weights ----------------------------------------------------------------------------------
+struct Linear16 {  // bf16 weight (N, K) row-major + fp32 bias (N) -- encoder GEMM operand B
+    DeviceBuffer<bf16> w;
+    DeviceBuffer<float> b;
+    int n = 0, k = 0;
+};
+struct Linear32 {  // fp32 weight (N, K) + bias -- decoder
+    DeviceBuffer<float> w;
+    DeviceBuffer<float> b;
+    int n = 0, k = 0;
+};
+struct DwConv {  // depthwise 3x3: weight (9, C) fp32, bias (C)
+    DeviceBuffer<float> w, b;
+    int c = 0;
+};
+struct Norm {
+    DeviceBuffer<float> g, b;
+};
+
+struct MBConvW { Linear16 conv1; DwConv conv2; Linear16 conv3; };
+struct MergeW { Linear16 conv1; DwConv conv2; Linear16 conv3; int stride = 2; };
+struct BlockW {
+    Norm attn_norm;
+    Linear16 qkv, proj;
+    DeviceBuffer<float> attn_bias;  // (heads, n, n)
+    DwConv local_conv;
+    Norm mlp_norm;
+    Linear16 fc1, fc2;
+};
+struct StageCfg { int dim, res, depth, heads, ws; };
+
+struct EncoderW {
+    DeviceBuffer<float> conv1_w, conv1_b;  // (27, 32), (32)
+    Linear16 conv2;                        // (64, 288) K = (ky, kx, ci)
+    MBConvW mb[2];
+    MergeW merge[3];
+    std::vector<BlockW> blocks[3];
+    Linear16 neck1;  // (256, 320)
+    Norm neck_ln1;
+    Linear16 neck2;  // (256, 2304) K = (ky, kx, ci)
+    Norm neck_ln2;
+};
+
+struct AttnW { Linear32 q, k, v, o; };
+struct DecLayerW {
+    AttnW self_attn, t2i, i2t;
+    Norm n1, n2, n3, n4;
+    Linear32 lin1, lin2;
+};
+struct DecoderW {
+    DeviceBuffer<float> gaussian, point_embed, not_a_point, no_mask, iou_token, mask_tokens;
+    DecLayerW layers[2];
+    AttnW final_attn;
+    Norm norm_final;
+    Linear32 up1;  // (256 = (dy,dx,co), 256)
+    Norm up_ln;    // LayerNorm2d(64)
+    Linear32 up2;  // (128 = (ey,ex,c2), 64)
+    Linear32 hyper[4][3];
+    Linear32 iou[3];
+    DeviceBuffer<float> dense_pe;  // (4096, 256)
+};
+
+// ---- workspaces -------------------------------------------------------------------------------
+struct EncoderWorkspace {
+    int max_batch = 0;
+    DeviceBuffer<bf16> c1, col, xa, xb, big[4];
+    DeviceBuffer<int> row_map[3];  // stage 1..3: windowed row -> token row (-1 = padding), for max_batch images
+    int win_rows[3] = {0, 0, 0};   // windowed rows per image
+    explicit EncoderWorkspace(int max_batch);
+};
+
+struct DecoderWorkspace {
+    int max_prompts = 0;
+    DeviceBuffer<float> coords, labels;                      // (P,2,2), (P,2)
+    DeviceBuffer<float> tok0, queries, tq, tk, tv, ta, tmp;  // (P,7,256)
+    DeviceBuffer<float> t128a, t128b;                        // (P,7,128)
+    DeviceBuffer<float> hid;                                 // (P,7,2048)
+    DeviceBuffer<float> h1, h2;                              // (P*4,256)
+    DeviceBuffer<float> hyper, iou;                          // (P,4,32), (P,4)
+    DeviceBuffer<float> keys, kpe, big256;                   // (P,4096,256)
+    DeviceBuffer<float> Kp, Vp, Qp, ao;                      // (P,4096,128)
+    DeviceBuffer<float> up2;                                 // (P,16384,128)
+    DeviceBuffer<float> low;                                 // (P,4,256,256)
+    DeviceBuffer<int> plane_index;                           // (P*3)
+    DeviceBuffer<float> iou_sel;                             // (P*3)
+    explicit DecoderWorkspace(int max_prompts);
+};
+
+// Prompt-independent decoder inputs derived once per image embedding.
+struct EmbeddingCache {
+    DeviceBuffer<float> keys0, kpe0;     // (4096, 256): embedding + no_mask_embed, and + dense PE
+    DeviceBuffer<float> K0, V0, Q0i;     // (4096, 128): layer-0 projections that do not depend on the prompt
+    bool ready = false;
+};
+
+struct Tap {  // debug: copy a named activation as fp32 to a device buffer
+    char const* name = nullptr;
+    float* out = nullptr;
+    size_t capacity = 0;  // floats
+    size_t written = 0;
+};
+
+class SamModel {
+  public:
+    SamModel(std::string const& weight_path, int num_sms);
+
+    // images: `batch` device descriptors of u8 images with identical (w, h, channels), w, h <= 1024.
+    // emb_out: (batch, 4096, 256) fp32, token-major (row = y*64 + x).
+    void encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const* images, int batch, int w, int h, int channels,
+                float* emb_out, Tap* tap = nullptr) const;
+
+    void prepare_embedding(cudaStream_t s, float const* emb, EmbeddingCache& cache) const;
+
+    // Runs the prompt encoder + mask decoder for P prompts (coords/labels already uploaded into ws).
+    // Results: ws.low (P, 4, 256, 256) logits and ws.iou (P, 4).
+    void decode(cudaStream_t s, DecoderWorkspace& ws, EmbeddingCache const& cache, int P) const;
+
+    static StageCfg stage(int i);  // i = 1..3
+
+  private:
+    void gemm16(cudaStream_t s, bf16 const* a, int64_t rows, Linear16 const& l, void* out, int act, bf16 const* residual,
+                int const* row_map, bool out_f32 = false) const;
+    void gemm32(cudaStream_t s, float const* a, int64_t rows, Linear32 const& l, float* out, int act) const;
+    void lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, int rows, Linear32 const& l, bool relu, float* y,
+             int64_t ys) const;
+    void attn_tokens(cudaStream_t s, DecoderWorkspace& ws, AttnW const& a, bool with_pe, bool residual, Norm const& n,
+                     int P) const;
+
+    EncoderW enc_;
+    DecoderW dec_;
+    int num_sms_ = 148;
+};
+
+}  // namespace dlimg

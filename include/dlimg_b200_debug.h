@@ -1,0 +1,35 @@
+/* dlimg_b200_debug.h -- kernel-level entry points of libdlimgedit.so used ONLY by the parity tests
+ * (tests/): they let a test drive one CUDA kernel (or one encoder stage) with its own device buffers and
+ * compare against the oracle.  Not part of the supported interface; may change between rounds. */
+#ifndef DLIMG_B200_DEBUG_H_
+#define DLIMG_B200_DEBUG_H_
+
+#include "dlimg_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dlimg_b200_Debug {
+    uint32_t struct_size;
+    /* C = epilogue(A[M,K] * B[N,K]^T).  Device pointers; elements are bf16 (tf32 == 0) or fp32 (tf32 != 0).
+     * simt != 0 runs the CUDA-core cross-check kernel instead of the tcgen05 kernel.  act: 0 none, 1 GELU(erf),
+     * 2 ReLU.  row_map (optional): output row per input row, -1 drops the row. */
+    dlimg_Result (*gemm)(void* stream, int tf32, int simt, void const* a, void const* b, int M, int N, int K,
+                         float const* bias, void const* residual, int const* row_map, int act, int out_f32, void* out);
+    /* Encodes `count` device-resident images and copies the activation called `name` (see model.cu) as fp32. */
+    dlimg_Result (*encode_tap)(dlimg_Environment, dlimg_ImageView const* dev_views, int count, char const* name,
+                               float* dev_out, size_t capacity, size_t* written);
+    /* Host-side resampling plan of the resize kernel: returns the tap count; first[out_size],
+     * weights[out_size * max_taps]. */
+    int (*resize_plan)(int in_size, int out_size, int max_taps, int* first, float* weights);
+    void (*srgb_tables)(float* decode256, float* threshold256);
+} dlimg_b200_Debug;
+
+DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DLIMG_B200_DEBUG_H_ */

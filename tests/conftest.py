@@ -1,0 +1,74 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with `pytest -m gpu`)")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def oracle_sam():
+    """Seeded synthetic MobileSAM (oracle/mobile_sam_ref.py); the same weights are written for the engine."""
+    import torch
+    from oracle.mobile_sam_ref import build_synthetic
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    return build_synthetic(0)
+
+
+@pytest.fixture(scope="session")
+def model_dir(tmp_path_factory, oracle_sam):
+    """<dir>/segmentation/mobile_sam_b200.bin holding the oracle's synthetic weights."""
+    from dlimgedit_b200 import weights_io
+    d = tmp_path_factory.mktemp("models")
+    os.makedirs(d / "segmentation")
+    weights_io.save(str(d / "segmentation" / weights_io.WEIGHT_FILE_NAME), weights_io.from_state_dict(oracle_sam.state_dict()))
+    return str(d)
+
+
+@pytest.fixture(scope="session")
+def env(model_dir):
+    import dlimgedit_b200 as dl
+    e = dl.Environment(dl.Options(dl.Backend.gpu, model_dir))
+    yield e
+    e.close()
+
+
+def synthetic_image(h, w, c, seed):
+    """Smooth-ish synthetic picture (blobs + noise) so that resampling and the network see structure."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((h, w, c), np.float32)
+    for ch in range(c):
+        acc = np.zeros((h, w), np.float32)
+        for _ in range(6):
+            cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+            s = rng.uniform(0.05, 0.3) * max(h, w)
+            acc += rng.uniform(-1, 1) * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+        img[..., ch] = acc
+    img = (img - img.min()) / (img.max() - img.min() + 1e-6) * 255
+    img += rng.normal(0, 6, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
