@@ -84,6 +84,11 @@ class _Prompt(ctypes.Structure):
                 ("y1", ctypes.c_int)]
 
 
+class _ProfileEntry(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 32), ("launches", ctypes.c_uint64), ("ms", ctypes.c_double),
+                ("flops", ctypes.c_double), ("bytes", ctypes.c_double)]
+
+
 class _Stats(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
 
@@ -128,12 +133,15 @@ class _Ext(ctypes.Structure):
         ("mask_postprocess", _F(_R, _H, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p)),
         ("threshold_mask", _F(_R, _H, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                               ctypes.c_void_p)),
+        ("profile_enable", _F(_R, _H, ctypes.c_int)),
+        ("profile_read", _F(_R, _H, ctypes.POINTER(_ProfileEntry), ctypes.c_int, c_i32p)),
     ]
 
 
 class _Debug(ctypes.Structure):
     _fields_ = [
         ("struct_size", ctypes.c_uint32),
+        ("act_is_bf16", ctypes.c_uint32),
         ("gemm", _F(_R, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                     ctypes.c_int, ctypes.c_void_p)),
@@ -266,6 +274,17 @@ class Environment:
         s = _Stats()
         _check(ext().get_stats(self._h, ctypes.byref(s)))
         return {"kernel_launches": s.kernel_launches, "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes}
+
+    def profile_enable(self, on: bool):
+        _check(ext().profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{kernel category: {launches, ms, flops, bytes}} since the last read (CUDA-event timed per launch)."""
+        arr = (_ProfileEntry * 32)()
+        n = ctypes.c_int(0)
+        _check(ext().profile_read(self._h, arr, 32, ctypes.byref(n)))
+        return {arr[i].name.decode(): {"launches": arr[i].launches, "ms": arr[i].ms, "flops": arr[i].flops,
+                                       "bytes": arr[i].bytes} for i in range(n.value)}
 
     def process_batch(self, views: Sequence[ImageView]) -> List["Segmentation"]:
         n = len(views)

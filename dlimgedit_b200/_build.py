@@ -22,6 +22,7 @@ SOURCES = [
     "model.cu",
     "weights.cpp",
     "image_io.cpp",
+    "profiler.cpp",
     "kernels/gemm.cu",
     "kernels/encoder_kernels.cu",
     "kernels/decoder_kernels.cu",
@@ -77,6 +78,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    soname = LIB_PATH + ".1"  # SOVERSION 1 like the reference (src/CMakeLists.txt:20-23); a copy, so it survives any sync
+    if not os.path.exists(soname) or os.path.getmtime(soname) < os.path.getmtime(LIB_PATH):
+        import shutil
+        shutil.copy2(LIB_PATH, soname)
     return LIB_PATH
 
 

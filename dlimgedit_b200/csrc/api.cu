@@ -6,6 +6,7 @@
 #include "engine.hpp"
 #include "image_io.hpp"
 #include "kernels/gemm.cuh"
+#include "profiler.hpp"
 
 #include <cstring>
 
@@ -165,6 +166,32 @@ dlimg_Result ext_threshold_mask(dlimg_Environment env, float const* logits, int 
     return try_([=] { to_impl(env).threshold_mask(logits, th, tw, w, h, out); });
 }
 
+dlimg_Result ext_profile_enable(dlimg_Environment env, int on) {
+    return try_([=] {
+        std::lock_guard<std::mutex> lock(to_impl(env).mutex());
+        Profiler::get().enable(on != 0);
+    });
+}
+dlimg_Result ext_profile_read(dlimg_Environment env, dlimg_b200_ProfileEntry* out, int capacity, int* count) {
+    return try_([=] {
+        std::lock_guard<std::mutex> lock(to_impl(env).mutex());
+        to_impl(env).bind_device();
+        auto const totals = Profiler::get().collect();
+        int n = 0;
+        for (int c = 0; c < CAT_COUNT && n < capacity; ++c) {
+            if (!totals[(size_t)c].launches) continue;
+            dlimg_b200_ProfileEntry& e = out[n++];
+            std::memset(&e, 0, sizeof(e));
+            std::strncpy(e.name, kernel_cat_name(c), sizeof(e.name) - 1);
+            e.launches = totals[(size_t)c].launches;
+            e.ms = totals[(size_t)c].ms;
+            e.flops = totals[(size_t)c].flops;
+            e.bytes = totals[(size_t)c].bytes;
+        }
+        *count = n;
+    });
+}
+
 dlimg_b200_Ext ext_;
 
 // ---- debug table (tests only; declared in include/dlimg_b200_debug.h) -----------------------------
@@ -256,6 +283,8 @@ DLIMG_B200_EXPORT dlimg_b200_Ext const* dlimg_b200_ext_init(void) {
     ext_.image_tensor = ext_image_tensor;
     ext_.mask_postprocess = ext_mask_postprocess;
     ext_.threshold_mask = ext_threshold_mask;
+    ext_.profile_enable = ext_profile_enable;
+    ext_.profile_read = ext_profile_read;
     return &ext_;
 }
 
@@ -263,6 +292,7 @@ DLIMG_B200_EXPORT dlimg_b200_Ext const* dlimg_b200_ext_init(void) {
 DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void) {
     using namespace dlimg;
     debug_.struct_size = sizeof(DebugApi);
+    debug_.act_is_bf16 = kActBf16 ? 1 : 0;
     debug_.gemm = dbg_gemm;
     debug_.encode_tap = dbg_encode_tap;
     debug_.resize_plan = dbg_resize_plan;

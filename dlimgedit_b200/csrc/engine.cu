@@ -466,9 +466,9 @@ void SegmentationImpl::embedding_nchw(float* out_host) {
     if (!encoded()) fail("segmentation handle holds no processed image");
     cudaStream_t const s = env_.stream();
     size_t const n = (size_t)dec::kImgTokens * kEmbedDim;
-    DeviceBuffer<float> tmp(n);
-    enc::tokens_to_nchw(s, emb_, 1, dec::kImgTokens, kEmbedDim, tmp.get());
-    CUDA_CHECK(cudaMemcpyAsync(out_host, tmp.get(), n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (!env_.emb_scratch_) env_.emb_scratch_.allocate(n);
+    enc::tokens_to_nchw(s, emb_, 1, dec::kImgTokens, kEmbedDim, env_.emb_scratch_.get());
+    CUDA_CHECK(cudaMemcpyAsync(out_host, env_.emb_scratch_.get(), n * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     g_d2h_bytes += n * sizeof(float);
 }

@@ -104,6 +104,7 @@ class EnvironmentImpl {
     std::map<std::pair<int, int>, DeviceAxisPlan> plans_;
     DeviceBuffer<uint8_t> mask_out_;       // device staging for host-destined masks
     DeviceBuffer<uint8_t*> plane_ptrs_;
+    DeviceBuffer<float> emb_scratch_;      // NCHW staging for get_embedding
 };
 
 class SegmentationImpl {

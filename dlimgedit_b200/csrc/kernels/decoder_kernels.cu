@@ -1,6 +1,8 @@
 // decoder_kernels.cu -- see decoder_kernels.cuh.
 #include "decoder_kernels.cuh"
 
+#include "../profiler.hpp"
+
 namespace dlimg {
 namespace dec {
 
@@ -429,17 +431,20 @@ __global__ void select_masks_kernel(float const* __restrict__ iou, int P, int mu
 
 // ---------------------------------------------------------------------------------------------
 void prompt_tokens(cudaStream_t s, float const* coords, float const* labels, int P, PromptParams const& pp, float* tokens) {
+    ProfScope prof(s, CAT_DEC_MISC);
     prompt_tokens_kernel<<<P, 256, 0, s>>>(coords, labels, pp, tokens);
     KERNEL_CHECK();
 }
 
 void dense_pe(cudaStream_t s, float const* gaussian, float* pos) {
+    ProfScope prof(s, CAT_DEC_MISC);
     dense_pe_kernel<<<kImgTokens, 256, 0, s>>>(gaussian, pos);
     KERNEL_CHECK();
 }
 
 void embed_prepare(cudaStream_t s, float const* emb, float const* no_mask, float const* pos, int64_t rows, float* keys0,
                    float* kpe0) {
+    ProfScope prof(s, CAT_DEC_MISC);
     int64_t const total4 = rows * (kDim / 4);
     embed_prepare_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, s>>>(emb, no_mask, pos, total4, keys0, kpe0);
     KERNEL_CHECK();
@@ -447,6 +452,7 @@ void embed_prepare(cudaStream_t s, float const* emb, float const* no_mask, float
 
 void linear_small(cudaStream_t s, float const* x, int64_t x_stride, float const* x2, int64_t x2_stride, int rows, int K,
                   float const* W, float const* b, int N, bool relu, float* y, int64_t y_stride) {
+    ProfScope prof(s, CAT_DEC_LINEAR);
     DLIMG_ASSERT(K <= 2048);
     static bool attr_set = false;
     if (!attr_set) {
@@ -460,12 +466,14 @@ void linear_small(cudaStream_t s, float const* x, int64_t x_stride, float const*
 }
 
 void token_self_attention(cudaStream_t s, float const* q, float const* k, float const* v, int P, float* out) {
+    ProfScope prof(s, CAT_DEC_ATTN);
     token_self_attention_kernel<<<P, 256, 0, s>>>(q, k, v, out);
     KERNEL_CHECK();
 }
 
 void token_to_image_attention(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride, int P,
                               float* out) {
+    ProfScope prof(s, CAT_DEC_ATTN);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_CHECK(cudaFuncSetAttribute(t2i_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT2iSmem));
@@ -477,6 +485,7 @@ void token_to_image_attention(cudaStream_t s, float const* q, float const* K, fl
 
 void image_to_token_attention(cudaStream_t s, float const* Q, int64_t q_stride, float const* kt, float const* vt, int P,
                               float* out) {
+    ProfScope prof(s, CAT_DEC_ATTN);
     dim3 grid(kImgTokens * kHeads / 256, P);
     i2t_attention_kernel<<<grid, 256, 0, s>>>(Q, q_stride, kt, vt, out);
     KERNEL_CHECK();
@@ -484,6 +493,7 @@ void image_to_token_attention(cudaStream_t s, float const* Q, int64_t q_stride, 
 
 void layernorm256(cudaStream_t s, float const* x, float const* res, int64_t res_mod, int64_t rows, float const* gamma,
                   float const* beta, float const* pos, int64_t pos_mod, float* out, float* out2) {
+    ProfScope prof(s, CAT_DEC_NORM);
     if (res_mod <= 0) res_mod = rows;
     if (pos_mod <= 0) pos_mod = rows;
     layernorm256_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, s>>>(x, res, res_mod, rows, gamma, beta, pos, pos_mod, out,
@@ -492,17 +502,20 @@ void layernorm256(cudaStream_t s, float const* x, float const* res, int64_t res_
 }
 
 void layernorm64_gelu(cudaStream_t s, float* x, int64_t rows, float const* gamma, float const* beta) {
+    ProfScope prof(s, CAT_DEC_NORM);
     layernorm64_gelu_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, s>>>(x, rows, gamma, beta);
     KERNEL_CHECK();
 }
 
 void mask_dot(cudaStream_t s, float const* hyper, float const* up2, int P, float* low) {
+    ProfScope prof(s, CAT_DEC_MISC);
     dim3 grid(65536 / 256, P);
     mask_dot_kernel<<<grid, 256, 0, s>>>(hyper, up2, low);
     KERNEL_CHECK();
 }
 
 void select_masks(cudaStream_t s, float const* iou, int P, int multi, int* plane_index, float* iou_out) {
+    ProfScope prof(s, CAT_DEC_MISC);
     select_masks_kernel<<<ceil_div(P, 128), 128, 0, s>>>(iou, P, multi, plane_index, iou_out);
     KERNEL_CHECK();
 }

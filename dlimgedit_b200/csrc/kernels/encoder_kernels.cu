@@ -1,6 +1,8 @@
 // encoder_kernels.cu -- see encoder_kernels.cuh.
 #include "encoder_kernels.cuh"
 
+#include "../profiler.hpp"
+
 namespace dlimg {
 namespace enc {
 
@@ -9,19 +11,19 @@ namespace {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ void unpack8(uint4 const& v, float (&f)[8]) {
-    __nv_bfloat162 const* h = reinterpret_cast<__nv_bfloat162 const*>(&v);
+    act2_t const* h = reinterpret_cast<act2_t const*>(&v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float2 t = __bfloat1622float2(h[i]);
+        float2 t = act22f2(h[i]);
         f[2 * i] = t.x;
         f[2 * i + 1] = t.y;
     }
 }
 __device__ __forceinline__ uint4 pack8(float const (&f)[8]) {
     uint4 v;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+    act2_t* h = reinterpret_cast<act2_t*>(&v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) h[i] = f22act2(f[2 * i], f[2 * i + 1]);
     return v;
 }
 
@@ -36,7 +38,7 @@ constexpr int kC1In = 2 * kC1Tile + 1;  // 33
 
 __global__ void __launch_bounds__(256) conv1_preprocess_kernel(ImageDesc const* __restrict__ imgs, Conv1Params p,
                                                                float const* __restrict__ weight,
-                                                               float const* __restrict__ bias, bf16* __restrict__ out) {
+                                                               float const* __restrict__ bias, act_t* __restrict__ out) {
     __shared__ float tile[kC1In * kC1In * 3];
     __shared__ __align__(16) float wsm[27 * 32];
     __shared__ float bsm[32];
@@ -101,8 +103,8 @@ __global__ void __launch_bounds__(256) conv1_preprocess_kernel(ImageDesc const* 
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void im2col3x3_kernel(bf16 const* __restrict__ in, int H, int W, int C8, int stride, int Ho, int Wo,
-                                 int64_t total, bf16* __restrict__ out) {
+__global__ void im2col3x3_kernel(act_t const* __restrict__ in, int H, int W, int C8, int stride, int Ho, int Wo,
+                                 int64_t total, act_t* __restrict__ out) {
     int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     int const c8 = (int)(t % C8);
@@ -121,9 +123,9 @@ __global__ void im2col3x3_kernel(bf16 const* __restrict__ in, int H, int W, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void dwconv3x3_kernel(bf16 const* __restrict__ in, int H, int W, int C8, int stride, int Ho, int Wo,
+__global__ void dwconv3x3_kernel(act_t const* __restrict__ in, int H, int W, int C8, int stride, int Ho, int Wo,
                                  int64_t total, float const* __restrict__ weight, float const* __restrict__ bias,
-                                 int gelu, bf16* __restrict__ out) {
+                                 int gelu, act_t* __restrict__ out) {
     int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     int const c8 = (int)(t % C8);
@@ -169,7 +171,7 @@ __global__ void dwconv3x3_kernel(bf16 const* __restrict__ in, int H, int W, int 
 // ---------------------------------------------------------------------------------------------
 constexpr int kLnMaxPairs = 5;  // C <= 320
 
-__global__ void __launch_bounds__(256) layernorm_rows_kernel(bf16 const* __restrict__ in, int rows, int C,
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(act_t const* __restrict__ in, int rows, int C,
                                                              int const* __restrict__ src_row,
                                                              float const* __restrict__ gamma,
                                                              float const* __restrict__ beta, float eps,
@@ -183,11 +185,11 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(bf16 const* __restr
     float2 x[kLnMaxPairs];
     float sum = 0.f;
     if (src >= 0) {
-        __nv_bfloat162 const* p = reinterpret_cast<__nv_bfloat162 const*>(in + src * C);
+        act2_t const* p = reinterpret_cast<act2_t const*>(in + src * C);
 #pragma unroll
         for (int i = 0; i < kLnMaxPairs; ++i) {
             int const idx = lane + 32 * i;
-            x[i] = idx < pairs ? __bfloat1622float2(p[idx]) : make_float2(0.f, 0.f);
+            x[i] = idx < pairs ? act22f2(p[idx]) : make_float2(0.f, 0.f);
             sum += x[i].x + x[i].y;
         }
     }
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(bf16 const* __restr
             y = bt;  // LayerNorm of an all-zero padding token
         }
         if (out_f32) reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + (int64_t)row * C)[idx] = y;
-        else reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(out) + (int64_t)row * C)[idx] = __floats2bfloat162_rn(y.x, y.y);
+        else reinterpret_cast<act2_t*>(reinterpret_cast<act_t*>(out) + (int64_t)row * C)[idx] = f22act2(y.x, y.y);
     }
 }
 
@@ -231,9 +233,9 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(bf16 const* __restr
 constexpr int kAttnWarps = 8;
 constexpr int kAttnMaxJ = 7;  // n <= 224 keys
 
-__global__ void __launch_bounds__(kAttnWarps * 32) window_attention_kernel(bf16 const* __restrict__ qkv, int n, int heads,
+__global__ void __launch_bounds__(kAttnWarps * 32) window_attention_kernel(act_t const* __restrict__ qkv, int n, int heads,
                                                                            float const* __restrict__ bias,
-                                                                           bf16* __restrict__ out) {
+                                                                           act_t* __restrict__ out) {
     extern __shared__ float sm[];
     float* Ks = sm;                       // [n][33]
     float* Vs = Ks + n * 33;              // [n][32]
@@ -245,15 +247,15 @@ __global__ void __launch_bounds__(kAttnWarps * 32) window_attention_kernel(bf16 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < n * 32; i += blockDim.x) {
         int const j = i >> 5, d = i & 31;
-        bf16 const* base = qkv + (row0 + j) * ld + h * 96;
-        Ks[j * 33 + d] = __bfloat162float(base[32 + d]);
-        Vs[j * 32 + d] = __bfloat162float(base[64 + d]);
+        act_t const* base = qkv + (row0 + j) * ld + h * 96;
+        Ks[j * 33 + d] = act2f(base[32 + d]);
+        Vs[j * 32 + d] = act2f(base[64 + d]);
     }
     __syncthreads();
     float const scale = 0.17677669529663687f;  // 32^-0.5
     float const* bias_h = bias + (int64_t)h * n * n;
     for (int i = warp; i < n; i += kAttnWarps) {
-        Qs[warp * 32 + lane] = __bfloat162float(qkv[(row0 + i) * ld + h * 96 + lane]);
+        Qs[warp * 32 + lane] = act2f(qkv[(row0 + i) * ld + h * 96 + lane]);
         __syncwarp();
         float s[kAttnMaxJ];
         float mx = -INFINITY;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) window_attention_kernel(bf16 
         __syncwarp();
         float o = 0.f;
         for (int j = 0; j < n; ++j) o = fmaf(Ps[warp * n + j], Vs[j * 32 + lane], o);
-        out[(row0 + i) * C + h * 32 + lane] = __float2bfloat16_rn(o);
+        out[(row0 + i) * C + h * 32 + lane] = f2act(o);
         __syncwarp();
     }
 }
@@ -313,52 +315,58 @@ __global__ void tokens_to_nchw_kernel(float const* __restrict__ in, int tokens, 
     }
 }
 
-__global__ void bf16_to_f32_kernel(bf16 const* __restrict__ in, int64_t n, float* __restrict__ out) {
+__global__ void act_to_f32_kernel(act_t const* __restrict__ in, int64_t n, float* __restrict__ out) {
     int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __bfloat162float(in[i]);
+    if (i < n) out[i] = act2f(in[i]);
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
 void conv1_preprocess(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h, int channels,
-                      float const* weight, float const* bias, bf16* out) {
+                      float const* weight, float const* bias, act_t* out) {
     DLIMG_ASSERT(w >= 1 && h >= 1 && w <= kImageSize && h <= kImageSize);
     int cmap[3];
     channel_map(channels, cmap);
     Conv1Params p{w, h, bytes_per_pixel(channels), cmap[0], cmap[1], cmap[2]};
+    ProfScope prof(s, CAT_CONV1, 2.0 * batch * 512 * 512 * 27 * 32,
+                   (double)batch * ((double)w * h * p.bpp + 512.0 * 512 * 32 * 2));
     dim3 grid(512 / kC1Tile, 512 / kC1Tile, batch), block(kC1Tile, kC1Tile);
     conv1_preprocess_kernel<<<grid, block, 0, s>>>(imgs, p, weight, bias, out);
     KERNEL_CHECK();
 }
 
-void im2col3x3(cudaStream_t s, bf16 const* in, int batch, int H, int W, int C, int stride, bf16* out) {
+void im2col3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, act_t* out) {
     DLIMG_ASSERT(C % 8 == 0);
     int const Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     int64_t const total = (int64_t)batch * Ho * Wo * 9 * (C / 8);
+    ProfScope prof(s, CAT_IM2COL, 0, (double)batch * ((double)H * W * C * 2 + (double)Ho * Wo * 9 * C * 2));
     im2col3x3_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(in, H, W, C / 8, stride, Ho, Wo, total, out);
     KERNEL_CHECK();
 }
 
-void dwconv3x3(cudaStream_t s, bf16 const* in, int batch, int H, int W, int C, int stride, float const* weight,
-               float const* bias, bool gelu, bf16* out) {
+void dwconv3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, float const* weight,
+               float const* bias, bool gelu, act_t* out) {
     DLIMG_ASSERT(C % 8 == 0);
     int const Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     int64_t const total = (int64_t)batch * Ho * Wo * (C / 8);
+    ProfScope prof(s, CAT_DWCONV, 2.0 * batch * Ho * Wo * C * 9, (double)batch * ((double)H * W + (double)Ho * Wo) * C * 2);
     dwconv3x3_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(in, H, W, C / 8, stride, Ho, Wo, total, weight,
                                                                       bias, gelu ? 1 : 0, out);
     KERNEL_CHECK();
 }
 
-void layernorm_rows(cudaStream_t s, bf16 const* in, int rows, int C, int const* src_row, float const* gamma,
+void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const* src_row, float const* gamma,
                     float const* beta, float eps, void* out, bool out_f32) {
     DLIMG_ASSERT(C % 2 == 0 && C <= kLnMaxPairs * 64);
+    ProfScope prof(s, CAT_LAYERNORM, 0, (double)rows * C * (2 + (out_f32 ? 4 : 2)));
     layernorm_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(in, rows, C, src_row, gamma, beta, eps, out, out_f32 ? 1 : 0);
     KERNEL_CHECK();
 }
 
-void window_attention(cudaStream_t s, bf16 const* qkv, int windows, int n, int heads, float const* bias, bf16* out) {
+void window_attention(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out) {
     DLIMG_ASSERT(n <= kAttnMaxJ * 32);
+    ProfScope prof(s, CAT_WIN_ATTN, 4.0 * windows * heads * n * n * 32, (double)windows * n * heads * 128 * 2);
     size_t const smem = sizeof(float) * ((size_t)n * 33 + (size_t)n * 32 + kAttnWarps * 32 + (size_t)kAttnWarps * n);
     static bool attr_set = false;
     if (!attr_set) {
@@ -370,13 +378,15 @@ void window_attention(cudaStream_t s, bf16 const* qkv, int windows, int n, int h
 }
 
 void tokens_to_nchw(cudaStream_t s, float const* in, int batch, int tokens, int C, float* out) {
+    ProfScope prof(s, CAT_OTHER);
     dim3 grid(ceil_div(tokens, 32), ceil_div(C, 32), batch), block(32, 8);
     tokens_to_nchw_kernel<<<grid, block, 0, s>>>(in, tokens, C, out);
     KERNEL_CHECK();
 }
 
-void bf16_to_f32(cudaStream_t s, bf16 const* in, int64_t n, float* out) {
-    bf16_to_f32_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(in, n, out);
+void act_to_f32(cudaStream_t s, act_t const* in, int64_t n, float* out) {
+    ProfScope prof(s, CAT_OTHER);
+    act_to_f32_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(in, n, out);
     KERNEL_CHECK();
 }
 

@@ -4,12 +4,12 @@
 
 #include "../common.hpp"
 
-#include <cuda_bf16.h>
+#include "../act.hpp"
 
 namespace dlimg {
 namespace enc {
 
-using bf16 = __nv_bfloat16;
+using dlimg::act_t;
 
 // One input image as the preprocessing kernels see it (device memory).
 struct ImageDesc {
@@ -23,29 +23,29 @@ struct ImageDesc {
 // (B, 512, 512, 32).  `w`,`h` is the valid (already <= 1024) extent; weight layout [27][32] (tap-major,
 // tap = (ky*3+kx)*3+ci), bias [32].
 void conv1_preprocess(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h, int channels,
-                      float const* weight, float const* bias, bf16* out);
+                      float const* weight, float const* bias, act_t* out);
 
 // im2col for 3x3 / pad 1 convolutions on NHWC bf16: out[(b,oy,ox)][(ky,kx,c)] (K = 9*C).
-void im2col3x3(cudaStream_t s, bf16 const* in, int batch, int H, int W, int C, int stride, bf16* out);
+void im2col3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, act_t* out);
 
 // Depthwise 3x3 / pad 1, NHWC bf16, fp32 weights [9][C] + bias [C] (BN folded), optional GELU.
-void dwconv3x3(cudaStream_t s, bf16 const* in, int batch, int H, int W, int C, int stride, float const* weight,
-               float const* bias, bool gelu, bf16* out);
+void dwconv3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, float const* weight,
+               float const* bias, bool gelu, act_t* out);
 
 // Row LayerNorm over C channels.  src_row (optional, length `rows`): gather index into `in`, -1 = the row
 // is window padding and the output is LN(0) = beta.  Output bf16 or fp32.
-void layernorm_rows(cudaStream_t s, bf16 const* in, int rows, int C, int const* src_row, float const* gamma,
+void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const* src_row, float const* gamma,
                     float const* beta, float eps, void* out, bool out_f32);
 
 // Windowed multi-head attention, head_dim 32.  qkv: (windows*n, heads*96) with per-head [q|k|v];
 // bias: (heads, n, n) fp32 (already gathered from attention_biases); out: (windows*n, heads*32).
-void window_attention(cudaStream_t s, bf16 const* qkv, int windows, int n, int heads, float const* bias, bf16* out);
+void window_attention(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out);
 
 // (tokens, C) fp32 -> (C, tokens) fp32 per image: the reference's NCHW `image_embeddings` layout.
 void tokens_to_nchw(cudaStream_t s, float const* in, int batch, int tokens, int C, float* out);
 
 // bf16 -> fp32 copy (debug taps).
-void bf16_to_f32(cudaStream_t s, bf16 const* in, int64_t n, float* out);
+void act_to_f32(cudaStream_t s, act_t const* in, int64_t n, float* out);
 
 }  // namespace enc
 }  // namespace dlimg

@@ -1,6 +1,8 @@
 // gemm.cu -- tcgen05 / TMEM / TMA GEMM for sm_100a (see gemm.cuh for the contract).
 #include "gemm.cuh"
 
+#include "../profiler.hpp"
+
 #include <cuda_runtime.h>
 
 #include <mutex>
@@ -135,16 +137,16 @@ __device__ __forceinline__ void epilogue_store16(uint32_t const (&r)[16], EpiPar
 #pragma unroll
         for (int i = 0; i < 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     } else {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + orow * ep.ldc + col;
+        act_t* o = reinterpret_cast<act_t*>(out) + orow * ep.ldc + col;
         if (ep.residual) {
-            uint4 const* r4 = reinterpret_cast<uint4 const*>(reinterpret_cast<__nv_bfloat16 const*>(ep.residual) + orow * ep.ldc + col);
+            uint4 const* r4 = reinterpret_cast<uint4 const*>(reinterpret_cast<act_t const*>(ep.residual) + orow * ep.ldc + col);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 uint4 x = r4[i];
-                __nv_bfloat162 const* h = reinterpret_cast<__nv_bfloat162 const*>(&x);
+                act2_t const* h = reinterpret_cast<act2_t const*>(&x);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float2 f = __bfloat1622float2(h[j]);
+                    float2 f = act22f2(h[j]);
                     v[8 * i + 2 * j] += f.x;
                     v[8 * i + 2 * j + 1] += f.y;
                 }
@@ -161,9 +163,9 @@ __device__ __forceinline__ void epilogue_store16(uint32_t const (&r)[16], EpiPar
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             uint4 x;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&x);
+            act2_t* h = reinterpret_cast<act2_t*>(&x);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+            for (int j = 0; j < 4; ++j) h[j] = f22act2(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
             o4[i] = x;
         }
     }
@@ -241,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             // instruction descriptor: D fp32, A/B bf16 or tf32, both K-major, N = block_n, M = 128
-            uint32_t const fmt = kTF32 ? 2u : 1u;
+            uint32_t const fmt = kTF32 ? 2u : (kActBf16 ? 1u : 0u);  // UMMA F16F32Format: F16 = 0, BF16 = 1, TF32 = 2
             uint32_t const idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) |
                                    ((uint32_t)(kBlockM >> 4) << 24);
             int stage = 0;
@@ -311,7 +313,7 @@ __device__ __forceinline__ float to_f32(T v);
 template <>
 __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
-__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32<act_t>(act_t v) { return act2f(v); }
 
 template <typename T>
 __global__ void gemm_simt_kernel(T const* __restrict__ A, int64_t lda, T const* __restrict__ B, int64_t ldb, int M, int N,
@@ -350,11 +352,11 @@ __global__ void gemm_simt_kernel(T const* __restrict__ A, int64_t lda, T const* 
         int64_t const o = orow * ep.ldc + n;
         if (ep.residual)
             v += ep.out_f32 ? reinterpret_cast<float const*>(ep.residual)[o]
-                            : __bfloat162float(reinterpret_cast<__nv_bfloat16 const*>(ep.residual)[o]);
+                            : act2f(reinterpret_cast<act_t const*>(ep.residual)[o]);
         if (ep.act == ACT_GELU) v = gelu_erf(v);
         else if (ep.act == ACT_RELU) v = fmaxf(v, 0.f);
         if (ep.out_f32) reinterpret_cast<float*>(out)[o] = v;
-        else reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(v);
+        else reinterpret_cast<act_t*>(out)[o] = f2act(v);
     }
 }
 
@@ -386,7 +388,9 @@ CUtensorMap make_map(Operand const& op, bool tf32, int box_rows) {
     cuuint64_t strides[1] = {(cuuint64_t)(pitch * esz)};
     cuuint32_t box[2] = {(cuuint32_t)(kKBytes / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode_fn()(&map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+    CUtensorMapDataType const dtype = tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                                           : (kActBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    CUresult r = encode_fn()(&map, dtype, 2,
                              const_cast<void*>(op.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -425,6 +429,8 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
     CUtensorMap ma = make_map(a, tf32, kBlockM);
     CUtensorMap mb = make_map(b, tf32, block_n);
     int const tiles = ceil_div(M, kBlockM) * (N / block_n);
+    ProfScope prof(stream, tf32 ? CAT_GEMM_TF32 : CAT_GEMM_BF16, 2.0 * M * N * K,
+                   (double)(tf32 ? 4 : 2) * ((double)M * K + (double)N * K) + (double)(ep.out_f32 ? 4 : 2) * M * N);
     int const grid = tiles < num_sms ? tiles : num_sms;
     static std::once_flag once;
     std::call_once(once, [] {
@@ -441,13 +447,14 @@ void launch_simt(cudaStream_t stream, bool f32_operands, Operand const& a, Opera
     int const M = (int)a.rows, N = (int)b.rows, K = (int)a.cols;
     DLIMG_ASSERT(a.cols == b.cols);
     EpiParams ep = to_params(epi, N);
+    ProfScope prof(stream, CAT_OTHER, 2.0 * M * N * K);
     dim3 grid(ceil_div(N, 32), ceil_div(M, 32)), block(32, 8);
     int64_t const lda = a.pitch ? a.pitch : a.cols, ldb = b.pitch ? b.pitch : b.cols;
     if (f32_operands)
         gemm_simt_kernel<float><<<grid, block, 0, stream>>>((float const*)a.ptr, lda, (float const*)b.ptr, ldb, M, N, K, out, ep);
     else
-        gemm_simt_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((__nv_bfloat16 const*)a.ptr, lda,
-                                                                     (__nv_bfloat16 const*)b.ptr, ldb, M, N, K, out, ep);
+        gemm_simt_kernel<act_t><<<grid, block, 0, stream>>>((act_t const*)a.ptr, lda,
+                                                                     (act_t const*)b.ptr, ldb, M, N, K, out, ep);
     KERNEL_CHECK();
 }
 

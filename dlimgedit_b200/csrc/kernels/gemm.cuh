@@ -14,7 +14,7 @@
 #include "../common.hpp"
 
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include "../act.hpp"
 
 namespace dlimg {
 namespace gemm {

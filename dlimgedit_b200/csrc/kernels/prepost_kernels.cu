@@ -1,6 +1,8 @@
 // prepost_kernels.cu -- see prepost_kernels.cuh.
 #include "prepost_kernels.cuh"
 
+#include "../profiler.hpp"
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -312,6 +314,7 @@ void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride
     DLIMG_ASSERT(h <= 65535);
     // torch: scale = float(input_size) / output_size
     float const sx = (float)rw / (float)w, sy = (float)rh / (float)h;
+    ProfScope prof(s, CAT_MASK_POST, 0, (double)count * (65536.0 * 4 + (double)w * h));
     dim3 block(256), grid(ceil_div(ceil_div(w, 4), 256), h, count);
     mask_post_kernel<<<grid, block, 0, s>>>(low_res, plane_stride, plane_index, rw, rh, w, h, sx, sy, out_planes, out_contig);
     KERNEL_CHECK();
@@ -322,6 +325,7 @@ void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride
 void resize_srgb(cudaStream_t s, uint8_t const* in, int in_w, int in_h, int stride, int bpp, ResizeDeviceTables const& t,
                  float* scratch, uint8_t* out, int out_w, int out_h) {
     int64_t const n1 = (int64_t)in_h * out_w * bpp;
+    ProfScope prof(s, CAT_RESIZE, 0, (double)in_h * stride + (double)out_h * out_w * bpp);
     resize_h_kernel<<<(unsigned)ceil_div64(n1, 256), 256, 0, s>>>(in, in_w, in_h, stride, bpp, out_w, t.decode, t.hfirst,
                                                                  t.hweights, t.htaps, scratch);
     KERNEL_CHECK();
@@ -335,6 +339,7 @@ void image_tensor(cudaStream_t s, uint8_t const* in, int w, int h, int stride, i
     int cmap[3];
     channel_map(channels, cmap);
     int64_t const n = (int64_t)w * h;
+    ProfScope prof(s, CAT_IMAGE_TENSOR, 0, (double)h * stride + (double)n * 12);
     image_tensor_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(in, w, h, stride, bytes_per_pixel(channels), cmap[0],
                                                                     cmap[1], cmap[2], out);
     KERNEL_CHECK();
@@ -352,6 +357,7 @@ void mask_postprocess_contiguous(cudaStream_t s, float const* low_res, int64_t p
 
 void threshold_mask(cudaStream_t s, float const* logits, int th, int tw, int w, int h, uint8_t* out) {
     DLIMG_ASSERT(w <= tw && h <= th);
+    ProfScope prof(s, CAT_MASK_POST, 0, (double)w * h * 5);
     int64_t const n = (int64_t)w * h;
     threshold_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(logits, tw, w, h, out);
     KERNEL_CHECK();

@@ -21,9 +21,9 @@ constexpr int kWindows[4] = {7, 7, 14, 7};
 constexpr int kRes[4] = {256, 128, 64, 64};
 constexpr float kBnEps = 1e-5f;
 
-std::vector<bf16> to_bf16(std::vector<float> const& v) {
-    std::vector<bf16> o(v.size());
-    for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+std::vector<act_t> to_act(std::vector<float> const& v) {
+    std::vector<act_t> o(v.size());
+    for (size_t i = 0; i < v.size(); ++i) o[i] = f2act(v[i]);
     return o;
 }
 
@@ -55,7 +55,7 @@ Linear16 load_conv_bn(WeightFile const& wf, std::string const& p, int cout, int 
     Linear16 l;
     l.n = cout;
     l.k = K;
-    l.w.upload(to_bf16(o));
+    l.w.upload(to_act(o));
     l.b.upload(shift);
     return l;
 }
@@ -78,7 +78,7 @@ Linear16 load_linear16(WeightFile const& wf, std::string const& p, int n, int k,
     Linear16 l;
     l.n = n;
     l.k = k;
-    l.w.upload(to_bf16(wf.get(p + ".weight", {n, k}).data));
+    l.w.upload(to_act(wf.get(p + ".weight", {n, k}).data));
     if (bias) l.b.upload(wf.get(p + ".bias", {n}).data);
     return l;
 }
@@ -129,10 +129,10 @@ std::vector<float> dense_attention_bias(HostTensor const& biases, int heads, int
     return dense;
 }
 
-void tap_bf16(cudaStream_t s, Tap* tap, char const* name, bf16 const* p, size_t n) {
+void tap_act(cudaStream_t s, Tap* tap, char const* name, act_t const* p, size_t n) {
     if (!tap || !tap->name || std::strcmp(tap->name, name) != 0) return;
     if (n > tap->capacity) fail(std::string("tap buffer too small for ") + name);
-    enc::bf16_to_f32(s, p, (int64_t)n, tap->out);
+    enc::act_to_f32(s, p, (int64_t)n, tap->out);
     tap->written = n;
 }
 
@@ -196,7 +196,7 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
         auto const& w1 = wf.get(E + "neck.0.weight", {256, 320, 1, 1});
         enc_.neck1.n = 256;
         enc_.neck1.k = 320;
-        enc_.neck1.w.upload(to_bf16(w1.data));
+        enc_.neck1.w.upload(to_act(w1.data));
         enc_.neck_ln1 = load_norm(wf, E + "neck.1", 256);
         auto const& w2 = wf.get(E + "neck.2.weight", {256, 256, 3, 3});
         std::vector<float> o((size_t)256 * 2304);
@@ -205,7 +205,7 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
                 for (int t = 0; t < 9; ++t) o[(size_t)oc * 2304 + (size_t)t * 256 + ci] = w2.data[((size_t)oc * 256 + ci) * 9 + t];
         enc_.neck2.n = 256;
         enc_.neck2.k = 2304;
-        enc_.neck2.w.upload(to_bf16(o));
+        enc_.neck2.w.upload(to_act(o));
         enc_.neck_ln2 = load_norm(wf, E + "neck.3", 256);
     }
 
@@ -329,8 +329,8 @@ DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
 }
 
 // ---------------------------------------------------------------------------------------------
-void SamModel::gemm16(cudaStream_t s, bf16 const* a, int64_t rows, Linear16 const& l, void* out, int act,
-                      bf16 const* residual, int const* row_map, bool out_f32) const {
+void SamModel::gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 const& l, void* out, int act,
+                      act_t const* residual, int const* row_map, bool out_f32) const {
     gemm::Operand A{a, rows, l.k, l.k};
     gemm::Operand B{l.w.get(), l.n, l.k, l.k};
     gemm::Epilogue e;
@@ -363,12 +363,12 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
 
     // PatchEmbed: fused preprocess + conv1 + GELU, then conv2 as im2col + GEMM
     enc::conv1_preprocess(s, images, batch, w, h, channels, enc_.conv1_w.get(), enc_.conv1_b.get(), ws.c1.get());
-    tap_bf16(s, tap, "conv1", ws.c1.get(), (size_t)B * 512 * 512 * 32);
+    tap_act(s, tap, "conv1", ws.c1.get(), (size_t)B * 512 * 512 * 32);
     enc::im2col3x3(s, ws.c1.get(), batch, 512, 512, 32, 2, ws.col.get());
-    bf16* x = ws.xa.get();
-    bf16* y = ws.xb.get();
+    act_t* x = ws.xa.get();
+    act_t* y = ws.xb.get();
     gemm16(s, ws.col.get(), B * 65536, enc_.conv2, x, ACT_NONE, nullptr, nullptr);
-    tap_bf16(s, tap, "patch_embed", x, (size_t)B * 65536 * 64);
+    tap_act(s, tap, "patch_embed", x, (size_t)B * 65536 * 64);
 
     // layer 0: MBConv x2 (1x1 expand + GELU, dw3x3 + GELU, 1x1 project + shortcut + GELU)
     for (int i = 0; i < 2; ++i) {
@@ -377,7 +377,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         enc::dwconv3x3(s, ws.big[0].get(), batch, 256, 256, 256, 1, m.conv2.w.get(), m.conv2.b.get(), true, ws.big[1].get());
         gemm16(s, ws.big[1].get(), B * 65536, m.conv3, y, ACT_GELU, x, nullptr);
         std::swap(x, y);
-        tap_bf16(s, tap, i == 0 ? "mb0" : "mb1", x, (size_t)B * 65536 * 64);
+        tap_act(s, tap, i == 0 ? "mb0" : "mb1", x, (size_t)B * 65536 * 64);
     }
 
     auto merge = [&](MergeW const& m, int res, char const* name) {
@@ -388,7 +388,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
                        ws.big[1].get());
         gemm16(s, ws.big[1].get(), B * out_res * out_res, m.conv3, y, ACT_NONE, nullptr, nullptr);
         std::swap(x, y);
-        tap_bf16(s, tap, name, x, (size_t)B * out_res * out_res * dout);
+        tap_act(s, tap, name, x, (size_t)B * out_res * out_res * dout);
     };
     merge(enc_.merge[0], 256, "layer0");
 
@@ -403,32 +403,32 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
             std::string const tn = "s" + std::to_string(st) + "b" + std::to_string(i);
             // attention branch: pad + partition + LN (gather), QKV, windowed attention, proj + un-partition + residual
             enc::layernorm_rows(s, x, (int)wrows, C, map, b.attn_norm.g.get(), b.attn_norm.b.get(), 1e-5f, ws.big[0].get(), false);
-            tap_bf16(s, tap, (tn + ".ln").c_str(), ws.big[0].get(), (size_t)wrows * C);
+            tap_act(s, tap, (tn + ".ln").c_str(), ws.big[0].get(), (size_t)wrows * C);
             gemm16(s, ws.big[0].get(), wrows, b.qkv, ws.big[1].get(), ACT_NONE, nullptr, nullptr);
-            tap_bf16(s, tap, (tn + ".qkv").c_str(), ws.big[1].get(), (size_t)wrows * 3 * C);
+            tap_act(s, tap, (tn + ".qkv").c_str(), ws.big[1].get(), (size_t)wrows * 3 * C);
             enc::window_attention(s, ws.big[1].get(), windows, n, c.heads, b.attn_bias.get(), ws.big[2].get());
-            tap_bf16(s, tap, (tn + ".att").c_str(), ws.big[2].get(), (size_t)wrows * C);
+            tap_act(s, tap, (tn + ".att").c_str(), ws.big[2].get(), (size_t)wrows * C);
             gemm16(s, ws.big[2].get(), wrows, b.proj, x, ACT_NONE, x, map);
-            tap_bf16(s, tap, (tn + ".proj").c_str(), x, (size_t)B * L * C);
+            tap_act(s, tap, (tn + ".proj").c_str(), x, (size_t)B * L * C);
             // local depthwise conv (no activation, no residual)
             enc::dwconv3x3(s, x, batch, c.res, c.res, C, 1, b.local_conv.w.get(), b.local_conv.b.get(), false, y);
-            tap_bf16(s, tap, (tn + ".lc").c_str(), y, (size_t)B * L * C);
+            tap_act(s, tap, (tn + ".lc").c_str(), y, (size_t)B * L * C);
             // MLP branch
             enc::layernorm_rows(s, y, (int)(B * L), C, nullptr, b.mlp_norm.g.get(), b.mlp_norm.b.get(), 1e-5f, ws.big[0].get(), false);
             gemm16(s, ws.big[0].get(), B * L, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, nullptr);
             gemm16(s, ws.big[1].get(), B * L, b.fc2, y, ACT_NONE, y, nullptr);
             std::swap(x, y);
-            tap_bf16(s, tap, tn.c_str(), x, (size_t)B * L * C);
+            tap_act(s, tap, tn.c_str(), x, (size_t)B * L * C);
         }
         if (st < 3) merge(enc_.merge[st], c.res, st == 1 ? "layer1" : "layer2");
     }
-    tap_bf16(s, tap, "layer3", x, (size_t)B * 4096 * 320);
+    tap_act(s, tap, "layer3", x, (size_t)B * 4096 * 320);
 
     // neck: 1x1 conv -> LayerNorm2d -> 3x3 conv -> LayerNorm2d (token-major, so LayerNorm2d is a row LayerNorm)
     gemm16(s, x, B * 4096, enc_.neck1, ws.big[0].get(), ACT_NONE, nullptr, nullptr);
     enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln1.g.get(), enc_.neck_ln1.b.get(), 1e-6f,
                         ws.big[1].get(), false);
-    tap_bf16(s, tap, "neck1", ws.big[1].get(), (size_t)B * 4096 * 256);
+    tap_act(s, tap, "neck1", ws.big[1].get(), (size_t)B * 4096 * 256);
     enc::im2col3x3(s, ws.big[1].get(), batch, 64, 64, 256, 1, ws.col.get());
     gemm16(s, ws.col.get(), B * 4096, enc_.neck2, ws.big[0].get(), ACT_NONE, nullptr, nullptr);
     enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f,

@@ -8,14 +8,13 @@
 #include "kernels/encoder_kernels.cuh"
 #include "weights.hpp"
 
-#include <cuda_bf16.h>
+#include "act.hpp"
 
 #include <string>
 #include <vector>
 
 namespace dlimg {
 
-using bf16 = __nv_bfloat16;
 
 template <typename T> class DeviceBuffer {
   public:
@@ -54,8 +53,8 @@ template <typename T> class DeviceBuffer {
 };
 
 // ---- weights ----------------------------------------------------------------------------------
-struct Linear16 {  // bf16 weight (N, K) row-major + fp32 bias (N) -- encoder GEMM operand B
-    DeviceBuffer<bf16> w;
+struct Linear16 {  // act_t weight (N, K) row-major + fp32 bias (N) -- encoder GEMM operand B
+    DeviceBuffer<act_t> w;
     DeviceBuffer<float> b;
     int n = 0, k = 0;
 };
@@ -118,7 +117,7 @@ struct DecoderW {
 // ---- workspaces -------------------------------------------------------------------------------
 struct EncoderWorkspace {
     int max_batch = 0;
-    DeviceBuffer<bf16> c1, col, xa, xb, big[4];
+    DeviceBuffer<act_t> c1, col, xa, xb, big[4];
     DeviceBuffer<int> row_map[3];  // stage 1..3: windowed row -> token row (-1 = padding), for max_batch images
     int win_rows[3] = {0, 0, 0};   // windowed rows per image
     explicit EncoderWorkspace(int max_batch);
@@ -173,7 +172,7 @@ class SamModel {
     static StageCfg stage(int i);  // i = 1..3
 
   private:
-    void gemm16(cudaStream_t s, bf16 const* a, int64_t rows, Linear16 const& l, void* out, int act, bf16 const* residual,
+    void gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 const& l, void* out, int act, act_t const* residual,
                 int const* row_map, bool out_f32 = false) const;
     void gemm32(cudaStream_t s, float const* a, int64_t rows, Linear32 const& l, float* out, int act) const;
     void lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, int rows, Linear32 const& l, bool relu, float* y,

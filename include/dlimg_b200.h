@@ -108,6 +108,15 @@ typedef struct dlimg_b200_Prompt {
     int x0, y0, x1, y1;
 } dlimg_b200_Prompt;
 
+/* One row of the optional per-kernel profile (see profile_enable / profile_read). */
+typedef struct dlimg_b200_ProfileEntry {
+    char name[32];     /* kernel category, e.g. "gemm_tcgen05_f16" */
+    uint64_t launches;
+    double ms;         /* summed CUDA-event time of those launches */
+    double flops;      /* algorithmic floating point operations (2*M*N*K for GEMMs), 0 if not tracked */
+    double bytes;      /* algorithmic bytes moved, 0 if not tracked */
+} dlimg_b200_ProfileEntry;
+
 typedef struct dlimg_b200_Stats {
     uint64_t kernel_launches; /* kernels of THIS library launched since the environment was created */
     uint64_t h2d_bytes;
@@ -163,6 +172,12 @@ struct dlimg_b200_Ext {
                                      uint8_t* dev_out);
     dlimg_Result (*threshold_mask)(dlimg_Environment, float const* dev_logits, int th, int tw, int w, int h,
                                    uint8_t* dev_out);
+
+    /* Per-kernel timing with CUDA events on the launching stream (adds two event records per launch, so
+     * switch it on only for an attribution pass).  profile_read waits for the recorded events, writes up to
+     * `capacity` non-empty categories, clears the recording and returns the number written through *count. */
+    dlimg_Result (*profile_enable)(dlimg_Environment, int on);
+    dlimg_Result (*profile_read)(dlimg_Environment, dlimg_b200_ProfileEntry* out, int capacity, int* count);
 };
 
 DLIMG_B200_EXPORT struct dlimg_b200_Ext const* dlimg_b200_ext_init(void);

@@ -12,6 +12,7 @@ extern "C" {
 
 typedef struct dlimg_b200_Debug {
     uint32_t struct_size;
+    uint32_t act_is_bf16; /* storage type of encoder activations / 16-bit GEMM operands: 0 = fp16, 1 = bf16 */
     /* C = epilogue(A[M,K] * B[N,K]^T).  Device pointers; elements are bf16 (tf32 == 0) or fp32 (tf32 != 0).
      * simt != 0 runs the CUDA-core cross-check kernel instead of the tcgen05 kernel.  act: 0 none, 1 GELU(erf),
      * 2 ReLU.  row_map (optional): output row per input row, -1 drops the row. */

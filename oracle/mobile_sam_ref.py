@@ -511,62 +511,34 @@ class SamOnnxDecoder(nn.Module):
 
 
 # --------------------------------------------------------------------------------------------
-# Deterministic synthetic weights (no checkpoint exists offline)
+# Weights: the oracle loads the SAME tensors the engine loads (state-dict names of SURVEY A.7)
 # --------------------------------------------------------------------------------------------
-def init_synthetic(sam: MobileSam, seed: int = 0) -> MobileSam:
-    """Seeded weights calibrated so activations stay O(1) through the network and the mask logits
-    are not degenerate.  Every parameter/buffer of the real checkpoint gets a non-trivial value
-    (BN running stats, LN affine, attention biases ...) so that a parity failure in any of them
-    is visible."""
-    g = torch.Generator().manual_seed(seed)
-
-    def rn(*shape, std=1.0):
-        return torch.randn(*shape, generator=g) * std
-
-    def ru(*shape, lo=0.0, hi=1.0):
-        return torch.rand(*shape, generator=g) * (hi - lo) + lo
-
+def load_numpy_state(sam: MobileSam, tensors) -> MobileSam:
+    """tensors: {state-dict name: float32 ndarray} (dlimgedit_b200.weights_io container contents).  Strict:
+    every floating-point entry of the model's state dict must be present with the right shape."""
+    sd = sam.state_dict()
     with torch.no_grad():
-        for name, m in sam.named_modules():
-            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
-                if isinstance(m, nn.ConvTranspose2d):
-                    fan_in = m.in_channels
-                else:
-                    fan_in = m.in_channels // m.groups * m.kernel_size[0] * m.kernel_size[1]
-                m.weight.copy_(rn(*m.weight.shape, std=1.0 / math.sqrt(fan_in)))
-                if m.bias is not None:
-                    m.bias.copy_(rn(*m.bias.shape, std=0.05))
-            elif isinstance(m, nn.Linear):
-                m.weight.copy_(rn(*m.weight.shape, std=1.0 / math.sqrt(m.in_features)))
-                m.bias.copy_(rn(*m.bias.shape, std=0.05))
-            elif isinstance(m, nn.BatchNorm2d):
-                m.weight.copy_(ru(*m.weight.shape, lo=0.7, hi=1.3))
-                m.bias.copy_(rn(*m.bias.shape, std=0.1))
-                m.running_mean.copy_(rn(*m.running_mean.shape, std=0.1))
-                m.running_var.copy_(ru(*m.running_var.shape, lo=0.6, hi=1.4))
-            elif isinstance(m, (nn.LayerNorm, LayerNorm2d)):
-                m.weight.copy_(ru(*m.weight.shape, lo=0.7, hi=1.3))
-                m.bias.copy_(rn(*m.bias.shape, std=0.1))
-            elif isinstance(m, nn.Embedding):
-                m.weight.copy_(rn(*m.weight.shape, std=0.5))
-            elif isinstance(m, WindowAttention):
-                m.attention_biases.copy_(rn(*m.attention_biases.shape, std=0.5))
-            elif isinstance(m, PositionEmbeddingRandom):
-                m.positional_encoding_gaussian_matrix.copy_(rn(2, 128, std=1.0))
-        # residual branches: damp the last conv/linear of each block so depth does not blow up the variance
-        for blk in sam.image_encoder.layers[0].blocks:
-            blk.conv3.bn.weight.mul_(0.5)
-        for layer in list(sam.image_encoder.layers)[1:]:
-            for blk in layer.blocks:
-                blk.attn.proj.weight.mul_(0.5)
-                blk.mlp.fc2.weight.mul_(0.5)
+        for k, v in sd.items():
+            if not v.dtype.is_floating_point:
+                continue  # BatchNorm num_batches_tracked
+            if k not in tensors:
+                raise KeyError(f"weight container lacks {k}")
+            t = torch.from_numpy(tensors[k])
+            if tuple(t.shape) != tuple(v.shape):
+                raise ValueError(f"{k}: container shape {tuple(t.shape)} != model shape {tuple(v.shape)}")
+            v.copy_(t)
+    extra = set(tensors) - set(sd)
+    if extra:
+        raise KeyError(f"weight container has unknown tensors: {sorted(extra)[:5]}")
     sam.eval()
     return sam
 
 
 def build_synthetic(seed: int = 0) -> MobileSam:
-    torch.manual_seed(seed)
-    return init_synthetic(MobileSam(), seed)
+    """Oracle model carrying the seeded synthetic weights of dlimgedit_b200.synthetic_weights (no checkpoint
+    exists offline)."""
+    from dlimgedit_b200 import synthetic_weights
+    return load_numpy_state(MobileSam(), synthetic_weights.make_state_dict(seed))
 
 
 def count_learnable(m: nn.Module) -> int:

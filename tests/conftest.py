@@ -40,12 +40,11 @@ def oracle_sam():
 
 
 @pytest.fixture(scope="session")
-def model_dir(tmp_path_factory, oracle_sam):
-    """<dir>/segmentation/mobile_sam_b200.bin holding the oracle's synthetic weights."""
-    from dlimgedit_b200 import weights_io
+def model_dir(tmp_path_factory):
+    """<dir>/segmentation/mobile_sam_b200.bin holding the seeded synthetic weights (the oracle loads the same)."""
+    from dlimgedit_b200 import synthetic_weights
     d = tmp_path_factory.mktemp("models")
-    os.makedirs(d / "segmentation")
-    weights_io.save(str(d / "segmentation" / weights_io.WEIGHT_FILE_NAME), weights_io.from_state_dict(oracle_sam.state_dict()))
+    synthetic_weights.write_model_dir(str(d), seed=0)
     return str(d)
 
 

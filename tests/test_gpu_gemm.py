@@ -1,0 +1,106 @@
+"""tcgen05 GEMM (dlimgedit_b200/csrc/kernels/gemm.cu) against a plain PyTorch fp32 reference of the same op.
+
+Tolerances: operands are bf16 (or tf32) with fp32 accumulation, so the reference is computed in fp32 from the
+same rounded operands; the 16-bit output adds one rounding (rel 2^-11 fp16 / 2^-8 bf16)."""
+import pytest
+import torch
+
+from gpu_util import act_dtype, gemm
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, bias, residual, act):
+    y = a.float() @ b.float().t()
+    if bias is not None:
+        y = y + bias
+    if residual is not None:
+        y = y + residual.float()
+    if act == 1:
+        y = torch.nn.functional.gelu(y)
+    elif act == 2:
+        y = torch.relu(y)
+    return y
+
+
+SHAPES = [  # (M, N, K): the encoder's real shapes incl. K tails (160, 288, 320) and M tails
+    (256, 64, 64), (1000, 256, 64), (4096, 64, 256), (777, 128, 64), (513, 160, 128), (4900, 480, 160),
+    (4096, 160, 640), (640, 64, 288), (4900, 960, 320), (4096, 1280, 320), (4096, 320, 1280), (4096, 256, 2304),
+    (17689, 384, 128), (100, 512, 128), (300, 16, 64),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_f16_gemm_plain(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(act_dtype())
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(act_dtype())
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = _ref(a, b, bias, None, 0)
+    out = gemm(a, b, bias=bias, out_f32=True)
+    assert torch.allclose(out, ref, atol=2e-3, rtol=2e-3), float((out - ref).abs().max())
+    out16 = gemm(a, b, bias=bias)
+    assert torch.allclose(out16.float(), ref, atol=2e-2, rtol=1e-2)
+    simt = gemm(a, b, bias=bias, out_f32=True, simt=True)
+    assert torch.allclose(simt, ref, atol=2e-3, rtol=2e-3)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_f16_gemm_epilogues(act):
+    g = torch.Generator(device="cuda").manual_seed(act)
+    M, N, K = 1234, 320, 160
+    a = torch.randn(M, K, device="cuda", generator=g).to(act_dtype())
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(act_dtype())
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).to(act_dtype())
+    ref = _ref(a, b, bias, res, act)
+    out = gemm(a, b, bias=bias, residual=res, act=act)
+    assert torch.allclose(out.float(), ref, atol=3e-2, rtol=1e-2), float((out.float() - ref).abs().max())
+    # no bias
+    out = gemm(a, b, act=act, out_f32=True)
+    assert torch.allclose(out, _ref(a, b, None, None, act), atol=2e-3, rtol=2e-3)
+
+
+def test_f16_gemm_row_scatter_in_place_residual():
+    """proj epilogue of a TinyViT block: windowed rows scatter to token rows, residual read in place, padding dropped."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K, rows = 900, 128, 128, 700
+    a = torch.randn(M, K, device="cuda", generator=g).to(act_dtype())
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(act_dtype())
+    bias = torch.randn(N, device="cuda", generator=g)
+    perm = torch.randperm(M, device="cuda", generator=g)
+    row_map = torch.full((M,), -1, device="cuda", dtype=torch.int32)
+    row_map[perm[:rows]] = torch.arange(rows, device="cuda", dtype=torch.int32)
+    x = torch.randn(rows, N, device="cuda", generator=g).to(act_dtype())
+    ref = x.float().clone()
+    full = _ref(a, b, bias, None, 0)
+    ref[row_map[perm[:rows]].long()] += full[perm[:rows]]
+    out = x.clone()
+    gemm(a, b, bias=bias, residual=out, row_map=row_map, out=out)
+    assert torch.allclose(out.float(), ref, atol=3e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 128, 256), (4096, 256, 128), (16384, 128, 64), (8192, 256, 256), (333, 128, 256)])
+def test_tf32_gemm(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.double() @ b.double().t() + bias.double()
+    out = gemm(a, b, bias=bias, out_f32=True)
+    # tf32 operands: 10-bit mantissa -> relative 2^-11 per product, accumulated in fp32
+    err = float((out.double() - ref).abs().max())
+    assert err < 5e-3, err
+    out_g = gemm(a, b, bias=bias, act=1, out_f32=True)
+    assert torch.allclose(out_g.double(), torch.nn.functional.gelu(ref), atol=5e-3)
+    simt = gemm(a, b, bias=bias, out_f32=True, simt=True)
+    assert torch.allclose(simt.double(), ref, atol=1e-4, rtol=1e-4)
+
+
+def test_gemm_back_to_back_is_deterministic():
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(65536, 64, device="cuda", generator=g).to(act_dtype())
+    b = torch.randn(256, 64, device="cuda", generator=g).to(act_dtype())
+    o1 = gemm(a, b)
+    o2 = gemm(a, b)
+    assert torch.equal(o1, o2)
