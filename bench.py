@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--prompts", type=int, default=64, help="prompts per decoder step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=6, help="images timed for the cpu_baseline")
+    ap.add_argument("--quick", action="store_true", help="device-resident legs only (used for the ncu launch list)")
     return ap.parse_args()
 
 
@@ -171,7 +172,11 @@ def run_ours(args):
     model_dir = tempfile.mkdtemp(prefix=f"dlimg_models_r{rank}_")
     synthetic_weights.write_model_dir(model_dir, seed=0)
     env = dl.Environment(dl.Options(dl.Backend.gpu, model_dir))
-    stream = torch.cuda.current_stream()
+    # All library work and the timing events share one explicit (non-default) stream: the legacy default
+    # stream has handle 0, which the C ABI reads as "use the environment's own stream".
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     env.set_stream(stream.cuda_stream)
 
     B, K, W = args.batch, args.steps, args.warmup
@@ -231,18 +236,24 @@ def run_ours(args):
     value = world * B * K / (ms * 1e-3)
 
     # ---------------- encoder end to end: pinned host pixels in, embeddings out ----------------
+    emb_host = torch.empty(B, 256, 64, 64, dtype=torch.float32).pin_memory()
+
     def step_e2e(i):
         segs = env.process_batch(host_views(i % n_sets))
-        for s in segs:
-            s.embedding()  # D2H of the (1,256,64,64) fp32 embedding, the reference keeps it in host memory
+        for j, s in enumerate(segs):
+            # D2H of the (1,256,64,64) fp32 embedding: the reference keeps it in host memory (segmentation.cpp:124)
+            s.embedding(out=emb_host[j].numpy())
         keep.append(segs)
 
-    for i in range(min(W, 2)):
-        step_e2e(i)
-    keep.clear()
     k_e2e = max(3, K // 2)
-    ms_e2e = timed(step_e2e, k_e2e)
-    keep.clear()
+    if args.quick:
+        ms_e2e = float("nan")
+    else:
+        for i in range(min(W, 2)):
+            step_e2e(i)
+        keep.clear()
+        ms_e2e = timed(step_e2e, k_e2e)
+        keep.clear()
     e2e_value = world * B * k_e2e / (ms_e2e * 1e-3)
 
     # ---------------- decoder: P point prompts on one cached embedding (config 3) ----------------
@@ -266,24 +277,29 @@ def run_ours(args):
     def step_dec_e2e(i):
         env.compute_masks_batch([seg] * P, prompts, multi=False)  # host masks + IoUs, D2H inside
 
-    step_dec_e2e(0)
-    ms_dec_e2e = timed(step_dec_e2e, 3)
+    if args.quick:
+        ms_dec_e2e = float("nan")
+    else:
+        step_dec_e2e(0)
+        ms_dec_e2e = timed(step_dec_e2e, 3)
     masks_per_s_e2e = world * P * 3 / (ms_dec_e2e * 1e-3)
 
     # ---------------- attribution pass: CUDA events around every kernel launch ----------------
     peaks = load_peaks()
-    env.profile_enable(True)
     prof_steps = 2
-    for i in range(prof_steps):
-        step_dev(i)
-    torch.cuda.synchronize()
-    prof = env.profile_read()
-    keep.clear()
-    for i in range(2):
-        step_dec(i)
-    torch.cuda.synchronize()
-    prof_dec = env.profile_read()
-    env.profile_enable(False)
+    prof, prof_dec = {}, {}
+    if not args.quick:
+        env.profile_enable(True)
+        for i in range(prof_steps):
+            step_dev(i)
+        torch.cuda.synchronize()
+        prof = env.profile_read()
+        keep.clear()
+        for i in range(2):
+            step_dec(i)
+        torch.cuda.synchronize()
+        prof_dec = env.profile_read()
+        env.profile_enable(False)
 
     total_ms = sum(v["ms"] for v in prof.values()) or 1.0
     kernels = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] // prof_steps,
@@ -307,7 +323,7 @@ def run_ours(args):
 
     # ---------------- CPU baseline (rank 0, N == 1 only) ----------------
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.quick:
         threads = os.cpu_count() or 1
         v = oracle_encoder_images_per_s(args.cpu_sample, threads)
         cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",

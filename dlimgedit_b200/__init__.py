@@ -149,6 +149,8 @@ class _Debug(ctypes.Structure):
                           ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t))),
         ("resize_plan", _F(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i32p, c_f32p)),
         ("srgb_tables", _F(None, c_f32p, c_f32p)),
+        ("window_attention", _F(_R, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                ctypes.c_void_p, ctypes.c_void_p)),
     ]
 
 
@@ -378,8 +380,11 @@ class Segmentation:
         return list(zip(masks, ious))
 
     # -- additive extension -----------------------------------------------------------------------
-    def embedding(self) -> np.ndarray:
-        out = np.empty((1, 256, 64, 64), np.float32)
+    def embedding(self, out: np.ndarray = None) -> np.ndarray:
+        """(1, 256, 64, 64) float32, NCHW like the reference's `image_embeddings`; `out` may be a pinned buffer."""
+        if out is None:
+            out = np.empty((1, 256, 64, 64), np.float32)
+        assert out.dtype == np.float32 and out.size == 256 * 64 * 64 and out.flags["C_CONTIGUOUS"]
         _check(ext().get_embedding(self._h, out.ctypes.data_as(c_f32p)))
         return out
 

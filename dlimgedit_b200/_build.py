@@ -25,7 +25,9 @@ SOURCES = [
     "profiler.cpp",
     "kernels/gemm.cu",
     "kernels/encoder_kernels.cu",
+    "kernels/window_attention.cu",
     "kernels/decoder_kernels.cu",
+    "kernels/t2i_attention.cu",
     "kernels/prepost_kernels.cu",
 ]
 

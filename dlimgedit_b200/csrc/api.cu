@@ -242,6 +242,15 @@ void dbg_srgb_tables(float* decode256, float* threshold256) {
     std::memcpy(threshold256, t.encode_threshold, sizeof(t.encode_threshold));
 }
 
+dlimg_Result dbg_window_attention(void* stream, int simt, void const* qkv, int windows, int n, int heads, float const* bias,
+                                  void* out) {
+    return try_([=] {
+        auto s = static_cast<cudaStream_t>(stream);
+        if (simt) enc::window_attention_simt(s, static_cast<act_t const*>(qkv), windows, n, heads, bias, static_cast<act_t*>(out));
+        else enc::window_attention(s, static_cast<act_t const*>(qkv), windows, n, heads, bias, static_cast<act_t*>(out));
+    });
+}
+
 DebugApi debug_;
 
 }  // namespace
@@ -297,6 +306,7 @@ DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void) {
     debug_.encode_tap = dbg_encode_tap;
     debug_.resize_plan = dbg_resize_plan;
     debug_.srgb_tables = dbg_srgb_tables;
+    debug_.window_attention = dbg_window_attention;
     return &debug_;
 }
 

@@ -471,7 +471,7 @@ void token_self_attention(cudaStream_t s, float const* q, float const* k, float 
     KERNEL_CHECK();
 }
 
-void token_to_image_attention(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride, int P,
+void token_to_image_attention_twopass(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride, int P,
                               float* out) {
     ProfScope prof(s, CAT_DEC_ATTN);
     static bool attr_set = false;

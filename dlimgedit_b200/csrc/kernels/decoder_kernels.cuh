@@ -41,8 +41,14 @@ void token_self_attention(cudaStream_t s, float const* q, float const* k, float 
 
 // Token -> image attention core: q (P, 7, 128); K, V (4096, 128) per prompt at stride kv_stride floats
 // (0 = shared by all prompts); 8 heads x 16 -> out (P, 7, 128).
+// `scratch` holds P * kT2iSplits * 7 * (128 + 16) floats of partial results (split-key softmax merge).
+constexpr int kT2iSplits = 4;
+constexpr size_t kT2iScratchPerPrompt = (size_t)kT2iSplits * kTokens * (128 + 16);
 void token_to_image_attention(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride, int P,
-                              float* out);
+                              float* scratch, float* out);
+// Older two-pass formulation of the same op, kept as a cross-check for tests.
+void token_to_image_attention_twopass(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride,
+                                      int P, float* out);
 
 // Image -> token attention core: Q (4096, 128) per prompt at stride q_stride (0 = shared); kt, vt (P, 7, 128)
 // -> out (P, 4096, 128).

@@ -123,49 +123,82 @@ __global__ void im2col3x3_kernel(act_t const* __restrict__ in, int H, int W, int
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void dwconv3x3_kernel(act_t const* __restrict__ in, int H, int W, int C8, int stride, int Ho, int Wo,
-                                 int64_t total, float const* __restrict__ weight, float const* __restrict__ bias,
-                                 int gelu, act_t* __restrict__ out) {
+// Each thread produces kTX horizontally adjacent outputs for 8 channels: the 72 filter taps are loaded once
+// into registers and every input column is read once per row and shared by up to three outputs, so the
+// kernel issues ~5x fewer load instructions per output than a pixel-per-thread mapping and stays HBM-bound.
+// Threads are ordered (channel group fastest) so a warp reads whole contiguous pixels.
+template <int kStride, int kTX>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(act_t const* __restrict__ in, int H, int W, int C8, int Ho, int Wo,
+                                                        int xgroups, int64_t total, float const* __restrict__ weight,
+                                                        float const* __restrict__ bias, int gelu,
+                                                        act_t* __restrict__ out) {
     int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     int const c8 = (int)(t % C8);
     int64_t r = t / C8;
-    int const ox = (int)(r % Wo);
-    int64_t r2 = r / Wo;
+    int const xg = (int)(r % xgroups);
+    int64_t r2 = r / xgroups;
     int const oy = (int)(r2 % Ho);
     int const b = (int)(r2 / Ho);
     int const C = C8 * 8;
-    float acc[8];
+    int const ox0 = xg * kTX;
+    constexpr int kCols = (kTX - 1) * kStride + 3;  // input columns feeding kTX outputs
+
+    float w[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        float4 const* w4 = reinterpret_cast<float4 const*>(weight + k * C + c8 * 8);
+        float4 const w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+        w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
+        w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
+    }
+    float acc[kTX][8];
     {
         float4 const* b4 = reinterpret_cast<float4 const*>(bias + c8 * 8);
         float4 const b0 = __ldg(b4), b1 = __ldg(b4 + 1);
-        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-        acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    }
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        int const iy = oy * stride + ky - 1;
-        if (iy < 0 || iy >= H) continue;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            int const ix = ox * stride + kx - 1;
-            if (ix < 0 || ix >= W) continue;
-            uint4 const v = __ldg(reinterpret_cast<uint4 const*>(in) + (((int64_t)b * H + iy) * W + ix) * C8 + c8);
-            float f[8];
-            unpack8(v, f);
-            float4 const* w4 = reinterpret_cast<float4 const*>(weight + (ky * 3 + kx) * C + c8 * 8);
-            float4 const w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-            acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
-            acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
-            acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
-            acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+        for (int o = 0; o < kTX; ++o) {
+            acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+            acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
         }
     }
-    if (gelu) {
+    int const ix0 = ox0 * kStride - 1;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = gelu_erf(acc[i]);
+    for (int ky = 0; ky < 3; ++ky) {
+        int const iy = oy * kStride + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+        uint4 const* row = reinterpret_cast<uint4 const*>(in) + ((int64_t)b * H + iy) * W * C8 + c8;
+        uint4 v[kCols];
+#pragma unroll
+        for (int c = 0; c < kCols; ++c) {
+            int const ix = ix0 + c;
+            v[c] = (ix >= 0 && ix < W) ? __ldg(row + (int64_t)ix * C8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int c = 0; c < kCols; ++c) {
+            float f[8];
+            unpack8(v[c], f);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                // input column c is tap kx of output o when c == o * kStride + kx
+                if ((c - kx) % kStride != 0) continue;
+                int const o = (c - kx) / kStride;
+                if (o < 0 || o >= kTX) continue;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(f[i], w[ky * 3 + kx][i], acc[o][i]);
+            }
+        }
     }
-    reinterpret_cast<uint4*>(out)[t] = pack8(acc);
+    uint4* orow = reinterpret_cast<uint4*>(out) + (((int64_t)b * Ho + oy) * Wo) * C8 + c8;
+#pragma unroll
+    for (int o = 0; o < kTX; ++o) {
+        if (ox0 + o >= Wo) break;
+        if (gelu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[o][i] = gelu_erf(acc[o][i]);
+        }
+        orow[(int64_t)(ox0 + o) * C8] = pack8(acc[o]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -349,10 +382,16 @@ void dwconv3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, 
                float const* bias, bool gelu, act_t* out) {
     DLIMG_ASSERT(C % 8 == 0);
     int const Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-    int64_t const total = (int64_t)batch * Ho * Wo * (C / 8);
+    DLIMG_ASSERT(stride == 1 || stride == 2);
+    constexpr int kTX = 4;
+    int const xgroups = ceil_div(Wo, kTX);
+    int64_t const total = (int64_t)batch * Ho * xgroups * (C / 8);
     ProfScope prof(s, CAT_DWCONV, 2.0 * batch * Ho * Wo * C * 9, (double)batch * ((double)H * W + (double)Ho * Wo) * C * 2);
-    dwconv3x3_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(in, H, W, C / 8, stride, Ho, Wo, total, weight,
-                                                                      bias, gelu ? 1 : 0, out);
+    unsigned const grid = (unsigned)ceil_div64(total, 256);
+    if (stride == 1)
+        dwconv3x3_kernel<1, kTX><<<grid, 256, 0, s>>>(in, H, W, C / 8, Ho, Wo, xgroups, total, weight, bias, gelu ? 1 : 0, out);
+    else
+        dwconv3x3_kernel<2, kTX><<<grid, 256, 0, s>>>(in, H, W, C / 8, Ho, Wo, xgroups, total, weight, bias, gelu ? 1 : 0, out);
     KERNEL_CHECK();
 }
 
@@ -364,9 +403,9 @@ void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const*
     KERNEL_CHECK();
 }
 
-void window_attention(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out) {
+void window_attention_simt(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out) {
     DLIMG_ASSERT(n <= kAttnMaxJ * 32);
-    ProfScope prof(s, CAT_WIN_ATTN, 4.0 * windows * heads * n * n * 32, (double)windows * n * heads * 128 * 2);
+    ProfScope prof(s, CAT_OTHER);
     size_t const smem = sizeof(float) * ((size_t)n * 33 + (size_t)n * 32 + kAttnWarps * 32 + (size_t)kAttnWarps * n);
     static bool attr_set = false;
     if (!attr_set) {

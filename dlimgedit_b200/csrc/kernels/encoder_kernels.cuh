@@ -40,6 +40,8 @@ void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const*
 // Windowed multi-head attention, head_dim 32.  qkv: (windows*n, heads*96) with per-head [q|k|v];
 // bias: (heads, n, n) fp32 (already gathered from attention_biases); out: (windows*n, heads*32).
 void window_attention(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out);
+// CUDA-core version of the same op (cross-check in tests).
+void window_attention_simt(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out);
 
 // (tokens, C) fp32 -> (C, tokens) fp32 per image: the reference's NCHW `image_embeddings` layout.
 void tokens_to_nchw(cudaStream_t s, float const* in, int batch, int tokens, int C, float* out);

@@ -14,7 +14,8 @@ namespace {
 
 constexpr int kAStageBytes = kBlockM * kKBytes;     // 16 KiB
 constexpr int kBStageBytes = kMaxBlockN * kKBytes;  // 32 KiB
-constexpr int kNumThreads = 192;
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, each takes every other 16-column slab
+constexpr int kNumThreads = 64 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;                      // two accumulator stages of up to 256 fp32 columns
 constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -207,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);
+            mbar_init(tempty_bar(s), kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -274,8 +275,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
     } else {
-        // ---------------- epilogue (4 warps; TMEM lane quarter = warp index mod 4) ----------------
+        // ---------------- epilogue (8 warps; TMEM lane quarter = warp index mod 4, column slabs interleaved) -------
         int const quarter = warp & 3;
+        int const half = (warp - 2) >> 2;
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int const acc = local & 1;
@@ -288,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             int64_t orow = -1;
             if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
             uint32_t const taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN);
-            for (int c = 0; c < block_n; c += 16) {
+            for (int c = half * 16; c < block_n; c += 32) {
                 uint32_t r[16];
                 tmem_ld16(taddr + (uint32_t)c, r);
                 tmem_ld_wait();

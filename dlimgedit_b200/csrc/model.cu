@@ -326,6 +326,7 @@ DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
     low.allocate(P * 4 * 65536);
     plane_index.allocate(P * 3);
     iou_sel.allocate(P * 3);
+    t2i_scratch.allocate(P * dec::kT2iScratchPerPrompt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -500,11 +501,11 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, EmbeddingCache const
         // (2) tokens attend to the image
         lin(s, ws.queries.get(), 256, ws.tok0.get(), R, l.t2i.q, false, ws.t128a.get(), 128);
         if (first) {
-            dec::token_to_image_attention(s, ws.t128a.get(), cache.K0.get(), cache.V0.get(), 0, P, ws.t128b.get());
+            dec::token_to_image_attention(s, ws.t128a.get(), cache.K0.get(), cache.V0.get(), 0, P, ws.t2i_scratch.get(), ws.t128b.get());
         } else {
             gemm32(s, kpe, IR, l.t2i.k, ws.Kp.get(), gemm::ACT_NONE);
             gemm32(s, keys, IR, l.t2i.v, ws.Vp.get(), gemm::ACT_NONE);
-            dec::token_to_image_attention(s, ws.t128a.get(), ws.Kp.get(), ws.Vp.get(), img_stride, P, ws.t128b.get());
+            dec::token_to_image_attention(s, ws.t128a.get(), ws.Kp.get(), ws.Vp.get(), img_stride, P, ws.t2i_scratch.get(), ws.t128b.get());
         }
         lin(s, ws.t128b.get(), 128, nullptr, R, l.t2i.o, false, ws.tmp.get(), 256);
         dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, l.n2.g.get(), l.n2.b.get(), nullptr, 0, ws.queries.get(), nullptr);
@@ -531,7 +532,7 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, EmbeddingCache const
     lin(s, ws.queries.get(), 256, ws.tok0.get(), R, dec_.final_attn.q, false, ws.t128a.get(), 128);
     gemm32(s, kpe, IR, dec_.final_attn.k, ws.Kp.get(), gemm::ACT_NONE);
     gemm32(s, keys, IR, dec_.final_attn.v, ws.Vp.get(), gemm::ACT_NONE);
-    dec::token_to_image_attention(s, ws.t128a.get(), ws.Kp.get(), ws.Vp.get(), img_stride, P, ws.t128b.get());
+    dec::token_to_image_attention(s, ws.t128a.get(), ws.Kp.get(), ws.Vp.get(), img_stride, P, ws.t2i_scratch.get(), ws.t128b.get());
     lin(s, ws.t128b.get(), 128, nullptr, R, dec_.final_attn.o, false, ws.tmp.get(), 256);
     dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, dec_.norm_final.g.get(), dec_.norm_final.b.get(), nullptr, 0,
                       ws.queries.get(), nullptr);

@@ -137,6 +137,7 @@ struct DecoderWorkspace {
     DeviceBuffer<float> low;                                 // (P,4,256,256)
     DeviceBuffer<int> plane_index;                           // (P*3)
     DeviceBuffer<float> iou_sel;                             // (P*3)
+    DeviceBuffer<float> t2i_scratch;                         // split-key partials of the token->image attention
     explicit DecoderWorkspace(int max_prompts);
 };
 

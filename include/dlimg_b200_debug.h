@@ -25,6 +25,10 @@ typedef struct dlimg_b200_Debug {
      * weights[out_size * max_taps]. */
     int (*resize_plan)(int in_size, int out_size, int max_taps, int* first, float* weights);
     void (*srgb_tables)(float* decode256, float* threshold256);
+    /* Windowed attention on device buffers: qkv (windows*n, heads*96) 16-bit, bias (heads, n, n) fp32 ->
+     * out (windows*n, heads*32) 16-bit.  simt != 0 runs the CUDA-core cross-check kernel. */
+    dlimg_Result (*window_attention)(void* stream, int simt, void const* qkv, int windows, int n, int heads,
+                                     float const* bias, void* out);
 } dlimg_b200_Debug;
 
 DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void);

@@ -126,3 +126,26 @@ def test_batch_equals_single(env, case):
     assert np.array_equal(e[0], e[2])          # same image, different batch slot -> identical
     assert np.array_equal(e[0], single)        # batch of 3 vs the reference-style single call
     assert not np.array_equal(e[0], e[1])
+
+
+@pytest.mark.parametrize("windows,n,heads", [(361, 49, 4), (25, 196, 5), (100, 49, 10), (3, 196, 5)])
+def test_window_attention_kernel(windows, n, heads):
+    """Tensor-core (mma.sync) windowed attention vs the CUDA-core kernel vs a plain PyTorch fp32 reference."""
+    import ctypes
+    from gpu_util import act_dtype
+    g = torch.Generator(device="cuda").manual_seed(n + heads)
+    qkv = torch.randn(windows * n, heads * 96, device="cuda", generator=g).to(act_dtype())
+    bias = torch.randn(heads, n, n, device="cuda", generator=g)
+    outs = []
+    for simt in (0, 1):
+        out = torch.zeros(windows * n, heads * 32, device="cuda", dtype=act_dtype())
+        r = dl.debug().window_attention(None, simt, qkv.data_ptr(), windows, n, heads, bias.data_ptr(), out.data_ptr())
+        assert r == 0, dl.api().last_error()
+        torch.cuda.synchronize()
+        outs.append(out.float())
+    x = qkv.float().view(windows, n, heads, 96)
+    q, k, v = (t.permute(0, 2, 1, 3) for t in x.split([32, 32, 32], dim=3))
+    ref = ((q @ k.transpose(-2, -1)) * 32 ** -0.5 + bias[None]).softmax(-1) @ v
+    ref = ref.permute(0, 2, 1, 3).reshape(windows * n, heads * 32)
+    for o in outs:
+        assert torch.allclose(o, ref, atol=2e-2 if act_dtype() == torch.bfloat16 else 4e-3, rtol=1e-2), float((o - ref).abs().max())
