@@ -246,8 +246,17 @@ dlimg_Result dbg_window_attention(void* stream, int simt, void const* qkv, int w
                                   void* out) {
     return try_([=] {
         auto s = static_cast<cudaStream_t>(stream);
-        if (simt) enc::window_attention_simt(s, static_cast<act_t const*>(qkv), windows, n, heads, bias, static_cast<act_t*>(out));
-        else enc::window_attention(s, static_cast<act_t const*>(qkv), windows, n, heads, bias, static_cast<act_t*>(out));
+        if (simt) {
+            enc::window_attention_simt(s, static_cast<act_t const*>(qkv), windows, n, heads, bias, static_cast<act_t*>(out));
+        } else {  // re-order the dense (heads, n, n) table for the tensor-core kernel
+            std::vector<float> dense((size_t)heads * n * n), frag(enc::attention_bias_fragment_floats(heads, n));
+            CUDA_CHECK(cudaMemcpy(dense.data(), bias, dense.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            enc::attention_bias_fragments(dense.data(), heads, n, frag.data());
+            DeviceBuffer<float> dfrag;
+            dfrag.upload(frag);
+            enc::window_attention(s, static_cast<act_t const*>(qkv), windows, n, heads, dfrag.get(), static_cast<act_t*>(out));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+        }
     });
 }
 

@@ -1,5 +1,6 @@
 // decoder_kernels.cu -- see decoder_kernels.cuh.
 #include "decoder_kernels.cuh"
+#include "gelu.cuh"
 
 #include "../profiler.hpp"
 
@@ -8,7 +9,7 @@ namespace dec {
 
 namespace {
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// gelu_erf: see gelu.cuh
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

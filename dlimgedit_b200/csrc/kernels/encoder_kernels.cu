@@ -1,5 +1,6 @@
 // encoder_kernels.cu -- see encoder_kernels.cuh.
 #include "encoder_kernels.cuh"
+#include "gelu.cuh"
 
 #include "../profiler.hpp"
 
@@ -8,7 +9,7 @@ namespace enc {
 
 namespace {
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// gelu_erf: see gelu.cuh
 
 __device__ __forceinline__ void unpack8(uint4 const& v, float (&f)[8]) {
     act2_t const* h = reinterpret_cast<act2_t const*>(&v);

@@ -38,9 +38,18 @@ void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const*
                     float const* beta, float eps, void* out, bool out_f32);
 
 // Windowed multi-head attention, head_dim 32.  qkv: (windows*n, heads*96) with per-head [q|k|v];
-// bias: (heads, n, n) fp32 (already gathered from attention_biases); out: (windows*n, heads*32).
+// out: (windows*n, heads*32).  bias: relative-position bias already gathered from attention_biases, in the
+// tensor-core accumulator order produced by attention_bias_fragments() below.
 void window_attention(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out);
-// CUDA-core version of the same op (cross-check in tests).
+// n rounded up to the tile the kernel is instantiated for (49 -> 64, 196 -> 208).
+inline int window_pad(int n) { return n <= 64 ? 64 : 208; }
+// Number of floats of the fragment-ordered bias table for `heads` heads.
+inline size_t attention_bias_fragment_floats(int heads, int n) { return (size_t)heads * window_pad(n) * window_pad(n); }
+// dense (heads, n, n) -> [head][query tile (n_pad/16)][key block (n_pad/8)][lane (32)][4]; for lane = 4*g + t the
+// four values are (row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1) of the 16 x 8 block; padded key columns
+// hold -inf (which masks them in the softmax), padded query rows 0.
+void attention_bias_fragments(float const* dense, int heads, int n, float* out);
+// CUDA-core version of the same op, dense (heads, n, n) bias (cross-check in tests).
 void window_attention_simt(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out);
 
 // (tokens, C) fp32 -> (C, tokens) fp32 per image: the reference's NCHW `image_embeddings` layout.

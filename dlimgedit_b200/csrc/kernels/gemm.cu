@@ -1,5 +1,6 @@
 // gemm.cu -- tcgen05 / TMEM / TMA GEMM for sm_100a (see gemm.cuh for the contract).
 #include "gemm.cuh"
+#include "gelu.cuh"
 
 #include "../profiler.hpp"
 
@@ -14,7 +15,7 @@ namespace {
 
 constexpr int kAStageBytes = kBlockM * kKBytes;     // 16 KiB
 constexpr int kBStageBytes = kMaxBlockN * kKBytes;  // 32 KiB
-constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, each takes every other 16-column slab
+constexpr int kEpiWarps = 16;                       // four per TMEM lane quarter; slabs of 16 columns are dealt round-robin
 constexpr int kNumThreads = 64 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;                      // two accumulator stages of up to 256 fp32 columns
 constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 256 /*barriers*/;
@@ -92,7 +93,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// gelu_erf: see gelu.cuh
 
 struct EpiParams {
     float const* bias;
@@ -277,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     } else {
         // ---------------- epilogue (8 warps; TMEM lane quarter = warp index mod 4, column slabs interleaved) -------
         int const quarter = warp & 3;
-        int const half = (warp - 2) >> 2;
+        int const slab = (warp - 2) >> 2;  // which of the kEpiWarps/4 warps of this lane quarter
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int const acc = local & 1;
@@ -290,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             int64_t orow = -1;
             if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
             uint32_t const taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN);
-            for (int c = half * 16; c < block_n; c += 32) {
+            for (int c = slab * 16; c < block_n; c += (kEpiWarps / 4) * 16) {
                 uint32_t r[16];
                 tmem_ld16(taddr + (uint32_t)c, r);
                 tmem_ld_wait();

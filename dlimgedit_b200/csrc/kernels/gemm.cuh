@@ -5,7 +5,7 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128-byte swizzle, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128, N=block_n, fp32 accumulators in TMEM,
 //                               two accumulator stages so the epilogue of tile i overlaps tile i+1)
-//   warps 2..9  epilogue       (tcgen05.ld -> bias / residual / activation -> bf16|fp32 global stores,
+//   warps 2..17 epilogue       (tcgen05.ld -> bias / residual / activation -> bf16|fp32 global stores,
 //                               optional row scatter used for window un-partition)
 // Operand element type is bf16 (kind::f16) for the encoder or fp32-as-tf32 (kind::tf32) for the decoder;
 // the shared-memory geometry is identical in bytes (128 B of K per row per stage).

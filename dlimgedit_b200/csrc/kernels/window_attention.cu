@@ -10,6 +10,8 @@
 
 #include "../profiler.hpp"
 
+#include <cmath>
+
 namespace dlimg {
 namespace enc {
 
@@ -72,7 +74,8 @@ __global__ void __launch_bounds__(kWarps * 32) window_attention_mma_kernel(act_t
     __syncthreads();
 
     float const scale = 0.17677669529663687f;  // 32^-0.5
-    float const* bias_h = bias + (int64_t)h * n * n;
+    // bias is pre-arranged in accumulator-fragment order: [head][query tile][key block][lane] x float4
+    float4 const* bias_h = reinterpret_cast<float4 const*>(bias) + (size_t)h * (kNPad / 16) * (kNPad / 8) * 32;
     uint32_t const* Qw = reinterpret_cast<uint32_t const*>(Qs);
     uint32_t const* Kw = reinterpret_cast<uint32_t const*>(Ks);
     uint32_t const* Vw = reinterpret_cast<uint32_t const*>(Vt);
@@ -101,22 +104,19 @@ __global__ void __launch_bounds__(kWarps * 32) window_attention_mma_kernel(act_t
                 mma16816(s[nb], aq[ks][0], aq[ks][1], aq[ks][2], aq[ks][3], b0, b1);
             }
         }
-        // ---- scale + bias + mask, row max ----
+        // ---- scale + bias (+ mask: the table holds -inf for padded key columns), row max ----
         float m0 = -INFINITY, m1 = -INFINITY;
         bool const v0 = r0 < n, v1 = r1 < n;
+        float4 const* bias_q = bias_h + (size_t)qt * (kNPad / 8) * 32 + lane;
 #pragma unroll
         for (int nb = 0; nb < kNPad / 8; ++nb) {
-            int const c = nb * 8 + 2 * t;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                bool const cv = c + e < n;
-                float const b0 = (cv && v0) ? __ldg(bias_h + (int64_t)r0 * n + c + e) : 0.f;
-                float const b1 = (cv && v1) ? __ldg(bias_h + (int64_t)r1 * n + c + e) : 0.f;
-                s[nb][e] = cv ? fmaf(s[nb][e], scale, b0) : -INFINITY;
-                s[nb][2 + e] = cv ? fmaf(s[nb][2 + e], scale, b1) : -INFINITY;
-                m0 = fmaxf(m0, s[nb][e]);
-                m1 = fmaxf(m1, s[nb][2 + e]);
-            }
+            float4 const bv = __ldg(bias_q + nb * 32);  // one coalesced 16-byte load per accumulator quad
+            s[nb][0] = fmaf(s[nb][0], scale, bv.x);
+            s[nb][1] = fmaf(s[nb][1], scale, bv.y);
+            s[nb][2] = fmaf(s[nb][2], scale, bv.z);
+            s[nb][3] = fmaf(s[nb][3], scale, bv.w);
+            m0 = fmaxf(m0, fmaxf(s[nb][0], s[nb][1]));
+            m1 = fmaxf(m1, fmaxf(s[nb][2], s[nb][3]));
         }
         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
@@ -179,6 +179,23 @@ void launch_mma(cudaStream_t s, act_t const* qkv, int windows, int n, int heads,
 }
 
 }  // namespace
+
+void attention_bias_fragments(float const* dense, int heads, int n, float* out) {
+    int const np = window_pad(n);
+    size_t i = 0;
+    for (int h = 0; h < heads; ++h)
+        for (int qt = 0; qt < np / 16; ++qt)
+            for (int nb = 0; nb < np / 8; ++nb)
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int e = 0; e < 4; ++e) {
+                        int const r = qt * 16 + (lane >> 2) + (e >= 2 ? 8 : 0);
+                        int const c = nb * 8 + 2 * (lane & 3) + (e & 1);
+                        float v = 0.f;
+                        if (c >= n) v = -INFINITY;
+                        else if (r < n) v = dense[((size_t)h * n + r) * n + c];
+                        out[i++] = v;
+                    }
+}
 
 void window_attention(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out) {
     ProfScope prof(s, CAT_WIN_ATTN, 4.0 * windows * heads * n * n * 32, (double)windows * n * heads * 128 * 2);

@@ -183,7 +183,12 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
             b.attn_norm = load_norm(wf, p + ".attn.norm", C);
             b.qkv = load_linear16(wf, p + ".attn.qkv", 3 * C, C);
             b.proj = load_linear16(wf, p + ".attn.proj", C, C);
-            b.attn_bias.upload(dense_attention_bias(wf.get(p + ".attn.attention_biases"), heads, ws));
+            {
+                std::vector<float> const dense = dense_attention_bias(wf.get(p + ".attn.attention_biases"), heads, ws);
+                std::vector<float> frag(enc::attention_bias_fragment_floats(heads, ws * ws));
+                enc::attention_bias_fragments(dense.data(), heads, ws * ws, frag.data());
+                b.attn_bias.upload(frag);
+            }
             b.local_conv = load_dw_bn(wf, p + ".local_conv", C);
             b.mlp_norm = load_norm(wf, p + ".mlp.norm", C);
             b.fc1 = load_linear16(wf, p + ".mlp.fc1", 4 * C, C);
