@@ -1,6 +1,8 @@
 // engine.cu -- see engine.hpp.
 #include "engine.hpp"
 
+#include "profiler.hpp"
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -42,6 +44,14 @@ void check_view(dlimg_ImageView const& v) {
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------
+StreamBuffer::StreamBuffer(size_t bytes, cudaStream_t stream) : stream_(stream) {
+    CUDA_CHECK(cudaMallocAsync(&ptr_, bytes, stream));
+}
+StreamBuffer::~StreamBuffer() {
+    if (ptr_) cudaFreeAsync(ptr_, stream_);
+}
 
 // ---------------------------------------------------------------------------------------------
 PinnedArena::PinnedArena(size_t bytes) : cap_(bytes) {
@@ -95,6 +105,13 @@ EnvironmentImpl::EnvironmentImpl(dlimg_Options const& opts) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     max_batch_ = env_int("DLIMG_B200_MAX_BATCH", 8, 1, 64);
     max_prompts_ = env_int("DLIMG_B200_MAX_PROMPTS", 32, 1, 256);
+    use_graphs_ = env_int("DLIMG_B200_GRAPHS", 1, 0, 1) != 0;
+    {   // keep freed stream-ordered allocations cached in the pool instead of returning them to the OS
+        cudaMemPool_t pool = nullptr;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device_));
+        uint64_t threshold = UINT64_MAX;
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    }
     pinned_ = std::make_unique<PinnedArena>((size_t)4 << 20);
     auto const& t = prepost::srgb_tables();
     srgb_decode_.upload(std::vector<float>(t.decode, t.decode + 256));
@@ -104,6 +121,7 @@ EnvironmentImpl::EnvironmentImpl(dlimg_Options const& opts) {
 EnvironmentImpl::~EnvironmentImpl() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
+    for (auto& g : encode_graphs_) cudaGraphExecDestroy(g.second.exec);
     if (own_stream_) cudaStreamDestroy(own_stream_);
 }
 
@@ -202,7 +220,43 @@ void EnvironmentImpl::encode_chunk(enc::ImageDesc const* host_descs, int batch, 
     void* staging = pinned_->take(bytes, s);
     std::memcpy(staging, host_descs, bytes);
     CUDA_CHECK(cudaMemcpyAsync(descs_.get(), staging, bytes, cudaMemcpyHostToDevice, s));
-    model().encode(s, encoder_ws(), descs_.get(), batch, size.w, size.h, channels, emb_out, tap);
+    SamModel& m = model();
+    EncoderWorkspace& ws = encoder_ws();
+    if (tap || !use_graphs_ || Profiler::get().enabled()) {  // eager launches (debug taps, per-kernel timing)
+        m.encode(s, ws, descs_.get(), batch, size.w, size.h, channels, emb_out, tap);
+        return;
+    }
+    // The ~130 launches of one encoder pass are captured once per (batch, extent, channel order) into a CUDA
+    // graph: every pointer it uses (workspace, weights, descriptor table, tensor maps) is stable, only the
+    // descriptor *contents* (uploaded above) and the destination of the final embedding copy change per call.
+    auto const key = std::make_tuple(batch, size.w, size.h, channels);
+    auto it = encode_graphs_.find(key);
+    if (it == encode_graphs_.end()) {
+        cudaGraph_t graph = nullptr;
+        uint64_t const launches_before = g_kernel_launches.load();
+        CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        try {
+            m.encode(s, ws, descs_.get(), batch, size.w, size.h, channels, ws.emb.get(), nullptr);
+        } catch (...) {
+            cudaStreamEndCapture(s, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        CUDA_CHECK(cudaStreamEndCapture(s, &graph));
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t const err = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CUDA_CHECK(err);
+        EncodeGraph eg;
+        eg.exec = exec;
+        eg.kernels = g_kernel_launches.load() - launches_before;  // kernel nodes recorded by this capture
+        g_kernel_launches -= eg.kernels;                          // they have not run yet
+        it = encode_graphs_.emplace(key, eg).first;
+    }
+    CUDA_CHECK(cudaGraphLaunch(it->second.exec, s));
+    count_launch(it->second.kernels);
+    CUDA_CHECK(cudaMemcpyAsync(emb_out, ws.emb.get(), sizeof(float) * (size_t)batch * dec::kImgTokens * kEmbedDim,
+                               cudaMemcpyDeviceToDevice, s));
 }
 
 void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, bool on_device, SegmentationImpl** out) {
@@ -230,14 +284,14 @@ void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, boo
     std::vector<enc::ImageDesc> descs((size_t)max_batch_);
     for (int start = 0; start < count; start += max_batch_) {
         int const B = std::min(max_batch_, count - start);
-        auto store = std::make_shared<DeviceBuffer<float>>((size_t)B * dec::kImgTokens * kEmbedDim);
+        auto store = std::make_shared<StreamBuffer>(sizeof(float) * (size_t)B * dec::kImgTokens * kEmbedDim, s);
         for (int i = 0; i < B; ++i) prepare_input(views[start + i], on_device, size, i, descs[(size_t)i]);
-        encode_chunk(descs.data(), B, size, views[0].channels, store->get(), nullptr);
+        encode_chunk(descs.data(), B, size, views[0].channels, store->floats(), nullptr);
         for (int i = 0; i < B; ++i) {
             SegmentationImpl* seg = out[start + i];
             seg->size_ = size;
             seg->emb_store_ = store;
-            seg->emb_ = store->get() + (size_t)i * dec::kImgTokens * kEmbedDim;
+            seg->emb_ = store->floats() + (size_t)i * dec::kImgTokens * kEmbedDim;
             seg->cache_.ready = false;
         }
     }

@@ -9,6 +9,7 @@
 #include "model.hpp"
 
 #include <map>
+#include <tuple>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -22,6 +23,21 @@ struct DeviceAxisPlan {
     DeviceBuffer<int> first;
     DeviceBuffer<float> weights;
     int taps = 0;
+};
+
+// Device memory from the stream-ordered allocator (cudaMallocAsync): per-call embedding stores are recycled from
+// the driver's pool instead of paying a blocking cudaMalloc / cudaFree per batch.
+class StreamBuffer {
+  public:
+    StreamBuffer(size_t bytes, cudaStream_t stream);
+    ~StreamBuffer();
+    StreamBuffer(StreamBuffer const&) = delete;
+    StreamBuffer& operator=(StreamBuffer const&) = delete;
+    float* floats() const { return static_cast<float*>(ptr_); }
+
+  private:
+    void* ptr_ = nullptr;
+    cudaStream_t stream_ = nullptr;
 };
 
 // Page-locked host arena for small parameter uploads (prompt coordinates, descriptors, pointer tables).
@@ -104,6 +120,9 @@ class EnvironmentImpl {
     std::map<std::pair<int, int>, DeviceAxisPlan> plans_;
     DeviceBuffer<uint8_t> mask_out_;       // device staging for host-destined masks
     DeviceBuffer<uint8_t*> plane_ptrs_;
+    bool use_graphs_ = true;  // $DLIMG_B200_GRAPHS=0 forces eager launches
+    struct EncodeGraph { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; };
+    std::map<std::tuple<int, int, int, int>, EncodeGraph> encode_graphs_;
     DeviceBuffer<float> emb_scratch_;      // NCHW staging for get_embedding
 };
 
@@ -124,7 +143,7 @@ class SegmentationImpl {
     friend class EnvironmentImpl;
     EnvironmentImpl& env_;
     prepost::LongestSide size_;
-    std::shared_ptr<DeviceBuffer<float>> emb_store_;  // shared by the images of one encoder chunk
+    std::shared_ptr<StreamBuffer> emb_store_;         // shared by the images of one encoder chunk
     float* emb_ = nullptr;                            // (4096, 256) fp32 token-major
     EmbeddingCache cache_;
 };

@@ -6,7 +6,9 @@
 
 #include <cuda_runtime.h>
 
+#include <map>
 #include <mutex>
+#include <tuple>
 
 namespace dlimg {
 namespace gemm {
@@ -381,7 +383,32 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+CUtensorMap encode_map(Operand const& op, bool tf32, int box_rows);
+
+// Tensor maps depend only on (pointer, shape, pitch, box, type); the engine's workspaces and weights have stable
+// addresses, so encoded maps are memoised instead of calling into the driver twice per GEMM launch.
 CUtensorMap make_map(Operand const& op, bool tf32, int box_rows) {
+    struct Key {
+        void const* ptr;
+        int64_t rows, cols, pitch;
+        int box_rows, tf32;
+        bool operator<(Key const& o) const {
+            return std::tie(ptr, rows, cols, pitch, box_rows, tf32) < std::tie(o.ptr, o.rows, o.cols, o.pitch, o.box_rows, o.tf32);
+        }
+    };
+    static std::mutex mutex;
+    static std::map<Key, CUtensorMap> cache;
+    Key const key{op.ptr, op.rows, op.cols, op.pitch ? op.pitch : op.cols, box_rows, tf32 ? 1 : 0};
+    std::lock_guard<std::mutex> lock(mutex);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        if (cache.size() > 8192) cache.clear();
+        it = cache.emplace(key, encode_map(op, tf32, box_rows)).first;
+    }
+    return it->second;
+}
+
+CUtensorMap encode_map(Operand const& op, bool tf32, int box_rows) {
     CUtensorMap map;
     int const esz = tf32 ? 4 : 2;
     int64_t const pitch = op.pitch ? op.pitch : op.cols;

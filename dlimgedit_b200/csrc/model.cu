@@ -291,6 +291,7 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
 EncoderWorkspace::EncoderWorkspace(int mb) : max_batch(mb) {
     size_t const B = (size_t)mb;
     c1.allocate(B * 512 * 512 * 32);
+    emb.allocate(B * 4096 * 256);
     col.allocate(B * 65536 * 288);
     xa.allocate(B * 65536 * 64);
     xb.allocate(B * 65536 * 64);

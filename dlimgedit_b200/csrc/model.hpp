@@ -118,6 +118,7 @@ struct DecoderW {
 struct EncoderWorkspace {
     int max_batch = 0;
     DeviceBuffer<act_t> c1, col, xa, xb, big[4];
+    DeviceBuffer<float> emb;       // (max_batch, 4096, 256) fp32: fixed destination of the captured encoder graph
     DeviceBuffer<int> row_map[3];  // stage 1..3: windowed row -> token row (-1 = padding), for max_batch images
     int win_rows[3] = {0, 0, 0};   // windowed rows per image
     explicit EncoderWorkspace(int max_batch);
