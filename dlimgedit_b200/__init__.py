@@ -10,6 +10,7 @@ libdlimgedit.so is missing or no Blackwell GPU is present.
 from __future__ import annotations
 
 import ctypes
+import weakref
 import enum
 import os
 from dataclasses import dataclass
@@ -250,12 +251,15 @@ class Environment:
         self._dir = options.model_directory.encode()
         opts = _Options(int(options.backend), self._dir)
         _check(api().create_environment(ctypes.byref(self._h), ctypes.byref(opts)))
+        self._segs = weakref.WeakSet()  # the environment must outlive its Segmentations (dlimgedit.hpp:98-100)
 
     def handle(self):
         return self._h
 
     def close(self):
         if getattr(self, "_h", None):
+            for s in list(getattr(self, "_segs", ())):  # garbage-collection order must not free the environment first
+                s.close()
             api().destroy_environment(self._h)
             self._h = None
 
@@ -339,6 +343,7 @@ class Segmentation:
         s = Segmentation()
         s._h = _H(h)
         s._env = env
+        env._segs.add(s)
         return s
 
     @staticmethod

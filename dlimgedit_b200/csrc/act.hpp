@@ -27,7 +27,12 @@ __host__ __device__ inline float act_sat(float v) { return v > 65504.0f ? 65504.
 __host__ __device__ inline float act2f(act_t v) { return __half2float(v); }
 __host__ __device__ inline act_t f2act(float v) { return __float2half_rn(act_sat(v)); }
 __device__ inline float2 act22f2(act2_t v) { return __half22float2(v); }
-__device__ inline act2_t f22act2(float a, float b) { return __floats2half2_rn(act_sat(a), act_sat(b)); }
+// one F2FP.SATFINITE.PACK_AB instead of four FMNMX + F2FP: the epilogues and depthwise kernels are issue-bound
+__device__ inline act2_t f22act2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return *reinterpret_cast<act2_t const*>(&r);
+}
 #endif
 
 }  // namespace dlimg

@@ -4,6 +4,8 @@
 
 #include "../profiler.hpp"
 
+#include <cstdlib>
+
 namespace dlimg {
 namespace enc {
 
@@ -124,37 +126,55 @@ __global__ void im2col3x3_kernel(act_t const* __restrict__ in, int H, int W, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// Each thread produces kTX horizontally adjacent outputs for 8 channels: the 72 filter taps are loaded once
-// into registers and every input column is read once per row and shared by up to three outputs, so the
-// kernel issues ~5x fewer load instructions per output than a pixel-per-thread mapping and stays HBM-bound.
-// Threads are ordered (channel group fastest) so a warp reads whole contiguous pixels.
-template <int kStride, int kTX>
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(act_t const* __restrict__ in, int H, int W, int C8, int Ho, int Wo,
-                                                        int xgroups, int64_t total, float const* __restrict__ weight,
-                                                        float const* __restrict__ bias, int gelu,
-                                                        act_t* __restrict__ out) {
-    int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    int const c8 = (int)(t % C8);
-    int64_t r = t / C8;
-    int const xg = (int)(r % xgroups);
-    int64_t r2 = r / xgroups;
-    int const oy = (int)(r2 % Ho);
-    int const b = (int)(r2 / Ho);
-    int const C = C8 * 8;
-    int const ox0 = xg * kTX;
+// Depthwise 3x3.  Each thread produces kTX horizontally adjacent outputs for 8 channels: the filter taps are
+// loaded once into registers and every input column is read once per row and shared by up to three outputs.
+// Threads are ordered (channel group fastest) so a warp reads whole contiguous pixels.  The channel count is a
+// template parameter so all column offsets are immediates (one 64-bit base per input row), and threads whose
+// window lies inside the row take a predicate-free path; grid = (x, output row, image).
+template <int kStride, int kTX, int kC8, bool kEdge, typename Acc>
+__device__ __forceinline__ void dwconv_rows(act_t const* __restrict__ in, int H, int W, int b, int oy, int c8, int ix0, Acc& acc) {
     constexpr int kCols = (kTX - 1) * kStride + 3;  // input columns feeding kTX outputs
-
-    float w[9][8];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        float4 const* w4 = reinterpret_cast<float4 const*>(weight + k * C + c8 * 8);
-        float4 const w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-        w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
-        w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
+    for (int ky = 0; ky < 3; ++ky) {
+        int const iy = oy * kStride + ky - 1;
+        if (iy < 0 || iy >= H) continue;  // block-uniform
+        uint4 const* row = reinterpret_cast<uint4 const*>(in) + (((int64_t)b * H + iy) * W + ix0) * kC8 + c8;
+        uint4 v[kCols];
+#pragma unroll
+        for (int c = 0; c < kCols; ++c) {
+            if (kEdge) {
+                int const ix = ix0 + c;
+                v[c] = (ix >= 0 && ix < W) ? __ldg(row + c * kC8) : make_uint4(0, 0, 0, 0);
+            } else {
+                v[c] = __ldg(row + c * kC8);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kCols; ++c) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                // input column c is tap kx of output o when c == o * kStride + kx
+                if ((c - kx) % kStride != 0) continue;
+                int const o = (c - kx) / kStride;
+                if (o < 0 || o >= kTX) continue;
+                acc.tap(o, ky * 3 + kx, v[c]);
+            }
+        }
     }
+}
+
+template <int kTX>
+struct DwAcc32 {  // fp32 taps and accumulators
+    float w[9][8];
     float acc[kTX][8];
-    {
+    __device__ __forceinline__ void init(float const* __restrict__ weight, float const* __restrict__ bias, int C, int c8) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            float4 const* w4 = reinterpret_cast<float4 const*>(weight + k * C + c8 * 8);
+            float4 const w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+            w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
+            w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
+        }
         float4 const* b4 = reinterpret_cast<float4 const*>(bias + c8 * 8);
         float4 const b0 = __ldg(b4), b1 = __ldg(b4 + 1);
 #pragma unroll
@@ -163,42 +183,76 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(act_t const* __restrict_
             acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
         }
     }
-    int const ix0 = ox0 * kStride - 1;
+    __device__ __forceinline__ void tap(int o, int k, uint4 const& v) {
+        float f[8];
+        unpack8(v, f);
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        int const iy = oy * kStride + ky - 1;
-        if (iy < 0 || iy >= H) continue;
-        uint4 const* row = reinterpret_cast<uint4 const*>(in) + ((int64_t)b * H + iy) * W * C8 + c8;
-        uint4 v[kCols];
-#pragma unroll
-        for (int c = 0; c < kCols; ++c) {
-            int const ix = ix0 + c;
-            v[c] = (ix >= 0 && ix < W) ? __ldg(row + (int64_t)ix * C8) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int c = 0; c < kCols; ++c) {
-            float f[8];
-            unpack8(v[c], f);
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                // input column c is tap kx of output o when c == o * kStride + kx
-                if ((c - kx) % kStride != 0) continue;
-                int const o = (c - kx) / kStride;
-                if (o < 0 || o >= kTX) continue;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(f[i], w[ky * 3 + kx][i], acc[o][i]);
-            }
-        }
+        for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(f[i], w[k][i], acc[o][i]);
     }
-    uint4* orow = reinterpret_cast<uint4*>(out) + (((int64_t)b * Ho + oy) * Wo) * C8 + c8;
-#pragma unroll
-    for (int o = 0; o < kTX; ++o) {
-        if (ox0 + o >= Wo) break;
+    __device__ __forceinline__ uint4 result(int o, bool gelu) {
         if (gelu) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[o][i] = gelu_erf(acc[o][i]);
         }
-        orow[(int64_t)(ox0 + o) * C8] = pack8(acc[o]);
+        return pack8(acc[o]);
+    }
+};
+
+#if !defined(DLIMG_B200_ACT_BF16)
+// Packed-half variant for the GELU'd depthwise convolutions (MBConv conv2, PatchMerging conv2): taps, bias and the
+// erf GELU all run as HFMA2 on fp16 pairs, so the inputs need no unpacking and every instruction covers two
+// channels.  The fp32 form spent ~48 issue slots per output (profiles/r01b: issue-bound at 62 %, 128 registers).
+// Accumulation is fp16: nine products of GELU-bounded activations with BN-folded weights, an error of ~3 ulp on a
+// value that is rounded to fp16 immediately afterwards anyway.
+template <int kTX>
+struct DwAccH2 {
+    uint4 w[9];
+    __half2 acc[kTX][4];
+    __device__ __forceinline__ void init(act_t const* __restrict__ weight, float const* __restrict__ bias, int C, int c8) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = __ldg(reinterpret_cast<uint4 const*>(weight + k * C + c8 * 8));
+        float4 const* b4 = reinterpret_cast<float4 const*>(bias + c8 * 8);
+        float4 const b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+        __half2 const h0 = f22act2(b0.x, b0.y), h1 = f22act2(b0.z, b0.w), h2 = f22act2(b1.x, b1.y), h3 = f22act2(b1.z, b1.w);
+#pragma unroll
+        for (int o = 0; o < kTX; ++o) { acc[o][0] = h0; acc[o][1] = h1; acc[o][2] = h2; acc[o][3] = h3; }
+    }
+    __device__ __forceinline__ void tap(int o, int k, uint4 const& v) {
+        __half2 const* f = reinterpret_cast<__half2 const*>(&v);
+        __half2 const* wk = reinterpret_cast<__half2 const*>(&w[k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[o][i] = __hfma2(f[i], wk[i], acc[o][i]);
+    }
+    __device__ __forceinline__ uint4 result(int o, bool) {
+        uint4 ov;
+        __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oh[i] = gelu_erf_h2(acc[o][i]);
+        return ov;
+    }
+};
+#endif
+
+template <int kStride, int kTX, int kC8, typename Acc, typename WeightT>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(act_t const* __restrict__ in, int H, int W, int Ho, int Wo, int xgroups,
+                                                        WeightT const* __restrict__ weight, float const* __restrict__ bias,
+                                                        int gelu, act_t* __restrict__ out) {
+    int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= xgroups * kC8) return;
+    int const c8 = t % kC8, xg = t / kC8;
+    int const oy = blockIdx.y, b = blockIdx.z;
+    int const ox0 = xg * kTX;
+    int const ix0 = ox0 * kStride - 1;
+    constexpr int kCols = (kTX - 1) * kStride + 3;
+    Acc acc;
+    acc.init(weight, bias, kC8 * 8, c8);
+    if (ix0 >= 0 && ix0 + kCols <= W) dwconv_rows<kStride, kTX, kC8, false>(in, H, W, b, oy, c8, ix0, acc);
+    else dwconv_rows<kStride, kTX, kC8, true>(in, H, W, b, oy, c8, ix0, acc);
+    uint4* orow = reinterpret_cast<uint4*>(out) + (((int64_t)b * Ho + oy) * Wo + ox0) * kC8 + c8;
+#pragma unroll
+    for (int o = 0; o < kTX; ++o) {
+        if (ox0 + o >= Wo) break;
+        orow[o * kC8] = acc.result(o, gelu != 0);
     }
 }
 
@@ -379,21 +433,36 @@ void im2col3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, 
     KERNEL_CHECK();
 }
 
+namespace {
+template <int kStride, int kC8>
+void launch_dwconv(cudaStream_t s, dim3 grid, act_t const* in, int H, int W, int Ho, int Wo, int xgroups, float const* weight,
+                   act_t const* weight16, float const* bias, bool gelu, act_t* out) {
+    constexpr int kTX = 4;
+#if !defined(DLIMG_B200_ACT_BF16)
+    static bool const acc32 = std::getenv("DLIMG_B200_DW_ACC32") != nullptr;  // A/B switch for parity experiments
+    if (gelu && weight16 && !acc32) {
+        dwconv3x3_kernel<kStride, kTX, kC8, DwAccH2<kTX>, act_t><<<grid, 256, 0, s>>>(in, H, W, Ho, Wo, xgroups, weight16, bias, 1, out);
+        return;
+    }
+#endif
+    (void)weight16;
+    dwconv3x3_kernel<kStride, kTX, kC8, DwAcc32<kTX>, float><<<grid, 256, 0, s>>>(in, H, W, Ho, Wo, xgroups, weight, bias, gelu ? 1 : 0, out);
+}
+}  // namespace
+
 void dwconv3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, float const* weight,
-               float const* bias, bool gelu, act_t* out) {
-    DLIMG_ASSERT(C % 8 == 0);
+               act_t const* weight16, float const* bias, bool gelu, act_t* out) {
     int const Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     DLIMG_ASSERT(stride == 1 || stride == 2);
-    constexpr int kTX = 4;
-    int const xgroups = ceil_div(Wo, kTX);
-    int64_t const total = (int64_t)batch * Ho * xgroups * (C / 8);
+    int const xgroups = ceil_div(Wo, 4);
     ProfScope prof(s, CAT_DWCONV, 2.0 * batch * Ho * Wo * C * 9, (double)batch * ((double)H * W + (double)Ho * Wo) * C * 2);
-    unsigned const grid = (unsigned)ceil_div64(total, 256);
-    if (stride == 1)
-        dwconv3x3_kernel<1, kTX><<<grid, 256, 0, s>>>(in, H, W, C / 8, Ho, Wo, xgroups, total, weight, bias, gelu ? 1 : 0, out);
-    else
-        dwconv3x3_kernel<2, kTX><<<grid, 256, 0, s>>>(in, H, W, C / 8, Ho, Wo, xgroups, total, weight, bias, gelu ? 1 : 0, out);
-    KERNEL_CHECK();
+    dim3 const grid((unsigned)ceil_div(xgroups * (C / 8), 256), (unsigned)Ho, (unsigned)batch);
+#define DLIMG_DW_CASE(S, CC) \
+    if (stride == S && C == CC) { launch_dwconv<S, CC / 8>(s, grid, in, H, W, Ho, Wo, xgroups, weight, weight16, bias, gelu, out); KERNEL_CHECK(); return; }
+    DLIMG_DW_CASE(1, 256) DLIMG_DW_CASE(2, 128) DLIMG_DW_CASE(2, 160) DLIMG_DW_CASE(1, 320)
+    DLIMG_DW_CASE(1, 128) DLIMG_DW_CASE(1, 160)
+#undef DLIMG_DW_CASE
+    fail("dwconv3x3: unsupported (stride, channels) = (" + std::to_string(stride) + ", " + std::to_string(C) + ")");
 }
 
 void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const* src_row, float const* gamma,

@@ -28,9 +28,10 @@ void conv1_preprocess(cudaStream_t s, ImageDesc const* imgs, int batch, int w, i
 // im2col for 3x3 / pad 1 convolutions on NHWC bf16: out[(b,oy,ox)][(ky,kx,c)] (K = 9*C).
 void im2col3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, act_t* out);
 
-// Depthwise 3x3 / pad 1, NHWC bf16, fp32 weights [9][C] + bias [C] (BN folded), optional GELU.
+// Depthwise 3x3 / pad 1, NHWC 16-bit, fp32 weights [9][C] + bias [C] (BN folded), optional GELU.  weight16 (optional):
+// the same filter in act_t; with fp16 storage the GELU'd convolutions then run in packed-half arithmetic.
 void dwconv3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, float const* weight,
-               float const* bias, bool gelu, act_t* out);
+               act_t const* weight16, float const* bias, bool gelu, act_t* out);
 
 // Row LayerNorm over C channels.  src_row (optional, length `rows`): gather index into `in`, -1 = the row
 // is window padding and the output is LN(0) = beta.  Output bf16 or fp32.

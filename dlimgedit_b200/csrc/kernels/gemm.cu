@@ -6,6 +6,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -16,11 +18,13 @@ namespace gemm {
 namespace {
 
 constexpr int kAStageBytes = kBlockM * kKBytes;     // 16 KiB
-constexpr int kBStageBytes = kMaxBlockN * kKBytes;  // 32 KiB
 constexpr int kEpiWarps = 16;                       // four per TMEM lane quarter; slabs of 16 columns are dealt round-robin
 constexpr int kNumThreads = 64 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;                      // two accumulator stages of up to 256 fp32 columns
-constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 256 /*barriers*/;
+// Output staging for the coalescing epilogue: 128 rows of up to 256 16-bit columns, rows padded by 16 bytes so that
+// the 16-byte shared-memory stores of 8 consecutive rows fall into distinct bank groups.
+constexpr int kStagePad = 16;
+
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(void const* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,20 +110,67 @@ struct EpiParams {
     int ldc;
 };
 
-// One 16-column slab of one accumulator row: bias -> residual -> activation -> store.
+__device__ __forceinline__ void add_bias16(float (&v)[16], float const* bias, int col) {
+    float4 const* b4 = reinterpret_cast<float4 const*>(bias + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 b = __ldg(b4 + i);
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+}
+
+// activation + conversion of 16 fp32 values to 16-bit storage (two 16-byte vectors)
+__device__ __forceinline__ void activate_pack16(float (&v)[16], int act, uint4 (&x)[2]) {
+    act2_t* h = reinterpret_cast<act2_t*>(x);
+#if !defined(DLIMG_B200_ACT_BF16)
+    if (act == ACT_GELU) {
+        // fp16 storage: round first, then the packed-half erf GELU (two values per instruction, see gelu.cuh)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = gelu_erf_h2(f22act2(v[2 * j], v[2 * j + 1]));
+        return;
+    }
+#endif
+    if (act == ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+    } else if (act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = f22act2(v[2 * j], v[2 * j + 1]);
+}
+
+// activation on 16 values already rounded to 16-bit storage
+__device__ __forceinline__ void activate_packed16(uint4 (&x)[2], int act) {
+    act2_t* h = reinterpret_cast<act2_t*>(x);
+    if (act == ACT_NONE) return;
+#if !defined(DLIMG_B200_ACT_BF16)
+    if (act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = gelu_erf_h2(h[j]);
+        return;
+    }
+#endif
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float2 f = act22f2(h[j]);
+#if defined(DLIMG_B200_ACT_BF16)
+        if (act == ACT_GELU) { f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); } else
+#endif
+        { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); }
+        h[j] = f22act2(f.x, f.y);
+    }
+}
+
+// One 16-column slab of one accumulator row, written by its own thread: bias -> residual -> activation -> store.
+// (Residual / row-scatter / fp32-output GEMMs; the wide 16-bit outputs take the staged path in the kernel.)
 __device__ __forceinline__ void epilogue_store16(uint32_t const (&r)[16], EpiParams const& ep, void* out, int64_t orow,
                                                  int col) {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-    if (ep.bias) {
-        float4 const* b4 = reinterpret_cast<float4 const*>(ep.bias + col);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 b = __ldg(b4 + i);
-            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-        }
-    }
+    if (ep.bias) add_bias16(v, ep.bias, col);
     if (ep.out_f32) {
         float* o = reinterpret_cast<float*>(out) + orow * ep.ldc + col;
         if (ep.residual) {
@@ -156,40 +207,54 @@ __device__ __forceinline__ void epilogue_store16(uint32_t const (&r)[16], EpiPar
                 }
             }
         }
-        if (ep.act == ACT_GELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-        } else if (ep.act == ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-        }
+        uint4 x[2];
+        activate_pack16(v, ep.act, x);
         uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            uint4 x;
-            act2_t* h = reinterpret_cast<act2_t*>(&x);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = f22act2(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
-            o4[i] = x;
-        }
+        o4[0] = x[0];
+        o4[1] = x[1];
     }
 }
 
-template <int kTF32>
+// Shared-memory plan (all sizes known on the host): [barriers | staging (kStaged) | stages x (A 16 KiB, B block_n*128 B)].
+// The stage count is whatever fits (up to kMaxStages): narrow-N GEMMs get deep rings (9 stages at block_n 64), which
+// they need because a stage then carries only 24 KiB towards the ~70 KiB per SM that HBM latency x bandwidth asks for.
+constexpr int kMaxStages = 10;
+constexpr int kBarrierBytes = 256;  // full[10], empty[10], tmem_full[2], tmem_empty[2], tmem slot
+constexpr int kSmemLimit = 227 * 1024;
+
+struct SmemPlan {
+    int stages, staging_bytes, total_bytes;
+};
+inline SmemPlan plan_smem(int block_n, bool staged) {
+    SmemPlan p;
+    p.staging_bytes = staged ? (int)round_up64((int64_t)kBlockM * (block_n * 2 + kStagePad), 1024) : 0;
+    int const stage_bytes = kAStageBytes + block_n * kKBytes;
+    int const fixed = 1024 /*align*/ + 1024 /*barriers, keeps the stages 1024-aligned*/ + p.staging_bytes;
+    p.stages = (kSmemLimit - fixed) / stage_bytes;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    p.total_bytes = fixed + p.stages * stage_bytes;
+    return p;
+}
+
+template <int kTF32, bool kStaged>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
-               int K, int block_n, void* out, EpiParams ep) {
+               int K, int block_n, int num_stages, int staging_bytes, void* out, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
     uint32_t const smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint32_t const a_base = smem_base;
-    uint32_t const b_base = smem_base + kStages * kAStageBytes;
-    uint32_t const bar_base = b_base + kStages * kBStageBytes;
-    // barrier slots (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
+    uint32_t const bar_base = smem_base;
+    uint32_t const stage_out = smem_base + 1024u;  // epilogue output staging (16-bit rows), kStaged only
+    uint32_t const ring_base = stage_out + (uint32_t)staging_bytes;
+    uint32_t const b_stage_bytes = (uint32_t)(block_n * kKBytes);
+    uint32_t const stage_bytes = kAStageBytes + b_stage_bytes;
+    auto a_stage = [&](int s) { return ring_base + (uint32_t)s * stage_bytes; };
+    auto b_stage = [&](int s) { return ring_base + (uint32_t)s * stage_bytes + kAStageBytes; };
+    // barrier slots (8 bytes each): full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], tmem ptr
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-    uint32_t const tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+    uint32_t const tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     int const warp = threadIdx.x >> 5;
@@ -205,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < num_stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -230,16 +295,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t const tx_bytes = (uint32_t)(kAStageBytes + block_n * kKBytes);
+            uint32_t const tx_bytes = stage_bytes;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int const m0 = (tile / n_tiles) * kBlockM;
                 int const n0 = (tile % n_tiles) * block_n;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), tx_bytes);
-                    tma_load_2d(a_base + stage * kAStageBytes, &tma_a, full_bar(stage), kb * elems_per_kb, m0);
-                    tma_load_2d(b_base + stage * kBStageBytes, &tma_b, full_bar(stage), kb * elems_per_kb, n0);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    tma_load_2d(a_stage(stage), &tma_a, full_bar(stage), kb * elems_per_kb, m0);
+                    tma_load_2d(b_stage(stage), &tma_b, full_bar(stage), kb * elems_per_kb, n0);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -264,44 +329,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     tc_fence_after();
                     int const valid_bytes = min(kKBytes, (K - kb * elems_per_kb) * elem_bytes);
                     int const n_instr = (valid_bytes + 31) >> 5;
-                    uint64_t const adesc = make_smem_desc(a_base + stage * kAStageBytes);
-                    uint64_t const bdesc = make_smem_desc(b_base + stage * kBStageBytes);
+                    uint64_t const adesc = make_smem_desc(a_stage(stage));
+                    uint64_t const bdesc = make_smem_desc(b_stage(stage));
                     for (int k = 0; k < n_instr; ++k) {
                         // advance 32 bytes of K inside the swizzle atom: +2 in the 16-byte address field
                         tc_mma<kTF32>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                       (uint32_t)((kb | k) != 0));
                     }
                     tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == num_stages) { stage = 0; phase ^= 1u; }
                 }
                 tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
             }
         }
     } else {
-        // ---------------- epilogue (8 warps; TMEM lane quarter = warp index mod 4, column slabs interleaved) -------
+        // ---------------- epilogue (16 warps; TMEM lane quarter = warp index mod 4, 16-column slabs dealt cyclically)
+        // The slabs of a tile are software-pipelined: the tcgen05.ld of slab k+1 is in flight while slab k is biased,
+        // activated and written (TMEM reads are ~64 B/clk/SM, i.e. ~2000 clk for a 128x256 fp32 tile: they have to
+        // overlap the arithmetic), and the accumulator stage is handed back to the MMA warp as soon as the last
+        // slab has landed in registers.  kStaged (plain 16-bit outputs): rows are staged in shared memory per lane
+        // quarter and written by the quarter's 128 threads as whole contiguous rows.
         int const quarter = warp & 3;
         int const slab = (warp - 2) >> 2;  // which of the kEpiWarps/4 warps of this lane quarter
+        constexpr int kSlabStride = (kEpiWarps / 4) * 16;
+        constexpr int kMaxSlabs = kMaxBlockN / kSlabStride;  // 4
+        uint32_t const pitch = (uint32_t)(block_n * 2 + kStagePad);
+        uint32_t const my_row = stage_out + (uint32_t)(quarter * 32 + lane) * pitch;
+        // cooperative store geometry: chunks of 16 bytes, cpr per row, 128 threads per quarter
+        int const cpr = block_n >> 3;
+        int const tq = slab * 32 + lane;
+        int const st_row0 = tq / cpr, st_chunk = tq - st_row0 * cpr, st_rows = 128 / cpr;
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int const acc = local & 1;
             uint32_t const acc_phase = (uint32_t)(local >> 1) & 1u;
             int const m0 = (tile / n_tiles) * kBlockM;
             int const n0 = (tile % n_tiles) * block_n;
+            int64_t orow = -1;
+            if (!kStaged) {
+                int const row = m0 + quarter * 32 + lane;
+                if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
+            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            int const row = m0 + quarter * 32 + lane;
-            int64_t orow = -1;
-            if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
             uint32_t const taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN);
-            for (int c = slab * 16; c < block_n; c += (kEpiWarps / 4) * 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + (uint32_t)c, r);
-                tmem_ld_wait();
-                if (orow >= 0) epilogue_store16(r, ep, out, orow, n0 + c);
+            uint32_t r[2][16];
+            if (slab * 16 < block_n) {
+                tmem_ld16(taddr + (uint32_t)(slab * 16), r[0]);
+            } else {  // narrow tiles (block_n < 64): this warp owns no slab
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+#pragma unroll
+            for (int k = 0; k < kMaxSlabs; ++k) {
+                int const c = slab * 16 + k * kSlabStride;
+                if (c < block_n) {
+                    tmem_ld_wait();  // slab k is in r[k & 1]
+                    if (k + 1 < kMaxSlabs && c + kSlabStride < block_n) {
+                        tmem_ld16(taddr + (uint32_t)(c + kSlabStride), r[(k + 1) & 1]);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));  // all of this warp's slabs are out of TMEM
+                    }
+                    if (kStaged) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
+                        if (ep.bias) add_bias16(v, ep.bias, n0 + c);
+                        uint4 x[2];
+                        activate_pack16(v, ep.act, x);
+                        uint32_t const dst = my_row + (uint32_t)c * 2u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x[0].x), "r"(x[0].y), "r"(x[0].z), "r"(x[0].w) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
+                    } else if (orow >= 0) {
+                        epilogue_store16(r[k & 1], ep, out, orow, n0 + c);
+                    }
+                }
+            }
+            if (kStaged) {
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+                if (st_row0 < st_rows) {
+                    for (int rr = st_row0; rr < 32; rr += st_rows) {
+                        int const grow = m0 + quarter * 32 + rr;
+                        if (grow < M) {
+                            uint4 x;
+                            uint32_t const src = stage_out + (uint32_t)(quarter * 32 + rr) * pitch + (uint32_t)st_chunk * 16u;
+                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(src));
+                            *reinterpret_cast<uint4*>(reinterpret_cast<act_t*>(out) + (int64_t)grow * ep.ldc + n0 + st_chunk * 8) = x;
+                        }
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");  // staging rows reusable
+            }
         }
     }
 
@@ -464,11 +585,21 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
     int const grid = tiles < num_sms ? tiles : num_sms;
     static std::once_flag once;
     std::call_once(once, [] {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     });
-    if (tf32) gemm_tc_kernel<1><<<grid, kNumThreads, kSmemBytes, stream>>>(ma, mb, M, N, K, block_n, out, ep);
-    else gemm_tc_kernel<0><<<grid, kNumThreads, kSmemBytes, stream>>>(ma, mb, M, N, K, block_n, out, ep);
+    // plain 16-bit outputs go through the coalescing (staged) epilogue; residual / scatter / fp32 outputs store directly
+    static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch
+    bool const staged = allow_staged && !tf32 && !ep.residual && !ep.row_map && !ep.out_f32 && block_n >= 64;
+    SmemPlan const sp = plan_smem(block_n, staged);
+    DLIMG_ASSERT(sp.stages >= 2);
+    if (tf32)
+        gemm_tc_kernel<1, false><<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep);
+    else if (staged)
+        gemm_tc_kernel<0, true><<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep);
+    else
+        gemm_tc_kernel<0, false><<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep);
     KERNEL_CHECK();
 }
 

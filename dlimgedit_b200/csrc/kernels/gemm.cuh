@@ -2,7 +2,7 @@
 //
 // Both operands are K-major (activations: rows = tokens; weights: rows = output features, exactly the
 // nn.Linear / 1x1-conv layout).  The kernel is a persistent, warp-specialised sm_100a pipeline:
-//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128-byte swizzle, 4-stage mbarrier ring)
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128-byte swizzle, mbarrier ring as deep as fits)
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128, N=block_n, fp32 accumulators in TMEM,
 //                               two accumulator stages so the epilogue of tile i overlaps tile i+1)
 //   warps 2..17 epilogue       (tcgen05.ld -> bias / residual / activation -> bf16|fp32 global stores,
@@ -38,7 +38,6 @@ struct Operand {
 };
 
 constexpr int kBlockM = 128;
-constexpr int kStages = 4;
 constexpr int kMaxBlockN = 256;
 constexpr int kKBytes = 128;  // bytes of K per row per stage == swizzle span
 

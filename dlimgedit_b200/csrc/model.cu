@@ -70,6 +70,7 @@ DwConv load_dw_bn(WeightFile const& wf, std::string const& p, int c) {
     DwConv d;
     d.c = c;
     d.w.upload(o);
+    d.w16.upload(to_act(o));
     d.b.upload(shift);
     return d;
 }
@@ -381,7 +382,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
     for (int i = 0; i < 2; ++i) {
         MBConvW const& m = enc_.mb[i];
         gemm16(s, x, B * 65536, m.conv1, ws.big[0].get(), ACT_GELU, nullptr, nullptr);
-        enc::dwconv3x3(s, ws.big[0].get(), batch, 256, 256, 256, 1, m.conv2.w.get(), m.conv2.b.get(), true, ws.big[1].get());
+        enc::dwconv3x3(s, ws.big[0].get(), batch, 256, 256, 256, 1, m.conv2.w.get(), m.conv2.w16.get(), m.conv2.b.get(), true, ws.big[1].get());
         gemm16(s, ws.big[1].get(), B * 65536, m.conv3, y, ACT_GELU, x, nullptr);
         std::swap(x, y);
         tap_act(s, tap, i == 0 ? "mb0" : "mb1", x, (size_t)B * 65536 * 64);
@@ -391,8 +392,8 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         int const out_res = m.stride == 2 ? res / 2 : res;
         int const dout = m.conv1.n;
         gemm16(s, x, B * res * res, m.conv1, ws.big[0].get(), ACT_GELU, nullptr, nullptr);
-        enc::dwconv3x3(s, ws.big[0].get(), batch, res, res, dout, m.stride, m.conv2.w.get(), m.conv2.b.get(), true,
-                       ws.big[1].get());
+        enc::dwconv3x3(s, ws.big[0].get(), batch, res, res, dout, m.stride, m.conv2.w.get(), m.conv2.w16.get(), m.conv2.b.get(),
+                       true, ws.big[1].get());
         gemm16(s, ws.big[1].get(), B * out_res * out_res, m.conv3, y, ACT_NONE, nullptr, nullptr);
         std::swap(x, y);
         tap_act(s, tap, name, x, (size_t)B * out_res * out_res * dout);
@@ -418,7 +419,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
             gemm16(s, ws.big[2].get(), wrows, b.proj, x, ACT_NONE, x, map);
             tap_act(s, tap, (tn + ".proj").c_str(), x, (size_t)B * L * C);
             // local depthwise conv (no activation, no residual)
-            enc::dwconv3x3(s, x, batch, c.res, c.res, C, 1, b.local_conv.w.get(), b.local_conv.b.get(), false, y);
+            enc::dwconv3x3(s, x, batch, c.res, c.res, C, 1, b.local_conv.w.get(), nullptr, b.local_conv.b.get(), false, y);
             tap_act(s, tap, (tn + ".lc").c_str(), y, (size_t)B * L * C);
             // MLP branch
             enc::layernorm_rows(s, y, (int)(B * L), C, nullptr, b.mlp_norm.g.get(), b.mlp_norm.b.get(), 1e-5f, ws.big[0].get(), false);

@@ -63,8 +63,9 @@ struct Linear32 {  // fp32 weight (N, K) + bias -- decoder
     DeviceBuffer<float> b;
     int n = 0, k = 0;
 };
-struct DwConv {  // depthwise 3x3: weight (9, C) fp32, bias (C)
+struct DwConv {  // depthwise 3x3: weight (9, C) fp32 (+ the same in act_t), bias (C)
     DeviceBuffer<float> w, b;
+    DeviceBuffer<act_t> w16;
     int c = 0;
 };
 struct Norm {
