@@ -145,13 +145,17 @@ class _Debug(ctypes.Structure):
         ("act_is_bf16", ctypes.c_uint32),
         ("gemm", _F(_R, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
-                    ctypes.c_int, ctypes.c_void_p)),
+                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)),
         ("encode_tap", _F(_R, _H, ctypes.POINTER(_ImageView), ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p,
                           ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t))),
         ("resize_plan", _F(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i32p, c_f32p)),
         ("srgb_tables", _F(None, c_f32p, c_f32p)),
-        ("window_attention", _F(_R, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                ctypes.c_void_p, ctypes.c_void_p)),
+        ("window_attention", _F(_R, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)),
+        ("window_attention_simt", _F(_R, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p)),
+        ("layernorm_stats", _F(_R, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                               ctypes.c_void_p)),
     ]
 
 

@@ -198,7 +198,8 @@ dlimg_b200_Ext ext_;
 using DebugApi = dlimg_b200_Debug;
 
 dlimg_Result dbg_gemm(void* stream, int tf32, int simt, void const* a, void const* b, int M, int N, int K, float const* bias,
-                      void const* residual, int const* row_map, int act, int out_f32, void* out) {
+                      void const* residual, int const* row_map, int act, int out_f32, void* out, float const* ln_stats,
+                      float const* ln_colsum) {
     return try_([=] {
         gemm::Operand A{a, M, K, K}, B{b, N, K, K};
         gemm::Epilogue e;
@@ -208,6 +209,8 @@ dlimg_Result dbg_gemm(void* stream, int tf32, int simt, void const* a, void cons
         e.act = act;
         e.out_f32 = out_f32;
         e.ldc = N;
+        e.ln_stats = reinterpret_cast<float2 const*>(ln_stats);
+        e.ln_colsum = ln_colsum;
         int dev = 0;
         CUDA_CHECK(cudaGetDevice(&dev));
         cudaDeviceProp prop;
@@ -242,21 +245,38 @@ void dbg_srgb_tables(float* decode256, float* threshold256) {
     std::memcpy(threshold256, t.encode_threshold, sizeof(t.encode_threshold));
 }
 
-dlimg_Result dbg_window_attention(void* stream, int simt, void const* qkv, int windows, int n, int heads, float const* bias,
-                                  void* out) {
+dlimg_Result dbg_window_attention(void* stream, void const* qkv, int batch, int res, int ws, int heads, void const* pad_qkv,
+                                  float const* bias, void* out) {
     return try_([=] {
         auto s = static_cast<cudaStream_t>(stream);
-        if (simt) {
-            enc::window_attention_simt(s, static_cast<act_t const*>(qkv), windows, n, heads, bias, static_cast<act_t*>(out));
-        } else {  // re-order the dense (heads, n, n) table for the tensor-core kernel
-            std::vector<float> dense((size_t)heads * n * n), frag(enc::attention_bias_fragment_floats(heads, n));
-            CUDA_CHECK(cudaMemcpy(dense.data(), bias, dense.size() * sizeof(float), cudaMemcpyDeviceToHost));
-            enc::attention_bias_fragments(dense.data(), heads, n, frag.data());
-            DeviceBuffer<float> dfrag;
-            dfrag.upload(frag);
-            enc::window_attention(s, static_cast<act_t const*>(qkv), windows, n, heads, dfrag.get(), static_cast<act_t*>(out));
-            CUDA_CHECK(cudaStreamSynchronize(s));
-        }
+        int const n = ws * ws;
+        // re-order the dense (heads, n, n) table for the tensor-core kernel
+        std::vector<float> dense((size_t)heads * n * n);
+        std::vector<uint16_t> frag(enc::attention_bias_fragment_count(heads, ws));
+        CUDA_CHECK(cudaMemcpy(dense.data(), bias, dense.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        enc::attention_bias_fragments(dense.data(), heads, ws, frag.data());
+        DeviceBuffer<uint16_t> dfrag;
+        dfrag.upload(frag);
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+        enc::window_attention(s, static_cast<act_t const*>(qkv), batch, res, ws, heads, static_cast<act_t const*>(pad_qkv),
+                              dfrag.get(), static_cast<act_t*>(out), prop.multiProcessorCount);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    });
+}
+
+dlimg_Result dbg_window_attention_simt(void* stream, void const* qkv, int windows, int n, int heads, float const* bias, void* out) {
+    return try_([=] {
+        enc::window_attention_simt(static_cast<cudaStream_t>(stream), static_cast<act_t const*>(qkv), windows, n, heads, bias,
+                                   static_cast<act_t*>(out));
+    });
+}
+
+dlimg_Result dbg_layernorm_stats(void* stream, void const* in, int rows, int C, float eps, float* out) {
+    return try_([=] {
+        enc::layernorm_stats(static_cast<cudaStream_t>(stream), static_cast<act_t const*>(in), rows, C, eps, reinterpret_cast<float2*>(out));
     });
 }
 
@@ -316,6 +336,8 @@ DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void) {
     debug_.resize_plan = dbg_resize_plan;
     debug_.srgb_tables = dbg_srgb_tables;
     debug_.window_attention = dbg_window_attention;
+    debug_.window_attention_simt = dbg_window_attention_simt;
+    debug_.layernorm_stats = dbg_layernorm_stats;
     return &debug_;
 }
 

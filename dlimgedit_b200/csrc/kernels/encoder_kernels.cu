@@ -318,6 +318,57 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(act_t const* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row statistics for the LayerNorms folded into GEMM epilogues: one warp per kStatRows rows, 16-byte loads, all
+// rows' loads issued before the first reduction, two-pass (mean, then centred variance) in registers.
+constexpr int kStatRows = 4;
+constexpr int kStatChunks = 2;  // 16-byte chunks per lane per row: C <= 512
+
+__global__ void __launch_bounds__(256) layernorm_stats_kernel(act_t const* __restrict__ in, int rows, int C8, float eps,
+                                                              float2* __restrict__ out) {
+    int const warp = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    int const row0 = warp * kStatRows;
+    if (row0 >= rows) return;
+    uint4 v[kStatRows][kStatChunks];
+#pragma unroll
+    for (int r = 0; r < kStatRows; ++r)
+#pragma unroll
+        for (int c = 0; c < kStatChunks; ++c) {
+            int const ch = lane + 32 * c;
+            v[r][c] = (row0 + r < rows && ch < C8) ? __ldg(reinterpret_cast<uint4 const*>(in) + (int64_t)(row0 + r) * C8 + ch)
+                                                   : make_uint4(0, 0, 0, 0);
+        }
+    float const inv_c = 1.0f / (float)(C8 * 8);
+#pragma unroll
+    for (int r = 0; r < kStatRows; ++r) {
+        float f[kStatChunks][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < kStatChunks; ++c) {
+            unpack8(v[r][c], f[c]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum += f[c][i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        float const mean = sum * inv_c;
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < kStatChunks; ++c) {
+            if (lane + 32 * c < C8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float const d = f[c][i] - mean;
+                    var = fmaf(d, d, var);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        if (lane == 0 && row0 + r < rows) out[row0 + r] = make_float2(mean, rsqrtf(var * inv_c + eps));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int kAttnWarps = 8;
 constexpr int kAttnMaxJ = 7;  // n <= 224 keys
 
@@ -470,6 +521,13 @@ void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const*
     DLIMG_ASSERT(C % 2 == 0 && C <= kLnMaxPairs * 64);
     ProfScope prof(s, CAT_LAYERNORM, 0, (double)rows * C * (2 + (out_f32 ? 4 : 2)));
     layernorm_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(in, rows, C, src_row, gamma, beta, eps, out, out_f32 ? 1 : 0);
+    KERNEL_CHECK();
+}
+
+void layernorm_stats(cudaStream_t s, act_t const* in, int rows, int C, float eps, float2* out) {
+    DLIMG_ASSERT(C % 8 == 0 && C / 8 <= 32 * kStatChunks);
+    ProfScope prof(s, CAT_LAYERNORM, 0, (double)rows * (C * 2 + 8));
+    layernorm_stats_kernel<<<ceil_div(rows, 8 * kStatRows), 256, 0, s>>>(in, rows, C / 8, eps, out);
     KERNEL_CHECK();
 }
 

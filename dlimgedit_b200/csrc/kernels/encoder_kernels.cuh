@@ -38,19 +38,24 @@ void dwconv3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, 
 void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const* src_row, float const* gamma,
                     float const* beta, float eps, void* out, bool out_f32);
 
-// Windowed multi-head attention, head_dim 32.  qkv: (windows*n, heads*96) with per-head [q|k|v];
-// out: (windows*n, heads*32).  bias: relative-position bias already gathered from attention_biases, in the
-// tensor-core accumulator order produced by attention_bias_fragments() below.
-void window_attention(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out);
-// n rounded up to the tile the kernel is instantiated for (49 -> 64, 196 -> 208).
-inline int window_pad(int n) { return n <= 64 ? 64 : 208; }
-// Number of floats of the fragment-ordered bias table for `heads` heads.
-inline size_t attention_bias_fragment_floats(int heads, int n) { return (size_t)heads * window_pad(n) * window_pad(n); }
-// dense (heads, n, n) -> [head][query tile (n_pad/16)][key block (n_pad/8)][lane (32)][4]; for lane = 4*g + t the
-// four values are (row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1) of the 16 x 8 block; padded key columns
-// hold -inf (which masks them in the softmax), padded query rows 0.
-void attention_bias_fragments(float const* dense, int heads, int n, float* out);
-// CUDA-core version of the same op, dense (heads, n, n) bias (cross-check in tests).
+// Per-row LayerNorm statistics (mean, 1/sqrt(var + eps)) of (rows, C) 16-bit activations.  The normalisation itself
+// is folded into the GEMM that consumes the row (gemm.cuh, Epilogue::ln_stats), so no normalised copy is written.
+void layernorm_stats(cudaStream_t s, act_t const* in, int rows, int C, float eps, float2* out);
+
+// Windowed multi-head attention, head_dim 32, on the un-partitioned token grid.  qkv: (batch*res*res, heads*96) with
+// per-head [q|k|v]; out: (batch*res*res, heads*32).  Windows are ws x ws over the grid zero-padded to a multiple of
+// ws; padded positions use pad_qkv (heads*96), the projection of LN(0).  bias_frag: relative-position bias from
+// attention_bias_fragments().
+void window_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int ws, int heads, act_t const* pad_qkv,
+                      uint16_t const* bias_frag, act_t* out, int num_sms);
+// Number of fp16 values of the fragment-ordered bias table.
+size_t attention_bias_fragment_count(int heads, int ws);
+// dense (heads, n, n) fp32 -> fp16 [head][query tile (16)][key block (8)][lane (32)][4], values scaled by log2(e); for
+// lane = 4*g + t the four values are (row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1) of the 16 x 8 block; key columns
+// beyond n hold -inf (which masks them in the softmax), query rows beyond n hold 0.
+void attention_bias_fragments(float const* dense, int heads, int ws, uint16_t* out);
+// CUDA-core reference of the attention core on already partitioned windows, dense (heads, n, n) fp32 bias; qkv
+// (windows*n, heads*96) -> out (windows*n, heads*32).  Cross-check in tests.
 void window_attention_simt(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out);
 
 // (tokens, C) fp32 -> (C, tokens) fp32 per image: the reference's NCHW `image_embeddings` layout.

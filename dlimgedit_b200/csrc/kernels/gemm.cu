@@ -105,6 +105,8 @@ struct EpiParams {
     float const* bias;
     void const* residual;
     int const* row_map;
+    float2 const* ln_stats;
+    float const* ln_colsum;
     int act;
     int out_f32;
     int ldc;
@@ -116,6 +118,20 @@ __device__ __forceinline__ void add_bias16(float (&v)[16], float const* bias, in
     for (int i = 0; i < 4; ++i) {
         float4 b = __ldg(b4 + i);
         v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+}
+
+// folded LayerNorm: v = rstd * acc + (bias - mean * rstd * colsum), see Epilogue::ln_stats
+__device__ __forceinline__ void ln_bias16(float (&v)[16], float const* bias, float const* colsum, int col, float rstd, float nmr) {
+    float4 const* b4 = reinterpret_cast<float4 const*>(bias + col);
+    float4 const* c4 = reinterpret_cast<float4 const*>(colsum + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 const b = __ldg(b4 + i), c = __ldg(c4 + i);
+        v[4 * i + 0] = fmaf(v[4 * i + 0], rstd, fmaf(nmr, c.x, b.x));
+        v[4 * i + 1] = fmaf(v[4 * i + 1], rstd, fmaf(nmr, c.y, b.y));
+        v[4 * i + 2] = fmaf(v[4 * i + 2], rstd, fmaf(nmr, c.z, b.z));
+        v[4 * i + 3] = fmaf(v[4 * i + 3], rstd, fmaf(nmr, c.w, b.w));
     }
 }
 
@@ -366,9 +382,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             int const m0 = (tile / n_tiles) * kBlockM;
             int const n0 = (tile % n_tiles) * block_n;
             int64_t orow = -1;
+            float rstd = 1.f, nmr = 0.f;  // folded LayerNorm: 1/std and -mean/std of this thread's row
             if (!kStaged) {
                 int const row = m0 + quarter * 32 + lane;
                 if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
+            } else if (ep.ln_stats) {
+                int const row = m0 + quarter * 32 + lane;
+                if (row < M) {
+                    float2 const st = __ldg(ep.ln_stats + row);
+                    rstd = st.y;
+                    nmr = -st.x * st.y;
+                }
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -397,7 +421,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
-                        if (ep.bias) add_bias16(v, ep.bias, n0 + c);
+                        if (ep.ln_stats) ln_bias16(v, ep.bias, ep.ln_colsum, n0 + c, rstd, nmr);
+                        else if (ep.bias) add_bias16(v, ep.bias, n0 + c);
                         uint4 x[2];
                         activate_pack16(v, ep.act, x);
                         uint32_t const dst = my_row + (uint32_t)c * 2u;
@@ -474,6 +499,10 @@ __global__ void gemm_simt_kernel(T const* __restrict__ A, int64_t lda, T const* 
         int64_t const orow = ep.row_map ? (int64_t)ep.row_map[m] : (int64_t)m;
         if (orow < 0) continue;
         float v = acc[i];
+        if (ep.ln_stats) {
+            float2 const st = ep.ln_stats[m];
+            v = st.y * (v - st.x * ep.ln_colsum[n]);
+        }
         if (ep.bias) v += ep.bias[n];
         int64_t const o = orow * ep.ldc + n;
         if (ep.residual)
@@ -554,6 +583,8 @@ EpiParams to_params(Epilogue const& e, int N) {
     p.bias = e.bias;
     p.residual = e.residual;
     p.row_map = e.row_map;
+    p.ln_stats = e.ln_stats;
+    p.ln_colsum = e.ln_colsum;
     p.act = e.act;
     p.out_f32 = e.out_f32;
     p.ldc = e.ldc ? e.ldc : N;
@@ -592,6 +623,8 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
     // plain 16-bit outputs go through the coalescing (staged) epilogue; residual / scatter / fp32 outputs store directly
     static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch
     bool const staged = allow_staged && !tf32 && !ep.residual && !ep.row_map && !ep.out_f32 && block_n >= 64;
+    if (ep.ln_stats && (!staged || !ep.bias || !ep.ln_colsum))
+        fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue), a bias and column sums");
     SmemPlan const sp = plan_smem(block_n, staged);
     DLIMG_ASSERT(sp.stages >= 2);
     if (tf32)

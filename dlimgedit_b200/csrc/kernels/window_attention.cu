@@ -1,16 +1,25 @@
-// window_attention.cu -- TinyViT windowed attention (49- or 196-token windows, head_dim 32) on tensor cores.
+// window_attention.cu -- TinyViT windowed attention (7x7 or 14x14 windows, head_dim 32) on tensor cores.
 //
-// One CTA per (window, head).  Q, K and V^T of that head sit in shared memory as 16-bit values; each warp
-// owns 16-query tiles: S = Q K^T with mma.sync m16n8k16 (fp32 accumulators, whole S row block in registers),
-// learned relative-position bias + softmax in registers (quad shuffles), P re-used in place as the A operand
-// of O = P V.  These windows are far below a 128-row tcgen05 tile (SURVEY section 7 "hard parts"), and the
-// attention core is only ~3-19 % of a stage's MACs, so the legacy warp-level MMA is the right tool here; the
-// tcgen05 kernel (gemm.cu) carries the QKV / proj / MLP GEMMs around it.
+// Input is the QKV projection of the UN-partitioned token grid, (B*res*res, heads*96) with per-head [q|k|v]; the
+// kernel does the window partition itself: a CTA gathers the tokens of one window (for a group of kHG heads) with
+// cp.async, positions that fall outside the image (TinyViT zero-pads the grid to a multiple of the window BEFORE the
+// in-attention LayerNorm and does NOT mask them) get the constant projection of LN(0) = beta, and the
+// result is scattered straight back to token order.  So neither a partitioned copy of the activations nor the QKV
+// rows of padding tokens ever exist in HBM.
+//
+// CTAs are persistent over (window, head group) items with a fixed head group, so the relative-position bias of
+// those heads is staged once (fp16, already in mma accumulator-fragment order and scaled by log2 e) and the next
+// item's tokens stream in (double buffer) while the current one is computed.  One warp per (head, 16-query tile):
+// S = Q K^T with mma.sync m16n8k16 fed by ldmatrix, online softmax over chunks of 64 keys in registers (exp2), P
+// re-used in place as the A operand of O += P V (V through ldmatrix.trans, no transposed copy).  These windows are far
+// below a 128-row tcgen05 tile and the attention core is 3-19 % of a stage's MACs, so the warp-level
+// MMA is the right tool; the kernel is bound by instruction issue, which is what this structure minimises.
 #include "encoder_kernels.cuh"
 
 #include "../profiler.hpp"
 
 #include <cmath>
+#include <cuda_fp16.h>
 
 namespace dlimg {
 namespace enc {
@@ -29,179 +38,288 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 #endif
 }
-
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     act2_t const v = f22act2(a, b);
     return *reinterpret_cast<uint32_t const*>(&v);
 }
+__device__ __forceinline__ uint32_t smem_u32(void const* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-constexpr int kWarps = 4;
-constexpr int kQKStride = 40;  // 16-bit elements per Q / K row (32 + 8 padding: conflict-free fragment loads)
+template <int kWS, int kHG>
+struct Cfg {
+    static constexpr int n = kWS * kWS;          // tokens per window: 49 / 196
+    static constexpr int NQ = (n + 15) / 16;     // 16-query tiles: 4 / 13
+    static constexpr int NK8 = (n + 7) / 8;      // 8-key blocks: 7 / 25
+    static constexpr int NKP = NQ * 16;          // token rows held in shared memory: 64 / 208
+    static constexpr int kWarps = kHG * NQ;      // one warp per (head, query tile)
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kRowBytes = kHG * 192 + 16;  // [q|k|v] of kHG heads + 16 B: rows land in distinct bank groups
+    static constexpr int kTileBytes = NKP * kRowBytes;
+    static constexpr int kBiasBytes = kHG * NQ * NK8 * 32 * 8;
+    static constexpr int kSmemBytes = kBiasBytes + 2 * kTileBytes;
+    static constexpr int kCPT = kHG * 12;        // 16-byte chunks per token
+};
 
-// kNPad: window tokens rounded up to a multiple of 16 (49 -> 64, 196 -> 208)
-template <int kNPad>
-__global__ void __launch_bounds__(kWarps * 32) window_attention_mma_kernel(act_t const* __restrict__ qkv, int n, int heads,
-                                                                           float const* __restrict__ bias,
-                                                                           act_t* __restrict__ out) {
-    constexpr int kVStride = kNPad + 8;  // 16-bit elements per V^T row
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    act_t* Qs = reinterpret_cast<act_t*>(smem_raw);  // [kNPad][kQKStride]
-    act_t* Ks = Qs + kNPad * kQKStride;              // [kNPad][kQKStride]
-    act_t* Vt = Ks + kNPad * kQKStride;              // [32][kVStride]
-
-    int const win = blockIdx.x / heads, h = blockIdx.x % heads;
-    int const ld = heads * 96, C = heads * 32;
-    int64_t const row0 = (int64_t)win * n;
-    int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int const g = lane >> 2, t = lane & 3;
-
-    // ---- stage Q, K (row-major) and V (transposed) of this head; padded tokens are zero ----
-    for (int i = tid; i < kNPad * 12; i += kWarps * 32) {
-        int const j = i / 12, part = i % 12;  // 12 x 16-byte chunks per token: 4 of q, 4 of k, 4 of v
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (j < n) v = *reinterpret_cast<uint4 const*>(qkv + (row0 + j) * ld + h * 96 + part * 8);
-        if (part < 4) {
-            *reinterpret_cast<uint4*>(Qs + j * kQKStride + part * 8) = v;
-        } else if (part < 8) {
-            *reinterpret_cast<uint4*>(Ks + j * kQKStride + (part - 4) * 8) = v;
-        } else {
-            act_t const* e = reinterpret_cast<act_t const*>(&v);
-            int const d0 = (part - 8) * 8;
+// One chunk of kCnt key blocks (8 keys each) of the online softmax for one (head, query tile).
+template <int kCnt, bool kFirst>
+__device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4], uint32_t k_addr, uint32_t v_addr, int row_bytes,
+                                             uint32_t bias_addr, float (&m)[2], float (&l)[2], float (&o)[4][4]) {
+    float const kScale = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
+    float s[kCnt][4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) Vt[(d0 + k) * kVStride + j] = e[k];
+    for (int j = 0; j < kCnt; ++j) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(k_addr + (uint32_t)((nb0 + j) * 8 * row_bytes), b0, b1, b2, b3);
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        mma16816(s[j], aq[0][0], aq[0][1], aq[0][2], aq[0][3], b0, b1);
+        mma16816(s[j], aq[1][0], aq[1][1], aq[1][2], aq[1][3], b2, b3);
+    }
+    float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kCnt; ++j) {
+        uint32_t w0, w1;
+        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(bias_addr + (uint32_t)((nb0 + j) * 256)));
+        float2 const f0 = __half22float2(*reinterpret_cast<__half2 const*>(&w0));
+        float2 const f1 = __half22float2(*reinterpret_cast<__half2 const*>(&w1));
+        s[j][0] = fmaf(s[j][0], kScale, f0.x);
+        s[j][1] = fmaf(s[j][1], kScale, f0.y);
+        s[j][2] = fmaf(s[j][2], kScale, f1.x);
+        s[j][3] = fmaf(s[j][3], kScale, f1.y);
+        cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
+        cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+    }
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+    if (kFirst) {
+        m[0] = cm0;
+        m[1] = cm1;
+    } else {  // every chunk holds at least one unmasked key, so the running maxima are finite from chunk 0 on
+        float const n0 = fmaxf(m[0], cm0), n1 = fmaxf(m[1], cm1);
+        float const a0 = ex2(m[0] - n0), a1 = ex2(m[1] - n1);
+        m[0] = n0;
+        m[1] = n1;
+        l[0] *= a0;
+        l[1] *= a1;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            o[d][0] *= a0; o[d][1] *= a0;
+            o[d][2] *= a1; o[d][3] *= a1;
         }
     }
-    __syncthreads();
-
-    float const scale = 0.17677669529663687f;  // 32^-0.5
-    // bias is pre-arranged in accumulator-fragment order: [head][query tile][key block][lane] x float4
-    float4 const* bias_h = reinterpret_cast<float4 const*>(bias) + (size_t)h * (kNPad / 16) * (kNPad / 8) * 32;
-    uint32_t const* Qw = reinterpret_cast<uint32_t const*>(Qs);
-    uint32_t const* Kw = reinterpret_cast<uint32_t const*>(Ks);
-    uint32_t const* Vw = reinterpret_cast<uint32_t const*>(Vt);
-
-    for (int qt = warp; qt * 16 < n; qt += kWarps) {
-        int const r0 = qt * 16 + g, r1 = r0 + 8;  // the two query rows this thread holds
-        // Q fragments for the two 16-wide k steps
-        uint32_t aq[2][4];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            aq[ks][0] = Qw[(r0 * kQKStride + ks * 16 + 2 * t) >> 1];
-            aq[ks][1] = Qw[(r1 * kQKStride + ks * 16 + 2 * t) >> 1];
-            aq[ks][2] = Qw[(r0 * kQKStride + ks * 16 + 8 + 2 * t) >> 1];
-            aq[ks][3] = Qw[(r1 * kQKStride + ks * 16 + 8 + 2 * t) >> 1];
+    for (int j = 0; j < kCnt; ++j) {
+        s[j][0] = ex2(s[j][0] - m[0]);
+        s[j][1] = ex2(s[j][1] - m[0]);
+        s[j][2] = ex2(s[j][2] - m[1]);
+        s[j][3] = ex2(s[j][3] - m[1]);
+        l[0] += s[j][0] + s[j][1];
+        l[1] += s[j][2] + s[j][3];
+    }
+    // O += P V, 16 keys per step; an odd trailing key block pairs with zeros
+#pragma unroll
+    for (int kb = 0; kb < (kCnt + 1) / 2; ++kb) {
+        uint32_t const a0 = pack2(s[2 * kb][0], s[2 * kb][1]);
+        uint32_t const a1 = pack2(s[2 * kb][2], s[2 * kb][3]);
+        uint32_t a2 = 0u, a3 = 0u;
+        if (2 * kb + 1 < kCnt) {
+            a2 = pack2(s[2 * kb + 1][0], s[2 * kb + 1][1]);
+            a3 = pack2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
         }
-        // ---- S = Q K^T ----
-        float s[kNPad / 8][4];
-#pragma unroll
-        for (int nb = 0; nb < kNPad / 8; ++nb) {
-            s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-            int const key = nb * 8 + g;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                uint32_t const b0 = Kw[(key * kQKStride + ks * 16 + 2 * t) >> 1];
-                uint32_t const b1 = Kw[(key * kQKStride + ks * 16 + 8 + 2 * t) >> 1];
-                mma16816(s[nb], aq[ks][0], aq[ks][1], aq[ks][2], aq[ks][3], b0, b1);
-            }
-        }
-        // ---- scale + bias (+ mask: the table holds -inf for padded key columns), row max ----
-        float m0 = -INFINITY, m1 = -INFINITY;
-        bool const v0 = r0 < n, v1 = r1 < n;
-        float4 const* bias_q = bias_h + (size_t)qt * (kNPad / 8) * 32 + lane;
-#pragma unroll
-        for (int nb = 0; nb < kNPad / 8; ++nb) {
-            float4 const bv = __ldg(bias_q + nb * 32);  // one coalesced 16-byte load per accumulator quad
-            s[nb][0] = fmaf(s[nb][0], scale, bv.x);
-            s[nb][1] = fmaf(s[nb][1], scale, bv.y);
-            s[nb][2] = fmaf(s[nb][2], scale, bv.z);
-            s[nb][3] = fmaf(s[nb][3], scale, bv.w);
-            m0 = fmaxf(m0, fmaxf(s[nb][0], s[nb][1]));
-            m1 = fmaxf(m1, fmaxf(s[nb][2], s[nb][3]));
-        }
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-        // ---- exp + row sum ----
-        float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-        for (int nb = 0; nb < kNPad / 8; ++nb) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                s[nb][e] = __expf(s[nb][e] - m0);
-                s[nb][2 + e] = __expf(s[nb][2 + e] - m1);
-                l0 += s[nb][e];
-                l1 += s[nb][2 + e];
-            }
-        }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        // ---- O = P V (P fragments come straight from the S accumulators) ----
-        float o[4][4];
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
-#pragma unroll
-        for (int kb = 0; kb < kNPad / 16; ++kb) {
-            uint32_t const a0 = pack2(s[2 * kb][0], s[2 * kb][1]);
-            uint32_t const a1 = pack2(s[2 * kb][2], s[2 * kb][3]);
-            uint32_t const a2 = pack2(s[2 * kb + 1][0], s[2 * kb + 1][1]);
-            uint32_t const a3 = pack2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
-#pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-                int const d = nb * 8 + g;
-                uint32_t const b0 = Vw[(d * kVStride + kb * 16 + 2 * t) >> 1];
-                uint32_t const b1 = Vw[(d * kVStride + kb * 16 + 8 + 2 * t) >> 1];
-                mma16816(o[nb], a0, a1, a2, a3, b0, b1);
-            }
-        }
-        float const inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
-            int const d = h * 32 + nb * 8 + 2 * t;
-            if (v0) *reinterpret_cast<act2_t*>(out + (row0 + r0) * C + d) = f22act2(o[nb][0] * inv0, o[nb][1] * inv0);
-            if (v1) *reinterpret_cast<act2_t*>(out + (row0 + r1) * C + d) = f22act2(o[nb][2] * inv1, o[nb][3] * inv1);
-        }
+        uint32_t const va = v_addr + (uint32_t)((nb0 + 2 * kb) * 8 * row_bytes);
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(va, b0, b1, b2, b3);  // dims 0-7 (keys 0-7, 8-15), dims 8-15
+        mma16816(o[0], a0, a1, a2, a3, b0, b1);
+        mma16816(o[1], a0, a1, a2, a3, b2, b3);
+        ldsm_x4_t(va + 32u, b0, b1, b2, b3);  // dims 16-23, 24-31
+        mma16816(o[2], a0, a1, a2, a3, b0, b1);
+        mma16816(o[3], a0, a1, a2, a3, b2, b3);
     }
 }
 
-template <int kNPad>
-void launch_mma(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out) {
-    size_t const smem = sizeof(act_t) * ((size_t)2 * kNPad * kQKStride + (size_t)32 * (kNPad + 8));
+template <int kWS, int kHG>
+__global__ void __launch_bounds__(Cfg<kWS, kHG>::kThreads, 1)
+window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int heads, act_t const* __restrict__ pad_qkv,
+                         __half const* __restrict__ bias_frag, act_t* __restrict__ out) {
+    using C = Cfg<kWS, kHG>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t const bias_s = smem_u32(smem);
+    uint32_t const tile_s[2] = {bias_s + C::kBiasBytes, bias_s + C::kBiasBytes + C::kTileBytes};
+    int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int const n_groups = heads / kHG;
+    int const hg = blockIdx.x % n_groups;
+    int const nw = (res + kWS - 1) / kWS;
+    int const total_windows = batch * nw * nw;
+    int const w_first = blockIdx.x / n_groups, w_stride = gridDim.x / n_groups;
+    int const ld = heads * 96;
+
+    // bias fragments of this head group (resident for the whole kernel) + zero the tiles once: token rows >= n stay
+    // zero for ever (K = 0 is masked by a -inf bias, V = 0 contributes nothing)
+    {
+        uint4 const* src = reinterpret_cast<uint4 const*>(bias_frag) + (size_t)hg * (C::kBiasBytes / 16);
+        for (int i = tid; i < C::kBiasBytes / 16; i += C::kThreads) reinterpret_cast<uint4*>(smem)[i] = __ldg(src + i);
+        uint4* t = reinterpret_cast<uint4*>(smem + C::kBiasBytes);
+        for (int i = tid; i < 2 * C::kTileBytes / 16; i += C::kThreads) t[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    auto load_item = [&](int win, int buf) {
+        int const b = win / (nw * nw), wr = win % (nw * nw);
+        int const y0 = (wr / nw) * kWS, x0 = (wr % nw) * kWS;
+        for (int q = tid; q < C::n * C::kCPT; q += C::kThreads) {
+            int const tok = q / C::kCPT, part = q % C::kCPT;
+            int const y = y0 + tok / kWS, x = x0 + tok % kWS;
+            uint32_t const dst = tile_s[buf] + (uint32_t)(tok * C::kRowBytes + part * 16);
+            if (y < res && x < res) {
+                act_t const* src = qkv + ((size_t)(b * res + y) * res + x) * ld + hg * kHG * 96 + part * 8;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            } else {
+                uint4 const v = __ldg(reinterpret_cast<uint4 const*>(pad_qkv + hg * kHG * 96 + part * 8));
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int const hh = warp / C::NQ, qt = warp % C::NQ;
+    int const g = lane >> 2, t = lane & 3;
+    // per-lane ldmatrix row addresses (relative to the tile)
+    uint32_t const q_off = (uint32_t)((qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * C::kRowBytes + (hh * 96 + ((lane >> 4) & 1) * 8) * 2);
+    uint32_t const k_off = (uint32_t)((lane & 7) * C::kRowBytes + (hh * 96 + 32 + (lane >> 3) * 8) * 2);
+    uint32_t const v_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * C::kRowBytes + (hh * 96 + 64 + ((lane >> 4) & 1) * 8) * 2);
+    uint32_t const bias_addr = bias_s + (uint32_t)((((hh * C::NQ + qt) * C::NK8) * 32 + lane) * 8);
+
+    int it = 0;
+    if (w_first < total_windows) load_item(w_first, 0);
+    for (int win = w_first; win < total_windows; win += w_stride, ++it) {
+        int const buf = it & 1;
+        if (win + w_stride < total_windows) {
+            load_item(win + w_stride, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // this item's tokens are visible to every warp
+
+        uint32_t const tile = tile_s[buf];
+        uint32_t aq[2][4];
+        ldsm_x4(tile + q_off, aq[0][0], aq[0][1], aq[0][2], aq[0][3]);
+        ldsm_x4(tile + q_off + 32u, aq[1][0], aq[1][1], aq[1][2], aq[1][3]);
+        float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+        float o[4][4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+        if constexpr (C::NK8 <= 8) {
+            attend_chunk<C::NK8, true>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
+        } else {
+            static_assert(C::NK8 <= 8 || C::NK8 == 25, "chunk schedule written for 196-token windows");
+            attend_chunk<8, true>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
+            attend_chunk<8, false>(8, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
+            attend_chunk<8, false>(16, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
+            attend_chunk<1, false>(24, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
+        }
+        l[0] += __shfl_xor_sync(0xffffffffu, l[0], 1);
+        l[0] += __shfl_xor_sync(0xffffffffu, l[0], 2);
+        l[1] += __shfl_xor_sync(0xffffffffu, l[1], 1);
+        l[1] += __shfl_xor_sync(0xffffffffu, l[1], 2);
+        float const inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+        // O (16-bit) goes into this task's own Q slot of the tile; the CTA then writes whole token rows
+        uint32_t const o_addr = tile + (uint32_t)((qt * 16 + g) * C::kRowBytes + (hh * 96 + 2 * t) * 2);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_addr + (uint32_t)(d * 16)), "r"(pack2(o[d][0] * inv0, o[d][1] * inv0)) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_addr + (uint32_t)(8 * C::kRowBytes + d * 16)), "r"(pack2(o[d][2] * inv1, o[d][3] * inv1)) : "memory");
+        }
+        __syncthreads();  // all heads' outputs of this window are in the tile
+
+        {
+            int const b = win / (nw * nw), wr = win % (nw * nw);
+            int const y0 = (wr / nw) * kWS, x0 = (wr % nw) * kWS;
+            int const Cout = heads * 32;
+            for (int q = tid; q < C::n * kHG * 4; q += C::kThreads) {
+                int const tok = q / (kHG * 4), part = q % (kHG * 4);
+                int const y = y0 + tok / kWS, x = x0 + tok % kWS;
+                if (y < res && x < res) {
+                    uint4 v;
+                    uint32_t const src = tile + (uint32_t)(tok * C::kRowBytes + ((part >> 2) * 96 + (part & 3) * 8) * 2);
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
+                    *reinterpret_cast<uint4*>(out + ((size_t)(b * res + y) * res + x) * Cout + (hg * kHG + (part >> 2)) * 32 + (part & 3) * 8) = v;
+                }
+            }
+        }
+        __syncthreads();  // the tile may be overwritten by the load issued two items ahead
+    }
+}
+
+template <int kWS, int kHG>
+void launch_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int heads, act_t const* pad_qkv,
+                      __half const* bias_frag, act_t* out, int num_sms) {
+    using C = Cfg<kWS, kHG>;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(window_attention_mma_kernel<kNPad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(window_attention_kernel2<kWS, kHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         attr_set = true;
     }
-    window_attention_mma_kernel<kNPad><<<windows * heads, kWarps * 32, smem, s>>>(qkv, n, heads, bias, out);
+    int const n_groups = heads / kHG;
+    int const nw = (res + kWS - 1) / kWS;
+    int const items = batch * nw * nw * n_groups;
+    int grid = (num_sms / n_groups) * n_groups;
+    if (grid > items) grid = items;
+    window_attention_kernel2<kWS, kHG><<<grid, C::kThreads, C::kSmemBytes, s>>>(qkv, batch, res, heads, pad_qkv, bias_frag, out);
     KERNEL_CHECK();
 }
 
 }  // namespace
 
-void attention_bias_fragments(float const* dense, int heads, int n, float* out) {
-    int const np = window_pad(n);
+int attention_head_group(int ws, int heads) {
+    if (ws == 14) return 1;
+    return heads % 5 == 0 ? 5 : (heads % 4 == 0 ? 4 : 0);
+}
+
+size_t attention_bias_fragment_count(int heads, int ws) {
+    int const n = ws * ws, nq = (n + 15) / 16, nk8 = (n + 7) / 8;
+    return (size_t)heads * nq * nk8 * 32 * 4;
+}
+
+void attention_bias_fragments(float const* dense, int heads, int ws, uint16_t* out) {
+    int const n = ws * ws, nq = (n + 15) / 16, nk8 = (n + 7) / 8;
+    float const log2e = 1.4426950408889634f;
     size_t i = 0;
     for (int h = 0; h < heads; ++h)
-        for (int qt = 0; qt < np / 16; ++qt)
-            for (int nb = 0; nb < np / 8; ++nb)
+        for (int qt = 0; qt < nq; ++qt)
+            for (int nb = 0; nb < nk8; ++nb)
                 for (int lane = 0; lane < 32; ++lane)
                     for (int e = 0; e < 4; ++e) {
                         int const r = qt * 16 + (lane >> 2) + (e >= 2 ? 8 : 0);
                         int const c = nb * 8 + 2 * (lane & 3) + (e & 1);
                         float v = 0.f;
-                        if (c >= n) v = -INFINITY;
-                        else if (r < n) v = dense[((size_t)h * n + r) * n + c];
-                        out[i++] = v;
+                        if (c >= n) v = -INFINITY;  // key padding of the tile: masked
+                        else if (r < n) v = dense[((size_t)h * n + r) * n + c] * log2e;
+                        __half const hv = __float2half_rn(v);
+                        out[i++] = *reinterpret_cast<uint16_t const*>(&hv);
                     }
 }
 
-void window_attention(cudaStream_t s, act_t const* qkv, int windows, int n, int heads, float const* bias, act_t* out) {
-    ProfScope prof(s, CAT_WIN_ATTN, 4.0 * windows * heads * n * n * 32, (double)windows * n * heads * 128 * 2);
-    if (n <= 64) launch_mma<64>(s, qkv, windows, n, heads, bias, out);
-    else if (n <= 208) launch_mma<208>(s, qkv, windows, n, heads, bias, out);
-    else fail("window_attention: unsupported window size " + std::to_string(n));
+void window_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int ws, int heads, act_t const* pad_qkv,
+                      uint16_t const* bias_frag, act_t* out, int num_sms) {
+    int const nw = (res + ws - 1) / ws, n = ws * ws;
+    ProfScope prof(s, CAT_WIN_ATTN, 4.0 * batch * nw * nw * heads * n * n * 32, (double)batch * res * res * heads * 128 * 2);
+    __half const* bf = reinterpret_cast<__half const*>(bias_frag);
+    if (ws == 7 && heads % 5 == 0) launch_attention<7, 5>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
+    else if (ws == 7 && heads % 4 == 0) launch_attention<7, 4>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
+    else if (ws == 14) launch_attention<14, 1>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
+    else fail("window_attention: unsupported (window, heads) = (" + std::to_string(ws) + ", " + std::to_string(heads) + ")");
 }
 
 }  // namespace enc

@@ -84,6 +84,40 @@ Linear16 load_linear16(WeightFile const& wf, std::string const& p, int n, int k,
     return l;
 }
 
+// Linear preceded by a LayerNorm, with the LayerNorm's affine part folded in: W' = W * gamma (per input feature),
+// b' = b + W beta.  colsum_n = sum_k W'_nk over the ROUNDED weights, so that the epilogue identity
+// LN(x) W^T + b = rstd (x W'^T - mean colsum) + b' holds exactly for the operand the tensor cores see.
+Linear16 load_linear16_ln(WeightFile const& wf, std::string const& p, std::string const& norm, int n, int k,
+                          std::vector<float>* bias_out = nullptr) {
+    auto const& w = wf.get(p + ".weight", {n, k}).data;
+    auto const& b = wf.get(p + ".bias", {n}).data;
+    auto const& g = wf.get(norm + ".weight", {k}).data;
+    auto const& beta = wf.get(norm + ".bias", {k}).data;
+    std::vector<float> wf32((size_t)n * k), bias((size_t)n), colsum((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        double acc = b[(size_t)i];
+        for (int j = 0; j < k; ++j) {
+            wf32[(size_t)i * k + j] = w[(size_t)i * k + j] * g[(size_t)j];
+            acc += (double)w[(size_t)i * k + j] * beta[(size_t)j];
+        }
+        bias[(size_t)i] = (float)acc;
+    }
+    std::vector<act_t> const w16 = to_act(wf32);
+    for (int i = 0; i < n; ++i) {
+        double acc = 0;
+        for (int j = 0; j < k; ++j) acc += (double)act2f(w16[(size_t)i * k + j]);
+        colsum[(size_t)i] = (float)acc;
+    }
+    Linear16 l;
+    l.n = n;
+    l.k = k;
+    l.w.upload(w16);
+    l.b.upload(bias);
+    l.colsum.upload(colsum);
+    if (bias_out) *bias_out = bias;
+    return l;
+}
+
 Linear32 load_linear32(WeightFile const& wf, std::string const& p, int n, int k) {
     Linear32 l;
     l.n = n;
@@ -181,18 +215,20 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
         for (int i = 0; i < kDepths[st]; ++i) {
             std::string const p = E + "layers." + std::to_string(st) + ".blocks." + std::to_string(i);
             BlockW b;
-            b.attn_norm = load_norm(wf, p + ".attn.norm", C);
-            b.qkv = load_linear16(wf, p + ".attn.qkv", 3 * C, C);
+            {
+                std::vector<float> qkv_bias;
+                b.qkv = load_linear16_ln(wf, p + ".attn.qkv", p + ".attn.norm", 3 * C, C, &qkv_bias);
+                b.qkv_pad.upload(to_act(qkv_bias));  // x = 0 -> mean 0, acc 0 -> the folded bias
+            }
             b.proj = load_linear16(wf, p + ".attn.proj", C, C);
             {
                 std::vector<float> const dense = dense_attention_bias(wf.get(p + ".attn.attention_biases"), heads, ws);
-                std::vector<float> frag(enc::attention_bias_fragment_floats(heads, ws * ws));
-                enc::attention_bias_fragments(dense.data(), heads, ws * ws, frag.data());
+                std::vector<uint16_t> frag(enc::attention_bias_fragment_count(heads, ws));
+                enc::attention_bias_fragments(dense.data(), heads, ws, frag.data());
                 b.attn_bias.upload(frag);
             }
             b.local_conv = load_dw_bn(wf, p + ".local_conv", C);
-            b.mlp_norm = load_norm(wf, p + ".mlp.norm", C);
-            b.fc1 = load_linear16(wf, p + ".mlp.fc1", 4 * C, C);
+            b.fc1 = load_linear16_ln(wf, p + ".mlp.fc1", p + ".mlp.norm", 4 * C, C);
             b.fc2 = load_linear16(wf, p + ".mlp.fc2", C, 4 * C);
             enc_.blocks[st - 1].push_back(std::move(b));
         }
@@ -297,22 +333,7 @@ EncoderWorkspace::EncoderWorkspace(int mb) : max_batch(mb) {
     xa.allocate(B * 65536 * 64);
     xb.allocate(B * 65536 * 64);
     for (auto& b : big) b.allocate(B * 65536 * 256);
-    for (int st = 1; st <= 3; ++st) {
-        StageCfg const c = SamModel::stage(st);
-        int const pad = (c.ws - c.res % c.ws) % c.ws, pr = c.res + pad, nw = pr / c.ws, n = c.ws * c.ws;
-        win_rows[st - 1] = nw * nw * n;
-        std::vector<int> map(B * (size_t)win_rows[st - 1]);
-        size_t m = 0;
-        for (int b = 0; b < mb; ++b)
-            for (int wy = 0; wy < nw; ++wy)
-                for (int wx = 0; wx < nw; ++wx)
-                    for (int iy = 0; iy < c.ws; ++iy)
-                        for (int ix = 0; ix < c.ws; ++ix) {
-                            int const y = wy * c.ws + iy, x = wx * c.ws + ix;
-                            map[m++] = (y < c.res && x < c.res) ? (b * c.res + y) * c.res + x : -1;
-                        }
-        row_map[st - 1].upload(map);
-    }
+    stats.allocate(B * 16384);
 }
 
 DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
@@ -338,16 +359,20 @@ DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
 
 // ---------------------------------------------------------------------------------------------
 void SamModel::gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 const& l, void* out, int act,
-                      act_t const* residual, int const* row_map, bool out_f32) const {
+                      act_t const* residual, float2 const* ln_stats, bool out_f32) const {
     gemm::Operand A{a, rows, l.k, l.k};
     gemm::Operand B{l.w.get(), l.n, l.k, l.k};
     gemm::Epilogue e;
     e.bias = l.b.get();
     e.residual = residual;
-    e.row_map = row_map;
     e.act = act;
     e.out_f32 = out_f32 ? 1 : 0;
     e.ldc = l.n;
+    if (ln_stats) {
+        DLIMG_ASSERT(l.colsum);
+        e.ln_stats = ln_stats;
+        e.ln_colsum = l.colsum.get();
+    }
     gemm::launch(s, false, A, B, out, e, num_sms_);
 }
 
@@ -375,15 +400,15 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
     enc::im2col3x3(s, ws.c1.get(), batch, 512, 512, 32, 2, ws.col.get());
     act_t* x = ws.xa.get();
     act_t* y = ws.xb.get();
-    gemm16(s, ws.col.get(), B * 65536, enc_.conv2, x, ACT_NONE, nullptr, nullptr);
+    gemm16(s, ws.col.get(), B * 65536, enc_.conv2, x, ACT_NONE, nullptr);
     tap_act(s, tap, "patch_embed", x, (size_t)B * 65536 * 64);
 
     // layer 0: MBConv x2 (1x1 expand + GELU, dw3x3 + GELU, 1x1 project + shortcut + GELU)
     for (int i = 0; i < 2; ++i) {
         MBConvW const& m = enc_.mb[i];
-        gemm16(s, x, B * 65536, m.conv1, ws.big[0].get(), ACT_GELU, nullptr, nullptr);
+        gemm16(s, x, B * 65536, m.conv1, ws.big[0].get(), ACT_GELU, nullptr);
         enc::dwconv3x3(s, ws.big[0].get(), batch, 256, 256, 256, 1, m.conv2.w.get(), m.conv2.w16.get(), m.conv2.b.get(), true, ws.big[1].get());
-        gemm16(s, ws.big[1].get(), B * 65536, m.conv3, y, ACT_GELU, x, nullptr);
+        gemm16(s, ws.big[1].get(), B * 65536, m.conv3, y, ACT_GELU, x);
         std::swap(x, y);
         tap_act(s, tap, i == 0 ? "mb0" : "mb1", x, (size_t)B * 65536 * 64);
     }
@@ -391,10 +416,10 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
     auto merge = [&](MergeW const& m, int res, char const* name) {
         int const out_res = m.stride == 2 ? res / 2 : res;
         int const dout = m.conv1.n;
-        gemm16(s, x, B * res * res, m.conv1, ws.big[0].get(), ACT_GELU, nullptr, nullptr);
+        gemm16(s, x, B * res * res, m.conv1, ws.big[0].get(), ACT_GELU, nullptr);
         enc::dwconv3x3(s, ws.big[0].get(), batch, res, res, dout, m.stride, m.conv2.w.get(), m.conv2.w16.get(), m.conv2.b.get(),
                        true, ws.big[1].get());
-        gemm16(s, ws.big[1].get(), B * out_res * out_res, m.conv3, y, ACT_NONE, nullptr, nullptr);
+        gemm16(s, ws.big[1].get(), B * out_res * out_res, m.conv3, y, ACT_NONE, nullptr);
         std::swap(x, y);
         tap_act(s, tap, name, x, (size_t)B * out_res * out_res * dout);
     };
@@ -402,43 +427,43 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
 
     for (int st = 1; st <= 3; ++st) {
         StageCfg const c = stage(st);
-        int const C = c.dim, L = c.res * c.res, n = c.ws * c.ws;
-        int64_t const wrows = B * ws.win_rows[st - 1];
-        int const windows = (int)(wrows / n);
-        int const* map = ws.row_map[st - 1].get();
+        int const C = c.dim, L = c.res * c.res;
+        int const rows = (int)(B * L);
+        float2* stats = ws.stats.get();
         for (int i = 0; i < c.depth; ++i) {
             BlockW const& b = enc_.blocks[st - 1][(size_t)i];
             std::string const tn = "s" + std::to_string(st) + "b" + std::to_string(i);
-            // attention branch: pad + partition + LN (gather), QKV, windowed attention, proj + un-partition + residual
-            enc::layernorm_rows(s, x, (int)wrows, C, map, b.attn_norm.g.get(), b.attn_norm.b.get(), 1e-5f, ws.big[0].get(), false);
-            tap_act(s, tap, (tn + ".ln").c_str(), ws.big[0].get(), (size_t)wrows * C);
-            gemm16(s, ws.big[0].get(), wrows, b.qkv, ws.big[1].get(), ACT_NONE, nullptr, nullptr);
-            tap_act(s, tap, (tn + ".qkv").c_str(), ws.big[1].get(), (size_t)wrows * 3 * C);
-            enc::window_attention(s, ws.big[1].get(), windows, n, c.heads, b.attn_bias.get(), ws.big[2].get());
-            tap_act(s, tap, (tn + ".att").c_str(), ws.big[2].get(), (size_t)wrows * C);
-            gemm16(s, ws.big[2].get(), wrows, b.proj, x, ACT_NONE, x, map);
-            tap_act(s, tap, (tn + ".proj").c_str(), x, (size_t)B * L * C);
+            // attention branch on the un-partitioned grid: LN statistics, QKV with the LayerNorm folded into the GEMM,
+            // windowed attention (does the partition / zero padding / un-partition itself), proj + residual in place
+            enc::layernorm_stats(s, x, rows, C, 1e-5f, stats);
+            gemm16(s, x, rows, b.qkv, ws.big[1].get(), ACT_NONE, nullptr, stats);
+            tap_act(s, tap, (tn + ".qkv").c_str(), ws.big[1].get(), (size_t)rows * 3 * C);
+            enc::window_attention(s, ws.big[1].get(), batch, c.res, c.ws, c.heads, b.qkv_pad.get(), b.attn_bias.get(),
+                                  ws.big[2].get(), num_sms_);
+            tap_act(s, tap, (tn + ".att").c_str(), ws.big[2].get(), (size_t)rows * C);
+            gemm16(s, ws.big[2].get(), rows, b.proj, x, ACT_NONE, x);
+            tap_act(s, tap, (tn + ".proj").c_str(), x, (size_t)rows * C);
             // local depthwise conv (no activation, no residual)
             enc::dwconv3x3(s, x, batch, c.res, c.res, C, 1, b.local_conv.w.get(), nullptr, b.local_conv.b.get(), false, y);
-            tap_act(s, tap, (tn + ".lc").c_str(), y, (size_t)B * L * C);
-            // MLP branch
-            enc::layernorm_rows(s, y, (int)(B * L), C, nullptr, b.mlp_norm.g.get(), b.mlp_norm.b.get(), 1e-5f, ws.big[0].get(), false);
-            gemm16(s, ws.big[0].get(), B * L, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, nullptr);
-            gemm16(s, ws.big[1].get(), B * L, b.fc2, y, ACT_NONE, y, nullptr);
+            tap_act(s, tap, (tn + ".lc").c_str(), y, (size_t)rows * C);
+            // MLP branch: LN folded into fc1 (+ GELU), fc2 + residual
+            enc::layernorm_stats(s, y, rows, C, 1e-5f, stats);
+            gemm16(s, y, rows, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, stats);
+            gemm16(s, ws.big[1].get(), rows, b.fc2, y, ACT_NONE, y);
             std::swap(x, y);
-            tap_act(s, tap, tn.c_str(), x, (size_t)B * L * C);
+            tap_act(s, tap, tn.c_str(), x, (size_t)rows * C);
         }
         if (st < 3) merge(enc_.merge[st], c.res, st == 1 ? "layer1" : "layer2");
     }
     tap_act(s, tap, "layer3", x, (size_t)B * 4096 * 320);
 
     // neck: 1x1 conv -> LayerNorm2d -> 3x3 conv -> LayerNorm2d (token-major, so LayerNorm2d is a row LayerNorm)
-    gemm16(s, x, B * 4096, enc_.neck1, ws.big[0].get(), ACT_NONE, nullptr, nullptr);
+    gemm16(s, x, B * 4096, enc_.neck1, ws.big[0].get(), ACT_NONE, nullptr);
     enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln1.g.get(), enc_.neck_ln1.b.get(), 1e-6f,
                         ws.big[1].get(), false);
     tap_act(s, tap, "neck1", ws.big[1].get(), (size_t)B * 4096 * 256);
     enc::im2col3x3(s, ws.big[1].get(), batch, 64, 64, 256, 1, ws.col.get());
-    gemm16(s, ws.col.get(), B * 4096, enc_.neck2, ws.big[0].get(), ACT_NONE, nullptr, nullptr);
+    gemm16(s, ws.col.get(), B * 4096, enc_.neck2, ws.big[0].get(), ACT_NONE, nullptr);
     enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f,
                         emb_out, true);
     if (tap && tap->name && std::strcmp(tap->name, "neck") == 0) {

@@ -56,6 +56,7 @@ template <typename T> class DeviceBuffer {
 struct Linear16 {  // act_t weight (N, K) row-major + fp32 bias (N) -- encoder GEMM operand B
     DeviceBuffer<act_t> w;
     DeviceBuffer<float> b;
+    DeviceBuffer<float> colsum;  // only for Linears with a folded LayerNorm in front: sum_k w[n][k] (of the rounded weights)
     int n = 0, k = 0;
 };
 struct Linear32 {  // fp32 weight (N, K) + bias -- decoder
@@ -75,11 +76,12 @@ struct Norm {
 struct MBConvW { Linear16 conv1; DwConv conv2; Linear16 conv3; };
 struct MergeW { Linear16 conv1; DwConv conv2; Linear16 conv3; int stride = 2; };
 struct BlockW {
-    Norm attn_norm;
+    // attn.norm and mlp.norm are folded into qkv and fc1 (gamma into the weights, beta into the bias; the per-row
+    // mean / rstd are applied in the GEMM epilogue), see gemm.cuh Epilogue::ln_stats
     Linear16 qkv, proj;
-    DeviceBuffer<float> attn_bias;  // (heads, n, n)
+    DeviceBuffer<act_t> qkv_pad;        // (3C): qkv of a zero-padding token = projection of LN(0) = beta
+    DeviceBuffer<uint16_t> attn_bias;   // fp16 fragment-ordered relative-position bias (attention_bias_fragments)
     DwConv local_conv;
-    Norm mlp_norm;
     Linear16 fc1, fc2;
 };
 struct StageCfg { int dim, res, depth, heads, ws; };
@@ -120,8 +122,7 @@ struct EncoderWorkspace {
     int max_batch = 0;
     DeviceBuffer<act_t> c1, col, xa, xb, big[4];
     DeviceBuffer<float> emb;       // (max_batch, 4096, 256) fp32: fixed destination of the captured encoder graph
-    DeviceBuffer<int> row_map[3];  // stage 1..3: windowed row -> token row (-1 = padding), for max_batch images
-    int win_rows[3] = {0, 0, 0};   // windowed rows per image
+    DeviceBuffer<float2> stats;    // (max_batch * 16384): per-token LayerNorm (mean, rstd) of the current block input
     explicit EncoderWorkspace(int max_batch);
 };
 
@@ -176,7 +177,7 @@ class SamModel {
 
   private:
     void gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 const& l, void* out, int act, act_t const* residual,
-                int const* row_map, bool out_f32 = false) const;
+                float2 const* ln_stats = nullptr, bool out_f32 = false) const;
     void gemm32(cudaStream_t s, float const* a, int64_t rows, Linear32 const& l, float* out, int act) const;
     void lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, int rows, Linear32 const& l, bool relu, float* y,
              int64_t ys) const;

@@ -15,9 +15,12 @@ typedef struct dlimg_b200_Debug {
     uint32_t act_is_bf16; /* storage type of encoder activations / 16-bit GEMM operands: 0 = fp16, 1 = bf16 */
     /* C = epilogue(A[M,K] * B[N,K]^T).  Device pointers; elements are bf16 (tf32 == 0) or fp32 (tf32 != 0).
      * simt != 0 runs the CUDA-core cross-check kernel instead of the tcgen05 kernel.  act: 0 none, 1 GELU(erf),
-     * 2 ReLU.  row_map (optional): output row per input row, -1 drops the row. */
+     * 2 ReLU.  row_map (optional): output row per input row, -1 drops the row.  ln_stats / ln_colsum (optional):
+     * folded LayerNorm, per-row (mean, rstd) pairs [M][2] and per-column weight sums [N]:
+     * out = rstd * (A B^T - mean * colsum) + bias. */
     dlimg_Result (*gemm)(void* stream, int tf32, int simt, void const* a, void const* b, int M, int N, int K,
-                         float const* bias, void const* residual, int const* row_map, int act, int out_f32, void* out);
+                         float const* bias, void const* residual, int const* row_map, int act, int out_f32, void* out,
+                         float const* ln_stats, float const* ln_colsum);
     /* Encodes `count` device-resident images and copies the activation called `name` (see model.cu) as fp32. */
     dlimg_Result (*encode_tap)(dlimg_Environment, dlimg_ImageView const* dev_views, int count, char const* name,
                                float* dev_out, size_t capacity, size_t* written);
@@ -25,10 +28,17 @@ typedef struct dlimg_b200_Debug {
      * weights[out_size * max_taps]. */
     int (*resize_plan)(int in_size, int out_size, int max_taps, int* first, float* weights);
     void (*srgb_tables)(float* decode256, float* threshold256);
-    /* Windowed attention on device buffers: qkv (windows*n, heads*96) 16-bit, bias (heads, n, n) fp32 ->
-     * out (windows*n, heads*32) 16-bit.  simt != 0 runs the CUDA-core cross-check kernel. */
-    dlimg_Result (*window_attention)(void* stream, int simt, void const* qkv, int windows, int n, int heads,
-                                     float const* bias, void* out);
+    /* Windowed attention on the un-partitioned token grid: qkv (batch*res*res, heads*96) 16-bit, ws x ws windows,
+     * pad_qkv (heads*96) 16-bit = the qkv of a zero-padding position, bias (heads, ws^2, ws^2) fp32 dense ->
+     * out (batch*res*res, heads*32) 16-bit. */
+    dlimg_Result (*window_attention)(void* stream, void const* qkv, int batch, int res, int ws, int heads,
+                                     void const* pad_qkv, float const* bias, void* out);
+    /* CUDA-core cross-check of the attention core on partitioned windows: qkv (windows*n, heads*96) ->
+     * out (windows*n, heads*32). */
+    dlimg_Result (*window_attention_simt)(void* stream, void const* qkv, int windows, int n, int heads,
+                                          float const* bias, void* out);
+    /* Per-row LayerNorm statistics: in (rows, C) 16-bit -> out (rows, 2) fp32 (mean, rstd). */
+    dlimg_Result (*layernorm_stats)(void* stream, void const* in, int rows, int C, float eps, float* out);
 } dlimg_b200_Debug;
 
 DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void);

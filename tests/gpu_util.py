@@ -12,7 +12,8 @@ def act_dtype():
     return torch.bfloat16 if dl.debug().act_is_bf16 else torch.float16
 
 
-def gemm(a, b, bias=None, residual=None, row_map=None, act=0, out_f32=False, simt=False, out_rows=None, out=None):
+def gemm(a, b, bias=None, residual=None, row_map=None, act=0, out_f32=False, simt=False, out_rows=None, out=None,
+         ln_stats=None, ln_colsum=None):
     """a (M,K), b (N,K) CUDA tensors, both act_dtype() or both fp32 (tf32 path).  Returns the output tensor."""
     M, K = a.shape
     N = b.shape[0]
@@ -23,7 +24,9 @@ def gemm(a, b, bias=None, residual=None, row_map=None, act=0, out_f32=False, sim
     r = dl.debug().gemm(None, int(tf32), int(simt), a.data_ptr(), b.data_ptr(), M, N, K,
                         bias.data_ptr() if bias is not None else None,
                         residual.data_ptr() if residual is not None else None,
-                        row_map.data_ptr() if row_map is not None else None, act, int(out_f32), out.data_ptr())
+                        row_map.data_ptr() if row_map is not None else None, act, int(out_f32), out.data_ptr(),
+                        ln_stats.data_ptr() if ln_stats is not None else None,
+                        ln_colsum.data_ptr() if ln_colsum is not None else None)
     if r != 0:
         raise dl.Exception(dl.api().last_error().decode())
     torch.cuda.synchronize()

@@ -104,3 +104,33 @@ def test_gemm_back_to_back_is_deterministic():
     o1 = gemm(a, b)
     o2 = gemm(a, b)
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(4096, 480, 160, 0), (1000, 512, 128, 1), (4096, 1280, 320, 1), (333, 384, 128, 0)])
+def test_f16_gemm_folded_layernorm(M, N, K, act):
+    """qkv / fc1 with the preceding LayerNorm folded in: A is the raw rows, gamma is in the weights, beta in the bias,
+    and the epilogue applies rstd * (acc - mean * colsum) + bias.  Reference: LayerNorm then Linear in fp32."""
+    import dlimgedit_b200 as dl
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 1.5 + 0.7).to(act_dtype())
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    gamma = 1 + 0.2 * torch.randn(K, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(K, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x.float(), (K,), gamma, beta, 1e-5) @ w.t() + b
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    w16 = (w * gamma).to(act_dtype())
+    bias = b + w @ beta
+    colsum = w16.float().sum(1).contiguous()
+    stats = torch.zeros(M, 2, device="cuda")
+    r = dl.debug().layernorm_stats(None, x.data_ptr(), M, K, 1e-5, stats.data_ptr())
+    assert r == 0, dl.api().last_error()
+    torch.cuda.synchronize()
+    xf = x.float()
+    assert torch.allclose(stats[:, 0], xf.mean(1), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(stats[:, 1], (xf.var(1, unbiased=False) + 1e-5).rsqrt(), atol=1e-5, rtol=1e-4)
+    out = gemm(x, w16, bias=bias, act=act, ln_stats=stats, ln_colsum=colsum)
+    assert torch.allclose(out.float(), ref, atol=2e-2, rtol=1e-2), float((out.float() - ref).abs().max())
+    simt = gemm(x, w16, bias=bias, act=act, ln_stats=stats, ln_colsum=colsum, simt=True, out_f32=True)
+    assert torch.allclose(simt, ref, atol=1e-2, rtol=1e-2), float((simt - ref).abs().max())
