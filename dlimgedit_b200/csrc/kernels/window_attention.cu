@@ -155,7 +155,7 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
     using C = Cfg<kWS, kHG>;
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t const bias_s = smem_u32(smem);
-    uint32_t const tile_s[2] = {bias_s + C::kBiasBytes, bias_s + C::kBiasBytes + C::kTileBytes};
+    uint32_t const tile0_s = bias_s + C::kBiasBytes;  // two token tiles (double buffer) follow the bias table
     int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int const n_groups = heads / kHG;
     int const hg = blockIdx.x % n_groups;
@@ -174,24 +174,36 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
     }
     __syncthreads();
 
+    // Token gather: a thread always moves the same 16-byte piece (`part`) of a token row and walks over tokens with a
+    // fixed stride, so the per-copy work is one small constant division and an address add.
+    constexpr int kLoadTok = C::kThreads / C::kCPT;  // tokens moved per sweep of the CTA
+    int const ld_part = tid % C::kCPT, ld_tok0 = tid / C::kCPT;
     auto load_item = [&](int win, int buf) {
         int const b = win / (nw * nw), wr = win % (nw * nw);
         int const y0 = (wr / nw) * kWS, x0 = (wr % nw) * kWS;
-        for (int q = tid; q < C::n * C::kCPT; q += C::kThreads) {
-            int const tok = q / C::kCPT, part = q % C::kCPT;
-            int const y = y0 + tok / kWS, x = x0 + tok % kWS;
-            uint32_t const dst = tile_s[buf] + (uint32_t)(tok * C::kRowBytes + part * 16);
-            if (y < res && x < res) {
-                act_t const* src = qkv + ((size_t)(b * res + y) * res + x) * ld + hg * kHG * 96 + part * 8;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            } else {
-                uint4 const v = __ldg(reinterpret_cast<uint4 const*>(pad_qkv + hg * kHG * 96 + part * 8));
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        act_t const* const src0 = qkv + ((size_t)(b * res + y0) * res + x0) * ld + hg * kHG * 96 + ld_part * 8;
+        uint32_t const dst0 = tile0_s + (uint32_t)(buf * C::kTileBytes + ld_part * 16);
+        if (ld_tok0 < kLoadTok) {
+#pragma unroll
+            for (int tok = ld_tok0, i = 0; i < (C::n + kLoadTok - 1) / kLoadTok; ++i, tok += kLoadTok) {
+                if (tok < C::n) {
+                    int const iy = tok / kWS, ix = tok - iy * kWS;
+                    uint32_t const dst = dst0 + (uint32_t)(tok * C::kRowBytes);
+                    if (y0 + iy < res && x0 + ix < res) {
+                        act_t const* src = src0 + (size_t)(iy * res + ix) * ld;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    } else {
+                        uint4 const v = __ldg(reinterpret_cast<uint4 const*>(pad_qkv + hg * kHG * 96 + ld_part * 8));
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    }
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    constexpr int kStoreTok = C::kThreads / (kHG * 4);  // output: kHG * 4 pieces of 16 bytes per token
+    int const st_part = tid % (kHG * 4), st_tok0 = tid / (kHG * 4);
     int const hh = warp / C::NQ, qt = warp % C::NQ;
     int const g = lane >> 2, t = lane & 3;
     // per-lane ldmatrix row addresses (relative to the tile)
@@ -212,7 +224,7 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
         }
         __syncthreads();  // this item's tokens are visible to every warp
 
-        uint32_t const tile = tile_s[buf];
+        uint32_t const tile = tile0_s + (uint32_t)(buf * C::kTileBytes);
         uint32_t aq[2][4];
         ldsm_x4(tile + q_off, aq[0][0], aq[0][1], aq[0][2], aq[0][3]);
         ldsm_x4(tile + q_off + 32u, aq[1][0], aq[1][1], aq[1][2], aq[1][3]);
@@ -243,18 +255,21 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
         }
         __syncthreads();  // all heads' outputs of this window are in the tile
 
-        {
+        if (st_tok0 < kStoreTok) {
             int const b = win / (nw * nw), wr = win % (nw * nw);
             int const y0 = (wr / nw) * kWS, x0 = (wr % nw) * kWS;
             int const Cout = heads * 32;
-            for (int q = tid; q < C::n * kHG * 4; q += C::kThreads) {
-                int const tok = q / (kHG * 4), part = q % (kHG * 4);
-                int const y = y0 + tok / kWS, x = x0 + tok % kWS;
-                if (y < res && x < res) {
-                    uint4 v;
-                    uint32_t const src = tile + (uint32_t)(tok * C::kRowBytes + ((part >> 2) * 96 + (part & 3) * 8) * 2);
-                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
-                    *reinterpret_cast<uint4*>(out + ((size_t)(b * res + y) * res + x) * Cout + (hg * kHG + (part >> 2)) * 32 + (part & 3) * 8) = v;
+            act_t* const dst0 = out + ((size_t)(b * res + y0) * res + x0) * Cout + hg * kHG * 32 + st_part * 8;
+            uint32_t const src0 = tile + (uint32_t)(((st_part >> 2) * 96 + (st_part & 3) * 8) * 2);
+#pragma unroll
+            for (int tok = st_tok0, i = 0; i < (C::n + kStoreTok - 1) / kStoreTok; ++i, tok += kStoreTok) {
+                if (tok < C::n) {
+                    int const iy = tok / kWS, ix = tok - iy * kWS;
+                    if (y0 + iy < res && x0 + ix < res) {
+                        uint4 v;
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src0 + (uint32_t)(tok * C::kRowBytes)));
+                        *reinterpret_cast<uint4*>(dst0 + (size_t)(iy * res + ix) * Cout) = v;
+                    }
                 }
             }
         }

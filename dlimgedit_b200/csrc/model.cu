@@ -494,6 +494,12 @@ void SamModel::prepare_embedding(cudaStream_t s, float const* emb, EmbeddingCach
 
 void SamModel::lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, int rows, Linear32 const& l, bool relu,
                    float* y, int64_t ys) const {
+    // token-side Linears on contiguous rows go to the tensor cores (tf32);
+    // the strided / position-encoded / tiny ones stay on the CUDA-core kernel
+    if (!x2 && xs == l.k && ys == l.n && l.n % 16 == 0) {  // by shape only: a prompt gets the same bits alone or in a batch
+        gemm32(s, x, rows, l, y, relu ? gemm::ACT_RELU : gemm::ACT_NONE);
+        return;
+    }
     dec::linear_small(s, x, xs, x2, xs, rows, l.k, l.w.get(), l.b.get(), l.n, relu, y, ys);
 }
 
