@@ -26,6 +26,7 @@ SOURCES = [
     "kernels/gemm.cu",
     "kernels/encoder_kernels.cu",
     "kernels/window_attention.cu",
+    "kernels/patch_embed.cu",
     "kernels/decoder_kernels.cu",
     "kernels/t2i_attention.cu",
     "kernels/prepost_kernels.cu",

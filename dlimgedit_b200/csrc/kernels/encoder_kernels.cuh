@@ -6,6 +6,8 @@
 
 #include "../act.hpp"
 
+#include <cuda.h>
+
 namespace dlimg {
 namespace enc {
 
@@ -24,6 +26,15 @@ struct ImageDesc {
 // tap = (ky*3+kx)*3+ci), bias [32].
 void conv1_preprocess(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h, int channels,
                       float const* weight, float const* bias, act_t* out);
+
+// The whole PatchEmbed in one kernel (patch_embed.cu): preprocess + conv1 + GELU + conv2 -> out (B, 256, 256, 64).
+// w1_frag: conv1 weights from patch_embed_w1_fragments(); w2_map: TMA descriptor of the conv2 weights as a K-major
+// (64, 320) matrix, K = (ky, kx, ci) zero-padded from 288, box 64 rows.  c1_debug (optional): also writes the
+// (B, 512, 512, 32) conv1 activation (debug tap).
+void patch_embed(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h, int channels, uint32_t const* w1_frag,
+                 float const* b1, CUtensorMap const& w2_map, float const* b2, act_t* out, act_t* c1_debug, int num_sms);
+// (27, 32) fp32 conv1 weights [(ky*3+kx)*3+ci][oc] -> 512 packed fp16 pairs in mma B-fragment order.
+void patch_embed_w1_fragments(float const* w27x32, uint32_t* out512);
 
 // im2col for 3x3 / pad 1 convolutions on NHWC bf16: out[(b,oy,ox)][(ky,kx,c)] (K = 9*C).
 void im2col3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, act_t* out);

@@ -46,6 +46,9 @@ constexpr int kBlockM = 128;
 constexpr int kMaxBlockN = 256;
 constexpr int kKBytes = 128;  // bytes of K per row per stage == swizzle span
 
+// Memoised TMA descriptor of a K-major operand: box = box_rows rows x 128 bytes of K, 128-byte swizzle.
+CUtensorMap make_tensor_map(Operand const& op, bool tf32, int box_rows);
+
 // Picks the widest legal tile width (multiple of 16, <= 256) that divides N.
 int pick_block_n(int N);
 

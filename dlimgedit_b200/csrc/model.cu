@@ -4,6 +4,7 @@
 #include "kernels/gemm.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -192,6 +193,17 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
         enc_.conv1_w.upload(o);
         enc_.conv1_b.upload(shift);
         enc_.conv2 = load_conv_bn(wf, E + "patch_embed.seq.2", 64, 32, 3);
+        {
+            std::vector<uint32_t> frag(512);
+            enc::patch_embed_w1_fragments(o.data(), frag.data());
+            enc_.conv1_frag.upload(frag);
+            std::vector<act_t> w2(64 * 288), w2p((size_t)64 * 320, f2act(0.f));
+            CUDA_CHECK(cudaMemcpy(w2.data(), enc_.conv2.w.get(), w2.size() * sizeof(act_t), cudaMemcpyDeviceToHost));
+            for (int n = 0; n < 64; ++n)
+                for (int k = 0; k < 288; ++k) w2p[(size_t)n * 320 + k] = w2[(size_t)n * 288 + k];
+            enc_.conv2_k320.upload(w2p);
+            enc_.conv2_map = gemm::make_tensor_map(gemm::Operand{enc_.conv2_k320.get(), 64, 320, 320}, false, 64);
+        }
     }
     // --- layer 0: MBConv x2
     for (int i = 0; i < 2; ++i) {
@@ -394,13 +406,22 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
     using gemm::ACT_GELU;
     using gemm::ACT_NONE;
 
-    // PatchEmbed: fused preprocess + conv1 + GELU, then conv2 as im2col + GEMM
-    enc::conv1_preprocess(s, images, batch, w, h, channels, enc_.conv1_w.get(), enc_.conv1_b.get(), ws.c1.get());
-    tap_act(s, tap, "conv1", ws.c1.get(), (size_t)B * 512 * 512 * 32);
-    enc::im2col3x3(s, ws.c1.get(), batch, 512, 512, 32, 2, ws.col.get());
+    // PatchEmbed: preprocess + conv1 + GELU + conv2 in one kernel (DLIMG_B200_UNFUSED_PATCH=1 keeps the three-kernel
+    // form: conv1, im2col, GEMM -- used to cross-check the fused kernel)
     act_t* x = ws.xa.get();
     act_t* y = ws.xb.get();
-    gemm16(s, ws.col.get(), B * 65536, enc_.conv2, x, ACT_NONE, nullptr);
+    static bool const unfused_patch = kActBf16 || std::getenv("DLIMG_B200_UNFUSED_PATCH") != nullptr;
+    if (unfused_patch) {
+        enc::conv1_preprocess(s, images, batch, w, h, channels, enc_.conv1_w.get(), enc_.conv1_b.get(), ws.c1.get());
+        tap_act(s, tap, "conv1", ws.c1.get(), (size_t)B * 512 * 512 * 32);
+        enc::im2col3x3(s, ws.c1.get(), batch, 512, 512, 32, 2, ws.col.get());
+        gemm16(s, ws.col.get(), B * 65536, enc_.conv2, x, ACT_NONE, nullptr);
+    } else {
+        bool const want_c1 = tap && tap->name && std::strcmp(tap->name, "conv1") == 0;
+        enc::patch_embed(s, images, batch, w, h, channels, enc_.conv1_frag.get(), enc_.conv1_b.get(), enc_.conv2_map,
+                         enc_.conv2.b.get(), x, want_c1 ? ws.c1.get() : nullptr, num_sms_);
+        tap_act(s, tap, "conv1", ws.c1.get(), (size_t)B * 512 * 512 * 32);
+    }
     tap_act(s, tap, "patch_embed", x, (size_t)B * 65536 * 64);
 
     // layer 0: MBConv x2 (1x1 expand + GELU, dw3x3 + GELU, 1x1 project + shortcut + GELU)

@@ -4,6 +4,8 @@
 #pragma once
 
 #include "common.hpp"
+
+#include <cuda.h>
 #include "kernels/decoder_kernels.cuh"
 #include "kernels/encoder_kernels.cuh"
 #include "weights.hpp"
@@ -89,6 +91,10 @@ struct StageCfg { int dim, res, depth, heads, ws; };
 struct EncoderW {
     DeviceBuffer<float> conv1_w, conv1_b;  // (27, 32), (32)
     Linear16 conv2;                        // (64, 288) K = (ky, kx, ci)
+    // fused PatchEmbed kernel: conv1 as mma fragments, conv2 K-padded to 320 with its TMA descriptor
+    DeviceBuffer<uint32_t> conv1_frag;
+    DeviceBuffer<act_t> conv2_k320;
+    CUtensorMap conv2_map;
     MBConvW mb[2];
     MergeW merge[3];
     std::vector<BlockW> blocks[3];
