@@ -223,11 +223,11 @@ struct DwAccH2 {
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[o][i] = __hfma2(f[i], wk[i], acc[o][i]);
     }
-    __device__ __forceinline__ uint4 result(int o, bool) {
+    __device__ __forceinline__ uint4 result(int o, bool gelu) {
         uint4 ov;
         __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) oh[i] = gelu_erf_h2(acc[o][i]);
+        for (int i = 0; i < 4; ++i) oh[i] = gelu ? gelu_erf_h2(acc[o][i]) : acc[o][i];
         return ov;
     }
 };
@@ -491,8 +491,8 @@ void launch_dwconv(cudaStream_t s, dim3 grid, act_t const* in, int H, int W, int
     constexpr int kTX = 4;
 #if !defined(DLIMG_B200_ACT_BF16)
     static bool const acc32 = std::getenv("DLIMG_B200_DW_ACC32") != nullptr;  // A/B switch for parity experiments
-    if (gelu && weight16 && !acc32) {
-        dwconv3x3_kernel<kStride, kTX, kC8, DwAccH2<kTX>, act_t><<<grid, 256, 0, s>>>(in, H, W, Ho, Wo, xgroups, weight16, bias, 1, out);
+    if (weight16 && !acc32) {
+        dwconv3x3_kernel<kStride, kTX, kC8, DwAccH2<kTX>, act_t><<<grid, 256, 0, s>>>(in, H, W, Ho, Wo, xgroups, weight16, bias, gelu ? 1 : 0, out);
         return;
     }
 #endif

@@ -464,7 +464,8 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
             tap_act(s, tap, (tn + ".att").c_str(), ws.big[2].get(), (size_t)rows * C);
             gemm16(s, ws.big[2].get(), rows, b.proj, x, ACT_NONE, x);
             tap_act(s, tap, (tn + ".proj").c_str(), x, (size_t)rows * C);
-            // local depthwise conv (no activation, no residual)
+            // local depthwise conv (no activation, no residual).  fp32 accumulation: its output IS the trunk (it replaces
+            // x), and the packed-half kernel cost 0.0006 of mask IoU here for 3 % of the step -- not worth it.
             enc::dwconv3x3(s, x, batch, c.res, c.res, C, 1, b.local_conv.w.get(), nullptr, b.local_conv.b.get(), false, y);
             tap_act(s, tap, (tn + ".lc").c_str(), y, (size_t)rows * C);
             // MLP branch: LN folded into fc1 (+ GELU), fc2 + residual

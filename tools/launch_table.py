@@ -9,7 +9,7 @@ L = collections.OrderedDict()
 for r in rows[hdr + 1:]:
     d = L.setdefault(int(r[0]), {'name': r[4].split('(')[0].split('::')[-1], 'grid': r[8]})
     d[r[12]] = float(r[14].replace(',', ''))
-starts = [i for i in L if 'conv1_preprocess' in L[i]['name']]
+starts = [i for i in L if 'conv1_preprocess' in L[i]['name'] or 'patch_embed' in L[i]['name']]
 step = int(sys.argv[sys.argv.index('--step') + 1]) if '--step' in sys.argv else 1
 s = starts[step]
 e = starts[step + 1] if step + 1 < len(starts) else max(L) + 1
