@@ -173,7 +173,8 @@ struct SmemPlan {
 };
 inline SmemPlan plan_smem(int block_n, bool staged) {
     SmemPlan p;
-    p.staging_bytes = staged ? (int)round_up64((int64_t)kBlockM * (block_n * 2 + kStagePad), 1024) : 0;
+    // 16 epilogue warps x 32 rows x (64-column share of the tile + pad), see the epilogue
+    p.staging_bytes = staged ? (int)round_up64((int64_t)kEpiWarps * 32 * ((((block_n >> 4) + 3) / 4) * 32 + kStagePad), 1024) : 0;
     int const stage_bytes = kAStageBytes + block_n * kKBytes;
     int const fixed = 1024 /*align*/ + 1024 /*barriers, keeps the stages 1024-aligned*/ + p.staging_bytes;
     p.stages = (kSmemLimit - fixed) / stage_bytes;
@@ -182,7 +183,9 @@ inline SmemPlan plan_smem(int block_n, bool staged) {
     return p;
 }
 
-template <int kTF32, bool kStaged>
+// kStaged kernels are additionally specialised on the activation (kAct) and on the folded LayerNorm (kLn), so the
+// slab loop carries no run-time branches; the direct kernels read both from EpiParams.
+template <int kTF32, bool kStaged, int kAct = ACT_NONE, bool kLn = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
                int K, int block_n, int num_stages, int staging_bytes, void* out, EpiParams ep) {
@@ -289,22 +292,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
     } else {
-        // ---------------- epilogue (16 warps; TMEM lane quarter = warp index mod 4, 16-column slabs dealt cyclically)
-        // The slabs of a tile are software-pipelined: the tcgen05.ld of slab k+1 is in flight while slab k is biased,
-        // activated and written (TMEM reads are ~64 B/clk/SM, i.e. ~2000 clk for a 128x256 fp32 tile: they have to
-        // overlap the arithmetic), and the accumulator stage is handed back to the MMA warp as soon as the last
-        // slab has landed in registers.  kStaged (plain 16-bit outputs): rows are staged in shared memory per lane
-        // quarter and written by the quarter's 128 threads as whole contiguous rows.
+        // ---------------- epilogue (16 warps; TMEM lane quarter = warp index mod 4) ----------------
+        // The block_n / 16 slabs of 16 columns are dealt to the four warps of a lane quarter as CONTIGUOUS ranges (at
+        // most 4 slabs = 64 columns each), so a warp owns a 32-row x (up to) 128-byte piece of the output tile.
+        // The slabs are software-pipelined: the tcgen05.ld of slab k+1 is in flight while slab k is biased, activated
+        // and written (TMEM reads are ~64 B/clk/SM, ~2000 clk for a 128x256 fp32 tile: they must overlap the
+        // arithmetic), and the accumulator stage is handed back to the MMA warp as soon as the last slab has landed
+        // in registers.  kStaged (plain 16-bit outputs): the warp transposes its piece through its own staging area
+        // in shared memory (row per lane in, 16-byte pieces of whole row segments out), so every global store
+        // instruction writes complete 64..128-byte segments and no CTA-level barrier is involved.
         int const quarter = warp & 3;
         int const slab = (warp - 2) >> 2;  // which of the kEpiWarps/4 warps of this lane quarter
-        constexpr int kSlabStride = (kEpiWarps / 4) * 16;
-        constexpr int kMaxSlabs = kMaxBlockN / kSlabStride;  // 4
-        uint32_t const pitch = (uint32_t)(block_n * 2 + kStagePad);
-        uint32_t const my_row = stage_out + (uint32_t)(quarter * 32 + lane) * pitch;
-        // cooperative store geometry: chunks of 16 bytes, cpr per row, 128 threads per quarter
-        int const cpr = block_n >> 3;
-        int const tq = slab * 32 + lane;
-        int const st_row0 = tq / cpr, st_chunk = tq - st_row0 * cpr, st_rows = 128 / cpr;
+        constexpr int kMaxSlabs = 4;
+        int const nslab = block_n >> 4;
+        int const s_cnt = nslab / 4 + (slab < (nslab & 3) ? 1 : 0);           // slabs of this warp
+        int const s_first = slab * (nslab / 4) + min(slab, nslab & 3);       // first slab
+        uint32_t const pitch = (uint32_t)(((nslab + 3) / 4) * 32 + kStagePad);  // bytes per staged row
+        uint32_t const my_stage = stage_out + (uint32_t)(quarter * 4 + slab) * 32u * pitch;
+        // store geometry: cpr 16-byte pieces per row segment, 32 / cpr rows per instruction
+        int const cpr = s_cnt * 2;
+        int const st_row0 = cpr ? lane / cpr : 32, st_chunk = cpr ? lane - st_row0 * cpr : 0, st_rows = cpr ? 32 / cpr : 1;
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int const acc = local & 1;
@@ -316,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (!kStaged) {
                 int const row = m0 + quarter * 32 + lane;
                 if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
-            } else if (ep.ln_stats) {
+            } else if (kLn) {
                 int const row = m0 + quarter * 32 + lane;
                 if (row < M) {
                     float2 const st = __ldg(ep.ln_stats + row);
@@ -326,10 +333,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            uint32_t const taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN);
+            uint32_t const taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN + s_first * 16);
             uint32_t r[2][16];
-            if (slab * 16 < block_n) {
-                tmem_ld16(taddr + (uint32_t)(slab * 16), r[0]);
+            if (s_cnt > 0) {
+                tmem_ld16(taddr, r[0]);
             } else {  // narrow tiles (block_n < 64): this warp owns no slab
                 tc_fence_before();
                 __syncwarp();
@@ -337,11 +344,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
 #pragma unroll
             for (int k = 0; k < kMaxSlabs; ++k) {
-                int const c = slab * 16 + k * kSlabStride;
-                if (c < block_n) {
+                if (k < s_cnt) {
+                    int const c = (s_first + k) * 16;
                     tmem_ld_wait();  // slab k is in r[k & 1]
-                    if (k + 1 < kMaxSlabs && c + kSlabStride < block_n) {
-                        tmem_ld16(taddr + (uint32_t)(c + kSlabStride), r[(k + 1) & 1]);
+                    if (k + 1 < kMaxSlabs && k + 1 < s_cnt) {
+                        tmem_ld16(taddr + (uint32_t)((k + 1) * 16), r[(k + 1) & 1]);
                     } else {
                         tc_fence_before();
                         __syncwarp();
@@ -351,11 +358,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
-                        if (ep.ln_stats) ln_bias16(v, ep.bias, ep.ln_colsum, n0 + c, rstd, nmr);
+                        if (kLn) ln_bias16(v, ep.bias, ep.ln_colsum, n0 + c, rstd, nmr);
                         else if (ep.bias) add_bias16(v, ep.bias, n0 + c);
                         uint4 x[2];
-                        activate_pack16(v, ep.act, x);
-                        uint32_t const dst = my_row + (uint32_t)c * 2u;
+                        activate_pack16(v, kAct, x);
+                        uint32_t const dst = my_stage + (uint32_t)lane * pitch + (uint32_t)(k * 32);
                         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x[0].x), "r"(x[0].y), "r"(x[0].z), "r"(x[0].w) : "memory");
                         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
                     } else if (orow >= 0) {
@@ -364,19 +371,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
             }
             if (kStaged) {
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+                __syncwarp();
                 if (st_row0 < st_rows) {
+                    act_t* const obase = reinterpret_cast<act_t*>(out) + n0 + s_first * 16 + st_chunk * 8;
                     for (int rr = st_row0; rr < 32; rr += st_rows) {
                         int const grow = m0 + quarter * 32 + rr;
                         if (grow < M) {
                             uint4 x;
-                            uint32_t const src = stage_out + (uint32_t)(quarter * 32 + rr) * pitch + (uint32_t)st_chunk * 16u;
+                            uint32_t const src = my_stage + (uint32_t)rr * pitch + (uint32_t)st_chunk * 16u;
                             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(src));
-                            *reinterpret_cast<uint4*>(reinterpret_cast<act_t*>(out) + (int64_t)grow * ep.ldc + n0 + st_chunk * 8) = x;
+                            *reinterpret_cast<uint4*>(obase + (int64_t)grow * ep.ldc) = x;
                         }
                     }
                 }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");  // staging rows reusable
+                __syncwarp();  // the staging area is private to this warp
             }
         }
     }
@@ -546,25 +554,30 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
     ProfScope prof(stream, tf32 ? CAT_GEMM_TF32 : CAT_GEMM_BF16, 2.0 * M * N * K,
                    (double)(tf32 ? 4 : 2) * ((double)M * K + (double)N * K) + (double)(ep.out_f32 ? 4 : 2) * M * N);
     int const grid = tiles < num_sms ? tiles : num_sms;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    });
     // plain 16-bit outputs go through the coalescing (staged) epilogue; residual / scatter / fp32 outputs store directly
     static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch
-    bool const staged = allow_staged && !tf32 && !ep.residual && !ep.row_map && !ep.out_f32 && block_n >= 64;
+    bool const staged = allow_staged && !tf32 && !ep.residual && !ep.row_map && !ep.out_f32 && block_n >= 64 &&
+                        (ep.act == ACT_NONE || ep.act == ACT_GELU);
     if (ep.ln_stats && (!staged || !ep.bias || !ep.ln_colsum))
         fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue), a bias and column sums");
     SmemPlan const sp = plan_smem(block_n, staged);
     DLIMG_ASSERT(sp.stages >= 2);
-    if (tf32)
-        gemm_tc_kernel<1, false><<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep);
-    else if (staged)
-        gemm_tc_kernel<0, true><<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep);
-    else
-        gemm_tc_kernel<0, false><<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep);
+    using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, void*, EpiParams);
+    Kernel kernel;
+    if (tf32) kernel = gemm_tc_kernel<1, false>;
+    else if (!staged) kernel = gemm_tc_kernel<0, false>;
+    else if (ep.ln_stats) kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, true> : gemm_tc_kernel<0, true, ACT_NONE, true>;
+    else kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, false> : gemm_tc_kernel<0, true, ACT_NONE, false>;
+    {
+        static std::mutex attr_mutex;
+        static std::map<void const*, bool> attr_done;
+        std::lock_guard<std::mutex> lock(attr_mutex);
+        if (!attr_done[(void const*)kernel]) {
+            CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            attr_done[(void const*)kernel] = true;
+        }
+    }
+    kernel<<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep);
     KERNEL_CHECK();
 }
 
