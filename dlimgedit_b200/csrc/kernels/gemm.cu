@@ -161,6 +161,50 @@ __device__ __forceinline__ void epilogue_store16(uint32_t const (&r)[16], EpiPar
     }
 }
 
+// The slabs of one warp for one tile, with a compile-time slab count so that the TMEM double buffer lives in fixed
+// registers (no moves) and the loop has no run-time conditions.
+struct SlabCtx {
+    uint32_t taddr;       // TMEM address of the warp's first slab (lane quarter + accumulator stage + column)
+    uint32_t tempty;      // accumulator-empty mbarrier of this stage
+    uint32_t stage_row;   // shared-memory address of this lane's staging row (kStaged)
+    int col0;             // global column of the first slab
+    int64_t orow;         // output row of this lane (direct path), -1 = none
+    float rstd, nmr;      // folded LayerNorm
+    int lane;
+};
+
+template <int kCnt, bool kStaged, int kAct, bool kLn>
+__device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams const& ep, void* out) {
+    uint32_t r[2][16];
+    tmem_ld16(cx.taddr, r[0]);
+#pragma unroll
+    for (int k = 0; k < kCnt; ++k) {
+        tmem_ld_wait();  // slab k is in r[k & 1]
+        if (k + 1 < kCnt) {
+            tmem_ld16(cx.taddr + (uint32_t)((k + 1) * 16), r[(k + 1) & 1]);
+        } else {
+            tc_fence_before();
+            __syncwarp();
+            if (cx.lane == 0) mbar_arrive(cx.tempty);  // all of this warp's slabs are out of TMEM
+        }
+        int const c = cx.col0 + k * 16;
+        if (kStaged) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
+            if (kLn) ln_bias16(v, ep.bias, ep.ln_colsum, c, cx.rstd, cx.nmr);
+            else if (ep.bias) add_bias16(v, ep.bias, c);
+            uint4 x[2];
+            activate_pack16(v, kAct, x);
+            uint32_t const dst = cx.stage_row + (uint32_t)(k * 32);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x[0].x), "r"(x[0].y), "r"(x[0].z), "r"(x[0].w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
+        } else if (cx.orow >= 0) {
+            epilogue_store16(r[k & 1], ep, out, cx.orow, c);
+        }
+    }
+}
+
 // Shared-memory plan (all sizes known on the host): [barriers | staging (kStaged) | stages x (A 16 KiB, B block_n*128 B)].
 // The stage count is whatever fits (up to kMaxStages): narrow-N GEMMs get deep rings (9 stages at block_n 64), which
 // they need because a stage then carries only 24 KiB towards the ~70 KiB per SM that HBM latency x bandwidth asks for.
@@ -303,7 +347,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // instruction writes complete 64..128-byte segments and no CTA-level barrier is involved.
         int const quarter = warp & 3;
         int const slab = (warp - 2) >> 2;  // which of the kEpiWarps/4 warps of this lane quarter
-        constexpr int kMaxSlabs = 4;
         int const nslab = block_n >> 4;
         int const s_cnt = nslab / 4 + (slab < (nslab & 3) ? 1 : 0);           // slabs of this warp
         int const s_first = slab * (nslab / 4) + min(slab, nslab & 3);       // first slab
@@ -333,42 +376,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            uint32_t const taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN + s_first * 16);
-            uint32_t r[2][16];
-            if (s_cnt > 0) {
-                tmem_ld16(taddr, r[0]);
-            } else {  // narrow tiles (block_n < 64): this warp owns no slab
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
-            }
-#pragma unroll
-            for (int k = 0; k < kMaxSlabs; ++k) {
-                if (k < s_cnt) {
-                    int const c = (s_first + k) * 16;
-                    tmem_ld_wait();  // slab k is in r[k & 1]
-                    if (k + 1 < kMaxSlabs && k + 1 < s_cnt) {
-                        tmem_ld16(taddr + (uint32_t)((k + 1) * 16), r[(k + 1) & 1]);
-                    } else {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(acc));  // all of this warp's slabs are out of TMEM
-                    }
-                    if (kStaged) {
-                        float v[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
-                        if (kLn) ln_bias16(v, ep.bias, ep.ln_colsum, n0 + c, rstd, nmr);
-                        else if (ep.bias) add_bias16(v, ep.bias, n0 + c);
-                        uint4 x[2];
-                        activate_pack16(v, kAct, x);
-                        uint32_t const dst = my_stage + (uint32_t)lane * pitch + (uint32_t)(k * 32);
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x[0].x), "r"(x[0].y), "r"(x[0].z), "r"(x[0].w) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
-                    } else if (orow >= 0) {
-                        epilogue_store16(r[k & 1], ep, out, orow, n0 + c);
-                    }
-                }
+            SlabCtx cx;
+            cx.taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN + s_first * 16);
+            cx.tempty = tempty_bar(acc);
+            cx.stage_row = my_stage + (uint32_t)lane * pitch;
+            cx.col0 = n0 + s_first * 16;
+            cx.orow = orow;
+            cx.rstd = rstd;
+            cx.nmr = nmr;
+            cx.lane = lane;
+            switch (s_cnt) {  // warp-uniform
+                case 4: epilogue_slabs<4, kStaged, kAct, kLn>(cx, ep, out); break;
+                case 3: epilogue_slabs<3, kStaged, kAct, kLn>(cx, ep, out); break;
+                case 2: epilogue_slabs<2, kStaged, kAct, kLn>(cx, ep, out); break;
+                case 1: epilogue_slabs<1, kStaged, kAct, kLn>(cx, ep, out); break;
+                default:  // narrow tiles (block_n < 64): this warp owns no slab
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    break;
             }
             if (kStaged) {
                 __syncwarp();
