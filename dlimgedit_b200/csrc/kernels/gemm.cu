@@ -171,6 +171,11 @@ struct SlabCtx {
     int64_t orow;         // output row of this lane (direct path), -1 = none
     float rstd, nmr;      // folded LayerNorm
     int lane;
+    uint32_t stage_base;  // shared-memory address of the warp's staging area, row pitch below (kStaged)
+    uint32_t pitch;
+    act_t* out_seg;       // output address of (first row of the warp's 32, first column of its range) (kStaged)
+    int64_t ldc;
+    int rows_valid;       // how many of the warp's 32 rows exist (M tail)
 };
 
 template <int kCnt, bool kStaged, int kAct, bool kLn>
@@ -202,6 +207,37 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
         } else if (cx.orow >= 0) {
             epilogue_store16(r[k & 1], ep, out, cx.orow, c);
         }
+    }
+    if (kStaged) {
+        // transpose through the warp's staging area: each instruction now covers 32 / cpr whole row segments
+        constexpr int kCpr = 2 * kCnt, kRows = 32 / kCpr, kIters = (32 + kRows - 1) / kRows;
+        __syncwarp();
+        int const row0 = cx.lane / kCpr, chunk = cx.lane - row0 * kCpr;
+        if (row0 < kRows) {
+            act_t* p = cx.out_seg + (int64_t)row0 * cx.ldc + chunk * 8;
+            constexpr int kBatch = 4;  // loads in flight per lane before their stores
+#pragma unroll
+            for (int it0 = 0; it0 < kIters; it0 += kBatch) {
+                uint4 x[kBatch];
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    int const rr = row0 + (it0 + j) * kRows;
+                    if (it0 + j < kIters && rr < 32) {
+                        uint32_t const src = cx.stage_base + (uint32_t)rr * cx.pitch + (uint32_t)chunk * 16u;
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x[j].x), "=r"(x[j].y), "=r"(x[j].z), "=r"(x[j].w) : "r"(src));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    int const rr = row0 + (it0 + j) * kRows;
+                    if (it0 + j < kIters) {
+                        if (rr < cx.rows_valid && rr < 32) *reinterpret_cast<uint4*>(p) = x[j];
+                        p += (int64_t)kRows * cx.ldc;
+                    }
+                }
+            }
+        }
+        __syncwarp();  // the staging area is private to this warp
     }
 }
 
@@ -352,9 +388,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int const s_first = slab * (nslab / 4) + min(slab, nslab & 3);       // first slab
         uint32_t const pitch = (uint32_t)(((nslab + 3) / 4) * 32 + kStagePad);  // bytes per staged row
         uint32_t const my_stage = stage_out + (uint32_t)(quarter * 4 + slab) * 32u * pitch;
-        // store geometry: cpr 16-byte pieces per row segment, 32 / cpr rows per instruction
-        int const cpr = s_cnt * 2;
-        int const st_row0 = cpr ? lane / cpr : 32, st_chunk = cpr ? lane - st_row0 * cpr : 0, st_rows = cpr ? 32 / cpr : 1;
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int const acc = local & 1;
@@ -385,6 +418,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             cx.rstd = rstd;
             cx.nmr = nmr;
             cx.lane = lane;
+            cx.stage_base = my_stage;
+            cx.pitch = pitch;
+            cx.out_seg = reinterpret_cast<act_t*>(out) + (int64_t)(m0 + quarter * 32) * ep.ldc + n0 + s_first * 16;
+            cx.ldc = ep.ldc;
+            cx.rows_valid = M - (m0 + quarter * 32);
             switch (s_cnt) {  // warp-uniform
                 case 4: epilogue_slabs<4, kStaged, kAct, kLn>(cx, ep, out); break;
                 case 3: epilogue_slabs<3, kStaged, kAct, kLn>(cx, ep, out); break;
@@ -395,22 +433,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(acc));
                     break;
-            }
-            if (kStaged) {
-                __syncwarp();
-                if (st_row0 < st_rows) {
-                    act_t* const obase = reinterpret_cast<act_t*>(out) + n0 + s_first * 16 + st_chunk * 8;
-                    for (int rr = st_row0; rr < 32; rr += st_rows) {
-                        int const grow = m0 + quarter * 32 + rr;
-                        if (grow < M) {
-                            uint4 x;
-                            uint32_t const src = my_stage + (uint32_t)rr * pitch + (uint32_t)st_chunk * 16u;
-                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(src));
-                            *reinterpret_cast<uint4*>(obase + (int64_t)grow * ep.ldc) = x;
-                        }
-                    }
-                }
-                __syncwarp();  // the staging area is private to this warp
             }
         }
     }
