@@ -240,14 +240,31 @@ def run_ours(args):
     value = world * B * K / (ms * 1e-3)
 
     # ---------------- encoder end to end: pinned host pixels in, embeddings out ----------------
-    emb_host = torch.empty(B, 256, 64, 64, dtype=torch.float32).pin_memory()
+    # Every step uploads its B images from pinned host memory (process_batch on host views: the copy runs on the
+    # library's upload stream) and reads back every embedding (get_embedding_async: the library's download stream).
+    # Nothing waits inside a step, so the upload of step i+1 and the download of step i-1 overlap the encoder of
+    # step i; the timed region ends after Environment.synchronize(), when the last embedding has reached the host.
+    n_out = 3
+    emb_host = [torch.empty(B, 256, 64, 64, dtype=torch.float32).pin_memory() for _ in range(n_out)]
 
     def step_e2e(i):
         segs = env.process_batch(host_views(i % n_sets))
+        dst = emb_host[i % n_out]
         for j, s in enumerate(segs):
             # D2H of the (1,256,64,64) fp32 embedding: the reference keeps it in host memory (segmentation.cpp:124)
-            s.embedding(out=emb_host[j].numpy())
+            s.embedding_async(dst[j].numpy())
         keep.append(segs)
+
+    def timed_e2e(steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step_e2e(i)
+        env.synchronize()  # all uploads, encoders and downloads of the timed steps are complete
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
 
     k_e2e = max(3, K // 2)
     if args.quick:
@@ -255,8 +272,9 @@ def run_ours(args):
     else:
         for i in range(min(W, 2)):
             step_e2e(i)
+        env.synchronize()
         keep.clear()
-        ms_e2e = timed(step_e2e, k_e2e)
+        ms_e2e = timed_e2e(k_e2e)
         keep.clear()
     e2e_value = world * B * k_e2e / (ms_e2e * 1e-3)
 
@@ -349,7 +367,7 @@ def run_ours(args):
                        "parallelism": f"image-sharded x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * img_bytes,
                     "d2h_bytes_per_step": B * 256 * 64 * 64 * 4, "ms_per_step": ms_e2e / k_e2e,
-                    "path": "ctypes -> dlimg_b200_Ext.process_batch(host views) + get_embedding per image"},
+                    "path": "ctypes -> dlimg_b200_Ext.process_batch(host views) + get_embedding_async per image, synchronize at the end"},
             "gpu_launches": int(launches),
             "clocks": clock_info,
             "roofline": roofline,

@@ -102,8 +102,7 @@ dlimg_Result ext_set_stream(dlimg_Environment env, void* stream) {
 
 dlimg_Result ext_synchronize(dlimg_Environment env) {
     return try_([=] {
-        to_impl(env).bind_device();
-        CUDA_CHECK(cudaStreamSynchronize(to_impl(env).stream()));
+        to_impl(env).synchronize();
     });
 }
 
@@ -147,6 +146,10 @@ dlimg_Result ext_compute_masks_batch(dlimg_Environment env, dlimg_Segmentation c
 
 dlimg_Result ext_get_embedding(dlimg_Segmentation seg, float* out_host) {
     return try_([=] { to_impl(seg).embedding_nchw(out_host); });
+}
+
+dlimg_Result ext_get_embedding_async(dlimg_Segmentation seg, float* out_host) {
+    return try_([=] { to_impl(seg).embedding_nchw_async(out_host); });
 }
 
 dlimg_Result ext_get_low_res_logits(dlimg_Segmentation seg, dlimg_b200_Prompt const* prompt, float* logits, float* iou) {
@@ -309,7 +312,7 @@ DLIMG_B200_EXPORT dlimg_Api const* dlimg_init(void) {
 DLIMG_B200_EXPORT dlimg_b200_Ext const* dlimg_b200_ext_init(void) {
     using namespace dlimg;
     ext_.struct_size = sizeof(dlimg_b200_Ext);
-    ext_.abi_version = 1;
+    ext_.abi_version = 2;
     ext_.set_stream = ext_set_stream;
     ext_.synchronize = ext_synchronize;
     ext_.get_stats = ext_get_stats;
@@ -323,6 +326,7 @@ DLIMG_B200_EXPORT dlimg_b200_Ext const* dlimg_b200_ext_init(void) {
     ext_.threshold_mask = ext_threshold_mask;
     ext_.profile_enable = ext_profile_enable;
     ext_.profile_read = ext_profile_read;
+    ext_.get_embedding_async = ext_get_embedding_async;
     return &ext_;
 }
 

@@ -48,9 +48,14 @@ void check_view(dlimg_ImageView const& v) {
 // ---------------------------------------------------------------------------------------------
 StreamBuffer::StreamBuffer(size_t bytes, cudaStream_t stream) : stream_(stream) {
     CUDA_CHECK(cudaMallocAsync(&ptr_, bytes, stream));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ready_, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&last_read_, cudaEventDisableTiming));
 }
 StreamBuffer::~StreamBuffer() {
+    if (read_) cudaStreamWaitEvent(stream_, last_read_, 0);  // a download on the copy-out stream may still be in flight
     if (ptr_) cudaFreeAsync(ptr_, stream_);
+    if (ready_) cudaEventDestroy(ready_);
+    if (last_read_) cudaEventDestroy(last_read_);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -103,6 +108,11 @@ EnvironmentImpl::EnvironmentImpl(dlimg_Options const& opts) {
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
     num_sms_ = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&h2d_done_, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&d2h_ready_, cudaEventDisableTiming));
+    for (auto& e : input_free_) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     max_batch_ = env_int("DLIMG_B200_MAX_BATCH", 8, 1, 64);
     max_prompts_ = env_int("DLIMG_B200_MAX_PROMPTS", 32, 1, 256);
     use_graphs_ = env_int("DLIMG_B200_GRAPHS", 1, 0, 1) != 0;
@@ -123,6 +133,19 @@ EnvironmentImpl::~EnvironmentImpl() {
     cudaDeviceSynchronize();
     for (auto& g : encode_graphs_) cudaGraphExecDestroy(g.second.exec);
     if (own_stream_) cudaStreamDestroy(own_stream_);
+    if (copy_in_) cudaStreamDestroy(copy_in_);
+    if (copy_out_) cudaStreamDestroy(copy_out_);
+    if (h2d_done_) cudaEventDestroy(h2d_done_);
+    if (d2h_ready_) cudaEventDestroy(d2h_ready_);
+    for (auto e : input_free_)
+        if (e) cudaEventDestroy(e);
+}
+
+void EnvironmentImpl::synchronize() {
+    bind_device();
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+    CUDA_CHECK(cudaStreamSynchronize(copy_in_));
+    CUDA_CHECK(cudaStreamSynchronize(copy_out_));
 }
 
 void EnvironmentImpl::bind_device() const { CUDA_CHECK(cudaSetDevice(device_)); }
@@ -178,21 +201,14 @@ prepost::ResizeDeviceTables EnvironmentImpl::resize_tables(int in_w, int in_h, i
     return t;
 }
 
-// Makes one image available to the encoder as device-resident u8 at <= 1024 on the long side.
-uint8_t* EnvironmentImpl::prepare_input(dlimg_ImageView const& view, bool on_device, prepost::LongestSide const& size, int slot,
-                                        enc::ImageDesc& desc) {
+// Makes one image (already in device memory: the caller's buffer or an uploaded copy) available to the encoder as
+// u8 at <= 1024 on the long side.
+uint8_t* EnvironmentImpl::prepare_input(dlimg_ImageView const& view, uint8_t const* dev_pixels, int dev_stride,
+                                        prepost::LongestSide const& size, int slot, enc::ImageDesc& desc) {
     cudaStream_t const s = stream();
     int const bpp = bytes_per_pixel(view.channels);
-    size_t const row = (size_t)view.width * bpp;
-    uint8_t const* src = view.pixels;
-    int src_stride = view.stride;
-    if (!on_device) {
-        uint8_t* dst = input_px_.get() + (size_t)slot * input_slot_bytes_;
-        CUDA_CHECK(cudaMemcpy2DAsync(dst, row, view.pixels, (size_t)view.stride, row, (size_t)view.height, cudaMemcpyHostToDevice, s));
-        g_h2d_bytes += row * (size_t)view.height;
-        src = dst;
-        src_stride = (int)row;
-    }
+    uint8_t const* src = dev_pixels;
+    int const src_stride = dev_stride;
     if (size.needs_resize) {
         size_t const need = (size_t)view.height * size.w * bpp;
         if (resize_scratch_.size() < need) {
@@ -271,12 +287,14 @@ void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, boo
     cudaStream_t const s = stream();
     prepost::LongestSide const size = prepost::resize_longest_side(views[0].width, views[0].height, kImageSize);
     int const bpp = bytes_per_pixel(views[0].channels);
+    size_t const row_bytes = (size_t)views[0].width * bpp;
     if (!on_device) {
         size_t const slot = ((size_t)views[0].width * views[0].height * bpp + 255) & ~(size_t)255;
-        if (slot > input_slot_bytes_ || !input_px_) {
-            CUDA_CHECK(cudaStreamSynchronize(s));
+        if (slot > input_slot_bytes_ || !input_px_[0]) {
+            synchronize();
             input_slot_bytes_ = slot;
-            input_px_.allocate(slot * (size_t)max_batch_);
+            for (auto& b : input_px_) b.allocate(slot * (size_t)max_batch_);
+            input_used_[0] = input_used_[1] = false;
         }
     }
     if (size.needs_resize && !resized_px_) resized_px_.allocate(kResizedSlot * (size_t)max_batch_);
@@ -284,19 +302,49 @@ void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, boo
     std::vector<enc::ImageDesc> descs((size_t)max_batch_);
     for (int start = 0; start < count; start += max_batch_) {
         int const B = std::min(max_batch_, count - start);
-        auto store = std::make_shared<StreamBuffer>(sizeof(float) * (size_t)B * dec::kImgTokens * kEmbedDim, s);
-        for (int i = 0; i < B; ++i) prepare_input(views[start + i], on_device, size, i, descs[(size_t)i]);
+        // one allocation per chunk: B token-major embeddings (what the decoder reads) + the same in NCHW (what
+        // get_embedding returns: the reference's `image_embeddings` layout), so a read is a plain copy
+        size_t const emb_floats = (size_t)dec::kImgTokens * kEmbedDim;
+        auto store = std::make_shared<StreamBuffer>(sizeof(float) * 2 * (size_t)B * emb_floats, s);
+        int const set = input_flip_;
+        if (!on_device) {
+            // upload on the copy stream into slot set `set`, once the encoder that last read it is done; the work
+            // stream only waits for this chunk's upload, so uploads run ahead of / alongside earlier encoders
+            if (input_used_[set]) CUDA_CHECK(cudaStreamWaitEvent(copy_in_, input_free_[set], 0));
+            for (int i = 0; i < B; ++i) {
+                dlimg_ImageView const& v = views[start + i];
+                uint8_t* dst = input_px_[set].get() + (size_t)i * input_slot_bytes_;
+                CUDA_CHECK(cudaMemcpy2DAsync(dst, row_bytes, v.pixels, (size_t)v.stride, row_bytes, (size_t)v.height,
+                                             cudaMemcpyHostToDevice, copy_in_));
+                g_h2d_bytes += row_bytes * (size_t)v.height;
+            }
+            CUDA_CHECK(cudaEventRecord(h2d_done_, copy_in_));
+            CUDA_CHECK(cudaStreamWaitEvent(s, h2d_done_, 0));
+        }
+        for (int i = 0; i < B; ++i) {
+            dlimg_ImageView const& v = views[start + i];
+            if (on_device) prepare_input(v, v.pixels, v.stride, size, i, descs[(size_t)i]);
+            else prepare_input(v, input_px_[set].get() + (size_t)i * input_slot_bytes_, (int)row_bytes, size, i, descs[(size_t)i]);
+        }
         encode_chunk(descs.data(), B, size, views[0].channels, store->floats(), nullptr);
+        enc::tokens_to_nchw(s, store->floats(), B, dec::kImgTokens, kEmbedDim, store->floats() + (size_t)B * emb_floats);
+        CUDA_CHECK(cudaEventRecord(store->ready(), s));
+        if (!on_device) {
+            CUDA_CHECK(cudaEventRecord(input_free_[set], s));
+            input_used_[set] = true;
+            input_flip_ ^= 1;
+        }
         for (int i = 0; i < B; ++i) {
             SegmentationImpl* seg = out[start + i];
             seg->size_ = size;
             seg->emb_store_ = store;
-            seg->emb_ = store->floats() + (size_t)i * dec::kImgTokens * kEmbedDim;
+            seg->emb_ = store->floats() + (size_t)i * emb_floats;
+            seg->emb_nchw_ = store->floats() + ((size_t)B + i) * emb_floats;
             seg->cache_.ready = false;
         }
     }
-    // host pixels are only borrowed for the duration of the call
-    if (!on_device) CUDA_CHECK(cudaStreamSynchronize(s));
+    // host pixels are only borrowed for the duration of the call: wait for the uploads (not for the encoder)
+    if (!on_device) CUDA_CHECK(cudaStreamSynchronize(copy_in_));
 }
 
 void EnvironmentImpl::compute_masks_batch(SegmentationImpl* const* segs, dlimg_b200_Prompt const* prompts, int count, bool multi,
@@ -472,7 +520,7 @@ size_t EnvironmentImpl::encode_tap(dlimg_ImageView const* views, int count, char
     prepost::LongestSide const size = prepost::resize_longest_side(views[0].width, views[0].height, kImageSize);
     if (size.needs_resize && !resized_px_) resized_px_.allocate(kResizedSlot * (size_t)max_batch_);
     std::vector<enc::ImageDesc> descs((size_t)count);
-    for (int i = 0; i < count; ++i) prepare_input(views[i], true, size, i, descs[(size_t)i]);
+    for (int i = 0; i < count; ++i) prepare_input(views[i], views[i].pixels, views[i].stride, size, i, descs[(size_t)i]);
     DeviceBuffer<float> emb((size_t)count * dec::kImgTokens * kEmbedDim);
     Tap tap;
     tap.name = tap_name;
@@ -514,17 +562,23 @@ void SegmentationImpl::compute_mask(int const* point, int const* region, uint8_t
     }
 }
 
-void SegmentationImpl::embedding_nchw(float* out_host) {
+// The encoder leaves an NCHW copy next to the token-major embedding; the device->host transfer runs on the copy-out
+// stream as soon as that chunk is ready, so it overlaps whatever the work stream does next.
+void SegmentationImpl::embedding_nchw_async(float* out_host) {
     std::lock_guard<std::mutex> lock(env_.mutex());
     env_.bind_device();
     if (!encoded()) fail("segmentation handle holds no processed image");
-    cudaStream_t const s = env_.stream();
     size_t const n = (size_t)dec::kImgTokens * kEmbedDim;
-    if (!env_.emb_scratch_) env_.emb_scratch_.allocate(n);
-    enc::tokens_to_nchw(s, emb_, 1, dec::kImgTokens, kEmbedDim, env_.emb_scratch_.get());
-    CUDA_CHECK(cudaMemcpyAsync(out_host, env_.emb_scratch_.get(), n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
+    CUDA_CHECK(cudaStreamWaitEvent(env_.copy_out_, emb_store_->ready(), 0));
+    CUDA_CHECK(cudaMemcpyAsync(out_host, emb_nchw_, n * sizeof(float), cudaMemcpyDeviceToHost, env_.copy_out_));
+    CUDA_CHECK(cudaEventRecord(emb_store_->last_read(), env_.copy_out_));
+    emb_store_->mark_read();
     g_d2h_bytes += n * sizeof(float);
+}
+
+void SegmentationImpl::embedding_nchw(float* out_host) {
+    embedding_nchw_async(out_host);
+    CUDA_CHECK(cudaStreamSynchronize(env_.copy_out_));
 }
 
 }  // namespace dlimg

@@ -34,10 +34,18 @@ class StreamBuffer {
     StreamBuffer(StreamBuffer const&) = delete;
     StreamBuffer& operator=(StreamBuffer const&) = delete;
     float* floats() const { return static_cast<float*>(ptr_); }
+    // Cross-stream lifetime of an embedding store: `ready` is recorded on the work stream once the encoder has
+    // filled the buffer, `last_read` on the copy-out stream after each download; the destructor makes the free wait
+    // for the last download.
+    cudaEvent_t ready() const { return ready_; }
+    cudaEvent_t last_read() const { return last_read_; }
+    void mark_read() { read_ = true; }
 
   private:
     void* ptr_ = nullptr;
     cudaStream_t stream_ = nullptr;
+    cudaEvent_t ready_ = nullptr, last_read_ = nullptr;
+    bool read_ = false;
 };
 
 // Page-locked host arena for small parameter uploads (prompt coordinates, descriptors, pointer tables).
@@ -65,6 +73,7 @@ class EnvironmentImpl {
     SamModel& model();  // loaded on first use (reference lazy.hpp:10-13)
     cudaStream_t stream() const { return user_stream_ ? user_stream_ : own_stream_; }
     void set_stream(cudaStream_t s) { user_stream_ = s; }
+    void synchronize();  // the work stream and both copy streams
     void bind_device() const;
 
     // Encodes `count` images (host or device pixels) and fills `out` with new handles.
@@ -95,8 +104,8 @@ class EnvironmentImpl {
     DeviceAxisPlan const& axis_plan(int in_size, int out_size);
     void encode_chunk(enc::ImageDesc const* host_descs, int batch, prepost::LongestSide const& size, int channels,
                       float* emb_out, Tap* tap);
-    uint8_t* prepare_input(dlimg_ImageView const& view, bool on_device, prepost::LongestSide const& size, int slot,
-                           enc::ImageDesc& desc);
+    uint8_t* prepare_input(dlimg_ImageView const& view, uint8_t const* dev_pixels, int dev_stride,
+                           prepost::LongestSide const& size, int slot, enc::ImageDesc& desc);
 
     int device_ = 0;
     int num_sms_ = 148;
@@ -111,7 +120,14 @@ class EnvironmentImpl {
     std::unique_ptr<EncoderWorkspace> enc_ws_;
     std::unique_ptr<DecoderWorkspace> dec_ws_;
     std::unique_ptr<PinnedArena> pinned_;
-    DeviceBuffer<uint8_t> input_px_;      // uploaded originals, max_batch slots
+    // Host pixels are uploaded on a dedicated copy stream into one of two slot sets, so the upload of call i+1
+    // overlaps the encoder of call i; embeddings leave on a second copy stream (get_embedding_async).
+    cudaStream_t copy_in_ = nullptr, copy_out_ = nullptr;
+    cudaEvent_t h2d_done_ = nullptr, d2h_ready_ = nullptr;
+    cudaEvent_t input_free_[2] = {nullptr, nullptr};  // the encoder that read slot set k has finished
+    bool input_used_[2] = {false, false};
+    int input_flip_ = 0;
+    DeviceBuffer<uint8_t> input_px_[2];   // uploaded originals, max_batch slots each
     DeviceBuffer<uint8_t> resized_px_;    // resized images (<= 1024 x 1024 x 4 each), max_batch slots
     DeviceBuffer<float> resize_scratch_;  // horizontal-pass intermediate
     size_t input_slot_bytes_ = 0;
@@ -123,7 +139,6 @@ class EnvironmentImpl {
     bool use_graphs_ = true;  // $DLIMG_B200_GRAPHS=0 forces eager launches
     struct EncodeGraph { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; };
     std::map<std::tuple<int, int, int, int>, EncodeGraph> encode_graphs_;
-    DeviceBuffer<float> emb_scratch_;      // NCHW staging for get_embedding
 };
 
 class SegmentationImpl {
@@ -132,7 +147,8 @@ class SegmentationImpl {
 
     void process(dlimg_ImageView const& view);  // reference segmentation.cpp:121-129
     void compute_mask(int const* point, int const* region, uint8_t** out_masks, float* out_accuracy);  // :131-174
-    void embedding_nchw(float* out_host);
+    void embedding_nchw(float* out_host);        // blocking
+    void embedding_nchw_async(float* out_host);  // returns at once; complete after EnvironmentImpl::synchronize()
 
     int width() const { return size_.orig_w; }
     int height() const { return size_.orig_h; }
@@ -145,6 +161,7 @@ class SegmentationImpl {
     prepost::LongestSide size_;
     std::shared_ptr<StreamBuffer> emb_store_;         // shared by the images of one encoder chunk
     float* emb_ = nullptr;                            // (4096, 256) fp32 token-major
+    float* emb_nchw_ = nullptr;                       // (256, 4096) fp32: the reference's `image_embeddings` layout
     EmbeddingCache cache_;
 };
 

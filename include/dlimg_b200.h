@@ -131,7 +131,7 @@ struct dlimg_b200_Ext {
      * the environment's own stream).  Batch calls are asynchronous with respect to the host unless
      * stated otherwise; use `synchronize` or your own events on that stream. */
     dlimg_Result (*set_stream)(dlimg_Environment, void* cuda_stream);
-    dlimg_Result (*synchronize)(dlimg_Environment);
+    dlimg_Result (*synchronize)(dlimg_Environment); /* the work stream and the library's two copy streams */
     dlimg_Result (*get_stats)(dlimg_Environment, dlimg_b200_Stats*);
 
     /* Encode `count` images.  views[i].pixels is a HOST pointer when pixels_on_device == 0 (copied
@@ -178,6 +178,12 @@ struct dlimg_b200_Ext {
      * `capacity` non-empty categories, clears the recording and returns the number written through *count. */
     dlimg_Result (*profile_enable)(dlimg_Environment, int on);
     dlimg_Result (*profile_read)(dlimg_Environment, dlimg_b200_ProfileEntry* out, int capacity, int* count);
+
+    /* abi_version >= 2.  get_embedding without the wait: the NCHW copy is queued behind the encoder and the
+     * device->host transfer runs on the library's copy-out stream, overlapping later work (e.g. the next
+     * process_batch, whose host->device upload runs on a third stream).  out_host should be page-locked and must
+     * stay valid until `synchronize` returns. */
+    dlimg_Result (*get_embedding_async)(dlimg_Segmentation, float* out_host);
 };
 
 DLIMG_B200_EXPORT struct dlimg_b200_Ext const* dlimg_b200_ext_init(void);

@@ -88,3 +88,21 @@ def test_launch_counter_moves(env):
     before = env.stats()["kernel_launches"]
     dl.Segmentation.process(dl.ImageView(synthetic_image(128, 128, 3, 2), channels=dl.Channels.rgb), env)
     assert env.stats()["kernel_launches"] > before + 50
+
+
+def test_async_embedding_read_matches_blocking(env):
+    """get_embedding_async (download stream) delivers the same bytes as the blocking read once synchronize returns, also
+    when several calls with host pixels are in flight (double-buffered upload slots)."""
+    import torch
+    from conftest import synthetic_image
+    imgs = [synthetic_image(1024, 1024, 4, seed=20 + i) for i in range(3)]
+    outs = [torch.empty(1, 256, 64, 64).pin_memory() for _ in imgs]
+    segs = []
+    for im, o in zip(imgs, outs):  # three back-to-back calls, nothing waits in between
+        seg = env.process_batch([dl.ImageView(im, channels=dl.Channels.rgba)])[0]
+        seg.embedding_async(o.numpy())
+        segs.append(seg)
+    env.synchronize()
+    for seg, o in zip(segs, outs):
+        assert np.array_equal(o.numpy(), seg.embedding())
+    assert not np.array_equal(outs[0].numpy(), outs[1].numpy())
