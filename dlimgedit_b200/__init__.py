@@ -309,17 +309,22 @@ class Environment:
         return segs
 
     def compute_masks_batch(self, segs: Sequence["Segmentation"], prompts: Sequence, multi: bool = False,
-                            masks_out: Sequence[int] = None, ious_out: int = 0):
-        """Host mode (masks_out None): returns (list of uint8 arrays (n, H, W), float32 array (count, n)).
+                            masks_out: Sequence[int] = None, ious_out: int = 0, host_out: Sequence[np.ndarray] = None,
+                            host_ious: np.ndarray = None):
+        """Host mode (masks_out None): returns (list of uint8 arrays (n, H, W), float32 array (count, n)); pass
+        `host_out` / `host_ious` to have the results written into your own (ideally page-locked) arrays instead of
+        freshly allocated pageable ones.
         Device mode: masks_out = device addresses (one per prompt, n*W*H bytes), ious_out = device address."""
         cnt = len(prompts)
         n = 3 if multi else 1
         harr = (_H * cnt)(*[s._h for s in segs])
         parr = (_Prompt * cnt)(*[_to_prompt(p) for p in prompts])
         if masks_out is None:
-            outs = [np.empty((n, s.extent().height, s.extent().width), np.uint8) for s in segs]
+            outs = host_out if host_out is not None else [np.empty((n, s.extent().height, s.extent().width), np.uint8) for s in segs]
+            assert len(outs) == cnt and all(o.dtype == np.uint8 and o.flags["C_CONTIGUOUS"] for o in outs)
             ptrs = (ctypes.c_void_p * cnt)(*[o.ctypes.data for o in outs])
-            ious = np.zeros((cnt, n), np.float32)
+            ious = host_ious if host_ious is not None else np.zeros((cnt, n), np.float32)
+            assert ious.dtype == np.float32 and ious.size == cnt * n
             _check(ext().compute_masks_batch(self._h, harr, parr, cnt, int(multi), ptrs,
                                              ctypes.c_void_p(ious.ctypes.data), 0))
             return outs, ious

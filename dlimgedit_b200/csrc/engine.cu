@@ -113,6 +113,8 @@ EnvironmentImpl::EnvironmentImpl(dlimg_Options const& opts) {
     CUDA_CHECK(cudaEventCreateWithFlags(&h2d_done_, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&d2h_ready_, cudaEventDisableTiming));
     for (auto& e : input_free_) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&mask_ready_, cudaEventDisableTiming));
+    for (auto& e : mask_free_) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     max_batch_ = env_int("DLIMG_B200_MAX_BATCH", 8, 1, 64);
     max_prompts_ = env_int("DLIMG_B200_MAX_PROMPTS", 32, 1, 256);
     use_graphs_ = env_int("DLIMG_B200_GRAPHS", 1, 0, 1) != 0;
@@ -138,6 +140,9 @@ EnvironmentImpl::~EnvironmentImpl() {
     if (h2d_done_) cudaEventDestroy(h2d_done_);
     if (d2h_ready_) cudaEventDestroy(d2h_ready_);
     for (auto e : input_free_)
+        if (e) cudaEventDestroy(e);
+    if (mask_ready_) cudaEventDestroy(mask_ready_);
+    for (auto e : mask_free_)
         if (e) cudaEventDestroy(e);
 }
 
@@ -356,12 +361,16 @@ void EnvironmentImpl::compute_masks_batch(SegmentationImpl* const* segs, dlimg_b
     SamModel& m = model();
     DecoderWorkspace& ws = decoder_ws();
     int const n = multi ? 3 : 1;
+    int const kHostGroup = env_int("DLIMG_B200_HOST_GROUP", 256, 1, 256);  // splitting a call into smaller decoder groups to overlap downloads costs more than it hides (18.3k -> 9.5k masks/s at 16), so the default keeps whole groups
+    int host_group = 0;
     int i = 0;
     while (i < count) {
         SegmentationImpl* seg = segs[i];
         if (!seg || !seg->encoded()) fail("compute_mask: segmentation handle holds no processed image");
         int j = i;
-        while (j < count && segs[j] == seg && j - i < max_prompts_) ++j;
+        // host-destined masks go in groups of at most kHostGroup prompts so that downloads overlap decoding
+        int const group_cap = on_device ? max_prompts_ : std::min(max_prompts_, kHostGroup);
+        while (j < count && segs[j] == seg && j - i < group_cap) ++j;
         int const P = j - i;
         if (!seg->cache_.ready) m.prepare_embedding(s, seg->emb_, seg->cache_);
 
@@ -412,24 +421,35 @@ void EnvironmentImpl::compute_masks_batch(SegmentationImpl* const* segs, dlimg_b
             prepost::mask_postprocess(s, ws.low.get(), 65536, ws.plane_index.get(), planes, seg->size_.w, seg->size_.h, W, H,
                                       plane_ptrs_.get());
         } else {
-            if (mask_out_.size() < plane_bytes * planes) {
-                CUDA_CHECK(cudaStreamSynchronize(s));
-                mask_out_.allocate(plane_bytes * planes);
+            int const flip = host_group & 1;
+            ++host_group;
+            if (mask_out_[flip].size() < plane_bytes * planes) {
+                synchronize();
+                mask_out_[flip].allocate(plane_bytes * (size_t)std::max(planes, std::min(max_prompts_, kHostGroup) * 3));
+                mask_used_[flip] = false;
             }
+            if (mask_used_[flip]) CUDA_CHECK(cudaStreamWaitEvent(s, mask_free_[flip], 0));  // its previous download is done
             prepost::mask_postprocess_contiguous(s, ws.low.get(), 65536, ws.plane_index.get(), planes, seg->size_.w,
-                                                 seg->size_.h, W, H, mask_out_.get());
-            for (int k = 0; k < planes; ++k)
-                CUDA_CHECK(cudaMemcpyAsync(planes_out[(size_t)i * n + k], mask_out_.get() + plane_bytes * k, plane_bytes,
-                                           cudaMemcpyDeviceToHost, s));
-            g_d2h_bytes += plane_bytes * planes;
-            if (ious_out) {
+                                                 seg->size_.h, W, H, mask_out_[flip].get());
+            if (ious_out) {  // tiny, and ws.iou_sel is rewritten by the next group: keep it on the work stream
                 CUDA_CHECK(cudaMemcpyAsync(ious_out + (size_t)i * n, ws.iou_sel.get(), sizeof(float) * (size_t)planes,
                                            cudaMemcpyDeviceToHost, s));
                 g_d2h_bytes += sizeof(float) * (size_t)planes;
             }
-            CUDA_CHECK(cudaStreamSynchronize(s));  // staging buffer is reused by the next group
+            CUDA_CHECK(cudaEventRecord(mask_ready_, s));
+            CUDA_CHECK(cudaStreamWaitEvent(copy_out_, mask_ready_, 0));
+            for (int k = 0; k < planes; ++k)
+                CUDA_CHECK(cudaMemcpyAsync(planes_out[(size_t)i * n + k], mask_out_[flip].get() + plane_bytes * k, plane_bytes,
+                                           cudaMemcpyDeviceToHost, copy_out_));
+            g_d2h_bytes += plane_bytes * planes;
+            CUDA_CHECK(cudaEventRecord(mask_free_[flip], copy_out_));
+            mask_used_[flip] = true;
         }
         i = j;
+    }
+    if (!on_device) {  // the caller's host buffers are complete when the call returns
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        CUDA_CHECK(cudaStreamSynchronize(copy_out_));
     }
 }
 

@@ -134,7 +134,11 @@ class EnvironmentImpl {
     DeviceBuffer<enc::ImageDesc> descs_;
     DeviceBuffer<float> srgb_decode_, srgb_threshold_;
     std::map<std::pair<int, int>, DeviceAxisPlan> plans_;
-    DeviceBuffer<uint8_t> mask_out_;       // device staging for host-destined masks
+    // device staging for host-destined masks, double-buffered: the download of one prompt group (copy-out stream)
+    // overlaps the decoder of the next
+    DeviceBuffer<uint8_t> mask_out_[2];
+    cudaEvent_t mask_ready_ = nullptr, mask_free_[2] = {nullptr, nullptr};
+    bool mask_used_[2] = {false, false};
     DeviceBuffer<uint8_t*> plane_ptrs_;
     bool use_graphs_ = true;  // $DLIMG_B200_GRAPHS=0 forces eager launches
     struct EncodeGraph { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; };
