@@ -36,7 +36,6 @@ struct EpiParams {
     void const* residual;
     int const* row_map;
     float2 const* ln_stats;
-    float const* ln_colsum;
     int act;
     int out_f32;
     int ldc;
@@ -51,17 +50,16 @@ __device__ __forceinline__ void add_bias16(float (&v)[16], float const* bias, in
     }
 }
 
-// folded LayerNorm: v = rstd * acc + (bias - mean * rstd * colsum), see Epilogue::ln_stats
-__device__ __forceinline__ void ln_bias16(float (&v)[16], float const* bias, float const* colsum, int col, float rstd, float nmr) {
+// folded LayerNorm with row-centred weights: v = rstd * acc + bias, see Epilogue::ln_stats
+__device__ __forceinline__ void ln_bias16(float (&v)[16], float const* bias, int col, float rstd) {
     float4 const* b4 = reinterpret_cast<float4 const*>(bias + col);
-    float4 const* c4 = reinterpret_cast<float4 const*>(colsum + col);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float4 const b = __ldg(b4 + i), c = __ldg(c4 + i);
-        v[4 * i + 0] = fmaf(v[4 * i + 0], rstd, fmaf(nmr, c.x, b.x));
-        v[4 * i + 1] = fmaf(v[4 * i + 1], rstd, fmaf(nmr, c.y, b.y));
-        v[4 * i + 2] = fmaf(v[4 * i + 2], rstd, fmaf(nmr, c.z, b.z));
-        v[4 * i + 3] = fmaf(v[4 * i + 3], rstd, fmaf(nmr, c.w, b.w));
+        float4 const b = __ldg(b4 + i);
+        v[4 * i + 0] = fmaf(v[4 * i + 0], rstd, b.x);
+        v[4 * i + 1] = fmaf(v[4 * i + 1], rstd, b.y);
+        v[4 * i + 2] = fmaf(v[4 * i + 2], rstd, b.z);
+        v[4 * i + 3] = fmaf(v[4 * i + 3], rstd, b.w);
     }
 }
 
@@ -169,7 +167,7 @@ struct SlabCtx {
     uint32_t stage_row;   // shared-memory address of this lane's staging row (kStaged)
     int col0;             // global column of the first slab
     int64_t orow;         // output row of this lane (direct path), -1 = none
-    float rstd, nmr;      // folded LayerNorm
+    float rstd;           // folded LayerNorm: 1 / sqrt(var + eps) of this lane's row
     int lane;
     uint32_t stage_base;  // shared-memory address of the warp's staging area, row pitch below (kStaged)
     uint32_t pitch;
@@ -197,7 +195,7 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
-            if (kLn) ln_bias16(v, ep.bias, ep.ln_colsum, c, cx.rstd, cx.nmr);
+            if (kLn) ln_bias16(v, ep.bias, c, cx.rstd);
             else if (ep.bias) add_bias16(v, ep.bias, c);
             uint4 x[2];
             activate_pack16(v, kAct, x);
@@ -395,17 +393,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             int const m0 = (tile / n_tiles) * kBlockM;
             int const n0 = (tile % n_tiles) * block_n;
             int64_t orow = -1;
-            float rstd = 1.f, nmr = 0.f;  // folded LayerNorm: 1/std and -mean/std of this thread's row
+            float rstd = 1.f;  // folded LayerNorm: 1/std of this thread's row
             if (!kStaged) {
                 int const row = m0 + quarter * 32 + lane;
                 if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
             } else if (kLn) {
                 int const row = m0 + quarter * 32 + lane;
-                if (row < M) {
-                    float2 const st = __ldg(ep.ln_stats + row);
-                    rstd = st.y;
-                    nmr = -st.x * st.y;
-                }
+                if (row < M) rstd = __ldg(ep.ln_stats + row).y;
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -416,7 +410,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             cx.col0 = n0 + s_first * 16;
             cx.orow = orow;
             cx.rstd = rstd;
-            cx.nmr = nmr;
             cx.lane = lane;
             cx.stage_base = my_stage;
             cx.pitch = pitch;
@@ -485,10 +478,7 @@ __global__ void gemm_simt_kernel(T const* __restrict__ A, int64_t lda, T const* 
         int64_t const orow = ep.row_map ? (int64_t)ep.row_map[m] : (int64_t)m;
         if (orow < 0) continue;
         float v = acc[i];
-        if (ep.ln_stats) {
-            float2 const st = ep.ln_stats[m];
-            v = st.y * (v - st.x * ep.ln_colsum[n]);
-        }
+        if (ep.ln_stats) v *= ep.ln_stats[m].y;  // row-centred weights: no mean term
         if (ep.bias) v += ep.bias[n];
         int64_t const o = orow * ep.ldc + n;
         if (ep.residual)
@@ -570,7 +560,6 @@ EpiParams to_params(Epilogue const& e, int N) {
     p.residual = e.residual;
     p.row_map = e.row_map;
     p.ln_stats = e.ln_stats;
-    p.ln_colsum = e.ln_colsum;
     p.act = e.act;
     p.out_f32 = e.out_f32;
     p.ldc = e.ldc ? e.ldc : N;
@@ -606,8 +595,8 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
     static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch
     bool const staged = allow_staged && !tf32 && !ep.residual && !ep.row_map && !ep.out_f32 && block_n >= 64 &&
                         (ep.act == ACT_NONE || ep.act == ACT_GELU);
-    if (ep.ln_stats && (!staged || !ep.bias || !ep.ln_colsum))
-        fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue), a bias and column sums");
+    if (ep.ln_stats && (!staged || !ep.bias))
+        fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue) and a bias");
     SmemPlan const sp = plan_smem(block_n, staged);
     DLIMG_ASSERT(sp.stages >= 2);
     using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, void*, EpiParams);

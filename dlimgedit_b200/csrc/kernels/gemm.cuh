@@ -28,11 +28,11 @@ struct Epilogue {
     int act = ACT_NONE;              // applied after bias and residual
     int out_f32 = 0;                 // 0: bf16 output, 1: fp32 output
     int ldc = 0;                     // output row pitch in elements (0 = N)
-    // LayerNorm folded into the GEMM (16-bit outputs without residual): with W' = W * gamma, b' = b + W beta (both
-    // prepared by the caller and passed as the B operand / bias) and the raw, un-normalised rows as A,
-    //   LN(x) W^T + b = rstd_m * (x W'^T - mean_m * colsum_n) + b'_n,   colsum_n = sum_k W'_nk.
-    float2 const* ln_stats = nullptr;  // [M] (mean, rstd) per row of A
-    float const* ln_colsum = nullptr;  // [N]
+    // LayerNorm folded into the GEMM (16-bit outputs without residual).  The caller passes the raw, un-normalised rows
+    // as A, W'' = W * gamma with every ROW of W'' centred (W''_nk -= mean_k W''_nk) as B and b' = b + W beta as bias:
+    //   LN(x) W^T + b = rstd_m * sum_k (x_mk - mean_m) (W gamma)_nk + b'_n = rstd_m * (x W''^T)_mn + b'_n
+    // because sum_k x_mk = K mean_m cancels the centring term -- so the epilogue needs only 1/std per row.
+    float2 const* ln_stats = nullptr;  // [M] (mean, rstd) per row of A; only rstd is read
 };
 
 struct Operand {

@@ -85,36 +85,33 @@ Linear16 load_linear16(WeightFile const& wf, std::string const& p, int n, int k,
     return l;
 }
 
-// Linear preceded by a LayerNorm, with the LayerNorm's affine part folded in: W' = W * gamma (per input feature),
-// b' = b + W beta.  colsum_n = sum_k W'_nk over the ROUNDED weights, so that the epilogue identity
-// LN(x) W^T + b = rstd (x W'^T - mean colsum) + b' holds exactly for the operand the tensor cores see.
+// Linear preceded by a LayerNorm, with the LayerNorm folded in: W'' = W * gamma (per input feature) with each row
+// centred, b' = b + W beta.  The GEMM on the raw rows then yields sum_k (x_k - mean) (W gamma)_nk directly and the
+// epilogue only scales by 1/std (gemm.cuh, Epilogue::ln_stats).
 Linear16 load_linear16_ln(WeightFile const& wf, std::string const& p, std::string const& norm, int n, int k,
                           std::vector<float>* bias_out = nullptr) {
     auto const& w = wf.get(p + ".weight", {n, k}).data;
     auto const& b = wf.get(p + ".bias", {n}).data;
     auto const& g = wf.get(norm + ".weight", {k}).data;
     auto const& beta = wf.get(norm + ".bias", {k}).data;
-    std::vector<float> wf32((size_t)n * k), bias((size_t)n), colsum((size_t)n);
+    std::vector<float> wf32((size_t)n * k), bias((size_t)n);
     for (int i = 0; i < n; ++i) {
-        double acc = b[(size_t)i];
+        double acc = b[(size_t)i], row_sum = 0;
         for (int j = 0; j < k; ++j) {
-            wf32[(size_t)i * k + j] = w[(size_t)i * k + j] * g[(size_t)j];
+            double const v = (double)w[(size_t)i * k + j] * g[(size_t)j];
+            row_sum += v;
             acc += (double)w[(size_t)i * k + j] * beta[(size_t)j];
         }
+        double const row_mean = row_sum / k;
+        for (int j = 0; j < k; ++j) wf32[(size_t)i * k + j] = (float)((double)w[(size_t)i * k + j] * g[(size_t)j] - row_mean);
         bias[(size_t)i] = (float)acc;
-    }
-    std::vector<act_t> const w16 = to_act(wf32);
-    for (int i = 0; i < n; ++i) {
-        double acc = 0;
-        for (int j = 0; j < k; ++j) acc += (double)act2f(w16[(size_t)i * k + j]);
-        colsum[(size_t)i] = (float)acc;
     }
     Linear16 l;
     l.n = n;
     l.k = k;
-    l.w.upload(w16);
+    l.w.upload(to_act(wf32));
     l.b.upload(bias);
-    l.colsum.upload(colsum);
+    l.ln_folded = true;
     if (bias_out) *bias_out = bias;
     return l;
 }
@@ -381,9 +378,8 @@ void SamModel::gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 con
     e.out_f32 = out_f32 ? 1 : 0;
     e.ldc = l.n;
     if (ln_stats) {
-        DLIMG_ASSERT(l.colsum);
+        DLIMG_ASSERT(l.ln_folded);
         e.ln_stats = ln_stats;
-        e.ln_colsum = l.colsum.get();
     }
     gemm::launch(s, false, A, B, out, e, num_sms_);
 }

@@ -58,7 +58,7 @@ template <typename T> class DeviceBuffer {
 struct Linear16 {  // act_t weight (N, K) row-major + fp32 bias (N) -- encoder GEMM operand B
     DeviceBuffer<act_t> w;
     DeviceBuffer<float> b;
-    DeviceBuffer<float> colsum;  // only for Linears with a folded LayerNorm in front: sum_k w[n][k] (of the rounded weights)
+    bool ln_folded = false;  // weights hold W * gamma with centred rows, bias holds b + W beta (LayerNorm folded in)
     int n = 0, k = 0;
 };
 struct Linear32 {  // fp32 weight (N, K) + bias -- decoder
