@@ -165,6 +165,7 @@ __device__ __forceinline__ void dwconv_rows(act_t const* __restrict__ in, int H,
 
 template <int kTX>
 struct DwAcc32 {  // fp32 taps and accumulators
+    static constexpr int kMinBlocks = 2;
     float w[9][8];
     float acc[kTX][8];
     __device__ __forceinline__ void init(float const* __restrict__ weight, float const* __restrict__ bias, int C, int c8) {
@@ -206,6 +207,7 @@ struct DwAcc32 {  // fp32 taps and accumulators
 // value that is rounded to fp16 immediately afterwards anyway.
 template <int kTX>
 struct DwAccH2 {
+    static constexpr int kMinBlocks = 3;  // 4 blocks (64 registers) measured the same: the spills eat the occupancy gain
     uint4 w[9];
     __half2 acc[kTX][4];
     __device__ __forceinline__ void init(act_t const* __restrict__ weight, float const* __restrict__ bias, int C, int c8) {
@@ -234,7 +236,7 @@ struct DwAccH2 {
 #endif
 
 template <int kStride, int kTX, int kC8, typename Acc, typename WeightT>
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(act_t const* __restrict__ in, int H, int W, int Ho, int Wo, int xgroups,
+__global__ void __launch_bounds__(256, Acc::kMinBlocks) dwconv3x3_kernel(act_t const* __restrict__ in, int H, int W, int Ho, int Wo, int xgroups,
                                                         WeightT const* __restrict__ weight, float const* __restrict__ bias,
                                                         int gelu, act_t* __restrict__ out) {
     int const t = blockIdx.x * blockDim.x + threadIdx.x;
