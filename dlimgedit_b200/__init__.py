@@ -146,7 +146,7 @@ class _Debug(ctypes.Structure):
         ("act_is_bf16", ctypes.c_uint32),
         ("gemm", _F(_R, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
-                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)),
+                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)),
         ("encode_tap", _F(_R, _H, ctypes.POINTER(_ImageView), ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p,
                           ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t))),
         ("resize_plan", _F(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i32p, c_f32p)),

@@ -202,7 +202,7 @@ using DebugApi = dlimg_b200_Debug;
 
 dlimg_Result dbg_gemm(void* stream, int tf32, int simt, void const* a, void const* b, int M, int N, int K, float const* bias,
                       void const* residual, int const* row_map, int act, int out_f32, void* out, float const* ln_stats,
-                      float const* ln_colsum) {
+                      int ln_parts, float* stats_out) {
     return try_([=] {
         gemm::Operand A{a, M, K, K}, B{b, N, K, K};
         gemm::Epilogue e;
@@ -213,7 +213,8 @@ dlimg_Result dbg_gemm(void* stream, int tf32, int simt, void const* a, void cons
         e.out_f32 = out_f32;
         e.ldc = N;
         e.ln_stats = reinterpret_cast<float2 const*>(ln_stats);
-        (void)ln_colsum;
+        e.ln_parts = ln_parts;
+        e.stats_out = reinterpret_cast<float2*>(stats_out);
         int dev = 0;
         CUDA_CHECK(cudaGetDevice(&dev));
         cudaDeviceProp prop;

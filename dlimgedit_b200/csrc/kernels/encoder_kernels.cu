@@ -258,6 +258,51 @@ __global__ void __launch_bounds__(256, Acc::kMinBlocks) dwconv3x3_kernel(act_t c
     }
 }
 
+// local_conv of a TinyViT block (stride 1, fp32 accumulation, no activation) that also leaves the LayerNorm row sums
+// of its output for the fc1 GEMM behind it (gemm.cuh, Epilogue::ln_parts = 1): a block holds kG whole groups of
+// 4 pixels x kC8 channel octets, every thread writes the (sum, sum of squares) of its 8 channels per pixel to shared
+// memory and kG * 4 threads add the kC8 partials of one pixel in a fixed order (reproducible, no atomics).
+template <int kC8, int kG>
+__global__ void __launch_bounds__(kC8 * kG) dwconv3x3_stats_kernel(act_t const* __restrict__ in, int H, int W, int xgroups,
+                                                                   float const* __restrict__ weight, float const* __restrict__ bias,
+                                                                   act_t* __restrict__ out, float2* __restrict__ stats) {
+    constexpr int kTX = 4, kCols = kTX + 2;
+    __shared__ float2 part[kG][kTX][kC8];
+    int const c8 = threadIdx.x % kC8, gl = threadIdx.x / kC8;
+    int const xg = blockIdx.x * kG + gl;  // xgroups is a multiple of kG (checked on the host)
+    int const oy = blockIdx.y, b = blockIdx.z;
+    int const ox0 = xg * kTX, ix0 = ox0 - 1;
+    DwAcc32<kTX> acc;
+    acc.init(weight, bias, kC8 * 8, c8);
+    if (ix0 >= 0 && ix0 + kCols <= W) dwconv_rows<1, kTX, kC8, false>(in, H, W, b, oy, c8, ix0, acc);
+    else dwconv_rows<1, kTX, kC8, true>(in, H, W, b, oy, c8, ix0, acc);
+    int64_t const row0 = ((int64_t)b * H + oy) * W + ox0;
+    uint4* orow = reinterpret_cast<uint4*>(out) + row0 * kC8 + c8;
+#pragma unroll
+    for (int o = 0; o < kTX; ++o) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s1 += acc.acc[o][i];
+            s2 = fmaf(acc.acc[o][i], acc.acc[o][i], s2);
+        }
+        part[gl][o][c8] = make_float2(s1, s2);
+        orow[o * kC8] = acc.result(o, false);
+    }
+    __syncthreads();
+    if (threadIdx.x < kG * kTX) {
+        int const g2 = threadIdx.x / kTX, o = threadIdx.x % kTX;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < kC8; ++k) {
+            float2 const v = part[g2][o][k];
+            s1 += v.x;
+            s2 += v.y;
+        }
+        stats[((int64_t)b * H + oy) * W + (blockIdx.x * kG + g2) * kTX + o] = make_float2(s1, s2);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 constexpr int kLnMaxPairs = 5;  // C <= 320
 
@@ -516,6 +561,23 @@ void dwconv3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, 
     DLIMG_DW_CASE(1, 128) DLIMG_DW_CASE(1, 160)
 #undef DLIMG_DW_CASE
     fail("dwconv3x3: unsupported (stride, channels) = (" + std::to_string(stride) + ", " + std::to_string(C) + ")");
+}
+
+void dwconv3x3_stats(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, float const* weight, float const* bias,
+                     act_t* out, float2* stats) {
+    int const xgroups = W / 4;
+    DLIMG_ASSERT(W % 4 == 0);
+    ProfScope prof(s, CAT_DWCONV, 2.0 * batch * H * W * C * 9, (double)batch * 2.0 * H * W * C * 2);
+#define DLIMG_DWS_CASE(CC, G)                                                                                             \
+    if (C == CC && xgroups % G == 0) {                                                                                    \
+        dim3 const grid((unsigned)(xgroups / G), (unsigned)H, (unsigned)batch);                                           \
+        dwconv3x3_stats_kernel<CC / 8, G><<<grid, (CC / 8) * G, 0, s>>>(in, H, W, xgroups, weight, bias, out, stats);     \
+        KERNEL_CHECK();                                                                                                   \
+        return;                                                                                                           \
+    }
+    DLIMG_DWS_CASE(128, 16) DLIMG_DWS_CASE(160, 8) DLIMG_DWS_CASE(320, 8)
+#undef DLIMG_DWS_CASE
+    fail("dwconv3x3_stats: unsupported (channels, width) = (" + std::to_string(C) + ", " + std::to_string(W) + ")");
 }
 
 void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const* src_row, float const* gamma,

@@ -44,6 +44,11 @@ void im2col3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, 
 void dwconv3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, float const* weight,
                act_t const* weight16, float const* bias, bool gelu, act_t* out);
 
+// Stride-1 depthwise 3x3 with fp32 accumulation and no activation (TinyViT local_conv) that also writes, per output
+// pixel, (sum, sum of squares) over its C channels: the LayerNorm row sums for the GEMM behind it.
+void dwconv3x3_stats(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, float const* weight, float const* bias,
+                     act_t* out, float2* stats);
+
 // Row LayerNorm over C channels.  src_row (optional, length `rows`): gather index into `in`, -1 = the row
 // is window padding and the output is LN(0) = beta.  Output bf16 or fp32.
 void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const* src_row, float const* gamma,

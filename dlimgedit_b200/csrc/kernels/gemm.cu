@@ -36,6 +36,9 @@ struct EpiParams {
     void const* residual;
     int const* row_map;
     float2 const* ln_stats;
+    float2* stats_out;
+    int ln_parts;
+    float ln_eps;
     int act;
     int out_f32;
     int ldc;
@@ -110,7 +113,7 @@ __device__ __forceinline__ void activate_packed16(uint4 (&x)[2], int act) {
 // One 16-column slab of one accumulator row, written by its own thread: bias -> residual -> activation -> store.
 // (Residual / row-scatter / fp32-output GEMMs; the wide 16-bit outputs take the staged path in the kernel.)
 __device__ __forceinline__ void epilogue_store16(uint32_t const (&r)[16], EpiParams const& ep, void* out, int64_t orow,
-                                                 int col) {
+                                                 int col, float& sum, float& sumsq) {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
@@ -151,6 +154,13 @@ __device__ __forceinline__ void epilogue_store16(uint32_t const (&r)[16], EpiPar
                 }
             }
         }
+        if (ep.stats_out) {  // LayerNorm statistics of the row this GEMM writes (no activation in this mode)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                sum += v[i];
+                sumsq = fmaf(v[i], v[i], sumsq);
+            }
+        }
         uint4 x[2];
         activate_pack16(v, ep.act, x);
         uint4* o4 = reinterpret_cast<uint4*>(o);
@@ -177,7 +187,7 @@ struct SlabCtx {
 };
 
 template <int kCnt, bool kStaged, int kAct, bool kLn>
-__device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams const& ep, void* out) {
+__device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams const& ep, void* out, float& sum, float& sumsq) {
     uint32_t r[2][16];
     tmem_ld16(cx.taddr, r[0]);
 #pragma unroll
@@ -203,7 +213,7 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x[0].x), "r"(x[0].y), "r"(x[0].z), "r"(x[0].w) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
         } else if (cx.orow >= 0) {
-            epilogue_store16(r[k & 1], ep, out, cx.orow, c);
+            epilogue_store16(r[k & 1], ep, out, cx.orow, c, sum, sumsq);
         }
     }
     if (kStaged) {
@@ -249,10 +259,11 @@ constexpr int kSmemLimit = 227 * 1024;
 struct SmemPlan {
     int stages, staging_bytes, total_bytes;
 };
-inline SmemPlan plan_smem(int block_n, bool staged) {
+inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false) {
     SmemPlan p;
     // 16 epilogue warps x 32 rows x (64-column share of the tile + pad), see the epilogue
     p.staging_bytes = staged ? (int)round_up64((int64_t)kEpiWarps * 32 * ((((block_n >> 4) + 3) / 4) * 32 + kStagePad), 1024) : 0;
+    if (!staged && stats) p.staging_bytes = 8192;  // two buffers of 16 warps x 32 lanes x (sum, sum of squares)
     int const stage_bytes = kAStageBytes + block_n * kKBytes;
     int const fixed = 1024 /*align*/ + 1024 /*barriers, keeps the stages 1024-aligned*/ + p.staging_bytes;
     p.stages = (kSmemLimit - fixed) / stage_bytes;
@@ -399,7 +410,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
             } else if (kLn) {
                 int const row = m0 + quarter * 32 + lane;
-                if (row < M) rstd = __ldg(ep.ln_stats + row).y;
+                if (row < M) {
+                    if (ep.ln_parts == 0) {
+                        rstd = __ldg(ep.ln_stats + row).y;
+                    } else {  // partial sums from the producing GEMM's epilogue, fixed order
+                        float sx = 0.f, sq = 0.f;
+                        for (int pp = 0; pp < ep.ln_parts; ++pp) {
+                            float2 const pv = __ldg(ep.ln_stats + (int64_t)row * ep.ln_parts + pp);
+                            sx += pv.x;
+                            sq += pv.y;
+                        }
+                        float const inv_k = 1.0f / (float)K, mean = sx * inv_k;
+                        rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv_k), 0.f) + ep.ln_eps);
+                    }
+                }
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -416,16 +440,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             cx.out_seg = reinterpret_cast<act_t*>(out) + (int64_t)(m0 + quarter * 32) * ep.ldc + n0 + s_first * 16;
             cx.ldc = ep.ldc;
             cx.rows_valid = M - (m0 + quarter * 32);
+            float row_sum = 0.f, row_sumsq = 0.f;
             switch (s_cnt) {  // warp-uniform
-                case 4: epilogue_slabs<4, kStaged, kAct, kLn>(cx, ep, out); break;
-                case 3: epilogue_slabs<3, kStaged, kAct, kLn>(cx, ep, out); break;
-                case 2: epilogue_slabs<2, kStaged, kAct, kLn>(cx, ep, out); break;
-                case 1: epilogue_slabs<1, kStaged, kAct, kLn>(cx, ep, out); break;
+                case 4: epilogue_slabs<4, kStaged, kAct, kLn>(cx, ep, out, row_sum, row_sumsq); break;
+                case 3: epilogue_slabs<3, kStaged, kAct, kLn>(cx, ep, out, row_sum, row_sumsq); break;
+                case 2: epilogue_slabs<2, kStaged, kAct, kLn>(cx, ep, out, row_sum, row_sumsq); break;
+                case 1: epilogue_slabs<1, kStaged, kAct, kLn>(cx, ep, out, row_sum, row_sumsq); break;
                 default:  // narrow tiles (block_n < 64): this warp owns no slab
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(acc));
                     break;
+            }
+            if (!kStaged && ep.stats_out) {
+                // row statistics of this tile: the four warps of a lane quarter hold pieces of the same 32 rows
+                uint32_t const red = stage_out + (uint32_t)((local & 1) * 4096);
+                uint32_t const mine = red + (uint32_t)(((quarter * 4 + slab) * 32 + lane) * 8);
+                asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(mine), "f"(row_sum), "f"(row_sumsq) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+                int const row = m0 + quarter * 32 + lane;
+                if (slab == 0 && row < M) {
+                    float sx = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4) {
+                        float a, b;
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)(((quarter * 4 + w4) * 32 + lane) * 8)));
+                        sx += a;
+                        sq += b;
+                    }
+                    ep.stats_out[(int64_t)row * n_tiles + (tile % n_tiles)] = make_float2(sx, sq);
+                }
+                // the other buffer is used by the next tile; a warp can only reach the tile after that once every warp
+                // of its quarter (including the reader above) has passed the next tile's barrier
             }
         }
     }
@@ -560,6 +606,9 @@ EpiParams to_params(Epilogue const& e, int N) {
     p.residual = e.residual;
     p.row_map = e.row_map;
     p.ln_stats = e.ln_stats;
+    p.stats_out = e.stats_out;
+    p.ln_parts = e.ln_parts;
+    p.ln_eps = e.ln_eps;
     p.act = e.act;
     p.out_f32 = e.out_f32;
     p.ldc = e.ldc ? e.ldc : N;
@@ -597,7 +646,9 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
                         (ep.act == ACT_NONE || ep.act == ACT_GELU);
     if (ep.ln_stats && (!staged || !ep.bias))
         fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue) and a bias");
-    SmemPlan const sp = plan_smem(block_n, staged);
+    if (ep.stats_out && (staged || ep.act != ACT_NONE || ep.row_map || ep.out_f32 || block_n < 64))
+        fail("GEMM: row statistics are produced by the direct 16-bit epilogue without activation only");
+    SmemPlan const sp = plan_smem(block_n, staged, ep.stats_out != nullptr);
     DLIMG_ASSERT(sp.stages >= 2);
     using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, void*, EpiParams);
     Kernel kernel;

@@ -32,7 +32,14 @@ struct Epilogue {
     // as A, W'' = W * gamma with every ROW of W'' centred (W''_nk -= mean_k W''_nk) as B and b' = b + W beta as bias:
     //   LN(x) W^T + b = rstd_m * sum_k (x_mk - mean_m) (W gamma)_nk + b'_n = rstd_m * (x W''^T)_mn + b'_n
     // because sum_k x_mk = K mean_m cancels the centring term -- so the epilogue needs only 1/std per row.
-    float2 const* ln_stats = nullptr;  // [M] (mean, rstd) per row of A; only rstd is read
+    float2 const* ln_stats = nullptr;  // ln_parts == 0: [M] (mean, rstd) per row of A (only rstd is read)
+    // ln_parts >= 1: ln_stats is [M][ln_parts] partial (sum x, sum x^2) written by the GEMM that produced A
+    // (stats_out below); 1/std = rsqrt(sum x^2 / K - (sum x / K)^2 + ln_eps) is formed in the epilogue.
+    int ln_parts = 0;
+    float ln_eps = 1e-5f;
+    // Direct epilogue without activation: also write, per output row and N tile, (sum v, sum v^2) of the row's values
+    // in this tile -> [M][N / block_n] float2.  Summed in a fixed order (no atomics): results are reproducible.
+    float2* stats_out = nullptr;
 };
 
 struct Operand {

@@ -343,6 +343,7 @@ EncoderWorkspace::EncoderWorkspace(int mb) : max_batch(mb) {
     xb.allocate(B * 65536 * 64);
     for (auto& b : big) b.allocate(B * 65536 * 256);
     stats.allocate(B * 16384);
+    stats_parts.allocate(B * 16384 * 2);
 }
 
 DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
@@ -368,7 +369,7 @@ DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
 
 // ---------------------------------------------------------------------------------------------
 void SamModel::gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 const& l, void* out, int act,
-                      act_t const* residual, float2 const* ln_stats, bool out_f32) const {
+                      act_t const* residual, float2 const* ln_stats, bool out_f32, int ln_parts, float2* stats_out) const {
     gemm::Operand A{a, rows, l.k, l.k};
     gemm::Operand B{l.w.get(), l.n, l.k, l.k};
     gemm::Epilogue e;
@@ -380,7 +381,9 @@ void SamModel::gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 con
     if (ln_stats) {
         DLIMG_ASSERT(l.ln_folded);
         e.ln_stats = ln_stats;
+        e.ln_parts = ln_parts;
     }
+    e.stats_out = stats_out;
     gemm::launch(s, false, A, B, out, e, num_sms_);
 }
 
@@ -447,13 +450,19 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         int const C = c.dim, L = c.res * c.res;
         int const rows = (int)(B * L);
         float2* stats = ws.stats.get();
+        int const fc2_parts = C / gemm::pick_block_n(C);  // N tiles of fc2 = partial sums per row
         for (int i = 0; i < c.depth; ++i) {
             BlockW const& b = enc_.blocks[st - 1][(size_t)i];
             std::string const tn = "s" + std::to_string(st) + "b" + std::to_string(i);
             // attention branch on the un-partitioned grid: LN statistics, QKV with the LayerNorm folded into the GEMM,
             // windowed attention (does the partition / zero padding / un-partition itself), proj + residual in place
-            enc::layernorm_stats(s, x, rows, C, 1e-5f, stats);
-            gemm16(s, x, rows, b.qkv, ws.big[1].get(), ACT_NONE, nullptr, stats);
+            // (block 0: a statistics kernel; later blocks: the previous block's fc2 epilogue already wrote the row sums)
+            if (i == 0) {
+                enc::layernorm_stats(s, x, rows, C, 1e-5f, stats);
+                gemm16(s, x, rows, b.qkv, ws.big[1].get(), ACT_NONE, nullptr, stats);
+            } else {
+                gemm16(s, x, rows, b.qkv, ws.big[1].get(), ACT_NONE, nullptr, ws.stats_parts.get(), false, fc2_parts);
+            }
             tap_act(s, tap, (tn + ".qkv").c_str(), ws.big[1].get(), (size_t)rows * 3 * C);
             enc::window_attention(s, ws.big[1].get(), batch, c.res, c.ws, c.heads, b.qkv_pad.get(), b.attn_bias.get(),
                                   ws.big[2].get(), num_sms_);
@@ -462,12 +471,13 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
             tap_act(s, tap, (tn + ".proj").c_str(), x, (size_t)rows * C);
             // local depthwise conv (no activation, no residual).  fp32 accumulation: its output IS the trunk (it replaces
             // x), and the packed-half kernel cost 0.0006 of mask IoU here for 3 % of the step -- not worth it.
-            enc::dwconv3x3(s, x, batch, c.res, c.res, C, 1, b.local_conv.w.get(), nullptr, b.local_conv.b.get(), false, y);
+            enc::dwconv3x3_stats(s, x, batch, c.res, c.res, C, b.local_conv.w.get(), b.local_conv.b.get(), y, stats);
             tap_act(s, tap, (tn + ".lc").c_str(), y, (size_t)rows * C);
-            // MLP branch: LN folded into fc1 (+ GELU), fc2 + residual
-            enc::layernorm_stats(s, y, rows, C, 1e-5f, stats);
-            gemm16(s, y, rows, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, stats);
-            gemm16(s, ws.big[1].get(), rows, b.fc2, y, ACT_NONE, y);
+            // MLP branch: LN folded into fc1 (row sums from the depthwise kernel above) + GELU, fc2 + residual
+            gemm16(s, y, rows, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, stats, false, 1);
+            // fc2 + residual; its epilogue also leaves the LayerNorm row sums of the result for the next block's qkv
+            gemm16(s, ws.big[1].get(), rows, b.fc2, y, ACT_NONE, y, nullptr, false, 0,
+                   i + 1 < c.depth ? ws.stats_parts.get() : nullptr);
             std::swap(x, y);
             tap_act(s, tap, tn.c_str(), x, (size_t)rows * C);
         }

@@ -129,6 +129,7 @@ struct EncoderWorkspace {
     DeviceBuffer<act_t> c1, col, xa, xb, big[4];
     DeviceBuffer<float> emb;       // (max_batch, 4096, 256) fp32: fixed destination of the captured encoder graph
     DeviceBuffer<float2> stats;    // (max_batch * 16384): per-token LayerNorm (mean, rstd) of the current block input
+    DeviceBuffer<float2> stats_parts;  // (max_batch * 16384 * 2): partial (sum, sum of squares) written by fc2's epilogue
     explicit EncoderWorkspace(int max_batch);
 };
 
@@ -183,7 +184,7 @@ class SamModel {
 
   private:
     void gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 const& l, void* out, int act, act_t const* residual,
-                float2 const* ln_stats = nullptr, bool out_f32 = false) const;
+                float2 const* ln_stats = nullptr, bool out_f32 = false, int ln_parts = 0, float2* stats_out = nullptr) const;
     void gemm32(cudaStream_t s, float const* a, int64_t rows, Linear32 const& l, float* out, int act) const;
     void lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, int rows, Linear32 const& l, bool relu, float* y,
              int64_t ys) const;

@@ -16,11 +16,13 @@ typedef struct dlimg_b200_Debug {
     /* C = epilogue(A[M,K] * B[N,K]^T).  Device pointers; elements are bf16 (tf32 == 0) or fp32 (tf32 != 0).
      * simt != 0 runs the CUDA-core cross-check kernel instead of the tcgen05 kernel.  act: 0 none, 1 GELU(erf),
      * 2 ReLU.  row_map (optional): output row per input row, -1 drops the row.  ln_stats / ln_colsum (optional):
-     * folded LayerNorm: per-row (mean, rstd) pairs [M][2]; B must hold gamma-scaled weights with centred rows, then
-     * out = rstd * (A B^T) + bias (see csrc/kernels/gemm.cuh).  ln_colsum is unused (kept for layout stability). */
+     * folded LayerNorm; B must hold gamma-scaled weights with centred rows, then out = rstd * (A B^T) + bias (see
+     * csrc/kernels/gemm.cuh): ln_parts == 0 -> per-row (mean, rstd) pairs [M][2]; ln_parts >= 1 -> [M][ln_parts]
+     * partial (sum, sum of squares) of the rows of A.  stats_out (optional): [M][N / block_n][2], the same partial
+     * sums of the rows this GEMM writes. */
     dlimg_Result (*gemm)(void* stream, int tf32, int simt, void const* a, void const* b, int M, int N, int K,
                          float const* bias, void const* residual, int const* row_map, int act, int out_f32, void* out,
-                         float const* ln_stats, float const* ln_colsum);
+                         float const* ln_stats, int ln_parts, float* stats_out);
     /* Encodes `count` device-resident images and copies the activation called `name` (see model.cu) as fp32. */
     dlimg_Result (*encode_tap)(dlimg_Environment, dlimg_ImageView const* dev_views, int count, char const* name,
                                float* dev_out, size_t capacity, size_t* written);

@@ -13,7 +13,7 @@ def act_dtype():
 
 
 def gemm(a, b, bias=None, residual=None, row_map=None, act=0, out_f32=False, simt=False, out_rows=None, out=None,
-         ln_stats=None, ln_colsum=None):
+         ln_stats=None, ln_parts=0, stats_out=None):
     """a (M,K), b (N,K) CUDA tensors, both act_dtype() or both fp32 (tf32 path).  Returns the output tensor."""
     M, K = a.shape
     N = b.shape[0]
@@ -25,8 +25,8 @@ def gemm(a, b, bias=None, residual=None, row_map=None, act=0, out_f32=False, sim
                         bias.data_ptr() if bias is not None else None,
                         residual.data_ptr() if residual is not None else None,
                         row_map.data_ptr() if row_map is not None else None, act, int(out_f32), out.data_ptr(),
-                        ln_stats.data_ptr() if ln_stats is not None else None,
-                        ln_colsum.data_ptr() if ln_colsum is not None else None)
+                        ln_stats.data_ptr() if ln_stats is not None else None, ln_parts,
+                        stats_out.data_ptr() if stats_out is not None else None)
     if r != 0:
         raise dl.Exception(dl.api().last_error().decode())
     torch.cuda.synchronize()

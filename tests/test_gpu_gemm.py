@@ -123,7 +123,6 @@ def test_f16_gemm_folded_layernorm(M, N, K, act):
     wg = w * gamma
     w16 = (wg - wg.mean(1, keepdim=True)).to(act_dtype())  # centred rows: the mean of x cancels inside the GEMM
     bias = b + w @ beta
-    colsum = None
     stats = torch.zeros(M, 2, device="cuda")
     r = dl.debug().layernorm_stats(None, x.data_ptr(), M, K, 1e-5, stats.data_ptr())
     assert r == 0, dl.api().last_error()
@@ -131,7 +130,37 @@ def test_f16_gemm_folded_layernorm(M, N, K, act):
     xf = x.float()
     assert torch.allclose(stats[:, 0], xf.mean(1), atol=1e-5, rtol=1e-5)
     assert torch.allclose(stats[:, 1], (xf.var(1, unbiased=False) + 1e-5).rsqrt(), atol=1e-5, rtol=1e-4)
-    out = gemm(x, w16, bias=bias, act=act, ln_stats=stats, ln_colsum=colsum)
+    out = gemm(x, w16, bias=bias, act=act, ln_stats=stats)
     assert torch.allclose(out.float(), ref, atol=2e-2, rtol=1e-2), float((out.float() - ref).abs().max())
-    simt = gemm(x, w16, bias=bias, act=act, ln_stats=stats, ln_colsum=colsum, simt=True, out_f32=True)
+    simt = gemm(x, w16, bias=bias, act=act, ln_stats=stats, simt=True, out_f32=True)
     assert torch.allclose(simt, ref, atol=1e-2, rtol=1e-2), float((simt - ref).abs().max())
+
+
+@pytest.mark.parametrize("M,C,K", [(4096, 160, 640), (1000, 128, 512), (4096, 320, 1280)])
+def test_f16_gemm_row_statistics_feed_the_next_folded_layernorm(M, C, K):
+    """fc2 (+ residual) writes per-row partial (sum, sum of squares) of its output next to the output itself; the
+    following qkv GEMM turns them into 1/std in its epilogue.  C = 320 runs as two N tiles -> two partial sums per row."""
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    h = torch.randn(M, K, device="cuda", generator=g).to(act_dtype())
+    w2 = (torch.randn(C, K, device="cuda", generator=g) / K ** 0.5).to(act_dtype())
+    b2 = torch.randn(C, device="cuda", generator=g)
+    res = (torch.randn(M, C, device="cuda", generator=g) + 0.5).to(act_dtype())
+    parts = 2 if C == 320 else 1
+    stats = torch.zeros(M, parts, 2, device="cuda")
+    x = gemm(h, w2, bias=b2, residual=res, stats_out=stats)
+    ref_x = h.float() @ w2.float().t() + b2 + res.float()
+    assert torch.allclose(x.float(), ref_x, atol=3e-2, rtol=1e-2)
+    s = stats.sum(1)
+    assert torch.allclose(s[:, 0], ref_x.sum(1), atol=2e-2, rtol=1e-3)
+    assert torch.allclose(s[:, 1], (ref_x * ref_x).sum(1), atol=5e-2, rtol=2e-3)
+    # consumer: LayerNorm folded into the next Linear, statistics taken from the partial sums
+    N = 3 * C
+    w = torch.randn(N, C, device="cuda", generator=g) / C ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(C, device="cuda", generator=g)
+    wg = w * gamma
+    w16 = (wg - wg.mean(1, keepdim=True)).to(act_dtype())
+    out = gemm(x, w16, bias=b + w @ beta, ln_stats=stats, ln_parts=parts)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.t() + b
+    assert torch.allclose(out.float(), ref, atol=3e-2, rtol=1e-2), float((out.float() - ref).abs().max())
