@@ -252,33 +252,42 @@ __global__ void __launch_bounds__(kT2iThreads) t2i_attention_kernel(float const*
 }
 
 // ---------------------------------------------------------------------------------------------
+// One thread per (image token, head); the 7 token keys / values of the prompt sit in shared memory as
+// [token][d / 4][head] float4, so the eight heads handled by neighbouring lanes read 128 contiguous bytes (the
+// [token][head][d] order put them 64 bytes apart: 4-way bank conflicts on every one of the 224 loads per thread).
 __global__ void __launch_bounds__(256) i2t_attention_kernel(float const* __restrict__ Q, int64_t q_stride,
                                                             float const* __restrict__ kt, float const* __restrict__ vt,
                                                             float* __restrict__ out) {
-    __shared__ float ks[kTokens * 128];
-    __shared__ float vs[kTokens * 128];
+    __shared__ float4 ks[kTokens * 4 * 8];
+    __shared__ float4 vs[kTokens * 4 * 8];
     int const p = blockIdx.y;
-    for (int i = threadIdx.x; i < kTokens * 128; i += blockDim.x) {
-        ks[i] = kt[(size_t)p * kTokens * 128 + i];
-        vs[i] = vt[(size_t)p * kTokens * 128 + i];
+    for (int i = threadIdx.x; i < kTokens * 32; i += blockDim.x) {
+        int const t = i >> 5, hh = (i >> 2) & 7, dq = i & 3;  // source order: [t][head][d / 4]
+        float4 const* ksrc = reinterpret_cast<float4 const*>(kt + (size_t)p * kTokens * 128);
+        float4 const* vsrc = reinterpret_cast<float4 const*>(vt + (size_t)p * kTokens * 128);
+        ks[(t * 4 + dq) * 8 + hh] = ksrc[i];
+        vs[(t * 4 + dq) * 8 + hh] = vsrc[i];
     }
     __syncthreads();
     int const idx = blockIdx.x * blockDim.x + threadIdx.x;  // (token, head)
     int const i = idx >> 3, h = idx & 7;
-    float qv[16];
+    float4 qv[4];
     float4 const* q4 = reinterpret_cast<float4 const*>(Q + (size_t)p * q_stride + (size_t)i * 128 + h * 16);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float4 const x = q4[c];
-        qv[4 * c] = x.x; qv[4 * c + 1] = x.y; qv[4 * c + 2] = x.z; qv[4 * c + 3] = x.w;
-    }
+    for (int c = 0; c < 4; ++c) qv[c] = q4[c];
     float s[kTokens];
     float mx = -INFINITY;
 #pragma unroll
     for (int t = 0; t < kTokens; ++t) {
         float a = 0.f;
 #pragma unroll
-        for (int d = 0; d < 16; ++d) a = fmaf(qv[d], ks[t * 128 + h * 16 + d], a);
+        for (int c = 0; c < 4; ++c) {
+            float4 const k4 = ks[(t * 4 + c) * 8 + h];
+            a = fmaf(qv[c].x, k4.x, a);
+            a = fmaf(qv[c].y, k4.y, a);
+            a = fmaf(qv[c].z, k4.z, a);
+            a = fmaf(qv[c].w, k4.w, a);
+        }
         s[t] = a * 0.25f;
         mx = fmaxf(mx, s[t]);
     }
@@ -289,18 +298,24 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(float const* __restr
         sum += s[t];
     }
     float const inv = 1.0f / sum;
-    float o[16];
+    float4 o[4];
 #pragma unroll
-    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+    for (int c = 0; c < 4; ++c) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < kTokens; ++t) {
         float const w = s[t] * inv;
 #pragma unroll
-        for (int d = 0; d < 16; ++d) o[d] = fmaf(w, vs[t * 128 + h * 16 + d], o[d]);
+        for (int c = 0; c < 4; ++c) {
+            float4 const v4 = vs[(t * 4 + c) * 8 + h];
+            o[c].x = fmaf(w, v4.x, o[c].x);
+            o[c].y = fmaf(w, v4.y, o[c].y);
+            o[c].z = fmaf(w, v4.z, o[c].z);
+            o[c].w = fmaf(w, v4.w, o[c].w);
+        }
     }
     float4* o4 = reinterpret_cast<float4*>(out + ((size_t)p * kImgTokens + i) * 128 + h * 16);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) o4[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+    for (int c = 0; c < 4; ++c) o4[c] = o[c];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -403,6 +418,42 @@ __global__ void __launch_bounds__(256) mask_dot_kernel(float const* __restrict__
     }
 #pragma unroll
     for (int m = 0; m < 4; ++m) low[((size_t)p * 4 + m) * 65536 + pix] = acc[m];
+}
+
+// The five 3-layer token MLPs at the end of the decoder (IoU head on the iou token, one hypernetwork per mask token):
+// one CTA per (prompt, head) runs all three layers with the activations in shared memory, a warp per output feature
+// with coalesced weight rows.  Replaces 15 launches of 14-23 us each (tools/gpu_dec_launches.sh).
+__global__ void __launch_bounds__(256) token_mlp3_kernel(float const* __restrict__ tokens, TokenMlp3 heads,
+                                                         float* __restrict__ hyper, float* __restrict__ iou) {
+    __shared__ __align__(16) float xa[kDim], xb[kDim];
+    int const p = blockIdx.x, m = blockIdx.y;  // m = 0: IoU head (token 0), m = 1..4: hypernetwork of mask token m
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    xa[threadIdx.x] = tokens[((size_t)p * kTokens + m) * kDim + threadIdx.x];
+    __syncthreads();
+    auto layer = [&](float const* __restrict__ W, float const* __restrict__ b, int n_out, float const* x, float* y, bool relu,
+                     int64_t y_stride_dummy) {
+        (void)y_stride_dummy;
+        float4 const x0 = reinterpret_cast<float4 const*>(x)[lane * 2], x1 = reinterpret_cast<float4 const*>(x)[lane * 2 + 1];
+        for (int n = warp; n < n_out; n += 8) {
+            float4 const* w4 = reinterpret_cast<float4 const*>(W + (size_t)n * kDim) + lane * 2;
+            float4 const w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+            float a = x0.x * w0.x;
+            a = fmaf(x0.y, w0.y, a); a = fmaf(x0.z, w0.z, a); a = fmaf(x0.w, w0.w, a);
+            a = fmaf(x1.x, w1.x, a); a = fmaf(x1.y, w1.y, a); a = fmaf(x1.z, w1.z, a); a = fmaf(x1.w, w1.w, a);
+            a = warp_sum(a);
+            if (lane == 0) {
+                a += b[n];
+                y[n] = relu ? fmaxf(a, 0.f) : a;
+            }
+        }
+    };
+    layer(heads.w[m][0], heads.b[m][0], kDim, xa, xb, true, 0);
+    __syncthreads();
+    layer(heads.w[m][1], heads.b[m][1], kDim, xb, xa, true, 0);
+    __syncthreads();
+    int const n_out = m == 0 ? 4 : 32;
+    float* dst = m == 0 ? iou + (size_t)p * 4 : hyper + ((size_t)p * 4 + (m - 1)) * 32;
+    layer(heads.w[m][2], heads.b[m][2], n_out, xa, dst, false, 0);
 }
 
 __global__ void select_masks_kernel(float const* __restrict__ iou, int P, int multi, int* __restrict__ plane_index,
@@ -512,6 +563,12 @@ void mask_dot(cudaStream_t s, float const* hyper, float const* up2, int P, float
     ProfScope prof(s, CAT_DEC_MISC);
     dim3 grid(65536 / 256, P);
     mask_dot_kernel<<<grid, 256, 0, s>>>(hyper, up2, low);
+    KERNEL_CHECK();
+}
+
+void token_mlp3(cudaStream_t s, float const* tokens, int P, TokenMlp3 const& heads, float* hyper, float* iou) {
+    ProfScope prof(s, CAT_DEC_LINEAR);
+    token_mlp3_kernel<<<dim3((unsigned)P, 5), 256, 0, s>>>(tokens, heads, hyper, iou);
     KERNEL_CHECK();
 }
 

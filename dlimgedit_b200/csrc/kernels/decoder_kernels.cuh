@@ -68,6 +68,14 @@ void layernorm64_gelu(cudaStream_t s, float* x, int64_t rows, float const* gamma
 // Y = 4y + 2dy + ey, X = 4x + 2dx + ex.
 void mask_dot(cudaStream_t s, float const* hyper, float const* up2, int P, float* low);
 
+// IoU head (slot 0, on token 0, 256 -> 256 -> 256 -> 4) and the four hypernetwork MLPs (slots 1..4, on mask tokens 1..4,
+// 256 -> 256 -> 256 -> 32), ReLU between layers: tokens (P, 7, 256) -> iou (P, 4), hyper (P, 4, 32).
+struct TokenMlp3 {
+    float const* w[5][3];
+    float const* b[5][3];
+};
+void token_mlp3(cudaStream_t s, float const* tokens, int P, TokenMlp3 const& heads, float* hyper, float* iou);
+
 // Mask selection of the decoder graphs.  iou (P, 4).
 //   multi == 0: plane_index[p] = p*4 + argmax(iou + (2 - 2.5) * [1000, 0, 0, 0]); iou_out[p] = iou of that token
 //   multi != 0: plane_index[p*3 + i] = p*4 + 1 + i; iou_out[p*3 + i] = iou[p, 1 + i]

@@ -638,7 +638,8 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
     CUtensorMap mb = make_map(b, tf32, block_n);
     int const tiles = ceil_div(M, kBlockM) * (N / block_n);
     ProfScope prof(stream, tf32 ? CAT_GEMM_TF32 : CAT_GEMM_BF16, 2.0 * M * N * K,
-                   (double)(tf32 ? 4 : 2) * ((double)M * K + (double)N * K) + (double)(ep.out_f32 ? 4 : 2) * M * N);
+                   (double)(tf32 ? 4 : 2) * ((double)M * K + (double)N * K) +
+                       (double)(ep.out_f32 ? 4 : 2) * M * N * (ep.residual ? 2.0 : 1.0));
     int const grid = tiles < num_sms ? tiles : num_sms;
     // plain 16-bit outputs go through the coalescing (staged) epilogue; residual / scatter / fp32 outputs store directly
     static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch

@@ -3,6 +3,8 @@
 
 #include "../profiler.hpp"
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -301,6 +303,94 @@ __global__ void __launch_bounds__(256) mask_post_kernel(float const* __restrict_
     }
 }
 
+// Same arithmetic, organised per block of kPostRows output rows: the 1024-grid samples those rows need (two grid
+// rows each, de-duplicated) are computed once into shared memory, then every output pixel combines four of them.
+// The per-pixel form above evaluates sample_1024 four times per output pixel; here it is ~1.25 (1024^2 output) to
+// ~0.3 (4K output) times, with bit-identical results (same operations in the same order).
+constexpr int kPostRows = 4;
+constexpr int kPostSlots = 2 * kPostRows;      // 1024-grid rows a block may need
+constexpr int kPostLowRows = 2 * kPostSlots;   // low-resolution rows those may need
+
+__global__ void __launch_bounds__(256) mask_post_rows_kernel(float const* __restrict__ low_res, int64_t plane_stride,
+                                                             int const* __restrict__ plane_index, int rw, int rh, int w,
+                                                             int h, float sx, float sy,
+                                                             uint8_t* const* __restrict__ out_planes,
+                                                             uint8_t* __restrict__ out_contig) {
+    extern __shared__ __align__(16) float post_smem[];
+    float (*grid_rows)[kImageSize] = reinterpret_cast<float (*)[kImageSize]>(post_smem);
+    float (*low_rows)[kLowRes] = reinterpret_cast<float (*)[kLowRes]>(post_smem + kPostSlots * kImageSize);
+    int const plane = blockIdx.y;
+    int const y0 = blockIdx.x * kPostRows;
+    float const* low = low_res + (plane_index ? plane_index[plane] : plane) * plane_stride;
+    // Every thread derives the (tiny) row tables itself -- no serial set-up phase.  The 1024-grid rows needed by the
+    // block's output rows are consecutive when the vertical scale is <= 1.75 (slot = row - first row); otherwise each
+    // output row gets its own two slots.  Likewise for the low-resolution rows behind them.
+    Lerp ly[kPostRows];
+#pragma unroll
+    for (int t = 0; t < kPostRows; ++t) ly[t] = lerp_coord(min(y0 + t, h - 1), sy, rh);
+    int const g_base = ly[0].i0, g_span = ly[kPostRows - 1].i1 - g_base + 1;
+    bool const g_dense = g_span <= kPostSlots;
+    int const n_slots = g_dense ? g_span : kPostSlots;
+    auto grid_row_of = [&](int slot) {
+        if (g_dense) return g_base + slot;
+        int r = 0;
+#pragma unroll
+        for (int t = 0; t < kPostRows; ++t) {
+            if (slot == 2 * t) r = ly[t].i0;
+            if (slot == 2 * t + 1) r = ly[t].i1;
+        }
+        return r;
+    };
+    int const l_base = lerp_coord(grid_row_of(0), 0.25f, kLowRes).i0;
+    int const l_span = lerp_coord(grid_row_of(n_slots - 1), 0.25f, kLowRes).i1 - l_base + 1;
+    bool const l_dense = g_dense && l_span <= kPostLowRows;
+    int const n_low = l_dense ? l_span : 2 * n_slots;
+    for (int i = threadIdx.x; i < n_low * kLowRes; i += blockDim.x) {
+        int const j = i >> 8;
+        int row;
+        if (l_dense) {
+            row = l_base + j;
+        } else {
+            Lerp const q = lerp_coord(grid_row_of(j >> 1), 0.25f, kLowRes);
+            row = (j & 1) ? q.i1 : q.i0;
+        }
+        low_rows[j][i & 255] = __ldg(low + row * kLowRes + (i & 255));
+    }
+    __syncthreads();
+    // grid_rows[slot][xx] = sample_1024(low, grid row of slot, xx), taps from shared memory; the horizontal
+    // coordinates are computed once per column and reused for every slot
+    for (int xx = threadIdx.x; xx < rw; xx += blockDim.x) {
+        Lerp const lx = lerp_coord(xx, 0.25f, kLowRes);
+        for (int slot = 0; slot < n_slots; ++slot) {
+            Lerp const q = lerp_coord(grid_row_of(slot), 0.25f, kLowRes);
+            float const* r0 = low_rows[l_dense ? q.i0 - l_base : 2 * slot];
+            float const* r1 = low_rows[l_dense ? q.i1 - l_base : 2 * slot + 1];
+            float const top = lx.l0 * r0[lx.i0] + lx.l1 * r0[lx.i1];
+            float const bot = lx.l0 * r1[lx.i0] + lx.l1 * r1[lx.i1];
+            grid_rows[slot][xx] = q.l0 * top + q.l1 * bot;
+        }
+    }
+    __syncthreads();
+    uint8_t* const plane_out = out_planes ? out_planes[plane] : out_contig + (size_t)plane * w * h;
+    // one pixel per lane and iteration: neighbouring lanes read neighbouring grid samples (no bank conflicts) and
+    // their byte stores coalesce into whole sectors; the horizontal coordinate is shared by the block's rows
+    for (int x = threadIdx.x; x < w; x += blockDim.x) {
+        Lerp const lx = lerp_coord(x, sx, rw);
+#pragma unroll
+        for (int t = 0; t < kPostRows; ++t) {
+            int const y = y0 + t;
+            if (y < h) {
+                float const* r0 = grid_rows[g_dense ? ly[t].i0 - g_base : 2 * t];
+                float const* r1 = grid_rows[g_dense ? ly[t].i1 - g_base : 2 * t + 1];
+                float const top = lx.l0 * r0[lx.i0] + lx.l1 * r0[lx.i1];
+                float const bot = lx.l0 * r1[lx.i0] + lx.l1 * r1[lx.i1];
+                float const v = ly[t].l0 * top + ly[t].l1 * bot;
+                plane_out[(size_t)y * w + x] = v > 0.f ? 255 : 0;
+            }
+        }
+    }
+}
+
 __global__ void threshold_kernel(float const* __restrict__ logits, int tw, int w, int h, uint8_t* __restrict__ out) {
     int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)w * h) return;
@@ -315,8 +405,20 @@ void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride
     // torch: scale = float(input_size) / output_size
     float const sx = (float)rw / (float)w, sy = (float)rh / (float)h;
     ProfScope prof(s, CAT_MASK_POST, 0, (double)count * (65536.0 * 4 + (double)w * h));
-    dim3 block(256), grid(ceil_div(ceil_div(w, 4), 256), h, count);
-    mask_post_kernel<<<grid, block, 0, s>>>(low_res, plane_stride, plane_index, rw, rh, w, h, sx, sy, out_planes, out_contig);
+    static bool const per_pixel = std::getenv("DLIMG_B200_MASK_POST_PIXEL") != nullptr;  // A/B: the per-pixel form
+    if (per_pixel) {
+        dim3 block(256), grid(ceil_div(ceil_div(w, 4), 256), h, count);
+        mask_post_kernel<<<grid, block, 0, s>>>(low_res, plane_stride, plane_index, rw, rh, w, h, sx, sy, out_planes, out_contig);
+    } else {
+        dim3 grid(ceil_div(h, kPostRows), count);
+        constexpr int kPostSmem = (kPostSlots * kImageSize + kPostLowRows * kLowRes) * (int)sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(mask_post_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostSmem));
+            attr_set = true;
+        }
+        mask_post_rows_kernel<<<grid, 256, kPostSmem, s>>>(low_res, plane_stride, plane_index, rw, rh, w, h, sx, sy, out_planes, out_contig);
+    }
     KERNEL_CHECK();
 }
 

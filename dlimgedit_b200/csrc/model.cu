@@ -603,15 +603,18 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, EmbeddingCache const
     dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, dec_.norm_final.g.get(), dec_.norm_final.b.get(), nullptr, 0,
                       ws.queries.get(), nullptr);
 
-    // IoU head on the iou token, hypernetwork MLPs on the four mask tokens (row stride 7*256 selects the token)
-    int64_t const ts = (int64_t)dec::kTokens * 256;
-    lin(s, ws.queries.get(), ts, nullptr, P, dec_.iou[0], true, ws.h1.get(), 256);
-    lin(s, ws.h1.get(), 256, nullptr, P, dec_.iou[1], true, ws.h2.get(), 256);
-    lin(s, ws.h2.get(), 256, nullptr, P, dec_.iou[2], false, ws.iou.get(), 4);
-    for (int m = 0; m < 4; ++m) {
-        lin(s, ws.queries.get() + (1 + m) * 256, ts, nullptr, P, dec_.hyper[m][0], true, ws.h1.get(), 256);
-        lin(s, ws.h1.get(), 256, nullptr, P, dec_.hyper[m][1], true, ws.h2.get(), 256);
-        lin(s, ws.h2.get(), 256, nullptr, P, dec_.hyper[m][2], false, ws.hyper.get() + m * 32, 128);
+    // IoU head on the iou token, hypernetwork MLPs on the four mask tokens: one kernel for the five 3-layer MLPs
+    {
+        dec::TokenMlp3 h;
+        for (int l = 0; l < 3; ++l) {
+            h.w[0][l] = dec_.iou[l].w.get();
+            h.b[0][l] = dec_.iou[l].b.get();
+            for (int m = 0; m < 4; ++m) {
+                h.w[1 + m][l] = dec_.hyper[m][l].w.get();
+                h.b[1 + m][l] = dec_.hyper[m][l].b.get();
+            }
+        }
+        dec::token_mlp3(s, ws.queries.get(), P, h, ws.hyper.get(), ws.iou.get());
     }
 
     // upscaling: two transposed 2x2/stride-2 convolutions as GEMMs in a blocked pixel layout
