@@ -66,14 +66,20 @@ struct Cfg {
     static constexpr int kRowBytes = kHG * 192 + 16;  // [q|k|v] of kHG heads + 16 B: rows land in distinct bank groups
     static constexpr int kTileBytes = NKP * kRowBytes;
     static constexpr int kBiasBytes = kHG * NQ * NK8 * 32 * 8;
-    static constexpr int kSmemBytes = kBiasBytes + 2 * kTileBytes;
+    // 14x14 windows: the 83 KB bias table of a head would cap the SM at ONE 13-warp CTA, and the kernel is latency
+    // bound; the table stays in global memory instead (read-only path, L1 / L2 resident) so that two CTAs fit.
+    static constexpr bool kBiasInSmem = kBiasBytes <= 48 * 1024;
+    static constexpr int kSmemBias = kBiasInSmem ? kBiasBytes : 0;
+    static constexpr int kSmemBytes = kSmemBias + 2 * kTileBytes;
+    static constexpr int kMinBlocks = kBiasInSmem ? 1 : 2;
     static constexpr int kCPT = kHG * 12;        // 16-byte chunks per token
 };
 
 // One chunk of kCnt key blocks (8 keys each) of the online softmax for one (head, query tile).
-template <int kCnt, bool kFirst>
+template <int kCnt, bool kFirst, bool kBiasInSmem>
 __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4], uint32_t k_addr, uint32_t v_addr, int row_bytes,
-                                             uint32_t bias_addr, float (&m)[2], float (&l)[2], float (&o)[4][4]) {
+                                             uint32_t bias_addr, uint2 const* __restrict__ bias_gl, float (&m)[2], float (&l)[2],
+                                             float (&o)[4][4]) {
     float const kScale = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
     float s[kCnt][4];
 #pragma unroll
@@ -88,7 +94,13 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
 #pragma unroll
     for (int j = 0; j < kCnt; ++j) {
         uint32_t w0, w1;
-        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(bias_addr + (uint32_t)((nb0 + j) * 256)));
+        if (kBiasInSmem) {
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(bias_addr + (uint32_t)((nb0 + j) * 256)));
+        } else {
+            uint2 const bw = __ldg(bias_gl + (nb0 + j) * 32);
+            w0 = bw.x;
+            w1 = bw.y;
+        }
         float2 const f0 = __half22float2(*reinterpret_cast<__half2 const*>(&w0));
         float2 const f1 = __half22float2(*reinterpret_cast<__half2 const*>(&w1));
         s[j][0] = fmaf(s[j][0], kScale, f0.x);
@@ -149,13 +161,13 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
 }
 
 template <int kWS, int kHG>
-__global__ void __launch_bounds__(Cfg<kWS, kHG>::kThreads, 1)
+__global__ void __launch_bounds__(Cfg<kWS, kHG>::kThreads, Cfg<kWS, kHG>::kMinBlocks)
 window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int heads, act_t const* __restrict__ pad_qkv,
                          __half const* __restrict__ bias_frag, act_t* __restrict__ out) {
     using C = Cfg<kWS, kHG>;
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t const bias_s = smem_u32(smem);
-    uint32_t const tile0_s = bias_s + C::kBiasBytes;  // two token tiles (double buffer) follow the bias table
+    uint32_t const tile0_s = bias_s + C::kSmemBias;  // two token tiles (double buffer) follow the bias table
     int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int const n_groups = heads / kHG;
     int const hg = blockIdx.x % n_groups;
@@ -168,8 +180,9 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
     // zero for ever (K = 0 is masked by a -inf bias, V = 0 contributes nothing)
     {
         uint4 const* src = reinterpret_cast<uint4 const*>(bias_frag) + (size_t)hg * (C::kBiasBytes / 16);
-        for (int i = tid; i < C::kBiasBytes / 16; i += C::kThreads) reinterpret_cast<uint4*>(smem)[i] = __ldg(src + i);
-        uint4* t = reinterpret_cast<uint4*>(smem + C::kBiasBytes);
+        if (C::kBiasInSmem)
+            for (int i = tid; i < C::kBiasBytes / 16; i += C::kThreads) reinterpret_cast<uint4*>(smem)[i] = __ldg(src + i);
+        uint4* t = reinterpret_cast<uint4*>(smem + C::kSmemBias);
         for (int i = tid; i < 2 * C::kTileBytes / 16; i += C::kThreads) t[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
@@ -211,6 +224,8 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
     uint32_t const k_off = (uint32_t)((lane & 7) * C::kRowBytes + (hh * 96 + 32 + (lane >> 3) * 8) * 2);
     uint32_t const v_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * C::kRowBytes + (hh * 96 + 64 + ((lane >> 4) & 1) * 8) * 2);
     uint32_t const bias_addr = bias_s + (uint32_t)((((hh * C::NQ + qt) * C::NK8) * 32 + lane) * 8);
+    uint2 const* const bias_gl = reinterpret_cast<uint2 const*>(bias_frag) + (size_t)hg * (C::kBiasBytes / 8) +
+                                 ((hh * C::NQ + qt) * C::NK8) * 32 + lane;
 
     int it = 0;
     if (w_first < total_windows) load_item(w_first, 0);
@@ -233,13 +248,16 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
 #pragma unroll
         for (int d = 0; d < 4; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
         if constexpr (C::NK8 <= 8) {
-            attend_chunk<C::NK8, true>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
+            attend_chunk<C::NK8, true, C::kBiasInSmem>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o);
         } else {
             static_assert(C::NK8 <= 8 || C::NK8 == 25, "chunk schedule written for 196-token windows");
-            attend_chunk<8, true>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
-            attend_chunk<8, false>(8, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
-            attend_chunk<8, false>(16, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
-            attend_chunk<1, false>(24, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, m, l, o);
+            // 25 key blocks in chunks of 4 (+1): with the bias table in global memory the kernel runs two CTAs per SM
+            // at 72 registers, and a 4-block chunk (16 score registers) is what fits without spilling
+            attend_chunk<4, true, C::kBiasInSmem>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o);
+#pragma unroll
+            for (int c0 = 4; c0 < 24; c0 += 4)
+                attend_chunk<4, false, C::kBiasInSmem>(c0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o);
+            attend_chunk<1, false, C::kBiasInSmem>(24, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o);
         }
         l[0] += __shfl_xor_sync(0xffffffffu, l[0], 1);
         l[0] += __shfl_xor_sync(0xffffffffu, l[0], 2);
@@ -289,7 +307,7 @@ void launch_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int 
     int const n_groups = heads / kHG;
     int const nw = (res + kWS - 1) / kWS;
     int const items = batch * nw * nw * n_groups;
-    int grid = (num_sms / n_groups) * n_groups;
+    int grid = (num_sms * C::kMinBlocks / n_groups) * n_groups;
     if (grid > items) grid = items;
     window_attention_kernel2<kWS, kHG><<<grid, C::kThreads, C::kSmemBytes, s>>>(qkv, batch, res, heads, pad_qkv, bias_frag, out);
     KERNEL_CHECK();
