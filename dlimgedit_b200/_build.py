@@ -27,6 +27,7 @@ SOURCES = [
     "kernels/encoder_kernels.cu",
     "kernels/window_attention.cu",
     "kernels/patch_embed.cu",
+    "kernels/mbconv_tail.cu",
     "kernels/decoder_kernels.cu",
     "kernels/t2i_attention.cu",
     "kernels/prepost_kernels.cu",

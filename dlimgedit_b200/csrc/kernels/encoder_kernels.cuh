@@ -36,6 +36,12 @@ void patch_embed(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h,
 // (27, 32) fp32 conv1 weights [(ky*3+kx)*3+ci][oc] -> 512 packed fp16 pairs in mma B-fragment order.
 void patch_embed_w1_fragments(float const* w27x32, uint32_t* out512);
 
+// Second half of an MBConv block in one kernel (mbconv_tail.cu): depthwise 3x3 + GELU on the (B, 256, 256, 256) expanded
+// tensor (given as a TMA descriptor from gemm::make_tensor_map_nhwc, box 128 ch x 18 x 10), then 1x1 conv 256 -> 64 +
+// shortcut + GELU.  w3_map: K-major (64, 256) project weights, box 64 rows.
+void mbconv_tail(cudaStream_t s, CUtensorMap const& expanded_map, int batch, act_t const* dw_w16, float const* dw_b,
+                 CUtensorMap const& w3_map, float const* b3, act_t const* shortcut, act_t* out, int num_sms);
+
 // im2col for 3x3 / pad 1 convolutions on NHWC bf16: out[(b,oy,ox)][(ky,kx,c)] (K = 9*C).
 void im2col3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, act_t* out);
 

@@ -619,6 +619,20 @@ EpiParams to_params(Epilogue const& e, int N) {
 
 CUtensorMap make_tensor_map(Operand const& op, bool tf32, int box_rows) { return make_map(op, tf32, box_rows); }
 
+CUtensorMap make_tensor_map_nhwc(void const* ptr, int batch, int H, int W, int C, int box_c, int box_w, int box_h) {
+    CUtensorMap map;
+    DLIMG_ASSERT((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (C * 2) % 16 == 0 && box_c <= 256 && box_w <= 256 && box_h <= 256);
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode_fn()(&map, kActBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                             const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled (NHWC) failed with code " + std::to_string((int)r));
+    return map;
+}
+
 int pick_block_n(int N) {
     for (int bn = kMaxBlockN; bn >= 16; bn -= 16)
         if (N % bn == 0) return bn;

@@ -56,6 +56,10 @@ constexpr int kKBytes = 128;  // bytes of K per row per stage == swizzle span
 // Memoised TMA descriptor of a K-major operand: box = box_rows rows x 128 bytes of K, 128-byte swizzle.
 CUtensorMap make_tensor_map(Operand const& op, bool tf32, int box_rows);
 
+// TMA descriptor of a 16-bit NHWC activation tensor for halo-tile loads: box = box_h x box_w pixels x box_c channels
+// of one image, no swizzle, out-of-bounds elements (the convolution's zero padding) read as zero.
+CUtensorMap make_tensor_map_nhwc(void const* ptr, int batch, int H, int W, int C, int box_c, int box_w, int box_h);
+
 // Picks the widest legal tile width (multiple of 16, <= 256) that divides N.
 int pick_block_n(int N);
 

@@ -423,12 +423,20 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
     }
     tap_act(s, tap, "patch_embed", x, (size_t)B * 65536 * 64);
 
-    // layer 0: MBConv x2 (1x1 expand + GELU, dw3x3 + GELU, 1x1 project + shortcut + GELU)
+    // layer 0: MBConv x2: 1x1 expand + GELU (GEMM), then depthwise 3x3 + GELU + 1x1 project + shortcut + GELU in one
+    // kernel (DLIMG_B200_UNFUSED_MBCONV=1 keeps the depthwise kernel + project GEMM, used to cross-check)
+    static bool const unfused_mbconv = kActBf16 || std::getenv("DLIMG_B200_UNFUSED_MBCONV") != nullptr;
     for (int i = 0; i < 2; ++i) {
         MBConvW const& m = enc_.mb[i];
         gemm16(s, x, B * 65536, m.conv1, ws.big[0].get(), ACT_GELU, nullptr);
-        enc::dwconv3x3(s, ws.big[0].get(), batch, 256, 256, 256, 1, m.conv2.w.get(), m.conv2.w16.get(), m.conv2.b.get(), true, ws.big[1].get());
-        gemm16(s, ws.big[1].get(), B * 65536, m.conv3, y, ACT_GELU, x);
+        if (unfused_mbconv) {
+            enc::dwconv3x3(s, ws.big[0].get(), batch, 256, 256, 256, 1, m.conv2.w.get(), m.conv2.w16.get(), m.conv2.b.get(), true, ws.big[1].get());
+            gemm16(s, ws.big[1].get(), B * 65536, m.conv3, y, ACT_GELU, x);
+        } else {
+            CUtensorMap const in_map = gemm::make_tensor_map_nhwc(ws.big[0].get(), batch, 256, 256, 256, 128, 18, 10);
+            CUtensorMap const w3_map = gemm::make_tensor_map(gemm::Operand{m.conv3.w.get(), 64, 256, 256}, false, 64);
+            enc::mbconv_tail(s, in_map, batch, m.conv2.w16.get(), m.conv2.b.get(), w3_map, m.conv3.b.get(), x, y, num_sms_);
+        }
         std::swap(x, y);
         tap_act(s, tap, i == 0 ? "mb0" : "mb1", x, (size_t)B * 65536 * 64);
     }

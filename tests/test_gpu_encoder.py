@@ -49,6 +49,26 @@ def test_conv1_and_patch_embed(env, oracle_sam, case):
     assert cosine(got, ref) > 0.9999 and _rel(got, ref) < 1.5e-2
 
 
+def test_mbconv_blocks(env, oracle_sam, case):
+    """Stage 0: expand GEMM + fused (depthwise 3x3 + GELU + project + shortcut + GELU) kernel, block by block."""
+    img, taps, _ = case
+    d = torch.from_numpy(img).cuda()
+    x = taps["patch_embed"]
+    for i, name in enumerate(["mb0", "mb1"]):
+        with torch.no_grad():
+            x = oracle_sam.image_encoder.layers[0].blocks[i](x)
+        got = encode_tap(env, [d], dl.Channels.rgba, name, 65536 * 64).cpu().view(65536, 64)
+        ref = _nchw_to_tokens(x)
+        c, r = cosine(got, ref), _rel(got, ref)
+        assert c > 0.9999 and r < 1.5e-2, (name, c, r)
+        # image border: the depthwise convolution's zero padding comes from the TMA out-of-bounds fill
+        edge = torch.zeros(256, 256, dtype=torch.bool)
+        edge[0, :] = edge[-1, :] = True
+        edge[:, 0] = edge[:, -1] = True
+        e = edge.flatten()
+        assert cosine(got[e], ref[e]) > 0.9999 and _rel(got[e], ref[e]) < 1.5e-2
+
+
 @pytest.mark.parametrize("name,tokens,dim", [("layer0", 16384, 128), ("layer1", 4096, 160), ("layer2", 4096, 320),
                                              ("layer3", 4096, 320)])
 def test_stage_outputs(env, case, name, tokens, dim):
