@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="images per step per GPU")
+    ap.add_argument("--batch", type=int, default=32, help="images per step per GPU")
     ap.add_argument("--prompts", type=int, default=64, help="prompts per decoder step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=6, help="images timed for the cpu_baseline")
