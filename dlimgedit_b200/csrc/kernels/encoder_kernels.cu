@@ -575,7 +575,7 @@ void dwconv3x3_stats(cudaStream_t s, act_t const* in, int batch, int H, int W, i
         KERNEL_CHECK();                                                                                                   \
         return;                                                                                                           \
     }
-    DLIMG_DWS_CASE(128, 16) DLIMG_DWS_CASE(160, 8) DLIMG_DWS_CASE(320, 8)
+    DLIMG_DWS_CASE(128, 16) DLIMG_DWS_CASE(160, 8) DLIMG_DWS_CASE(320, 4)  // 256 / 160 / 160 threads: 2-3 blocks per SM at 128 registers
 #undef DLIMG_DWS_CASE
     fail("dwconv3x3_stats: unsupported (channels, width) = (" + std::to_string(C) + ", " + std::to_string(W) + ")");
 }
