@@ -7,6 +7,7 @@ rep = sys.argv[1]
 out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h = rows[0]
+units = rows[1]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_warps',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum',
@@ -31,5 +32,5 @@ for k, r in enumerate(rows[2:]):
                     continue
             except ValueError:
                 pass
-            print(w, '=', v)
+            print(w, '=', v, units[h.index(w)])
     print('---')
