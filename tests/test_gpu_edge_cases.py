@@ -95,3 +95,33 @@ def test_prompt_sweep_1_to_256(env):
         assert np.allclose(pi, ious[:n], atol=1e-6)
     for k in (0, 3, 255):
         assert np.array_equal(full[k][0], seg.compute_mask(prompts[k]))
+
+
+def test_repeatable_bits_across_runs_and_batch_slots(env):
+    """Race check by repetition (compute-sanitizer is closed on this pool): the same images give the same bits on every
+    run, in every batch slot and next to different neighbours -- the persistent kernels hand tiles, mbarrier phases and
+    shared-memory buffers from one image to the next, so a synchronisation slip would show up here."""
+    imgs = [synthetic_image(1024, 1024, 4, seed=40 + i) for i in range(5)]
+    dev = [torch.from_numpy(im).cuda() for im in imgs]
+
+    def run(order):
+        views = [dl.ImageView(dev[i].data_ptr(), dl.Extent(1024, 1024), dl.Channels.rgba, device=True) for i in order]
+        segs = env.process_batch(views)
+        env.synchronize()
+        return [s.embedding() for s in segs]
+
+    base = run([0, 1, 2, 3, 4])
+    for _ in range(3):
+        again = run([0, 1, 2, 3, 4])
+        for a, b in zip(base, again):
+            assert np.array_equal(a, b)
+    shuffled = run([4, 2, 0, 3, 1, 0, 0])
+    for slot, i in enumerate([4, 2, 0, 3, 1, 0, 0]):
+        assert np.array_equal(shuffled[slot], base[i])
+    # decoder: the same prompts, repeated and reordered
+    seg = env.process_batch([dl.ImageView(dev[0].data_ptr(), dl.Extent(1024, 1024), dl.Channels.rgba, device=True)])[0]
+    prompts = [dl.Point(100 + 37 * k, 900 - 29 * k) for k in range(20)]
+    m0, i0 = env.compute_masks_batch([seg] * 20, prompts, multi=False)
+    m1, i1 = env.compute_masks_batch([seg] * 20, prompts[::-1], multi=False)
+    for k in range(20):
+        assert np.array_equal(m0[k], m1[19 - k]) and i0[k, 0] == i1[19 - k, 0]
