@@ -157,6 +157,8 @@ class _Debug(ctypes.Structure):
                                      ctypes.c_void_p, ctypes.c_void_p)),
         ("layernorm_stats", _F(_R, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                ctypes.c_void_p)),
+        ("mlp_fused", _F(_R, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)),
     ]
 
 

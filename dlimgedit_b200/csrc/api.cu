@@ -278,6 +278,19 @@ dlimg_Result dbg_window_attention_simt(void* stream, void const* qkv, int window
     });
 }
 
+dlimg_Result dbg_mlp_fused(void* stream, void const* x, int rows, int C, void const* w1, float const* b1, float const* ln_sums,
+                           void const* w2, float const* b2, void* out, float* stats_out) {
+    return try_([=] {
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+        if (!gemm::mlp_fused_supported(C)) fail("mlp_fused: unsupported width " + std::to_string(C));
+        gemm::launch_mlp_fused(static_cast<cudaStream_t>(stream), x, rows, C, w1, b1, reinterpret_cast<float2 const*>(ln_sums), 1e-5f, w2,
+                               b2, out, reinterpret_cast<float2*>(stats_out), prop.multiProcessorCount);
+    });
+}
+
 dlimg_Result dbg_layernorm_stats(void* stream, void const* in, int rows, int C, float eps, float* out) {
     return try_([=] {
         enc::layernorm_stats(static_cast<cudaStream_t>(stream), static_cast<act_t const*>(in), rows, C, eps, reinterpret_cast<float2*>(out));
@@ -343,6 +356,7 @@ DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void) {
     debug_.window_attention = dbg_window_attention;
     debug_.window_attention_simt = dbg_window_attention_simt;
     debug_.layernorm_stats = dbg_layernorm_stats;
+    debug_.mlp_fused = dbg_mlp_fused;
     return &debug_;
 }
 

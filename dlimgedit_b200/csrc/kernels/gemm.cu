@@ -483,6 +483,287 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused TinyViT MLP: out = x + fc2(GELU(fc1(LN(x)))) for a 128-row tile, with the 4C-wide hidden activation living only
+// in TMEM and shared memory.  LN is folded into fc1 (row-centred weights, 1/std from row sums), fc2's epilogue adds the
+// residual and leaves the LayerNorm row sums of the result for the next block's qkv.
+//
+//   per tile:   A (128 x C, KB1 k-blocks) by TMA, double-buffered across tiles
+//   per chunk h of 64 hidden units (NH = 4C / 64 chunks):
+//     MMA1(h)   D1[h & 1] (128 x 64 fp32, TMEM) = A * W1[h*64 .. +64, :]^T           W1 chunk: TMA ring of 2
+//     EPI1(h)   16 warps, one 16-column slab each: TMEM -> rstd * acc + bias -> GELU -> fp16 -> H[h & 1] in shared
+//               memory in the 128B-swizzled K-major layout (the A operand of the second GEMM)
+//     MMA2(h)   D2 (128 x C fp32, TMEM) += H[h & 1] * W2[:, h*64 .. +64]^T             W2 chunk: TMA ring of 2
+//   EPI2        D2 -> + bias + residual -> fp16 -> global, row sums (fixed-order) -> stats_out
+//
+// MMA1(h + 1) is issued before MMA2(h), so the tensor pipe works on the next chunk while the epilogue warps turn the
+// current one into the H operand.  C <= 160 (one N tile for fc2, TMEM: 160 + 2 * 64 columns).
+struct MlpParams {
+    int M, C;                    // rows, model width (128 or 160)
+    float const* b1;             // [4C] folded fc1 bias
+    float const* b2;             // [C]
+    float2 const* ln_stats;      // [M] partial (sum, sum of squares) of the rows of x (ln_parts == 1)
+    float ln_eps;
+    act_t const* residual;       // [M][C] (= x)
+    act_t* out;                  // [M][C]
+    float2* stats_out;           // [M] (sum, sum of squares) of the output rows, or null
+};
+
+constexpr int kMlpChunk = 64;
+
+struct MlpSmem {
+    int kb1, a_bytes, w1_bytes, w2_bytes, total;
+    // layout: [barriers 1 KiB][red 8 KiB][A x2][W1 x2][W2 x2][H x2]
+};
+inline MlpSmem plan_mlp(int C) {
+    MlpSmem m;
+    m.kb1 = (C + 63) / 64;
+    m.a_bytes = m.kb1 * kAStageBytes;
+    m.w1_bytes = m.kb1 * kMlpChunk * kKBytes;
+    m.w2_bytes = C * kKBytes;
+    m.total = 1024 + 1024 + 8192 + 2 * (m.a_bytes + m.w1_bytes + m.w2_bytes + kAStageBytes);
+    return m;
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w1,
+                 const __grid_constant__ CUtensorMap tma_w2, MlpParams p, int kb1, int a_bytes, int w1_bytes, int w2_bytes) {
+    extern __shared__ uint8_t smem_raw[];
+    uint32_t const smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint32_t const bar_base = smem_base;
+    uint32_t const red_base = smem_base + 1024u;
+    uint32_t const a_base = red_base + 8192u;
+    uint32_t const w1_base = a_base + 2u * (uint32_t)a_bytes;
+    uint32_t const w2_base = w1_base + 2u * (uint32_t)w1_bytes;
+    uint32_t const h_base = w2_base + 2u * (uint32_t)w2_bytes;
+    // barrier slots (8 bytes each)
+    auto a_full = [&](int s) { return bar_base + 8u * (0 + s); };
+    auto a_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+    auto w1_full = [&](int s) { return bar_base + 8u * (4 + s); };
+    auto w1_empty = [&](int s) { return bar_base + 8u * (6 + s); };
+    auto w2_full = [&](int s) { return bar_base + 8u * (8 + s); };
+    auto w2_empty = [&](int s) { return bar_base + 8u * (10 + s); };
+    auto d1_full = [&](int s) { return bar_base + 8u * (12 + s); };
+    auto d1_empty = [&](int s) { return bar_base + 8u * (14 + s); };
+    auto h_full = [&](int s) { return bar_base + 8u * (16 + s); };
+    auto h_empty = [&](int s) { return bar_base + 8u * (18 + s); };
+    uint32_t const d2_full = bar_base + 8u * 20, d2_empty = bar_base + 8u * 21, tmem_slot = bar_base + 8u * 22;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int const C = p.C, NH = (4 * C) / kMlpChunk;
+    int const m_tiles = (p.M + kBlockM - 1) / kBlockM;
+    int const k_tail_bytes = (C - (kb1 - 1) * 64) * 2;  // valid bytes of the last k-block of the first GEMM
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_w1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_w2) : "memory");
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1);
+            mbar_init(w1_full(s), 1); mbar_init(w1_empty(s), 1);
+            mbar_init(w2_full(s), 1); mbar_init(w2_empty(s), 1);
+            mbar_init(d1_full(s), 1); mbar_init(d1_empty(s), kEpiWarps);
+            mbar_init(h_full(s), kEpiWarps); mbar_init(h_empty(s), 1);
+        }
+        mbar_init(d2_full, 1);
+        mbar_init(d2_empty, kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t const tmem_base = *tmem_slot_ptr;
+    uint32_t const tmem_d2 = tmem_base;           // columns [0, C)
+    uint32_t const tmem_d1 = tmem_base + 256u;    // two buffers of 64 columns
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            int lt = 0;
+            uint32_t w_use = 0;  // chunk counter across tiles: ring slot = w_use & 1, parity = (w_use >> 1) & 1
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++lt) {
+                int const as = lt & 1;
+                mbar_wait(a_empty(as), ((uint32_t)(lt >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(a_full(as), (uint32_t)a_bytes);
+                for (int kb = 0; kb < kb1; ++kb)
+                    tma_load_2d(a_base + as * a_bytes + kb * kAStageBytes, &tma_x, a_full(as), kb * 64, tile * kBlockM);
+                for (int h = 0; h < NH; ++h, ++w_use) {
+                    int const ws = w_use & 1;
+                    uint32_t const par = ((w_use >> 1) & 1u) ^ 1u;
+                    mbar_wait(w1_empty(ws), par);
+                    mbar_expect_tx(w1_full(ws), (uint32_t)w1_bytes);
+                    for (int kb = 0; kb < kb1; ++kb)
+                        tma_load_2d(w1_base + ws * w1_bytes + kb * (kMlpChunk * kKBytes), &tma_w1, w1_full(ws), kb * 64, h * kMlpChunk);
+                    mbar_wait(w2_empty(ws), par);
+                    mbar_expect_tx(w2_full(ws), (uint32_t)w2_bytes);
+                    tma_load_2d(w2_base + ws * w2_bytes, &tma_w2, w2_full(ws), h * kMlpChunk, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            uint32_t const fmt = kActBf16 ? 1u : 0u;
+            uint32_t const idesc1 = make_idesc(fmt, kBlockM, kMlpChunk);
+            uint32_t const idesc2 = make_idesc(fmt, kBlockM, C);
+            int lt = 0;
+            uint32_t u1 = 0, u2 = 0;  // chunk counters of the first / second GEMM across tiles
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++lt) {
+                int const as = lt & 1;
+                mbar_wait(a_full(as), (uint32_t)(lt >> 1) & 1u);
+                tc_fence_after();
+                for (int h = 0; h <= NH; ++h) {
+                    if (h < NH) {
+                        int const s1 = u1 & 1;
+                        uint32_t const par = (u1 >> 1) & 1u;
+                        mbar_wait(w1_full(s1), par);
+                        mbar_wait(d1_empty(s1), par ^ 1u);
+                        tc_fence_after();
+                        for (int kb = 0; kb < kb1; ++kb) {
+                            int const n_instr = kb + 1 < kb1 ? 4 : (k_tail_bytes + 31) >> 5;
+                            uint64_t const adesc = make_smem_desc(a_base + as * a_bytes + kb * kAStageBytes);
+                            uint64_t const bdesc = make_smem_desc(w1_base + s1 * w1_bytes + kb * (kMlpChunk * kKBytes));
+                            for (int k = 0; k < n_instr; ++k)
+                                tc_mma<0>(tmem_d1 + (uint32_t)(s1 * kMlpChunk), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1,
+                                          (uint32_t)((kb | k) != 0));
+                        }
+                        tc_commit(w1_empty(s1));
+                        tc_commit(d1_full(s1));
+                        if (h == NH - 1) tc_commit(a_empty(as));
+                        ++u1;
+                    }
+                    if (h >= 1) {
+                        int const g = h - 1, s2 = u2 & 1;
+                        uint32_t const par = (u2 >> 1) & 1u;
+                        mbar_wait(h_full(s2), par);
+                        mbar_wait(w2_full(s2), par);
+                        if (g == 0) mbar_wait(d2_empty, ((uint32_t)lt & 1u) ^ 1u);
+                        tc_fence_after();
+                        uint64_t const adesc = make_smem_desc(h_base + s2 * kAStageBytes);
+                        uint64_t const bdesc = make_smem_desc(w2_base + s2 * w2_bytes);
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma<0>(tmem_d2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (uint32_t)((g | k) != 0));
+                        tc_commit(w2_empty(s2));
+                        tc_commit(h_empty(s2));
+                        if (g == NH - 1) tc_commit(d2_full);
+                        ++u2;
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue warps ----------------
+        int const quarter = warp & 3, slab = (warp - 2) >> 2;
+        int const nslab = C >> 4;
+        int const s_cnt = nslab / 4 + (slab < (nslab & 3) ? 1 : 0);
+        int const s_first = slab * (nslab / 4) + min(slab, nslab & 3);
+        EpiParams ep;
+        ep.bias = p.b2;
+        ep.residual = p.residual;
+        ep.row_map = nullptr;
+        ep.ln_stats = nullptr;
+        ep.stats_out = p.stats_out;
+        ep.ln_parts = 0;
+        ep.ln_eps = p.ln_eps;
+        ep.act = ACT_NONE;
+        ep.out_f32 = 0;
+        ep.ldc = C;
+        int lt = 0;
+        uint32_t u = 0;  // chunk counter across tiles
+        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++lt) {
+            int const m0 = tile * kBlockM;
+            int const row = m0 + quarter * 32 + lane;
+            float rstd = 1.f;
+            if (row < p.M) {
+                float2 const pv = __ldg(p.ln_stats + row);
+                float const inv_k = 1.0f / (float)C, mean = pv.x * inv_k;
+                rstd = rsqrtf(fmaxf(fmaf(-mean, mean, pv.y * inv_k), 0.f) + p.ln_eps);
+            }
+            for (int h = 0; h < NH; ++h, ++u) {
+                int const sb = u & 1;
+                uint32_t const par = (u >> 1) & 1u;
+                mbar_wait(d1_full(sb), par);
+                tc_fence_after();
+                uint32_t r[16];
+                tmem_ld16(tmem_d1 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sb * kMlpChunk + slab * 16), r);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d1_empty(sb));
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                ln_bias16(v, p.b1, h * kMlpChunk + slab * 16, rstd);
+                uint4 x[2];
+                activate_pack16(v, ACT_GELU, x);
+                mbar_wait(h_empty(sb), par ^ 1u);  // the second GEMM of chunk h - 2 has finished reading this buffer
+                int const hrow = quarter * 32 + lane;
+                uint32_t const rowaddr = h_base + (uint32_t)(sb * kAStageBytes + hrow * 128);
+                uint32_t const c0 = (uint32_t)(slab * 2), sw = (uint32_t)(hrow & 7);
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + ((c0 ^ sw) << 4)), "r"(x[0].x), "r"(x[0].y), "r"(x[0].z), "r"(x[0].w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + (((c0 + 1) ^ sw) << 4)), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(h_full(sb));
+            }
+            // ---- second GEMM's accumulator: + bias + residual -> 16-bit -> global, row sums ----
+            mbar_wait(d2_full, (uint32_t)lt & 1u);
+            tc_fence_after();
+            SlabCtx cx;
+            cx.taddr = tmem_d2 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s_first * 16);
+            cx.tempty = d2_empty;
+            cx.stage_row = 0;
+            cx.col0 = s_first * 16;
+            cx.orow = row < p.M ? (int64_t)row : -1;
+            cx.rstd = 1.f;
+            cx.lane = lane;
+            cx.stage_base = 0;
+            cx.pitch = 0;
+            cx.out_seg = nullptr;
+            cx.ldc = C;
+            cx.rows_valid = p.M - (m0 + quarter * 32);
+            float row_sum = 0.f, row_sumsq = 0.f;
+            switch (s_cnt) {
+                case 3: epilogue_slabs<3, false, ACT_NONE, false>(cx, ep, p.out, row_sum, row_sumsq); break;
+                case 2: epilogue_slabs<2, false, ACT_NONE, false>(cx, ep, p.out, row_sum, row_sumsq); break;
+                default:
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d2_empty);
+                    break;
+            }
+            if (p.stats_out) {
+                uint32_t const red = red_base + (uint32_t)((lt & 1) * 4096);
+                uint32_t const mine = red + (uint32_t)(((quarter * 4 + slab) * 32 + lane) * 8);
+                asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(mine), "f"(row_sum), "f"(row_sumsq) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+                if (slab == 0 && row < p.M) {
+                    float sx = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4) {
+                        float a, b;
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)(((quarter * 4 + w4) * 32 + lane) * 8)));
+                        sx += a;
+                        sq += b;
+                    }
+                    p.stats_out[row] = make_float2(sx, sq);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
 // ---- CUDA-core cross-check / small-M kernel -------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
@@ -681,6 +962,43 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
         }
     }
     kernel<<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep);
+    KERNEL_CHECK();
+}
+
+bool mlp_fused_supported(int C) {
+#if defined(DLIMG_B200_ACT_BF16)
+    (void)C;
+    return false;
+#else
+    return (C == 128 || C == 160) && plan_mlp(C).total <= kSmemLimit;
+#endif
+}
+
+void launch_mlp_fused(cudaStream_t stream, void const* x, int64_t rows, int C, void const* w1, float const* b1,
+                      float2 const* ln_stats, float ln_eps, void const* w2, float const* b2, void* out, float2* stats_out,
+                      int num_sms) {
+    DLIMG_ASSERT(mlp_fused_supported(C));
+    int const M = (int)rows, H = 4 * C;
+    MlpSmem const sp = plan_mlp(C);
+    CUtensorMap const mx = make_map(Operand{x, rows, C, C}, false, kBlockM);
+    CUtensorMap const m1 = make_map(Operand{w1, H, C, C}, false, kMlpChunk);
+    CUtensorMap const m2 = make_map(Operand{w2, C, H, H}, false, C);
+    MlpParams p;
+    p.M = M;
+    p.C = C;
+    p.b1 = b1;
+    p.b2 = b2;
+    p.ln_stats = ln_stats;
+    p.ln_eps = ln_eps;
+    p.residual = static_cast<act_t const*>(x);
+    p.out = static_cast<act_t*>(out);
+    p.stats_out = stats_out;
+    ProfScope prof(stream, CAT_GEMM_BF16, 4.0 * M * (double)C * H, 2.0 * ((double)M * C * 3 + 2.0 * C * H));
+    static std::once_flag once;
+    std::call_once(once, [] { CUDA_CHECK(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); });
+    int const tiles = ceil_div(M, kBlockM);
+    int const grid = tiles < num_sms ? tiles : num_sms;
+    mlp_fused_kernel<<<grid, kNumThreads, sp.total, stream>>>(mx, m1, m2, p, sp.kb1, sp.a_bytes, sp.w1_bytes, sp.w2_bytes);
     KERNEL_CHECK();
 }
 

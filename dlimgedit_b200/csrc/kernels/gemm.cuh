@@ -67,6 +67,15 @@ int pick_block_n(int N);
 void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, void* out, Epilogue const& epi,
             int num_sms);
 
+// Fused TinyViT MLP for C = 128 / 160: out = x + fc2(GELU(fc1(LN(x)))) with the hidden activation kept in TMEM / shared
+// memory.  x (rows, C) 16-bit (also the residual; out may alias x), w1 (4C, C) with the LayerNorm folded in (gamma-scaled,
+// row-centred), b1 (4C) folded bias, ln_stats (rows) partial (sum, sum of squares) of x's rows, w2 (C, 4C), b2 (C);
+// stats_out (optional, rows): (sum, sum of squares) of the output rows.
+bool mlp_fused_supported(int C);
+void launch_mlp_fused(cudaStream_t stream, void const* x, int64_t rows, int C, void const* w1, float const* b1,
+                      float2 const* ln_stats, float ln_eps, void const* w2, float const* b2, void* out, float2* stats_out,
+                      int num_sms);
+
 // Plain CUDA-core GEMM with the same contract; used by tests to cross-check the tensor-core kernel and
 // for tiny problems (M < 64) where a 128-row tile would be mostly padding.
 void launch_simt(cudaStream_t stream, bool f32_operands, Operand const& a, Operand const& b, void* out,

@@ -459,6 +459,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         int const rows = (int)(B * L);
         float2* stats = ws.stats.get();
         int const fc2_parts = C / gemm::pick_block_n(C);  // N tiles of fc2 = partial sums per row
+        static bool const fused_mlp = std::getenv("DLIMG_B200_UNFUSED_MLP") == nullptr;
         for (int i = 0; i < c.depth; ++i) {
             BlockW const& b = enc_.blocks[st - 1][(size_t)i];
             std::string const tn = "s" + std::to_string(st) + "b" + std::to_string(i);
@@ -482,10 +483,16 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
             enc::dwconv3x3_stats(s, x, batch, c.res, c.res, C, b.local_conv.w.get(), b.local_conv.b.get(), y, stats);
             tap_act(s, tap, (tn + ".lc").c_str(), y, (size_t)rows * C);
             // MLP branch: LN folded into fc1 (row sums from the depthwise kernel above) + GELU, fc2 + residual
-            gemm16(s, y, rows, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, stats, false, 1);
-            // fc2 + residual; its epilogue also leaves the LayerNorm row sums of the result for the next block's qkv
-            gemm16(s, ws.big[1].get(), rows, b.fc2, y, ACT_NONE, y, nullptr, false, 0,
-                   i + 1 < c.depth ? ws.stats_parts.get() : nullptr);
+            float2* const next_stats = i + 1 < c.depth ? ws.stats_parts.get() : nullptr;
+            if (fused_mlp && gemm::mlp_fused_supported(C)) {
+                // one kernel: fc1 (+ folded LN, GELU) -> hidden activation in TMEM / shared memory -> fc2 + residual
+                gemm::launch_mlp_fused(s, y, rows, C, b.fc1.w.get(), b.fc1.b.get(), stats, 1e-5f, b.fc2.w.get(), b.fc2.b.get(), y,
+                                       next_stats, num_sms_);
+            } else {
+                gemm16(s, y, rows, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, stats, false, 1);
+                // fc2 + residual; its epilogue also leaves the LayerNorm row sums of the result for the next block's qkv
+                gemm16(s, ws.big[1].get(), rows, b.fc2, y, ACT_NONE, y, nullptr, false, 0, next_stats);
+            }
             std::swap(x, y);
             tap_act(s, tap, tn.c_str(), x, (size_t)rows * C);
         }

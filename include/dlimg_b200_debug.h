@@ -41,6 +41,11 @@ typedef struct dlimg_b200_Debug {
                                           float const* bias, void* out);
     /* Per-row LayerNorm statistics: in (rows, C) 16-bit -> out (rows, 2) fp32 (mean, rstd). */
     dlimg_Result (*layernorm_stats)(void* stream, void const* in, int rows, int C, float eps, float* out);
+    /* Fused TinyViT MLP (C = 128 / 160): out = x + fc2(GELU(fc1(LN(x)))).  w1 (4C, C): gamma-scaled, row-centred fc1
+     * weights; b1 (4C): folded bias; ln_sums (rows, 2): (sum, sum of squares) of x's rows; w2 (C, 4C); b2 (C);
+     * stats_out (optional, rows x 2): the same sums of the output rows. */
+    dlimg_Result (*mlp_fused)(void* stream, void const* x, int rows, int C, void const* w1, float const* b1,
+                              float const* ln_sums, void const* w2, float const* b2, void* out, float* stats_out);
 } dlimg_b200_Debug;
 
 DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void);

@@ -164,3 +164,42 @@ def test_f16_gemm_row_statistics_feed_the_next_folded_layernorm(M, C, K):
     out = gemm(x, w16, bias=b + w @ beta, ln_stats=stats, ln_parts=parts)
     ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.t() + b
     assert torch.allclose(out.float(), ref, atol=3e-2, rtol=1e-2), float((out.float() - ref).abs().max())
+
+
+@pytest.mark.parametrize("M,C", [(4096, 160), (1000, 128), (40000, 160), (300, 128)])
+def test_fused_mlp(M, C):
+    """fc1 (+ folded LayerNorm, GELU) -> hidden activation in TMEM / shared memory -> fc2 + residual, one kernel.
+    Reference: plain PyTorch fp32 LayerNorm / Linear / GELU / Linear on the same 16-bit input."""
+    import dlimgedit_b200 as dl
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    H = 4 * C
+    x = (torch.randn(M, C, device="cuda", generator=g) * 1.3 + 0.4).to(act_dtype())
+    w1 = torch.randn(H, C, device="cuda", generator=g) / C ** 0.5
+    b1 = 0.2 * torch.randn(H, device="cuda", generator=g)
+    w2 = torch.randn(C, H, device="cuda", generator=g) / H ** 0.5
+    b2 = 0.2 * torch.randn(C, device="cuda", generator=g)
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(C, device="cuda", generator=g)
+    xf = x.float()
+    hid = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xf, (C,), gamma, beta, 1e-5) @ w1.t() + b1)
+    ref = xf + hid @ w2.t() + b2
+    wg = w1 * gamma
+    w1c = (wg - wg.mean(1, keepdim=True)).to(act_dtype()).contiguous()
+    b1f = (b1 + w1 @ beta).contiguous()
+    sums = torch.stack([xf.sum(1), (xf * xf).sum(1)], 1).contiguous()
+    out = torch.zeros(M, C, device="cuda", dtype=act_dtype())
+    stats = torch.zeros(M, 2, device="cuda")
+    r = dl.debug().mlp_fused(None, x.data_ptr(), M, C, w1c.data_ptr(), b1f.data_ptr(), sums.data_ptr(),
+                             w2.to(act_dtype()).contiguous().data_ptr(), b2.data_ptr(), out.data_ptr(), stats.data_ptr())
+    assert r == 0, dl.api().last_error()
+    torch.cuda.synchronize()
+    assert torch.allclose(out.float(), ref, atol=4e-2, rtol=1.5e-2), float((out.float() - ref).abs().max())
+    assert torch.allclose(stats[:, 0], ref.sum(1), atol=5e-2, rtol=2e-3)
+    assert torch.allclose(stats[:, 1], (ref * ref).sum(1), atol=0.2, rtol=4e-3)
+    # in place (out aliases x), as the engine calls it
+    xi = x.clone()
+    r = dl.debug().mlp_fused(None, xi.data_ptr(), M, C, w1c.data_ptr(), b1f.data_ptr(), sums.data_ptr(),
+                             w2.to(act_dtype()).contiguous().data_ptr(), b2.data_ptr(), xi.data_ptr(), None)
+    assert r == 0, dl.api().last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(xi, out)
