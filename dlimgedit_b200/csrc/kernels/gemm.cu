@@ -347,12 +347,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // ---------------- MMA issuer: the whole warp walks the schedule, one elected lane issues ----------------
+        // (under `lane == 0` the compiler wraps every tcgen05.mma in an elect / branch loop and moves its descriptors
+        // from vector to uniform registers one by one; converged + elect.sync keeps it all on the uniform datapath)
+        {
             // instruction descriptor: D fp32, A/B bf16 or tf32, both K-major, N = block_n, M = 128
             uint32_t const fmt = kTF32 ? 2u : (kActBf16 ? 1u : 0u);  // UMMA F16F32Format: F16 = 0, BF16 = 1, TF32 = 2
-            uint32_t const idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) |
-                                   ((uint32_t)(kBlockM >> 4) << 24);
+            uint32_t const idesc = make_idesc(fmt, kBlockM, block_n);
+            uint64_t const adesc0 = make_smem_desc(a_stage(0)), bdesc0 = make_smem_desc(b_stage(0));
+            uint64_t const stage_step = (uint64_t)(stage_bytes >> 4);  // descriptor address field: 16-byte units
+            int const tail_bytes = (K - (num_kb - 1) * elems_per_kb) * elem_bytes;
+            int const tail_instr = (tail_bytes + 31) >> 5;
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -365,19 +370,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    int const valid_bytes = min(kKBytes, (K - kb * elems_per_kb) * elem_bytes);
-                    int const n_instr = (valid_bytes + 31) >> 5;
-                    uint64_t const adesc = make_smem_desc(a_stage(stage));
-                    uint64_t const bdesc = make_smem_desc(b_stage(stage));
-                    for (int k = 0; k < n_instr; ++k) {
+                    if (elect_one()) {
+                        uint64_t const adesc = adesc0 + (uint64_t)stage * stage_step;
+                        uint64_t const bdesc = bdesc0 + (uint64_t)stage * stage_step;
                         // advance 32 bytes of K inside the swizzle atom: +2 in the 16-byte address field
-                        tc_mma<kTF32>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                      (uint32_t)((kb | k) != 0));
+                        if (kb + 1 < num_kb) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma<kTF32>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        } else {
+                            for (int k = 0; k < tail_instr; ++k)
+                                tc_mma<kTF32>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                            tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                        }
+                        tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
                     }
-                    tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                    __syncwarp();
                     if (++stage == num_stages) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
             }
         }
     } else {
@@ -488,16 +498,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // in TMEM and shared memory.  LN is folded into fc1 (row-centred weights, 1/std from row sums), fc2's epilogue adds the
 // residual and leaves the LayerNorm row sums of the result for the next block's qkv.
 //
-//   per tile:   A (128 x C, KB1 k-blocks) by TMA, double-buffered across tiles
-//   per chunk h of 64 hidden units (NH = 4C / 64 chunks):
-//     MMA1(h)   D1[h & 1] (128 x 64 fp32, TMEM) = A * W1[h*64 .. +64, :]^T           W1 chunk: TMA ring of 2
-//     EPI1(h)   16 warps, one 16-column slab each: TMEM -> rstd * acc + bias -> GELU -> fp16 -> H[h & 1] in shared
+// The work of one CTA is a stream of chunks q = (tile, h), h = 64 hidden units, NH = 4C / 64 chunks per tile:
+//     MMA1(q)   D1[q & 3] (128 x 64 fp32, TMEM) = A(tile) * W1[h*64 .. +64, :]^T       W1 chunk: TMA ring of 2 or 4
+//     EPI1(q)   16 warps, one 16-column slab each: TMEM -> rstd * acc + bias -> GELU -> fp16 -> H[q & 1] in shared
 //               memory in the 128B-swizzled K-major layout (the A operand of the second GEMM)
-//     MMA2(h)   D2 (128 x C fp32, TMEM) += H[h & 1] * W2[:, h*64 .. +64]^T             W2 chunk: TMA ring of 2
-//   EPI2        D2 -> + bias + residual -> fp16 -> global, row sums (fixed-order) -> stats_out
+//     MMA2(q)   D2 (128 x C fp32, TMEM) += H[q & 1] * W2[:, h*64 .. +64]^T              W2 chunk: TMA ring of 2
+//   per tile:   A (128 x C) by TMA, double-buffered;  EPI2: D2 -> + bias + residual -> fp16 -> global, row sums
 //
-// MMA1(h + 1) is issued before MMA2(h), so the tensor pipe works on the next chunk while the epilogue warps turn the
-// current one into the H operand.  C <= 160 (one N tile for fc2, TMEM: 160 + 2 * 64 columns).
+// MMA1 runs kMlpLead chunks ahead of MMA2 (across tile boundaries), so an accumulator of the first GEMM is always
+// waiting when the epilogue warps finish a chunk: the round trip "H ready -> MMA2 -> MMA1 -> D1 ready" is off the
+// critical path, which is the epilogue warps' instruction issue.  C <= 160 (one N tile for fc2; TMEM: 160 + 4 * 64).
 struct MlpParams {
     int M, C;                    // rows, model width (128 or 160)
     float const* b1;             // [4C] folded fc1 bias
@@ -510,10 +520,11 @@ struct MlpParams {
 };
 
 constexpr int kMlpChunk = 64;
+constexpr int kMlpLead = 3;      // MMA1 chunks in flight ahead of MMA2 (D1 ring of kMlpLead + 1 = 4)
 
 struct MlpSmem {
-    int kb1, a_bytes, w1_bytes, w2_bytes, total;
-    // layout: [barriers 1 KiB][red 8 KiB][A x2][W1 x2][W2 x2][H x2]
+    int kb1, a_bytes, w1_bytes, w2_bytes, w1_ring_log, total;
+    // layout: [barriers 1 KiB][red 8 KiB][A x2][W1 x ring][W2 x2][H x2]
 };
 inline MlpSmem plan_mlp(int C) {
     MlpSmem m;
@@ -521,38 +532,91 @@ inline MlpSmem plan_mlp(int C) {
     m.a_bytes = m.kb1 * kAStageBytes;
     m.w1_bytes = m.kb1 * kMlpChunk * kKBytes;
     m.w2_bytes = C * kKBytes;
-    m.total = 1024 + 1024 + 8192 + 2 * (m.a_bytes + m.w1_bytes + m.w2_bytes + kAStageBytes);
+    int const fixed = 1024 + 1024 + 8192 + 2 * (m.a_bytes + m.w2_bytes + kAStageBytes);
+    m.w1_ring_log = fixed + 4 * m.w1_bytes <= kSmemLimit ? 2 : 1;
+    m.total = fixed + (m.w1_bytes << m.w1_ring_log);
     return m;
+}
+
+// fc2 accumulator slabs of one warp: + bias + residual (prefetched) -> 16-bit -> global, row sums
+template <int kCnt>
+__device__ __forceinline__ void mlp_epilogue2(uint32_t taddr, uint32_t d2_empty, int lane, float const* bias, int col0,
+                                              uint4 const (&res)[3][2], act_t* orow, bool stats, float& sum, float& sumsq) {
+    uint32_t r[2][16];
+    tmem_ld16(taddr, r[0]);
+#pragma unroll
+    for (int k = 0; k < kCnt; ++k) {
+        tmem_ld_wait();
+        if (k + 1 < kCnt) {
+            tmem_ld16(taddr + (uint32_t)((k + 1) * 16), r[(k + 1) & 1]);
+        } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d2_empty);
+        }
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
+        add_bias16(v, bias, col0 + k * 16);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            act2_t const* h = reinterpret_cast<act2_t const*>(&res[k][i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 const f = act22f2(h[j]);
+                v[8 * i + 2 * j] += f.x;
+                v[8 * i + 2 * j + 1] += f.y;
+            }
+        }
+        if (stats) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                sum += v[i];
+                sumsq = fmaf(v[i], v[i], sumsq);
+            }
+        }
+        uint4 x[2];
+        activate_pack16(v, ACT_NONE, x);
+        if (orow) {
+            uint4* o4 = reinterpret_cast<uint4*>(orow + k * 16);
+            o4[0] = x[0];
+            o4[1] = x[1];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kNumThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w1,
-                 const __grid_constant__ CUtensorMap tma_w2, MlpParams p, int kb1, int a_bytes, int w1_bytes, int w2_bytes) {
+                 const __grid_constant__ CUtensorMap tma_w2, MlpParams p, int kb1, int a_bytes, int w1_bytes, int w2_bytes,
+                 int w1_ring_log) {
     extern __shared__ uint8_t smem_raw[];
     uint32_t const smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint32_t const bar_base = smem_base;
     uint32_t const red_base = smem_base + 1024u;
     uint32_t const a_base = red_base + 8192u;
     uint32_t const w1_base = a_base + 2u * (uint32_t)a_bytes;
-    uint32_t const w2_base = w1_base + 2u * (uint32_t)w1_bytes;
+    uint32_t const w2_base = w1_base + ((uint32_t)w1_bytes << w1_ring_log);
     uint32_t const h_base = w2_base + 2u * (uint32_t)w2_bytes;
     // barrier slots (8 bytes each)
     auto a_full = [&](int s) { return bar_base + 8u * (0 + s); };
     auto a_empty = [&](int s) { return bar_base + 8u * (2 + s); };
-    auto w1_full = [&](int s) { return bar_base + 8u * (4 + s); };
-    auto w1_empty = [&](int s) { return bar_base + 8u * (6 + s); };
-    auto w2_full = [&](int s) { return bar_base + 8u * (8 + s); };
-    auto w2_empty = [&](int s) { return bar_base + 8u * (10 + s); };
-    auto d1_full = [&](int s) { return bar_base + 8u * (12 + s); };
-    auto d1_empty = [&](int s) { return bar_base + 8u * (14 + s); };
-    auto h_full = [&](int s) { return bar_base + 8u * (16 + s); };
-    auto h_empty = [&](int s) { return bar_base + 8u * (18 + s); };
-    uint32_t const d2_full = bar_base + 8u * 20, d2_empty = bar_base + 8u * 21, tmem_slot = bar_base + 8u * 22;
+    auto w2_full = [&](int s) { return bar_base + 8u * (4 + s); };
+    auto w2_empty = [&](int s) { return bar_base + 8u * (6 + s); };
+    auto h_full = [&](int s) { return bar_base + 8u * (8 + s); };
+    auto h_empty = [&](int s) { return bar_base + 8u * (10 + s); };
+    auto w1_full = [&](int s) { return bar_base + 8u * (12 + s); };
+    auto w1_empty = [&](int s) { return bar_base + 8u * (16 + s); };
+    auto d1_full = [&](int s) { return bar_base + 8u * (20 + s); };
+    auto d1_empty = [&](int s) { return bar_base + 8u * (24 + s); };
+    uint32_t const d2_full = bar_base + 8u * 28, d2_empty = bar_base + 8u * 29, tmem_slot = bar_base + 8u * 30;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int const C = p.C, NH = (4 * C) / kMlpChunk;
     int const m_tiles = (p.M + kBlockM - 1) / kBlockM;
+    int const my_tiles = (int)blockIdx.x < m_tiles ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    uint32_t const total = (uint32_t)(my_tiles * NH);   // chunks this CTA processes
+    uint32_t const w1_mask = (1u << w1_ring_log) - 1u;
     int const k_tail_bytes = (C - (kb1 - 1) * 64) * 2;  // valid bytes of the last k-block of the first GEMM
 
     if (warp == 0 && lane == 0) {
@@ -561,10 +625,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_w2) : "memory");
         for (int s = 0; s < 2; ++s) {
             mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1);
-            mbar_init(w1_full(s), 1); mbar_init(w1_empty(s), 1);
             mbar_init(w2_full(s), 1); mbar_init(w2_empty(s), 1);
-            mbar_init(d1_full(s), 1); mbar_init(d1_empty(s), kEpiWarps);
             mbar_init(h_full(s), kEpiWarps); mbar_init(h_empty(s), 1);
+        }
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(w1_full(s), 1); mbar_init(w1_empty(s), 1);
+            mbar_init(d1_full(s), 1); mbar_init(d1_empty(s), kEpiWarps);
         }
         mbar_init(d2_full, 1);
         mbar_init(d2_empty, kEpiWarps);
@@ -579,81 +645,103 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
     tc_fence_after();
     uint32_t const tmem_base = *tmem_slot_ptr;
     uint32_t const tmem_d2 = tmem_base;           // columns [0, C)
-    uint32_t const tmem_d1 = tmem_base + 256u;    // two buffers of 64 columns
+    uint32_t const tmem_d1 = tmem_base + 256u;    // four buffers of 64 columns
 
     if (warp == 0) {
-        // ---------------- TMA producer ----------------
-        if (lane == 0) {
-            int lt = 0;
-            uint32_t w_use = 0;  // chunk counter across tiles: ring slot = w_use & 1, parity = (w_use >> 1) & 1
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++lt) {
-                int const as = lt & 1;
-                mbar_wait(a_empty(as), ((uint32_t)(lt >> 1) & 1u) ^ 1u);
-                mbar_expect_tx(a_full(as), (uint32_t)a_bytes);
-                for (int kb = 0; kb < kb1; ++kb)
-                    tma_load_2d(a_base + as * a_bytes + kb * kAStageBytes, &tma_x, a_full(as), kb * 64, tile * kBlockM);
-                for (int h = 0; h < NH; ++h, ++w_use) {
-                    int const ws = w_use & 1;
-                    uint32_t const par = ((w_use >> 1) & 1u) ^ 1u;
-                    mbar_wait(w1_empty(ws), par);
-                    mbar_expect_tx(w1_full(ws), (uint32_t)w1_bytes);
+        // ---------------- TMA producer: A and W1 run kMlpLead chunks ahead of W2, like the MMAs that consume them ----
+        if (lane == 0 && total > 0) {
+            uint32_t q1 = 0;   // next first-GEMM chunk to load
+            int h1 = 0, lt1 = 0;
+            auto load_first = [&]() {
+                if (h1 == 0) {
+                    int const as = lt1 & 1;
+                    mbar_wait(a_empty(as), ((uint32_t)(lt1 >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(a_full(as), (uint32_t)a_bytes);
+                    int const tile = (int)blockIdx.x + lt1 * (int)gridDim.x;
                     for (int kb = 0; kb < kb1; ++kb)
-                        tma_load_2d(w1_base + ws * w1_bytes + kb * (kMlpChunk * kKBytes), &tma_w1, w1_full(ws), kb * 64, h * kMlpChunk);
-                    mbar_wait(w2_empty(ws), par);
-                    mbar_expect_tx(w2_full(ws), (uint32_t)w2_bytes);
-                    tma_load_2d(w2_base + ws * w2_bytes, &tma_w2, w2_full(ws), h * kMlpChunk, 0);
+                        tma_load_2d(a_base + as * a_bytes + kb * kAStageBytes, &tma_x, a_full(as), kb * 64, tile * kBlockM);
                 }
+                int const ws = (int)(q1 & w1_mask);
+                mbar_wait(w1_empty(ws), ((q1 >> w1_ring_log) & 1u) ^ 1u);
+                mbar_expect_tx(w1_full(ws), (uint32_t)w1_bytes);
+                for (int kb = 0; kb < kb1; ++kb)
+                    tma_load_2d(w1_base + ws * w1_bytes + kb * (kMlpChunk * kKBytes), &tma_w1, w1_full(ws), kb * 64, h1 * kMlpChunk);
+                ++q1;
+                if (++h1 == NH) { h1 = 0; ++lt1; }
+            };
+            for (int j = 0; j < kMlpLead && q1 < total; ++j) load_first();
+            int h2 = 0;
+            for (uint32_t q = 0; q < total; ++q) {
+                int const ws = (int)(q & 1u);
+                mbar_wait(w2_empty(ws), ((q >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(w2_full(ws), (uint32_t)w2_bytes);
+                tma_load_2d(w2_base + ws * w2_bytes, &tma_w2, w2_full(ws), h2 * kMlpChunk, 0);
+                if (++h2 == NH) h2 = 0;
+                if (q1 < total) load_first();
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // ---------------- MMA issuer: the whole warp walks the schedule, one elected lane issues ----------------
+        if (total > 0) {
             uint32_t const fmt = kActBf16 ? 1u : 0u;
             uint32_t const idesc1 = make_idesc(fmt, kBlockM, kMlpChunk);
             uint32_t const idesc2 = make_idesc(fmt, kBlockM, C);
-            int lt = 0;
-            uint32_t u1 = 0, u2 = 0;  // chunk counters of the first / second GEMM across tiles
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++lt) {
-                int const as = lt & 1;
-                mbar_wait(a_full(as), (uint32_t)(lt >> 1) & 1u);
+            uint64_t const a_desc0 = make_smem_desc(a_base), w1_desc0 = make_smem_desc(w1_base);
+            uint64_t const h_desc0 = make_smem_desc(h_base), w2_desc0 = make_smem_desc(w2_base);
+            // descriptor address fields are in 16-byte units
+            uint64_t const a_step = (uint64_t)(a_bytes >> 4), w1_step = (uint64_t)(w1_bytes >> 4), w2_step = (uint64_t)(w2_bytes >> 4);
+            int const tail_instr = (k_tail_bytes + 31) >> 5;
+            uint32_t q1 = 0;
+            int h1 = 0, lt1 = 0;
+            auto issue_first = [&]() {
+                int const as = lt1 & 1;
+                if (h1 == 0) mbar_wait(a_full(as), (uint32_t)(lt1 >> 1) & 1u);
+                int const s1 = (int)(q1 & w1_mask), d = (int)(q1 & 3u);
+                mbar_wait(w1_full(s1), (q1 >> w1_ring_log) & 1u);
+                mbar_wait(d1_empty(d), ((q1 >> 2) & 1u) ^ 1u);
                 tc_fence_after();
-                for (int h = 0; h <= NH; ++h) {
-                    if (h < NH) {
-                        int const s1 = u1 & 1;
-                        uint32_t const par = (u1 >> 1) & 1u;
-                        mbar_wait(w1_full(s1), par);
-                        mbar_wait(d1_empty(s1), par ^ 1u);
-                        tc_fence_after();
-                        for (int kb = 0; kb < kb1; ++kb) {
-                            int const n_instr = kb + 1 < kb1 ? 4 : (k_tail_bytes + 31) >> 5;
-                            uint64_t const adesc = make_smem_desc(a_base + as * a_bytes + kb * kAStageBytes);
-                            uint64_t const bdesc = make_smem_desc(w1_base + s1 * w1_bytes + kb * (kMlpChunk * kKBytes));
-                            for (int k = 0; k < n_instr; ++k)
-                                tc_mma<0>(tmem_d1 + (uint32_t)(s1 * kMlpChunk), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1,
-                                          (uint32_t)((kb | k) != 0));
-                        }
-                        tc_commit(w1_empty(s1));
-                        tc_commit(d1_full(s1));
-                        if (h == NH - 1) tc_commit(a_empty(as));
-                        ++u1;
-                    }
-                    if (h >= 1) {
-                        int const g = h - 1, s2 = u2 & 1;
-                        uint32_t const par = (u2 >> 1) & 1u;
-                        mbar_wait(h_full(s2), par);
-                        mbar_wait(w2_full(s2), par);
-                        if (g == 0) mbar_wait(d2_empty, ((uint32_t)lt & 1u) ^ 1u);
-                        tc_fence_after();
-                        uint64_t const adesc = make_smem_desc(h_base + s2 * kAStageBytes);
-                        uint64_t const bdesc = make_smem_desc(w2_base + s2 * w2_bytes);
+                if (elect_one()) {
+                    uint64_t adesc = a_desc0 + (uint64_t)as * a_step;
+                    uint64_t bdesc = w1_desc0 + (uint64_t)s1 * w1_step;
+                    uint32_t const dst = tmem_d1 + (uint32_t)(d * kMlpChunk);
+                    for (int kb = 0; kb + 1 < kb1; ++kb) {
+#pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            tc_mma<0>(tmem_d2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (uint32_t)((g | k) != 0));
-                        tc_commit(w2_empty(s2));
-                        tc_commit(h_empty(s2));
-                        if (g == NH - 1) tc_commit(d2_full);
-                        ++u2;
+                            tc_mma<0>(dst, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (uint32_t)((kb | k) != 0));
+                        adesc += (uint64_t)(kAStageBytes >> 4);
+                        bdesc += (uint64_t)((kMlpChunk * kKBytes) >> 4);
                     }
+                    for (int k = 0; k < tail_instr; ++k) tc_mma<0>(dst, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, 1u);
+                    tc_commit(w1_empty(s1));
+                    tc_commit(d1_full(d));
+                    if (h1 == NH - 1) tc_commit(a_empty(as));
                 }
+                __syncwarp();
+                ++q1;
+                if (++h1 == NH) { h1 = 0; ++lt1; }
+            };
+            for (int j = 0; j < kMlpLead && q1 < total; ++j) issue_first();
+            int h2 = 0, lt2 = 0;
+            for (uint32_t q = 0; q < total; ++q) {
+                int const s2 = (int)(q & 1u);
+                uint32_t const par = (q >> 1) & 1u;
+                mbar_wait(h_full(s2), par);
+                mbar_wait(w2_full(s2), par);
+                if (h2 == 0) mbar_wait(d2_empty, ((uint32_t)lt2 & 1u) ^ 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    uint64_t const adesc = h_desc0 + (uint64_t)s2 * (uint64_t)(kAStageBytes >> 4);
+                    uint64_t const bdesc = w2_desc0 + (uint64_t)s2 * w2_step;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma<0>(tmem_d2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (uint32_t)((h2 | k) != 0));
+                    tc_commit(w2_empty(s2));
+                    tc_commit(h_empty(s2));
+                    if (h2 == NH - 1) tc_commit(d2_full);
+                }
+                __syncwarp();
+                if (++h2 == NH) { h2 = 0; ++lt2; }
+                if (q1 < total) issue_first();
             }
         }
     } else {
@@ -662,46 +750,57 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
         int const nslab = C >> 4;
         int const s_cnt = nslab / 4 + (slab < (nslab & 3) ? 1 : 0);
         int const s_first = slab * (nslab / 4) + min(slab, nslab & 3);
-        EpiParams ep;
-        ep.bias = p.b2;
-        ep.residual = p.residual;
-        ep.row_map = nullptr;
-        ep.ln_stats = nullptr;
-        ep.stats_out = p.stats_out;
-        ep.ln_parts = 0;
-        ep.ln_eps = p.ln_eps;
-        ep.act = ACT_NONE;
-        ep.out_f32 = 0;
-        ep.ldc = C;
         int lt = 0;
         uint32_t u = 0;  // chunk counter across tiles
         for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++lt) {
             int const m0 = tile * kBlockM;
             int const row = m0 + quarter * 32 + lane;
+            bool const valid = row < p.M;
             float rstd = 1.f;
-            if (row < p.M) {
+            if (valid) {
                 float2 const pv = __ldg(p.ln_stats + row);
                 float const inv_k = 1.0f / (float)C, mean = pv.x * inv_k;
                 rstd = rsqrtf(fmaxf(fmaf(-mean, mean, pv.y * inv_k), 0.f) + p.ln_eps);
             }
+            uint4 res[3][2] = {};
             for (int h = 0; h < NH; ++h, ++u) {
-                int const sb = u & 1;
-                uint32_t const par = (u >> 1) & 1u;
-                mbar_wait(d1_full(sb), par);
+                int const sb = (int)(u & 1u), d = (int)(u & 3u);
+                // this chunk's bias and (before the last chunk) the residual of the tile: in flight during the wait below
+                float4 bq[4];
+                {
+                    float4 const* b4 = reinterpret_cast<float4 const*>(p.b1 + h * kMlpChunk + slab * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) bq[i] = __ldg(b4 + i);
+                }
+                if (h == NH - 1 && valid) {
+                    uint4 const* r4 = reinterpret_cast<uint4 const*>(p.residual + (int64_t)row * C + s_first * 16);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (k < s_cnt) {
+                            res[k][0] = __ldg(r4 + 2 * k);
+                            res[k][1] = __ldg(r4 + 2 * k + 1);
+                        }
+                    }
+                }
+                mbar_wait(d1_full(d), (u >> 2) & 1u);
                 tc_fence_after();
                 uint32_t r[16];
-                tmem_ld16(tmem_d1 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sb * kMlpChunk + slab * 16), r);
+                tmem_ld16(tmem_d1 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * kMlpChunk + slab * 16), r);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(d1_empty(sb));
+                if (lane == 0) mbar_arrive(d1_empty(d));
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                ln_bias16(v, p.b1, h * kMlpChunk + slab * 16, rstd);
+                for (int i = 0; i < 4; ++i) {
+                    v[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), rstd, bq[i].x);
+                    v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), rstd, bq[i].y);
+                    v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), rstd, bq[i].z);
+                    v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), rstd, bq[i].w);
+                }
                 uint4 x[2];
                 activate_pack16(v, ACT_GELU, x);
-                mbar_wait(h_empty(sb), par ^ 1u);  // the second GEMM of chunk h - 2 has finished reading this buffer
+                mbar_wait(h_empty(sb), ((u >> 1) & 1u) ^ 1u);  // the second GEMM of chunk u - 2 has finished reading this buffer
                 int const hrow = quarter * 32 + lane;
                 uint32_t const rowaddr = h_base + (uint32_t)(sb * kAStageBytes + hrow * 128);
                 uint32_t const c0 = (uint32_t)(slab * 2), sw = (uint32_t)(hrow & 7);
@@ -714,35 +813,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
             // ---- second GEMM's accumulator: + bias + residual -> 16-bit -> global, row sums ----
             mbar_wait(d2_full, (uint32_t)lt & 1u);
             tc_fence_after();
-            SlabCtx cx;
-            cx.taddr = tmem_d2 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s_first * 16);
-            cx.tempty = d2_empty;
-            cx.stage_row = 0;
-            cx.col0 = s_first * 16;
-            cx.orow = row < p.M ? (int64_t)row : -1;
-            cx.rstd = 1.f;
-            cx.lane = lane;
-            cx.stage_base = 0;
-            cx.pitch = 0;
-            cx.out_seg = nullptr;
-            cx.ldc = C;
-            cx.rows_valid = p.M - (m0 + quarter * 32);
+            uint32_t const taddr = tmem_d2 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s_first * 16);
+            act_t* const orow = valid ? p.out + (int64_t)row * C + s_first * 16 : nullptr;
             float row_sum = 0.f, row_sumsq = 0.f;
-            switch (s_cnt) {
-                case 3: epilogue_slabs<3, false, ACT_NONE, false>(cx, ep, p.out, row_sum, row_sumsq); break;
-                case 2: epilogue_slabs<2, false, ACT_NONE, false>(cx, ep, p.out, row_sum, row_sumsq); break;
-                default:
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(d2_empty);
-                    break;
-            }
+            if (s_cnt == 3) mlp_epilogue2<3>(taddr, d2_empty, lane, p.b2, s_first * 16, res, orow, p.stats_out != nullptr, row_sum, row_sumsq);
+            else mlp_epilogue2<2>(taddr, d2_empty, lane, p.b2, s_first * 16, res, orow, p.stats_out != nullptr, row_sum, row_sumsq);
             if (p.stats_out) {
                 uint32_t const red = red_base + (uint32_t)((lt & 1) * 4096);
                 uint32_t const mine = red + (uint32_t)(((quarter * 4 + slab) * 32 + lane) * 8);
                 asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(mine), "f"(row_sum), "f"(row_sumsq) : "memory");
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
-                if (slab == 0 && row < p.M) {
+                if (slab == 0 && valid) {
                     float sx = 0.f, sq = 0.f;
 #pragma unroll
                     for (int w4 = 0; w4 < 4; ++w4) {
@@ -998,7 +1079,7 @@ void launch_mlp_fused(cudaStream_t stream, void const* x, int64_t rows, int C, v
     std::call_once(once, [] { CUDA_CHECK(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); });
     int const tiles = ceil_div(M, kBlockM);
     int const grid = tiles < num_sms ? tiles : num_sms;
-    mlp_fused_kernel<<<grid, kNumThreads, sp.total, stream>>>(mx, m1, m2, p, sp.kb1, sp.a_bytes, sp.w1_bytes, sp.w2_bytes);
+    mlp_fused_kernel<<<grid, kNumThreads, sp.total, stream>>>(mx, m1, m2, p, sp.kb1, sp.a_bytes, sp.w1_bytes, sp.w2_bytes, sp.w1_ring_log);
     KERNEL_CHECK();
 }
 
