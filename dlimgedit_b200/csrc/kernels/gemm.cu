@@ -524,7 +524,7 @@ constexpr int kMlpLead = 3;      // MMA1 chunks in flight ahead of MMA2 (D1 ring
 
 struct MlpSmem {
     int kb1, a_bytes, w1_bytes, w2_bytes, w1_ring_log, total;
-    // layout: [barriers 1 KiB][red 8 KiB][A x2][W1 x ring][W2 x2][H x2]
+    // layout: [barriers 1 KiB][row-sum exchange 4 KiB][b1, b2 4 KiB][A x2][W1 x ring][W2 x2][H x2]
 };
 inline MlpSmem plan_mlp(int C) {
     MlpSmem m;
@@ -540,7 +540,7 @@ inline MlpSmem plan_mlp(int C) {
 
 // fc2 accumulator slabs of one warp: + bias + residual (prefetched) -> 16-bit -> global, row sums
 template <int kCnt>
-__device__ __forceinline__ void mlp_epilogue2(uint32_t taddr, uint32_t d2_empty, int lane, float const* bias, int col0,
+__device__ __forceinline__ void mlp_epilogue2(uint32_t taddr, uint32_t d2_empty, int lane, uint32_t bias_s, int col0,
                                               uint4 const (&res)[3][2], act_t* orow, bool stats, float& sum, float& sumsq) {
     uint32_t r[2][16];
     tmem_ld16(taddr, r[0]);
@@ -557,7 +557,13 @@ __device__ __forceinline__ void mlp_epilogue2(uint32_t taddr, uint32_t d2_empty,
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
-        add_bias16(v, bias, col0 + k * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 b;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                         : "r"(bias_s + (uint32_t)((col0 + k * 16 + 4 * i) * 4)));
+            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             act2_t const* h = reinterpret_cast<act2_t const*>(&res[k][i]);
@@ -593,6 +599,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
     uint32_t const smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint32_t const bar_base = smem_base;
     uint32_t const red_base = smem_base + 1024u;
+    uint32_t const bias_base = red_base + 4096u;  // b1 (4C floats) then b2 (C floats)
     uint32_t const a_base = red_base + 8192u;
     uint32_t const w1_base = a_base + 2u * (uint32_t)a_bytes;
     uint32_t const w2_base = w1_base + ((uint32_t)w1_bytes << w1_ring_log);
@@ -639,6 +646,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 5 * C; i += kNumThreads) {  // both bias vectors: read by every warp for every chunk
+        float const b = i < 4 * C ? __ldg(p.b1 + i) : __ldg(p.b2 + (i - 4 * C));
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * (uint32_t)i), "f"(b) : "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -752,40 +763,75 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
         int const s_first = slab * (nslab / 4) + min(slab, nslab & 3);
         int lt = 0;
         uint32_t u = 0;  // chunk counter across tiles
-        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++lt) {
-            int const m0 = tile * kBlockM;
-            int const row = m0 + quarter * 32 + lane;
-            bool const valid = row < p.M;
-            float rstd = 1.f;
-            if (valid) {
-                float2 const pv = __ldg(p.ln_stats + row);
-                float const inv_k = 1.0f / (float)C, mean = pv.x * inv_k;
-                rstd = rsqrtf(fmaxf(fmaf(-mean, mean, pv.y * inv_k), 0.f) + p.ln_eps);
-            }
-            uint4 res[3][2] = {};
-            for (int h = 0; h < NH; ++h, ++u) {
-                int const sb = (int)(u & 1u), d = (int)(u & 3u);
-                // this chunk's bias and (before the last chunk) the residual of the tile: in flight during the wait below
-                float4 bq[4];
-                {
-                    float4 const* b4 = reinterpret_cast<float4 const*>(p.b1 + h * kMlpChunk + slab * 16);
+        float2 pv_next = make_float2(0.f, 1.f);  // this lane's row sums, fetched one tile ahead
+        if ((int)blockIdx.x * kBlockM + quarter * 32 + lane < p.M) pv_next = __ldg(p.ln_stats + (int)blockIdx.x * kBlockM + quarter * 32 + lane);
+        uint4 res[3][2] = {};
+        auto load_residual = [&](int row) {
+            if (row < p.M) {
+                uint4 const* r4 = reinterpret_cast<uint4 const*>(p.residual + (int64_t)row * C + s_first * 16);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) bq[i] = __ldg(b4 + i);
-                }
-                if (h == NH - 1 && valid) {
-                    uint4 const* r4 = reinterpret_cast<uint4 const*>(p.residual + (int64_t)row * C + s_first * 16);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        if (k < s_cnt) {
-                            res[k][0] = __ldg(r4 + 2 * k);
-                            res[k][1] = __ldg(r4 + 2 * k + 1);
-                        }
+                for (int k = 0; k < 3; ++k) {
+                    if (k < s_cnt) {
+                        res[k][0] = __ldg(r4 + 2 * k);
+                        res[k][1] = __ldg(r4 + 2 * k + 1);
                     }
                 }
+            }
+        };
+        // second GEMM's accumulator of tile number `t` of this CTA: + bias + residual -> 16-bit -> global, row sums
+        auto finish_tile = [&](int row, int t) {
+            bool const valid = row < p.M;
+            mbar_wait(d2_full, (uint32_t)t & 1u);
+            tc_fence_after();
+            uint32_t const taddr = tmem_d2 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s_first * 16);
+            act_t* const orow = valid ? p.out + (int64_t)row * C + s_first * 16 : nullptr;
+            float row_sum = 0.f, row_sumsq = 0.f;
+            if (s_cnt == 3) mlp_epilogue2<3>(taddr, d2_empty, lane, bias_base + 16u * (uint32_t)C, s_first * 16, res, orow, p.stats_out != nullptr, row_sum, row_sumsq);
+            else mlp_epilogue2<2>(taddr, d2_empty, lane, bias_base + 16u * (uint32_t)C, s_first * 16, res, orow, p.stats_out != nullptr, row_sum, row_sumsq);
+            if (p.stats_out) {
+                // one exchange buffer is enough: a warp gets to write the next tile's sums only after that tile's second
+                // GEMM has finished, which takes an h_full arrival per chunk from the reader below
+                uint32_t const mine = red_base + (uint32_t)(((quarter * 4 + slab) * 32 + lane) * 8);
+                asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(mine), "f"(row_sum), "f"(row_sumsq) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+                if (slab == 0 && valid) {
+                    float sx = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4) {
+                        float a, b;
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(red_base + (uint32_t)(((quarter * 4 + w4) * 32 + lane) * 8)));
+                        sx += a;
+                        sq += b;
+                    }
+                    p.stats_out[row] = make_float2(sx, sq);
+                }
+            }
+        };
+        int prev_row = 0;
+        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++lt) {
+            int const row = tile * kBlockM + quarter * 32 + lane;
+            float rstd;
+            {
+                float const inv_k = 1.0f / (float)C, mean = pv_next.x * inv_k;
+                rstd = rsqrtf(fmaxf(fmaf(-mean, mean, pv_next.y * inv_k), 0.f) + p.ln_eps);
+                int const next_row = row + (int)gridDim.x * kBlockM;
+                if (next_row < p.M) pv_next = __ldg(p.ln_stats + next_row);
+            }
+            for (int h = 0; h < NH; ++h, ++u) {
+                int const sb = (int)(u & 1u), d = (int)(u & 3u);
+                // The previous tile is finished one chunk late: its last MMA2 and the residual loads are then hidden
+                // behind this chunk, and the MMA warp already has kMlpLead first-GEMM chunks of this tile in flight.
+                bool const finish_prev = h == 0 && lt > 0;
+                if (finish_prev) load_residual(prev_row);
                 mbar_wait(d1_full(d), (u >> 2) & 1u);
                 tc_fence_after();
                 uint32_t r[16];
                 tmem_ld16(tmem_d1 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * kMlpChunk + slab * 16), r);
+                float4 bq[4];  // this slab's folded bias (broadcast reads), under the TMEM load
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bq[i].x), "=f"(bq[i].y), "=f"(bq[i].z), "=f"(bq[i].w)
+                                 : "r"(bias_base + (uint32_t)((h * kMlpChunk + slab * 16 + 4 * i) * 4)));
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -809,32 +855,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(h_full(sb));
+                if (finish_prev) finish_tile(prev_row, lt - 1);
             }
-            // ---- second GEMM's accumulator: + bias + residual -> 16-bit -> global, row sums ----
-            mbar_wait(d2_full, (uint32_t)lt & 1u);
-            tc_fence_after();
-            uint32_t const taddr = tmem_d2 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s_first * 16);
-            act_t* const orow = valid ? p.out + (int64_t)row * C + s_first * 16 : nullptr;
-            float row_sum = 0.f, row_sumsq = 0.f;
-            if (s_cnt == 3) mlp_epilogue2<3>(taddr, d2_empty, lane, p.b2, s_first * 16, res, orow, p.stats_out != nullptr, row_sum, row_sumsq);
-            else mlp_epilogue2<2>(taddr, d2_empty, lane, p.b2, s_first * 16, res, orow, p.stats_out != nullptr, row_sum, row_sumsq);
-            if (p.stats_out) {
-                uint32_t const red = red_base + (uint32_t)((lt & 1) * 4096);
-                uint32_t const mine = red + (uint32_t)(((quarter * 4 + slab) * 32 + lane) * 8);
-                asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(mine), "f"(row_sum), "f"(row_sumsq) : "memory");
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
-                if (slab == 0 && valid) {
-                    float sx = 0.f, sq = 0.f;
-#pragma unroll
-                    for (int w4 = 0; w4 < 4; ++w4) {
-                        float a, b;
-                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)(((quarter * 4 + w4) * 32 + lane) * 8)));
-                        sx += a;
-                        sq += b;
-                    }
-                    p.stats_out[row] = make_float2(sx, sq);
-                }
-            }
+            prev_row = row;
+        }
+        if (lt > 0) {
+            load_residual(prev_row);
+            finish_tile(prev_row, lt - 1);
         }
     }
 
