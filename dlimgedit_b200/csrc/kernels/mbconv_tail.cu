@@ -196,22 +196,25 @@ mbconv_tail_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();  // A blocks of this half complete; the input buffer has been consumed by every thread
 
-        if (tid == 0) {
-            if (u + kInBufs < n_units) issue_load(u + kInBufs);  // refill the buffer just consumed
+        if (tid < 32) {  // converged warp + one elected lane: TMA refill and the 8 MMAs issue from uniform registers
             if (!w_ready) mbar_wait(bar_w, 0);
             tc_fence_after();
+            if (elect_one()) {
+                if (u + kInBufs < n_units) issue_load(u + kInBufs);  // refill the buffer just consumed
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                int const kb = 2 * half + j;
-                uint64_t const adesc = make_smem_desc(a_s + j * kABlockBytes);
-                uint64_t const bdesc = make_smem_desc(w_s + kb * kWBlockBytes);
+                for (int j = 0; j < 2; ++j) {
+                    int const kb = 2 * half + j;
+                    uint64_t const adesc = make_smem_desc(a_s + j * kABlockBytes);
+                    uint64_t const bdesc = make_smem_desc(w_s + kb * kWBlockBytes);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma<0>(tmem + (uint32_t)(acc * kCout), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                              (uint32_t)((kb | k) != 0));
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma<0>(tmem + (uint32_t)(acc * kCout), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                }
+                tc_commit(bar_afree);
+                if (half == 1) tc_commit(bar_acc0 + 8 * acc);
             }
-            tc_commit(bar_afree);
-            if (half == 1) tc_commit(bar_acc0 + 8 * acc);
+            __syncwarp();
         }
         w_ready = true;
 

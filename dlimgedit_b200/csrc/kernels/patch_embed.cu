@@ -294,18 +294,21 @@ patch_embed_kernel(ImageDesc const* __restrict__ imgs, PatchParams p, uint32_t c
         __syncthreads();
 
         // ---- P4: conv2 as 128 x 64 x 320 on the tensor core (asynchronous; collected in the next iteration) ----
-        if (tid == 0) {
+        if (tid < 32) {  // converged warp + one elected lane: the 20 MMAs issue back to back from uniform registers
             if (!w2_ready) mbar_wait(bar_w, 0);
             tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int kb = 0; kb < kKBlocks; ++kb) {
-                uint64_t const adesc = make_smem_desc(a_s + kb * kABlockBytes);
-                uint64_t const bdesc = make_smem_desc(w2_s + kb * kBBlockBytes);
+                for (int kb = 0; kb < kKBlocks; ++kb) {
+                    uint64_t const adesc = make_smem_desc(a_s + kb * kABlockBytes);
+                    uint64_t const bdesc = make_smem_desc(w2_s + kb * kBBlockBytes);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma<0>(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma<0>(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                }
+                tc_commit(bar_mma);
             }
-            tc_commit(bar_mma);
+            __syncwarp();
         }
         w2_ready = true;
         prev_tile = tile;
