@@ -258,22 +258,58 @@ __global__ void __launch_bounds__(256, Acc::kMinBlocks) dwconv3x3_kernel(act_t c
     }
 }
 
+// fp32 accumulators with the filter in shared memory ([tap][channel] floats): 72 fewer registers per thread than
+// DwAcc32, which is what lets three or four blocks of the latency-bound local_conv kernel share an SM.
+template <int kTX>
+struct DwAcc32S {
+    float const* w;  // shared memory, this thread's 8 channels of tap 0; taps are C floats apart
+    int C;
+    float acc[kTX][8];
+    __device__ __forceinline__ void init(float const* wsm, float const* __restrict__ bias, int C_, int c8) {
+        w = wsm + c8 * 8;
+        C = C_;
+        float4 const* b4 = reinterpret_cast<float4 const*>(bias + c8 * 8);
+        float4 const b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+#pragma unroll
+        for (int o = 0; o < kTX; ++o) {
+            acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+            acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+        }
+    }
+    __device__ __forceinline__ void tap(int o, int k, uint4 const& v) {
+        float f[8];
+        unpack8(v, f);
+        float4 const w0 = *reinterpret_cast<float4 const*>(w + k * C), w1 = *reinterpret_cast<float4 const*>(w + k * C + 4);
+        acc[o][0] = fmaf(f[0], w0.x, acc[o][0]); acc[o][1] = fmaf(f[1], w0.y, acc[o][1]);
+        acc[o][2] = fmaf(f[2], w0.z, acc[o][2]); acc[o][3] = fmaf(f[3], w0.w, acc[o][3]);
+        acc[o][4] = fmaf(f[4], w1.x, acc[o][4]); acc[o][5] = fmaf(f[5], w1.y, acc[o][5]);
+        acc[o][6] = fmaf(f[6], w1.z, acc[o][6]); acc[o][7] = fmaf(f[7], w1.w, acc[o][7]);
+    }
+    __device__ __forceinline__ uint4 result(int o, bool) { return pack8(acc[o]); }
+};
+
 // local_conv of a TinyViT block (stride 1, fp32 accumulation, no activation) that also leaves the LayerNorm row sums
-// of its output for the fc1 GEMM behind it (gemm.cuh, Epilogue::ln_parts = 1): a block holds kG whole groups of
-// 4 pixels x kC8 channel octets, every thread writes the (sum, sum of squares) of its 8 channels per pixel to shared
-// memory and kG * 4 threads add the kC8 partials of one pixel in a fixed order (reproducible, no atomics).
-template <int kC8, int kG>
-__global__ void __launch_bounds__(kC8 * kG) dwconv3x3_stats_kernel(act_t const* __restrict__ in, int H, int W, int xgroups,
+// of its output for the fc1 GEMM / fused MLP behind it: a block holds kG whole groups of 4 pixels x kC8 channel
+// octets, every thread writes the (sum, sum of squares) of its 8 channels per pixel to shared memory and kG * 4
+// threads add the kC8 partials of one pixel in a fixed order (reproducible, no atomics).  When a group's kC8 threads
+// sit inside one warp (kC8 = 16) the exchange needs a warp barrier only.
+template <int kC8, int kG, int kMinBlocks>
+__global__ void __launch_bounds__(kC8 * kG, kMinBlocks) dwconv3x3_stats_kernel(act_t const* __restrict__ in, int H, int W, int xgroups,
                                                                    float const* __restrict__ weight, float const* __restrict__ bias,
                                                                    act_t* __restrict__ out, float2* __restrict__ stats) {
-    constexpr int kTX = 4, kCols = kTX + 2;
+    constexpr int kTX = 4, kCols = kTX + 2, kC = kC8 * 8;
+    constexpr bool kWarpLocal = 32 % kC8 == 0;  // the kC8 threads of a group never straddle a warp
     __shared__ float2 part[kG][kTX][kC8];
+    __shared__ __align__(16) float wsm[9 * kC];
+    for (int i = threadIdx.x; i < 9 * kC / 4; i += kC8 * kG)
+        reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<float4 const*>(weight) + i);
+    __syncthreads();
     int const c8 = threadIdx.x % kC8, gl = threadIdx.x / kC8;
     int const xg = blockIdx.x * kG + gl;  // xgroups is a multiple of kG (checked on the host)
     int const oy = blockIdx.y, b = blockIdx.z;
     int const ox0 = xg * kTX, ix0 = ox0 - 1;
-    DwAcc32<kTX> acc;
-    acc.init(weight, bias, kC8 * 8, c8);
+    DwAcc32S<kTX> acc;
+    acc.init(wsm, bias, kC, c8);
     if (ix0 >= 0 && ix0 + kCols <= W) dwconv_rows<1, kTX, kC8, false>(in, H, W, b, oy, c8, ix0, acc);
     else dwconv_rows<1, kTX, kC8, true>(in, H, W, b, oy, c8, ix0, acc);
     int64_t const row0 = ((int64_t)b * H + oy) * W + ox0;
@@ -289,17 +325,31 @@ __global__ void __launch_bounds__(kC8 * kG) dwconv3x3_stats_kernel(act_t const* 
         part[gl][o][c8] = make_float2(s1, s2);
         orow[o * kC8] = acc.result(o, false);
     }
-    __syncthreads();
-    if (threadIdx.x < kG * kTX) {
-        int const g2 = threadIdx.x / kTX, o = threadIdx.x % kTX;
-        float s1 = 0.f, s2 = 0.f;
+    if (kWarpLocal) {
+        __syncwarp();
+        if (c8 < kTX) {  // lanes 0..3 of each group: one pixel each
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll 4
-        for (int k = 0; k < kC8; ++k) {
-            float2 const v = part[g2][o][k];
-            s1 += v.x;
-            s2 += v.y;
+            for (int k = 0; k < kC8; ++k) {
+                float2 const v = part[gl][c8][k];
+                s1 += v.x;
+                s2 += v.y;
+            }
+            stats[row0 + c8] = make_float2(s1, s2);
         }
-        stats[((int64_t)b * H + oy) * W + (blockIdx.x * kG + g2) * kTX + o] = make_float2(s1, s2);
+    } else {
+        __syncthreads();
+        if (threadIdx.x < kG * kTX) {
+            int const g2 = threadIdx.x / kTX, o = threadIdx.x % kTX;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < kC8; ++k) {
+                float2 const v = part[g2][o][k];
+                s1 += v.x;
+                s2 += v.y;
+            }
+            stats[((int64_t)b * H + oy) * W + (blockIdx.x * kG + g2) * kTX + o] = make_float2(s1, s2);
+        }
     }
 }
 
@@ -568,14 +618,14 @@ void dwconv3x3_stats(cudaStream_t s, act_t const* in, int batch, int H, int W, i
     int const xgroups = W / 4;
     DLIMG_ASSERT(W % 4 == 0);
     ProfScope prof(s, CAT_DWCONV, 2.0 * batch * H * W * C * 9, (double)batch * 2.0 * H * W * C * 2);
-#define DLIMG_DWS_CASE(CC, G)                                                                                             \
+#define DLIMG_DWS_CASE(CC, G, MB)                                                                                           \
     if (C == CC && xgroups % G == 0) {                                                                                    \
         dim3 const grid((unsigned)(xgroups / G), (unsigned)H, (unsigned)batch);                                           \
-        dwconv3x3_stats_kernel<CC / 8, G><<<grid, (CC / 8) * G, 0, s>>>(in, H, W, xgroups, weight, bias, out, stats);     \
+        dwconv3x3_stats_kernel<CC / 8, G, MB><<<grid, (CC / 8) * G, 0, s>>>(in, H, W, xgroups, weight, bias, out, stats); \
         KERNEL_CHECK();                                                                                                   \
         return;                                                                                                           \
     }
-    DLIMG_DWS_CASE(128, 16) DLIMG_DWS_CASE(160, 8) DLIMG_DWS_CASE(320, 4)  // 256 / 160 / 160 threads: 2-3 blocks per SM at 128 registers
+    DLIMG_DWS_CASE(128, 16, 3) DLIMG_DWS_CASE(160, 8, 5) DLIMG_DWS_CASE(320, 4, 5)  // 256 / 160 / 160 threads
 #undef DLIMG_DWS_CASE
     fail("dwconv3x3_stats: unsupported (channels, width) = (" + std::to_string(C) + ", " + std::to_string(W) + ")");
 }
