@@ -186,7 +186,7 @@ struct SlabCtx {
     int rows_valid;       // how many of the warp's 32 rows exist (M tail)
 };
 
-template <int kCnt, bool kStaged, int kAct, bool kLn>
+template <int kCnt, bool kStaged, int kAct, bool kLn, bool kRes = false>
 __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams const& ep, void* out, float& sum, float& sumsq) {
     uint32_t r[2][16];
     tmem_ld16(cx.taddr, r[0]);
@@ -207,9 +207,33 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
             if (kLn) ln_bias16(v, ep.bias, c, cx.rstd);
             else if (ep.bias) add_bias16(v, ep.bias, c);
+            uint32_t const dst = cx.stage_row + (uint32_t)(k * 32);
+            if (kRes) {
+                // the residual piece of this tile is already in the staging area (cp.async, whole row segments); this
+                // lane adds its row's 16 values in fp32 and puts the rounded sums back in the same place
+                uint4 rs[2];
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rs[0].x), "=r"(rs[0].y), "=r"(rs[0].z), "=r"(rs[0].w) : "r"(dst));
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rs[1].x), "=r"(rs[1].y), "=r"(rs[1].z), "=r"(rs[1].w) : "r"(dst + 16u));
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    act2_t const* h = reinterpret_cast<act2_t const*>(&rs[i]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float2 const f = act22f2(h[j]);
+                        v[8 * i + 2 * j] += f.x;
+                        v[8 * i + 2 * j + 1] += f.y;
+                    }
+                }
+                if (ep.stats_out) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        sum += v[i];
+                        sumsq = fmaf(v[i], v[i], sumsq);
+                    }
+                }
+            }
             uint4 x[2];
             activate_pack16(v, kAct, x);
-            uint32_t const dst = cx.stage_row + (uint32_t)(k * 32);
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x[0].x), "r"(x[0].y), "r"(x[0].z), "r"(x[0].w) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
         } else if (cx.orow >= 0) {
@@ -263,7 +287,7 @@ inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false) {
     SmemPlan p;
     // 16 epilogue warps x 32 rows x (64-column share of the tile + pad), see the epilogue
     p.staging_bytes = staged ? (int)round_up64((int64_t)kEpiWarps * 32 * ((((block_n >> 4) + 3) / 4) * 32 + kStagePad), 1024) : 0;
-    if (!staged && stats) p.staging_bytes = 8192;  // two buffers of 16 warps x 32 lanes x (sum, sum of squares)
+    if (stats) p.staging_bytes += 8192;  // two buffers of 16 warps x 32 lanes x (sum, sum of squares), behind the staging
     int const stage_bytes = kAStageBytes + block_n * kKBytes;
     int const fixed = 1024 /*align*/ + 1024 /*barriers, keeps the stages 1024-aligned*/ + p.staging_bytes;
     p.stages = (kSmemLimit - fixed) / stage_bytes;
@@ -274,7 +298,7 @@ inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false) {
 
 // kStaged kernels are additionally specialised on the activation (kAct) and on the folded LayerNorm (kLn), so the
 // slab loop carries no run-time branches; the direct kernels read both from EpiParams.
-template <int kTF32, bool kStaged, int kAct = ACT_NONE, bool kLn = false>
+template <int kTF32, bool kStaged, int kAct = ACT_NONE, bool kLn = false, bool kRes = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
                int K, int block_n, int num_stages, int staging_bytes, void* out, EpiParams ep) {
@@ -407,6 +431,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int const s_first = slab * (nslab / 4) + min(slab, nslab & 3);       // first slab
         uint32_t const pitch = (uint32_t)(((nslab + 3) / 4) * 32 + kStagePad);  // bytes per staged row
         uint32_t const my_stage = stage_out + (uint32_t)(quarter * 4 + slab) * 32u * pitch;
+        // kRes (staged kernels with a 16-bit residual): the warp's 32 x (s_cnt * 32 B) piece of the residual is copied
+        // into its staging area with cp.async as whole row segments -- one tile ahead, right after the staging area has
+        // been drained -- so neither the residual reads nor the output writes touch partial 128-byte lines.
+        auto prefetch_residual = [&](int tile) {
+            if (s_cnt == 0) return;
+            int const m0 = (tile / n_tiles) * kBlockM + quarter * 32;
+            int const n0 = (tile % n_tiles) * block_n + s_first * 16;
+            act_t const* seg = reinterpret_cast<act_t const*>(ep.residual) + (int64_t)m0 * ep.ldc + n0;
+            int const cpr = 2 * s_cnt, rows_it = 32 / cpr;  // 16-byte pieces per row, rows per instruction
+            int const row0 = lane / cpr, chunk = lane - row0 * cpr;
+            int const rows_valid = min(32, M - m0);
+            if (row0 < rows_it) {
+                for (int rr = row0; rr < rows_valid; rr += rows_it) {
+                    uint32_t const dst = my_stage + (uint32_t)rr * pitch + (uint32_t)chunk * 16u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(seg + (int64_t)rr * ep.ldc + chunk * 8) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (kRes && (int)blockIdx.x < total_tiles) prefetch_residual(blockIdx.x);
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int const acc = local & 1;
@@ -437,6 +481,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            if (kRes) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
             SlabCtx cx;
             cx.taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN + s_first * 16);
             cx.tempty = tempty_bar(acc);
@@ -452,19 +500,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             cx.rows_valid = M - (m0 + quarter * 32);
             float row_sum = 0.f, row_sumsq = 0.f;
             switch (s_cnt) {  // warp-uniform
-                case 4: epilogue_slabs<4, kStaged, kAct, kLn>(cx, ep, out, row_sum, row_sumsq); break;
-                case 3: epilogue_slabs<3, kStaged, kAct, kLn>(cx, ep, out, row_sum, row_sumsq); break;
-                case 2: epilogue_slabs<2, kStaged, kAct, kLn>(cx, ep, out, row_sum, row_sumsq); break;
-                case 1: epilogue_slabs<1, kStaged, kAct, kLn>(cx, ep, out, row_sum, row_sumsq); break;
+                case 4: epilogue_slabs<4, kStaged, kAct, kLn, kRes>(cx, ep, out, row_sum, row_sumsq); break;
+                case 3: epilogue_slabs<3, kStaged, kAct, kLn, kRes>(cx, ep, out, row_sum, row_sumsq); break;
+                case 2: epilogue_slabs<2, kStaged, kAct, kLn, kRes>(cx, ep, out, row_sum, row_sumsq); break;
+                case 1: epilogue_slabs<1, kStaged, kAct, kLn, kRes>(cx, ep, out, row_sum, row_sumsq); break;
                 default:  // narrow tiles (block_n < 64): this warp owns no slab
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(acc));
                     break;
             }
-            if (!kStaged && ep.stats_out) {
+            if (kRes && tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + (int)gridDim.x);
+            if ((!kStaged || kRes) && ep.stats_out) {
                 // row statistics of this tile: the four warps of a lane quarter hold pieces of the same 32 rows
-                uint32_t const red = stage_out + (uint32_t)((local & 1) * 4096);
+                uint32_t const red = stage_out + (uint32_t)(staging_bytes - 8192 + (local & 1) * 4096);
                 uint32_t const mine = red + (uint32_t)(((quarter * 4 + slab) * 32 + lane) * 8);
                 asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(mine), "f"(row_sum), "f"(row_sumsq) : "memory");
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
@@ -1046,18 +1095,21 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
     int const grid = tiles < num_sms ? tiles : num_sms;
     // plain 16-bit outputs go through the coalescing (staged) epilogue; residual / scatter / fp32 outputs store directly
     static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch
-    bool const staged = allow_staged && !tf32 && !ep.residual && !ep.row_map && !ep.out_f32 && block_n >= 64 &&
-                        (ep.act == ACT_NONE || ep.act == ACT_GELU);
+    static bool const allow_staged_res = !std::getenv("DLIMG_B200_GEMM_DIRECT_RESIDUAL");  // A/B switch
+    bool const res_ok = !ep.residual || (allow_staged_res && ep.act == ACT_NONE && !ep.ln_stats);
+    bool const staged = allow_staged && !tf32 && res_ok && !ep.row_map && !ep.out_f32 && block_n >= 64 &&
+                        (ep.act == ACT_NONE || ep.act == ACT_GELU) && (!ep.stats_out || ep.residual);
     if (ep.ln_stats && (!staged || !ep.bias))
         fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue) and a bias");
-    if (ep.stats_out && (staged || ep.act != ACT_NONE || ep.row_map || ep.out_f32 || block_n < 64))
-        fail("GEMM: row statistics are produced by the direct 16-bit epilogue without activation only");
+    if (ep.stats_out && (ep.act != ACT_NONE || ep.row_map || ep.out_f32 || block_n < 64))
+        fail("GEMM: row statistics are produced by the 16-bit epilogues without activation only");
     SmemPlan const sp = plan_smem(block_n, staged, ep.stats_out != nullptr);
     DLIMG_ASSERT(sp.stages >= 2);
     using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, void*, EpiParams);
     Kernel kernel;
     if (tf32) kernel = gemm_tc_kernel<1, false>;
     else if (!staged) kernel = gemm_tc_kernel<0, false>;
+    else if (ep.residual) kernel = gemm_tc_kernel<0, true, ACT_NONE, false, true>;
     else if (ep.ln_stats) kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, true> : gemm_tc_kernel<0, true, ACT_NONE, true>;
     else kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, false> : gemm_tc_kernel<0, true, ACT_NONE, false>;
     {
