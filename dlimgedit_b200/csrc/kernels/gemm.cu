@@ -587,10 +587,13 @@ inline MlpSmem plan_mlp(int C) {
     return m;
 }
 
-// fc2 accumulator slabs of one warp: + bias + residual (prefetched) -> 16-bit -> global, row sums
+// fc2 accumulator slabs of one warp: + bias + residual -> 16-bit, row sums.  The residual is the tile's own A operand,
+// still in shared memory (128B-swizzled K-major: row r, 16-byte piece j of k-block kb at kb * 16 KiB + r * 128 +
+// ((j ^ (r & 7)) << 4)); each lane reads its row's pieces, adds in fp32 and puts the rounded result back in place,
+// from where the warp then copies whole row segments to global memory.
 template <int kCnt>
 __device__ __forceinline__ void mlp_epilogue2(uint32_t taddr, uint32_t d2_empty, int lane, uint32_t bias_s, int col0,
-                                              uint4 const (&res)[3][2], act_t* orow, bool stats, float& sum, float& sumsq) {
+                                              uint32_t a_buf, int trow, bool stats, float& sum, float& sumsq) {
     uint32_t r[2][16];
     tmem_ld16(taddr, r[0]);
 #pragma unroll
@@ -603,6 +606,13 @@ __device__ __forceinline__ void mlp_epilogue2(uint32_t taddr, uint32_t d2_empty,
             __syncwarp();
             if (lane == 0) mbar_arrive(d2_empty);
         }
+        int const col = col0 + k * 16;
+        uint32_t const rowaddr = a_buf + (uint32_t)((col >> 6) * kAStageBytes + trow * 128);
+        uint32_t const j0 = (uint32_t)((col & 63) >> 3), sw = (uint32_t)(trow & 7);
+        uint32_t const p0 = rowaddr + ((j0 ^ sw) << 4), p1 = rowaddr + (((j0 + 1) ^ sw) << 4);
+        uint4 rs[2];
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rs[0].x), "=r"(rs[0].y), "=r"(rs[0].z), "=r"(rs[0].w) : "r"(p0));
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rs[1].x), "=r"(rs[1].y), "=r"(rs[1].z), "=r"(rs[1].w) : "r"(p1));
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
@@ -610,12 +620,12 @@ __device__ __forceinline__ void mlp_epilogue2(uint32_t taddr, uint32_t d2_empty,
         for (int i = 0; i < 4; ++i) {
             float4 b;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                         : "r"(bias_s + (uint32_t)((col0 + k * 16 + 4 * i) * 4)));
+                         : "r"(bias_s + (uint32_t)((col + 4 * i) * 4)));
             v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            act2_t const* h = reinterpret_cast<act2_t const*>(&res[k][i]);
+            act2_t const* h = reinterpret_cast<act2_t const*>(&rs[i]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float2 const f = act22f2(h[j]);
@@ -632,11 +642,8 @@ __device__ __forceinline__ void mlp_epilogue2(uint32_t taddr, uint32_t d2_empty,
         }
         uint4 x[2];
         activate_pack16(v, ACT_NONE, x);
-        if (orow) {
-            uint4* o4 = reinterpret_cast<uint4*>(orow + k * 16);
-            o4[0] = x[0];
-            o4[1] = x[1];
-        }
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(p0), "r"(x[0].x), "r"(x[0].y), "r"(x[0].z), "r"(x[0].w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(p1), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
     }
 }
 
@@ -680,7 +687,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_w1) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_w2) : "memory");
         for (int s = 0; s < 2; ++s) {
-            mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1);
+            mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1 + kEpiWarps);
             mbar_init(w2_full(s), 1); mbar_init(w2_empty(s), 1);
             mbar_init(h_full(s), kEpiWarps); mbar_init(h_empty(s), 1);
         }
@@ -814,29 +821,38 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
         uint32_t u = 0;  // chunk counter across tiles
         float2 pv_next = make_float2(0.f, 1.f);  // this lane's row sums, fetched one tile ahead
         if ((int)blockIdx.x * kBlockM + quarter * 32 + lane < p.M) pv_next = __ldg(p.ln_stats + (int)blockIdx.x * kBlockM + quarter * 32 + lane);
-        uint4 res[3][2] = {};
-        auto load_residual = [&](int row) {
-            if (row < p.M) {
-                uint4 const* r4 = reinterpret_cast<uint4 const*>(p.residual + (int64_t)row * C + s_first * 16);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (k < s_cnt) {
-                        res[k][0] = __ldg(r4 + 2 * k);
-                        res[k][1] = __ldg(r4 + 2 * k + 1);
-                    }
-                }
-            }
-        };
-        // second GEMM's accumulator of tile number `t` of this CTA: + bias + residual -> 16-bit -> global, row sums
+        // second GEMM's accumulator of tile number `t` of this CTA: + bias + residual -> 16-bit -> global, row sums.
+        // The A buffer of the tile doubles as the residual source and the staging area of the output, so it goes back
+        // to the TMA producer from here (a_empty: the MMA warp's commit + one arrival per epilogue warp).
         auto finish_tile = [&](int row, int t) {
             bool const valid = row < p.M;
+            uint32_t const a_buf = a_base + (uint32_t)((t & 1) * a_bytes);
+            int const trow = quarter * 32 + lane;
             mbar_wait(d2_full, (uint32_t)t & 1u);
             tc_fence_after();
             uint32_t const taddr = tmem_d2 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s_first * 16);
-            act_t* const orow = valid ? p.out + (int64_t)row * C + s_first * 16 : nullptr;
             float row_sum = 0.f, row_sumsq = 0.f;
-            if (s_cnt == 3) mlp_epilogue2<3>(taddr, d2_empty, lane, bias_base + 16u * (uint32_t)C, s_first * 16, res, orow, p.stats_out != nullptr, row_sum, row_sumsq);
-            else mlp_epilogue2<2>(taddr, d2_empty, lane, bias_base + 16u * (uint32_t)C, s_first * 16, res, orow, p.stats_out != nullptr, row_sum, row_sumsq);
+            if (s_cnt == 3) mlp_epilogue2<3>(taddr, d2_empty, lane, bias_base + 16u * (uint32_t)C, s_first * 16, a_buf, trow, p.stats_out != nullptr, row_sum, row_sumsq);
+            else mlp_epilogue2<2>(taddr, d2_empty, lane, bias_base + 16u * (uint32_t)C, s_first * 16, a_buf, trow, p.stats_out != nullptr, row_sum, row_sumsq);
+            __syncwarp();
+            {   // whole row segments of the warp's 32 x (s_cnt * 32 B) piece: shared memory -> global
+                int const cpr = 2 * s_cnt, rows_it = 32 / cpr;
+                int const row0 = lane / cpr, chunk = lane - row0 * cpr;
+                int const gc = s_first * 2 + chunk;  // 16-byte piece within the row
+                int const first_row = row - lane;     // global row of the warp's first row
+                if (row0 < rows_it) {
+                    for (int rr = row0; rr < 32 && first_row + rr < p.M; rr += rows_it) {
+                        int const tr = quarter * 32 + rr;
+                        uint32_t const src = a_buf + (uint32_t)((gc >> 3) * kAStageBytes + tr * 128) + ((uint32_t)((gc & 7) ^ (tr & 7)) << 4);
+                        uint4 x;
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(src));
+                        *reinterpret_cast<uint4*>(p.out + (int64_t)(first_row + rr) * C + gc * 8) = x;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses to A before the next TMA write
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_empty(t & 1));
             if (p.stats_out) {
                 // one exchange buffer is enough: a warp gets to write the next tile's sums only after that tile's second
                 // GEMM has finished, which takes an h_full arrival per chunk from the reader below
@@ -868,10 +884,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
             }
             for (int h = 0; h < NH; ++h, ++u) {
                 int const sb = (int)(u & 1u), d = (int)(u & 3u);
-                // The previous tile is finished one chunk late: its last MMA2 and the residual loads are then hidden
-                // behind this chunk, and the MMA warp already has kMlpLead first-GEMM chunks of this tile in flight.
+                // The previous tile is finished one chunk late: its last MMA2 is then hidden behind this chunk, and the
+                // MMA warp already has kMlpLead first-GEMM chunks of this tile in flight.
                 bool const finish_prev = h == 0 && lt > 0;
-                if (finish_prev) load_residual(prev_row);
                 mbar_wait(d1_full(d), (u >> 2) & 1u);
                 tc_fence_after();
                 uint32_t r[16];
@@ -908,10 +923,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
             }
             prev_row = row;
         }
-        if (lt > 0) {
-            load_residual(prev_row);
-            finish_tile(prev_row, lt - 1);
-        }
+        if (lt > 0) finish_tile(prev_row, lt - 1);
     }
 
     tc_fence_before();
