@@ -273,6 +273,14 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
     }
 }
 
+// Implicit-GEMM 3x3 convolution (stride 1, zero padding 1) over a 16-bit NHWC tensor: the A operand of k-block
+// (tap, channel block) of a tile of 128 consecutive pixels (128 / W whole image rows) is one 4D TMA box of the input
+// shifted by the tap, out-of-image elements zero-filled by TMA -- the im2col matrix never exists.  w == 0: plain GEMM.
+struct ConvParams {
+    int w = 0, h = 0;  // image width (divides 128) and height (multiple of 128 / w)
+    int cblocks = 0;   // channels / 64
+};
+
 // Shared-memory plan (all sizes known on the host): [barriers | staging (kStaged) | stages x (A 16 KiB, B block_n*128 B)].
 // The stage count is whatever fits (up to kMaxStages): narrow-N GEMMs get deep rings (9 stages at block_n 64), which
 // they need because a stage then carries only 24 KiB towards the ~70 KiB per SM that HBM latency x bandwidth asks for.
@@ -301,7 +309,7 @@ inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false) {
 template <int kTF32, bool kStaged, int kAct = ACT_NONE, bool kLn = false, bool kRes = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
-               int K, int block_n, int num_stages, int staging_bytes, void* out, EpiParams ep) {
+               int K, int block_n, int num_stages, int staging_bytes, void* out, EpiParams ep, ConvParams conv) {
     extern __shared__ uint8_t smem_raw[];
     uint32_t const smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint32_t const bar_base = smem_base;
@@ -361,10 +369,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int const m0 = (tile / n_tiles) * kBlockM;
                 int const n0 = (tile % n_tiles) * block_n;
+                int img = 0, y0 = 0;
+                if (conv.w > 0) {
+                    int const rows_pt = kBlockM / conv.w, tiles_per_img = conv.h / rows_pt, mt = tile / n_tiles;
+                    img = mt / tiles_per_img;
+                    y0 = (mt - img * tiles_per_img) * rows_pt;
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), tx_bytes);
-                    tma_load_2d(a_stage(stage), &tma_a, full_bar(stage), kb * elems_per_kb, m0);
+                    if (conv.w > 0) {
+                        int const tap = kb / conv.cblocks, cb = kb - tap * conv.cblocks, ky = tap / 3, kx = tap - ky * 3;
+                        tma_load_4d(a_stage(stage), &tma_a, full_bar(stage), cb * 64, kx - 1, y0 + ky - 1, img);
+                    } else {
+                        tma_load_2d(a_stage(stage), &tma_a, full_bar(stage), kb * elems_per_kb, m0);
+                    }
                     tma_load_2d(b_stage(stage), &tma_b, full_bar(stage), kb * elems_per_kb, n0);
                     if (++stage == num_stages) { stage = 0; phase ^= 1u; }
                 }
@@ -1069,8 +1088,10 @@ EpiParams to_params(Epilogue const& e, int N) {
 
 CUtensorMap make_tensor_map(Operand const& op, bool tf32, int box_rows) { return make_map(op, tf32, box_rows); }
 
-CUtensorMap make_tensor_map_nhwc(void const* ptr, int batch, int H, int W, int C, int box_c, int box_w, int box_h) {
+CUtensorMap make_tensor_map_nhwc(void const* ptr, int batch, int H, int W, int C, int box_c, int box_w, int box_h,
+                                 bool swizzle128) {
     CUtensorMap map;
+    DLIMG_ASSERT(!swizzle128 || box_c == 64);  // one 128-byte swizzle row per pixel
     DLIMG_ASSERT((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (C * 2) % 16 == 0 && box_c <= 256 && box_w <= 256 && box_h <= 256);
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
@@ -1078,7 +1099,8 @@ CUtensorMap make_tensor_map_nhwc(void const* ptr, int batch, int H, int W, int C
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode_fn()(&map, kActBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                              const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled (NHWC) failed with code " + std::to_string((int)r));
     return map;
 }
@@ -1089,8 +1111,29 @@ int pick_block_n(int N) {
     return 0;
 }
 
+namespace {
+struct ConvInput {
+    int batch, H, W, C;
+};
+void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, void* out, Epilogue const& epi,
+                 int num_sms, ConvInput const* ci);
+}  // namespace
+
 void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, void* out, Epilogue const& epi,
             int num_sms) {
+    launch_impl(stream, tf32, a, b, out, epi, num_sms, nullptr);
+}
+
+void launch_conv3x3(cudaStream_t stream, void const* in, int batch, int H, int W, int C, Operand const& b, void* out,
+                    Epilogue const& epi, int num_sms) {
+    DLIMG_ASSERT(W > 0 && kBlockM % W == 0 && H % (kBlockM / W) == 0 && C % 64 == 0 && b.cols == 9 * (int64_t)C);
+    ConvInput const ci{batch, H, W, C};
+    launch_impl(stream, false, Operand{in, (int64_t)batch * H * W, 9 * (int64_t)C, 0}, b, out, epi, num_sms, &ci);
+}
+
+namespace {
+void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, void* out, Epilogue const& epi,
+                 int num_sms, ConvInput const* ci) {
     int const M = (int)a.rows, N = (int)b.rows, K = (int)a.cols;
     DLIMG_ASSERT(a.cols == b.cols);
     DLIMG_ASSERT(M > 0 && N > 0 && K > 0);
@@ -1098,11 +1141,18 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
     if (block_n == 0) fail("GEMM: N must be a multiple of 16, got " + std::to_string(N));
     EpiParams ep = to_params(epi, N);
     DLIMG_ASSERT(ep.ldc % (ep.out_f32 ? 4 : 8) == 0);
-    CUtensorMap ma = make_map(a, tf32, kBlockM);
+    ConvParams conv;
+    if (ci) {
+        conv.w = ci->W;
+        conv.h = ci->H;
+        conv.cblocks = ci->C / 64;
+    }
+    CUtensorMap ma = ci ? make_tensor_map_nhwc(a.ptr, ci->batch, ci->H, ci->W, ci->C, 64, ci->W, kBlockM / ci->W, true)
+                        : make_map(a, tf32, kBlockM);
     CUtensorMap mb = make_map(b, tf32, block_n);
     int const tiles = ceil_div(M, kBlockM) * (N / block_n);
     ProfScope prof(stream, tf32 ? CAT_GEMM_TF32 : CAT_GEMM_BF16, 2.0 * M * N * K,
-                   (double)(tf32 ? 4 : 2) * ((double)M * K + (double)N * K) +
+                   (double)(tf32 ? 4 : 2) * ((double)M * (ci ? ci->C : K) + (double)N * K) +
                        (double)(ep.out_f32 ? 4 : 2) * M * N * (ep.residual ? 2.0 : 1.0));
     int const grid = tiles < num_sms ? tiles : num_sms;
     // plain 16-bit outputs go through the coalescing (staged) epilogue; residual / scatter / fp32 outputs store directly
@@ -1117,7 +1167,7 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
         fail("GEMM: row statistics are produced by the 16-bit epilogues without activation only");
     SmemPlan const sp = plan_smem(block_n, staged, ep.stats_out != nullptr);
     DLIMG_ASSERT(sp.stages >= 2);
-    using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, void*, EpiParams);
+    using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, void*, EpiParams, ConvParams);
     Kernel kernel;
     if (tf32) kernel = gemm_tc_kernel<1, false>;
     else if (!staged) kernel = gemm_tc_kernel<0, false>;
@@ -1133,9 +1183,10 @@ void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, 
             attr_done[(void const*)kernel] = true;
         }
     }
-    kernel<<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep);
+    kernel<<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep, conv);
     KERNEL_CHECK();
 }
+}  // namespace
 
 bool mlp_fused_supported(int C) {
 #if defined(DLIMG_B200_ACT_BF16)

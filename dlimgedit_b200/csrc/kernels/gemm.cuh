@@ -58,7 +58,9 @@ CUtensorMap make_tensor_map(Operand const& op, bool tf32, int box_rows);
 
 // TMA descriptor of a 16-bit NHWC activation tensor for halo-tile loads: box = box_h x box_w pixels x box_c channels
 // of one image, no swizzle, out-of-bounds elements (the convolution's zero padding) read as zero.
-CUtensorMap make_tensor_map_nhwc(void const* ptr, int batch, int H, int W, int C, int box_c, int box_w, int box_h);
+// swizzle128 (box_c == 64): every pixel is one 128-byte row of a SWIZZLE_128B K-major operand tile (implicit GEMM).
+CUtensorMap make_tensor_map_nhwc(void const* ptr, int batch, int H, int W, int C, int box_c, int box_w, int box_h,
+                                 bool swizzle128 = false);
 
 // Picks the widest legal tile width (multiple of 16, <= 256) that divides N.
 int pick_block_n(int N);
@@ -66,6 +68,12 @@ int pick_block_n(int N);
 // Encodes the two tensor maps and launches.  tf32 != 0 selects fp32 operands with kind::tf32.
 void launch(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, void* out, Epilogue const& epi,
             int num_sms);
+
+// 3x3 convolution (stride 1, zero padding 1) of a 16-bit NHWC tensor as an implicit GEMM: in (batch, H, W, C), b (N, 9 * C)
+// with K index = tap * C + channel (tap = ky * 3 + kx), out (batch * H * W, N).  128 % W == 0, H % (128 / W) == 0,
+// C % 64 == 0.  Same epilogues as launch().
+void launch_conv3x3(cudaStream_t stream, void const* in, int batch, int H, int W, int C, Operand const& b, void* out,
+                    Epilogue const& epi, int num_sms);
 
 // Fused TinyViT MLP for C = 128 / 160: out = x + fc2(GELU(fc1(LN(x)))) with the hidden activation kept in TMEM / shared
 // memory.  x (rows, C) 16-bit (also the residual; out may alias x), w1 (4C, C) with the LayerNorm folded in (gamma-scaled,

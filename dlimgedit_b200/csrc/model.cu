@@ -505,8 +505,17 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
     enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln1.g.get(), enc_.neck_ln1.b.get(), 1e-6f,
                         ws.big[1].get(), false);
     tap_act(s, tap, "neck1", ws.big[1].get(), (size_t)B * 4096 * 256);
-    enc::im2col3x3(s, ws.big[1].get(), batch, 64, 64, 256, 1, ws.col.get());
-    gemm16(s, ws.col.get(), B * 4096, enc_.neck2, ws.big[0].get(), ACT_NONE, nullptr);
+    static bool const neck_im2col = kActBf16 || std::getenv("DLIMG_B200_NECK_IM2COL") != nullptr;  // A/B switch
+    if (neck_im2col) {
+        enc::im2col3x3(s, ws.big[1].get(), batch, 64, 64, 256, 1, ws.col.get());
+        gemm16(s, ws.col.get(), B * 4096, enc_.neck2, ws.big[0].get(), ACT_NONE, nullptr);
+    } else {  // implicit GEMM: shifted 4D TMA boxes of the NHWC activation are the A operand
+        gemm::Epilogue e;
+        e.bias = enc_.neck2.b.get();
+        e.ldc = enc_.neck2.n;
+        gemm::launch_conv3x3(s, ws.big[1].get(), batch, 64, 64, 256, gemm::Operand{enc_.neck2.w.get(), enc_.neck2.n, enc_.neck2.k, enc_.neck2.k},
+                             ws.big[0].get(), e, num_sms_);
+    }
     enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f,
                         emb_out, true);
     if (tap && tap->name && std::strcmp(tap->name, "neck") == 0) {
