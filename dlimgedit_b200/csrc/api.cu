@@ -278,6 +278,21 @@ dlimg_Result dbg_window_attention_simt(void* stream, void const* qkv, int window
     });
 }
 
+dlimg_Result dbg_conv3x3(void* stream, void const* in, int batch, int H, int W, int C, void const* weight, float const* bias, int N,
+                         void* out) {
+    return try_([=] {
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+        gemm::Epilogue e;
+        e.bias = bias;
+        e.ldc = N;
+        gemm::launch_conv3x3(static_cast<cudaStream_t>(stream), in, batch, H, W, C, gemm::Operand{weight, N, 9 * (int64_t)C, 9 * (int64_t)C},
+                             out, e, prop.multiProcessorCount);
+    });
+}
+
 dlimg_Result dbg_mlp_fused(void* stream, void const* x, int rows, int C, void const* w1, float const* b1, float const* ln_sums,
                            void const* w2, float const* b2, void* out, float* stats_out) {
     return try_([=] {
@@ -357,6 +372,7 @@ DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void) {
     debug_.window_attention_simt = dbg_window_attention_simt;
     debug_.layernorm_stats = dbg_layernorm_stats;
     debug_.mlp_fused = dbg_mlp_fused;
+    debug_.conv3x3 = dbg_conv3x3;
     return &debug_;
 }
 

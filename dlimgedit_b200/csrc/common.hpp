@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace dlimg {
 
@@ -75,4 +76,30 @@ inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::m
         ::dlimg::count_launch();                                                                     \
         CUDA_CHECK(cudaGetLastError());                                                              \
     } while (0)
+
+// Programmatic dependent launch: a kernel launched through launch_pdl() may start (prologue: barrier / TMEM setup,
+// constant staging) while the previous kernel in the stream is still draining; it must execute pdl_wait() before it
+// touches anything the previous kernel reads or writes, and calls pdl_trigger() to let its own successor do the same.
+// Works in stream capture (the graph gets programmatic edges).  DLIMG_B200_PDL_MASK (bit per kernel family below)
+// selects which kernels are launched that way (A/B switch; 0 = none).
+enum PdlFamily : int { PDL_GEMM = 0, PDL_ATTENTION, PDL_LOCAL_CONV, PDL_MBCONV, PDL_PATCH_EMBED, PDL_DWCONV, PDL_ROWS };
+bool pdl_enabled(int family);
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(int family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled(family) ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 } // namespace dlimg

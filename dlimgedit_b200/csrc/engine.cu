@@ -11,6 +11,13 @@
 namespace dlimg {
 
 std::atomic<uint64_t> g_kernel_launches{0};
+bool pdl_enabled(int family) {
+    static unsigned const mask = [] {
+        char const* e = std::getenv("DLIMG_B200_PDL_MASK");
+        return e ? (unsigned)std::strtoul(e, nullptr, 0) : 0u;  // measured: no gain inside the CUDA graph (profiles/r01f)
+    }();
+    return (mask >> family) & 1u;
+}
 std::atomic<uint64_t> g_h2d_bytes{0};
 std::atomic<uint64_t> g_d2h_bytes{0};
 

@@ -239,6 +239,8 @@ template <int kStride, int kTX, int kC8, typename Acc, typename WeightT>
 __global__ void __launch_bounds__(256, Acc::kMinBlocks) dwconv3x3_kernel(act_t const* __restrict__ in, int H, int W, int Ho, int Wo, int xgroups,
                                                         WeightT const* __restrict__ weight, float const* __restrict__ bias,
                                                         int gelu, act_t* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     int const t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= xgroups * kC8) return;
     int const c8 = t % kC8, xg = t / kC8;
@@ -303,6 +305,8 @@ __global__ void __launch_bounds__(kC8 * kG, kMinBlocks) dwconv3x3_stats_kernel(a
     __shared__ __align__(16) float wsm[9 * kC];
     for (int i = threadIdx.x; i < 9 * kC / 4; i += kC8 * kG)
         reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<float4 const*>(weight) + i);
+    pdl_wait();  // the filter is a constant; in / out / stats belong to the neighbouring kernels
+    pdl_trigger();
     __syncthreads();
     int const c8 = threadIdx.x % kC8, gl = threadIdx.x / kC8;
     int const xg = blockIdx.x * kG + gl;  // xgroups is a multiple of kG (checked on the host)
@@ -361,6 +365,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(act_t const* __rest
                                                              float const* __restrict__ gamma,
                                                              float const* __restrict__ beta, float eps,
                                                              void* __restrict__ out, int out_f32) {
+    pdl_wait();
+    pdl_trigger();
     int const row = blockIdx.x * 8 + (threadIdx.x >> 5);
     int const lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -422,6 +428,8 @@ constexpr int kStatChunks = 2;  // 16-byte chunks per lane per row: C <= 512
 
 __global__ void __launch_bounds__(256) layernorm_stats_kernel(act_t const* __restrict__ in, int rows, int C8, float eps,
                                                               float2* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     int const warp = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     int const row0 = warp * kStatRows;
     if (row0 >= rows) return;
@@ -535,6 +543,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32) window_attention_kernel(act_t
 
 // ---------------------------------------------------------------------------------------------
 __global__ void tokens_to_nchw_kernel(float const* __restrict__ in, int tokens, int C, float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float tile[32][33];
     int const b = blockIdx.z;
     int const t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -589,12 +599,12 @@ void launch_dwconv(cudaStream_t s, dim3 grid, act_t const* in, int H, int W, int
 #if !defined(DLIMG_B200_ACT_BF16)
     static bool const acc32 = std::getenv("DLIMG_B200_DW_ACC32") != nullptr;  // A/B switch for parity experiments
     if (weight16 && !acc32) {
-        dwconv3x3_kernel<kStride, kTX, kC8, DwAccH2<kTX>, act_t><<<grid, 256, 0, s>>>(in, H, W, Ho, Wo, xgroups, weight16, bias, gelu ? 1 : 0, out);
+        launch_pdl(PDL_DWCONV, dwconv3x3_kernel<kStride, kTX, kC8, DwAccH2<kTX>, act_t>, grid, dim3(256), 0, s, in, H, W, Ho, Wo, xgroups, weight16, bias, gelu ? 1 : 0, out);
         return;
     }
 #endif
     (void)weight16;
-    dwconv3x3_kernel<kStride, kTX, kC8, DwAcc32<kTX>, float><<<grid, 256, 0, s>>>(in, H, W, Ho, Wo, xgroups, weight, bias, gelu ? 1 : 0, out);
+    launch_pdl(PDL_DWCONV, dwconv3x3_kernel<kStride, kTX, kC8, DwAcc32<kTX>, float>, grid, dim3(256), 0, s, in, H, W, Ho, Wo, xgroups, weight, bias, gelu ? 1 : 0, out);
 }
 }  // namespace
 
@@ -621,7 +631,7 @@ void dwconv3x3_stats(cudaStream_t s, act_t const* in, int batch, int H, int W, i
 #define DLIMG_DWS_CASE(CC, G, MB)                                                                                           \
     if (C == CC && xgroups % G == 0) {                                                                                    \
         dim3 const grid((unsigned)(xgroups / G), (unsigned)H, (unsigned)batch);                                           \
-        dwconv3x3_stats_kernel<CC / 8, G, MB><<<grid, (CC / 8) * G, 0, s>>>(in, H, W, xgroups, weight, bias, out, stats); \
+        launch_pdl(PDL_LOCAL_CONV, dwconv3x3_stats_kernel<CC / 8, G, MB>, grid, dim3((CC / 8) * G), 0, s, in, H, W, xgroups, weight, bias, out, stats); \
         KERNEL_CHECK();                                                                                                   \
         return;                                                                                                           \
     }
@@ -634,14 +644,14 @@ void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const*
                     float const* beta, float eps, void* out, bool out_f32) {
     DLIMG_ASSERT(C % 2 == 0 && C <= kLnMaxPairs * 64);
     ProfScope prof(s, CAT_LAYERNORM, 0, (double)rows * C * (2 + (out_f32 ? 4 : 2)));
-    layernorm_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(in, rows, C, src_row, gamma, beta, eps, out, out_f32 ? 1 : 0);
+    launch_pdl(PDL_ROWS, layernorm_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, s, in, rows, C, src_row, gamma, beta, eps, out, out_f32 ? 1 : 0);
     KERNEL_CHECK();
 }
 
 void layernorm_stats(cudaStream_t s, act_t const* in, int rows, int C, float eps, float2* out) {
     DLIMG_ASSERT(C % 8 == 0 && C / 8 <= 32 * kStatChunks);
     ProfScope prof(s, CAT_LAYERNORM, 0, (double)rows * (C * 2 + 8));
-    layernorm_stats_kernel<<<ceil_div(rows, 8 * kStatRows), 256, 0, s>>>(in, rows, C / 8, eps, out);
+    launch_pdl(PDL_ROWS, layernorm_stats_kernel, dim3(ceil_div(rows, 8 * kStatRows)), dim3(256), 0, s, in, rows, C / 8, eps, out);
     KERNEL_CHECK();
 }
 
@@ -661,7 +671,7 @@ void window_attention_simt(cudaStream_t s, act_t const* qkv, int windows, int n,
 void tokens_to_nchw(cudaStream_t s, float const* in, int batch, int tokens, int C, float* out) {
     ProfScope prof(s, CAT_OTHER);
     dim3 grid(ceil_div(tokens, 32), ceil_div(C, 32), batch), block(32, 8);
-    tokens_to_nchw_kernel<<<grid, block, 0, s>>>(in, tokens, C, out);
+    launch_pdl(PDL_ROWS, tokens_to_nchw_kernel, grid, block, 0, s, in, tokens, C, out);
     KERNEL_CHECK();
 }
 

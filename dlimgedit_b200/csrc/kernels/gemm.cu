@@ -358,6 +358,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();     // everything above is independent of the previous kernel in the stream
+    pdl_trigger();  // the next kernel may run its own prologue as soon as SMs drain
     uint32_t const tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
@@ -729,6 +731,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();     // barriers, TMEM and the bias vectors above do not depend on the previous kernel in the stream
+    pdl_trigger();
     uint32_t const tmem_base = *tmem_slot_ptr;
     uint32_t const tmem_d2 = tmem_base;           // columns [0, C)
     uint32_t const tmem_d1 = tmem_base + 256u;    // four buffers of 64 columns
@@ -1183,7 +1187,8 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
             attr_done[(void const*)kernel] = true;
         }
     }
-    kernel<<<grid, kNumThreads, sp.total_bytes, stream>>>(ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out, ep, conv);
+    launch_pdl(PDL_GEMM, kernel, dim3(grid), dim3(kNumThreads), (size_t)sp.total_bytes, stream, ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out,
+               ep, conv);
     KERNEL_CHECK();
 }
 }  // namespace
@@ -1221,7 +1226,8 @@ void launch_mlp_fused(cudaStream_t stream, void const* x, int64_t rows, int C, v
     std::call_once(once, [] { CUDA_CHECK(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)); });
     int const tiles = ceil_div(M, kBlockM);
     int const grid = tiles < num_sms ? tiles : num_sms;
-    mlp_fused_kernel<<<grid, kNumThreads, sp.total, stream>>>(mx, m1, m2, p, sp.kb1, sp.a_bytes, sp.w1_bytes, sp.w2_bytes, sp.w1_ring_log);
+    launch_pdl(PDL_GEMM, mlp_fused_kernel, dim3(grid), dim3(kNumThreads), (size_t)sp.total, stream, mx, m1, m2, p, sp.kb1, sp.a_bytes, sp.w1_bytes,
+               sp.w2_bytes, sp.w1_ring_log);
     KERNEL_CHECK();
 }
 

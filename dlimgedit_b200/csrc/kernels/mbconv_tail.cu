@@ -74,6 +74,8 @@ mbconv_tail_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();  // barriers, TMEM and the depthwise filter above do not depend on the previous kernel in the stream
+    pdl_trigger();
     uint32_t const tmem = *reinterpret_cast<uint32_t const*>(gen + kSmemBar + 64);
 
     int const my_tiles = tiles > (int)blockIdx.x ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -259,7 +261,7 @@ void mbconv_tail(cudaStream_t s, CUtensorMap const& expanded_map, int batch, act
         attr_set = true;
     }
     int const grid = tiles < num_sms ? tiles : num_sms;
-    mbconv_tail_kernel<<<grid, kThreads, kSmemBytes, s>>>(expanded_map, w3_map, dw_w16, dw_b, b3, shortcut, out, tiles);
+    launch_pdl(PDL_MBCONV, mbconv_tail_kernel, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, s, expanded_map, w3_map, dw_w16, dw_b, b3, shortcut, out, tiles);
     KERNEL_CHECK();
 #endif
 }

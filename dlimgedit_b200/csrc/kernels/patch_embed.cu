@@ -99,6 +99,8 @@ patch_embed_kernel(ImageDesc const* __restrict__ imgs, PatchParams p, uint32_t c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();  // first kernel of an encoder pass: its output buffer may still be read by the previous pass
+    pdl_trigger();
     uint32_t const tmem = *reinterpret_cast<uint32_t const*>(gen + kSmemBar + 16);
     if (tid == 0) {  // conv2 weights: 5 k-blocks of (64 x 64) halves, resident for the whole kernel
         mbar_expect_tx(bar_w, kKBlocks * kBBlockBytes);
@@ -368,8 +370,8 @@ void patch_embed(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h,
         attr_set = true;
     }
     int const grid = p.tiles < num_sms ? p.tiles : num_sms;
-    if (c1_debug) patch_embed_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(imgs, p, w1_frag, b1, w2_map, b2, out, c1_debug);
-    else patch_embed_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(imgs, p, w1_frag, b1, w2_map, b2, out, nullptr);
+    if (c1_debug) launch_pdl(PDL_PATCH_EMBED, patch_embed_kernel<true>, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, s, imgs, p, w1_frag, b1, w2_map, b2, out, c1_debug);
+    else launch_pdl(PDL_PATCH_EMBED, patch_embed_kernel<false>, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, s, imgs, p, w1_frag, b1, w2_map, b2, out, (act_t*)nullptr);
     KERNEL_CHECK();
 #endif
 }

@@ -185,6 +185,8 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
         uint4* t = reinterpret_cast<uint4*>(smem + C::kSmemBias);
         for (int i = tid; i < 2 * C::kTileBytes / 16; i += C::kThreads) t[i] = make_uint4(0, 0, 0, 0);
     }
+    pdl_wait();  // the bias table is a constant; qkv / out belong to the neighbouring kernels
+    pdl_trigger();
     __syncthreads();
 
     // Token gather: a thread always moves the same 16-byte piece (`part`) of a token row and walks over tokens with a
@@ -309,7 +311,8 @@ void launch_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int 
     int const items = batch * nw * nw * n_groups;
     int grid = (num_sms * C::kMinBlocks / n_groups) * n_groups;
     if (grid > items) grid = items;
-    window_attention_kernel2<kWS, kHG><<<grid, C::kThreads, C::kSmemBytes, s>>>(qkv, batch, res, heads, pad_qkv, bias_frag, out);
+    launch_pdl(PDL_ATTENTION, window_attention_kernel2<kWS, kHG>, dim3(grid), dim3(C::kThreads), (size_t)C::kSmemBytes, s, qkv, batch, res, heads, pad_qkv,
+               bias_frag, out);
     KERNEL_CHECK();
 }
 

@@ -46,6 +46,11 @@ typedef struct dlimg_b200_Debug {
      * stats_out (optional, rows x 2): the same sums of the output rows. */
     dlimg_Result (*mlp_fused)(void* stream, void const* x, int rows, int C, void const* w1, float const* b1,
                               float const* ln_sums, void const* w2, float const* b2, void* out, float* stats_out);
+    /* 3x3 convolution (stride 1, zero padding 1) as an implicit GEMM: in (batch, H, W, C) 16-bit NHWC, weight (N, 9 * C)
+     * 16-bit with K index = (ky * 3 + kx) * C + channel, bias (N) fp32, out (batch * H * W, N) 16-bit.
+     * 128 % W == 0, H % (128 / W) == 0, C % 64 == 0, N % 16 == 0. */
+    dlimg_Result (*conv3x3)(void* stream, void const* in, int batch, int H, int W, int C, void const* weight,
+                            float const* bias, int N, void* out);
 } dlimg_b200_Debug;
 
 DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void);

@@ -203,3 +203,21 @@ def test_fused_mlp(M, C):
     assert r == 0, dl.api().last_error()
     torch.cuda.synchronize()
     assert torch.equal(xi, out)
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 64, 64, 256, 256), (3, 8, 32, 64, 48), (1, 6, 128, 128, 160)])
+def test_conv3x3_implicit_gemm(B, H, W, C, N):
+    """3x3 convolution with zero padding as an implicit GEMM (4D TMA boxes shifted by the tap, out-of-image elements
+    zero-filled by TMA) against torch.nn.functional.conv2d in fp32 on the same 16-bit inputs."""
+    import dlimgedit_b200 as dl
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + C)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(act_dtype())
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) / (9 * C) ** 0.5).to(act_dtype())
+    b = 0.3 * torch.randn(N, device="cuda", generator=g)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
+    wk = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()  # K index = (ky * 3 + kx) * C + c
+    out = torch.zeros(B * H * W, N, device="cuda", dtype=act_dtype())
+    r = dl.debug().conv3x3(None, x.data_ptr(), B, H, W, C, wk.data_ptr(), b.data_ptr(), N, out.data_ptr())
+    assert r == 0, dl.api().last_error()
+    torch.cuda.synchronize()
+    assert torch.allclose(out.float().view(B, H, W, N), ref, atol=2e-2, rtol=1e-2), float((out.float().view(B, H, W, N) - ref).abs().max())
