@@ -66,6 +66,28 @@ __device__ __forceinline__ void ln_bias16(float (&v)[16], float const* bias, int
     }
 }
 
+// The same two with the bias vector staged in shared memory (broadcast reads; the global loads above cost the staged
+// epilogues ~10 % of their time in exposed L1 latency, profiles/r01f).
+__device__ __forceinline__ void add_bias16_s(float (&v)[16], uint32_t bias_s, int col) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 b;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_s + (uint32_t)((col + 4 * i) * 4)));
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+}
+__device__ __forceinline__ void ln_bias16_s(float (&v)[16], uint32_t bias_s, int col, float rstd) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 b;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_s + (uint32_t)((col + 4 * i) * 4)));
+        v[4 * i + 0] = fmaf(v[4 * i + 0], rstd, b.x);
+        v[4 * i + 1] = fmaf(v[4 * i + 1], rstd, b.y);
+        v[4 * i + 2] = fmaf(v[4 * i + 2], rstd, b.z);
+        v[4 * i + 3] = fmaf(v[4 * i + 3], rstd, b.w);
+    }
+}
+
 // activation + conversion of 16 fp32 values to 16-bit storage (two 16-byte vectors)
 __device__ __forceinline__ void activate_pack16(float (&v)[16], int act, uint4 (&x)[2]) {
     act2_t* h = reinterpret_cast<act2_t*>(x);
@@ -184,6 +206,7 @@ struct SlabCtx {
     act_t* out_seg;       // output address of (first row of the warp's 32, first column of its range) (kStaged)
     int64_t ldc;
     int rows_valid;       // how many of the warp's 32 rows exist (M tail)
+    uint32_t bias_s;      // shared-memory copy of the bias vector (kStaged; 0 = read it from global memory)
 };
 
 template <int kCnt, bool kStaged, int kAct, bool kLn, bool kRes = false>
@@ -205,8 +228,8 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
-            if (kLn) ln_bias16(v, ep.bias, c, cx.rstd);
-            else if (ep.bias) add_bias16(v, ep.bias, c);
+            if (kLn) ln_bias16_s(v, cx.bias_s, c, cx.rstd);  // staged kernels always hold the bias vector (or zeros)
+            else add_bias16_s(v, cx.bias_s, c);
             uint32_t const dst = cx.stage_row + (uint32_t)(k * 32);
             if (kRes) {
                 // the residual piece of this tile is already in the staging area (cp.async, whole row segments); this
@@ -291,11 +314,12 @@ constexpr int kSmemLimit = 227 * 1024;
 struct SmemPlan {
     int stages, staging_bytes, total_bytes;
 };
-inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false) {
+inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false, int bias_bytes = 0) {
     SmemPlan p;
     // 16 epilogue warps x 32 rows x (64-column share of the tile + pad), see the epilogue
     p.staging_bytes = staged ? (int)round_up64((int64_t)kEpiWarps * 32 * ((((block_n >> 4) + 3) / 4) * 32 + kStagePad), 1024) : 0;
     if (stats) p.staging_bytes += 8192;  // two buffers of 16 warps x 32 lanes x (sum, sum of squares), behind the staging
+    p.staging_bytes += bias_bytes;       // the bias vector, behind both
     int const stage_bytes = kAStageBytes + block_n * kKBytes;
     int const fixed = 1024 /*align*/ + 1024 /*barriers, keeps the stages 1024-aligned*/ + p.staging_bytes;
     p.stages = (kSmemLimit - fixed) / stage_bytes;
@@ -309,7 +333,7 @@ inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false) {
 template <int kTF32, bool kStaged, int kAct = ACT_NONE, bool kLn = false, bool kRes = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
-               int K, int block_n, int num_stages, int staging_bytes, void* out, EpiParams ep, ConvParams conv) {
+               int K, int block_n, int num_stages, int staging_bytes, int bias_bytes, void* out, EpiParams ep, ConvParams conv) {
     extern __shared__ uint8_t smem_raw[];
     uint32_t const smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint32_t const bar_base = smem_base;
@@ -354,6 +378,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    uint32_t const bias_s = bias_bytes ? stage_out + (uint32_t)(staging_bytes - bias_bytes) : 0u;
+    if (bias_bytes) {  // weights: independent of the previous kernel
+        for (int i = threadIdx.x; i < N; i += kNumThreads)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * (uint32_t)i), "f"(ep.bias ? __ldg(ep.bias + i) : 0.f) : "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -519,6 +548,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             cx.out_seg = reinterpret_cast<act_t*>(out) + (int64_t)(m0 + quarter * 32) * ep.ldc + n0 + s_first * 16;
             cx.ldc = ep.ldc;
             cx.rows_valid = M - (m0 + quarter * 32);
+            cx.bias_s = bias_s;
             float row_sum = 0.f, row_sumsq = 0.f;
             switch (s_cnt) {  // warp-uniform
                 case 4: epilogue_slabs<4, kStaged, kAct, kLn, kRes>(cx, ep, out, row_sum, row_sumsq); break;
@@ -534,7 +564,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (kRes && tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + (int)gridDim.x);
             if ((!kStaged || kRes) && ep.stats_out) {
                 // row statistics of this tile: the four warps of a lane quarter hold pieces of the same 32 rows
-                uint32_t const red = stage_out + (uint32_t)(staging_bytes - 8192 + (local & 1) * 4096);
+                uint32_t const red = stage_out + (uint32_t)(staging_bytes - bias_bytes - 8192 + (local & 1) * 4096);
                 uint32_t const mine = red + (uint32_t)(((quarter * 4 + slab) * 32 + lane) * 8);
                 asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(mine), "f"(row_sum), "f"(row_sumsq) : "memory");
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
@@ -1164,14 +1194,15 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     static bool const allow_staged_res = !std::getenv("DLIMG_B200_GEMM_DIRECT_RESIDUAL");  // A/B switch
     bool const res_ok = !ep.residual || (allow_staged_res && ep.act == ACT_NONE && !ep.ln_stats);
     bool const staged = allow_staged && !tf32 && res_ok && !ep.row_map && !ep.out_f32 && block_n >= 64 &&
-                        (ep.act == ACT_NONE || ep.act == ACT_GELU) && (!ep.stats_out || ep.residual);
+                        (ep.act == ACT_NONE || ep.act == ACT_GELU) && (!ep.stats_out || ep.residual) && N <= 2048;
     if (ep.ln_stats && (!staged || !ep.bias))
         fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue) and a bias");
     if (ep.stats_out && (ep.act != ACT_NONE || ep.row_map || ep.out_f32 || block_n < 64))
         fail("GEMM: row statistics are produced by the 16-bit epilogues without activation only");
-    SmemPlan const sp = plan_smem(block_n, staged, ep.stats_out != nullptr);
+    int const bias_bytes = staged ? (int)round_up64((int64_t)N * 4, 1024) : 0;
+    SmemPlan const sp = plan_smem(block_n, staged, ep.stats_out != nullptr, bias_bytes);
     DLIMG_ASSERT(sp.stages >= 2);
-    using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, void*, EpiParams, ConvParams);
+    using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, int, void*, EpiParams, ConvParams);
     Kernel kernel;
     if (tf32) kernel = gemm_tc_kernel<1, false>;
     else if (!staged) kernel = gemm_tc_kernel<0, false>;
@@ -1187,8 +1218,8 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
             attr_done[(void const*)kernel] = true;
         }
     }
-    launch_pdl(PDL_GEMM, kernel, dim3(grid), dim3(kNumThreads), (size_t)sp.total_bytes, stream, ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, out,
-               ep, conv);
+    launch_pdl(PDL_GEMM, kernel, dim3(grid), dim3(kNumThreads), (size_t)sp.total_bytes, stream, ma, mb, M, N, K, block_n, sp.stages, sp.staging_bytes, bias_bytes,
+               out, ep, conv);
     KERNEL_CHECK();
 }
 }  // namespace
