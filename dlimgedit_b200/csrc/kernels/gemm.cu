@@ -501,6 +501,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         if (kRes && (int)blockIdx.x < total_tiles) prefetch_residual(blockIdx.x);
+        // folded LayerNorm: (mean, rstd) of this lane's row (ln_parts == 0) or its (sum, sum of squares), the partial
+        // sums of the producing kernel added in a fixed order
+        auto load_ln = [&](int tile) {
+            int const row = (tile / n_tiles) * kBlockM + quarter * 32 + lane;
+            float2 r = make_float2(0.f, 1.f);
+            if (row < M) {
+                if (ep.ln_parts == 0) {
+                    r = __ldg(ep.ln_stats + row);
+                } else {
+                    float sx = 0.f, sq = 0.f;
+                    for (int pp = 0; pp < ep.ln_parts; ++pp) {
+                        float2 const pv = __ldg(ep.ln_stats + (int64_t)row * ep.ln_parts + pp);
+                        sx += pv.x;
+                        sq += pv.y;
+                    }
+                    r = make_float2(sx, sq);
+                }
+            }
+            return r;
+        };
+        float2 ln_next = make_float2(0.f, 1.f);
+        if (kStaged && kLn && (int)blockIdx.x < total_tiles) ln_next = load_ln(blockIdx.x);
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int const acc = local & 1;
@@ -513,21 +535,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 int const row = m0 + quarter * 32 + lane;
                 if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
             } else if (kLn) {
-                int const row = m0 + quarter * 32 + lane;
-                if (row < M) {
-                    if (ep.ln_parts == 0) {
-                        rstd = __ldg(ep.ln_stats + row).y;
-                    } else {  // partial sums from the producing GEMM's epilogue, fixed order
-                        float sx = 0.f, sq = 0.f;
-                        for (int pp = 0; pp < ep.ln_parts; ++pp) {
-                            float2 const pv = __ldg(ep.ln_stats + (int64_t)row * ep.ln_parts + pp);
-                            sx += pv.x;
-                            sq += pv.y;
-                        }
-                        float const inv_k = 1.0f / (float)K, mean = sx * inv_k;
-                        rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv_k), 0.f) + ep.ln_eps);
-                    }
+                // the row statistics were fetched one tile ahead (their latency used to sit in front of every tile)
+                if (ep.ln_parts == 0) {
+                    rstd = ln_next.y;
+                } else {
+                    float const inv_k = 1.0f / (float)K, mean = ln_next.x * inv_k;
+                    rstd = rsqrtf(fmaxf(fmaf(-mean, mean, ln_next.y * inv_k), 0.f) + ep.ln_eps);
                 }
+                if (tile + (int)gridDim.x < total_tiles) ln_next = load_ln(tile + (int)gridDim.x);
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
