@@ -231,7 +231,7 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             if (kLn) ln_bias16_s(v, cx.bias_s, c, cx.rstd);  // staged kernels always hold the bias vector (or zeros)
             else add_bias16_s(v, cx.bias_s, c);
             uint32_t const dst = cx.stage_row + (uint32_t)(k * 32);
-            if (kRes) {
+            if (kRes && ep.residual) {
                 // the residual piece of this tile is already in the staging area (cp.async, whole row segments); this
                 // lane adds its row's 16 values in fp32 and puts the rounded sums back in the same place
                 uint4 rs[2];
@@ -247,12 +247,12 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
                         v[8 * i + 2 * j + 1] += f.y;
                     }
                 }
-                if (ep.stats_out) {
+            }
+            if (kRes && ep.stats_out) {  // LayerNorm row sums of what this GEMM writes (fp32 values, fixed order)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        sum += v[i];
-                        sumsq = fmaf(v[i], v[i], sumsq);
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    sum += v[i];
+                    sumsq = fmaf(v[i], v[i], sumsq);
                 }
             }
             uint4 x[2];
@@ -485,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // into its staging area with cp.async as whole row segments -- one tile ahead, right after the staging area has
         // been drained -- so neither the residual reads nor the output writes touch partial 128-byte lines.
         auto prefetch_residual = [&](int tile) {
-            if (s_cnt == 0) return;
+            if (s_cnt == 0 || !ep.residual) return;  // (the kernel also serves plain GEMMs that only want row sums)
             int const m0 = (tile / n_tiles) * kBlockM + quarter * 32;
             int const n0 = (tile % n_tiles) * block_n + s_first * 16;
             act_t const* seg = reinterpret_cast<act_t const*>(ep.residual) + (int64_t)m0 * ep.ldc + n0;
@@ -1209,7 +1209,7 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     static bool const allow_staged_res = !std::getenv("DLIMG_B200_GEMM_DIRECT_RESIDUAL");  // A/B switch
     bool const res_ok = !ep.residual || (allow_staged_res && ep.act == ACT_NONE && !ep.ln_stats);
     bool const staged = allow_staged && !tf32 && res_ok && !ep.row_map && !ep.out_f32 && block_n >= 64 &&
-                        (ep.act == ACT_NONE || ep.act == ACT_GELU) && (!ep.stats_out || ep.residual) && N <= 2048;
+                        (ep.act == ACT_NONE || ep.act == ACT_GELU) && (!ep.stats_out || (ep.act == ACT_NONE && !ep.ln_stats)) && N <= 2048;
     if (ep.ln_stats && (!staged || !ep.bias))
         fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue) and a bias");
     if (ep.stats_out && (ep.act != ACT_NONE || ep.row_map || ep.out_f32 || block_n < 64))
@@ -1221,7 +1221,7 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     Kernel kernel;
     if (tf32) kernel = gemm_tc_kernel<1, false>;
     else if (!staged) kernel = gemm_tc_kernel<0, false>;
-    else if (ep.residual) kernel = gemm_tc_kernel<0, true, ACT_NONE, false, true>;
+    else if (ep.residual || ep.stats_out) kernel = gemm_tc_kernel<0, true, ACT_NONE, false, true>;
     else if (ep.ln_stats) kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, true> : gemm_tc_kernel<0, true, ACT_NONE, true>;
     else kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, false> : gemm_tc_kernel<0, true, ACT_NONE, false>;
     {

@@ -441,13 +441,17 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         tap_act(s, tap, i == 0 ? "mb0" : "mb1", x, (size_t)B * 65536 * 64);
     }
 
+    static bool const merge_stats = !kActBf16 && std::getenv("DLIMG_B200_LN_STATS_KERNEL") == nullptr;  // A/B switch
+    // conv3 of a PatchMerging block also leaves the LayerNorm row sums of its output for the qkv GEMM of the stage's
+    // first block (same form as the fc2 / fused-MLP epilogues of the later blocks)
     auto merge = [&](MergeW const& m, int res, char const* name) {
         int const out_res = m.stride == 2 ? res / 2 : res;
         int const dout = m.conv1.n;
         gemm16(s, x, B * res * res, m.conv1, ws.big[0].get(), ACT_GELU, nullptr);
         enc::dwconv3x3(s, ws.big[0].get(), batch, res, res, dout, m.stride, m.conv2.w.get(), m.conv2.w16.get(), m.conv2.b.get(),
                        true, ws.big[1].get());
-        gemm16(s, ws.big[1].get(), B * out_res * out_res, m.conv3, y, ACT_NONE, nullptr);
+        gemm16(s, ws.big[1].get(), B * out_res * out_res, m.conv3, y, ACT_NONE, nullptr, nullptr, false, 0,
+               merge_stats ? ws.stats_parts.get() : nullptr);
         std::swap(x, y);
         tap_act(s, tap, name, x, (size_t)B * out_res * out_res * dout);
     };
@@ -465,8 +469,8 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
             std::string const tn = "s" + std::to_string(st) + "b" + std::to_string(i);
             // attention branch on the un-partitioned grid: LN statistics, QKV with the LayerNorm folded into the GEMM,
             // windowed attention (does the partition / zero padding / un-partition itself), proj + residual in place
-            // (block 0: a statistics kernel; later blocks: the previous block's fc2 epilogue already wrote the row sums)
-            if (i == 0) {
+            // (the row sums come from the epilogue of whatever produced x: PatchMerging conv3, fc2 or the fused MLP)
+            if (i == 0 && !merge_stats) {
                 enc::layernorm_stats(s, x, rows, C, 1e-5f, stats);
                 gemm16(s, x, rows, b.qkv, ws.big[1].get(), ACT_NONE, nullptr, stats);
             } else {
