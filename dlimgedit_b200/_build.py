@@ -28,6 +28,7 @@ SOURCES = [
     "kernels/window_attention.cu",
     "kernels/patch_embed.cu",
     "kernels/mbconv_tail.cu",
+    "kernels/local_conv.cu",
     "kernels/decoder_kernels.cu",
     "kernels/t2i_attention.cu",
     "kernels/prepost_kernels.cu",

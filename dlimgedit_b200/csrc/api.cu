@@ -278,6 +278,25 @@ dlimg_Result dbg_window_attention_simt(void* stream, void const* qkv, int window
     });
 }
 
+dlimg_Result dbg_local_conv(void* stream, void const* in, int batch, int H, int W, int C, float const* weight, float const* bias,
+                            void* out, float* stats, int tma) {
+    return try_([=] {
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+        auto const s = static_cast<cudaStream_t>(stream);
+        if (tma) {
+            if (!enc::local_conv_tma_supported(H, W, C)) fail("local_conv: unsupported shape for the TMA kernel");
+            enc::local_conv_tma(s, static_cast<act_t const*>(in), batch, H, W, C, weight, bias, static_cast<act_t*>(out),
+                                reinterpret_cast<float2*>(stats), prop.multiProcessorCount);
+        } else {
+            enc::dwconv3x3_stats(s, static_cast<act_t const*>(in), batch, H, W, C, weight, bias, static_cast<act_t*>(out),
+                                 reinterpret_cast<float2*>(stats));
+        }
+    });
+}
+
 dlimg_Result dbg_conv3x3(void* stream, void const* in, int batch, int H, int W, int C, void const* weight, float const* bias, int N,
                          void* out) {
     return try_([=] {
@@ -373,6 +392,7 @@ DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void) {
     debug_.layernorm_stats = dbg_layernorm_stats;
     debug_.mlp_fused = dbg_mlp_fused;
     debug_.conv3x3 = dbg_conv3x3;
+    debug_.local_conv = dbg_local_conv;
     return &debug_;
 }
 

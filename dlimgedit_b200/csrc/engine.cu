@@ -241,7 +241,7 @@ uint8_t* EnvironmentImpl::prepare_input(dlimg_ImageView const& view, uint8_t con
 }
 
 void EnvironmentImpl::encode_chunk(enc::ImageDesc const* host_descs, int batch, prepost::LongestSide const& size, int channels,
-                                   float* emb_out, Tap* tap) {
+                                   float* emb_out, Tap* tap, float* emb_nchw_out) {
     cudaStream_t const s = stream();
     if (!descs_) descs_.allocate((size_t)max_batch_);
     size_t const bytes = sizeof(enc::ImageDesc) * (size_t)batch;
@@ -251,12 +251,13 @@ void EnvironmentImpl::encode_chunk(enc::ImageDesc const* host_descs, int batch, 
     SamModel& m = model();
     EncoderWorkspace& ws = encoder_ws();
     if (tap || !use_graphs_ || Profiler::get().enabled()) {  // eager launches (debug taps, per-kernel timing)
-        m.encode(s, ws, descs_.get(), batch, size.w, size.h, channels, emb_out, tap);
+        m.encode(s, ws, descs_.get(), batch, size.w, size.h, channels, emb_out, tap, emb_nchw_out);
         return;
     }
     // The ~130 launches of one encoder pass are captured once per (batch, extent, channel order) into a CUDA
     // graph: every pointer it uses (workspace, weights, descriptor table, tensor maps) is stable, only the
-    // descriptor *contents* (uploaded above) and the destination of the final embedding copy change per call.
+    // descriptor *contents* (uploaded above) and the destination of the embedding change per call -- so the graph ends
+    // in front of the final LayerNorm2d, which is launched behind it straight into the caller's store (both layouts).
     auto const key = std::make_tuple(batch, size.w, size.h, channels);
     auto it = encode_graphs_.find(key);
     if (it == encode_graphs_.end()) {
@@ -264,7 +265,7 @@ void EnvironmentImpl::encode_chunk(enc::ImageDesc const* host_descs, int batch, 
         uint64_t const launches_before = g_kernel_launches.load();
         CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         try {
-            m.encode(s, ws, descs_.get(), batch, size.w, size.h, channels, ws.emb.get(), nullptr);
+            m.encode(s, ws, descs_.get(), batch, size.w, size.h, channels, nullptr, nullptr, nullptr, /*finish=*/false);
         } catch (...) {
             cudaStreamEndCapture(s, &graph);
             if (graph) cudaGraphDestroy(graph);
@@ -283,8 +284,7 @@ void EnvironmentImpl::encode_chunk(enc::ImageDesc const* host_descs, int batch, 
     }
     CUDA_CHECK(cudaGraphLaunch(it->second.exec, s));
     count_launch(it->second.kernels);
-    CUDA_CHECK(cudaMemcpyAsync(emb_out, ws.emb.get(), sizeof(float) * (size_t)batch * dec::kImgTokens * kEmbedDim,
-                               cudaMemcpyDeviceToDevice, s));
+    m.neck_finish(s, ws, batch, emb_out, emb_nchw_out);
 }
 
 void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, bool on_device, SegmentationImpl** out) {
@@ -338,8 +338,7 @@ void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, boo
             if (on_device) prepare_input(v, v.pixels, v.stride, size, i, descs[(size_t)i]);
             else prepare_input(v, input_px_[set].get() + (size_t)i * input_slot_bytes_, (int)row_bytes, size, i, descs[(size_t)i]);
         }
-        encode_chunk(descs.data(), B, size, views[0].channels, store->floats(), nullptr);
-        enc::tokens_to_nchw(s, store->floats(), B, dec::kImgTokens, kEmbedDim, store->floats() + (size_t)B * emb_floats);
+        encode_chunk(descs.data(), B, size, views[0].channels, store->floats(), nullptr, store->floats() + (size_t)B * emb_floats);
         CUDA_CHECK(cudaEventRecord(store->ready(), s));
         if (!on_device) {
             CUDA_CHECK(cudaEventRecord(input_free_[set], s));

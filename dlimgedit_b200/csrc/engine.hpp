@@ -103,7 +103,7 @@ class EnvironmentImpl {
     prepost::ResizeDeviceTables resize_tables(int in_w, int in_h, int out_w, int out_h);
     DeviceAxisPlan const& axis_plan(int in_size, int out_size);
     void encode_chunk(enc::ImageDesc const* host_descs, int batch, prepost::LongestSide const& size, int channels,
-                      float* emb_out, Tap* tap);
+                      float* emb_out, Tap* tap, float* emb_nchw_out = nullptr);
     uint8_t* prepare_input(dlimg_ImageView const& view, uint8_t const* dev_pixels, int dev_stride,
                            prepost::LongestSide const& size, int slot, enc::ImageDesc& desc);
 

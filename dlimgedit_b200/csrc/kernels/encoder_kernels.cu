@@ -421,6 +421,65 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(act_t const* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Final LayerNorm2d of the neck (C = 256) writing the embedding in both layouts the engine keeps: token-major fp32 (the
+// decoder's input) and NCHW fp32 (what get_embedding returns).  A block normalises 32 consecutive tokens of one image
+// (same arithmetic as layernorm_rows_kernel), writes the rows, and transposes through shared memory so that every
+// channel's 32 tokens leave as one 128-byte segment.
+__global__ void __launch_bounds__(256) layernorm256_tokens_nchw_kernel(act_t const* __restrict__ in, int tokens,
+                                                                       float const* __restrict__ gamma, float const* __restrict__ beta,
+                                                                       float eps, float* __restrict__ out_tok, float* __restrict__ out_nchw) {
+    constexpr int C = 256;
+    __shared__ float tile[C][33];
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int const b = blockIdx.y, t0 = blockIdx.x * 32;
+    float2 g[4], bt[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        g[i] = reinterpret_cast<float2 const*>(gamma)[lane + 32 * i];
+        bt[i] = reinterpret_cast<float2 const*>(beta)[lane + 32 * i];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int const tl = warp * 4 + r;
+        int64_t const row = (int64_t)b * tokens + t0 + tl;
+        act2_t const* p = reinterpret_cast<act2_t const*>(in + row * C);
+        float2 x[4];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            x[i] = act22f2(p[lane + 32 * i]);
+            sum += x[i].x + x[i].y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        float const mean = sum / (float)C;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float const a = x[i].x - mean, c = x[i].y - mean;
+            var += a * a + c * c;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        float const rstd = rsqrtf(var / (float)C + eps);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int const idx = lane + 32 * i;
+            float2 y;
+            y.x = (x[i].x - mean) * rstd * g[i].x + bt[i].x;
+            y.y = (x[i].y - mean) * rstd * g[i].y + bt[i].y;
+            reinterpret_cast<float2*>(out_tok + row * C)[idx] = y;
+            tile[2 * idx][tl] = y.x;
+            tile[2 * idx + 1][tl] = y.y;
+        }
+    }
+    __syncthreads();
+    float* const dst = out_nchw + (int64_t)b * C * tokens + t0 + lane;
+#pragma unroll 8
+    for (int c = warp * 32; c < warp * 32 + 32; ++c) dst[(int64_t)c * tokens] = tile[c][lane];
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row statistics for the LayerNorms folded into GEMM epilogues: one warp per kStatRows rows, 16-byte loads, all
 // rows' loads issued before the first reduction, two-pass (mean, then centred variance) in registers.
 constexpr int kStatRows = 4;
@@ -645,6 +704,14 @@ void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const*
     DLIMG_ASSERT(C % 2 == 0 && C <= kLnMaxPairs * 64);
     ProfScope prof(s, CAT_LAYERNORM, 0, (double)rows * C * (2 + (out_f32 ? 4 : 2)));
     launch_pdl(PDL_ROWS, layernorm_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, s, in, rows, C, src_row, gamma, beta, eps, out, out_f32 ? 1 : 0);
+    KERNEL_CHECK();
+}
+
+void layernorm256_tokens_nchw(cudaStream_t s, act_t const* in, int batch, int tokens, float const* gamma, float const* beta,
+                              float eps, float* out_tok, float* out_nchw) {
+    DLIMG_ASSERT(tokens % 32 == 0);
+    ProfScope prof(s, CAT_LAYERNORM, 0, (double)batch * tokens * 256 * (2 + 4 + 4));
+    layernorm256_tokens_nchw_kernel<<<dim3((unsigned)(tokens / 32), (unsigned)batch), 256, 0, s>>>(in, tokens, gamma, beta, eps, out_tok, out_nchw);
     KERNEL_CHECK();
 }
 

@@ -55,6 +55,19 @@ void dwconv3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, 
 void dwconv3x3_stats(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, float const* weight, float const* bias,
                      act_t* out, float2* stats);
 
+// The same operation from TMA-loaded halo tiles (local_conv.cu): persistent CTAs, 8 x 16-pixel tiles, C = 128 / 160 / 320
+// (320 as two channel parts: stats then holds local_conv_parts(C) partial sums per pixel, [rows][parts]).  Output
+// bit-identical to dwconv3x3_stats.  H % 8 == 0, W % 16 == 0.
+bool local_conv_tma_supported(int H, int W, int C);
+int local_conv_parts(int C);
+void local_conv_tma(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, float const* weight, float const* bias,
+                    act_t* out, float2* stats, int num_sms);
+
+// LayerNorm over C = 256 channels of (batch, tokens, 256) 16-bit rows, written twice as fp32: token-major (batch, tokens,
+// 256) and NCHW (batch, 256, tokens).  tokens % 32 == 0.
+void layernorm256_tokens_nchw(cudaStream_t s, act_t const* in, int batch, int tokens, float const* gamma, float const* beta,
+                              float eps, float* out_tok, float* out_nchw);
+
 // Row LayerNorm over C channels.  src_row (optional, length `rows`): gather index into `in`, -1 = the row
 // is window padding and the output is LN(0) = beta.  Output bf16 or fp32.
 void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const* src_row, float const* gamma,

@@ -1,0 +1,218 @@
+// local_conv.cu -- the depthwise 3x3 `local_conv` of a TinyViT block (stride 1, zero padding 1, BN folded, no activation)
+// from TMA-loaded halo tiles, with the LayerNorm row sums of its output for the MLP behind it.
+//
+// The register-tiled form (dwconv3x3_stats_kernel, encoder_kernels.cu) issues 18 global 16-byte loads per 4 x 8
+// outputs and waits for them at 17-24 resident warps per SM: 2.7-3.4x off the HBM time of its 2 x C bytes per pixel
+// (profiles/r01f).  Here a persistent CTA walks over units = (8 x 16-pixel tile, channel part of <= 160 channels):
+//   TMA   4-D box (channels, 18, 10, 1) at (part * Cu, x0 - 1, y0 - 1, image), three units in flight; out-of-image
+//         elements arrive as zeros = the convolution's padding, so the arithmetic has no edge cases
+//   DW    thread = (channel octet, run of 4 pixels, tile row): 18 LDS.128 of activations, the fp32 filter from shared
+//         memory, fp32 accumulation in exactly the order of the register-tiled kernel (bit-identical output)
+//   OUT   16-byte stores (a pixel's octets are adjacent lanes), per-pixel (sum, sum of squares) through a
+//         double-buffered shared-memory exchange, added in a fixed order by one thread per pixel after the tile's
+//         only CTA barrier (which also hands the drained input buffer back to the TMA thread)
+// C = 320 runs as two channel parts of 160; the consumer adds the two partial row sums (gemm Epilogue::ln_parts = 2).
+#include "encoder_kernels.cuh"
+#include "gemm.cuh"
+#include "tcgen05.cuh"
+
+#include "../profiler.hpp"
+
+namespace dlimg {
+namespace enc {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kTH = 8, kTW = 16, kHH = kTH + 2, kHW = kTW + 2;  // tile and halo
+constexpr int kInBufs = 3;
+
+template <int kC8>
+struct LcCfg {
+    static constexpr int kCu = kC8 * 8;                       // channels per unit
+    static constexpr int kThreads = kC8 * 4 * kTH;            // (octet, 4-pixel run, row)
+    static constexpr int kInBytes = kHH * kHW * kCu * 2;      // one halo tile
+    static constexpr int kPartBytes = kTH * kTW * kC8 * 8;    // (sum, sum of squares) per (pixel, octet)
+    static constexpr int kSmemIn = 0;
+    static constexpr int kSmemPart = kSmemIn + kInBufs * kInBytes;
+    static constexpr int kSmemBar = kSmemPart + 2 * kPartBytes;
+    static constexpr int kSmemW = kSmemBar + 64;              // filter [9][C] fp32 + bias [C], C known at run time
+};
+
+__device__ __forceinline__ void unpack8h(uint4 const& v, float (&f)[8]) {
+    act2_t const* h = reinterpret_cast<act2_t const*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 const t = act22f2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+template <int kC8>
+__global__ void __launch_bounds__(LcCfg<kC8>::kThreads, 1)
+local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __restrict__ weight, float const* __restrict__ bias,
+                  act_t* __restrict__ out, float2* __restrict__ stats, int H, int W, int C, int units) {
+    using L = LcCfg<kC8>;
+    extern __shared__ uint8_t smem_raw[];
+    uint32_t const base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
+    uint32_t const in_s = base + L::kSmemIn, bar = base + L::kSmemBar;
+    float2* const part = reinterpret_cast<float2*>(gen + L::kSmemPart);
+    float* const wsm = reinterpret_cast<float*>(gen + L::kSmemW);  // [9][C], then bias [C]
+    int const tid = threadIdx.x;
+    int const parts = C / L::kCu, tiles_x = W / kTW, tiles_per_img = tiles_x * (H / kTH);
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
+        for (int i = 0; i < kInBufs; ++i) mbar_init(bar + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 9 * C; i += L::kThreads) wsm[i] = __ldg(weight + i);
+    for (int i = tid; i < C; i += L::kThreads) wsm[9 * C + i] = __ldg(bias + i);
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+
+    int const my_units = units > (int)blockIdx.x ? (units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // unit -> (image, tile origin, channel part); the parts of a tile are adjacent units
+    auto locate = [&](int u, int& b, int& oy0, int& ox0, int& pt) {
+        int const unit = (int)blockIdx.x + u * (int)gridDim.x;
+        int const tile = unit / parts;
+        pt = unit - tile * parts;
+        b = tile / tiles_per_img;
+        int const tr = tile - b * tiles_per_img;
+        oy0 = (tr / tiles_x) * kTH;
+        ox0 = (tr % tiles_x) * kTW;
+    };
+    auto issue_load = [&](int u) {
+        int b, oy0, ox0, pt;
+        locate(u, b, oy0, ox0, pt);
+        int const buf = u % kInBufs;
+        mbar_expect_tx(bar + 8 * buf, (uint32_t)L::kInBytes);
+        tma_load_4d(in_s + buf * L::kInBytes, &in_map, bar + 8 * buf, pt * L::kCu, ox0 - 1, oy0 - 1, b);
+    };
+    if (tid == 0)
+        for (int u = 0; u < kInBufs && u < my_units; ++u) issue_load(u);
+
+    int const c8 = tid % kC8, xg = (tid / kC8) & 3, ty = tid / (kC8 * 4);
+    uint32_t in_phase = 0;
+    for (int u = 0; u < my_units; ++u) {
+        int b, oy0, ox0, pt;
+        locate(u, b, oy0, ox0, pt);
+        int const buf = u % kInBufs;
+        float const* const w = wsm + pt * L::kCu + c8 * 8;
+        float acc[4][8];
+        {
+            float4 const b0 = *reinterpret_cast<float4 const*>(w + 9 * C), b1 = *reinterpret_cast<float4 const*>(w + 9 * C + 4);
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+                acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+            }
+        }
+        mbar_wait(bar + 8 * buf, (in_phase >> buf) & 1u);
+        in_phase ^= 1u << buf;
+        uint32_t const tile_in = in_s + buf * L::kInBytes + (uint32_t)(((ty * kHW + xg * 4) * L::kCu + c8 * 8) * 2);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            uint4 v[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(v[c].x), "=r"(v[c].y), "=r"(v[c].z), "=r"(v[c].w)
+                             : "r"(tile_in + (uint32_t)(((ky * kHW + c) * L::kCu) * 2)));
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                float f[8];
+                unpack8h(v[c], f);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    int const o = c - kx;
+                    if (o < 0 || o >= 4) continue;
+                    float const* wk = w + (ky * 3 + kx) * C;
+                    float4 const w0 = *reinterpret_cast<float4 const*>(wk), w1 = *reinterpret_cast<float4 const*>(wk + 4);
+                    acc[o][0] = fmaf(f[0], w0.x, acc[o][0]); acc[o][1] = fmaf(f[1], w0.y, acc[o][1]);
+                    acc[o][2] = fmaf(f[2], w0.z, acc[o][2]); acc[o][3] = fmaf(f[3], w0.w, acc[o][3]);
+                    acc[o][4] = fmaf(f[4], w1.x, acc[o][4]); acc[o][5] = fmaf(f[5], w1.y, acc[o][5]);
+                    acc[o][6] = fmaf(f[6], w1.z, acc[o][6]); acc[o][7] = fmaf(f[7], w1.w, acc[o][7]);
+                }
+            }
+        }
+        // output + per-(pixel, octet) partial row sums
+        int const oy = oy0 + ty, ox = ox0 + xg * 4;
+        int64_t const row0 = ((int64_t)b * H + oy) * W + ox;
+        uint4* const orow = reinterpret_cast<uint4*>(out + row0 * C + pt * L::kCu) + c8;
+        float2* const mypart = part + (u & 1) * (kTH * kTW * kC8) + ((ty * kTW + xg * 4) * kC8 + c8);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s1 += acc[o][i];
+                s2 = fmaf(acc[o][i], acc[o][i], s2);
+            }
+            mypart[o * kC8] = make_float2(s1, s2);
+            uint4 ov;
+            act2_t* oh = reinterpret_cast<act2_t*>(&ov);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) oh[i] = f22act2(acc[o][2 * i], acc[o][2 * i + 1]);
+            orow[(size_t)o * (C / 8)] = ov;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the buffer before its next TMA write
+        __syncthreads();  // the input buffer is drained and the partial sums of this unit are visible
+        if (tid == 0 && u + kInBufs < my_units) issue_load(u + kInBufs);
+        if (tid < kTH * kTW) {  // one thread per pixel: fixed-order sum over the unit's octets
+            float2 const* p = part + (u & 1) * (kTH * kTW * kC8) + tid * kC8;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < kC8; ++k) {
+                float2 const v = p[k];
+                s1 += v.x;
+                s2 += v.y;
+            }
+            int const py = tid / kTW, px = tid - py * kTW;
+            stats[(((int64_t)b * H + oy0 + py) * W + ox0 + px) * parts + pt] = make_float2(s1, s2);
+        }
+        // (the other exchange buffer is written by the next unit; this one again only after the next unit's barrier,
+        //  by which time the readers above are done with it)
+    }
+}
+
+template <int kC8>
+void launch_local_conv(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, float const* weight, float const* bias,
+                       act_t* out, float2* stats, int num_sms) {
+    using L = LcCfg<kC8>;
+    int const smem = L::kSmemW + 10 * C * 4 + 128;
+    DLIMG_ASSERT(smem <= 227 * 1024);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(local_conv_kernel<kC8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    CUtensorMap const map = gemm::make_tensor_map_nhwc(in, batch, H, W, C, L::kCu, kHW, kHH);
+    int const units = batch * (H / kTH) * (W / kTW) * (C / L::kCu);
+    int const grid = units < num_sms ? units : num_sms;
+    launch_pdl(PDL_LOCAL_CONV, local_conv_kernel<kC8>, dim3(grid), dim3(L::kThreads), (size_t)smem, s, map, weight, bias, out, stats, H, W, C, units);
+    KERNEL_CHECK();
+}
+
+}  // namespace
+
+int local_conv_parts(int C) { return C == 320 ? 2 : 1; }
+
+bool local_conv_tma_supported(int H, int W, int C) {
+    return H % kTH == 0 && W % kTW == 0 && (C == 128 || C == 160 || C == 320);
+}
+
+void local_conv_tma(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, float const* weight, float const* bias,
+                    act_t* out, float2* stats, int num_sms) {
+    DLIMG_ASSERT(local_conv_tma_supported(H, W, C));
+    ProfScope prof(s, CAT_DWCONV, 2.0 * batch * H * W * C * 9, (double)batch * 2.0 * H * W * C * 2);
+    if (C == 128) launch_local_conv<16>(s, in, batch, H, W, C, weight, bias, out, stats, num_sms);
+    else launch_local_conv<20>(s, in, batch, H, W, C, weight, bias, out, stats, num_sms);  // C = 160, or 320 as two parts
+}
+
+}  // namespace enc
+}  // namespace dlimg

@@ -337,7 +337,6 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
 EncoderWorkspace::EncoderWorkspace(int mb) : max_batch(mb) {
     size_t const B = (size_t)mb;
     c1.allocate(B * 512 * 512 * 32);
-    emb.allocate(B * 4096 * 256);
     col.allocate(B * 65536 * 288);
     xa.allocate(B * 65536 * 64);
     xb.allocate(B * 65536 * 64);
@@ -399,7 +398,7 @@ void SamModel::gemm32(cudaStream_t s, float const* a, int64_t rows, Linear32 con
 }
 
 void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const* images, int batch, int w, int h,
-                      int channels, float* emb_out, Tap* tap) const {
+                      int channels, float* emb_out, Tap* tap, float* emb_nchw_out, bool finish) const {
     DLIMG_ASSERT(batch >= 1 && batch <= ws.max_batch);
     int64_t const B = batch;
     using gemm::ACT_GELU;
@@ -464,6 +463,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         float2* stats = ws.stats.get();
         int const fc2_parts = C / gemm::pick_block_n(C);  // N tiles of fc2 = partial sums per row
         static bool const fused_mlp = std::getenv("DLIMG_B200_UNFUSED_MLP") == nullptr;
+        static bool const lc_tma = !kActBf16 && std::getenv("DLIMG_B200_LOCAL_CONV_REG") == nullptr;  // A/B switch
         for (int i = 0; i < c.depth; ++i) {
             BlockW const& b = enc_.blocks[st - 1][(size_t)i];
             std::string const tn = "s" + std::to_string(st) + "b" + std::to_string(i);
@@ -484,7 +484,13 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
             tap_act(s, tap, (tn + ".proj").c_str(), x, (size_t)rows * C);
             // local depthwise conv (no activation, no residual).  fp32 accumulation: its output IS the trunk (it replaces
             // x), and the packed-half kernel cost 0.0006 of mask IoU here for 3 % of the step -- not worth it.
-            enc::dwconv3x3_stats(s, x, batch, c.res, c.res, C, b.local_conv.w.get(), b.local_conv.b.get(), y, stats);
+            int lc_parts = 1;  // partial row sums per pixel
+            if (lc_tma && enc::local_conv_tma_supported(c.res, c.res, C)) {
+                enc::local_conv_tma(s, x, batch, c.res, c.res, C, b.local_conv.w.get(), b.local_conv.b.get(), y, stats, num_sms_);
+                lc_parts = enc::local_conv_parts(C);
+            } else {
+                enc::dwconv3x3_stats(s, x, batch, c.res, c.res, C, b.local_conv.w.get(), b.local_conv.b.get(), y, stats);
+            }
             tap_act(s, tap, (tn + ".lc").c_str(), y, (size_t)rows * C);
             // MLP branch: LN folded into fc1 (row sums from the depthwise kernel above) + GELU, fc2 + residual
             float2* const next_stats = i + 1 < c.depth ? ws.stats_parts.get() : nullptr;
@@ -493,7 +499,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
                 gemm::launch_mlp_fused(s, y, rows, C, b.fc1.w.get(), b.fc1.b.get(), stats, 1e-5f, b.fc2.w.get(), b.fc2.b.get(), y,
                                        next_stats, num_sms_);
             } else {
-                gemm16(s, y, rows, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, stats, false, 1);
+                gemm16(s, y, rows, b.fc1, ws.big[1].get(), ACT_GELU, nullptr, stats, false, lc_parts);
                 // fc2 + residual; its epilogue also leaves the LayerNorm row sums of the result for the next block's qkv
                 gemm16(s, ws.big[1].get(), rows, b.fc2, y, ACT_NONE, y, nullptr, false, 0, next_stats);
             }
@@ -520,8 +526,17 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         gemm::launch_conv3x3(s, ws.big[1].get(), batch, 64, 64, 256, gemm::Operand{enc_.neck2.w.get(), enc_.neck2.n, enc_.neck2.k, enc_.neck2.k},
                              ws.big[0].get(), e, num_sms_);
     }
-    enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f,
-                        emb_out, true);
+    if (finish) neck_finish(s, ws, batch, emb_out, emb_nchw_out, tap);
+}
+
+void SamModel::neck_finish(cudaStream_t s, EncoderWorkspace& ws, int batch, float* emb_out, float* emb_nchw_out, Tap* tap) const {
+    int64_t const B = batch;
+    if (emb_nchw_out)
+        enc::layernorm256_tokens_nchw(s, ws.big[0].get(), batch, 4096, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f, emb_out,
+                                      emb_nchw_out);
+    else
+        enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f,
+                            emb_out, true);
     if (tap && tap->name && std::strcmp(tap->name, "neck") == 0) {
         size_t const n = (size_t)B * 4096 * 256;
         if (n > tap->capacity) fail("tap buffer too small for neck");

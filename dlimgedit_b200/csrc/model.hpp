@@ -127,7 +127,6 @@ struct DecoderW {
 struct EncoderWorkspace {
     int max_batch = 0;
     DeviceBuffer<act_t> c1, col, xa, xb, big[4];
-    DeviceBuffer<float> emb;       // (max_batch, 4096, 256) fp32: fixed destination of the captured encoder graph
     DeviceBuffer<float2> stats;    // (max_batch * 16384): per-token LayerNorm (mean, rstd) of the current block input
     DeviceBuffer<float2> stats_parts;  // (max_batch * 16384 * 2): partial (sum, sum of squares) written by fc2's epilogue
     explicit EncoderWorkspace(int max_batch);
@@ -171,8 +170,12 @@ class SamModel {
 
     // images: `batch` device descriptors of u8 images with identical (w, h, channels), w, h <= 1024.
     // emb_out: (batch, 4096, 256) fp32, token-major (row = y*64 + x).
+    // emb_nchw_out (optional): the same embedding as (batch, 256, 64, 64) fp32.  finish = false stops in front of the
+    // final LayerNorm2d (its input is ws.big[0]); neck_finish() then writes the embedding -- the engine captures the
+    // trunk into a CUDA graph and finishes eagerly into whichever store the call owns.
     void encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const* images, int batch, int w, int h, int channels,
-                float* emb_out, Tap* tap = nullptr) const;
+                float* emb_out, Tap* tap = nullptr, float* emb_nchw_out = nullptr, bool finish = true) const;
+    void neck_finish(cudaStream_t s, EncoderWorkspace& ws, int batch, float* emb_out, float* emb_nchw_out, Tap* tap = nullptr) const;
 
     void prepare_embedding(cudaStream_t s, float const* emb, EmbeddingCache& cache) const;
 

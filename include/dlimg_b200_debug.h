@@ -51,6 +51,12 @@ typedef struct dlimg_b200_Debug {
      * 128 % W == 0, H % (128 / W) == 0, C % 64 == 0, N % 16 == 0. */
     dlimg_Result (*conv3x3)(void* stream, void const* in, int batch, int H, int W, int C, void const* weight,
                             float const* bias, int N, void* out);
+    /* TinyViT local_conv: depthwise 3x3 (stride 1, zero padding 1), fp32 accumulation, no activation.  in / out (batch, H,
+     * W, C) 16-bit NHWC, weight (9, C) fp32 with tap = ky * 3 + kx, bias (C); stats (batch * H * W, parts, 2) fp32:
+     * (sum, sum of squares) of the output pixel's channels (parts = 2 for C = 320 with tma != 0, else 1).
+     * tma != 0: the TMA halo-tile kernel (H % 8 == 0, W % 16 == 0, C in {128, 160, 320}); 0: the register-tiled kernel. */
+    dlimg_Result (*local_conv)(void* stream, void const* in, int batch, int H, int W, int C, float const* weight,
+                               float const* bias, void* out, float* stats, int tma);
 } dlimg_b200_Debug;
 
 DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void);

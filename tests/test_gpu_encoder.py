@@ -184,3 +184,32 @@ def test_window_attention_kernel(batch, res, ws, heads):
     torch.cuda.synchronize()
     simt = simt.view(batch, nw, nw, ws, ws, heads * 32).transpose(2, 3).reshape(batch, pr, pr, heads * 32)[:, :res, :res]
     assert torch.allclose(simt.reshape(batch * res * res, heads * 32).float(), ref, **tol)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 128, 128, 128), (3, 64, 64, 160), (2, 64, 64, 320), (1, 8, 32, 160)])
+def test_local_conv_tma_matches_register_kernel(B, H, W, C):
+    """The TMA halo-tile local_conv against the register-tiled kernel (bit-identical output: same fp32 operation
+    order) and against torch.nn.functional.conv2d; row sums against sums of the fp32 convolution."""
+    from gpu_util import act_dtype
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(act_dtype())
+    w = torch.randn(9, C, device="cuda", generator=g) / 3
+    b = 0.2 * torch.randn(C, device="cuda", generator=g)
+    parts = 2 if C == 320 else 1
+    out_t = torch.zeros(B, H, W, C, device="cuda", dtype=act_dtype())
+    out_r = torch.zeros_like(out_t)
+    st_t = torch.zeros(B * H * W, parts, 2, device="cuda")
+    st_r = torch.zeros(B * H * W, 1, 2, device="cuda")
+    dbg = dl.debug()
+    assert dbg.local_conv(None, x.data_ptr(), B, H, W, C, w.data_ptr(), b.data_ptr(), out_t.data_ptr(), st_t.data_ptr(), 1) == 0, dl.api().last_error()
+    assert dbg.local_conv(None, x.data_ptr(), B, H, W, C, w.data_ptr(), b.data_ptr(), out_r.data_ptr(), st_r.data_ptr(), 0) == 0, dl.api().last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(out_t, out_r)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.t().reshape(C, 1, 3, 3).contiguous(), b, padding=1, groups=C)
+    ref = ref.permute(0, 2, 3, 1)
+    assert torch.allclose(out_t.float(), ref, atol=2e-2, rtol=1e-2)
+    tot = st_t.sum(1)
+    assert torch.allclose(tot, st_r[:, 0], atol=1e-3, rtol=1e-5)
+    flat = ref.reshape(-1, C)
+    assert torch.allclose(tot[:, 0], flat.sum(1), atol=2e-2, rtol=1e-3)
+    assert torch.allclose(tot[:, 1], (flat * flat).sum(1), atol=5e-2, rtol=2e-3)
