@@ -9,8 +9,10 @@
 //   DW    thread = (channel octet, run of 4 pixels, tile row): 18 LDS.128 of activations, the fp32 filter from shared
 //         memory, fp32 accumulation in exactly the order of the register-tiled kernel (bit-identical output)
 //   OUT   16-byte stores (a pixel's octets are adjacent lanes), per-pixel (sum, sum of squares) through a
-//         double-buffered shared-memory exchange, added in a fixed order by one thread per pixel after the tile's
-//         only CTA barrier (which also hands the drained input buffer back to the TMA thread)
+//         double-buffered shared-memory exchange, added in a fixed order by one thread per pixel
+//   SYNC  no CTA-wide barrier: the threads of two tile rows (4 or 5 whole warps) meet at a named barrier for the row-sum
+//         exchange, and the last warp to finish reading an input buffer (a shared-memory counter) issues the TMA load
+//         that refills it, so the warp groups drift apart and cover each other's shared-memory latency
 // C = 320 runs as two channel parts of 160; the consumer adds the two partial row sums (gemm Epilogue::ln_parts = 2).
 #include "encoder_kernels.cuh"
 #include "gemm.cuh"
@@ -32,6 +34,8 @@ template <int kC8>
 struct LcCfg {
     static constexpr int kCu = kC8 * 8;                       // channels per unit
     static constexpr int kThreads = kC8 * 4 * kTH;            // (octet, 4-pixel run, row)
+    static constexpr int kGroup = kC8 * 8;                    // threads of two tile rows: 4 or 5 whole warps
+    static constexpr int kMaxRegs = (65536 / kThreads) / 8 * 8;  // one CTA per SM: give the compiler the whole file
     static constexpr int kInBytes = kHH * kHW * kCu * 2;      // one halo tile
     static constexpr int kPartBytes = kTH * kTW * kC8 * 8;    // (sum, sum of squares) per (pixel, octet)
     static constexpr int kSmemIn = 0;
@@ -51,7 +55,7 @@ __device__ __forceinline__ void unpack8h(uint4 const& v, float (&f)[8]) {
 }
 
 template <int kC8>
-__global__ void __launch_bounds__(LcCfg<kC8>::kThreads, 1)
+__global__ void __launch_bounds__(LcCfg<kC8>::kThreads, 1) __maxnreg__(LcCfg<kC8>::kMaxRegs)
 local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __restrict__ weight, float const* __restrict__ bias,
                   act_t* __restrict__ out, float2* __restrict__ stats, int H, int W, int C, int units) {
     using L = LcCfg<kC8>;
@@ -64,9 +68,15 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
     int const tid = threadIdx.x;
     int const parts = C / L::kCu, tiles_x = W / kTW, tiles_per_img = tiles_x * (H / kTH);
 
+    static_assert(L::kGroup % 32 == 0, "row-pair groups must be whole warps");
+    // barriers: full[kInBufs] at 0; drained-warp counters [kInBufs] (int) at 32
+    int* const drained = reinterpret_cast<int*>(gen + L::kSmemBar + 32);
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
-        for (int i = 0; i < kInBufs; ++i) mbar_init(bar + 8 * i, 1);
+        for (int i = 0; i < kInBufs; ++i) {
+            mbar_init(bar + 8 * i, 1);
+            drained[i] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 9 * C; i += L::kThreads) wsm[i] = __ldg(weight + i);
@@ -86,6 +96,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
         oy0 = (tr / tiles_x) * kTH;
         ox0 = (tr % tiles_x) * kTW;
     };
+
     auto issue_load = [&](int u) {
         int b, oy0, ox0, pt;
         locate(u, b, oy0, ox0, pt);
@@ -97,7 +108,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
         for (int u = 0; u < kInBufs && u < my_units; ++u) issue_load(u);
 
     int const c8 = tid % kC8, xg = (tid / kC8) & 3, ty = tid / (kC8 * 4);
-    uint32_t in_phase = 0;
+    int const grp = tid / L::kGroup, gtid = tid - grp * L::kGroup;  // row pair and index within it
     for (int u = 0; u < my_units; ++u) {
         int b, oy0, ox0, pt;
         locate(u, b, oy0, ox0, pt);
@@ -112,8 +123,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
                 acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
             }
         }
-        mbar_wait(bar + 8 * buf, (in_phase >> buf) & 1u);
-        in_phase ^= 1u << buf;
+        mbar_wait(bar + 8 * buf, ((uint32_t)(u / kInBufs)) & 1u);
         uint32_t const tile_in = in_s + buf * L::kInBytes + (uint32_t)(((ty * kHW + xg * 4) * L::kCu + c8 * 8) * 2);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -123,6 +133,17 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
                 asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(v[c].x), "=r"(v[c].y), "=r"(v[c].z), "=r"(v[c].w)
                              : "r"(tile_in + (uint32_t)(((ky * kHW + c) * L::kCu) * 2)));
+            if (ky == 2) {  // this warp's last reads of the buffer have been issued: the last warp to get here refills it
+                asm volatile("" ::: "memory");  // (compiler: keep the counter update behind the loads above)
+                __syncwarp();
+                if ((tid & 31) == 0 && atomicAdd(&drained[buf], 1) == L::kThreads / 32 - 1) {
+                    drained[buf] = 0;
+                    if (u + kInBufs < my_units) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue_load(u + kInBufs);
+                    }
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
                 float f[8];
@@ -160,11 +181,11 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
             for (int i = 0; i < 4; ++i) oh[i] = f22act2(acc[o][2 * i], acc[o][2 * i + 1]);
             orow[(size_t)o * (C / 8)] = ov;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the buffer before its next TMA write
-        __syncthreads();  // the input buffer is drained and the partial sums of this unit are visible
-        if (tid == 0 && u + kInBufs < my_units) issue_load(u + kInBufs);
-        if (tid < kTH * kTW) {  // one thread per pixel: fixed-order sum over the unit's octets
-            float2 const* p = part + (u & 1) * (kTH * kTW * kC8) + tid * kC8;
+        // the partial sums of this row pair's 32 pixels are visible to its first warp
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(L::kGroup) : "memory");
+        if (gtid < 2 * kTW) {  // one thread per pixel of the row pair: fixed-order sum over the unit's octets
+            int const pix = grp * 2 * kTW + gtid;
+            float2 const* p = part + (u & 1) * (kTH * kTW * kC8) + pix * kC8;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 4
             for (int k = 0; k < kC8; ++k) {
@@ -172,11 +193,11 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
                 s1 += v.x;
                 s2 += v.y;
             }
-            int const py = tid / kTW, px = tid - py * kTW;
+            int const py = pix / kTW, px = pix - py * kTW;
             stats[(((int64_t)b * H + oy0 + py) * W + ox0 + px) * parts + pt] = make_float2(s1, s2);
         }
         // (the other exchange buffer is written by the next unit; this one again only after the next unit's barrier,
-        //  by which time the readers above are done with it)
+        //  which the readers above reach after they are done with it)
     }
 }
 
