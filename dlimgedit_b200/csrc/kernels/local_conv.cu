@@ -37,7 +37,8 @@ struct LcCfg {
     static constexpr int kGroup = kC8 * 8;                    // threads of two tile rows: 4 or 5 whole warps
     static constexpr int kMaxRegs = (65536 / kThreads) / 8 * 8;  // one CTA per SM: give the compiler the whole file
     static constexpr int kInBytes = kHH * kHW * kCu * 2;      // one halo tile
-    static constexpr int kPartBytes = kTH * kTW * kC8 * 8;    // (sum, sum of squares) per (pixel, octet)
+    static constexpr int kPartPitch = kC8 + 1;                // float2 per pixel row of the exchange (+1: conflict-free reads)
+    static constexpr int kPartBytes = kTH * kTW * kPartPitch * 8;  // (sum, sum of squares) per (pixel, octet)
     static constexpr int kSmemIn = 0;
     static constexpr int kSmemPart = kSmemIn + kInBufs * kInBytes;
     static constexpr int kSmemBar = kSmemPart + 2 * kPartBytes;
@@ -79,8 +80,12 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 9 * C; i += L::kThreads) wsm[i] = __ldg(weight + i);
-    for (int i = tid; i < C; i += L::kThreads) wsm[9 * C + i] = __ldg(bias + i);
+    // filter and bias in shared memory as [tap][half of the octet][octet][4]: the 16 / 20 lanes of a pixel read
+    // consecutive 16-byte pieces (the natural [tap][channel] order makes every such read a 2-way bank conflict)
+    for (int i = tid; i < 10 * C; i += L::kThreads) {
+        int const k = i / C, ch = i - k * C;
+        wsm[((k * 2 + ((ch >> 2) & 1)) * (C >> 3) + (ch >> 3)) * 4 + (ch & 3)] = k < 9 ? __ldg(weight + i) : __ldg(bias + ch);
+    }
     __syncthreads();
     pdl_wait();
     pdl_trigger();
@@ -113,10 +118,10 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
         int b, oy0, ox0, pt;
         locate(u, b, oy0, ox0, pt);
         int const buf = u % kInBufs;
-        float const* const w = wsm + pt * L::kCu + c8 * 8;
+        float const* const w = wsm + (pt * kC8 + c8) * 4;  // tap k: halves at w + k * C and w + k * C + C / 2
         float acc[4][8];
         {
-            float4 const b0 = *reinterpret_cast<float4 const*>(w + 9 * C), b1 = *reinterpret_cast<float4 const*>(w + 9 * C + 4);
+            float4 const b0 = *reinterpret_cast<float4 const*>(w + 9 * C), b1 = *reinterpret_cast<float4 const*>(w + 9 * C + (C >> 1));
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
                 acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
@@ -153,7 +158,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
                     int const o = c - kx;
                     if (o < 0 || o >= 4) continue;
                     float const* wk = w + (ky * 3 + kx) * C;
-                    float4 const w0 = *reinterpret_cast<float4 const*>(wk), w1 = *reinterpret_cast<float4 const*>(wk + 4);
+                    float4 const w0 = *reinterpret_cast<float4 const*>(wk), w1 = *reinterpret_cast<float4 const*>(wk + (C >> 1));
                     acc[o][0] = fmaf(f[0], w0.x, acc[o][0]); acc[o][1] = fmaf(f[1], w0.y, acc[o][1]);
                     acc[o][2] = fmaf(f[2], w0.z, acc[o][2]); acc[o][3] = fmaf(f[3], w0.w, acc[o][3]);
                     acc[o][4] = fmaf(f[4], w1.x, acc[o][4]); acc[o][5] = fmaf(f[5], w1.y, acc[o][5]);
@@ -165,7 +170,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
         int const oy = oy0 + ty, ox = ox0 + xg * 4;
         int64_t const row0 = ((int64_t)b * H + oy) * W + ox;
         uint4* const orow = reinterpret_cast<uint4*>(out + row0 * C + pt * L::kCu) + c8;
-        float2* const mypart = part + (u & 1) * (kTH * kTW * kC8) + ((ty * kTW + xg * 4) * kC8 + c8);
+        float2* const mypart = part + (u & 1) * (kTH * kTW * L::kPartPitch) + ((ty * kTW + xg * 4) * L::kPartPitch + c8);
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
             float s1 = 0.f, s2 = 0.f;
@@ -174,7 +179,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
                 s1 += acc[o][i];
                 s2 = fmaf(acc[o][i], acc[o][i], s2);
             }
-            mypart[o * kC8] = make_float2(s1, s2);
+            mypart[o * L::kPartPitch] = make_float2(s1, s2);
             uint4 ov;
             act2_t* oh = reinterpret_cast<act2_t*>(&ov);
 #pragma unroll
@@ -185,7 +190,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(L::kGroup) : "memory");
         if (gtid < 2 * kTW) {  // one thread per pixel of the row pair: fixed-order sum over the unit's octets
             int const pix = grp * 2 * kTW + gtid;
-            float2 const* p = part + (u & 1) * (kTH * kTW * kC8) + pix * kC8;
+            float2 const* p = part + (u & 1) * (kTH * kTW * L::kPartPitch) + pix * L::kPartPitch;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 4
             for (int k = 0; k < kC8; ++k) {
