@@ -344,7 +344,7 @@ def run_ours(args):
     # pass), below the B200 ridge point (measured 1407.6 TFLOP/s / 6537.6 GB/s = 215 flop/byte): its roofline is HBM.
     # achieved = algorithmic bytes (A + B + C [+ residual], each once) of its launches / their CUDA-event time.
     gemm_gbs = g.get("bytes", 0.0) / (g["ms"] * 1e-3) / 1e9 if g["ms"] else 0.0
-    roofline = {"bound": "hbm", "kernel": "gemm_tc_kernel<f16> (tcgen05.mma + TMA, all encoder GEMMs)", "achieved": gemm_gbs,
+    roofline = {"bound": "hbm", "kernel": "gemm_tc_kernel<f16> + mlp_fused_kernel (tcgen05.mma + TMA: all encoder GEMMs, the neck 3x3 conv and the fused MLPs)", "achieved": gemm_gbs,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gemm_gbs / peaks["hbm_gbs"],
                 "peak_source": peaks["source"] + " STREAM-style copy bandwidth",
                 "traffic": traffic, "algorithmic_bytes_per_launch": (g.get("bytes", 0.0) / g["launches"]) if g["launches"] else None,
