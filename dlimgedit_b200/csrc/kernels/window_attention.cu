@@ -78,37 +78,49 @@ struct Cfg {
 // One chunk of kCnt key blocks (8 keys each) of the online softmax for one (head, query tile).
 template <int kCnt, bool kFirst, bool kBiasInSmem>
 __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4], uint32_t k_addr, uint32_t v_addr, int row_bytes,
-                                             uint32_t bias_addr, uint2 const* __restrict__ bias_gl, float (&m)[2], float (&l)[2],
+                                             uint32_t bias_addr, float4 const* __restrict__ bias_gl, float (&m)[2], float (&l)[2],
                                              float (&o)[4][4]) {
     float const kScale = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
     float s[kCnt][4];
-#pragma unroll
-    for (int j = 0; j < kCnt; ++j) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(k_addr + (uint32_t)((nb0 + j) * 8 * row_bytes), b0, b1, b2, b3);
-        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-        mma16816(s[j], aq[0][0], aq[0][1], aq[0][2], aq[0][3], b0, b1);
-        mma16816(s[j], aq[1][0], aq[1][1], aq[1][2], aq[1][3], b2, b3);
-    }
     float cm0 = -INFINITY, cm1 = -INFINITY;
+    if (kBiasInSmem) {
+        // bias fragments (fp16, pre-multiplied by log2 e) in shared memory: s = q.k * scale * log2 e + bias
 #pragma unroll
-    for (int j = 0; j < kCnt; ++j) {
-        uint32_t w0, w1;
-        if (kBiasInSmem) {
-            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(bias_addr + (uint32_t)((nb0 + j) * 256)));
-        } else {
-            uint2 const bw = __ldg(bias_gl + (nb0 + j) * 32);
-            w0 = bw.x;
-            w1 = bw.y;
+        for (int j = 0; j < kCnt; ++j) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(k_addr + (uint32_t)((nb0 + j) * 8 * row_bytes), b0, b1, b2, b3);
+            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+            mma16816(s[j], aq[0][0], aq[0][1], aq[0][2], aq[0][3], b0, b1);
+            mma16816(s[j], aq[1][0], aq[1][1], aq[1][2], aq[1][3], b2, b3);
         }
-        float2 const f0 = __half22float2(*reinterpret_cast<__half2 const*>(&w0));
-        float2 const f1 = __half22float2(*reinterpret_cast<__half2 const*>(&w1));
-        s[j][0] = fmaf(s[j][0], kScale, f0.x);
-        s[j][1] = fmaf(s[j][1], kScale, f0.y);
-        s[j][2] = fmaf(s[j][2], kScale, f1.x);
-        s[j][3] = fmaf(s[j][3], kScale, f1.y);
-        cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
-        cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+#pragma unroll
+        for (int j = 0; j < kCnt; ++j) {
+            uint32_t w0, w1;
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(bias_addr + (uint32_t)((nb0 + j) * 256)));
+            float2 const f0 = __half22float2(*reinterpret_cast<__half2 const*>(&w0));
+            float2 const f1 = __half22float2(*reinterpret_cast<__half2 const*>(&w1));
+            s[j][0] = fmaf(s[j][0], kScale, f0.x);
+            s[j][1] = fmaf(s[j][1], kScale, f0.y);
+            s[j][2] = fmaf(s[j][2], kScale, f1.x);
+            s[j][3] = fmaf(s[j][3], kScale, f1.y);
+            cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
+            cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+        }
+    } else {
+        // bias fragments (fp32, divided by the qk scale) from global memory are the initial accumulators of the MMA:
+        // s = q.k + bias / scale, and the scale * log2 e moves into the exponent below -- eight instructions fewer per
+        // key block than converting and adding an fp16 bias
+#pragma unroll
+        for (int j = 0; j < kCnt; ++j) {
+            float4 const bw = __ldg(bias_gl + (nb0 + j) * 32);
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(k_addr + (uint32_t)((nb0 + j) * 8 * row_bytes), b0, b1, b2, b3);
+            s[j][0] = bw.x; s[j][1] = bw.y; s[j][2] = bw.z; s[j][3] = bw.w;
+            mma16816(s[j], aq[0][0], aq[0][1], aq[0][2], aq[0][3], b0, b1);
+            mma16816(s[j], aq[1][0], aq[1][1], aq[1][2], aq[1][3], b2, b3);
+            cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
+            cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+        }
     }
     cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
     cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
@@ -119,7 +131,7 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
         m[1] = cm1;
     } else {  // every chunk holds at least one unmasked key, so the running maxima are finite from chunk 0 on
         float const n0 = fmaxf(m[0], cm0), n1 = fmaxf(m[1], cm1);
-        float const a0 = ex2(m[0] - n0), a1 = ex2(m[1] - n1);
+        float const a0 = ex2((m[0] - n0) * (kBiasInSmem ? 1.0f : kScale)), a1 = ex2((m[1] - n1) * (kBiasInSmem ? 1.0f : kScale));
         m[0] = n0;
         m[1] = n1;
         l[0] *= a0;
@@ -130,12 +142,20 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
             o[d][2] *= a1; o[d][3] *= a1;
         }
     }
+    float const e0 = -m[0] * kScale, e1 = -m[1] * kScale;  // (global-bias path: scores are still unscaled)
 #pragma unroll
     for (int j = 0; j < kCnt; ++j) {
-        s[j][0] = ex2(s[j][0] - m[0]);
-        s[j][1] = ex2(s[j][1] - m[0]);
-        s[j][2] = ex2(s[j][2] - m[1]);
-        s[j][3] = ex2(s[j][3] - m[1]);
+        if (kBiasInSmem) {
+            s[j][0] = ex2(s[j][0] - m[0]);
+            s[j][1] = ex2(s[j][1] - m[0]);
+            s[j][2] = ex2(s[j][2] - m[1]);
+            s[j][3] = ex2(s[j][3] - m[1]);
+        } else {
+            s[j][0] = ex2(fmaf(s[j][0], kScale, e0));
+            s[j][1] = ex2(fmaf(s[j][1], kScale, e0));
+            s[j][2] = ex2(fmaf(s[j][2], kScale, e1));
+            s[j][3] = ex2(fmaf(s[j][3], kScale, e1));
+        }
         l[0] += s[j][0] + s[j][1];
         l[1] += s[j][2] + s[j][3];
     }
@@ -226,8 +246,8 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
     uint32_t const k_off = (uint32_t)((lane & 7) * C::kRowBytes + (hh * 96 + 32 + (lane >> 3) * 8) * 2);
     uint32_t const v_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * C::kRowBytes + (hh * 96 + 64 + ((lane >> 4) & 1) * 8) * 2);
     uint32_t const bias_addr = bias_s + (uint32_t)((((hh * C::NQ + qt) * C::NK8) * 32 + lane) * 8);
-    uint2 const* const bias_gl = reinterpret_cast<uint2 const*>(bias_frag) + (size_t)hg * (C::kBiasBytes / 8) +
-                                 ((hh * C::NQ + qt) * C::NK8) * 32 + lane;
+    float4 const* const bias_gl = reinterpret_cast<float4 const*>(bias_frag) + (size_t)hg * (C::kBiasBytes / 8) +
+                                  ((hh * C::NQ + qt) * C::NK8) * 32 + lane;  // (fp32 fragments: one float4 per lane and key block)
 
     int it = 0;
     if (w_first < total_windows) load_item(w_first, 0);
@@ -323,14 +343,19 @@ int attention_head_group(int ws, int heads) {
     return heads % 5 == 0 ? 5 : (heads % 4 == 0 ? 4 : 0);
 }
 
+// 7 x 7 windows: fp16 fragments pre-multiplied by log2 e (they live in shared memory).  14 x 14 windows: fp32 fragments
+// divided by the qk scale (read from global memory straight into the MMA accumulators), two uint16 slots per value.
+static bool bias_fragments_fp32(int ws) { return !Cfg<14, 1>::kBiasInSmem && ws == 14; }
+
 size_t attention_bias_fragment_count(int heads, int ws) {
     int const n = ws * ws, nq = (n + 15) / 16, nk8 = (n + 7) / 8;
-    return (size_t)heads * nq * nk8 * 32 * 4;
+    return (size_t)heads * nq * nk8 * 32 * 4 * (bias_fragments_fp32(ws) ? 2 : 1);
 }
 
 void attention_bias_fragments(float const* dense, int heads, int ws, uint16_t* out) {
     int const n = ws * ws, nq = (n + 15) / 16, nk8 = (n + 7) / 8;
     float const log2e = 1.4426950408889634f;
+    bool const f32 = bias_fragments_fp32(ws);
     size_t i = 0;
     for (int h = 0; h < heads; ++h)
         for (int qt = 0; qt < nq; ++qt)
@@ -341,9 +366,15 @@ void attention_bias_fragments(float const* dense, int heads, int ws, uint16_t* o
                         int const c = nb * 8 + 2 * (lane & 3) + (e & 1);
                         float v = 0.f;
                         if (c >= n) v = -INFINITY;  // key padding of the tile: masked
-                        else if (r < n) v = dense[((size_t)h * n + r) * n + c] * log2e;
-                        __half const hv = __float2half_rn(v);
-                        out[i++] = *reinterpret_cast<uint16_t const*>(&hv);
+                        else if (r < n) v = dense[((size_t)h * n + r) * n + c];
+                        if (f32) {
+                            if (c < n) v *= 5.656854249492381f;  // / 32^-0.5
+                            reinterpret_cast<float*>(out)[i++] = v;
+                        } else {
+                            if (c < n) v *= log2e;
+                            __half const hv = __float2half_rn(v);
+                            out[i++] = *reinterpret_cast<uint16_t const*>(&hv);
+                        }
                     }
 }
 
