@@ -34,7 +34,7 @@ constexpr int kTH = 8, kTW = 16;               // output tile
 constexpr int kC1H = 2 * kTH + 1, kC1W = 2 * kTW + 1;  // 17 x 33 conv1 outputs
 constexpr int kInH = 2 * kC1H + 1, kInW = 2 * kC1W + 1;  // 35 x 67 input pixels
 constexpr int kInPitch = 68;                   // pixels per tile row (even: keeps (k, k+1) pairs 4-byte aligned)
-constexpr int kC1Pitch = 80;                   // bytes per conv1 pixel in shared memory (64 + 16)
+constexpr int kC1Pitch = 80;                   // bytes per conv1 pixel in shared memory (64 + 16; the data starts at 0 or 16)
 constexpr int kThreads = 576;                  // 18 warps: the 36 conv1 mma tiles split evenly
 constexpr int kKBlocks = 5;                    // K = 9 taps * 32 channels = 288, padded to 320
 constexpr int kABlockBytes = 128 * 128;        // one k-block of A: 128 rows x 128 B
@@ -130,7 +130,9 @@ patch_embed_kernel(ImageDesc const* __restrict__ imgs, PatchParams p, uint32_t c
     float const inv_sd[3] = {1.0f / 58.395f, 1.0f / 57.12f, 1.0f / 57.375f};  // the result is rounded to fp16 right away
     uint32_t const idesc = make_idesc(0u, 128, 64);
     // P3 / P5 geometry of this thread
-    int const a_row = tid >> 2, a_cc = tid & 3;               // A row (output pixel) and 16-byte piece of the 64-byte tap
+    // A row (output pixel) and 16-byte piece of the 64-byte tap.  A quarter-warp holds 8 consecutive rows and ONE piece:
+    // its swizzled STS.128 then hit eight different 16-byte bank groups (rows x 4 pieces per quarter-warp collided 2-way)
+    int const a_row = (tid >> 5) * 8 + (tid & 7), a_cc = (tid >> 3) & 3;
     int const a_ty = a_row >> 4, a_tx = a_row & 15;
     int const quarter = warp & 3, col0 = (warp >> 2) * 16;    // epilogue: TMEM lane quarter, 16 of the 64 columns
 
@@ -256,7 +258,9 @@ patch_embed_kernel(ImageDesc const* __restrict__ imgs, PatchParams p, uint32_t c
                 int const cy = q[hh] / kC1W, cx = q[hh] - cy * kC1W;
                 int const Y = 2 * oy0 - 1 + cy, X = 2 * ox0 - 1 + cx;  // position in the 512 x 512 conv1 map
                 bool const inside = Y >= 0 && X >= 0;                   // the upper bounds cannot be exceeded
-                uint32_t const dst = c1_s + (uint32_t)(q[hh] * kC1Pitch + 2 * t * 2);
+                // pixels 8..15, 24..31 of a row sit 16 bytes further into their 80-byte slot: the P3 reads of 8
+                // consecutive output pixels (conv1 x stride 2 = 160 bytes) then cover all eight 16-byte bank groups
+                uint32_t const dst = c1_s + (uint32_t)(q[hh] * kC1Pitch + ((cx >> 3) & 1) * 16 + 2 * t * 2);
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
                     __half2 v = gelu_erf_h2(__floats2half2_rn(acc[nb][2 * hh] + bias1[nb].x, acc[nb][2 * hh + 1] + bias1[nb].y));
@@ -286,7 +290,7 @@ patch_embed_kernel(ImageDesc const* __restrict__ imgs, PatchParams p, uint32_t c
                 uint4 v;
                 asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                             : "r"(c1_s + (uint32_t)((cy * kC1W + cx) * kC1Pitch + a_cc * 16)));
+                             : "r"(c1_s + (uint32_t)((cy * kC1W + cx) * kC1Pitch + ((cx >> 3) & 1) * 16 + a_cc * 16)));
                 int const j = (tap & 1) * 4 + a_cc;  // 16-byte piece within the 128-byte row of k-block tap / 2
                 uint32_t const dst = a_s + (uint32_t)((tap >> 1) * kABlockBytes + a_row * 128 + ((j ^ (a_row & 7)) << 4));
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
