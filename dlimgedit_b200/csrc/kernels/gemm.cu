@@ -191,6 +191,16 @@ __device__ __forceinline__ void epilogue_store16(uint32_t const (&r)[16], EpiPar
     }
 }
 
+// Byte offset of 16-byte piece `chunk` of row `row` in a warp's staging area (32 rows x cnt * 32 bytes).  The area is
+// written row-per-lane (8 consecutive rows, same piece, per quarter-warp) and read piece-per-lane (whole row segments
+// across consecutive lanes); both must spread over the eight 16-byte bank groups.  128-byte rows do that with a 16-byte
+// pad; 64- and 96-byte rows need an XOR swizzle instead (with padding one of the two phases conflicts 2-way).
+__device__ __forceinline__ uint32_t stage_offset(int cnt, int row, int chunk) {
+    if (cnt == 2) return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+    if (cnt == 3) return (uint32_t)(row * 96 + ((chunk ^ ((row >> 2) & 1)) << 4));
+    return (uint32_t)(row * (cnt * 32 + kStagePad) + (chunk << 4));
+}
+
 // The slabs of one warp for one tile, with a compile-time slab count so that the TMEM double buffer lives in fixed
 // registers (no moves) and the loop has no run-time conditions.
 struct SlabCtx {
@@ -230,13 +240,14 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
             if (kLn) ln_bias16_s(v, cx.bias_s, c, cx.rstd);  // staged kernels always hold the bias vector (or zeros)
             else add_bias16_s(v, cx.bias_s, c);
-            uint32_t const dst = cx.stage_row + (uint32_t)(k * 32);
+            uint32_t const dst = cx.stage_base + stage_offset(kCnt, cx.lane, 2 * k);
+            uint32_t const dst1 = cx.stage_base + stage_offset(kCnt, cx.lane, 2 * k + 1);
             if (kRes && ep.residual) {
                 // the residual piece of this tile is already in the staging area (cp.async, whole row segments); this
                 // lane adds its row's 16 values in fp32 and puts the rounded sums back in the same place
                 uint4 rs[2];
                 asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rs[0].x), "=r"(rs[0].y), "=r"(rs[0].z), "=r"(rs[0].w) : "r"(dst));
-                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rs[1].x), "=r"(rs[1].y), "=r"(rs[1].z), "=r"(rs[1].w) : "r"(dst + 16u));
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rs[1].x), "=r"(rs[1].y), "=r"(rs[1].z), "=r"(rs[1].w) : "r"(dst1));
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     act2_t const* h = reinterpret_cast<act2_t const*>(&rs[i]);
@@ -258,7 +269,7 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             uint4 x[2];
             activate_pack16(v, kAct, x);
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(x[0].x), "r"(x[0].y), "r"(x[0].z), "r"(x[0].w) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst1), "r"(x[1].x), "r"(x[1].y), "r"(x[1].z), "r"(x[1].w) : "memory");
         } else if (cx.orow >= 0) {
             epilogue_store16(r[k & 1], ep, out, cx.orow, c, sum, sumsq);
         }
@@ -278,7 +289,7 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
                 for (int j = 0; j < kBatch; ++j) {
                     int const rr = row0 + (it0 + j) * kRows;
                     if (it0 + j < kIters && rr < 32) {
-                        uint32_t const src = cx.stage_base + (uint32_t)rr * cx.pitch + (uint32_t)chunk * 16u;
+                        uint32_t const src = cx.stage_base + stage_offset(kCnt, rr, chunk);
                         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x[j].x), "=r"(x[j].y), "=r"(x[j].z), "=r"(x[j].w) : "r"(src));
                     }
                 }
@@ -494,7 +505,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             int const rows_valid = min(32, M - m0);
             if (row0 < rows_it) {
                 for (int rr = row0; rr < rows_valid; rr += rows_it) {
-                    uint32_t const dst = my_stage + (uint32_t)rr * pitch + (uint32_t)chunk * 16u;
+                    uint32_t const dst = my_stage + stage_offset(s_cnt, rr, chunk);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(seg + (int64_t)rr * ep.ldc + chunk * 8) : "memory");
                 }
             }
