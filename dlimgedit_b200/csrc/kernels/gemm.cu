@@ -206,13 +206,11 @@ __device__ __forceinline__ uint32_t stage_offset(int cnt, int row, int chunk) {
 struct SlabCtx {
     uint32_t taddr;       // TMEM address of the warp's first slab (lane quarter + accumulator stage + column)
     uint32_t tempty;      // accumulator-empty mbarrier of this stage
-    uint32_t stage_row;   // shared-memory address of this lane's staging row (kStaged)
     int col0;             // global column of the first slab
     int64_t orow;         // output row of this lane (direct path), -1 = none
     float rstd;           // folded LayerNorm: 1 / sqrt(var + eps) of this lane's row
     int lane;
-    uint32_t stage_base;  // shared-memory address of the warp's staging area, row pitch below (kStaged)
-    uint32_t pitch;
+    uint32_t stage_base;  // shared-memory address of the warp's staging area (kStaged), laid out by stage_offset()
     act_t* out_seg;       // output address of (first row of the warp's 32, first column of its range) (kStaged)
     int64_t ldc;
     int rows_valid;       // how many of the warp's 32 rows exist (M tail)
@@ -564,13 +562,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             SlabCtx cx;
             cx.taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMaxBlockN + s_first * 16);
             cx.tempty = tempty_bar(acc);
-            cx.stage_row = my_stage + (uint32_t)lane * pitch;
             cx.col0 = n0 + s_first * 16;
             cx.orow = orow;
             cx.rstd = rstd;
             cx.lane = lane;
             cx.stage_base = my_stage;
-            cx.pitch = pitch;
             cx.out_seg = reinterpret_cast<act_t*>(out) + (int64_t)(m0 + quarter * 32) * ep.ldc + n0 + s_first * 16;
             cx.ldc = ep.ldc;
             cx.rows_valid = M - (m0 + quarter * 32);
@@ -640,7 +636,6 @@ struct MlpParams {
     float const* b2;             // [C]
     float2 const* ln_stats;      // [M] partial (sum, sum of squares) of the rows of x (ln_parts == 1)
     float ln_eps;
-    act_t const* residual;       // [M][C] (= x)
     act_t* out;                  // [M][C]
     float2* stats_out;           // [M] (sum, sum of squares) of the output rows, or null
 };
@@ -1197,9 +1192,16 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     int const M = (int)a.rows, N = (int)b.rows, K = (int)a.cols;
     DLIMG_ASSERT(a.cols == b.cols);
     DLIMG_ASSERT(M > 0 && N > 0 && K > 0);
-    int const block_n = pick_block_n(N);
+    int block_n = pick_block_n(N);
     if (block_n == 0) fail("GEMM: N must be a multiple of 16, got " + std::to_string(N));
     EpiParams ep = to_params(epi, N);
+    // Small problems (the decoder's token-side Linears, single-image encoder passes): narrower tiles put more SMs to
+    // work and shorten the per-CTA k-loop.  The sum over K of an output element does not depend on the tile width, so
+    // results are bit-identical; producers of row sums keep their width (the consumer counts the partial sums).
+    if (!ep.stats_out) {
+        int const tiles_m = ceil_div(M, kBlockM);
+        while (block_n >= 128 && block_n % 32 == 0 && N % (block_n / 2) == 0 && 2 * tiles_m * (N / block_n) <= num_sms) block_n /= 2;
+    }
     DLIMG_ASSERT(ep.ldc % (ep.out_f32 ? 4 : 8) == 0);
     ConvParams conv;
     if (ci) {
@@ -1275,7 +1277,6 @@ void launch_mlp_fused(cudaStream_t stream, void const* x, int64_t rows, int C, v
     p.b2 = b2;
     p.ln_stats = ln_stats;
     p.ln_eps = ln_eps;
-    p.residual = static_cast<act_t const*>(x);
     p.out = static_cast<act_t*>(out);
     p.stats_out = stats_out;
     ProfScope prof(stream, CAT_GEMM_BF16, 4.0 * M * (double)C * H, 2.0 * ((double)M * C * 3 + 2.0 * C * H));
