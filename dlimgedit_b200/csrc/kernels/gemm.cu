@@ -212,12 +212,13 @@ struct SlabCtx {
     int lane;
     uint32_t stage_base;  // shared-memory address of the warp's staging area (kStaged), laid out by stage_offset()
     act_t* out_seg;       // output address of (first row of the warp's 32, first column of its range) (kStaged)
+    int64_t out_off;      // the same as an element offset (fp32 outputs)
     int64_t ldc;
     int rows_valid;       // how many of the warp's 32 rows exist (M tail)
     uint32_t bias_s;      // shared-memory copy of the bias vector (kStaged; 0 = read it from global memory)
 };
 
-template <int kCnt, bool kStaged, int kAct, bool kLn, bool kRes = false>
+template <int kCnt, bool kStaged, int kAct, bool kLn, bool kRes = false, bool kF32 = false>
 __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams const& ep, void* out, float& sum, float& sumsq) {
     uint32_t r[2][16];
     tmem_ld16(cx.taddr, r[0]);
@@ -232,7 +233,51 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             if (cx.lane == 0) mbar_arrive(cx.tempty);  // all of this warp's slabs are out of TMEM
         }
         int const c = cx.col0 + k * 16;
-        if (kStaged) {
+        if (kStaged && kF32) {
+            // fp32 output (decoder): the slabs go through the staging area in pairs (128-byte rows, XOR-swizzled; a
+            // trailing single slab as 64-byte rows), so that every store instruction writes whole 128-byte lines
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
+            add_bias16_s(v, cx.bias_s, c);
+            if (ep.act == ACT_GELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+            } else if (ep.act == ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+            constexpr int kPairs = (kCnt + 1) / 2;
+            int const pair = k >> 1;
+            bool const full = 2 * pair + 1 < kCnt;  // this pair holds two slabs (compile-time after unrolling)
+            int const cnt = full ? 4 : 2;           // in units of 32-byte half-slabs: reuse the 16-bit layouts
+            (void)kPairs;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int const chunk = (k & 1) * 4 + i;
+                uint32_t const dst = cx.stage_base + (full ? (uint32_t)(cx.lane * 128 + ((chunk ^ (cx.lane & 7)) << 4))
+                                                           : stage_offset(2, cx.lane, chunk));
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+            }
+            if ((k & 1) == 1 || k == kCnt - 1) {  // pair complete: whole row segments -> global
+                __syncwarp();
+                int const cpr = 2 * cnt, rows_it = 32 / cpr;  // 16-byte pieces per row (8 / 4), rows per instruction
+                int const row0 = cx.lane / cpr, chunk = cx.lane - row0 * cpr;
+                float* pdst = reinterpret_cast<float*>(out) + cx.out_off + (int64_t)row0 * cx.ldc + pair * 32 + chunk * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    int const rr = row0 + it * rows_it;
+                    if (it < cpr) {
+                        uint32_t const src = cx.stage_base + (full ? (uint32_t)(rr * 128 + ((chunk ^ (rr & 7)) << 4)) : stage_offset(2, rr, chunk));
+                        float4 x;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(src));
+                        if (rr < cx.rows_valid) *reinterpret_cast<float4*>(pdst) = x;
+                        pdst += (int64_t)rows_it * cx.ldc;
+                    }
+                }
+                __syncwarp();
+            }
+        } else if (kStaged) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
@@ -272,7 +317,7 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             epilogue_store16(r[k & 1], ep, out, cx.orow, c, sum, sumsq);
         }
     }
-    if (kStaged) {
+    if (kStaged && !kF32) {
         // transpose through the warp's staging area: each instruction now covers 32 / cpr whole row segments
         constexpr int kCpr = 2 * kCnt, kRows = 32 / kCpr, kIters = (32 + kRows - 1) / kRows;
         __syncwarp();
@@ -323,10 +368,11 @@ constexpr int kSmemLimit = 227 * 1024;
 struct SmemPlan {
     int stages, staging_bytes, total_bytes;
 };
-inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false, int bias_bytes = 0) {
+inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false, int bias_bytes = 0, bool tf32 = false) {
     SmemPlan p;
     // 16 epilogue warps x 32 rows x (64-column share of the tile + pad), see the epilogue
     p.staging_bytes = staged ? (int)round_up64((int64_t)kEpiWarps * 32 * ((((block_n >> 4) + 3) / 4) * 32 + kStagePad), 1024) : 0;
+    if (staged && tf32) p.staging_bytes = kEpiWarps * 32 * 128;  // fp32 outputs: pairs of slabs as 128-byte rows
     if (stats) p.staging_bytes += 8192;  // two buffers of 16 warps x 32 lanes x (sum, sum of squares), behind the staging
     p.staging_bytes += bias_bytes;       // the bias vector, behind both
     int const stage_bytes = kAStageBytes + block_n * kKBytes;
@@ -488,7 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int const nslab = block_n >> 4;
         int const s_cnt = nslab / 4 + (slab < (nslab & 3) ? 1 : 0);           // slabs of this warp
         int const s_first = slab * (nslab / 4) + min(slab, nslab & 3);       // first slab
-        uint32_t const pitch = (uint32_t)(((nslab + 3) / 4) * 32 + kStagePad);  // bytes per staged row
+        uint32_t const pitch = kTF32 ? 128u : (uint32_t)(((nslab + 3) / 4) * 32 + kStagePad);  // bytes per staged row
         uint32_t const my_stage = stage_out + (uint32_t)(quarter * 4 + slab) * 32u * pitch;
         // kRes (staged kernels with a 16-bit residual): the warp's 32 x (s_cnt * 32 B) piece of the residual is copied
         // into its staging area with cp.async as whole row segments -- one tile ahead, right after the staging area has
@@ -567,16 +613,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             cx.rstd = rstd;
             cx.lane = lane;
             cx.stage_base = my_stage;
-            cx.out_seg = reinterpret_cast<act_t*>(out) + (int64_t)(m0 + quarter * 32) * ep.ldc + n0 + s_first * 16;
+            cx.out_off = (int64_t)(m0 + quarter * 32) * ep.ldc + n0 + s_first * 16;
+            cx.out_seg = reinterpret_cast<act_t*>(out) + cx.out_off;
             cx.ldc = ep.ldc;
             cx.rows_valid = M - (m0 + quarter * 32);
             cx.bias_s = bias_s;
             float row_sum = 0.f, row_sumsq = 0.f;
             switch (s_cnt) {  // warp-uniform
-                case 4: epilogue_slabs<4, kStaged, kAct, kLn, kRes>(cx, ep, out, row_sum, row_sumsq); break;
-                case 3: epilogue_slabs<3, kStaged, kAct, kLn, kRes>(cx, ep, out, row_sum, row_sumsq); break;
-                case 2: epilogue_slabs<2, kStaged, kAct, kLn, kRes>(cx, ep, out, row_sum, row_sumsq); break;
-                case 1: epilogue_slabs<1, kStaged, kAct, kLn, kRes>(cx, ep, out, row_sum, row_sumsq); break;
+                case 4: epilogue_slabs<4, kStaged, kAct, kLn, kRes, kTF32 != 0>(cx, ep, out, row_sum, row_sumsq); break;
+                case 3: epilogue_slabs<3, kStaged, kAct, kLn, kRes, kTF32 != 0>(cx, ep, out, row_sum, row_sumsq); break;
+                case 2: epilogue_slabs<2, kStaged, kAct, kLn, kRes, kTF32 != 0>(cx, ep, out, row_sum, row_sumsq); break;
+                case 1: epilogue_slabs<1, kStaged, kAct, kLn, kRes, kTF32 != 0>(cx, ep, out, row_sum, row_sumsq); break;
                 default:  // narrow tiles (block_n < 64): this warp owns no slab
                     tc_fence_before();
                     __syncwarp();
@@ -1221,18 +1268,22 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch
     static bool const allow_staged_res = !std::getenv("DLIMG_B200_GEMM_DIRECT_RESIDUAL");  // A/B switch
     bool const res_ok = !ep.residual || (allow_staged_res && ep.act == ACT_NONE && !ep.ln_stats);
-    bool const staged = allow_staged && !tf32 && res_ok && !ep.row_map && !ep.out_f32 && block_n >= 64 &&
-                        (ep.act == ACT_NONE || ep.act == ACT_GELU) && (!ep.stats_out || (ep.act == ACT_NONE && !ep.ln_stats)) && N <= 2048;
+    static bool const allow_staged_f32 = !std::getenv("DLIMG_B200_GEMM_DIRECT_F32");  // A/B switch
+    bool const staged_f32 = allow_staged && allow_staged_f32 && tf32 && ep.out_f32 && !ep.residual && !ep.row_map && !ep.stats_out &&
+                            !ep.ln_stats && block_n >= 64 && N <= 2048;
+    bool const staged = staged_f32 ||
+                        (allow_staged && !tf32 && res_ok && !ep.row_map && !ep.out_f32 && block_n >= 64 &&
+                         (ep.act == ACT_NONE || ep.act == ACT_GELU) && (!ep.stats_out || (ep.act == ACT_NONE && !ep.ln_stats)) && N <= 2048);
     if (ep.ln_stats && (!staged || !ep.bias))
         fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue) and a bias");
     if (ep.stats_out && (ep.act != ACT_NONE || ep.row_map || ep.out_f32 || block_n < 64))
         fail("GEMM: row statistics are produced by the 16-bit epilogues without activation only");
     int const bias_bytes = staged ? (int)round_up64((int64_t)N * 4, 1024) : 0;
-    SmemPlan const sp = plan_smem(block_n, staged, ep.stats_out != nullptr, bias_bytes);
+    SmemPlan const sp = plan_smem(block_n, staged, ep.stats_out != nullptr, bias_bytes, tf32);
     DLIMG_ASSERT(sp.stages >= 2);
     using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, int, void*, EpiParams, ConvParams);
     Kernel kernel;
-    if (tf32) kernel = gemm_tc_kernel<1, false>;
+    if (tf32) kernel = staged ? gemm_tc_kernel<1, true> : gemm_tc_kernel<1, false>;
     else if (!staged) kernel = gemm_tc_kernel<0, false>;
     else if (ep.residual || ep.stats_out) kernel = gemm_tc_kernel<0, true, ACT_NONE, false, true>;
     else if (ep.ln_stats) kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, true> : gemm_tc_kernel<0, true, ACT_NONE, true>;
