@@ -316,10 +316,11 @@ class Environment:
 
     def compute_masks_batch(self, segs: Sequence["Segmentation"], prompts: Sequence, multi: bool = False,
                             masks_out: Sequence[int] = None, ious_out: int = 0, host_out: Sequence[np.ndarray] = None,
-                            host_ious: np.ndarray = None):
+                            host_ious: np.ndarray = None, host_async: bool = False):
         """Host mode (masks_out None): returns (list of uint8 arrays (n, H, W), float32 array (count, n)); pass
         `host_out` / `host_ious` to have the results written into your own (ideally page-locked) arrays instead of
-        freshly allocated pageable ones.
+        freshly allocated pageable ones; with `host_async` the call returns once the work is queued and the arrays are
+        complete after `Environment.synchronize()` (downloads then overlap the decoder of the following calls).
         Device mode: masks_out = device addresses (one per prompt, n*W*H bytes), ious_out = device address."""
         cnt = len(prompts)
         n = 3 if multi else 1
@@ -332,7 +333,7 @@ class Environment:
             ious = host_ious if host_ious is not None else np.zeros((cnt, n), np.float32)
             assert ious.dtype == np.float32 and ious.size == cnt * n
             _check(ext().compute_masks_batch(self._h, harr, parr, cnt, int(multi), ptrs,
-                                             ctypes.c_void_p(ious.ctypes.data), 0))
+                                             ctypes.c_void_p(ious.ctypes.data), 2 if host_async else 0))
             return outs, ious
         ptrs = (ctypes.c_void_p * cnt)(*[int(a) for a in masks_out])
         _check(ext().compute_masks_batch(self._h, harr, parr, cnt, int(multi), ptrs, ctypes.c_void_p(ious_out), 1))

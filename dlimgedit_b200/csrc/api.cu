@@ -140,7 +140,7 @@ dlimg_Result ext_compute_masks_batch(dlimg_Environment env, dlimg_Segmentation c
             size_t const plane = (size_t)impl[(size_t)i]->width() * impl[(size_t)i]->height();
             for (int m = 0; m < n; ++m) planes[(size_t)i * n + m] = masks_out[i] + plane * m;
         }
-        to_impl(env).compute_masks_batch(impl.data(), prompts, count, multi != 0, planes.data(), ious_out, on_device != 0);
+        to_impl(env).compute_masks_batch(impl.data(), prompts, count, multi != 0, planes.data(), ious_out, on_device);
     });
 }
 

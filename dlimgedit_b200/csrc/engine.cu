@@ -359,8 +359,9 @@ void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, boo
 }
 
 void EnvironmentImpl::compute_masks_batch(SegmentationImpl* const* segs, dlimg_b200_Prompt const* prompts, int count, bool multi,
-                                          uint8_t* const* planes_out, float* ious_out, bool on_device) {
+                                          uint8_t* const* planes_out, float* ious_out, int placement) {
     if (count <= 0) return;
+    bool const on_device = placement == 1, async_host = placement == 2;
     std::lock_guard<std::mutex> lock(mutex_);
     bind_device();
     cudaStream_t const s = stream();
@@ -368,7 +369,6 @@ void EnvironmentImpl::compute_masks_batch(SegmentationImpl* const* segs, dlimg_b
     DecoderWorkspace& ws = decoder_ws();
     int const n = multi ? 3 : 1;
     int const kHostGroup = env_int("DLIMG_B200_HOST_GROUP", 256, 1, 256);  // splitting a call into smaller decoder groups to overlap downloads costs more than it hides (18.3k -> 9.5k masks/s at 16), so the default keeps whole groups
-    int host_group = 0;
     int i = 0;
     while (i < count) {
         SegmentationImpl* seg = segs[i];
@@ -427,8 +427,8 @@ void EnvironmentImpl::compute_masks_batch(SegmentationImpl* const* segs, dlimg_b
             prepost::mask_postprocess(s, ws.low.get(), 65536, ws.plane_index.get(), planes, seg->size_.w, seg->size_.h, W, H,
                                       plane_ptrs_.get());
         } else {
-            int const flip = host_group & 1;
-            ++host_group;
+            int const flip = host_group_ & 1;
+            ++host_group_;
             if (mask_out_[flip].size() < plane_bytes * planes) {
                 synchronize();
                 mask_out_[flip].allocate(plane_bytes * (size_t)std::max(planes, std::min(max_prompts_, kHostGroup) * 3));
@@ -453,7 +453,7 @@ void EnvironmentImpl::compute_masks_batch(SegmentationImpl* const* segs, dlimg_b
         }
         i = j;
     }
-    if (!on_device) {  // the caller's host buffers are complete when the call returns
+    if (!on_device && !async_host) {  // the caller's host buffers are complete when the call returns
         CUDA_CHECK(cudaStreamSynchronize(s));
         CUDA_CHECK(cudaStreamSynchronize(copy_out_));
     }
@@ -581,10 +581,10 @@ void SegmentationImpl::compute_mask(int const* point, int const* region, uint8_t
     bool const is_single = out_masks[1] == nullptr;  // reference segmentation.cpp:154
     if (is_single) {
         DLIMG_ASSERT(out_masks[0] != nullptr);
-        env_.compute_masks_batch(&self, &pr, 1, false, out_masks, nullptr, false);  // accuracy is not written (:162-165)
+        env_.compute_masks_batch(&self, &pr, 1, false, out_masks, nullptr, 0);  // accuracy is not written (:162-165)
     } else {
         for (int i = 0; i < 3; ++i) DLIMG_ASSERT(out_masks[i] != nullptr);
-        env_.compute_masks_batch(&self, &pr, 1, true, out_masks, out_accuracy, false);
+        env_.compute_masks_batch(&self, &pr, 1, true, out_masks, out_accuracy, 0);
     }
 }
 

@@ -80,7 +80,7 @@ class EnvironmentImpl {
     void process_batch(dlimg_ImageView const* views, int count, bool on_device, SegmentationImpl** out);
     // Prompts -> masks.  See dlimg_b200_Ext::compute_masks_batch.
     void compute_masks_batch(SegmentationImpl* const* segs, dlimg_b200_Prompt const* prompts, int count, bool multi,
-                             uint8_t* const* masks_out, float* ious_out, bool on_device);
+                             uint8_t* const* masks_out, float* ious_out, int placement /* 0 host, 1 device, 2 host asynchronous */);
     void low_res_logits(SegmentationImpl& seg, dlimg_b200_Prompt const& prompt, float* logits_host, float* iou_host);
 
     // Stand-alone stages (device pointers)
@@ -139,6 +139,7 @@ class EnvironmentImpl {
     DeviceBuffer<uint8_t> mask_out_[2];
     cudaEvent_t mask_ready_ = nullptr, mask_free_[2] = {nullptr, nullptr};
     bool mask_used_[2] = {false, false};
+    int host_group_ = 0;  // alternates the two device-side mask staging buffers across prompt groups AND calls
     DeviceBuffer<uint8_t*> plane_ptrs_;
     bool use_graphs_ = true;  // $DLIMG_B200_GRAPHS=0 forces eager launches
     struct EncodeGraph { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; };

@@ -144,7 +144,9 @@ struct dlimg_b200_Ext {
     /* Answer `count` prompts; prompt i refers to segs[i] (handles may repeat).  multi == 0: one mask
      * per prompt (best of tokens 1..3 by predicted IoU, as the single-mask decoder graph does);
      * multi == 1: three masks per prompt (tokens 1..3).  masks_out[i] points at n*W_i*H_i bytes
-     * (n = multi ? 3 : 1) on the device (masks_on_device != 0) or host.  ious_out: count*n floats
+     * (n = multi ? 3 : 1) on the device (masks_on_device == 1) or host (0: complete when the call returns;
+     * 2: asynchronous -- the downloads run on the library's copy-out stream under the decoder of the following
+     * calls and the buffers, ideally page-locked, are complete after `synchronize`).  ious_out: count*n floats
      * (same memory space as masks), may be NULL. */
     dlimg_Result (*compute_masks_batch)(dlimg_Environment, dlimg_Segmentation const* segs,
                                         dlimg_b200_Prompt const* prompts, int count, int multi,

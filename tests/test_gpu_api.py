@@ -106,3 +106,26 @@ def test_async_embedding_read_matches_blocking(env):
     for seg, o in zip(segs, outs):
         assert np.array_equal(o.numpy(), seg.embedding())
     assert not np.array_equal(outs[0].numpy(), outs[1].numpy())
+
+
+def test_async_host_masks_match_blocking(env):
+    """masks_on_device = 2: host masks whose downloads overlap the following calls; complete after synchronize()."""
+    import torch
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (600, 800, 3), dtype=np.uint8)
+    seg = dl.Segmentation.process(dl.ImageView(img, channels=dl.Channels.rgb), env)
+    prompts = [dl.Point(int(rng.integers(0, 800)), int(rng.integers(0, 600))) for _ in range(12)]
+    ref, ref_ious = env.compute_masks_batch([seg] * 12, prompts, multi=False)
+    sets = []
+    for k in range(3):  # three calls in flight into three sets of page-locked buffers
+        hm = [torch.empty(1, 600, 800, dtype=torch.uint8).pin_memory() for _ in range(12)]
+        hi = torch.empty(12, 1, dtype=torch.float32).pin_memory()
+        env.compute_masks_batch([seg] * 12, prompts, multi=False, host_out=[m.numpy() for m in hm], host_ious=hi.numpy(),
+                                host_async=True)
+        sets.append((hm, hi))
+    env.synchronize()
+    for hm, hi in sets:
+        for a, b in zip(hm, ref):
+            assert np.array_equal(a.numpy(), b)
+        assert np.array_equal(hi.numpy(), ref_ious)
+    seg.close()
