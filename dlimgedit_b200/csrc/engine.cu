@@ -254,7 +254,7 @@ void EnvironmentImpl::encode_chunk(enc::ImageDesc const* host_descs, int batch, 
         m.encode(s, ws, descs_.get(), batch, size.w, size.h, channels, emb_out, tap, emb_nchw_out);
         return;
     }
-    // The ~130 launches of one encoder pass are captured once per (batch, extent, channel order) into a CUDA
+    // The ~70 launches of one encoder pass are captured once per (batch, extent, channel order) into a CUDA
     // graph: every pointer it uses (workspace, weights, descriptor table, tensor maps) is stable, only the
     // descriptor *contents* (uploaded above) and the destination of the embedding change per call -- so the graph ends
     // in front of the final LayerNorm2d, which is launched behind it straight into the caller's store (both layouts).
