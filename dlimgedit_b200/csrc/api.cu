@@ -94,10 +94,7 @@ dlimg_Api api_;
 
 // ---- part 2 -----------------------------------------------------------------------------------
 dlimg_Result ext_set_stream(dlimg_Environment env, void* stream) {
-    return try_([=] {
-        std::lock_guard<std::mutex> lock(to_impl(env).mutex());
-        to_impl(env).set_stream(static_cast<cudaStream_t>(stream));
-    });
+    return try_([=] { to_impl(env).set_stream(static_cast<cudaStream_t>(stream)); });
 }
 
 dlimg_Result ext_synchronize(dlimg_Environment env) {
@@ -106,11 +103,10 @@ dlimg_Result ext_synchronize(dlimg_Environment env) {
     });
 }
 
-dlimg_Result ext_get_stats(dlimg_Environment, dlimg_b200_Stats* out) {
+dlimg_Result ext_get_stats(dlimg_Environment env, dlimg_b200_Stats* out) {
     return try_([=] {
-        out->kernel_launches = g_kernel_launches.load();
-        out->h2d_bytes = g_h2d_bytes.load();
-        out->d2h_bytes = g_d2h_bytes.load();
+        DLIMG_ASSERT(env && out);
+        to_impl(env).stats(*out);
     });
 }
 
@@ -170,16 +166,11 @@ dlimg_Result ext_threshold_mask(dlimg_Environment env, float const* logits, int 
 }
 
 dlimg_Result ext_profile_enable(dlimg_Environment env, int on) {
-    return try_([=] {
-        std::lock_guard<std::mutex> lock(to_impl(env).mutex());
-        Profiler::get().enable(on != 0);
-    });
+    return try_([=] { to_impl(env).profile_enable(on != 0); });
 }
 dlimg_Result ext_profile_read(dlimg_Environment env, dlimg_b200_ProfileEntry* out, int capacity, int* count) {
     return try_([=] {
-        std::lock_guard<std::mutex> lock(to_impl(env).mutex());
-        to_impl(env).bind_device();
-        auto const totals = Profiler::get().collect();
+        auto const totals = to_impl(env).profile_collect();
         int n = 0;
         for (int c = 0; c < CAT_COUNT && n < capacity; ++c) {
             if (!totals[(size_t)c].launches) continue;

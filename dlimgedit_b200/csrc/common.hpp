@@ -65,11 +65,16 @@ constexpr int kLowRes = 256;       // low-resolution mask size
 
 #include <atomic>
 namespace dlimg {
-// Process-wide tally of kernels launched by this library (reported through dlimg_b200_Ext::get_stats).
-extern std::atomic<uint64_t> g_kernel_launches;
-extern std::atomic<uint64_t> g_h2d_bytes;
-extern std::atomic<uint64_t> g_d2h_bytes;
-inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+// Kernels launched and bytes copied by this library, per environment (reported through dlimg_b200_Ext::get_stats).
+// The engine binds the environment a call belongs to to the calling thread (EnvironmentImpl::Scope); launches outside
+// any environment (model load, the test-only debug table) go to a process-wide fallback.
+struct EnvCounters {
+    std::atomic<uint64_t> kernel_launches{0}, h2d_bytes{0}, d2h_bytes{0};
+};
+extern EnvCounters g_unbound_counters;
+extern thread_local EnvCounters* tl_counters;
+inline EnvCounters& counters() { return tl_counters ? *tl_counters : g_unbound_counters; }
+inline void count_launch(uint64_t n = 1) { counters().kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 // Launch-configuration errors surface immediately; execution errors at the next synchronising call.
 #define KERNEL_CHECK()                                                                               \
     do {                                                                                             \

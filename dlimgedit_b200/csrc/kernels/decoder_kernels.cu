@@ -58,21 +58,6 @@ __global__ void __launch_bounds__(256) dense_pe_kernel(float const* __restrict__
     pos[(size_t)tok * kDim + j] = pe_feature(cx, cy, G, j);
 }
 
-__global__ void embed_prepare_kernel(float const* __restrict__ emb, float const* __restrict__ no_mask,
-                                     float const* __restrict__ pos, int64_t total4, float* __restrict__ keys0,
-                                     float* __restrict__ kpe0) {
-    int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total4) return;
-    int const c4 = (int)(t % (kDim / 4));
-    int64_t const row = t / (kDim / 4);
-    float4 const e = reinterpret_cast<float4 const*>(emb)[t];
-    float4 const n = reinterpret_cast<float4 const*>(no_mask)[c4];
-    float4 const q = reinterpret_cast<float4 const*>(pos)[(row % kImgTokens) * (kDim / 4) + c4];
-    float4 const k = make_float4(e.x + n.x, e.y + n.y, e.z + n.z, e.w + n.w);
-    reinterpret_cast<float4*>(keys0)[t] = k;
-    reinterpret_cast<float4*>(kpe0)[t] = make_float4(k.x + q.x, k.y + q.y, k.z + q.z, k.w + q.w);
-}
-
 // ---------------------------------------------------------------------------------------------
 constexpr int kLinRows = 8;   // rows per block
 constexpr int kLinWarps = 8;
@@ -156,108 +141,14 @@ __global__ void __launch_bounds__(256) token_self_attention_kernel(float const* 
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int kT2iThreads = 256;
-constexpr size_t kT2iSmem = sizeof(float) * ((size_t)kTokens * kImgTokens + kTokens * 16 + 8 * kTokens + kTokens + 2 * kTokens * 16);
-
-__global__ void __launch_bounds__(kT2iThreads) t2i_attention_kernel(float const* __restrict__ q, float const* __restrict__ K,
-                                                                    float const* __restrict__ V, int64_t kv_stride,
-                                                                    float* __restrict__ out) {
-    extern __shared__ float sm[];
-    float* S = sm;                                  // [7][4096]
-    float* qs = S + kTokens * kImgTokens;           // [7][16]
-    float* red = qs + kTokens * 16;                 // [8 warps][7]
-    float* stat = red + 8 * kTokens;                // [7]
-    float* part = stat + kTokens;                   // [2][7*16]
-    int const p = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
-    int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float const* Kp = K + (size_t)p * kv_stride + h * 16;
-    float const* Vp = V + (size_t)p * kv_stride + h * 16;
-    if (tid < kTokens * 16) qs[tid] = q[((size_t)p * kTokens + tid / 16) * 128 + h * 16 + (tid % 16)];
-    __syncthreads();
-    // phase A: scores + running max
-    float mx[kTokens];
-#pragma unroll
-    for (int t = 0; t < kTokens; ++t) mx[t] = -INFINITY;
-    for (int i = tid; i < kImgTokens; i += kT2iThreads) {
-        float kv[16];
-        float4 const* k4 = reinterpret_cast<float4 const*>(Kp + (size_t)i * 128);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float4 const x = k4[c];
-            kv[4 * c] = x.x; kv[4 * c + 1] = x.y; kv[4 * c + 2] = x.z; kv[4 * c + 3] = x.w;
-        }
-#pragma unroll
-        for (int t = 0; t < kTokens; ++t) {
-            float a = 0.f;
-#pragma unroll
-            for (int d = 0; d < 16; ++d) a = fmaf(qs[t * 16 + d], kv[d], a);
-            a *= 0.25f;  // 1/sqrt(16)
-            S[t * kImgTokens + i] = a;
-            mx[t] = fmaxf(mx[t], a);
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < kTokens; ++t) {
-        float const m = warp_max(mx[t]);
-        if (lane == 0) red[warp * kTokens + t] = m;
-    }
-    __syncthreads();
-    if (tid < kTokens) {
-        float m = red[tid];
-        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w * kTokens + tid]);
-        stat[tid] = m;
-    }
-    __syncthreads();
-    // phase B: exponentials + sums
-    float sum[kTokens];
-#pragma unroll
-    for (int t = 0; t < kTokens; ++t) sum[t] = 0.f;
-    for (int i = tid; i < kImgTokens; i += kT2iThreads) {
-#pragma unroll
-        for (int t = 0; t < kTokens; ++t) {
-            float const e = expf(S[t * kImgTokens + i] - stat[t]);
-            S[t * kImgTokens + i] = e;
-            sum[t] += e;
-        }
-    }
-    __syncthreads();  // everyone has read stat[] (max) before it is overwritten with the sums
-#pragma unroll
-    for (int t = 0; t < kTokens; ++t) {
-        float const v = warp_sum(sum[t]);
-        if (lane == 0) red[warp * kTokens + t] = v;
-    }
-    __syncthreads();
-    if (tid < kTokens) {
-        float v = 0.f;
-        for (int w = 0; w < 8; ++w) v += red[w * kTokens + tid];
-        stat[tid] = v;
-    }
-    __syncthreads();
-    // phase C: out[t][d] = sum_i P[t][i] V[i][d] / sum[t]; two halves of the keys in parallel
-    if (tid < 2 * kTokens * 16) {
-        int const half = tid / (kTokens * 16), td = tid % (kTokens * 16);
-        int const t = td / 16, d = td % 16;
-        float a = 0.f;
-        int const i0 = half * (kImgTokens / 2);
-        float const* Srow = S + t * kImgTokens;
-#pragma unroll 4
-        for (int i = i0; i < i0 + kImgTokens / 2; ++i) a = fmaf(Srow[i], __ldg(Vp + (size_t)i * 128 + d), a);
-        part[half * kTokens * 16 + td] = a;
-    }
-    __syncthreads();
-    if (tid < kTokens * 16) {
-        int const t = tid / 16, d = tid % 16;
-        out[((size_t)p * kTokens + t) * 128 + h * 16 + d] = (part[tid] + part[kTokens * 16 + tid]) / stat[t];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// One thread per (image token, head); the 7 token keys / values of the prompt sit in shared memory as
-// [token][d / 4][head] float4, so the eight heads handled by neighbouring lanes read 128 contiguous bytes (the
-// [token][head][d] order put them 64 bytes apart: 4-way bank conflicts on every one of the 224 loads per thread).
-__global__ void __launch_bounds__(256) i2t_attention_kernel(float const* __restrict__ Q, int64_t q_stride,
+// Image -> token attention core, one thread per (image token, head).  Q rows are 16-bit (the [K|V|Q] projection of the
+// image stream, row pitch q_pitch elements); the 7 token keys / values of the prompt sit in shared memory as
+// [token][d / 4][head] float4, so the eight heads handled by neighbouring lanes read 128 contiguous bytes.  Output:
+// 16-bit (P, 4096, 128), the A operand of the out-projection GEMM.
+__global__ void __launch_bounds__(256) i2t_attention_kernel(act_t const* __restrict__ Q, act_t const* const* __restrict__ Qptrs,
+                                                            int64_t q_prompt_stride, int q_pitch, int q_off,
                                                             float const* __restrict__ kt, float const* __restrict__ vt,
-                                                            float* __restrict__ out) {
+                                                            act_t* __restrict__ out) {
     __shared__ float4 ks[kTokens * 4 * 8];
     __shared__ float4 vs[kTokens * 4 * 8];
     int const p = blockIdx.y;
@@ -271,10 +162,20 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(float const* __restr
     __syncthreads();
     int const idx = blockIdx.x * blockDim.x + threadIdx.x;  // (token, head)
     int const i = idx >> 3, h = idx & 7;
-    float4 qv[4];
-    float4 const* q4 = reinterpret_cast<float4 const*>(Q + (size_t)p * q_stride + (size_t)i * 128 + h * 16);
+    act_t const* qbase = (Qptrs ? Qptrs[p] : Q + (size_t)p * q_prompt_stride) + q_off;
+    float qv[16];
+    {
+        uint4 const* q4 = reinterpret_cast<uint4 const*>(qbase + (size_t)i * q_pitch + h * 16);
+        uint4 const a = __ldg(q4), b = __ldg(q4 + 1);
+        act2_t const* ha = reinterpret_cast<act2_t const*>(&a);
+        act2_t const* hb = reinterpret_cast<act2_t const*>(&b);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) qv[c] = q4[c];
+        for (int j = 0; j < 4; ++j) {
+            float2 const fa = act22f2(ha[j]), fb = act22f2(hb[j]);
+            qv[2 * j] = fa.x; qv[2 * j + 1] = fa.y;
+            qv[8 + 2 * j] = fb.x; qv[8 + 2 * j + 1] = fb.y;
+        }
+    }
     float s[kTokens];
     float mx = -INFINITY;
 #pragma unroll
@@ -283,10 +184,10 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(float const* __restr
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             float4 const k4 = ks[(t * 4 + c) * 8 + h];
-            a = fmaf(qv[c].x, k4.x, a);
-            a = fmaf(qv[c].y, k4.y, a);
-            a = fmaf(qv[c].z, k4.z, a);
-            a = fmaf(qv[c].w, k4.w, a);
+            a = fmaf(qv[4 * c + 0], k4.x, a);
+            a = fmaf(qv[4 * c + 1], k4.y, a);
+            a = fmaf(qv[4 * c + 2], k4.z, a);
+            a = fmaf(qv[4 * c + 3], k4.w, a);
         }
         s[t] = a * 0.25f;
         mx = fmaxf(mx, s[t]);
@@ -298,24 +199,73 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(float const* __restr
         sum += s[t];
     }
     float const inv = 1.0f / sum;
-    float4 o[4];
+    float o[16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 16; ++c) o[c] = 0.f;
 #pragma unroll
     for (int t = 0; t < kTokens; ++t) {
         float const w = s[t] * inv;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             float4 const v4 = vs[(t * 4 + c) * 8 + h];
-            o[c].x = fmaf(w, v4.x, o[c].x);
-            o[c].y = fmaf(w, v4.y, o[c].y);
-            o[c].z = fmaf(w, v4.z, o[c].z);
-            o[c].w = fmaf(w, v4.w, o[c].w);
+            o[4 * c + 0] = fmaf(w, v4.x, o[4 * c + 0]);
+            o[4 * c + 1] = fmaf(w, v4.y, o[4 * c + 1]);
+            o[4 * c + 2] = fmaf(w, v4.z, o[4 * c + 2]);
+            o[4 * c + 3] = fmaf(w, v4.w, o[4 * c + 3]);
         }
     }
-    float4* o4 = reinterpret_cast<float4*>(out + ((size_t)p * kImgTokens + i) * 128 + h * 16);
+    uint4 ov[2];
+    act2_t* oh = reinterpret_cast<act2_t*>(ov);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) o4[c] = o[c];
+    for (int j = 0; j < 8; ++j) oh[j] = f22act2(o[2 * j], o[2 * j + 1]);
+    uint4* o4 = reinterpret_cast<uint4*>(out + ((size_t)p * kImgTokens + i) * 128 + h * 16);
+    o4[0] = ov[0];
+    o4[1] = ov[1];
+}
+
+// keys <- LayerNorm_256(x + res) on the 16-bit image stream (eps 1e-5, fp32 statistics): one warp per row, 16-byte
+// loads.  The residual of prompt p is res_ptrs[p] (layer 0: the image's own prompt-independent keys) or
+// res + p * 4096 * 256.  In-place (out == res) is allowed: a row is read and written by the same lane.
+__global__ void __launch_bounds__(256) layernorm256_img_kernel(act_t const* __restrict__ x, act_t const* res,
+                                                               act_t const* const* __restrict__ res_ptrs, int64_t rows,
+                                                               float const* __restrict__ gamma, float const* __restrict__ beta,
+                                                               act_t* out) {
+    int64_t const row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int const lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    int64_t const p = row / kImgTokens, tok = row - p * kImgTokens;
+    act_t const* r = (res_ptrs ? res_ptrs[p] : res + p * kImgTokens * kDim) + tok * kDim;
+    uint4 const xa = __ldg(reinterpret_cast<uint4 const*>(x + row * kDim) + lane);
+    uint4 const ra = *(reinterpret_cast<uint4 const*>(r) + lane);
+    act2_t const* xh = reinterpret_cast<act2_t const*>(&xa);
+    act2_t const* rh = reinterpret_cast<act2_t const*>(&ra);
+    float v[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float2 const a = act22f2(xh[j]), b = act22f2(rh[j]);
+        v[2 * j] = a.x + b.x;
+        v[2 * j + 1] = a.y + b.y;
+        sum += v[2 * j] + v[2 * j + 1];
+    }
+    float const mean = warp_sum(sum) * (1.0f / kDim);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float const d = v[i] - mean;
+        var = fmaf(d, d, var);
+    }
+    float const rstd = rsqrtf(warp_sum(var) * (1.0f / kDim) + 1e-5f);
+    float4 const g0 = __ldg(reinterpret_cast<float4 const*>(gamma) + 2 * lane), g1 = __ldg(reinterpret_cast<float4 const*>(gamma) + 2 * lane + 1);
+    float4 const b0 = __ldg(reinterpret_cast<float4 const*>(beta) + 2 * lane), b1 = __ldg(reinterpret_cast<float4 const*>(beta) + 2 * lane + 1);
+    float const gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float const bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint4 ov;
+    act2_t* oh = reinterpret_cast<act2_t*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        oh[j] = f22act2((v[2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j], (v[2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]);
+    *(reinterpret_cast<uint4*>(out + row * kDim) + lane) = ov;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -373,25 +323,53 @@ __global__ void __launch_bounds__(256) layernorm256_kernel(float const* x, float
     }
 }
 
-__global__ void __launch_bounds__(256) layernorm64_gelu_kernel(float* __restrict__ x, int64_t rows,
+// In-place LayerNorm2d over groups of 64 channels (eps 1e-6) + exact GELU on 16-bit rows of 64: eight lanes per row
+// (16 bytes each), four rows per warp.
+__global__ void __launch_bounds__(256) layernorm64_gelu_kernel(act_t* __restrict__ x, int64_t rows,
                                                                float const* __restrict__ gamma,
                                                                float const* __restrict__ beta) {
-    int64_t const row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    int const lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    float2 v = reinterpret_cast<float2*>(x + row * 64)[lane];
-    float const mean = warp_sum(v.x + v.y) * (1.0f / 64.0f);
-    float const dx = v.x - mean, dy = v.y - mean;
-    float const rstd = rsqrtf(warp_sum(dx * dx + dy * dy) * (1.0f / 64.0f) + 1e-6f);
-    float2 const g = reinterpret_cast<float2 const*>(gamma)[lane];
-    float2 const b = reinterpret_cast<float2 const*>(beta)[lane];
-    v.x = gelu_erf(dx * rstd * g.x + b.x);
-    v.y = gelu_erf(dy * rstd * g.y + b.y);
-    reinterpret_cast<float2*>(x + row * 64)[lane] = v;
+    int64_t const row = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 + ((threadIdx.x & 31) >> 3);
+    int const l8 = threadIdx.x & 7;
+    bool const ok = row < rows;
+    uint4 xa = make_uint4(0, 0, 0, 0);
+    if (ok) xa = *(reinterpret_cast<uint4 const*>(x + row * 64) + l8);
+    act2_t const* xh = reinterpret_cast<act2_t const*>(&xa);
+    float v[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float2 const a = act22f2(xh[j]);
+        v[2 * j] = a.x;
+        v[2 * j + 1] = a.y;
+        sum += a.x + a.y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float const mean = sum * (1.0f / 64.0f);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float const d = v[i] - mean;
+        var = fmaf(d, d, var);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    float const rstd = rsqrtf(var * (1.0f / 64.0f) + 1e-6f);
+    float4 const g0 = __ldg(reinterpret_cast<float4 const*>(gamma) + 2 * l8), g1 = __ldg(reinterpret_cast<float4 const*>(gamma) + 2 * l8 + 1);
+    float4 const b0 = __ldg(reinterpret_cast<float4 const*>(beta) + 2 * l8), b1 = __ldg(reinterpret_cast<float4 const*>(beta) + 2 * l8 + 1);
+    float const gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float const bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint4 ov;
+    act2_t* oh = reinterpret_cast<act2_t*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        oh[j] = f22act2(gelu_erf((v[2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j]),
+                        gelu_erf((v[2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]));
+    if (ok) *(reinterpret_cast<uint4*>(x + row * 64) + l8) = ov;
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mask_dot_kernel(float const* __restrict__ hyper, float const* __restrict__ up2,
+__global__ void __launch_bounds__(256) mask_dot_kernel(float const* __restrict__ hyper, act_t const* __restrict__ up2,
                                                        float* __restrict__ low) {
     __shared__ float hs[4 * 32];
     int const p = blockIdx.y;
@@ -402,18 +380,21 @@ __global__ void __launch_bounds__(256) mask_dot_kernel(float const* __restrict__
     int const y = Y >> 2, dy = (Y >> 1) & 1, ey = Y & 1;
     int const x = X >> 2, dx = (X >> 1) & 1, ex = X & 1;
     size_t const row = ((size_t)(y * 64 + x) * 4 + dy * 2 + dx);
-    float4 const* u4 = reinterpret_cast<float4 const*>(up2 + ((size_t)p * 16384 + row) * 128 + (ey * 2 + ex) * 32);
+    uint4 const* u4 = reinterpret_cast<uint4 const*>(up2 + ((size_t)p * 16384 + row) * 128 + (ey * 2 + ex) * 32);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float4 const u = __ldg(u4 + c);
+    for (int c = 0; c < 4; ++c) {
+        uint4 const u = __ldg(u4 + c);
+        act2_t const* uh = reinterpret_cast<act2_t const*>(&u);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            float const* hm = hs + m * 32 + c * 4;
-            acc[m] = fmaf(u.x, hm[0], acc[m]);
-            acc[m] = fmaf(u.y, hm[1], acc[m]);
-            acc[m] = fmaf(u.z, hm[2], acc[m]);
-            acc[m] = fmaf(u.w, hm[3], acc[m]);
+        for (int j = 0; j < 4; ++j) {
+            float2 const f = act22f2(uh[j]);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                float const* hm = hs + m * 32 + c * 8 + 2 * j;
+                acc[m] = fmaf(f.x, hm[0], acc[m]);
+                acc[m] = fmaf(f.y, hm[1], acc[m]);
+            }
         }
     }
 #pragma unroll
@@ -456,6 +437,11 @@ __global__ void __launch_bounds__(256) token_mlp3_kernel(float const* __restrict
     layer(heads.w[m][2], heads.b[m][2], n_out, xa, dst, false, 0);
 }
 
+__global__ void f32_to_act_kernel(float const* __restrict__ in, int64_t n, act_t* __restrict__ out) {
+    int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = f2act(in[i]);
+}
+
 __global__ void select_masks_kernel(float const* __restrict__ iou, int P, int multi, int* __restrict__ plane_index,
                                     float* __restrict__ iou_out) {
     int const p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -494,14 +480,6 @@ void dense_pe(cudaStream_t s, float const* gaussian, float* pos) {
     KERNEL_CHECK();
 }
 
-void embed_prepare(cudaStream_t s, float const* emb, float const* no_mask, float const* pos, int64_t rows, float* keys0,
-                   float* kpe0) {
-    ProfScope prof(s, CAT_DEC_MISC);
-    int64_t const total4 = rows * (kDim / 4);
-    embed_prepare_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, s>>>(emb, no_mask, pos, total4, keys0, kpe0);
-    KERNEL_CHECK();
-}
-
 void linear_small(cudaStream_t s, float const* x, int64_t x_stride, float const* x2, int64_t x2_stride, int rows, int K,
                   float const* W, float const* b, int N, bool relu, float* y, int64_t y_stride) {
     ProfScope prof(s, CAT_DEC_LINEAR);
@@ -523,23 +501,19 @@ void token_self_attention(cudaStream_t s, float const* q, float const* k, float 
     KERNEL_CHECK();
 }
 
-void token_to_image_attention_twopass(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride, int P,
-                              float* out) {
-    ProfScope prof(s, CAT_DEC_ATTN);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(t2i_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT2iSmem));
-        attr_set = true;
-    }
-    t2i_attention_kernel<<<P * kHeads, kT2iThreads, kT2iSmem, s>>>(q, K, V, kv_stride, out);
+void image_to_token_attention(cudaStream_t s, act_t const* Q, act_t const* const* Qptrs, int64_t q_prompt_stride, int q_pitch,
+                              int q_off, float const* kt, float const* vt, int P, act_t* out) {
+    ProfScope prof(s, CAT_DEC_ATTN, 4.0 * P * kTokens * kImgTokens * 128, (double)P * kImgTokens * 128 * 4);
+    dim3 grid(kImgTokens * kHeads / 256, P);
+    i2t_attention_kernel<<<grid, 256, 0, s>>>(Q, Qptrs, q_prompt_stride, q_pitch, q_off, kt, vt, out);
     KERNEL_CHECK();
 }
 
-void image_to_token_attention(cudaStream_t s, float const* Q, int64_t q_stride, float const* kt, float const* vt, int P,
-                              float* out) {
-    ProfScope prof(s, CAT_DEC_ATTN);
-    dim3 grid(kImgTokens * kHeads / 256, P);
-    i2t_attention_kernel<<<grid, 256, 0, s>>>(Q, q_stride, kt, vt, out);
+void layernorm256_img(cudaStream_t s, act_t const* x, act_t const* res, act_t const* const* res_ptrs, int P, float const* gamma,
+                      float const* beta, act_t* out) {
+    int64_t const rows = (int64_t)P * kImgTokens;
+    ProfScope prof(s, CAT_DEC_NORM, 0, (double)rows * kDim * 6);
+    layernorm256_img_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, s>>>(x, res, res_ptrs, rows, gamma, beta, out);
     KERNEL_CHECK();
 }
 
@@ -553,14 +527,14 @@ void layernorm256(cudaStream_t s, float const* x, float const* res, int64_t res_
     KERNEL_CHECK();
 }
 
-void layernorm64_gelu(cudaStream_t s, float* x, int64_t rows, float const* gamma, float const* beta) {
-    ProfScope prof(s, CAT_DEC_NORM);
-    layernorm64_gelu_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, s>>>(x, rows, gamma, beta);
+void layernorm64_gelu(cudaStream_t s, act_t* x, int64_t rows, float const* gamma, float const* beta) {
+    ProfScope prof(s, CAT_DEC_NORM, 0, (double)rows * 64 * 4);
+    layernorm64_gelu_kernel<<<(unsigned)ceil_div64(rows, 32), 256, 0, s>>>(x, rows, gamma, beta);
     KERNEL_CHECK();
 }
 
-void mask_dot(cudaStream_t s, float const* hyper, float const* up2, int P, float* low) {
-    ProfScope prof(s, CAT_DEC_MISC);
+void mask_dot(cudaStream_t s, float const* hyper, act_t const* up2, int P, float* low) {
+    ProfScope prof(s, CAT_DEC_MISC, 2.0 * P * 65536 * 128, (double)P * (16384.0 * 128 * 2 + 4 * 65536 * 4));
     dim3 grid(65536 / 256, P);
     mask_dot_kernel<<<grid, 256, 0, s>>>(hyper, up2, low);
     KERNEL_CHECK();
@@ -569,6 +543,12 @@ void mask_dot(cudaStream_t s, float const* hyper, float const* up2, int P, float
 void token_mlp3(cudaStream_t s, float const* tokens, int P, TokenMlp3 const& heads, float* hyper, float* iou) {
     ProfScope prof(s, CAT_DEC_LINEAR);
     token_mlp3_kernel<<<dim3((unsigned)P, 5), 256, 0, s>>>(tokens, heads, hyper, iou);
+    KERNEL_CHECK();
+}
+
+void f32_to_act(cudaStream_t s, float const* in, int64_t n, act_t* out) {
+    ProfScope prof(s, CAT_DEC_MISC);
+    f32_to_act_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(in, n, out);
     KERNEL_CHECK();
 }
 

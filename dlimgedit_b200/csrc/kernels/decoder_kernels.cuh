@@ -1,9 +1,12 @@
-// decoder_kernels.cuh -- fp32 CUDA-core kernels of the SAM prompt encoder + two-way mask decoder.
-// The large image-side projections (4096 rows per prompt) go through the tf32 tcgen05 GEMM (gemm.cuh);
-// everything here is token-side (7 rows per prompt), attention cores, LayerNorms and glue.
+// decoder_kernels.cuh -- CUDA-core kernels of the SAM prompt encoder + two-way mask decoder.
+// The image-side stream (4096 rows per prompt) is stored in 16 bits (act_t) and its projections go through the
+// tcgen05 GEMM (gemm.cuh); the token side (7 rows per prompt) stays fp32.  Everything here is token-side Linears,
+// the attention cores, LayerNorms and glue.
 #pragma once
 
 #include "../common.hpp"
+
+#include "../act.hpp"
 
 namespace dlimg {
 namespace dec {
@@ -27,10 +30,6 @@ void prompt_tokens(cudaStream_t s, float const* coords, float const* labels, int
 // Dense positional encoding of the 64x64 grid -> (4096, 256) token-major.
 void dense_pe(cudaStream_t s, float const* gaussian, float* pos);
 
-// keys0 = emb + no_mask_embed ; kpe0 = keys0 + pos.  rows = batch * 4096 (pos repeats per image).
-void embed_prepare(cudaStream_t s, float const* emb, float const* no_mask, float const* pos, int64_t rows, float* keys0,
-                   float* kpe0);
-
 // y[r, :] = act( (x[r, :] (+ x2[r, :])) @ W^T + b ).  Row r of x lives at x + r*x_stride (same for x2), of y at
 // y + r*y_stride.  W is (N, K) row-major.  relu != 0 applies ReLU.  K <= 2048.
 void linear_small(cudaStream_t s, float const* x, int64_t x_stride, float const* x2, int64_t x2_stride, int rows, int K,
@@ -39,34 +38,40 @@ void linear_small(cudaStream_t s, float const* x, int64_t x_stride, float const*
 // Token self-attention: q, k, v (P, 7, 256) already projected; 8 heads x 32 -> out (P, 7, 256).
 void token_self_attention(cudaStream_t s, float const* q, float const* k, float const* v, int P, float* out);
 
-// Token -> image attention core: q (P, 7, 128); K, V (4096, 128) per prompt at stride kv_stride floats
-// (0 = shared by all prompts); 8 heads x 16 -> out (P, 7, 128).
+// Token -> image attention core: q (P, 7, 128) fp32; K and V rows of the image stream in 16 bits: row i of prompt p at
+// base_p + i * pitch (K) and base_p + v_off + i * pitch (V), where base_p = ptrs[p] (per-prompt tables, layer 0: the
+// image's prompt-independent projections) or base + p * prompt_stride; 8 heads x 16 -> out (P, 7, 128) fp32.
 // `scratch` holds P * kT2iSplits * 7 * (128 + 16) floats of partial results (split-key softmax merge).
 constexpr int kT2iSplits = 4;
 constexpr size_t kT2iScratchPerPrompt = (size_t)kT2iSplits * kTokens * (128 + 16);
-void token_to_image_attention(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride, int P,
-                              float* scratch, float* out);
-// Older two-pass formulation of the same op, kept as a cross-check for tests.
-void token_to_image_attention_twopass(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride,
-                                      int P, float* out);
+void token_to_image_attention(cudaStream_t s, float const* q, act_t const* base, act_t const* const* ptrs, int64_t prompt_stride,
+                              int pitch, int v_off, int P, float* scratch, float* out);
 
-// Image -> token attention core: Q (4096, 128) per prompt at stride q_stride (0 = shared); kt, vt (P, 7, 128)
-// -> out (P, 4096, 128).
-void image_to_token_attention(cudaStream_t s, float const* Q, int64_t q_stride, float const* kt, float const* vt, int P,
-                              float* out);
+// Image -> token attention core: Q rows (16-bit, 128 wide) of prompt p at Qp + q_off + i * q_pitch, Qp = Qptrs[p] or
+// Q + p * q_prompt_stride; kt, vt (P, 7, 128) fp32 -> out (P, 4096, 128) 16-bit.
+void image_to_token_attention(cudaStream_t s, act_t const* Q, act_t const* const* Qptrs, int64_t q_prompt_stride, int q_pitch,
+                              int q_off, float const* kt, float const* vt, int P, act_t* out);
+
+// fp32 -> 16-bit storage (load-time tables).
+void f32_to_act(cudaStream_t s, float const* in, int64_t n, act_t* out);
+
+// Image stream: out = LayerNorm_256(x + res) (eps 1e-5) on 16-bit rows, P * 4096 of them; the residual rows of prompt p
+// are res_ptrs[p] (4096, 256) or res + p * 4096 * 256.  out == res is allowed.
+void layernorm256_img(cudaStream_t s, act_t const* x, act_t const* res, act_t const* const* res_ptrs, int P, float const* gamma,
+                      float const* beta, act_t* out);
 
 // out = LayerNorm_256(x + res) (eps 1e-5); optionally out2 = out + pos.  res row = row % res_mod, pos row =
 // row % pos_mod.  res / pos / out2 may be null.  In-place (out == x) is allowed.
 void layernorm256(cudaStream_t s, float const* x, float const* res, int64_t res_mod, int64_t rows, float const* gamma,
                   float const* beta, float const* pos, int64_t pos_mod, float* out, float* out2);
 
-// In-place LayerNorm2d over groups of 64 channels (eps 1e-6) followed by exact GELU; rows of 64 floats.
-void layernorm64_gelu(cudaStream_t s, float* x, int64_t rows, float const* gamma, float const* beta);
+// In-place LayerNorm2d over groups of 64 channels (eps 1e-6) followed by exact GELU; 16-bit rows of 64.
+void layernorm64_gelu(cudaStream_t s, act_t* x, int64_t rows, float const* gamma, float const* beta);
 
-// low[p, m, Y, X] = sum_c hyper[p, m, c] * up2[p, blocked(Y, X), c]  (m = 0..3), where up2 is the blocked
+// low[p, m, Y, X] = sum_c hyper[p, m, c] * up2[p, blocked(Y, X), c]  (m = 0..3), where up2 (16-bit) is the blocked
 // output of the two transposed convolutions: row ((y*64+x)*4 + dy*2+dx), col (ey*2+ex)*32 + c, with
 // Y = 4y + 2dy + ey, X = 4x + 2dx + ex.
-void mask_dot(cudaStream_t s, float const* hyper, float const* up2, int P, float* low);
+void mask_dot(cudaStream_t s, float const* hyper, act_t const* up2, int P, float* low);
 
 // IoU head (slot 0, on token 0, 256 -> 256 -> 256 -> 4) and the four hypernetwork MLPs (slots 1..4, on mask tokens 1..4,
 // 256 -> 256 -> 256 -> 32), ReLU between layers: tokens (P, 7, 256) -> iou (P, 4), hyper (P, 4, 32).

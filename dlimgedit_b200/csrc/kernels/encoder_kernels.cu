@@ -427,16 +427,18 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(act_t const* __rest
 // channel's 32 tokens leave as one 128-byte segment.
 __global__ void __launch_bounds__(256) layernorm256_tokens_nchw_kernel(act_t const* __restrict__ in, int tokens,
                                                                        float const* __restrict__ gamma, float const* __restrict__ beta,
-                                                                       float eps, float* __restrict__ out_tok, float* __restrict__ out_nchw) {
+                                                                       float eps, float const* __restrict__ no_mask,
+                                                                       act_t* __restrict__ out_keys, float* __restrict__ out_nchw) {
     constexpr int C = 256;
     __shared__ float tile[C][33];
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int const b = blockIdx.y, t0 = blockIdx.x * 32;
-    float2 g[4], bt[4];
+    float2 g[4], bt[4], nm[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         g[i] = reinterpret_cast<float2 const*>(gamma)[lane + 32 * i];
         bt[i] = reinterpret_cast<float2 const*>(beta)[lane + 32 * i];
+        nm[i] = reinterpret_cast<float2 const*>(no_mask)[lane + 32 * i];
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -468,7 +470,9 @@ __global__ void __launch_bounds__(256) layernorm256_tokens_nchw_kernel(act_t con
             float2 y;
             y.x = (x[i].x - mean) * rstd * g[i].x + bt[i].x;
             y.y = (x[i].y - mean) * rstd * g[i].y + bt[i].y;
-            reinterpret_cast<float2*>(out_tok + row * C)[idx] = y;
+            // the decoder's layer-0 image stream: embedding + no_mask_embed (the dense prompt embedding of the reference's
+            // constant empty mask input, segmentation.cpp:43-45), 16-bit token-major
+            reinterpret_cast<act2_t*>(out_keys + row * C)[idx] = f22act2(y.x + nm[i].x, y.y + nm[i].y);
             tile[2 * idx][tl] = y.x;
             tile[2 * idx + 1][tl] = y.y;
         }
@@ -708,10 +712,10 @@ void layernorm_rows(cudaStream_t s, act_t const* in, int rows, int C, int const*
 }
 
 void layernorm256_tokens_nchw(cudaStream_t s, act_t const* in, int batch, int tokens, float const* gamma, float const* beta,
-                              float eps, float* out_tok, float* out_nchw) {
+                              float eps, float const* no_mask, act_t* out_keys, float* out_nchw) {
     DLIMG_ASSERT(tokens % 32 == 0);
-    ProfScope prof(s, CAT_LAYERNORM, 0, (double)batch * tokens * 256 * (2 + 4 + 4));
-    layernorm256_tokens_nchw_kernel<<<dim3((unsigned)(tokens / 32), (unsigned)batch), 256, 0, s>>>(in, tokens, gamma, beta, eps, out_tok, out_nchw);
+    ProfScope prof(s, CAT_LAYERNORM, 0, (double)batch * tokens * 256 * (2 + 2 + 4));
+    layernorm256_tokens_nchw_kernel<<<dim3((unsigned)(tokens / 32), (unsigned)batch), 256, 0, s>>>(in, tokens, gamma, beta, eps, no_mask, out_keys, out_nchw);
     KERNEL_CHECK();
 }
 

@@ -63,10 +63,11 @@ int local_conv_parts(int C);
 void local_conv_tma(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, float const* weight, float const* bias,
                     act_t* out, float2* stats, int num_sms);
 
-// LayerNorm over C = 256 channels of (batch, tokens, 256) 16-bit rows, written twice as fp32: token-major (batch, tokens,
-// 256) and NCHW (batch, 256, tokens).  tokens % 32 == 0.
+// Final LayerNorm2d of the neck over C = 256 channels of (batch, tokens, 256) 16-bit rows, written twice: fp32 NCHW
+// (batch, 256, tokens) -- the reference's `image_embeddings` -- and 16-bit token-major (batch, tokens, 256) with
+// no_mask (256) added -- the decoder's layer-0 image stream.  tokens % 32 == 0.
 void layernorm256_tokens_nchw(cudaStream_t s, act_t const* in, int batch, int tokens, float const* gamma, float const* beta,
-                              float eps, float* out_tok, float* out_nchw);
+                              float eps, float const* no_mask, act_t* out_keys, float* out_nchw);
 
 // Row LayerNorm over C channels.  src_row (optional, length `rows`): gather index into `in`, -1 = the row
 // is window padding and the output is LN(0) = beta.  Output bf16 or fp32.

@@ -42,6 +42,7 @@ struct EpiParams {
     int act;
     int out_f32;
     int ldc;
+    int res_mod;   // staged residual: residual row = output row % res_mod (0 = output row)
 };
 
 __device__ __forceinline__ void add_bias16(float (&v)[16], float const* bias, int col) {
@@ -543,7 +544,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (s_cnt == 0 || !ep.residual) return;  // (the kernel also serves plain GEMMs that only want row sums)
             int const m0 = (tile / n_tiles) * kBlockM + quarter * 32;
             int const n0 = (tile % n_tiles) * block_n + s_first * 16;
-            act_t const* seg = reinterpret_cast<act_t const*>(ep.residual) + (int64_t)m0 * ep.ldc + n0;
+            // res_mod: the residual is a (res_mod, N) table shared by every group of res_mod output rows (a multiple of
+            // the tile height, so a tile never straddles two groups) -- the decoder's position terms
+            int const r0 = ep.res_mod ? m0 % ep.res_mod : m0;
+            act_t const* seg = reinterpret_cast<act_t const*>(ep.residual) + (int64_t)r0 * ep.ldc + n0;
             int const cpr = 2 * s_cnt, rows_it = 32 / cpr;  // 16-byte pieces per row, rows per instruction
             int const row0 = lane / cpr, chunk = lane - row0 * cpr;
             int const rows_valid = min(32, M - m0);
@@ -1183,6 +1187,7 @@ EpiParams to_params(Epilogue const& e, int N) {
     p.act = e.act;
     p.out_f32 = e.out_f32;
     p.ldc = e.ldc ? e.ldc : N;
+    p.res_mod = e.res_mod;
     return p;
 }
 
@@ -1268,12 +1273,14 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch
     static bool const allow_staged_res = !std::getenv("DLIMG_B200_GEMM_DIRECT_RESIDUAL");  // A/B switch
     bool const res_ok = !ep.residual || (allow_staged_res && ep.act == ACT_NONE && !ep.ln_stats);
+    if (ep.res_mod) DLIMG_ASSERT(ep.residual && ep.res_mod % kBlockM == 0 && M % ep.res_mod == 0);
     static bool const allow_staged_f32 = !std::getenv("DLIMG_B200_GEMM_DIRECT_F32");  // A/B switch
     bool const staged_f32 = allow_staged && allow_staged_f32 && tf32 && ep.out_f32 && !ep.residual && !ep.row_map && !ep.stats_out &&
                             !ep.ln_stats && block_n >= 64 && N <= 2048;
     bool const staged = staged_f32 ||
                         (allow_staged && !tf32 && res_ok && !ep.row_map && !ep.out_f32 && block_n >= 64 &&
                          (ep.act == ACT_NONE || ep.act == ACT_GELU) && (!ep.stats_out || (ep.act == ACT_NONE && !ep.ln_stats)) && N <= 2048);
+    if (ep.res_mod && !(staged && !tf32)) fail("GEMM: a residual table (res_mod) needs the staged 16-bit epilogue");
     if (ep.ln_stats && (!staged || !ep.bias))
         fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue) and a bias");
     if (ep.stats_out && (ep.act != ACT_NONE || ep.row_map || ep.out_f32 || block_n < 64))

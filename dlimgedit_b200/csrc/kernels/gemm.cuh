@@ -24,6 +24,7 @@ enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 struct Epilogue {
     float const* bias = nullptr;     // [N] fp32, or null
     void const* residual = nullptr;  // same element type / pitch as the output, indexed by OUTPUT row
+    int res_mod = 0;                 // != 0 (16-bit staged epilogue only): residual row = output row % res_mod
     int const* row_map = nullptr;    // [M] -> output row (-1 = drop the row), or null for identity
     int act = ACT_NONE;              // applied after bias and residual
     int out_f32 = 0;                 // 0: bf16 output, 1: fp32 output

@@ -10,6 +10,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 
 namespace dlimg {
 namespace prepost {
@@ -177,6 +179,135 @@ LongestSide resize_longest_side(int w, int h, int max_side) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// Correctly rounded linear -> sRGB8: code = number of thresholds <= acc (ascending, thr[0] = -inf); eight
+// branch-free steps of a binary search over the shared-memory table.
+__device__ __forceinline__ int srgb_encode(float acc, float const* __restrict__ thr) {
+    int lo = 0;
+#pragma unroll
+    for (int step = 128; step > 0; step >>= 1) lo += acc >= thr[lo + step] ? step : 0;
+    return lo;
+}
+
+// ---- resize: ONE kernel, separable through shared memory (reference image.cpp:37-51) ----------------------------
+// A block produces a tile of tr x tc output pixels.  The input rows the tile needs are decoded (u8 -> linear float,
+// table look-up, edge pixels clamped) `ch` rows at a time into shared memory; thread j owns H-pass column
+// j = (output column, channel) with its filter taps in registers and leaves the horizontally filtered rows in shared
+// memory; the vertical pass + linear->sRGB8 encode then reads four neighbouring columns per thread (LDS.128) and writes
+// four bytes at once.  No intermediate ever reaches HBM (the two-pass form wrote in_h x out_w x bpp floats and read
+// them back).  Multiplications and additions stay separate (__fmul_rn / __fadd_rn), in ascending tap order from 0,
+// exactly like the reference filter -- results are bit-identical to oracle/c/prepost_ref.c.
+struct ResizeTile {
+    int tr = 0, tc = 0;          // output rows / columns per block; tc * bpp <= 256 and a multiple of 4
+    int nr_max = 0, nc_max = 0;  // most input rows / columns any tile needs (exact, from the axis plans)
+    int ch = 8;                  // input rows decoded per pass (one per warp)
+    int smem_bytes = 0;
+};
+
+template <int BPP, int KT>
+__global__ void __launch_bounds__(256) resize_tile_kernel(uint8_t const* __restrict__ in, int in_w, int in_h, int stride,
+                                                          ResizeDeviceTables t, ResizeTile g, uint8_t* __restrict__ out,
+                                                          int out_w, int out_h) {
+    extern __shared__ __align__(16) float rs_smem[];
+    int const row_elems = g.tc * BPP;            // H-pass outputs per input row
+    int const px_per_row = g.nc_max + KT;        // staged pixels per input row (tail zero-filled: taps >= htaps read it)
+    int const in_elems = px_per_row * BPP;
+    float* const s_dec = rs_smem;
+    float* const s_thr = s_dec + 256;
+    float* const s_vw = s_thr + 256;
+    float* const s_hb = s_vw + ((g.tr * t.vtaps + 3) & ~3);
+    float* const s_in = s_hb + g.nr_max * row_elems;
+    int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int const ox0 = blockIdx.x * g.tc, oy0 = blockIdx.y * g.tr;
+    int const tcv = min(g.tc, out_w - ox0), trv = min(g.tr, out_h - oy0);
+    s_dec[tid] = __ldg(t.decode + tid);
+    s_thr[tid] = __ldg(t.encode_threshold + tid);
+    for (int i = tid; i < trv * t.vtaps; i += 256) s_vw[i] = __ldg(t.vweights + (size_t)oy0 * t.vtaps + i);
+    int const r_lo = __ldg(t.vfirst + oy0), r_hi = __ldg(t.vfirst + oy0 + trv - 1) + t.vtaps - 1;
+    int const nr = r_hi - r_lo + 1;
+    int const c_lo = __ldg(t.hfirst + ox0), c_hi = __ldg(t.hfirst + ox0 + tcv - 1) + t.htaps - 1;
+    int const nc = c_hi - c_lo + 1;
+    bool const hactive = tid < tcv * BPP;
+    float w[KT];
+    int foff = 0;
+    {
+        int const ox = ox0 + tid / BPP, c = tid % BPP;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) w[k] = (hactive && k < t.htaps) ? __ldg(t.hweights + (size_t)ox * t.htaps + k) : 0.0f;
+        if (hactive) foff = (__ldg(t.hfirst + ox) - c_lo) * BPP + c;
+    }
+    __syncthreads();
+    for (int rc = 0; rc < nr; rc += g.ch) {
+        int const chv = min(g.ch, nr - rc);
+        // decode: warp = staged row, lane = pixel
+        for (int rr = warp; rr < chv; rr += 8) {
+            int const y = min(max(r_lo + rc + rr, 0), in_h - 1);
+            uint8_t const* src_row = in + (size_t)y * stride;
+            float* dst_row = s_in + rr * in_elems;
+            for (int px = lane; px < px_per_row; px += 32) {
+                float* dst = dst_row + px * BPP;
+                if (px < nc) {
+                    int const x = min(max(c_lo + px, 0), in_w - 1);
+                    uint8_t const* src = src_row + (size_t)x * BPP;
+                    if (BPP == 4 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+                        uint32_t const p = __ldg(reinterpret_cast<uint32_t const*>(src));
+                        dst[0] = s_dec[p & 255u];
+                        dst[1] = s_dec[(p >> 8) & 255u];
+                        dst[2] = s_dec[(p >> 16) & 255u];
+                        dst[3] = s_dec[p >> 24];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BPP; ++c) dst[c] = s_dec[__ldg(src + c)];
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BPP; ++c) dst[c] = 0.0f;
+                }
+            }
+        }
+        __syncthreads();
+        if (hactive) {
+            for (int rr = 0; rr < chv; ++rr) {
+                float const* row = s_in + rr * in_elems + foff;
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < KT; ++k) acc = __fadd_rn(acc, __fmul_rn(row[k * BPP], w[k]));
+                s_hb[(rc + rr) * row_elems + tid] = acc;
+            }
+        }
+        __syncthreads();
+    }
+    // vertical pass + encode: four neighbouring columns per thread
+    int const quads = row_elems >> 2, valid_elems = tcv * BPP;
+    for (int i = tid; i < trv * quads; i += 256) {
+        int const oyl = i / quads, j = (i - oyl * quads) * 4;
+        if (j >= valid_elems) continue;
+        int const rbase = __ldg(t.vfirst + oy0 + oyl) - r_lo;
+        float const* vw = s_vw + oyl * t.vtaps;
+        float const* col = s_hb + rbase * row_elems + j;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < t.vtaps; ++k) {
+            float4 const v = *reinterpret_cast<float4 const*>(col + k * row_elems);
+            float const wk = vw[k];
+            acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, wk));
+            acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, wk));
+            acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, wk));
+            acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, wk));
+        }
+        uint32_t const b0 = (uint32_t)srgb_encode(acc.x, s_thr), b1 = (uint32_t)srgb_encode(acc.y, s_thr);
+        uint32_t const b2 = (uint32_t)srgb_encode(acc.z, s_thr), b3 = (uint32_t)srgb_encode(acc.w, s_thr);
+        uint8_t* dst = out + ((size_t)(oy0 + oyl) * out_w + ox0) * BPP + j;
+        if (j + 4 <= valid_elems && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+            *reinterpret_cast<uint32_t*>(dst) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        } else {
+            uint32_t const b[4] = {b0, b1, b2, b3};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j + e < valid_elems) dst[e] = (uint8_t)b[e];
+        }
+    }
+}
+
+// Two-pass fallback for extreme reductions (more than 32 taps per axis, or tiles that do not fit shared memory).
 // Horizontal pass: (in_h, in_w, bpp) u8 -> (in_h, out_w, bpp) linear float.
 __global__ void resize_h_kernel(uint8_t const* __restrict__ in, int in_w, int in_h, int stride, int bpp, int out_w,
                                 float const* __restrict__ decode, int const* __restrict__ first,
@@ -222,26 +353,48 @@ __global__ void resize_v_kernel(float const* __restrict__ in, int in_h, int row_
         int const y = min(max(f + k, 0), in_h - 1);
         acc = __fadd_rn(acc, __fmul_rn(in[(size_t)y * row_elems + x], w[k]));
     }
-    // code = number of thresholds <= acc, thresholds ascending (thr[0] = -inf)
-    int lo = 0, hi = 255;
-    while (lo < hi) {
-        int const mid = (lo + hi + 1) >> 1;
-        if (acc >= thr[mid]) lo = mid;
-        else hi = mid - 1;
-    }
-    out[t] = (uint8_t)lo;
+    out[t] = (uint8_t)srgb_encode(acc, thr);
 }
 
-__global__ void image_tensor_kernel(uint8_t const* __restrict__ in, int w, int h, int stride, int bpp, int c0, int c1,
-                                    int c2, float* __restrict__ out) {
+// ---- create_image_tensor (reference segmentation.cpp:81-106): four pixels per thread, 48 contiguous output bytes ----
+template <int BPP>
+__global__ void __launch_bounds__(256) image_tensor_kernel(uint8_t const* __restrict__ in, int w, int h, int stride, int c0,
+                                                           int c1, int c2, float* __restrict__ out) {
+    int const groups = (w + 3) >> 2;
     int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)w * h) return;
-    int const x = (int)(t % w), y = (int)(t / w);
-    uint8_t const* px = in + (size_t)y * stride + (size_t)x * bpp;
-    float* o = out + t * 3;
-    o[0] = (float)px[c0];
-    o[1] = (float)px[c1];
-    o[2] = (float)px[c2];
+    if (t >= (int64_t)groups * h) return;
+    int const y = (int)(t / groups), x0 = (int)(t - (int64_t)y * groups) * 4;
+    int const n = min(4, w - x0);
+    uint8_t const* px = in + (size_t)y * stride + (size_t)x0 * BPP;
+    float v[12];
+    if (BPP == 4 && n == 4 && (reinterpret_cast<uintptr_t>(px) & 15) == 0) {
+        uint4 const q = __ldg(reinterpret_cast<uint4 const*>(px));
+        uint32_t const p[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[3 * i + 0] = (float)((p[i] >> (8 * c0)) & 255u);
+            v[3 * i + 1] = (float)((p[i] >> (8 * c1)) & 255u);
+            v[3 * i + 2] = (float)((p[i] >> (8 * c2)) & 255u);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint8_t const* p = px + i * BPP;
+            bool const ok = i < n;
+            v[3 * i + 0] = ok ? (float)__ldg(p + c0) : 0.f;
+            v[3 * i + 1] = ok ? (float)__ldg(p + c1) : 0.f;
+            v[3 * i + 2] = ok ? (float)__ldg(p + c2) : 0.f;
+        }
+    }
+    float* o = out + ((size_t)y * w + x0) * 3;
+    if (n == 4 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        float4* o4 = reinterpret_cast<float4*>(o);
+        o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+        o4[2] = make_float4(v[8], v[9], v[10], v[11]);
+    } else {
+        for (int i = 0; i < 3 * n; ++i) o[i] = v[i];
+    }
 }
 
 struct Lerp {
@@ -269,7 +422,7 @@ __device__ __forceinline__ float sample_1024(float const* __restrict__ low, int 
     return ly.l0 * top + ly.l1 * bot;
 }
 
-// 4 output pixels per thread along x, written as one 32-bit store when aligned.
+// Per-pixel form (no shared memory): the fallback for outputs wider than 32768 pixels.
 __global__ void __launch_bounds__(256) mask_post_kernel(float const* __restrict__ low_res, int64_t plane_stride,
                                                         int const* __restrict__ plane_index, int rw, int rh, int w,
                                                         int h, float sx, float sy,
@@ -303,131 +456,315 @@ __global__ void __launch_bounds__(256) mask_post_kernel(float const* __restrict_
     }
 }
 
-// Same arithmetic, organised per block of kPostRows output rows: the 1024-grid samples those rows need (two grid
-// rows each, de-duplicated) are computed once into shared memory, then every output pixel combines four of them.
-// The per-pixel form above evaluates sample_1024 four times per output pixel; here it is ~1.25 (1024^2 output) to
-// ~0.3 (4K output) times, with bit-identical results (same operations in the same order).
-constexpr int kPostRows = 4;
-constexpr int kPostSlots = 2 * kPostRows;      // 1024-grid rows a block may need
-constexpr int kPostLowRows = 2 * kPostSlots;   // low-resolution rows those may need
+// ---- mask post-processing: 256 -> 1024 bilinear, crop, -> (h, w) bilinear, > 0 -> 0 / 255 -----------------------------
+// (decoder-graph post-processing, SURVEY A.5, + write_mask_image, reference segmentation.cpp:108-116.)
+// A block produces kRows complete output rows of one mask.  Same operations in the same order as the per-pixel form
+// above, but every intermediate is computed once per block and kept in shared memory:
+//   1. the few low-resolution rows the block needs                                     s_low[n_low][256]
+//   2. their horizontal interpolation at the 1024 grid                                 s_h[n_low][1024]
+//   3. (general case) the vertical interpolation = the 1024-grid rows the block needs  s_grid[n_slots][1024]
+//   4. output pixels: second bilinear from s_grid, threshold, byte into a staging copy of the block's output rows
+//      (kIdentity: the resized extent equals the output extent, the second bilinear has weights 1 / 0 and the output
+//      is the thresholded vertical interpolation of step 3 directly)
+//   5. the staged rows -- a contiguous byte range of the packed plane -- go out as 16-byte vectors (the staging copy
+//      starts at the same offset mod 16 as the global range, so both sides are aligned).
+// The previous form issued one byte store per lane (32 B per warp instruction) and reached 0.055 of the HBM rate.
+struct PostGeom {
+    int rw, rh, w, h;
+    float sx, sy;
+    int n_slots, n_low;  // upper bounds of the 1024-grid rows / low-resolution rows a block needs (host)
+};
 
-__global__ void __launch_bounds__(256) mask_post_rows_kernel(float const* __restrict__ low_res, int64_t plane_stride,
-                                                             int const* __restrict__ plane_index, int rw, int rh, int w,
-                                                             int h, float sx, float sy,
+template <bool kIdentity, int kRows>
+__global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __restrict__ low_res, int64_t plane_stride,
+                                                             int const* __restrict__ plane_index, PostGeom g,
                                                              uint8_t* const* __restrict__ out_planes,
                                                              uint8_t* __restrict__ out_contig) {
-    extern __shared__ __align__(16) float post_smem[];
-    float (*grid_rows)[kImageSize] = reinterpret_cast<float (*)[kImageSize]>(post_smem);
-    float (*low_rows)[kLowRes] = reinterpret_cast<float (*)[kLowRes]>(post_smem + kPostSlots * kImageSize);
+    extern __shared__ __align__(16) uint8_t post_smem[];
+    float* const s_low = reinterpret_cast<float*>(post_smem);
+    float* const s_h = s_low + g.n_low * kLowRes;
+    float* const s_grid = s_h + g.n_low * kImageSize;
+    uint8_t* const s_out = reinterpret_cast<uint8_t*>(s_grid + (kIdentity ? 0 : g.n_slots * kImageSize));
+    int const tid = threadIdx.x;
     int const plane = blockIdx.y;
-    int const y0 = blockIdx.x * kPostRows;
+    int const y0 = blockIdx.x * kRows;
+    int const rows_valid = min(kRows, g.h - y0);
     float const* low = low_res + (plane_index ? plane_index[plane] : plane) * plane_stride;
-    // Every thread derives the (tiny) row tables itself -- no serial set-up phase.  The 1024-grid rows needed by the
-    // block's output rows are consecutive when the vertical scale is <= 1.75 (slot = row - first row); otherwise each
-    // output row gets its own two slots.  Likewise for the low-resolution rows behind them.
-    Lerp ly[kPostRows];
-#pragma unroll
-    for (int t = 0; t < kPostRows; ++t) ly[t] = lerp_coord(min(y0 + t, h - 1), sy, rh);
-    int const g_base = ly[0].i0, g_span = ly[kPostRows - 1].i1 - g_base + 1;
-    bool const g_dense = g_span <= kPostSlots;
-    int const n_slots = g_dense ? g_span : kPostSlots;
-    auto grid_row_of = [&](int slot) {
-        if (g_dense) return g_base + slot;
-        int r = 0;
-#pragma unroll
-        for (int t = 0; t < kPostRows; ++t) {
-            if (slot == 2 * t) r = ly[t].i0;
-            if (slot == 2 * t + 1) r = ly[t].i1;
-        }
-        return r;
-    };
-    int const l_base = lerp_coord(grid_row_of(0), 0.25f, kLowRes).i0;
-    int const l_span = lerp_coord(grid_row_of(n_slots - 1), 0.25f, kLowRes).i1 - l_base + 1;
-    bool const l_dense = g_dense && l_span <= kPostLowRows;
-    int const n_low = l_dense ? l_span : 2 * n_slots;
-    for (int i = threadIdx.x; i < n_low * kLowRes; i += blockDim.x) {
-        int const j = i >> 8;
-        int row;
-        if (l_dense) {
-            row = l_base + j;
-        } else {
-            Lerp const q = lerp_coord(grid_row_of(j >> 1), 0.25f, kLowRes);
-            row = (j & 1) ? q.i1 : q.i0;
-        }
-        low_rows[j][i & 255] = __ldg(low + row * kLowRes + (i & 255));
+    uint8_t* const plane_out = out_planes ? out_planes[plane] : out_contig + (size_t)plane * g.w * g.h;
+
+    // rows of the 1024 grid this block needs, and the low-resolution rows behind them (both contiguous ranges)
+    int g_base, g_last;
+    if (kIdentity) {
+        g_base = y0;
+        g_last = y0 + rows_valid - 1;
+    } else {
+        g_base = lerp_coord(y0, g.sy, g.rh).i0;
+        g_last = lerp_coord(y0 + rows_valid - 1, g.sy, g.rh).i1;
+    }
+    int const l_base = lerp_coord(g_base, 0.25f, kLowRes).i0;
+    int const l_last = lerp_coord(g_last, 0.25f, kLowRes).i1;
+    int const n_low = l_last - l_base + 1, n_slots = g_last - g_base + 1;
+    if (n_low > g.n_low || (!kIdentity && n_slots > g.n_slots)) __trap();  // the host bounds are exact upper bounds
+
+    {   // 1. low-resolution rows (16-byte loads; planes are 256 KiB apart)
+        float4 const* src = reinterpret_cast<float4 const*>(low + (size_t)l_base * kLowRes);
+        float4* dst = reinterpret_cast<float4*>(s_low);
+        for (int i = tid; i < n_low * (kLowRes / 4); i += 256) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    // grid_rows[slot][xx] = sample_1024(low, grid row of slot, xx), taps from shared memory; the horizontal
-    // coordinates are computed once per column and reused for every slot
-    for (int xx = threadIdx.x; xx < rw; xx += blockDim.x) {
+    // 2. horizontal interpolation of those rows at grid columns 0 .. rw-1
+    for (int xx = tid; xx < g.rw; xx += 256) {
         Lerp const lx = lerp_coord(xx, 0.25f, kLowRes);
-        for (int slot = 0; slot < n_slots; ++slot) {
-            Lerp const q = lerp_coord(grid_row_of(slot), 0.25f, kLowRes);
-            float const* r0 = low_rows[l_dense ? q.i0 - l_base : 2 * slot];
-            float const* r1 = low_rows[l_dense ? q.i1 - l_base : 2 * slot + 1];
-            float const top = lx.l0 * r0[lx.i0] + lx.l1 * r0[lx.i1];
-            float const bot = lx.l0 * r1[lx.i0] + lx.l1 * r1[lx.i1];
-            grid_rows[slot][xx] = q.l0 * top + q.l1 * bot;
+        for (int j = 0; j < n_low; ++j) {
+            float const* r = s_low + j * kLowRes;
+            s_h[j * kImageSize + xx] = lx.l0 * r[lx.i0] + lx.l1 * r[lx.i1];
         }
     }
     __syncthreads();
-    uint8_t* const plane_out = out_planes ? out_planes[plane] : out_contig + (size_t)plane * w * h;
-    // one pixel per lane and iteration: neighbouring lanes read neighbouring grid samples (no bank conflicts) and
-    // their byte stores coalesce into whole sectors; the horizontal coordinate is shared by the block's rows
-    for (int x = threadIdx.x; x < w; x += blockDim.x) {
-        Lerp const lx = lerp_coord(x, sx, rw);
+    int const mis = (int)(reinterpret_cast<uintptr_t>(plane_out + (size_t)y0 * g.w) & 15);
+    if (kIdentity) {
+        // 4. output row y = grid row y: vertical interpolation + threshold
+        Lerp q[kRows];
 #pragma unroll
-        for (int t = 0; t < kPostRows; ++t) {
-            int const y = y0 + t;
-            if (y < h) {
-                float const* r0 = grid_rows[g_dense ? ly[t].i0 - g_base : 2 * t];
-                float const* r1 = grid_rows[g_dense ? ly[t].i1 - g_base : 2 * t + 1];
-                float const top = lx.l0 * r0[lx.i0] + lx.l1 * r0[lx.i1];
-                float const bot = lx.l0 * r1[lx.i0] + lx.l1 * r1[lx.i1];
-                float const v = ly[t].l0 * top + ly[t].l1 * bot;
-                plane_out[(size_t)y * w + x] = v > 0.f ? 255 : 0;
+        for (int t = 0; t < kRows; ++t) {
+            q[t] = lerp_coord(min(y0 + t, g.h - 1), 0.25f, kLowRes);
+            q[t].i0 -= l_base;
+            q[t].i1 -= l_base;
+        }
+        for (int x = tid; x < g.w; x += 256) {
+            int ca = -1, cb = -1;
+            float ha = 0.f, hb = 0.f;
+#pragma unroll
+            for (int t = 0; t < kRows; ++t) {
+                if (t < rows_valid) {
+                    int const a = q[t].i0, b = q[t].i1;  // block-uniform
+                    float top, bot;
+                    if (a == ca) top = ha; else if (a == cb) top = hb; else top = s_h[a * kImageSize + x];
+                    if (b == a) bot = top; else if (b == cb) bot = hb; else if (b == ca) bot = ha; else bot = s_h[b * kImageSize + x];
+                    ca = a; ha = top; cb = b; hb = bot;
+                    float const v = q[t].l0 * top + q[t].l1 * bot;
+                    s_out[mis + t * g.w + x] = v > 0.f ? 255 : 0;
+                }
+            }
+        }
+    } else {
+        // 3. the 1024-grid rows
+        for (int slot = 0; slot < n_slots; ++slot) {
+            Lerp const q = lerp_coord(g_base + slot, 0.25f, kLowRes);
+            float const* r0 = s_h + (q.i0 - l_base) * kImageSize;
+            float const* r1 = s_h + (q.i1 - l_base) * kImageSize;
+            for (int xx = tid; xx < g.rw; xx += 256) s_grid[slot * kImageSize + xx] = q.l0 * r0[xx] + q.l1 * r1[xx];
+        }
+        __syncthreads();
+        // 4. second bilinear + threshold
+        Lerp ly[kRows];
+#pragma unroll
+        for (int t = 0; t < kRows; ++t) {
+            ly[t] = lerp_coord(min(y0 + t, g.h - 1), g.sy, g.rh);
+            ly[t].i0 -= g_base;
+            ly[t].i1 -= g_base;
+        }
+        for (int x = tid; x < g.w; x += 256) {
+            Lerp const lx = lerp_coord(x, g.sx, g.rw);
+            int ca = -1, cb = -1;
+            float ha = 0.f, hb = 0.f;
+#pragma unroll
+            for (int t = 0; t < kRows; ++t) {
+                if (t < rows_valid) {
+                    int const a = ly[t].i0, b = ly[t].i1;  // block-uniform
+                    float top, bot;
+                    if (a == ca) top = ha;
+                    else if (a == cb) top = hb;
+                    else { float const* r = s_grid + a * kImageSize; top = lx.l0 * r[lx.i0] + lx.l1 * r[lx.i1]; }
+                    if (b == a) bot = top;
+                    else if (b == cb) bot = hb;
+                    else if (b == ca) bot = ha;
+                    else { float const* r = s_grid + b * kImageSize; bot = lx.l0 * r[lx.i0] + lx.l1 * r[lx.i1]; }
+                    ca = a; ha = top; cb = b; hb = bot;
+                    float const v = ly[t].l0 * top + ly[t].l1 * bot;
+                    s_out[mis + t * g.w + x] = v > 0.f ? 255 : 0;
+                }
             }
         }
     }
+    __syncthreads();
+    // 5. staged rows -> global: head bytes up to the first 16-byte boundary, 16-byte vectors, tail bytes
+    {
+        int const nbytes = rows_valid * g.w;
+        uint8_t* const gdst = plane_out + (size_t)y0 * g.w;
+        int const head = min(nbytes, (16 - mis) & 15);
+        int const nvec = (nbytes - head) >> 4;
+        int const tail0 = head + (nvec << 4);
+        if (tid < head) gdst[tid] = s_out[mis + tid];
+        uint4 const* sv = reinterpret_cast<uint4 const*>(s_out + mis + head);
+        uint4* gv = reinterpret_cast<uint4*>(gdst + head);
+        for (int i = tid; i < nvec; i += 256) gv[i] = sv[i];
+        if (tid < nbytes - tail0) gdst[tail0 + tid] = s_out[mis + tail0 + tid];
+    }
 }
 
-__global__ void threshold_kernel(float const* __restrict__ logits, int tw, int w, int h, uint8_t* __restrict__ out) {
-    int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)w * h) return;
-    int const x = (int)(t % w), y = (int)(t / w);
-    out[t] = logits[(size_t)y * tw + x] > 0 ? 255 : 0;
+// write_mask_image (reference segmentation.cpp:108-116): four outputs per thread.
+__global__ void __launch_bounds__(256) threshold_kernel(float const* __restrict__ logits, int tw, int w, int h,
+                                                        uint8_t* __restrict__ out) {
+    int64_t const t0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    int64_t const total = (int64_t)w * h;
+    if (t0 >= total) return;
+    uint32_t m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t const t = t0 + i;
+        m[i] = 0;
+        if (t < total) {
+            int const y = (int)(t / w), x = (int)(t - (int64_t)y * w);
+            m[i] = __ldg(logits + (size_t)y * tw + x) > 0 ? 255u : 0u;
+        }
+    }
+    if (t0 + 4 <= total && (reinterpret_cast<uintptr_t>(out + t0) & 3) == 0) {
+        *reinterpret_cast<uint32_t*>(out + t0) = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
+    } else {
+        for (int i = 0; i < 4 && t0 + i < total; ++i) out[t0 + i] = (uint8_t)m[i];
+    }
+}
+
+template <typename K> void set_smem_limit(K kernel, int bytes) {
+    static std::mutex mutex;
+    static std::map<void const*, int> done;  // per kernel: largest limit requested so far (per process; all devices alike)
+    std::lock_guard<std::mutex> lock(mutex);
+    int& cur = done[(void const*)kernel];
+    if (bytes > cur) {
+        CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        cur = bytes;
+    }
+}
+
+constexpr int kPostSmemBudget = 72 * 1024;  // three blocks per SM
+
+template <bool kIdentity, int kRows>
+void launch_post_tile(cudaStream_t s, float const* low_res, int64_t plane_stride, int const* plane_index, int count,
+                      PostGeom const& g, int smem, uint8_t* const* out_planes, uint8_t* out_contig) {
+    set_smem_limit(mask_post_tile_kernel<kIdentity, kRows>, smem);
+    dim3 grid(ceil_div(g.h, kRows), count);
+    mask_post_tile_kernel<kIdentity, kRows><<<grid, 256, smem, s>>>(low_res, plane_stride, plane_index, g, out_planes, out_contig);
+}
+
+// shared-memory need of a kRows-row block; fills the exact upper bounds of the rows it may touch
+int post_plan(PostGeom& g, bool identity, int rows) {
+    // span of i1(last) - i0(first) + 1 over `n` consecutive destinations at source step `scale`: <= scale*(n-1) + 3
+    auto span = [](float scale, int n, int limit) { return std::min(limit, (int)std::ceil((double)scale * (n - 1)) + 3); };
+    g.n_slots = identity ? rows : span(g.sy, rows, g.rh);
+    g.n_low = span(0.25f, g.n_slots, kLowRes);
+    return g.n_low * (kLowRes + kImageSize) * 4 + (identity ? 0 : g.n_slots * kImageSize * 4) + rows * g.w + 32;
 }
 
 void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride, int const* plane_index, int count, int rw,
                       int rh, int w, int h, uint8_t* const* out_planes, uint8_t* out_contig) {
     DLIMG_ASSERT(count > 0 && w > 0 && h > 0 && rw > 0 && rh > 0 && rw <= kImageSize && rh <= kImageSize);
-    DLIMG_ASSERT(h <= 65535);
     // torch: scale = float(input_size) / output_size
-    float const sx = (float)rw / (float)w, sy = (float)rh / (float)h;
+    PostGeom g;
+    g.rw = rw; g.rh = rh; g.w = w; g.h = h;
+    g.sx = (float)rw / (float)w;
+    g.sy = (float)rh / (float)h;
     ProfScope prof(s, CAT_MASK_POST, 0, (double)count * (65536.0 * 4 + (double)w * h));
-    static bool const per_pixel = std::getenv("DLIMG_B200_MASK_POST_PIXEL") != nullptr;  // A/B: the per-pixel form
-    if (per_pixel) {
+    bool const identity = rw == w && rh == h;
+    int rows = 0, smem = 0;
+    for (int r : {8, 4, 2, 1}) {
+        smem = post_plan(g, identity, r);
+        if (smem <= kPostSmemBudget) { rows = r; break; }
+    }
+    if (rows == 0) {  // very wide outputs: per-pixel form
+        DLIMG_ASSERT(h <= 65535 && count <= 65535);
         dim3 block(256), grid(ceil_div(ceil_div(w, 4), 256), h, count);
-        mask_post_kernel<<<grid, block, 0, s>>>(low_res, plane_stride, plane_index, rw, rh, w, h, sx, sy, out_planes, out_contig);
-    } else {
-        dim3 grid(ceil_div(h, kPostRows), count);
-        constexpr int kPostSmem = (kPostSlots * kImageSize + kPostLowRows * kLowRes) * (int)sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(mask_post_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostSmem));
-            attr_set = true;
+        mask_post_kernel<<<grid, block, 0, s>>>(low_res, plane_stride, plane_index, rw, rh, w, h, g.sx, g.sy, out_planes, out_contig);
+        KERNEL_CHECK();
+        return;
+    }
+    DLIMG_ASSERT(count <= 65535);
+    if (identity) {
+        switch (rows) {
+            case 8: launch_post_tile<true, 8>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+            case 4: launch_post_tile<true, 4>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+            case 2: launch_post_tile<true, 2>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+            default: launch_post_tile<true, 1>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
         }
-        mask_post_rows_kernel<<<grid, 256, kPostSmem, s>>>(low_res, plane_stride, plane_index, rw, rh, w, h, sx, sy, out_planes, out_contig);
+    } else {
+        switch (rows) {
+            case 8: launch_post_tile<false, 8>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+            case 4: launch_post_tile<false, 4>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+            case 2: launch_post_tile<false, 2>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+            default: launch_post_tile<false, 1>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+        }
     }
     KERNEL_CHECK();
 }
 
+// Tile shape for the single-kernel resize: the largest candidate whose shared-memory need fits the budget.
+ResizeTile plan_resize_tile(ResizeDeviceTables const& t, int bpp, int kt, int out_w, int out_h) {
+    static int const kRowsCand[] = {16, 8, 4, 2, 1};
+    int const tc_full = bpp == 3 ? 80 : 256 / bpp;  // 240 / 256 threads own an H-pass column
+    ResizeTile best;
+    for (int tc = tc_full; tc >= 8 && best.tr == 0; tc /= 2) {
+        if ((tc * bpp) % 4 != 0) continue;
+        for (int tr : kRowsCand) {
+            ResizeTile g;
+            g.tr = tr;
+            g.tc = tc;
+            for (int oy0 = 0; oy0 < out_h; oy0 += tr)
+                g.nr_max = std::max(g.nr_max, t.vfirst_host[std::min(oy0 + tr, out_h) - 1] + t.vtaps - t.vfirst_host[oy0]);
+            for (int ox0 = 0; ox0 < out_w; ox0 += tc)
+                g.nc_max = std::max(g.nc_max, t.hfirst_host[std::min(ox0 + tc, out_w) - 1] + t.htaps - t.hfirst_host[ox0]);
+            g.ch = 8;
+            int64_t const floats = 512 + ((tr * t.vtaps + 3) & ~3) + (int64_t)g.nr_max * tc * bpp + (int64_t)g.ch * (g.nc_max + kt) * bpp;
+            if (floats * 4 <= 100 * 1024) {
+                g.smem_bytes = (int)(floats * 4);
+                best = g;
+                break;
+            }
+        }
+    }
+    return best;
+}
+
+template <int BPP>
+bool launch_resize_tile(cudaStream_t s, uint8_t const* in, int in_w, int in_h, int stride, ResizeDeviceTables const& t,
+                        uint8_t* out, int out_w, int out_h) {
+    int const kt = t.htaps <= 4 ? 4 : t.htaps <= 8 ? 8 : t.htaps <= 16 ? 16 : t.htaps <= 32 ? 32 : 0;
+    if (kt == 0 || !t.hfirst_host || !t.vfirst_host) return false;
+    ResizeTile const g = plan_resize_tile(t, BPP, kt, out_w, out_h);
+    if (g.tr == 0) return false;
+    dim3 grid(ceil_div(out_w, g.tc), ceil_div(out_h, g.tr));
+    auto go = [&](auto kernel) {
+        set_smem_limit(kernel, g.smem_bytes);
+        kernel<<<grid, 256, g.smem_bytes, s>>>(in, in_w, in_h, stride, t, g, out, out_w, out_h);
+    };
+    switch (kt) {
+        case 4: go(resize_tile_kernel<BPP, 4>); break;
+        case 8: go(resize_tile_kernel<BPP, 8>); break;
+        case 16: go(resize_tile_kernel<BPP, 16>); break;
+        default: go(resize_tile_kernel<BPP, 32>); break;
+    }
+    KERNEL_CHECK();
+    return true;
+}
+
 }  // namespace
+
+size_t resize_scratch_floats(ResizeDeviceTables const& t, int in_h, int bpp, int out_w, int out_h) {
+    int const kt = t.htaps <= 4 ? 4 : t.htaps <= 8 ? 8 : t.htaps <= 16 ? 16 : t.htaps <= 32 ? 32 : 0;
+    bool const tiled = kt != 0 && t.hfirst_host && t.vfirst_host && (bpp == 1 || bpp == 3 || bpp == 4) &&
+                       plan_resize_tile(t, bpp, kt, out_w, out_h).tr != 0;
+    return tiled ? 0 : (size_t)in_h * out_w * bpp;  // only the two-pass fallback needs an intermediate
+}
 
 void resize_srgb(cudaStream_t s, uint8_t const* in, int in_w, int in_h, int stride, int bpp, ResizeDeviceTables const& t,
                  float* scratch, uint8_t* out, int out_w, int out_h) {
+    ProfScope prof(s, CAT_RESIZE, 0, (double)in_h * in_w * bpp + (double)out_h * out_w * bpp);
+    bool done = false;
+    if (bpp == 1) done = launch_resize_tile<1>(s, in, in_w, in_h, stride, t, out, out_w, out_h);
+    else if (bpp == 3) done = launch_resize_tile<3>(s, in, in_w, in_h, stride, t, out, out_w, out_h);
+    else if (bpp == 4) done = launch_resize_tile<4>(s, in, in_w, in_h, stride, t, out, out_w, out_h);
+    if (done) return;
+    DLIMG_ASSERT(scratch != nullptr);
     int64_t const n1 = (int64_t)in_h * out_w * bpp;
-    ProfScope prof(s, CAT_RESIZE, 0, (double)in_h * stride + (double)out_h * out_w * bpp);
     resize_h_kernel<<<(unsigned)ceil_div64(n1, 256), 256, 0, s>>>(in, in_w, in_h, stride, bpp, out_w, t.decode, t.hfirst,
                                                                  t.hweights, t.htaps, scratch);
     KERNEL_CHECK();
@@ -440,10 +777,14 @@ void resize_srgb(cudaStream_t s, uint8_t const* in, int in_w, int in_h, int stri
 void image_tensor(cudaStream_t s, uint8_t const* in, int w, int h, int stride, int channels, float* out) {
     int cmap[3];
     channel_map(channels, cmap);
-    int64_t const n = (int64_t)w * h;
-    ProfScope prof(s, CAT_IMAGE_TENSOR, 0, (double)h * stride + (double)n * 12);
-    image_tensor_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(in, w, h, stride, bytes_per_pixel(channels), cmap[0],
-                                                                    cmap[1], cmap[2], out);
+    int64_t const n = (int64_t)((w + 3) / 4) * h;
+    ProfScope prof(s, CAT_IMAGE_TENSOR, 0, (double)h * w * bytes_per_pixel(channels) + (double)w * h * 12);
+    unsigned const blocks = (unsigned)ceil_div64(n, 256);
+    switch (bytes_per_pixel(channels)) {
+        case 1: image_tensor_kernel<1><<<blocks, 256, 0, s>>>(in, w, h, stride, cmap[0], cmap[1], cmap[2], out); break;
+        case 3: image_tensor_kernel<3><<<blocks, 256, 0, s>>>(in, w, h, stride, cmap[0], cmap[1], cmap[2], out); break;
+        default: image_tensor_kernel<4><<<blocks, 256, 0, s>>>(in, w, h, stride, cmap[0], cmap[1], cmap[2], out); break;
+    }
     KERNEL_CHECK();
 }
 
@@ -460,7 +801,7 @@ void mask_postprocess_contiguous(cudaStream_t s, float const* low_res, int64_t p
 void threshold_mask(cudaStream_t s, float const* logits, int th, int tw, int w, int h, uint8_t* out) {
     DLIMG_ASSERT(w <= tw && h <= th);
     ProfScope prof(s, CAT_MASK_POST, 0, (double)w * h * 5);
-    int64_t const n = (int64_t)w * h;
+    int64_t const n = ((int64_t)w * h + 3) / 4;
     threshold_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(logits, tw, w, h, out);
     KERNEL_CHECK();
 }

@@ -1,6 +1,6 @@
 // prepost_kernels.cuh -- byte/pixel kernels either side of the network: resize (reference
 // image.cpp:37-51), channel map (segmentation.cpp:81-106), mask upsample + threshold
-// (decoder-graph post-processing, SURVEY A.5, + segmentation.cpp:108-116).  All HBM-bound.
+// (decoder-graph post-processing, SURVEY A.5, + segmentation.cpp:108-116).
 #pragma once
 
 #include "../common.hpp"
@@ -36,10 +36,15 @@ struct ResizeDeviceTables {
     float const* encode_threshold;  // [256]
     int const* hfirst; float const* hweights; int htaps;
     int const* vfirst; float const* vweights; int vtaps;
+    int const* hfirst_host = nullptr;  // host copies of the first-tap tables: the tile planner reads them
+    int const* vfirst_host = nullptr;
 };
 
-// u8 (in_h, in_w, bpp) with byte stride -> packed u8 (out_h, out_w, bpp).  `scratch` holds
-// in_h*out_w*bpp floats.
+// Floats of scratch resize_srgb needs: 0 when the single-kernel tile form applies (<= 32 horizontal taps and a tile
+// that fits shared memory), in_h*out_w*bpp for the two-pass fallback.
+size_t resize_scratch_floats(ResizeDeviceTables const& t, int in_h, int bpp, int out_w, int out_h);
+
+// u8 (in_h, in_w, bpp) with byte stride -> packed u8 (out_h, out_w, bpp).
 void resize_srgb(cudaStream_t s, uint8_t const* in, int in_w, int in_h, int stride, int bpp, ResizeDeviceTables const& t,
                  float* scratch, uint8_t* out, int out_w, int out_h);
 

@@ -1,7 +1,7 @@
 // t2i_attention.cu -- token -> image attention core of the SAM two-way transformer, flash-decoding style.
 //
 // 7 query tokens x 8 heads (16 dims each) attend to 4096 image keys.  Every K / V row is 128 contiguous
-// floats (all heads), so a warp streams whole rows with one coalesced 512-byte load each: lane l owns
+// 16-bit values (all heads), so a warp streams whole rows with one coalesced 256-byte load each: lane l owns
 // dims 4l..4l+3 (head l/4), the 4 lanes of a head finish the 16-dim dot product with two shuffles, and
 // each lane keeps an online-softmax state (max, sum, 4 accumulators) for the 7 tokens.  Keys are split
 // over 8 warps x kT2iSplits blocks per prompt; partial (max, sum, acc) triples are merged in shared memory
@@ -19,16 +19,22 @@ constexpr int kWarps = 8;
 constexpr int kChunk = 4;  // keys per warp iteration (8 independent 512-byte row loads in flight)
 constexpr int kPartStride = 128 + 16;  // per (split, token): 128 accumulators, 8 maxima, 8 sums
 
-__global__ void __launch_bounds__(kWarps * 32) t2i_flash_kernel(float const* __restrict__ q, float const* __restrict__ K,
-                                                                float const* __restrict__ V, int64_t kv_stride,
-                                                                float* __restrict__ part) {
+__device__ __forceinline__ float4 load4(act_t const* p) {
+    uint2 const u = __ldg(reinterpret_cast<uint2 const*>(p));
+    float2 const a = act22f2(*reinterpret_cast<act2_t const*>(&u.x)), b = act22f2(*reinterpret_cast<act2_t const*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void __launch_bounds__(kWarps * 32) t2i_flash_kernel(float const* __restrict__ q, act_t const* __restrict__ base,
+                                                                act_t const* const* __restrict__ ptrs, int64_t prompt_stride,
+                                                                int pitch, int v_off, float* __restrict__ part) {
     __shared__ float sm_acc[kWarps][kTokens][128];
     __shared__ float sm_m[kWarps][kTokens][kHeads];
     __shared__ float sm_s[kWarps][kTokens][kHeads];
     int const p = blockIdx.x, split = blockIdx.y;
     int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float const* Kp = K + (size_t)p * kv_stride + 4 * lane;
-    float const* Vp = V + (size_t)p * kv_stride + 4 * lane;
+    act_t const* Kp = (ptrs ? ptrs[p] : base + (size_t)p * prompt_stride) + 4 * lane;
+    act_t const* Vp = Kp + v_off;
 
     float qr[kTokens][4];
 #pragma unroll
@@ -49,8 +55,8 @@ __global__ void __launch_bounds__(kWarps * 32) t2i_flash_kernel(float const* __r
         float4 kk[kChunk], vv[kChunk];
 #pragma unroll
         for (int c = 0; c < kChunk; ++c) {
-            kk[c] = __ldg(reinterpret_cast<float4 const*>(Kp + (size_t)(i + c) * 128));
-            vv[c] = __ldg(reinterpret_cast<float4 const*>(Vp + (size_t)(i + c) * 128));
+            kk[c] = load4(Kp + (size_t)(i + c) * pitch);
+            vv[c] = load4(Vp + (size_t)(i + c) * pitch);
         }
 #pragma unroll
         for (int t = 0; t < kTokens; ++t) {
@@ -133,13 +139,13 @@ __global__ void __launch_bounds__(128) t2i_combine_kernel(float const* __restric
 
 }  // namespace
 
-void token_to_image_attention(cudaStream_t s, float const* q, float const* K, float const* V, int64_t kv_stride, int P,
-                              float* scratch, float* out) {
+void token_to_image_attention(cudaStream_t s, float const* q, act_t const* base, act_t const* const* ptrs, int64_t prompt_stride,
+                              int pitch, int v_off, int P, float* scratch, float* out) {
     static_assert(kT2iScratchPerPrompt == (size_t)kT2iSplits * kTokens * kPartStride, "scratch layout");
     static_assert(kImgTokens % (kT2iSplits * kWarps * kChunk) == 0, "key split must be even");
     {
-        ProfScope prof(s, CAT_DEC_ATTN, 4.0 * P * kTokens * kImgTokens * 128, (double)P * kImgTokens * 128 * 8);
-        t2i_flash_kernel<<<dim3(P, kT2iSplits), kWarps * 32, 0, s>>>(q, K, V, kv_stride, scratch);
+        ProfScope prof(s, CAT_DEC_ATTN, 4.0 * P * kTokens * kImgTokens * 128, (double)P * kImgTokens * 128 * 4);
+        t2i_flash_kernel<<<dim3(P, kT2iSplits), kWarps * 32, 0, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
         KERNEL_CHECK();
     }
     ProfScope prof(s, CAT_DEC_ATTN);

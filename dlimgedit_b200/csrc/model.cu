@@ -275,12 +275,47 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
     dec_.no_mask.upload(wf.get(P + "no_mask_embed.weight", {1, 256}).data);
     dec_.iou_token.upload(wf.get(D + "iou_token.weight", {1, 256}).data);
     dec_.mask_tokens.upload(wf.get(D + "mask_tokens.weight", {4, 256}).data);
+    // dense positional encoding of the 64 x 64 grid (a constant of the model): only its projections are kept
+    DeviceBuffer<float> dense_pe((size_t)dec::kImgTokens * dec::kDim);
+    dec::dense_pe(nullptr, dec_.gaussian.get(), dense_pe.get());
+    // [Wa; Wb; Wc] (rows concatenated) as one 16-bit GEMM operand + the table pos @ [Wa^T | 0 | Wc^T] (see DecoderW)
+    auto load_image_proj = [&](std::vector<std::pair<std::string, bool>> const& parts, Linear16& lin, DeviceBuffer<act_t>& pos_table) {
+        int const n = 128 * (int)parts.size();
+        std::vector<float> w((size_t)n * 256), wpos((size_t)n * 256, 0.f), bias((size_t)n);
+        for (size_t i = 0; i < parts.size(); ++i) {
+            auto const& pw = wf.get(parts[i].first + ".weight", {128, 256}).data;
+            auto const& pb = wf.get(parts[i].first + ".bias", {128}).data;
+            std::copy(pw.begin(), pw.end(), w.begin() + i * 128 * 256);
+            std::copy(pb.begin(), pb.end(), bias.begin() + i * 128);
+            if (parts[i].second) std::copy(pw.begin(), pw.end(), wpos.begin() + i * 128 * 256);  // this part sees keys + pos
+        }
+        lin.n = n;
+        lin.k = 256;
+        lin.w.upload(to_act(w));
+        lin.b.upload(bias);
+        DeviceBuffer<float> wpos_d, table((size_t)dec::kImgTokens * n);
+        wpos_d.upload(wpos);
+        gemm::Epilogue e;
+        e.out_f32 = 1;
+        e.ldc = n;
+        gemm::launch_simt(nullptr, true, gemm::Operand{dense_pe.get(), dec::kImgTokens, 256, 256}, gemm::Operand{wpos_d.get(), n, 256, 256},
+                          table.get(), e);  // fp32 CUDA-core GEMM, once at load
+        pos_table.allocate((size_t)dec::kImgTokens * n);
+        dec::f32_to_act(nullptr, table.get(), (int64_t)dec::kImgTokens * n, pos_table.get());
+        CUDA_CHECK(cudaDeviceSynchronize());
+    };
     for (int i = 0; i < 2; ++i) {
         std::string const p = D + "transformer.layers." + std::to_string(i);
         DecLayerW& l = dec_.layers[i];
         l.self_attn = load_attn(wf, p + ".self_attn", 256, 256);
-        l.t2i = load_attn(wf, p + ".cross_attn_token_to_image", 256, 128);
-        l.i2t = load_attn(wf, p + ".cross_attn_image_to_token", 256, 128);
+        l.t2i_q = load_linear32(wf, p + ".cross_attn_token_to_image.q_proj", 128, 256);
+        l.t2i_o = load_linear32(wf, p + ".cross_attn_token_to_image.out_proj", 256, 128);
+        l.i2t_k = load_linear32(wf, p + ".cross_attn_image_to_token.k_proj", 128, 256);
+        l.i2t_v = load_linear32(wf, p + ".cross_attn_image_to_token.v_proj", 128, 256);
+        l.i2t_out = load_linear16(wf, p + ".cross_attn_image_to_token.out_proj", 256, 128);
+        load_image_proj({{p + ".cross_attn_token_to_image.k_proj", true}, {p + ".cross_attn_token_to_image.v_proj", false},
+                         {p + ".cross_attn_image_to_token.q_proj", true}},
+                        dec_.kvq[i], dec_.pos_kvq[i]);
         l.n1 = load_norm(wf, p + ".norm1", 256);
         l.n2 = load_norm(wf, p + ".norm2", 256);
         l.n3 = load_norm(wf, p + ".norm3", 256);
@@ -288,7 +323,12 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
         l.lin1 = load_linear32(wf, p + ".mlp.lin1", 2048, 256);
         l.lin2 = load_linear32(wf, p + ".mlp.lin2", 256, 2048);
     }
-    dec_.final_attn = load_attn(wf, D + "transformer.final_attn_token_to_image", 256, 128);
+    {
+        std::string const p = D + "transformer.final_attn_token_to_image";
+        dec_.final_q = load_linear32(wf, p + ".q_proj", 128, 256);
+        dec_.final_o = load_linear32(wf, p + ".out_proj", 256, 128);
+        load_image_proj({{p + ".k_proj", true}, {p + ".v_proj", false}}, dec_.kv_final, dec_.pos_kv_final);
+    }
     dec_.norm_final = load_norm(wf, D + "transformer.norm_final_attn", 256);
     {
         // ConvTranspose2d(256, 64, 2, 2): weight (cin, cout, 2, 2) -> GEMM operand ((dy,dx,co), ci)
@@ -302,7 +342,7 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
             for (int co = 0; co < 64; ++co) bb[(size_t)t * 64 + co] = b.data[(size_t)co];
         dec_.up1.n = 256;
         dec_.up1.k = 256;
-        dec_.up1.w.upload(o);
+        dec_.up1.w.upload(to_act(o));
         dec_.up1.b.upload(bb);
         dec_.up_ln = load_norm(wf, D + "output_upscaling.1", 64);
         auto const& w2 = wf.get(D + "output_upscaling.3.weight", {64, 32, 2, 2});
@@ -315,7 +355,7 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
             for (int c2 = 0; c2 < 32; ++c2) bb2[(size_t)t * 32 + c2] = b2.data[(size_t)c2];
         dec_.up2.n = 128;
         dec_.up2.k = 64;
-        dec_.up2.w.upload(o2);
+        dec_.up2.w.upload(to_act(o2));
         dec_.up2.b.upload(bb2);
     }
     for (int m = 0; m < 4; ++m) {
@@ -328,8 +368,6 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
     dec_.iou[1] = load_linear32(wf, D + "iou_prediction_head.layers.1", 256, 256);
     dec_.iou[2] = load_linear32(wf, D + "iou_prediction_head.layers.2", 4, 256);
 
-    dec_.dense_pe.allocate((size_t)dec::kImgTokens * dec::kDim);
-    dec::dense_pe(nullptr, dec_.gaussian.get(), dec_.dense_pe.get());
     CUDA_CHECK(cudaDeviceSynchronize());
 }
 
@@ -347,18 +385,17 @@ EncoderWorkspace::EncoderWorkspace(int mb) : max_batch(mb) {
 
 DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
     size_t const P = (size_t)mp;
-    coords.allocate(P * 4);
-    labels.allocate(P * 2);
+    param_block.allocate(DecoderParams::bytes(mp));
     for (auto* b : {&tok0, &queries, &tq, &tk, &tv, &ta, &tmp}) b->allocate(P * 7 * 256);
     t128a.allocate(P * 7 * 128);
     t128b.allocate(P * 7 * 128);
     hid.allocate(P * 7 * 2048);
-    h1.allocate(P * 4 * 256);
-    h2.allocate(P * 4 * 256);
     hyper.allocate(P * 4 * 32);
     iou.allocate(P * 4);
-    for (auto* b : {&keys, &kpe, &big256}) b->allocate(P * 4096 * 256);
-    for (auto* b : {&Kp, &Vp, &Qp, &ao}) b->allocate(P * 4096 * 128);
+    keys.allocate(P * 4096 * 256);
+    big.allocate(P * 4096 * 256);
+    kvq.allocate(P * 4096 * 384);
+    ao.allocate(P * 4096 * 128);
     up2.allocate(P * 16384 * 128);
     low.allocate(P * 4 * 65536);
     plane_index.allocate(P * 3);
@@ -366,14 +403,24 @@ DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
     t2i_scratch.allocate(P * dec::kT2iScratchPerPrompt);
 }
 
+DecoderParams DecoderWorkspace::layout(uint8_t* base, int P) {
+    DecoderParams d;
+    d.coords = reinterpret_cast<float*>(base);
+    d.labels = d.coords + (size_t)P * 4;
+    d.keys0 = reinterpret_cast<act_t const**>(d.labels + (size_t)P * 2);
+    d.kvq0 = d.keys0 + P;
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 void SamModel::gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 const& l, void* out, int act,
-                      act_t const* residual, float2 const* ln_stats, bool out_f32, int ln_parts, float2* stats_out) const {
+                      act_t const* residual, float2 const* ln_stats, bool out_f32, int ln_parts, float2* stats_out, int res_mod) const {
     gemm::Operand A{a, rows, l.k, l.k};
     gemm::Operand B{l.w.get(), l.n, l.k, l.k};
     gemm::Epilogue e;
     e.bias = l.b.get();
     e.residual = residual;
+    e.res_mod = res_mod;
     e.act = act;
     e.out_f32 = out_f32 ? 1 : 0;
     e.ldc = l.n;
@@ -398,7 +445,7 @@ void SamModel::gemm32(cudaStream_t s, float const* a, int64_t rows, Linear32 con
 }
 
 void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const* images, int batch, int w, int h,
-                      int channels, float* emb_out, Tap* tap, float* emb_nchw_out, bool finish) const {
+                      int channels, float* emb_nchw_out, act_t* keys0_out, act_t* kvq0_out, Tap* tap, bool finish) const {
     DLIMG_ASSERT(batch >= 1 && batch <= ws.max_batch);
     int64_t const B = batch;
     using gemm::ACT_GELU;
@@ -526,43 +573,20 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         gemm::launch_conv3x3(s, ws.big[1].get(), batch, 64, 64, 256, gemm::Operand{enc_.neck2.w.get(), enc_.neck2.n, enc_.neck2.k, enc_.neck2.k},
                              ws.big[0].get(), e, num_sms_);
     }
-    if (finish) neck_finish(s, ws, batch, emb_out, emb_nchw_out, tap);
+    if (finish) neck_finish(s, ws, batch, emb_nchw_out, keys0_out, kvq0_out);
 }
 
-void SamModel::neck_finish(cudaStream_t s, EncoderWorkspace& ws, int batch, float* emb_out, float* emb_nchw_out, Tap* tap) const {
-    int64_t const B = batch;
-    if (emb_nchw_out)
-        enc::layernorm256_tokens_nchw(s, ws.big[0].get(), batch, 4096, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f, emb_out,
-                                      emb_nchw_out);
-    else
-        enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f,
-                            emb_out, true);
-    if (tap && tap->name && std::strcmp(tap->name, "neck") == 0) {
-        size_t const n = (size_t)B * 4096 * 256;
-        if (n > tap->capacity) fail("tap buffer too small for neck");
-        CUDA_CHECK(cudaMemcpyAsync(tap->out, emb_out, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        tap->written = n;
-    }
+// Final LayerNorm2d of the neck -> the reference's NCHW fp32 embedding + the decoder's 16-bit layer-0 image stream, then the
+// layer-0 image-side projections of the two-way transformer (tokens -> image keys / values, image -> tokens queries): they
+// depend on the image only, so they are computed here, once per image and batched over the chunk, not per prompt.
+void SamModel::neck_finish(cudaStream_t s, EncoderWorkspace& ws, int batch, float* emb_nchw_out, act_t* keys0_out, act_t* kvq0_out) const {
+    enc::layernorm256_tokens_nchw(s, ws.big[0].get(), batch, 4096, enc_.neck_ln2.g.get(), enc_.neck_ln2.b.get(), 1e-6f,
+                                  dec_.no_mask.get(), keys0_out, emb_nchw_out);
+    gemm16(s, keys0_out, (int64_t)batch * dec::kImgTokens, dec_.kvq[0], kvq0_out, gemm::ACT_NONE, dec_.pos_kvq[0].get(), nullptr, false,
+           0, nullptr, dec::kImgTokens);
 }
 
 // ---------------------------------------------------------------------------------------------
-void SamModel::prepare_embedding(cudaStream_t s, float const* emb, EmbeddingCache& c) const {
-    size_t const n256 = (size_t)dec::kImgTokens * 256, n128 = (size_t)dec::kImgTokens * 128;
-    if (!c.keys0) {
-        c.keys0.allocate(n256);
-        c.kpe0.allocate(n256);
-        c.K0.allocate(n128);
-        c.V0.allocate(n128);
-        c.Q0i.allocate(n128);
-    }
-    dec::embed_prepare(s, emb, dec_.no_mask.get(), dec_.dense_pe.get(), dec::kImgTokens, c.keys0.get(), c.kpe0.get());
-    DecLayerW const& l0 = dec_.layers[0];
-    gemm32(s, c.kpe0.get(), dec::kImgTokens, l0.t2i.k, c.K0.get(), gemm::ACT_NONE);
-    gemm32(s, c.keys0.get(), dec::kImgTokens, l0.t2i.v, c.V0.get(), gemm::ACT_NONE);
-    gemm32(s, c.kpe0.get(), dec::kImgTokens, l0.i2t.q, c.Q0i.get(), gemm::ACT_NONE);
-    c.ready = true;
-}
-
 void SamModel::lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, int rows, Linear32 const& l, bool relu,
                    float* y, int64_t ys) const {
     // token-side Linears on contiguous rows go to the tensor cores (tf32);
@@ -588,61 +612,52 @@ void SamModel::attn_tokens(cudaStream_t s, DecoderWorkspace& ws, AttnW const& a,
                       ws.queries.get(), nullptr);
 }
 
-void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, EmbeddingCache const& cache, int P) const {
+void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P) const {
     DLIMG_ASSERT(P >= 1 && P <= ws.max_prompts);
-    DLIMG_ASSERT(cache.ready);
+    DecoderParams const prm = DecoderWorkspace::layout(ws.param_block.get(), P);
     int const R = P * dec::kTokens;
     int64_t const IR = (int64_t)P * dec::kImgTokens;  // image-side rows
-    int64_t const img_stride = (int64_t)dec::kImgTokens * 128;
+    int64_t const kvq_stride = (int64_t)dec::kImgTokens * 384, kv_stride = (int64_t)dec::kImgTokens * 256;
 
     dec::PromptParams pp{dec_.gaussian.get(), dec_.point_embed.get(), dec_.not_a_point.get(), dec_.iou_token.get(),
                          dec_.mask_tokens.get()};
-    dec::prompt_tokens(s, ws.coords.get(), ws.labels.get(), P, pp, ws.tok0.get());
+    dec::prompt_tokens(s, prm.coords, prm.labels, P, pp, ws.tok0.get());
     CUDA_CHECK(cudaMemcpyAsync(ws.queries.get(), ws.tok0.get(), sizeof(float) * (size_t)R * 256, cudaMemcpyDeviceToDevice, s));
 
-    float const* keys = cache.keys0.get();  // layer 0 reads the shared, prompt-independent tensors
-    float const* kpe = cache.kpe0.get();
     for (int li = 0; li < 2; ++li) {
         DecLayerW const& l = dec_.layers[li];
         bool const first = li == 0;
         // (1) token self-attention (layer 0: no positional encoding, output replaces the queries)
         attn_tokens(s, ws, l.self_attn, !first, !first, l.n1, P);
+        // image-side projections [K | V | Q] of this layer from the image stream: layer 0's depend on the image only and
+        // come with the embedding (per-prompt tables); layer 1's are one GEMM with the position terms added by its epilogue
+        if (!first)
+            gemm16(s, ws.keys.get(), IR, dec_.kvq[1], ws.kvq.get(), gemm::ACT_NONE, dec_.pos_kvq[1].get(), nullptr, false, 0, nullptr,
+                   dec::kImgTokens);
         // (2) tokens attend to the image
-        lin(s, ws.queries.get(), 256, ws.tok0.get(), R, l.t2i.q, false, ws.t128a.get(), 128);
-        if (first) {
-            dec::token_to_image_attention(s, ws.t128a.get(), cache.K0.get(), cache.V0.get(), 0, P, ws.t2i_scratch.get(), ws.t128b.get());
-        } else {
-            gemm32(s, kpe, IR, l.t2i.k, ws.Kp.get(), gemm::ACT_NONE);
-            gemm32(s, keys, IR, l.t2i.v, ws.Vp.get(), gemm::ACT_NONE);
-            dec::token_to_image_attention(s, ws.t128a.get(), ws.Kp.get(), ws.Vp.get(), img_stride, P, ws.t2i_scratch.get(), ws.t128b.get());
-        }
-        lin(s, ws.t128b.get(), 128, nullptr, R, l.t2i.o, false, ws.tmp.get(), 256);
+        lin(s, ws.queries.get(), 256, ws.tok0.get(), R, l.t2i_q, false, ws.t128a.get(), 128);
+        dec::token_to_image_attention(s, ws.t128a.get(), ws.kvq.get(), first ? prm.kvq0 : nullptr, kvq_stride, 384, 128, P,
+                                      ws.t2i_scratch.get(), ws.t128b.get());
+        lin(s, ws.t128b.get(), 128, nullptr, R, l.t2i_o, false, ws.tmp.get(), 256);
         dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, l.n2.g.get(), l.n2.b.get(), nullptr, 0, ws.queries.get(), nullptr);
         // (3) token MLP
         lin(s, ws.queries.get(), 256, nullptr, R, l.lin1, true, ws.hid.get(), 2048);
         lin(s, ws.hid.get(), 2048, nullptr, R, l.lin2, false, ws.tmp.get(), 256);
         dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, l.n3.g.get(), l.n3.b.get(), nullptr, 0, ws.queries.get(), nullptr);
-        // (4) image attends to the tokens; keys <- LN(keys + out_proj(attn)), and keys + pos for the next consumer
-        lin(s, ws.queries.get(), 256, ws.tok0.get(), R, l.i2t.k, false, ws.t128a.get(), 128);
-        lin(s, ws.queries.get(), 256, nullptr, R, l.i2t.v, false, ws.t128b.get(), 128);
-        if (first) {
-            dec::image_to_token_attention(s, cache.Q0i.get(), 0, ws.t128a.get(), ws.t128b.get(), P, ws.ao.get());
-        } else {
-            gemm32(s, kpe, IR, l.i2t.q, ws.Qp.get(), gemm::ACT_NONE);
-            dec::image_to_token_attention(s, ws.Qp.get(), img_stride, ws.t128a.get(), ws.t128b.get(), P, ws.ao.get());
-        }
-        gemm32(s, ws.ao.get(), IR, l.i2t.o, ws.big256.get(), gemm::ACT_NONE);
-        dec::layernorm256(s, ws.big256.get(), keys, first ? dec::kImgTokens : IR, IR, l.n4.g.get(), l.n4.b.get(),
-                          dec_.dense_pe.get(), dec::kImgTokens, ws.keys.get(), ws.kpe.get());
-        keys = ws.keys.get();
-        kpe = ws.kpe.get();
+        // (4) image attends to the tokens: keys <- LN(keys + out_proj(attn)); Q is column block 2 of [K | V | Q]
+        lin(s, ws.queries.get(), 256, ws.tok0.get(), R, l.i2t_k, false, ws.t128a.get(), 128);
+        lin(s, ws.queries.get(), 256, nullptr, R, l.i2t_v, false, ws.t128b.get(), 128);
+        dec::image_to_token_attention(s, ws.kvq.get(), first ? prm.kvq0 : nullptr, kvq_stride, 384, 256, ws.t128a.get(), ws.t128b.get(),
+                                      P, ws.ao.get());
+        gemm16(s, ws.ao.get(), IR, l.i2t_out, ws.big.get(), gemm::ACT_NONE, nullptr);
+        dec::layernorm256_img(s, ws.big.get(), ws.keys.get(), first ? prm.keys0 : nullptr, P, l.n4.g.get(), l.n4.b.get(), ws.keys.get());
     }
     // final token -> image attention
-    lin(s, ws.queries.get(), 256, ws.tok0.get(), R, dec_.final_attn.q, false, ws.t128a.get(), 128);
-    gemm32(s, kpe, IR, dec_.final_attn.k, ws.Kp.get(), gemm::ACT_NONE);
-    gemm32(s, keys, IR, dec_.final_attn.v, ws.Vp.get(), gemm::ACT_NONE);
-    dec::token_to_image_attention(s, ws.t128a.get(), ws.Kp.get(), ws.Vp.get(), img_stride, P, ws.t2i_scratch.get(), ws.t128b.get());
-    lin(s, ws.t128b.get(), 128, nullptr, R, dec_.final_attn.o, false, ws.tmp.get(), 256);
+    gemm16(s, ws.keys.get(), IR, dec_.kv_final, ws.kvq.get(), gemm::ACT_NONE, dec_.pos_kv_final.get(), nullptr, false, 0, nullptr,
+           dec::kImgTokens);
+    lin(s, ws.queries.get(), 256, ws.tok0.get(), R, dec_.final_q, false, ws.t128a.get(), 128);
+    dec::token_to_image_attention(s, ws.t128a.get(), ws.kvq.get(), nullptr, kv_stride, 256, 128, P, ws.t2i_scratch.get(), ws.t128b.get());
+    lin(s, ws.t128b.get(), 128, nullptr, R, dec_.final_o, false, ws.tmp.get(), 256);
     dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, dec_.norm_final.g.get(), dec_.norm_final.b.get(), nullptr, 0,
                       ws.queries.get(), nullptr);
 
@@ -661,9 +676,9 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, EmbeddingCache const
     }
 
     // upscaling: two transposed 2x2/stride-2 convolutions as GEMMs in a blocked pixel layout
-    gemm32(s, keys, IR, dec_.up1, ws.big256.get(), gemm::ACT_NONE);
-    dec::layernorm64_gelu(s, ws.big256.get(), IR * 4, dec_.up_ln.g.get(), dec_.up_ln.b.get());
-    gemm32(s, ws.big256.get(), IR * 4, dec_.up2, ws.up2.get(), gemm::ACT_GELU);
+    gemm16(s, ws.keys.get(), IR, dec_.up1, ws.big.get(), gemm::ACT_NONE, nullptr);
+    dec::layernorm64_gelu(s, ws.big.get(), IR * 4, dec_.up_ln.g.get(), dec_.up_ln.b.get());
+    gemm16(s, ws.big.get(), IR * 4, dec_.up2, ws.up2.get(), gemm::ACT_GELU, nullptr);
     dec::mask_dot(s, ws.hyper.get(), ws.up2.get(), P, ws.low.get());
 }
 

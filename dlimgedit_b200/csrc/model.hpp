@@ -104,23 +104,33 @@ struct EncoderW {
     Norm neck_ln2;
 };
 
-struct AttnW { Linear32 q, k, v, o; };
+struct AttnW { Linear32 q, k, v, o; };  // token-side projections (fp32); the image-side ones live in DecoderW below
 struct DecLayerW {
-    AttnW self_attn, t2i, i2t;
+    AttnW self_attn;
+    Linear32 t2i_q, t2i_o;   // tokens -> image attention: query and output projections (token rows)
+    Linear32 i2t_k, i2t_v;   // image -> tokens attention: key / value projections (token rows)
+    Linear16 i2t_out;        // (256, 128) output projection of image -> tokens attention (image rows, 16-bit)
     Norm n1, n2, n3, n4;
     Linear32 lin1, lin2;
 };
 struct DecoderW {
     DeviceBuffer<float> gaussian, point_embed, not_a_point, no_mask, iou_token, mask_tokens;
     DecLayerW layers[2];
-    AttnW final_attn;
+    Linear32 final_q, final_o;
     Norm norm_final;
-    Linear32 up1;  // (256 = (dy,dx,co), 256)
+    // Image-side projections as 16-bit GEMM operands.  The projections that see `keys + pos` (attention keys of
+    // tokens -> image, queries of image -> tokens) are split as keys W^T + (pos W^T): the second term does not depend on the
+    // image or the prompt and is a (4096, N) table added by the GEMM epilogue (Epilogue::res_mod), so `keys + pos`
+    // is never materialised.
+    Linear16 kvq[2];                // (384, 256): [t2i.k | t2i.v | i2t.q] of layer 0 / 1, concatenated along N
+    DeviceBuffer<act_t> pos_kvq[2]; // (4096, 384): [pos Wk^T | 0 | pos Wq^T]
+    Linear16 kv_final;              // (256, 256): [k | v] of the final tokens -> image attention
+    DeviceBuffer<act_t> pos_kv_final;  // (4096, 256): [pos Wk^T | 0]
+    Linear16 up1;  // (256 = (dy,dx,co), 256)
     Norm up_ln;    // LayerNorm2d(64)
-    Linear32 up2;  // (128 = (ey,ex,c2), 64)
+    Linear16 up2;  // (128 = (ey,ex,c2), 64)
     Linear32 hyper[4][3];
     Linear32 iou[3];
-    DeviceBuffer<float> dense_pe;  // (4096, 256)
 };
 
 // ---- workspaces -------------------------------------------------------------------------------
@@ -132,29 +142,35 @@ struct EncoderWorkspace {
     explicit EncoderWorkspace(int max_batch);
 };
 
+// Per-prompt inputs of one decoder pass, uploaded by the engine in ONE copy: prompt p of the pass reads the
+// prompt-independent tensors of ITS image through keys0[p] / kvq0[p], so prompts of different images share a pass.
+struct DecoderParams {
+    float* coords = nullptr;               // (P, 2, 2) in 1024-space
+    float* labels = nullptr;               // (P, 2)
+    act_t const** keys0 = nullptr;         // (P) -> (4096, 256): embedding + no_mask_embed of the prompt's image
+    act_t const** kvq0 = nullptr;          // (P) -> (4096, 384): its layer-0 [K | V | Q] projections
+    static size_t bytes(int P) { return (size_t)P * (6 * sizeof(float) + 2 * sizeof(void*)); }
+};
+
 struct DecoderWorkspace {
     int max_prompts = 0;
-    DeviceBuffer<float> coords, labels;                      // (P,2,2), (P,2)
+    DeviceBuffer<uint8_t> param_block;                       // DecoderParams::bytes(max_prompts), laid out per pass by layout()
     DeviceBuffer<float> tok0, queries, tq, tk, tv, ta, tmp;  // (P,7,256)
     DeviceBuffer<float> t128a, t128b;                        // (P,7,128)
     DeviceBuffer<float> hid;                                 // (P,7,2048)
-    DeviceBuffer<float> h1, h2;                              // (P*4,256)
     DeviceBuffer<float> hyper, iou;                          // (P,4,32), (P,4)
-    DeviceBuffer<float> keys, kpe, big256;                   // (P,4096,256)
-    DeviceBuffer<float> Kp, Vp, Qp, ao;                      // (P,4096,128)
-    DeviceBuffer<float> up2;                                 // (P,16384,128)
+    DeviceBuffer<act_t> keys, big;                           // (P,4096,256) image stream / GEMM output in front of a LayerNorm
+    DeviceBuffer<act_t> kvq;                                 // (P,4096,384) [K | V | Q] of layer 1; (P,4096,256) [K | V] final
+    DeviceBuffer<act_t> ao;                                  // (P,4096,128) image -> tokens attention output
+    DeviceBuffer<act_t> up2;                                 // (P,16384,128)
     DeviceBuffer<float> low;                                 // (P,4,256,256)
     DeviceBuffer<int> plane_index;                           // (P*3)
     DeviceBuffer<float> iou_sel;                             // (P*3)
     DeviceBuffer<float> t2i_scratch;                         // split-key partials of the token->image attention
     explicit DecoderWorkspace(int max_prompts);
-};
-
-// Prompt-independent decoder inputs derived once per image embedding.
-struct EmbeddingCache {
-    DeviceBuffer<float> keys0, kpe0;     // (4096, 256): embedding + no_mask_embed, and + dense PE
-    DeviceBuffer<float> K0, V0, Q0i;     // (4096, 128): layer-0 projections that do not depend on the prompt
-    bool ready = false;
+    // The parameter block of a pass with P prompts, based at `base` (the device block, or a host staging copy of it):
+    // [coords P*4 floats | labels P*2 floats | keys0 P pointers | kvq0 P pointers], DecoderParams::bytes(P) in all.
+    static DecoderParams layout(uint8_t* base, int P);
 };
 
 struct Tap {  // debug: copy a named activation as fp32 to a device buffer
@@ -169,25 +185,25 @@ class SamModel {
     SamModel(std::string const& weight_path, int num_sms);
 
     // images: `batch` device descriptors of u8 images with identical (w, h, channels), w, h <= 1024.
-    // emb_out: (batch, 4096, 256) fp32, token-major (row = y*64 + x).
-    // emb_nchw_out (optional): the same embedding as (batch, 256, 64, 64) fp32.  finish = false stops in front of the
-    // final LayerNorm2d (its input is ws.big[0]); neck_finish() then writes the embedding -- the engine captures the
-    // trunk into a CUDA graph and finishes eagerly into whichever store the call owns.
+    // Outputs per image: emb_nchw_out (batch, 256, 64, 64) fp32 (the reference's `image_embeddings`), keys0_out (batch, 4096,
+    // 256) 16-bit (embedding + no_mask_embed, token-major) and kvq0_out (batch, 4096, 384) 16-bit (the decoder's layer-0
+    // image-side projections, which depend on the image only).  finish = false stops in front of the final LayerNorm2d
+    // (its input is ws.big[0]); neck_finish() then writes the outputs -- the engine captures the trunk into a CUDA graph
+    // and finishes eagerly into whichever store the call owns.
     void encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const* images, int batch, int w, int h, int channels,
-                float* emb_out, Tap* tap = nullptr, float* emb_nchw_out = nullptr, bool finish = true) const;
-    void neck_finish(cudaStream_t s, EncoderWorkspace& ws, int batch, float* emb_out, float* emb_nchw_out, Tap* tap = nullptr) const;
+                float* emb_nchw_out, act_t* keys0_out, act_t* kvq0_out, Tap* tap = nullptr, bool finish = true) const;
+    void neck_finish(cudaStream_t s, EncoderWorkspace& ws, int batch, float* emb_nchw_out, act_t* keys0_out, act_t* kvq0_out) const;
 
-    void prepare_embedding(cudaStream_t s, float const* emb, EmbeddingCache& cache) const;
-
-    // Runs the prompt encoder + mask decoder for P prompts (coords/labels already uploaded into ws).
-    // Results: ws.low (P, 4, 256, 256) logits and ws.iou (P, 4).
-    void decode(cudaStream_t s, DecoderWorkspace& ws, EmbeddingCache const& cache, int P) const;
+    // Runs the prompt encoder + mask decoder for P prompts whose parameter block (DecoderWorkspace::layout(ws.param_block, P))
+    // has been filled by the engine.  Results: ws.low (P, 4, 256, 256) logits and ws.iou (P, 4).
+    void decode(cudaStream_t s, DecoderWorkspace& ws, int P) const;
 
     static StageCfg stage(int i);  // i = 1..3
 
   private:
     void gemm16(cudaStream_t s, act_t const* a, int64_t rows, Linear16 const& l, void* out, int act, act_t const* residual,
-                float2 const* ln_stats = nullptr, bool out_f32 = false, int ln_parts = 0, float2* stats_out = nullptr) const;
+                float2 const* ln_stats = nullptr, bool out_f32 = false, int ln_parts = 0, float2* stats_out = nullptr,
+                int res_mod = 0) const;
     void gemm32(cudaStream_t s, float const* a, int64_t rows, Linear32 const& l, float* out, int act) const;
     void lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, int rows, Linear32 const& l, bool relu, float* y,
              int64_t ys) const;

@@ -11,9 +11,28 @@ char const* kernel_cat_name(int cat) {
     return (cat >= 0 && cat < CAT_COUNT) ? names[cat] : "?";
 }
 
+namespace {
+thread_local Profiler* tl_profiler = nullptr;
+}
+
 Profiler& Profiler::get() {
+    if (tl_profiler) return *tl_profiler;
     static Profiler p;
     return p;
+}
+
+Profiler* Profiler::bind(Profiler* p) {
+    Profiler* const prev = tl_profiler;
+    tl_profiler = p;
+    return prev;
+}
+
+Profiler::~Profiler() {
+    for (auto& r : recs_) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto e : pool_) cudaEventDestroy(e);
 }
 
 void Profiler::enable(bool on) {

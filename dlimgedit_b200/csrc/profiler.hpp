@@ -18,7 +18,10 @@ char const* kernel_cat_name(int cat);
 
 class Profiler {
   public:
+    // The profiler of the environment bound to the calling thread (EnvironmentImpl::Scope), else a process-wide one.
     static Profiler& get();
+    static Profiler* bind(Profiler* p);  // returns the previous binding of this thread
+    ~Profiler();
     bool enabled() const { return enabled_; }
     void enable(bool on);
     void begin(cudaStream_t s, int cat, double flops, double bytes);
