@@ -1,6 +1,7 @@
-// image_io.cpp -- see image_io.hpp.  Minimal PNG / PNM codec written for this library (no stb).
+// image_io.cpp -- see image_io.hpp.  Minimal PNG / baseline-JPEG / PNM codec written for this library (no stb).
 #include "image_io.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -94,7 +95,11 @@ struct Huffman {
     }
 };
 
-std::vector<uint8_t> inflate(uint8_t const* data, size_t n) {
+constexpr uint32_t kMaxImageDim = 1u << 24;          // like stb_image's STBI_MAX_DIMENSIONS
+constexpr uint64_t kMaxImageBytes = (uint64_t)1 << 31;  // decoded pixels of one image
+
+// `limit`: the caller knows how many bytes the stream may expand to; anything beyond is a malformed (or hostile) file
+std::vector<uint8_t> inflate(uint8_t const* data, size_t n, size_t limit) {
     static uint16_t const lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     static uint16_t const lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
     static uint16_t const dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -113,6 +118,7 @@ std::vector<uint8_t> inflate(uint8_t const* data, size_t n) {
             uint32_t const len = br.p[br.pos] | (br.p[br.pos + 1] << 8);
             br.pos += 4;
             if (br.pos + len > br.n) fail("PNG: truncated stored block");
+            if (out.size() + len > limit) fail("PNG: deflate stream larger than the image it encodes");
             out.insert(out.end(), br.p + br.pos, br.p + br.pos + len);
             br.pos += len;
         } else if (type == 1 || type == 2) {
@@ -155,7 +161,10 @@ std::vector<uint8_t> inflate(uint8_t const* data, size_t n) {
             }
             for (;;) {
                 int sym = lit.decode(br);
-                if (sym < 256) out.push_back((uint8_t)sym);
+                if (sym < 256) {
+                    if (out.size() >= limit) fail("PNG: deflate stream larger than the image it encodes");
+                    out.push_back((uint8_t)sym);
+                }
                 else if (sym == 256) break;
                 else {
                     sym -= 257;
@@ -165,6 +174,7 @@ std::vector<uint8_t> inflate(uint8_t const* data, size_t n) {
                     if (ds >= 30) fail("PNG: invalid distance symbol");
                     size_t const d = dbase[ds] + br.bits(dext[ds]);
                     if (d > out.size()) fail("PNG: distance too far back");
+                    if (out.size() + (size_t)len > limit) fail("PNG: deflate stream larger than the image it encodes");
                     size_t const start = out.size() - d;
                     for (int k = 0; k < len; ++k) out.push_back(out[start + (size_t)k]);
                 }
@@ -192,6 +202,7 @@ uint8_t* load_png(std::vector<uint8_t> const& file, char const* path, int* exten
         if (pos + 12 + len > file.size()) fail(std::string("Failed to load image ") + path + ": truncated PNG");
         uint8_t const* d = &file[pos + 8];
         if (!std::memcmp(type, "IHDR", 4)) {
+            if (len != 13) fail(std::string("Failed to load image ") + path + ": malformed PNG header");
             w = be32(d); h = be32(d + 4); depth = d[8]; color = d[9]; interlace = d[12];
         } else if (!std::memcmp(type, "IDAT", 4)) {
             idat.insert(idat.end(), d, d + len);
@@ -203,9 +214,13 @@ uint8_t* load_png(std::vector<uint8_t> const& file, char const* path, int* exten
     int const ch = color == 0 ? 1 : color == 2 ? 3 : color == 6 ? 4 : 0;
     if (!w || !h || depth != 8 || !ch || interlace)
         fail(std::string("Failed to load image ") + path + ": only 8-bit grey/RGB/RGBA non-interlaced PNG is supported");
-    std::vector<uint8_t> raw = inflate(idat.data(), idat.size());
+    // sizes in 64 bits, bounded before anything is allocated (a 2^31 x 2^31 header must not wrap to a small buffer)
+    if (w > kMaxImageDim || h > kMaxImageDim || (uint64_t)w * h * (uint64_t)ch > kMaxImageBytes)
+        fail(std::string("Failed to load image ") + path + ": image too large");
     size_t const row = (size_t)w * ch;
-    if (raw.size() < (row + 1) * h) fail(std::string("Failed to load image ") + path + ": PNG data too short");
+    size_t const expect = (row + 1) * (size_t)h;
+    std::vector<uint8_t> raw = inflate(idat.data(), idat.size(), expect);
+    if (raw.size() < expect) fail(std::string("Failed to load image ") + path + ": PNG data too short");
     uint8_t* px = new uint8_t[row * h];
     for (uint32_t y = 0; y < h; ++y) {
         uint8_t const* src = &raw[(row + 1) * y];
@@ -243,20 +258,446 @@ uint8_t* load_pnm(std::vector<uint8_t> const& file, char const* path, int* exten
         }
         int v = 0;
         bool any = false;
-        while (pos < file.size() && file[pos] >= '0' && file[pos] <= '9') { v = v * 10 + (file[pos++] - '0'); any = true; }
+        while (pos < file.size() && file[pos] >= '0' && file[pos] <= '9') {
+            if (v > (int)kMaxImageDim) fail(std::string("Failed to load image ") + path + ": malformed PNM header");
+            v = v * 10 + (file[pos++] - '0');
+            any = true;
+        }
         if (!any) fail(std::string("Failed to load image ") + path + ": malformed PNM header");
         return v;
     };
     int const ch = file[1] == '5' ? 1 : 3;
     int const w = next_int(), h = next_int(), maxv = next_int();
     ++pos;  // single whitespace after maxval
-    if (maxv != 255 || w <= 0 || h <= 0 || pos + (size_t)w * h * ch > file.size())
+    if (maxv != 255 || w <= 0 || h <= 0 || (uint32_t)w > kMaxImageDim || (uint32_t)h > kMaxImageDim ||
+        (uint64_t)w * h * ch > kMaxImageBytes || pos + (size_t)w * h * ch > file.size())
         fail(std::string("Failed to load image ") + path + ": unsupported PNM variant");
     uint8_t* px = new uint8_t[(size_t)w * h * ch];
     std::memcpy(px, &file[pos], (size_t)w * h * ch);
     extent[0] = w;
     extent[1] = h;
     *channels = ch;
+    return px;
+}
+
+// ---- baseline JPEG (ITU T.81 sequential DCT, 8-bit, Huffman) ------------------------------------------------------
+// The reference's load_image is stbi_load (image.cpp:11-23), which reads JPEG; test/input/truck.jpg is the one real
+// fixture of the reference.  Restated from the published stb_image algorithm so that pixels come out the way the
+// reference sees them: integer IDCT with 12-bit constants, "hv_2" triangle-filter chroma upsampling, 20-bit fixed-point
+// YCbCr -> RGB.  Progressive and arithmetic-coded files are refused.
+struct JpegHuff {
+    uint8_t size[257];
+    uint16_t code[256];
+    uint8_t values[256];
+    int maxcode[18];
+    int delta[17];
+    int n = 0;
+    void build(uint8_t const* counts, uint8_t const* vals, int nvals) {
+        int k = 0;
+        for (int i = 0; i < 16; ++i)
+            for (int j = 0; j < counts[i]; ++j) size[k++] = (uint8_t)(i + 1);
+        size[k] = 0;
+        n = k;
+        if (n != nvals || n > 256) fail("JPEG: bad Huffman table");
+        std::memcpy(values, vals, (size_t)n);
+        int c = 0;
+        k = 0;
+        for (int j = 1; j <= 16; ++j) {
+            delta[j] = k - c;
+            if (size[k] == j) {
+                while (size[k] == j) code[k++] = (uint16_t)c++;
+                if (c - 1 >= (1 << j)) fail("JPEG: bad code lengths");
+            }
+            maxcode[j] = c << (16 - j);
+            c <<= 1;
+        }
+        maxcode[17] = 0x7fffffff;
+    }
+};
+
+struct JpegBits {
+    uint8_t const* p;
+    size_t n, pos;
+    uint32_t buf = 0;
+    int cnt = 0;
+    bool hit_marker = false;
+    void fill() {
+        while (cnt <= 24) {
+            int b = 0;
+            if (!hit_marker && pos < n) {
+                b = p[pos++];
+                if (b == 0xFF) {
+                    int const c = pos < n ? p[pos] : 0xD9;
+                    if (c == 0) ++pos;           // stuffed zero
+                    else { hit_marker = true; --pos; b = 0; }  // a marker: feed zeros from here on
+                }
+            }
+            buf |= (uint32_t)b << (24 - cnt);
+            cnt += 8;
+        }
+    }
+    int decode(JpegHuff const& h) {
+        if (cnt < 16) fill();
+        uint32_t const top = buf >> 16;
+        int len = 1;
+        while (len <= 16 && (int)top >= h.maxcode[len]) ++len;
+        if (len > 16) fail("JPEG: bad Huffman code");
+        int const idx = (int)((buf >> (32 - len)) & ((1u << len) - 1)) + h.delta[len];
+        if (idx < 0 || idx >= h.n) fail("JPEG: bad Huffman code");
+        buf <<= len;
+        cnt -= len;
+        return h.values[idx];
+    }
+    int receive_extend(int nbits) {  // T.81 F.2.2.1: nbits magnitude bits, sign-extended
+        if (nbits == 0) return 0;
+        if (cnt < nbits) fill();
+        int const v = (int)(buf >> (32 - nbits));
+        buf <<= nbits;
+        cnt -= nbits;
+        return v < (1 << (nbits - 1)) ? v - (1 << nbits) + 1 : v;
+    }
+    void reset() { buf = 0; cnt = 0; hit_marker = false; }
+};
+
+inline uint8_t jclamp(int x) { return (uint8_t)((unsigned)x > 255 ? (x < 0 ? 0 : 255) : x); }
+
+#define DLIMG_F2F(x) ((int)(((x) * 4096 + 0.5)))
+#define DLIMG_IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)        \
+    int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;   \
+    p2 = s2;                                                  \
+    p3 = s6;                                                  \
+    p1 = (p2 + p3) * DLIMG_F2F(0.5411961f);                   \
+    t2 = p1 + p3 * DLIMG_F2F(-1.847759065f);                  \
+    t3 = p1 + p2 * DLIMG_F2F(0.765366865f);                   \
+    p2 = s0;                                                  \
+    p3 = s4;                                                  \
+    t0 = (p2 + p3) * 4096;                                    \
+    t1 = (p2 - p3) * 4096;                                    \
+    x0 = t0 + t3;                                             \
+    x3 = t0 - t3;                                             \
+    x1 = t1 + t2;                                             \
+    x2 = t1 - t2;                                             \
+    t0 = s7;                                                  \
+    t1 = s5;                                                  \
+    t2 = s3;                                                  \
+    t3 = s1;                                                  \
+    p3 = t0 + t2;                                             \
+    p4 = t1 + t3;                                             \
+    p1 = t0 + t3;                                             \
+    p2 = t1 + t2;                                             \
+    p5 = (p3 + p4) * DLIMG_F2F(1.175875602f);                 \
+    t0 = t0 * DLIMG_F2F(0.298631336f);                        \
+    t1 = t1 * DLIMG_F2F(2.053119869f);                        \
+    t2 = t2 * DLIMG_F2F(3.072711026f);                        \
+    t3 = t3 * DLIMG_F2F(1.501321110f);                        \
+    p1 = p5 + p1 * DLIMG_F2F(-0.899976223f);                  \
+    p2 = p5 + p2 * DLIMG_F2F(-2.562915447f);                  \
+    p3 = p3 * DLIMG_F2F(-1.961570560f);                       \
+    p4 = p4 * DLIMG_F2F(-0.390180644f);                       \
+    t3 += p1 + p4;                                            \
+    t2 += p2 + p3;                                            \
+    t1 += p2 + p4;                                            \
+    t0 += p1 + p3;
+
+void jpeg_idct_block(uint8_t* out, int out_stride, short const data[64]) {
+    int val[64], *v = val;
+    short const* d = data;
+    for (int i = 0; i < 8; ++i, ++d, ++v) {  // columns
+        if (d[8] == 0 && d[16] == 0 && d[24] == 0 && d[32] == 0 && d[40] == 0 && d[48] == 0 && d[56] == 0) {
+            int const dcterm = d[0] * 4;
+            v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dcterm;
+        } else {
+            DLIMG_IDCT_1D(d[0], d[8], d[16], d[24], d[32], d[40], d[48], d[56])
+            x0 += 512; x1 += 512; x2 += 512; x3 += 512;  // constants scaled by 1 << 12; keep 2 extra bits
+            v[0] = (x0 + t3) >> 10;
+            v[56] = (x0 - t3) >> 10;
+            v[8] = (x1 + t2) >> 10;
+            v[48] = (x1 - t2) >> 10;
+            v[16] = (x2 + t1) >> 10;
+            v[40] = (x2 - t1) >> 10;
+            v[24] = (x3 + t0) >> 10;
+            v[32] = (x3 - t0) >> 10;
+        }
+    }
+    v = val;
+    uint8_t* o = out;
+    for (int i = 0; i < 8; ++i, v += 8, o += out_stride) {  // rows: remove 1 << 17, round, + 128
+        DLIMG_IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
+        x0 += 65536 + (128 << 17);
+        x1 += 65536 + (128 << 17);
+        x2 += 65536 + (128 << 17);
+        x3 += 65536 + (128 << 17);
+        o[0] = jclamp((x0 + t3) >> 17);
+        o[7] = jclamp((x0 - t3) >> 17);
+        o[1] = jclamp((x1 + t2) >> 17);
+        o[6] = jclamp((x1 - t2) >> 17);
+        o[2] = jclamp((x2 + t1) >> 17);
+        o[5] = jclamp((x2 - t1) >> 17);
+        o[3] = jclamp((x3 + t0) >> 17);
+        o[4] = jclamp((x3 - t0) >> 17);
+    }
+}
+#undef DLIMG_IDCT_1D
+#undef DLIMG_F2F
+
+struct JpegComp {
+    int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
+    int w2 = 0, h2 = 0;  // padded plane extent
+    int dc_pred = 0;
+    std::vector<uint8_t> data;
+};
+
+// one row of chroma at full horizontal resolution from the two nearest source rows (3/4 near + 1/4 far vertically,
+// then 3/4 - 1/4 horizontally), stb_image's stbi__resample_row_hv_2
+void resample_hv2(uint8_t* out, uint8_t const* in_near, uint8_t const* in_far, int w) {
+    if (w == 1) {
+        out[0] = out[1] = (uint8_t)((3 * in_near[0] + in_far[0] + 2) >> 2);
+        return;
+    }
+    int t1 = 3 * in_near[0] + in_far[0];
+    out[0] = (uint8_t)((t1 + 2) >> 2);
+    for (int i = 1; i < w; ++i) {
+        int const t0 = t1;
+        t1 = 3 * in_near[i] + in_far[i];
+        out[i * 2 - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4);
+        out[i * 2] = (uint8_t)((3 * t1 + t0 + 8) >> 4);
+    }
+    out[w * 2 - 1] = (uint8_t)((t1 + 2) >> 2);
+}
+void resample_h2(uint8_t* out, uint8_t const* in, int w) {  // stbi__resample_row_h_2
+    if (w == 1) {
+        out[0] = out[1] = in[0];
+        return;
+    }
+    out[0] = in[0];
+    out[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2);
+    int i;
+    for (i = 1; i < w - 1; ++i) {
+        int const n = 3 * in[i] + 2;
+        out[i * 2 + 0] = (uint8_t)((n + in[i - 1]) >> 2);
+        out[i * 2 + 1] = (uint8_t)((n + in[i + 1]) >> 2);
+    }
+    out[i * 2 + 0] = (uint8_t)((in[w - 2] * 3 + in[w - 1] + 2) >> 2);
+    out[i * 2 + 1] = in[w - 1];
+}
+
+uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* extent, int* channels) {
+    static uint8_t const zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                       41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                       30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    auto bad = [&](char const* why) { fail(std::string("Failed to load image ") + path + ": " + why); };
+    uint16_t quant[4][64] = {};
+    JpegHuff dc[4], ac[4];
+    bool have_dc[4] = {}, have_ac[4] = {};
+    std::vector<JpegComp> comps;
+    int W = 0, H = 0, restart = 0, hmax = 1, vmax = 1;
+    bool adobe_transform_rgb = false, jfif = false;
+    size_t pos = 2;
+    auto u16 = [&](size_t at) {
+        if (at + 2 > file.size()) bad("truncated JPEG");
+        return (int)((file[at] << 8) | file[at + 1]);
+    };
+    bool scan_found = false;
+    while (!scan_found) {
+        while (pos < file.size() && file[pos] != 0xFF) ++pos;
+        while (pos < file.size() && file[pos] == 0xFF) ++pos;
+        if (pos >= file.size()) bad("no scan in JPEG");
+        int const marker = file[pos++];
+        if (marker == 0xD8 || marker == 0x01 || (marker >= 0xD0 && marker <= 0xD7)) continue;
+        if (marker == 0xD9) bad("no scan in JPEG");
+        int const len = u16(pos);
+        if (len < 2 || pos + (size_t)len > file.size()) bad("truncated JPEG segment");
+        uint8_t const* d = &file[pos + 2];
+        int const n = len - 2;
+        switch (marker) {
+        case 0xDB:  // quantisation tables
+            for (int i = 0; i < n;) {
+                int const pq = d[i] >> 4, tq = d[i] & 15;
+                if (tq > 3 || pq > 1 || i + 1 + 64 * (pq + 1) > n) bad("bad DQT");
+                for (int k = 0; k < 64; ++k) quant[tq][zigzag[k]] = pq ? (uint16_t)((d[i + 1 + 2 * k] << 8) | d[i + 2 + 2 * k]) : d[i + 1 + k];
+                i += 1 + 64 * (pq + 1);
+            }
+            break;
+        case 0xC4:  // Huffman tables
+            for (int i = 0; i < n;) {
+                if (i + 17 > n) bad("bad DHT");
+                int const tc = d[i] >> 4, th = d[i] & 15;
+                int total = 0;
+                for (int k = 0; k < 16; ++k) total += d[i + 1 + k];
+                if (tc > 1 || th > 3 || total > 256 || i + 17 + total > n) bad("bad DHT");
+                (tc ? ac : dc)[th].build(d + i + 1, d + i + 17, total);
+                (tc ? have_ac : have_dc)[th] = true;
+                i += 17 + total;
+            }
+            break;
+        case 0xC0: case 0xC1: {  // baseline / extended sequential, Huffman
+            if (n < 6 || d[0] != 8) bad("only 8-bit JPEG is supported");
+            H = (d[1] << 8) | d[2];
+            W = (d[3] << 8) | d[4];
+            int const nc = d[5];
+            if (W <= 0 || H <= 0 || (nc != 1 && nc != 3) || n < 6 + 3 * nc) bad("unsupported JPEG frame");
+            if ((uint64_t)W * H * 3 > kMaxImageBytes) bad("image too large");
+            comps.resize((size_t)nc);
+            for (int i = 0; i < nc; ++i) {
+                comps[(size_t)i].id = d[6 + 3 * i];
+                comps[(size_t)i].h = d[7 + 3 * i] >> 4;
+                comps[(size_t)i].v = d[7 + 3 * i] & 15;
+                comps[(size_t)i].tq = d[8 + 3 * i];
+                if (comps[(size_t)i].h < 1 || comps[(size_t)i].h > 4 || comps[(size_t)i].v < 1 || comps[(size_t)i].v > 4 || comps[(size_t)i].tq > 3)
+                    bad("bad JPEG frame header");
+                hmax = std::max(hmax, comps[(size_t)i].h);
+                vmax = std::max(vmax, comps[(size_t)i].v);
+            }
+            break;
+        }
+        case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
+            bad("only baseline (sequential Huffman) JPEG is supported");
+            break;
+        case 0xDD: restart = n >= 2 ? ((d[0] << 8) | d[1]) : 0; break;
+        case 0xE0: jfif = n >= 5 && !std::memcmp(d, "JFIF", 5); break;
+        case 0xEE: if (n >= 12 && !std::memcmp(d, "Adobe", 5)) adobe_transform_rgb = d[11] == 0; break;
+        case 0xDA: {
+            if (comps.empty()) bad("scan before frame header");
+            int const ns = d[0];
+            if (ns != (int)comps.size() || n < 1 + 2 * ns + 3) bad("only single-scan (interleaved) JPEG is supported");
+            for (int i = 0; i < ns; ++i) {
+                int const cid = d[1 + 2 * i];
+                JpegComp* c = nullptr;
+                for (auto& cc : comps)
+                    if (cc.id == cid) c = &cc;
+                if (!c) bad("bad scan component");
+                c->td = d[2 + 2 * i] >> 4;
+                c->ta = d[2 + 2 * i] & 15;
+                if (c->td > 3 || c->ta > 3 || !have_dc[c->td] || !have_ac[c->ta]) bad("missing Huffman table");
+            }
+            scan_found = true;
+            break;
+        }
+        default: break;  // APPn, COM, ...
+        }
+        pos += (size_t)len;
+    }
+    (void)jfif;
+    // entropy-coded segment -> component planes (each padded to whole MCUs)
+    int const mcu_w = 8 * hmax, mcu_h = 8 * vmax;
+    int const mcux = (W + mcu_w - 1) / mcu_w, mcuy = (H + mcu_h - 1) / mcu_h;
+    for (auto& c : comps) {
+        c.w2 = mcux * c.h * 8;
+        c.h2 = mcuy * c.v * 8;
+        c.data.assign((size_t)c.w2 * c.h2, 0);
+    }
+    JpegBits br{file.data(), file.size(), pos};
+    int todo = restart ? restart : 0x7fffffff;
+    auto decode_block = [&](JpegComp& c, short (&blk)[64]) {
+        std::memset(blk, 0, sizeof(blk));
+        int const t = br.decode(dc[c.td]);
+        if (t > 15) bad("bad DC code");
+        int const diff = br.receive_extend(t);
+        c.dc_pred += diff;
+        blk[0] = (short)(c.dc_pred * quant[c.tq][0]);
+        for (int k = 1; k < 64;) {
+            int const rs = br.decode(ac[c.ta]);
+            int const s = rs & 15, r = rs >> 4;
+            if (s == 0) {
+                if (rs != 0xF0) break;  // end of block
+                k += 16;
+            } else {
+                k += r;
+                if (k > 63) bad("bad AC run");
+                int const z = zigzag[k++];
+                blk[z] = (short)(br.receive_extend(s) * quant[c.tq][z]);
+            }
+        }
+    };
+    for (int my = 0; my < mcuy; ++my)
+        for (int mx = 0; mx < mcux; ++mx) {
+            for (auto& c : comps)
+                for (int by = 0; by < c.v; ++by)
+                    for (int bx = 0; bx < c.h; ++bx) {
+                        short blk[64];
+                        decode_block(c, blk);
+                        jpeg_idct_block(&c.data[(size_t)((my * c.v + by) * 8) * c.w2 + (size_t)(mx * c.h + bx) * 8], c.w2, blk);
+                    }
+            if (--todo <= 0) {  // restart interval: byte-align, expect RSTn, reset the predictors
+                br.reset();
+                size_t q = br.pos;
+                while (q + 1 < file.size() && !(file[q] == 0xFF && file[q + 1] >= 0xD0 && file[q + 1] <= 0xD7)) {
+                    if (file[q] == 0xFF && file[q + 1] == 0xD9) break;
+                    ++q;
+                }
+                if (q + 1 < file.size() && file[q + 1] != 0xD9) br.pos = q + 2;
+                for (auto& c : comps) c.dc_pred = 0;
+                todo = restart;
+            }
+        }
+    // planes -> interleaved pixels
+    int const nc = (int)comps.size();
+    uint8_t* px = new uint8_t[(size_t)W * H * (nc == 1 ? 1 : 3)];
+    if (nc == 1) {
+        for (int y = 0; y < H; ++y) std::memcpy(px + (size_t)y * W, &comps[0].data[(size_t)y * comps[0].w2], (size_t)W);
+        extent[0] = W; extent[1] = H; *channels = 1;
+        return px;
+    }
+    struct Up { int hs, vs, ystep, ypos, w_lores; uint8_t const *line0, *line1; std::vector<uint8_t> buf; };
+    Up up[3];
+    for (int k = 0; k < 3; ++k) {
+        JpegComp const& c = comps[(size_t)k];
+        up[k].hs = hmax / c.h;
+        up[k].vs = vmax / c.v;
+        if (!((up[k].hs == 1 || up[k].hs == 2) && (up[k].vs == 1 || up[k].vs == 2))) {
+            delete[] px;
+            bad("unsupported chroma subsampling");
+        }
+        up[k].ystep = up[k].vs >> 1;
+        up[k].ypos = 0;
+        up[k].w_lores = (W + up[k].hs - 1) / up[k].hs;
+        up[k].line0 = up[k].line1 = c.data.data();
+        up[k].buf.assign((size_t)W + 3, 0);
+    }
+    int const plane_rows[3] = {(H + up[0].vs - 1) / up[0].vs, (H + up[1].vs - 1) / up[1].vs, (H + up[2].vs - 1) / up[2].vs};
+    for (int y = 0; y < H; ++y) {
+        uint8_t const* row[3];
+        for (int k = 0; k < 3; ++k) {
+            Up& u = up[k];
+            bool const y_bot = u.ystep >= (u.vs >> 1);
+            uint8_t const* in_near = y_bot ? u.line1 : u.line0;
+            uint8_t const* in_far = y_bot ? u.line0 : u.line1;
+            if (u.hs == 1 && u.vs == 1) {
+                row[k] = in_near;
+            } else if (u.hs == 2 && u.vs == 2) {
+                resample_hv2(u.buf.data(), in_near, in_far, u.w_lores);
+                row[k] = u.buf.data();
+            } else if (u.hs == 2) {
+                resample_h2(u.buf.data(), in_near, u.w_lores);
+                row[k] = u.buf.data();
+            } else {  // vs == 2 only: stbi__resample_row_v_2
+                for (int i = 0; i < u.w_lores; ++i) u.buf[(size_t)i] = (uint8_t)((3 * in_near[i] + in_far[i] + 2) >> 2);
+                row[k] = u.buf.data();
+            }
+            if (++u.ystep >= u.vs) {
+                u.ystep = 0;
+                u.line0 = u.line1;
+                if (++u.ypos < plane_rows[k]) u.line1 += comps[(size_t)k].w2;
+            }
+        }
+        uint8_t* out = px + (size_t)y * W * 3;
+        if (adobe_transform_rgb) {
+            for (int x = 0; x < W; ++x) { out[3 * x] = row[0][x]; out[3 * x + 1] = row[1][x]; out[3 * x + 2] = row[2][x]; }
+        } else {
+            auto f2fix = [](float v) { return ((int)(v * 4096.0f + 0.5f)) << 8; };
+            for (int x = 0; x < W; ++x) {
+                int const y_fixed = (row[0][x] << 20) + (1 << 19);
+                int const cr = row[2][x] - 128, cb = row[1][x] - 128;
+                int r = y_fixed + cr * f2fix(1.40200f);
+                int g = y_fixed + (cr * -f2fix(0.71414f)) + ((cb * -f2fix(0.34414f)) & (int)0xffff0000);
+                int b = y_fixed + cb * f2fix(1.77200f);
+                out[3 * x] = jclamp(r >> 20);
+                out[3 * x + 1] = jclamp(g >> 20);
+                out[3 * x + 2] = jclamp(b >> 20);
+            }
+        }
+    }
+    extent[0] = W; extent[1] = H; *channels = 3;
     return px;
 }
 
@@ -275,7 +716,8 @@ uint8_t* load_image(char const* filepath, int* out_extent, int* out_channels) {
     static uint8_t const png_sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     if (file.size() > 8 && !std::memcmp(file.data(), png_sig, 8)) return load_png(file, filepath, out_extent, out_channels);
     if (file.size() > 2 && file[0] == 'P' && (file[1] == '5' || file[1] == '6')) return load_pnm(file, filepath, out_extent, out_channels);
-    fail(std::string("Failed to load image ") + filepath + ": unsupported format (PNG and binary PGM/PPM are supported)");
+    if (file.size() > 4 && file[0] == 0xFF && file[1] == 0xD8) return load_jpeg(file, filepath, out_extent, out_channels);
+    fail(std::string("Failed to load image ") + filepath + ": unsupported format (PNG, baseline JPEG and binary PGM/PPM are supported)");
 }
 
 // reference image.cpp:25-35: mask / rgb / rgba only, rows written packed (the reference also ignores stride)

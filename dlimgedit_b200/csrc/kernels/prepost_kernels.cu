@@ -458,24 +458,92 @@ __global__ void __launch_bounds__(256) mask_post_kernel(float const* __restrict_
 
 // ---- mask post-processing: 256 -> 1024 bilinear, crop, -> (h, w) bilinear, > 0 -> 0 / 255 -----------------------------
 // (decoder-graph post-processing, SURVEY A.5, + write_mask_image, reference segmentation.cpp:108-116.)
-// A block produces kRows complete output rows of one mask.  Same operations in the same order as the per-pixel form
-// above, but every intermediate is computed once per block and kept in shared memory:
+// Same operations in the same order as the per-pixel form above.  The previous block-of-rows kernel issued one byte
+// store per lane (32 B per warp instruction) and reached 0.055 of the HBM rate; here every lane produces 4 or 8
+// neighbouring output bytes per row, keeps the horizontally interpolated source rows it needs in registers across the
+// output rows of its strip, and writes whole 32- / 64-bit words (128 / 256 contiguous bytes per warp instruction).
+
+__device__ __forceinline__ uint32_t pack_mask4(float const* v) {
+    return (v[0] > 0.f ? 0x000000ffu : 0u) | (v[1] > 0.f ? 0x0000ff00u : 0u) | (v[2] > 0.f ? 0x00ff0000u : 0u) |
+           (v[3] > 0.f ? 0xff000000u : 0u);
+}
+
+// Identity case: the resized extent equals the output extent (long side == 1024), so the second bilinear has weights
+// 1 / 0 and output pixel (y, x) is the thresholded 256 -> 1024 interpolation itself.  A thread owns 8 neighbouring
+// columns of an 8-row strip: the two low-resolution rows an output row blends change every 4 rows, and their
+// horizontal interpolation at the thread's columns (8 + 8 registers) is carried from row to row.  No shared memory, no
+// barriers: the 256 KiB plane stays in L1 / L2.
+constexpr int kIdRows = 8;
+__global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __restrict__ low_res, int64_t plane_stride,
+                                                                 int const* __restrict__ plane_index, int w, int h,
+                                                                 uint8_t* const* __restrict__ out_planes,
+                                                                 uint8_t* __restrict__ out_contig) {
+    int const plane = blockIdx.y;
+    int const x0 = (threadIdx.x & 127) * 8;
+    int const ys = (blockIdx.x * 2 + (threadIdx.x >> 7)) * kIdRows;
+    if (x0 >= w || ys >= h) return;
+    float const* __restrict__ low = low_res + (plane_index ? plane_index[plane] : plane) * plane_stride;
+    uint8_t* const plane_out = out_planes ? out_planes[plane] : out_contig + (size_t)plane * w * h;
+    Lerp lx[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) lx[e] = lerp_coord(min(x0 + e, w - 1), 0.25f, kLowRes);
+    auto hrow = [&](int r, float (&o)[8]) {
+        float const* row = low + r * kLowRes;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = lx[e].l0 * __ldg(row + lx[e].i0) + lx[e].l1 * __ldg(row + lx[e].i1);
+    };
+    int c0 = -1, c1 = -1;
+    float h0[8], h1[8];
+#pragma unroll
+    for (int t = 0; t < kIdRows; ++t) {
+        int const y = ys + t;
+        if (y < h) {
+            Lerp const q = lerp_coord(y, 0.25f, kLowRes);
+            if (q.i0 != c0) {
+                if (q.i0 == c1) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h0[e] = h1[e];
+                } else {
+                    hrow(q.i0, h0);
+                }
+                c0 = q.i0;
+            }
+            if (q.i1 != c1) {
+                if (q.i1 == c0) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h1[e] = h0[e];
+                } else {
+                    hrow(q.i1, h1);
+                }
+                c1 = q.i1;
+            }
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = q.l0 * h0[e] + q.l1 * h1[e];
+            uint8_t* dst = plane_out + (size_t)y * w + x0;
+            if (x0 + 8 <= w && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_mask4(v), pack_mask4(v + 4));
+            } else {
+                for (int e = 0; e < 8 && x0 + e < w; ++e) dst[e] = v[e] > 0.f ? 255 : 0;
+            }
+        }
+    }
+}
+
+// General case.  A block produces kRows complete output rows of one mask; every intermediate is computed once per
+// block and kept in shared memory:
 //   1. the few low-resolution rows the block needs                                     s_low[n_low][256]
 //   2. their horizontal interpolation at the 1024 grid                                 s_h[n_low][1024]
-//   3. (general case) the vertical interpolation = the 1024-grid rows the block needs  s_grid[n_slots][1024]
-//   4. output pixels: second bilinear from s_grid, threshold, byte into a staging copy of the block's output rows
-//      (kIdentity: the resized extent equals the output extent, the second bilinear has weights 1 / 0 and the output
-//      is the thresholded vertical interpolation of step 3 directly)
-//   5. the staged rows -- a contiguous byte range of the packed plane -- go out as 16-byte vectors (the staging copy
-//      starts at the same offset mod 16 as the global range, so both sides are aligned).
-// The previous form issued one byte store per lane (32 B per warp instruction) and reached 0.055 of the HBM rate.
+//   3. the vertical interpolation = the 1024-grid rows the block needs                 s_grid[n_slots][1024]
+//   4. output pixels: a thread owns 4 neighbouring columns; the second bilinear's horizontal half for the two grid rows
+//      of an output row is carried in registers from row to row (when enlarging, several output rows share the pair).
 struct PostGeom {
     int rw, rh, w, h;
     float sx, sy;
     int n_slots, n_low;  // upper bounds of the 1024-grid rows / low-resolution rows a block needs (host)
 };
 
-template <bool kIdentity, int kRows>
+template <int kRows>
 __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __restrict__ low_res, int64_t plane_stride,
                                                              int const* __restrict__ plane_index, PostGeom g,
                                                              uint8_t* const* __restrict__ out_planes,
@@ -484,7 +552,6 @@ __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __rest
     float* const s_low = reinterpret_cast<float*>(post_smem);
     float* const s_h = s_low + g.n_low * kLowRes;
     float* const s_grid = s_h + g.n_low * kImageSize;
-    uint8_t* const s_out = reinterpret_cast<uint8_t*>(s_grid + (kIdentity ? 0 : g.n_slots * kImageSize));
     int const tid = threadIdx.x;
     int const plane = blockIdx.y;
     int const y0 = blockIdx.x * kRows;
@@ -493,18 +560,12 @@ __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __rest
     uint8_t* const plane_out = out_planes ? out_planes[plane] : out_contig + (size_t)plane * g.w * g.h;
 
     // rows of the 1024 grid this block needs, and the low-resolution rows behind them (both contiguous ranges)
-    int g_base, g_last;
-    if (kIdentity) {
-        g_base = y0;
-        g_last = y0 + rows_valid - 1;
-    } else {
-        g_base = lerp_coord(y0, g.sy, g.rh).i0;
-        g_last = lerp_coord(y0 + rows_valid - 1, g.sy, g.rh).i1;
-    }
+    int const g_base = lerp_coord(y0, g.sy, g.rh).i0;
+    int const g_last = lerp_coord(y0 + rows_valid - 1, g.sy, g.rh).i1;
     int const l_base = lerp_coord(g_base, 0.25f, kLowRes).i0;
     int const l_last = lerp_coord(g_last, 0.25f, kLowRes).i1;
     int const n_low = l_last - l_base + 1, n_slots = g_last - g_base + 1;
-    if (n_low > g.n_low || (!kIdentity && n_slots > g.n_slots)) __trap();  // the host bounds are exact upper bounds
+    if (n_low > g.n_low || n_slots > g.n_slots) __trap();  // the host bounds are exact upper bounds
 
     {   // 1. low-resolution rows (16-byte loads; planes are 256 KiB apart)
         float4 const* src = reinterpret_cast<float4 const*>(low + (size_t)l_base * kLowRes);
@@ -521,85 +582,66 @@ __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __rest
         }
     }
     __syncthreads();
-    int const mis = (int)(reinterpret_cast<uintptr_t>(plane_out + (size_t)y0 * g.w) & 15);
-    if (kIdentity) {
-        // 4. output row y = grid row y: vertical interpolation + threshold
-        Lerp q[kRows];
-#pragma unroll
-        for (int t = 0; t < kRows; ++t) {
-            q[t] = lerp_coord(min(y0 + t, g.h - 1), 0.25f, kLowRes);
-            q[t].i0 -= l_base;
-            q[t].i1 -= l_base;
-        }
-        for (int x = tid; x < g.w; x += 256) {
-            int ca = -1, cb = -1;
-            float ha = 0.f, hb = 0.f;
-#pragma unroll
-            for (int t = 0; t < kRows; ++t) {
-                if (t < rows_valid) {
-                    int const a = q[t].i0, b = q[t].i1;  // block-uniform
-                    float top, bot;
-                    if (a == ca) top = ha; else if (a == cb) top = hb; else top = s_h[a * kImageSize + x];
-                    if (b == a) bot = top; else if (b == cb) bot = hb; else if (b == ca) bot = ha; else bot = s_h[b * kImageSize + x];
-                    ca = a; ha = top; cb = b; hb = bot;
-                    float const v = q[t].l0 * top + q[t].l1 * bot;
-                    s_out[mis + t * g.w + x] = v > 0.f ? 255 : 0;
-                }
-            }
-        }
-    } else {
-        // 3. the 1024-grid rows
-        for (int slot = 0; slot < n_slots; ++slot) {
-            Lerp const q = lerp_coord(g_base + slot, 0.25f, kLowRes);
-            float const* r0 = s_h + (q.i0 - l_base) * kImageSize;
-            float const* r1 = s_h + (q.i1 - l_base) * kImageSize;
-            for (int xx = tid; xx < g.rw; xx += 256) s_grid[slot * kImageSize + xx] = q.l0 * r0[xx] + q.l1 * r1[xx];
-        }
-        __syncthreads();
-        // 4. second bilinear + threshold
-        Lerp ly[kRows];
-#pragma unroll
-        for (int t = 0; t < kRows; ++t) {
-            ly[t] = lerp_coord(min(y0 + t, g.h - 1), g.sy, g.rh);
-            ly[t].i0 -= g_base;
-            ly[t].i1 -= g_base;
-        }
-        for (int x = tid; x < g.w; x += 256) {
-            Lerp const lx = lerp_coord(x, g.sx, g.rw);
-            int ca = -1, cb = -1;
-            float ha = 0.f, hb = 0.f;
-#pragma unroll
-            for (int t = 0; t < kRows; ++t) {
-                if (t < rows_valid) {
-                    int const a = ly[t].i0, b = ly[t].i1;  // block-uniform
-                    float top, bot;
-                    if (a == ca) top = ha;
-                    else if (a == cb) top = hb;
-                    else { float const* r = s_grid + a * kImageSize; top = lx.l0 * r[lx.i0] + lx.l1 * r[lx.i1]; }
-                    if (b == a) bot = top;
-                    else if (b == cb) bot = hb;
-                    else if (b == ca) bot = ha;
-                    else { float const* r = s_grid + b * kImageSize; bot = lx.l0 * r[lx.i0] + lx.l1 * r[lx.i1]; }
-                    ca = a; ha = top; cb = b; hb = bot;
-                    float const v = ly[t].l0 * top + ly[t].l1 * bot;
-                    s_out[mis + t * g.w + x] = v > 0.f ? 255 : 0;
-                }
-            }
-        }
+    // 3. the 1024-grid rows
+    for (int slot = 0; slot < n_slots; ++slot) {
+        Lerp const q = lerp_coord(g_base + slot, 0.25f, kLowRes);
+        float const* r0 = s_h + (q.i0 - l_base) * kImageSize;
+        float const* r1 = s_h + (q.i1 - l_base) * kImageSize;
+        for (int xx = tid; xx < g.rw; xx += 256) s_grid[slot * kImageSize + xx] = q.l0 * r0[xx] + q.l1 * r1[xx];
     }
     __syncthreads();
-    // 5. staged rows -> global: head bytes up to the first 16-byte boundary, 16-byte vectors, tail bytes
-    {
-        int const nbytes = rows_valid * g.w;
-        uint8_t* const gdst = plane_out + (size_t)y0 * g.w;
-        int const head = min(nbytes, (16 - mis) & 15);
-        int const nvec = (nbytes - head) >> 4;
-        int const tail0 = head + (nvec << 4);
-        if (tid < head) gdst[tid] = s_out[mis + tid];
-        uint4 const* sv = reinterpret_cast<uint4 const*>(s_out + mis + head);
-        uint4* gv = reinterpret_cast<uint4*>(gdst + head);
-        for (int i = tid; i < nvec; i += 256) gv[i] = sv[i];
-        if (tid < nbytes - tail0) gdst[tail0 + tid] = s_out[mis + tail0 + tid];
+    // 4. second bilinear + threshold
+    Lerp ly[kRows];
+#pragma unroll
+    for (int t = 0; t < kRows; ++t) {
+        ly[t] = lerp_coord(min(y0 + t, g.h - 1), g.sy, g.rh);
+        ly[t].i0 -= g_base;
+        ly[t].i1 -= g_base;
+    }
+    for (int x0 = 4 * tid; x0 < g.w; x0 += 1024) {
+        Lerp lx[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) lx[e] = lerp_coord(min(x0 + e, g.w - 1), g.sx, g.rw);
+        auto hrow = [&](int slot, float (&o)[4]) {
+            float const* r = s_grid + slot * kImageSize;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = lx[e].l0 * r[lx[e].i0] + lx[e].l1 * r[lx[e].i1];
+        };
+        int ca = -1, cb = -1;
+        float ha[4], hb[4];
+#pragma unroll
+        for (int t = 0; t < kRows; ++t) {
+            if (t < rows_valid) {
+                int const a = ly[t].i0, b = ly[t].i1;  // block-uniform
+                if (a != ca) {
+                    if (a == cb) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) ha[e] = hb[e];
+                    } else {
+                        hrow(a, ha);
+                    }
+                    ca = a;
+                }
+                if (b != cb) {
+                    if (b == ca) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) hb[e] = ha[e];
+                    } else {
+                        hrow(b, hb);
+                    }
+                    cb = b;
+                }
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = ly[t].l0 * ha[e] + ly[t].l1 * hb[e];
+                uint8_t* dst = plane_out + (size_t)(y0 + t) * g.w + x0;
+                if (x0 + 4 <= g.w && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+                    *reinterpret_cast<uint32_t*>(dst) = pack_mask4(v);
+                } else {
+                    for (int e = 0; e < 4 && x0 + e < g.w; ++e) dst[e] = v[e] > 0.f ? 255 : 0;
+                }
+            }
+        }
     }
 }
 
@@ -639,60 +681,57 @@ template <typename K> void set_smem_limit(K kernel, int bytes) {
 
 constexpr int kPostSmemBudget = 72 * 1024;  // three blocks per SM
 
-template <bool kIdentity, int kRows>
+template <int kRows>
 void launch_post_tile(cudaStream_t s, float const* low_res, int64_t plane_stride, int const* plane_index, int count,
                       PostGeom const& g, int smem, uint8_t* const* out_planes, uint8_t* out_contig) {
-    set_smem_limit(mask_post_tile_kernel<kIdentity, kRows>, smem);
+    set_smem_limit(mask_post_tile_kernel<kRows>, smem);
     dim3 grid(ceil_div(g.h, kRows), count);
-    mask_post_tile_kernel<kIdentity, kRows><<<grid, 256, smem, s>>>(low_res, plane_stride, plane_index, g, out_planes, out_contig);
+    mask_post_tile_kernel<kRows><<<grid, 256, smem, s>>>(low_res, plane_stride, plane_index, g, out_planes, out_contig);
 }
 
 // shared-memory need of a kRows-row block; fills the exact upper bounds of the rows it may touch
-int post_plan(PostGeom& g, bool identity, int rows) {
+int post_plan(PostGeom& g, int rows) {
     // span of i1(last) - i0(first) + 1 over `n` consecutive destinations at source step `scale`: <= scale*(n-1) + 3
     auto span = [](float scale, int n, int limit) { return std::min(limit, (int)std::ceil((double)scale * (n - 1)) + 3); };
-    g.n_slots = identity ? rows : span(g.sy, rows, g.rh);
+    g.n_slots = span(g.sy, rows, g.rh);
     g.n_low = span(0.25f, g.n_slots, kLowRes);
-    return g.n_low * (kLowRes + kImageSize) * 4 + (identity ? 0 : g.n_slots * kImageSize * 4) + rows * g.w + 32;
+    return g.n_low * (kLowRes + kImageSize) * 4 + g.n_slots * kImageSize * 4;
 }
 
 void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride, int const* plane_index, int count, int rw,
                       int rh, int w, int h, uint8_t* const* out_planes, uint8_t* out_contig) {
     DLIMG_ASSERT(count > 0 && w > 0 && h > 0 && rw > 0 && rh > 0 && rw <= kImageSize && rh <= kImageSize);
+    DLIMG_ASSERT(count <= 65535);
     // torch: scale = float(input_size) / output_size
     PostGeom g;
     g.rw = rw; g.rh = rh; g.w = w; g.h = h;
     g.sx = (float)rw / (float)w;
     g.sy = (float)rh / (float)h;
     ProfScope prof(s, CAT_MASK_POST, 0, (double)count * (65536.0 * 4 + (double)w * h));
-    bool const identity = rw == w && rh == h;
+    if (rw == w && rh == h) {  // long side == 1024: the second resize is the identity
+        dim3 grid(ceil_div(h, 2 * kIdRows), count);
+        mask_post_identity_kernel<<<grid, 256, 0, s>>>(low_res, plane_stride, plane_index, w, h, out_planes, out_contig);
+        KERNEL_CHECK();
+        return;
+    }
     int rows = 0, smem = 0;
-    for (int r : {8, 4, 2, 1}) {
-        smem = post_plan(g, identity, r);
+    for (int r : {16, 8, 4, 2, 1}) {
+        smem = post_plan(g, r);
         if (smem <= kPostSmemBudget) { rows = r; break; }
     }
-    if (rows == 0) {  // very wide outputs: per-pixel form
-        DLIMG_ASSERT(h <= 65535 && count <= 65535);
+    if (rows == 0) {  // cannot happen for rh <= 1024 (one row needs 3 + 3 source rows); kept as a guard
+        DLIMG_ASSERT(h <= 65535);
         dim3 block(256), grid(ceil_div(ceil_div(w, 4), 256), h, count);
         mask_post_kernel<<<grid, block, 0, s>>>(low_res, plane_stride, plane_index, rw, rh, w, h, g.sx, g.sy, out_planes, out_contig);
         KERNEL_CHECK();
         return;
     }
-    DLIMG_ASSERT(count <= 65535);
-    if (identity) {
-        switch (rows) {
-            case 8: launch_post_tile<true, 8>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-            case 4: launch_post_tile<true, 4>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-            case 2: launch_post_tile<true, 2>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-            default: launch_post_tile<true, 1>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-        }
-    } else {
-        switch (rows) {
-            case 8: launch_post_tile<false, 8>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-            case 4: launch_post_tile<false, 4>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-            case 2: launch_post_tile<false, 2>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-            default: launch_post_tile<false, 1>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-        }
+    switch (rows) {
+        case 16: launch_post_tile<16>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+        case 8: launch_post_tile<8>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+        case 4: launch_post_tile<4>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+        case 2: launch_post_tile<2>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
+        default: launch_post_tile<1>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
     }
     KERNEL_CHECK();
 }

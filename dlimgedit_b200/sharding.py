@@ -14,10 +14,6 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
-def fake_score(image: int, prompt: int) -> float:
-    return float(((image * 131 + prompt * 17) % 1000) / 1000.0)
-
-
 def gather_scores(local: np.ndarray, n_images: int, rank: int, world: int) -> np.ndarray:
     """local: (len(shard), P) float32 scores of this rank's images -> (n_images, P) on every rank.
     Ragged shards are padded to the longest shard for the all_gather (NCCL and gloo need equal sizes)."""

@@ -26,9 +26,17 @@ WINDOWS = (7, 7, 14, 7)
 
 
 class _Gen:
-    def __init__(self, seed: int):
+    def __init__(self, seed: int, stress: bool = False):
         self.rng = np.random.default_rng(seed)
         self.t: Dict[str, np.ndarray] = {}
+        self.stress = stress
+
+    def _affine(self, shape, lo, hi, cap):
+        """Norm scale: benign = uniform(lo, hi); stress = the same times a heavy log-normal tail, capped at `cap`."""
+        w = self.rng.uniform(lo, hi, shape)
+        if self.stress:
+            w = np.minimum(w * np.exp(self.rng.standard_normal(shape) * 0.5), cap)
+        return w.astype(np.float32)
 
     def normal(self, name, shape, std):
         self.t[name] = (self.rng.standard_normal(shape) * std).astype(np.float32)
@@ -38,8 +46,8 @@ class _Gen:
 
     def conv_bn(self, p, cout, cin_per_group, ks, gamma_scale=1.0):
         self.normal(p + ".c.weight", (cout, cin_per_group, ks, ks), 1.0 / math.sqrt(cin_per_group * ks * ks))
-        self.uniform(p + ".bn.weight", (cout,), 0.7 * gamma_scale, 1.3 * gamma_scale)
-        self.normal(p + ".bn.bias", (cout,), 0.1)
+        self.t[p + ".bn.weight"] = self._affine((cout,), 0.7 * gamma_scale, 1.3 * gamma_scale, 8.0 * gamma_scale)
+        self.normal(p + ".bn.bias", (cout,), 0.5 if self.stress else 0.1)
         self.normal(p + ".bn.running_mean", (cout,), 0.1)
         self.uniform(p + ".bn.running_var", (cout,), 0.6, 1.4)
 
@@ -48,8 +56,8 @@ class _Gen:
         self.normal(p + ".bias", (n,), 0.05)
 
     def norm(self, p, c):
-        self.uniform(p + ".weight", (c,), 0.7, 1.3)
-        self.normal(p + ".bias", (c,), 0.1)
+        self.t[p + ".weight"] = self._affine((c,), 0.7, 1.3, 4.0)
+        self.normal(p + ".bias", (c,), 0.5 if self.stress else 0.1)
 
     def attn(self, p, dim, internal):
         for n in ("q_proj", "k_proj", "v_proj"):
@@ -57,8 +65,13 @@ class _Gen:
         self.linear(p + ".out_proj", dim, internal)
 
 
-def make_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
-    g = _Gen(seed)
+def make_state_dict(seed: int = 0, stress: bool = False) -> Dict[str, np.ndarray]:
+    """stress = False: every tensor O(1), BN gamma in [0.7, 1.3] (benign).  stress = True: heavy-tailed BN / LN scales
+    (up to 8 / 4), larger norm biases and residual branches 2x stronger, so the encoder trunk grows to 1e2..1e3 with a
+    large per-token mean -- the regime in which 16-bit activation storage and the E[x^2] - mean^2 LayerNorm statistics
+    of the fused epilogues would break first (real TinyViT residual streams are not O(1))."""
+    g = _Gen(seed, stress)
+    rs = 2.0 if stress else 1.0  # residual-branch scale
     E = "image_encoder."
     g.conv_bn(E + "patch_embed.seq.0", 32, 3, 3)
     g.conv_bn(E + "patch_embed.seq.2", 64, 32, 3)
@@ -66,7 +79,7 @@ def make_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
         p = f"{E}layers.0.blocks.{i}"
         g.conv_bn(p + ".conv1", 256, 64, 1)
         g.conv_bn(p + ".conv2", 256, 1, 3)
-        g.conv_bn(p + ".conv3", 64, 256, 1, gamma_scale=0.5)
+        g.conv_bn(p + ".conv3", 64, 256, 1, gamma_scale=0.5 * rs)
     for i in range(3):  # PatchMerging after layers 0..2
         p = f"{E}layers.{i}.downsample"
         g.conv_bn(p + ".conv1", DIMS[i + 1], DIMS[i], 1)
@@ -78,12 +91,12 @@ def make_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
             p = f"{E}layers.{st}.blocks.{i}"
             g.norm(p + ".attn.norm", c)
             g.linear(p + ".attn.qkv", 3 * c, c)
-            g.linear(p + ".attn.proj", c, c, scale=0.5)
+            g.linear(p + ".attn.proj", c, c, scale=0.5 * rs)
             g.normal(p + ".attn.attention_biases", (HEADS[st], ws * ws), 0.5)
             g.conv_bn(p + ".local_conv", c, 1, 3)
             g.norm(p + ".mlp.norm", c)
             g.linear(p + ".mlp.fc1", 4 * c, c)
-            g.linear(p + ".mlp.fc2", c, 4 * c, scale=0.5)
+            g.linear(p + ".mlp.fc2", c, 4 * c, scale=0.5 * rs)
     g.norm(E + "norm_head", 320)         # unused by the forward pass, present in the checkpoint
     g.linear(E + "head", 1000, 320)      # idem
     g.normal(E + "neck.0.weight", (256, 320, 1, 1), 1.0 / math.sqrt(320))
@@ -130,11 +143,11 @@ def make_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
     return g.t
 
 
-def write_model_dir(model_dir: str, seed: int = 0) -> str:
+def write_model_dir(model_dir: str, seed: int = 0, stress: bool = False) -> str:
     d = os.path.join(model_dir, "segmentation")
     os.makedirs(d, exist_ok=True)
     path = os.path.join(d, weights_io.WEIGHT_FILE_NAME)
-    weights_io.save(path, make_state_dict(seed))
+    weights_io.save(path, make_state_dict(seed, stress))
     return path
 
 

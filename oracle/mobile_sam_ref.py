@@ -534,11 +534,11 @@ def load_numpy_state(sam: MobileSam, tensors) -> MobileSam:
     return sam
 
 
-def build_synthetic(seed: int = 0) -> MobileSam:
+def build_synthetic(seed: int = 0, stress: bool = False) -> MobileSam:
     """Oracle model carrying the seeded synthetic weights of dlimgedit_b200.synthetic_weights (no checkpoint
-    exists offline)."""
+    exists offline); stress = heavy-tailed norm scales and strong residual branches (see make_state_dict)."""
     from dlimgedit_b200 import synthetic_weights
-    return load_numpy_state(MobileSam(), synthetic_weights.make_state_dict(seed))
+    return load_numpy_state(MobileSam(), synthetic_weights.make_state_dict(seed, stress))
 
 
 def count_learnable(m: nn.Module) -> int:

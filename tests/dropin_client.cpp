@@ -5,6 +5,7 @@
 //
 // usage: dropin_client <model_dir> <raw_rgba_file> <width> <height> <out_prefix>
 #include <dlimgedit/dlimgedit.hpp>
+#include <dlimg_b200.hpp>  // this repo: C++ wrappers of the additive batch table, next to the reference façade
 
 #include <cstdio>
 #include <fstream>
@@ -51,6 +52,26 @@ int main(int argc, char** argv) {
         std::cout << "png roundtrip: " << (reloaded.size() == mask.size() &&
                                            std::equal(mask.pixels(), mask.pixels() + mask.size(), reloaded.pixels()))
                   << "\n";
+
+        // the additive extension through include/dlimg_b200.hpp: a batch of two images in one encoder pass, prompts of both
+        // images in one decoder pass; results must equal the one-at-a-time reference calls above
+        {
+            std::vector<uint8_t> flipped(pixels.rbegin(), pixels.rend());
+            ImageView views[2] = {view, ImageView(flipped.data(), Extent{w, h}, Channels::rgba)};
+            std::vector<Segmentation> segs = b200::process_batch(env, views, 2);
+            Segmentation const* owners[3] = {&segs[0], &segs[1], &segs[0]};
+            b200::Prompt prompts[3] = {Point{w / 3, h / 2}, Point{w / 2, h / 2}, Region(Point{w / 8, h / 8}, Extent{w / 2, h / 2})};
+            std::vector<Image> out;
+            for (int i = 0; i < 3; ++i) out.emplace_back(Extent{w, h}, Channels::mask);
+            uint8_t* ptrs[3] = {out[0].pixels(), out[1].pixels(), out[2].pixels()};
+            float ious[3] = {0, 0, 0};
+            b200::compute_masks_batch(env, owners, prompts, 3, false, ptrs, ious);
+            bool const same = std::equal(mask.pixels(), mask.pixels() + mask.size(), out[0].pixels()) &&
+                              std::equal(box.pixels(), box.pixels() + box.size(), out[2].pixels());
+            Image second = segs[1].compute_mask(Point{w / 2, h / 2});
+            bool const same2 = std::equal(second.pixels(), second.pixels() + second.size(), out[1].pixels());
+            std::cout << "batch extension: " << (same && same2) << " launches " << b200::stats(env).kernel_launches << "\n";
+        }
 
         // error path: exceptions carry last_error() text (dlimgedit.impl.hpp:7-11)
         try {

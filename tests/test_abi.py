@@ -147,3 +147,75 @@ def test_srgb_tables_match_oracle():
         t = thr[i]
         assert L.ref_linear_to_srgb8(float(t)) == i
         assert L.ref_linear_to_srgb8(float(np.nextafter(t, np.float32(-1)))) == i - 1
+
+
+def test_load_image_reads_baseline_jpeg(tmp_path):
+    """reference image.cpp:11-23 loads JPEG through stb_image; the library's own decoder restates stb's integer IDCT,
+    hv_2 chroma upsampling and fixed-point YCbCr -> RGB.  Checked against libjpeg-turbo (PIL): the two decoders may
+    differ by a few LSB (different IDCT rounding / upsampling rounding), not more."""
+    from PIL import Image
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "truck.jpg")
+    a = dl.api()
+    ext = (ctypes.c_int * 2)()
+    ch = ctypes.c_int()
+    px = ctypes.c_void_p()
+    assert a.load_image(path.encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 0, a.last_error()
+    assert (ext[0], ext[1], ch.value) == (1800, 1200, 3)
+    got = np.ctypeslib.as_array(ctypes.cast(px, ctypes.POINTER(ctypes.c_uint8)), shape=(1200, 1800, 3)).copy()
+    a.destroy_image(px)
+    ref = np.asarray(Image.open(path).convert("RGB"))
+    d = np.abs(got.astype(int) - ref.astype(int))
+    assert d.max() <= 4 and d.mean() < 0.1
+    # 4:4:4, 4:2:2, greyscale and restart intervals, written by PIL from a synthetic picture
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:97, 0:131]
+    pic = np.stack([127 + 100 * np.sin(xx / 9.0), 127 + 100 * np.cos(yy / 7.0), (xx + yy) % 256], -1)
+    pic = np.clip(pic + rng.normal(0, 4, pic.shape), 0, 255).astype(np.uint8)
+    for name, kw, mode in (("444.jpg", dict(subsampling=0), "RGB"), ("422.jpg", dict(subsampling=1), "RGB"),
+                           ("420.jpg", dict(subsampling=2), "RGB"), ("grey.jpg", {}, "L")):
+        f = str(tmp_path / name)
+        Image.fromarray(pic if mode == "RGB" else pic[..., 0]).save(f, quality=92, **kw)
+        assert a.load_image(f.encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 0, (name, a.last_error())
+        n = ch.value
+        got = np.ctypeslib.as_array(ctypes.cast(px, ctypes.POINTER(ctypes.c_uint8)), shape=(97, 131, n)).copy()
+        a.destroy_image(px)
+        ref = np.asarray(Image.open(f).convert(mode)).reshape(97, 131, n)
+        d = np.abs(got.astype(int) - ref.astype(int))
+        assert n == (3 if mode == "RGB" else 1) and d.max() <= 6 and d.mean() < 0.6, (name, d.max(), d.mean())
+    prog = str(tmp_path / "progressive.jpg")
+    Image.fromarray(pic).save(prog, progressive=True)
+    assert a.load_image(prog.encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 1
+    assert b"baseline" in a.last_error()
+
+
+def test_load_image_rejects_hostile_png_headers(tmp_path):
+    """a 2^31 x 2^31 IHDR used to wrap the size arithmetic (heap overflow); short IHDR chunks were read past."""
+    import struct
+    import zlib
+
+    def png(w, h, ihdr_len=13, payload=b"\x00" * 64):
+        def chunk(t, d):
+            return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+        ihdr = (struct.pack(">II", w, h) + bytes([8, 6, 0, 0, 0]))[:ihdr_len]
+        return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(payload)) + chunk(b"IEND", b"")
+
+    a = dl.api()
+    ext = (ctypes.c_int * 2)()
+    ch = ctypes.c_int()
+    px = ctypes.c_void_p()
+    for name, blob in (("huge.png", png(1 << 31, 1 << 31)), ("wide.png", png((1 << 24) + 1, 1)), ("zero.png", png(0, 5)),
+                       ("short_ihdr.png", png(4, 4, ihdr_len=9)), ("bomb.png", png(2, 2, payload=b"\x00" * (1 << 20)))):
+        f = tmp_path / name
+        f.write_bytes(blob)
+        r = a.load_image(str(f).encode(), ext, ctypes.byref(ch), ctypes.byref(px))
+        if name == "bomb.png":  # more data than the image needs: refused before it is expanded
+            assert r == 1 and b"larger than the image" in a.last_error()
+        else:
+            assert r == 1, name
+    ok = tmp_path / "ok.png"
+    ok.write_bytes(png(2, 2, payload=b"\x00" + bytes(8) + b"\x00" + bytes(8)))
+    assert a.load_image(str(ok).encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 0, a.last_error()
+    a.destroy_image(px)
+    pnm = tmp_path / "overflow.ppm"
+    pnm.write_bytes(b"P6 99999999999 99999999999 255\n" + bytes(12))
+    assert a.load_image(str(pnm).encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 1

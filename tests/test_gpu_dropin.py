@@ -28,6 +28,7 @@ def test_reference_header_client(env, model_dir, tmp_path):
     assert "cpu supported: 0" in r.stdout and "gpu supported: 1" in r.stdout
     assert f"extent: {w}x{h}" in r.stdout
     assert "png roundtrip: 1" in r.stdout
+    assert "batch extension: 1" in r.stdout  # include/dlimg_b200.hpp: batched calls equal the one-at-a-time reference calls
     assert "error: Model path /nonexistent/models does not exist" in r.stdout
 
     seg = dl.Segmentation.process(dl.ImageView(img, channels=dl.Channels.rgba), env)

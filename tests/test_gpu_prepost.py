@@ -132,7 +132,8 @@ def test_resize_passthrough_when_scale_is_one(env):
     assert np.array_equal(_resize(env, img, dl.Channels.rgb), img)
 
 
-@pytest.mark.parametrize("h,w", [(1024, 1024), (1200, 1800), (2160, 3840), (512, 512), (683, 1024), (333, 1001)])
+@pytest.mark.parametrize("h,w", [(1024, 1024), (1200, 1800), (2160, 3840), (512, 512), (683, 1024), (333, 1001), (1024, 683),
+                                 (1024, 1019), (50, 100), (1500, 4097), (1023, 1024), (7, 9000)])
 def test_mask_postprocess_matches_torch(env, oracle_sam, h, w):
     """Fused 256->1024 bilinear, crop, ->(h,w) bilinear, >0: against the oracle's two F.interpolate calls."""
     from oracle.mobile_sam_ref import SamOnnxDecoder
@@ -151,3 +152,28 @@ def test_mask_postprocess_matches_torch(env, oracle_sam, h, w):
     near_zero = float((ref_logits.abs() < 1e-5).float().mean())
     # only pixels whose logit is within float rounding of 0 may differ
     assert mismatch <= near_zero + 1e-6, (mismatch, near_zero)
+
+
+def test_resize_matches_committed_golden_vectors(env):
+    """tests/golden/prepost_vectors.npz (oracle outputs committed as bytes): the GPU path reproduces them, packed and
+    with padded rows, without the oracle library being involved at all."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prepost_vectors.npz"))
+    chans = {"shrink_rgb": dl.Channels.rgb, "shrink_rgba": dl.Channels.rgba, "enlarge_rgb": dl.Channels.rgb, "enlarge_mask": dl.Channels.mask}
+    for name, ch in chans.items():
+        img, ref = g[f"resize_{name}_in"], g[f"resize_{name}_out"]
+        h, w, bpp = img.shape
+        t = torch.from_numpy(img).cuda()
+        out = torch.zeros(ref.size, dtype=torch.uint8, device="cuda")
+        ext = (ctypes.c_int * 2)()
+        for pad in (0, 12):
+            stride = w * bpp + pad
+            buf = torch.zeros(h, stride, dtype=torch.uint8, device="cuda")
+            buf[:, : w * bpp] = t.view(h, -1)
+            v = dl.ImageView(buf.data_ptr(), dl.Extent(w, h), ch, stride, device=True).to_c()
+            _check(dl.ext().resize_longest_side(env.handle(), ctypes.byref(v), max(ref.shape[0], ref.shape[1]), out.data_ptr(), ext))
+            env.synchronize()
+            assert (ext[0], ext[1]) == (ref.shape[1], ref.shape[0]), name
+            assert np.array_equal(out.cpu().numpy().reshape(ref.shape), ref), (name, pad)
+    for ch in (1, 3, 4, 5, 6):
+        assert np.array_equal(_image_tensor(env, g[f"tensor_{ch}_in"], dl.Channels(ch)), g[f"tensor_{ch}_out"])

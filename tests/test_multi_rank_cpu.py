@@ -16,13 +16,18 @@ sys.path.insert(0, ROOT)
 from dlimgedit_b200 import sharding  # noqa: E402
 
 
+def fake_score(image: int, prompt: int) -> float:
+    """Stand-in for "encode the image and answer the prompt": a deterministic score per (image, prompt)."""
+    return float(((image * 131 + prompt * 17) % 1000) / 1000.0)
+
+
 def _worker(rank, world, port, n_images, prompts_per_image, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mine = sharding.shard_indices(n_images, rank, world)
     # stand-in for "encode my images and answer their prompts": a deterministic score per (image, prompt)
-    local = np.array([[sharding.fake_score(i, p) for p in range(prompts_per_image)] for i in mine], np.float32)
+    local = np.array([[fake_score(i, p) for p in range(prompts_per_image)] for i in mine], np.float32)
     full = sharding.gather_scores(local, n_images, rank, world)
     if rank == 0:
         np.save(os.path.join(out_dir, "scores.npy"), full)
@@ -45,5 +50,5 @@ def test_two_rank_gather(tmp_path, n_images):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, n_images, prompts, str(tmp_path)), nprocs=world, join=True)
     full = np.load(tmp_path / "scores.npy")
-    ref = np.array([[sharding.fake_score(i, p) for p in range(prompts)] for i in range(n_images)], np.float32)
+    ref = np.array([[fake_score(i, p) for p in range(prompts)] for i in range(n_images)], np.float32)
     assert full.shape == (n_images, prompts) and np.array_equal(full, ref)
