@@ -30,6 +30,7 @@ SOURCES = [
     "kernels/mbconv_tail.cu",
     "kernels/local_conv.cu",
     "kernels/decoder_kernels.cu",
+    "kernels/decoder_tokens.cu",
     "kernels/t2i_attention.cu",
     "kernels/prepost_kernels.cu",
 ]

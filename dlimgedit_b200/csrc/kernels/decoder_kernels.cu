@@ -31,12 +31,14 @@ __device__ __forceinline__ float pe_feature(float cx, float cy, float const* __r
 }
 
 __global__ void __launch_bounds__(256) prompt_tokens_kernel(float const* __restrict__ coords, float const* __restrict__ labels,
-                                                            PromptParams pp, float* __restrict__ tokens) {
+                                                            PromptParams pp, float* __restrict__ tokens,
+                                                            float* __restrict__ queries) {
     int const p = blockIdx.x, j = threadIdx.x;
     float* out = tokens + (size_t)p * kTokens * kDim;
-    out[j] = pp.iou_token[j];
+    float* out2 = queries + (size_t)p * kTokens * kDim;  // the transformer's running token state starts as a copy
+    out[j] = out2[j] = pp.iou_token[j];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) out[(1 + m) * kDim + j] = pp.mask_tokens[m * kDim + j];
+    for (int m = 0; m < 4; ++m) out[(1 + m) * kDim + j] = out2[(1 + m) * kDim + j] = pp.mask_tokens[m * kDim + j];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         float const cx = (coords[(p * 2 + i) * 2 + 0] + 0.5f) / 1024.0f;
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(256) prompt_tokens_kernel(float const* __restr
         v = v + pp.not_a_point[j] * (lab == -1.0f ? 1.0f : 0.0f);
 #pragma unroll
         for (int e = 0; e < 4; ++e) v = v + pp.point_embed[e * kDim + j] * (lab == (float)e ? 1.0f : 0.0f);
-        out[(5 + i) * kDim + j] = v;
+        out[(5 + i) * kDim + j] = out2[(5 + i) * kDim + j] = v;
     }
 }
 
@@ -143,8 +145,7 @@ __global__ void __launch_bounds__(256) token_self_attention_kernel(float const* 
 // ---------------------------------------------------------------------------------------------
 // Image -> token attention core, one thread per (image token, head).  Q rows are 16-bit (the [K|V|Q] projection of the
 // image stream, row pitch q_pitch elements); the 7 token keys / values of the prompt sit in shared memory as
-// [token][d / 4][head] float4, so the eight heads handled by neighbouring lanes read 128 contiguous bytes.  Output:
-// 16-bit (P, 4096, 128), the A operand of the out-projection GEMM.
+// [token][d / 4][head] float4.  Output: 16-bit (P, 4096, 128), the A operand of the out-projection GEMM.
 __global__ void __launch_bounds__(256) i2t_attention_kernel(act_t const* __restrict__ Q, act_t const* const* __restrict__ Qptrs,
                                                             int64_t q_prompt_stride, int q_pitch, int q_off,
                                                             float const* __restrict__ kt, float const* __restrict__ vt,
@@ -160,8 +161,10 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(act_t const* __restr
         vs[(t * 4 + dq) * 8 + hh] = vsrc[i];
     }
     __syncthreads();
-    int const idx = blockIdx.x * blockDim.x + threadIdx.x;  // (token, head)
-    int const i = idx >> 3, h = idx & 7;
+    // warp = head, lane = image token: the 7 x 16 keys / values of the warp's head are the same shared-memory words for
+    // every lane (one broadcast wavefront per load; with lane = head each 16-byte load took four), and every lane reads /
+    // writes whole 32-byte sectors of its own token row
+    int const i = blockIdx.x * 32 + (threadIdx.x & 31), h = threadIdx.x >> 5;
     act_t const* qbase = (Qptrs ? Qptrs[p] : Q + (size_t)p * q_prompt_stride) + q_off;
     float qv[16];
     {
@@ -468,9 +471,10 @@ __global__ void select_masks_kernel(float const* __restrict__ iou, int P, int mu
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-void prompt_tokens(cudaStream_t s, float const* coords, float const* labels, int P, PromptParams const& pp, float* tokens) {
+void prompt_tokens(cudaStream_t s, float const* coords, float const* labels, int P, PromptParams const& pp, float* tokens,
+                   float* queries) {
     ProfScope prof(s, CAT_DEC_MISC);
-    prompt_tokens_kernel<<<P, 256, 0, s>>>(coords, labels, pp, tokens);
+    prompt_tokens_kernel<<<P, 256, 0, s>>>(coords, labels, pp, tokens, queries);
     KERNEL_CHECK();
 }
 

@@ -24,8 +24,10 @@ struct PromptParams {
     float const* mask_tokens;    // (4, 256)
 };
 
-// coords (P, 2, 2) already in 1024-space, labels (P, 2) -> tokens (P, 7, 256).
-void prompt_tokens(cudaStream_t s, float const* coords, float const* labels, int P, PromptParams const& pp, float* tokens);
+// coords (P, 2, 2) already in 1024-space, labels (P, 2) -> tokens (P, 7, 256), written twice: `tokens` (the token-side
+// positional encoding, kept) and `queries` (the transformer's running state).
+void prompt_tokens(cudaStream_t s, float const* coords, float const* labels, int P, PromptParams const& pp, float* tokens,
+                   float* queries);
 
 // Dense positional encoding of the 64x64 grid -> (4096, 256) token-major.
 void dense_pe(cudaStream_t s, float const* gaussian, float* pos);
@@ -42,8 +44,9 @@ void token_self_attention(cudaStream_t s, float const* q, float const* k, float 
 // base_p + i * pitch (K) and base_p + v_off + i * pitch (V), where base_p = ptrs[p] (per-prompt tables, layer 0: the
 // image's prompt-independent projections) or base + p * prompt_stride; 8 heads x 16 -> out (P, 7, 128) fp32.
 // `scratch` holds P * kT2iSplits * 7 * (128 + 16) floats of partial results (split-key softmax merge).
-constexpr int kT2iSplits = 4;
+constexpr int kT2iSplits = 8;
 constexpr size_t kT2iScratchPerPrompt = (size_t)kT2iSplits * kTokens * (128 + 16);
+// out == nullptr: leave the partials in `scratch` (token_post_t2i merges them).
 void token_to_image_attention(cudaStream_t s, float const* q, act_t const* base, act_t const* const* ptrs, int64_t prompt_stride,
                               int pitch, int v_off, int P, float* scratch, float* out);
 
@@ -80,6 +83,45 @@ struct TokenMlp3 {
     float const* b[5][3];
 };
 void token_mlp3(cudaStream_t s, float const* tokens, int P, TokenMlp3 const& heads, float* hyper, float* iou);
+
+// ---- fused token-side blocks (decoder_tokens.cu): one CTA per prompt, weights transposed to (K, N) ------------------------
+// [+pe] -> q, k, v -> 8-head self-attention over the 7 tokens -> out projection -> [+residual] LayerNorm -> queries (in
+// place), then out_next (P, 7, 128) = (queries + pe) w_next^T + b_next: the query projection of tokens -> image attention.
+struct TokenAttnBlock {
+    float* queries;       // (P, 7, 256) in / out
+    float const* pe;      // (P, 7, 256) the prompt tokens (positional encoding of the token side)
+    float const *wq_t, *bq, *wk_t, *bk, *wv_t, *bv, *wo_t, *bo;  // (256, 256) transposed weights, (256) biases
+    float const *gamma, *beta;
+    int with_pe, residual;  // layer 0: q = k = v = queries, output replaces them; later: q = k = queries + pe, residual
+    float const *w_next_t, *b_next;  // (256, 128), (128)
+    float* out_next;
+};
+void token_attn_block(cudaStream_t s, TokenAttnBlock const& p, int P);
+
+// Merge of the split-key partials of token_to_image_attention (see `scratch`) -> out projection 128 -> 256 -> + queries ->
+// LayerNorm -> queries (in place).
+struct TokenPostT2i {
+    float const* partials;  // P * kT2iScratchPerPrompt
+    float* queries;
+    float const *wo_t, *bo;  // (128, 256) transposed, (256)
+    float const *gamma, *beta;
+};
+void token_post_t2i(cudaStream_t s, TokenPostT2i const& p, int P);
+
+// queries <- LayerNorm(queries + mlp_out); then `count` (<= 3) projections 256 -> 128 of the new queries (+ pe if
+// with_pe[j]) -> out[j] (P, 7, 128).
+struct TokenPostMlp {
+    float* queries;
+    float const* mlp_out;
+    float const* pe;
+    float const *gamma, *beta;
+    int count;
+    float const* w_t[3];  // (256, 128) transposed
+    float const* b[3];
+    int with_pe[3];
+    float* out[3];
+};
+void token_post_mlp(cudaStream_t s, TokenPostMlp const& p, int P);
 
 // Mask selection of the decoder graphs.  iou (P, 4).
 //   multi == 0: plane_index[p] = p*4 + argmax(iou + (2 - 2.5) * [1000, 0, 0, 0]); iou_out[p] = iou of that token

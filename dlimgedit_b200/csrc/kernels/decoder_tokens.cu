@@ -1,0 +1,336 @@
+// decoder_tokens.cu -- the token side of the SAM two-way transformer (7 tokens x 256 per prompt) as a few fused kernels.
+//
+// Per prompt the token side is tiny (7 rows), but as separate launches -- three projections, the attention core, the output
+// projection, a LayerNorm, the next projection ... -- it was 23 launches per layer of 5-22 us each, 30 % of a 64-prompt
+// pass, all of it launch and dependency latency (profiles/r02a_summary.md).  Here a CLUSTER OF FOUR CTAs owns one prompt
+// and keeps its 7 x 256 state in (distributed) shared memory across a whole block of the layer:
+//     token_attn_block     [+pe] -> q, k, v projections -> 8-head self-attention -> out projection -> [+residual] LayerNorm
+//                          -> query projection of the following tokens->image attention
+//     token_post_t2i       merge of the split-key attention partials -> out projection -> +residual -> LayerNorm
+//     token_post_mlp       +residual -> LayerNorm -> key / value projections of image->tokens attention (and the query
+//                          projection of the final attention)
+// CTA c of a cluster computes output features [64c, 64c + 64) of every 256-wide projection (= attention heads 2c, 2c + 1,
+// so the attention core needs no exchange) and [32c, 32c + 32) of the 128-wide ones: it reads a QUARTER of each weight
+// matrix (a single CTA per prompt had to pull every 256 KB matrix through one SM's L2 port: 60 us per block).  What the
+// next step needs from the other three CTAs -- the attention output, the LayerNorm row sums, the normalised rows --
+// travels through distributed shared memory (st.shared::cluster) followed by a cluster barrier.
+// The 7-row MLP (256 -> 2048 -> 256) stays on the tensor-core GEMM: its 4 MB of weights want to be read once per pass.
+// Weights are stored transposed (K, N) so that neighbouring threads read neighbouring output features of one k: coalesced
+// rows, each value used for the prompt's 7 rows.  fp32 FMA throughout; a prompt's result does not depend on which other
+// prompts share the pass.
+#include "decoder_kernels.cuh"
+
+#include "../profiler.hpp"
+
+#include <cooperative_groups.h>
+
+#include <map>
+#include <mutex>
+
+namespace dlimg {
+namespace dec {
+
+namespace {
+
+namespace cg = cooperative_groups;
+
+constexpr int kT = kTokens;      // 7
+constexpr int kThreads = 256;
+constexpr int kCl = 4;           // CTAs per prompt
+constexpr int kS256 = kDim / kCl;  // 64: this CTA's features of a 256-wide projection
+constexpr int kS128 = 128 / kCl;   // 32: ... of a 128-wide one
+
+// out_s[r][f] = bias[n0 + f] + sum_k xs[r][k] * Wt[k][n0 + f]   for r < 7, f < NOUT, with all 256 threads: thread
+// (part, f) sums its share of k, the 256 / NOUT partial sums meet in shared memory.
+// xs: shared [7][K]; Wt: global (K, N) row-major; scratch: shared [256 / NOUT][7][NOUT]; out_s: shared [7][NOUT].
+template <int NOUT>
+__device__ __forceinline__ void cta_proj(float const* xs, int K, float const* __restrict__ Wt, int N, int n0,
+                                         float const* __restrict__ bias, float* scratch, float* out_s) {
+    constexpr int kParts = kThreads / NOUT;
+    int const f = threadIdx.x % NOUT, part = threadIdx.x / NOUT;
+    int const kper = K / kParts, k0 = part * kper;
+    float acc[kT];
+#pragma unroll
+    for (int r = 0; r < kT; ++r) acc[r] = 0.f;
+    float const* w = Wt + (size_t)k0 * N + n0 + f;
+#pragma unroll 4
+    for (int k = 0; k < kper; k += 4) {
+        float const w0 = __ldg(w + (size_t)(k + 0) * N), w1 = __ldg(w + (size_t)(k + 1) * N);
+        float const w2 = __ldg(w + (size_t)(k + 2) * N), w3 = __ldg(w + (size_t)(k + 3) * N);
+#pragma unroll
+        for (int r = 0; r < kT; ++r) {
+            float4 const x = *reinterpret_cast<float4 const*>(xs + r * K + k0 + k);
+            acc[r] = fmaf(x.x, w0, acc[r]);
+            acc[r] = fmaf(x.y, w1, acc[r]);
+            acc[r] = fmaf(x.z, w2, acc[r]);
+            acc[r] = fmaf(x.w, w3, acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kT; ++r) scratch[(part * kT + r) * NOUT + f] = acc[r];
+    __syncthreads();
+    for (int i = threadIdx.x; i < kT * NOUT; i += kThreads) {
+        int const ff = i % NOUT;
+        float s = __ldg(bias + n0 + ff);
+#pragma unroll
+        for (int p = 0; p < kParts; ++p) s += scratch[p * kT * NOUT + i];
+        out_s[i] = s;
+    }
+    __syncthreads();
+}
+
+// LayerNorm over 256 features that are spread over the cluster: this CTA holds v[r][f] for its 64 features (shared [7][64]).
+// Every CTA leaves its per-row (sum, sum of squares) in the `ln_part` buffer of all four; after the cluster barrier each
+// CTA has the four partial pairs of every row.  stats (shared [7][2]) <- (mean, rstd).
+__device__ __forceinline__ void cluster_row_stats(cg::cluster_group& cluster, float const* v_s, float* ln_part /* [4][7][2] */,
+                                                  float* stats) {
+    int const rank = (int)cluster.block_rank();
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < kT) {  // warp r reduces row r of the local slice
+        float const a = v_s[warp * kS256 + lane], b = v_s[warp * kS256 + 32 + lane];
+        float s = a + b, q = a * a + b * b;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane < kCl) {  // lane d delivers to CTA d
+            float* dst = cluster.map_shared_rank(ln_part, lane);
+            dst[(rank * kT + warp) * 2 + 0] = s;
+            dst[(rank * kT + warp) * 2 + 1] = q;
+        }
+    }
+    cluster.sync();
+    if (threadIdx.x < kT) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int c = 0; c < kCl; ++c) {
+            s += ln_part[(c * kT + threadIdx.x) * 2 + 0];
+            q += ln_part[(c * kT + threadIdx.x) * 2 + 1];
+        }
+        float const mean = s * (1.0f / kDim);
+        stats[threadIdx.x * 2 + 0] = mean;
+        stats[threadIdx.x * 2 + 1] = rsqrtf(fmaxf(q * (1.0f / kDim) - mean * mean, 0.f) + 1e-5f);
+    }
+    __syncthreads();
+}
+
+// copies this CTA's [7][64] slice into columns [64 * rank, +64) of a [7][256] buffer in every CTA of the cluster
+__device__ __forceinline__ void cluster_scatter_slice(cg::cluster_group& cluster, float const* slice_s, float* full /* [7][256] */) {
+    int const rank = (int)cluster.block_rank();
+    for (int i = threadIdx.x; i < kCl * kT * kS256; i += kThreads) {
+        int const dst_cta = i / (kT * kS256), j = i % (kT * kS256), r = j / kS256, f = j % kS256;
+        cluster.map_shared_rank(full, dst_cta)[r * kDim + rank * kS256 + f] = slice_s[j];
+    }
+}
+
+struct AttnSmem {
+    float xs[kT * kDim], xp[kT * kDim], full[kT * kDim];  // queries, queries (+ pe), gathered rows (attention output / new rows)
+    float q[kT * kS256], k[kT * kS256], v[kT * kS256], o[kT * kS256];
+    float scratch[kThreads * kT];
+    float sc[2 * kT * kT];
+    float ln_part[kCl * kT * 2], stats[kT * 2];
+};
+
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_attn_block_kernel(TokenAttnBlock p) {
+    extern __shared__ __align__(16) uint8_t tok_smem[];
+    AttnSmem& sm = *reinterpret_cast<AttnSmem*>(tok_smem);
+    cg::cluster_group cluster = cg::this_cluster();
+    int const rank = (int)cluster.block_rank();
+    int const prompt = blockIdx.x / kCl, n = threadIdx.x;
+    int const n0 = rank * kS256;
+    float* q_g = p.queries + (size_t)prompt * kT * kDim;
+    float const* pe_g = p.pe + (size_t)prompt * kT * kDim;
+#pragma unroll
+    for (int r = 0; r < kT; ++r) {
+        float const x = q_g[r * kDim + n], e = pe_g[r * kDim + n];
+        sm.xs[r * kDim + n] = x;
+        sm.xp[r * kDim + n] = p.with_pe ? x + e : x;
+    }
+    __syncthreads();
+    // q, k from queries (+ pe), v from queries: this CTA's 64 features = heads 2 * rank, 2 * rank + 1
+    cta_proj<kS256>(sm.xp, kDim, p.wq_t, kDim, n0, p.bq, sm.scratch, sm.q);
+    cta_proj<kS256>(sm.xp, kDim, p.wk_t, kDim, n0, p.bk, sm.scratch, sm.k);
+    cta_proj<kS256>(sm.xs, kDim, p.wv_t, kDim, n0, p.bv, sm.scratch, sm.v);
+    // scores of the two local heads: 2 x 7 x 7, head_dim 32, scale 1 / sqrt(32)
+    if (n < 2 * kT * kT) {
+        int const h = n / (kT * kT), t = (n / kT) % kT, u = n % kT;
+        float const* qq = sm.q + t * kS256 + h * 32;
+        float const* kk = sm.k + u * kS256 + h * 32;
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) s = fmaf(qq[(d + u) & 31], kk[(d + u) & 31], s);  // rotated start: rows are 64 floats apart
+        sm.sc[n] = s * 0.17677669529663687f;
+    }
+    __syncthreads();
+    if (n < 2 * kT) {  // softmax over the 7 keys of (head, query)
+        float* row = sm.sc + n * kT;
+        float mx = row[0];
+#pragma unroll
+        for (int u = 1; u < kT; ++u) mx = fmaxf(mx, row[u]);
+        float e[kT], sum = 0.f;
+#pragma unroll
+        for (int u = 0; u < kT; ++u) {
+            e[u] = expf(row[u] - mx);
+            sum += e[u];
+        }
+#pragma unroll
+        for (int u = 0; u < kT; ++u) row[u] = e[u] / sum;
+    }
+    __syncthreads();
+    if (n < kS256) {  // attention output of feature n (head n / 32)
+        int const h = n >> 5;
+        float vv[kT];
+#pragma unroll
+        for (int u = 0; u < kT; ++u) vv[u] = sm.v[u * kS256 + n];
+#pragma unroll
+        for (int t = 0; t < kT; ++t) {
+            float const* w = sm.sc + (h * kT + t) * kT;
+            float o = 0.f;
+#pragma unroll
+            for (int u = 0; u < kT; ++u) o = fmaf(w[u], vv[u], o);
+            sm.o[t * kS256 + n] = o;
+        }
+    }
+    __syncthreads();
+    cluster_scatter_slice(cluster, sm.o, sm.full);  // every CTA needs all 256 features as the input of the out projection
+    cluster.sync();
+    cta_proj<kS256>(sm.full, kDim, p.wo_t, kDim, n0, p.bo, sm.scratch, sm.o);
+    if (p.residual) {
+        for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] += sm.xs[(i / kS256) * kDim + n0 + (i % kS256)];
+        __syncthreads();
+    }
+    cluster_row_stats(cluster, sm.o, sm.ln_part, sm.stats);
+    for (int i = n; i < kT * kS256; i += kThreads) {
+        int const r = i / kS256, c = n0 + (i % kS256);
+        float const y = (sm.o[i] - sm.stats[2 * r]) * sm.stats[2 * r + 1] * __ldg(p.gamma + c) + __ldg(p.beta + c);
+        q_g[r * kDim + c] = y;
+        sm.o[i] = y + pe_g[r * kDim + c];  // input of the following query projection
+    }
+    __syncthreads();
+    cluster.sync();  // (every CTA is past its out projection: `full` may be overwritten)
+    cluster_scatter_slice(cluster, sm.o, sm.full);
+    cluster.sync();
+    // query projection of tokens -> image attention: (queries + pe) W^T + b, 256 -> 128; this CTA's 32 features
+    cta_proj<kS128>(sm.full, kDim, p.w_next_t, 128, rank * kS128, p.b_next, sm.scratch, sm.q);
+    for (int i = n; i < kT * kS128; i += kThreads)
+        p.out_next[((size_t)prompt * kT + i / kS128) * 128 + rank * kS128 + (i % kS128)] = sm.q[i];
+    cluster.sync();  // no CTA exits while another may still write into its shared memory
+}
+
+struct PostSmem {
+    float in_full[kT * kDim], xp_full[kT * kDim];
+    float o[kT * kS256], p32[kT * kS128];
+    float scratch[kThreads * kT];
+    float ln_part[kCl * kT * 2], stats[kT * 2];
+};
+
+// tokens -> image attention, second half: merge the split-key partials (max / sum / accumulators per split), output
+// projection 128 -> 256, + residual, LayerNorm.
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_post_t2i_kernel(TokenPostT2i p) {
+    extern __shared__ __align__(16) uint8_t tok_smem[];
+    PostSmem& sm = *reinterpret_cast<PostSmem*>(tok_smem);
+    cg::cluster_group cluster = cg::this_cluster();
+    int const rank = (int)cluster.block_rank();
+    int const prompt = blockIdx.x / kCl, n = threadIdx.x, n0 = rank * kS256;
+    constexpr int kPart = 128 + 16;
+    for (int i = n; i < kT * 128; i += kThreads) {  // (every CTA merges all 7 x 128 values: they are its GEMM input)
+        int const t = i >> 7, d = i & 127, h = d >> 4;
+        float const* src = p.partials + ((size_t)prompt * kT2iSplits * kT + t) * kPart;
+        size_t const split_stride = (size_t)kT * kPart;
+        float M = -INFINITY;
+#pragma unroll
+        for (int sp = 0; sp < kT2iSplits; ++sp) M = fmaxf(M, src[sp * split_stride + 128 + h]);
+        float A = 0.f, S = 0.f;
+#pragma unroll
+        for (int sp = 0; sp < kT2iSplits; ++sp) {
+            float const e = __expf(src[sp * split_stride + 128 + h] - M);
+            A = fmaf(src[sp * split_stride + d], e, A);
+            S = fmaf(src[sp * split_stride + 136 + h], e, S);
+        }
+        sm.in_full[i] = A / S;
+    }
+    __syncthreads();
+    float* q_g = p.queries + (size_t)prompt * kT * kDim;
+    cta_proj<kS256>(sm.in_full, 128, p.wo_t, kDim, n0, p.bo, sm.scratch, sm.o);
+    for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] += q_g[(i / kS256) * kDim + n0 + (i % kS256)];
+    __syncthreads();
+    cluster_row_stats(cluster, sm.o, sm.ln_part, sm.stats);
+    for (int i = n; i < kT * kS256; i += kThreads) {
+        int const r = i / kS256, c = n0 + (i % kS256);
+        q_g[r * kDim + c] = (sm.o[i] - sm.stats[2 * r]) * sm.stats[2 * r + 1] * __ldg(p.gamma + c) + __ldg(p.beta + c);
+    }
+    cluster.sync();
+}
+
+// After the token MLP: queries <- LayerNorm(queries + mlp_out), then up to three 256 -> 128 projections of the new
+// queries (with or without the positional encoding added): keys / values of image -> tokens attention, and after the
+// last layer the queries of the final tokens -> image attention.
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_post_mlp_kernel(TokenPostMlp p) {
+    extern __shared__ __align__(16) uint8_t tok_smem[];
+    PostSmem& sm = *reinterpret_cast<PostSmem*>(tok_smem);
+    cg::cluster_group cluster = cg::this_cluster();
+    int const rank = (int)cluster.block_rank();
+    int const prompt = blockIdx.x / kCl, n = threadIdx.x, n0 = rank * kS256;
+    float* q_g = p.queries + (size_t)prompt * kT * kDim;
+    float const* m_g = p.mlp_out + (size_t)prompt * kT * kDim;
+    float const* pe_g = p.pe + (size_t)prompt * kT * kDim;
+    for (int i = n; i < kT * kS256; i += kThreads) {
+        int const g = (i / kS256) * kDim + n0 + (i % kS256);
+        sm.o[i] = q_g[g] + m_g[g];
+    }
+    __syncthreads();
+    cluster_row_stats(cluster, sm.o, sm.ln_part, sm.stats);
+    for (int i = n; i < kCl * kT * kS256; i += kThreads) {  // normalised slice -> global + both gathered buffers of every CTA
+        int const dst_cta = i / (kT * kS256), j = i % (kT * kS256), r = j / kS256, c = n0 + (j % kS256);
+        float const y = (sm.o[j] - sm.stats[2 * r]) * sm.stats[2 * r + 1] * __ldg(p.gamma + c) + __ldg(p.beta + c);
+        if (dst_cta == 0) q_g[r * kDim + c] = y;
+        cluster.map_shared_rank(sm.in_full, dst_cta)[r * kDim + c] = y;
+        cluster.map_shared_rank(sm.xp_full, dst_cta)[r * kDim + c] = y + pe_g[r * kDim + c];
+    }
+    cluster.sync();
+    for (int j = 0; j < p.count; ++j) {
+        cta_proj<kS128>(p.with_pe[j] ? sm.xp_full : sm.in_full, kDim, p.w_t[j], 128, rank * kS128, p.b[j], sm.scratch, sm.p32);
+        for (int i = n; i < kT * kS128; i += kThreads)
+            p.out[j][((size_t)prompt * kT + i / kS128) * 128 + rank * kS128 + (i % kS128)] = sm.p32[i];
+        __syncthreads();
+    }
+    cluster.sync();
+}
+
+template <typename K, typename P> void launch_cluster(K kernel, size_t smem, cudaStream_t s, int prompts, P const& params) {
+    static std::mutex mutex;
+    static std::map<void const*, bool> done;
+    {
+        std::lock_guard<std::mutex> lock(mutex);
+        if (!done[(void const*)kernel]) {
+            CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            done[(void const*)kernel] = true;
+        }
+    }
+    kernel<<<prompts * kCl, kThreads, smem, s>>>(params);  // cluster shape comes from __cluster_dims__
+}
+
+}  // namespace
+
+void token_attn_block(cudaStream_t s, TokenAttnBlock const& p, int P) {
+    ProfScope prof(s, CAT_DEC_LINEAR, 2.0 * P * kT * kDim * (4.0 * kDim + 128));
+    launch_cluster(token_attn_block_kernel, sizeof(AttnSmem), s, P, p);
+    KERNEL_CHECK();
+}
+
+void token_post_t2i(cudaStream_t s, TokenPostT2i const& p, int P) {
+    ProfScope prof(s, CAT_DEC_LINEAR, 2.0 * P * kT * 128 * kDim);
+    launch_cluster(token_post_t2i_kernel, sizeof(PostSmem), s, P, p);
+    KERNEL_CHECK();
+}
+
+void token_post_mlp(cudaStream_t s, TokenPostMlp const& p, int P) {
+    DLIMG_ASSERT(p.count >= 1 && p.count <= 3);
+    ProfScope prof(s, CAT_DEC_LINEAR, 2.0 * P * kT * kDim * 128 * p.count);
+    launch_cluster(token_post_mlp_kernel, sizeof(PostSmem), s, P, p);
+    KERNEL_CHECK();
+}
+
+}  // namespace dec
+}  // namespace dlimg

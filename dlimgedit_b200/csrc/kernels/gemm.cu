@@ -43,6 +43,9 @@ struct EpiParams {
     int out_f32;
     int ldc;
     int res_mod;   // staged residual: residual row = output row % res_mod (0 = output row)
+    float const* fuse_a;  // kFuse 1: LayerNorm2d gamma (64); kFuse 2: hypernetwork weights (prompts, 4, 32)
+    float const* fuse_b;  // kFuse 1: LayerNorm2d beta (64)
+    float* fuse_out;      // kFuse 2: low-resolution mask logits (prompts, 4, 256, 256)
 };
 
 __device__ __forceinline__ void add_bias16(float (&v)[16], float const* bias, int col) {
@@ -217,11 +220,40 @@ struct SlabCtx {
     int64_t ldc;
     int rows_valid;       // how many of the warp's 32 rows exist (M tail)
     uint32_t bias_s;      // shared-memory copy of the bias vector (kStaged; 0 = read it from global memory)
+    int64_t row0;         // global row of the warp's first row
+    int rows_total;       // M
 };
 
-template <int kCnt, bool kStaged, int kAct, bool kLn, bool kRes = false, bool kF32 = false>
+// kFuse (staged 16-bit GELU epilogues of the mask decoder's upscaling, one warp = one 64- / 32-column group of a row):
+//   1  the warp's 64 columns are one LayerNorm2d group (output_upscaling.1 on the (dy, dx) block of the first transposed
+//      convolution): statistics from a first pass over the accumulators, then normalise -> GELU -> store as usual.
+//   2  the warp's 32 columns are the 32 channels of one output pixel (ey, ex) of the second transposed convolution: after
+//      GELU they are dotted with the prompt's four hypernetwork vectors and ONLY the four mask logits are written
+//      (mask_decoder: masks = hyper_in @ upscaled_embedding) -- the upscaled tensor never reaches memory.
+template <int kCnt, bool kStaged, int kAct, bool kLn, bool kRes = false, bool kF32 = false, int kFuse = 0>
 __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams const& ep, void* out, float& sum, float& sumsq) {
     uint32_t r[2][16];
+    float ln_mean = 0.f, ln_rstd = 1.f;
+    float dot[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kFuse == 1) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kCnt; ++k) {
+            tmem_ld16(cx.taddr + (uint32_t)(k * 16), r[0]);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[0][i]);
+            add_bias16_s(v, cx.bias_s, cx.col0 + k * 16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                s1 += v[i];
+                s2 = fmaf(v[i], v[i], s2);
+            }
+        }
+        ln_mean = s1 * (1.0f / (16 * kCnt));
+        ln_rstd = rsqrtf(fmaxf(s2 * (1.0f / (16 * kCnt)) - ln_mean * ln_mean, 0.f) + 1e-6f);
+    }
     tmem_ld16(cx.taddr, r[0]);
 #pragma unroll
     for (int k = 0; k < kCnt; ++k) {
@@ -284,6 +316,39 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[k & 1][i]);
             if (kLn) ln_bias16_s(v, cx.bias_s, c, cx.rstd);  // staged kernels always hold the bias vector (or zeros)
             else add_bias16_s(v, cx.bias_s, c);
+            if (kFuse == 1) {
+                float4 const* g4 = reinterpret_cast<float4 const*>(ep.fuse_a + (c & 63));
+                float4 const* b4 = reinterpret_cast<float4 const*>(ep.fuse_b + (c & 63));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 const g = __ldg(g4 + i), b = __ldg(b4 + i);
+                    v[4 * i + 0] = (v[4 * i + 0] - ln_mean) * ln_rstd * g.x + b.x;
+                    v[4 * i + 1] = (v[4 * i + 1] - ln_mean) * ln_rstd * g.y + b.y;
+                    v[4 * i + 2] = (v[4 * i + 2] - ln_mean) * ln_rstd * g.z + b.z;
+                    v[4 * i + 3] = (v[4 * i + 3] - ln_mean) * ln_rstd * g.w + b.w;
+                }
+            }
+            if (kFuse == 2) {
+                uint4 x[2];
+                activate_pack16(v, kAct, x);  // the same 16-bit values the unfused path stored
+                act2_t const* h = reinterpret_cast<act2_t const*>(x);
+                int64_t const prompt = (cx.row0 + cx.lane) >> 14;  // 16384 blocked pixels per prompt
+                float const* hy = ep.fuse_a + prompt * 128 + (c & 31);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    float4 const* h4 = reinterpret_cast<float4 const*>(hy + m * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 const w = __ldg(h4 + i);
+                        float2 const a = act22f2(h[2 * i]), b = act22f2(h[2 * i + 1]);
+                        dot[m] = fmaf(a.x, w.x, dot[m]);
+                        dot[m] = fmaf(a.y, w.y, dot[m]);
+                        dot[m] = fmaf(b.x, w.z, dot[m]);
+                        dot[m] = fmaf(b.y, w.w, dot[m]);
+                    }
+                }
+                continue;
+            }
             uint32_t const dst = cx.stage_base + stage_offset(kCnt, cx.lane, 2 * k);
             uint32_t const dst1 = cx.stage_base + stage_offset(kCnt, cx.lane, 2 * k + 1);
             if (kRes && ep.residual) {
@@ -317,6 +382,19 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
         } else if (cx.orow >= 0) {
             epilogue_store16(r[k & 1], ep, out, cx.orow, c, sum, sumsq);
         }
+    }
+    if (kFuse == 2) {
+        // blocked pixel row ((y * 64 + x) * 4 + dy * 2 + dx) of the prompt, column group (ey, ex) -> logit pixel (Y, X)
+        int64_t const row = cx.row0 + cx.lane;
+        if (row < cx.rows_total) {
+            int64_t const prompt = row >> 14;
+            int const rr = (int)(row & 16383), pix = rr >> 2, dy = (rr >> 1) & 1, dx = rr & 1, g = (cx.col0 >> 5) & 3;
+            int const Y = 4 * (pix >> 6) + 2 * dy + (g >> 1), X = 4 * (pix & 63) + 2 * dx + (g & 1);
+            float* o = ep.fuse_out + (prompt * 4) * 65536 + Y * 256 + X;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) o[(int64_t)m * 65536] = dot[m];
+        }
+        return;
     }
     if (kStaged && !kF32) {
         // transpose through the warp's staging area: each instruction now covers 32 / cpr whole row segments
@@ -386,7 +464,7 @@ inline SmemPlan plan_smem(int block_n, bool staged, bool stats = false, int bias
 
 // kStaged kernels are additionally specialised on the activation (kAct) and on the folded LayerNorm (kLn), so the
 // slab loop carries no run-time branches; the direct kernels read both from EpiParams.
-template <int kTF32, bool kStaged, int kAct = ACT_NONE, bool kLn = false, bool kRes = false>
+template <int kTF32, bool kStaged, int kAct = ACT_NONE, bool kLn = false, bool kRes = false, int kFuse = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
                int K, int block_n, int num_stages, int staging_bytes, int bias_bytes, void* out, EpiParams ep, ConvParams conv) {
@@ -622,7 +700,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             cx.ldc = ep.ldc;
             cx.rows_valid = M - (m0 + quarter * 32);
             cx.bias_s = bias_s;
+            cx.row0 = m0 + quarter * 32;
+            cx.rows_total = M;
             float row_sum = 0.f, row_sumsq = 0.f;
+            if (kFuse == 1) {  // block_n == 256: every warp owns the 64 columns of one LayerNorm2d group
+                epilogue_slabs<4, kStaged, kAct, kLn, kRes, kTF32 != 0, 1>(cx, ep, out, row_sum, row_sumsq);
+                continue;
+            }
+            if (kFuse == 2) {  // block_n == 128: every warp owns the 32 channels of one output pixel
+                epilogue_slabs<2, kStaged, kAct, kLn, kRes, kTF32 != 0, 2>(cx, ep, out, row_sum, row_sumsq);
+                continue;
+            }
             switch (s_cnt) {  // warp-uniform
                 case 4: epilogue_slabs<4, kStaged, kAct, kLn, kRes, kTF32 != 0>(cx, ep, out, row_sum, row_sumsq); break;
                 case 3: epilogue_slabs<3, kStaged, kAct, kLn, kRes, kTF32 != 0>(cx, ep, out, row_sum, row_sumsq); break;
@@ -1188,6 +1276,9 @@ EpiParams to_params(Epilogue const& e, int N) {
     p.out_f32 = e.out_f32;
     p.ldc = e.ldc ? e.ldc : N;
     p.res_mod = e.res_mod;
+    p.fuse_a = e.fuse_a;
+    p.fuse_b = e.fuse_b;
+    p.fuse_out = e.fuse_out;
     return p;
 }
 
@@ -1250,7 +1341,10 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     // Small problems (the decoder's token-side Linears, single-image encoder passes): narrower tiles put more SMs to
     // work and shorten the per-CTA k-loop.  The sum over K of an output element does not depend on the tile width, so
     // results are bit-identical; producers of row sums keep their width (the consumer counts the partial sums).
-    if (!ep.stats_out) {
+    if (epi.fuse) {
+        DLIMG_ASSERT(!tf32 && !ci && ep.act == ACT_GELU && !ep.residual && !ep.ln_stats && !ep.stats_out && !ep.row_map && !ep.out_f32);
+        DLIMG_ASSERT((epi.fuse == 1 && N == 256 && ep.fuse_a && ep.fuse_b) || (epi.fuse == 2 && N == 128 && M % 16384 == 0 && ep.fuse_a && ep.fuse_out));
+    } else if (!ep.stats_out) {
         int const tiles_m = ceil_div(M, kBlockM);
         while (block_n >= 128 && block_n % 32 == 0 && N % (block_n / 2) == 0 && 2 * tiles_m * (N / block_n) <= num_sms) block_n /= 2;
     }
@@ -1295,6 +1389,10 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     else if (ep.residual || ep.stats_out) kernel = gemm_tc_kernel<0, true, ACT_NONE, false, true>;
     else if (ep.ln_stats) kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, true> : gemm_tc_kernel<0, true, ACT_NONE, true>;
     else kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, false> : gemm_tc_kernel<0, true, ACT_NONE, false>;
+    if (epi.fuse) {
+        DLIMG_ASSERT(staged);
+        kernel = epi.fuse == 1 ? gemm_tc_kernel<0, true, ACT_GELU, false, false, 1> : gemm_tc_kernel<0, true, ACT_GELU, false, false, 2>;
+    }
     {
         static std::mutex attr_mutex;
         static std::map<void const*, bool> attr_done;

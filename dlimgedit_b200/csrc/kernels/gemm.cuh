@@ -41,6 +41,14 @@ struct Epilogue {
     // Direct epilogue without activation: also write, per output row and N tile, (sum v, sum v^2) of the row's values
     // in this tile -> [M][N / block_n] float2.  Summed in a fixed order (no atomics): results are reproducible.
     float2* stats_out = nullptr;
+    // Fused tails of the mask decoder's upscaling (16-bit GELU epilogue; see epilogue_slabs in gemm.cu):
+    //   fuse = 1, N == 256: LayerNorm2d(64, eps 1e-6) over every 64-column group (gamma = fuse_a, beta = fuse_b) before the GELU
+    //   fuse = 2, N == 128, M = prompts * 16384: the GELU'd 32-channel groups are dotted with the prompt's hypernetwork
+    //             vectors fuse_a (prompts, 4, 32) and only the mask logits fuse_out (prompts, 4, 256, 256) are written
+    int fuse = 0;
+    float const* fuse_a = nullptr;
+    float const* fuse_b = nullptr;
+    float* fuse_out = nullptr;
 };
 
 struct Operand {

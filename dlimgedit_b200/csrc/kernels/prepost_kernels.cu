@@ -190,12 +190,15 @@ __device__ __forceinline__ int srgb_encode(float acc, float const* __restrict__ 
 
 // ---- resize: ONE kernel, separable through shared memory (reference image.cpp:37-51) ----------------------------
 // A block produces a tile of tr x tc output pixels.  The input rows the tile needs are decoded (u8 -> linear float,
-// table look-up, edge pixels clamped) `ch` rows at a time into shared memory; thread j owns H-pass column
-// j = (output column, channel) with its filter taps in registers and leaves the horizontally filtered rows in shared
-// memory; the vertical pass + linear->sRGB8 encode then reads four neighbouring columns per thread (LDS.128) and writes
-// four bytes at once.  No intermediate ever reaches HBM (the two-pass form wrote in_h x out_w x bpp floats and read
-// them back).  Multiplications and additions stay separate (__fmul_rn / __fadd_rn), in ascending tap order from 0,
-// exactly like the reference filter -- results are bit-identical to oracle/c/prepost_ref.c.
+// table look-up, edge pixels clamped) `ch` rows at a time into shared memory; thread (row group, j) owns H-pass column
+// j = (output column, channel) with its filter taps in registers, filters two input rows at a time (two independent
+// add chains) and leaves the horizontally filtered rows in shared memory; the vertical pass + linear->sRGB8 encode then
+// reads four neighbouring columns per thread (LDS.128) and writes four bytes at once.  No intermediate ever reaches HBM
+// (the two-pass form wrote in_h x out_w x bpp floats and read them back).  Multiplications and additions stay separate
+// (__fmul_rn / __fadd_rn), in ascending tap order from 0, exactly like the reference filter -- results are bit-identical
+// to oracle/c/prepost_ref.c.  Tall, narrow tiles (32 x 40 at 4K) keep the halo the two filters re-read at 9 % / 7 %.
+// The kernel is bound by FP32 issue, not by HBM: 4K -> 1024 needs 15 + 15 taps of 2 instructions per output element on
+// top of the decode, ~6e8 thread instructions against 27 MB of traffic.
 struct ResizeTile {
     int tr = 0, tc = 0;          // output rows / columns per block; tc * bpp <= 256 and a multiple of 4
     int nr_max = 0, nc_max = 0;  // most input rows / columns any tile needs (exact, from the axis plans)
@@ -226,52 +229,88 @@ __global__ void __launch_bounds__(256) resize_tile_kernel(uint8_t const* __restr
     int const nr = r_hi - r_lo + 1;
     int const c_lo = __ldg(t.hfirst + ox0), c_hi = __ldg(t.hfirst + ox0 + tcv - 1) + t.htaps - 1;
     int const nc = c_hi - c_lo + 1;
-    bool const hactive = tid < tcv * BPP;
+    // H-pass geometry: 256 / row_elems row groups share the rows of a chunk
+    int const groups = min(256 / row_elems, g.ch), rows_per_group = g.ch / groups;
+    int const grp = tid / row_elems, j = tid - grp * row_elems;
+    bool const hactive = grp < groups && j < tcv * BPP;
     float w[KT];
     int foff = 0;
     {
-        int const ox = ox0 + tid / BPP, c = tid % BPP;
+        int const ox = ox0 + j / BPP, c = j % BPP;
 #pragma unroll
         for (int k = 0; k < KT; ++k) w[k] = (hactive && k < t.htaps) ? __ldg(t.hweights + (size_t)ox * t.htaps + k) : 0.0f;
         if (hactive) foff = (__ldg(t.hfirst + ox) - c_lo) * BPP + c;
     }
+    bool const interior = c_lo >= 0 && c_hi < in_w;  // no horizontal clamping in this tile: staged bytes are contiguous
+    int const row_bytes = nc * BPP;
+    // The bytes of the NEXT chunk's rows are fetched into registers before the H-pass of the current chunk and decoded
+    // after it: the trip to L2 / HBM hides behind the filter arithmetic (without it the kernel sat at 30 % issue
+    // utilisation, half of its stalls on these loads: profiles/r02a_summary.md).  One staged row per warp (g.ch == 8).
+    constexpr int kPre = 24;
+    bool const use_pre = interior && g.ch == 8 && row_bytes <= 32 * kPre;
+    uint8_t pre[kPre];
+    auto prefetch = [&](int rc) {
+        if (warp < min(g.ch, nr - rc)) {
+            int const y = min(max(r_lo + rc + warp, 0), in_h - 1);
+            uint8_t const* src = in + (size_t)y * stride + (size_t)c_lo * BPP;
+#pragma unroll
+            for (int i = 0; i < kPre; ++i) {
+                int const e = lane + 32 * i;
+                pre[i] = e < row_bytes ? __ldg(src + e) : (uint8_t)0;
+            }
+        }
+    };
+    if (use_pre) prefetch(0);
     __syncthreads();
     for (int rc = 0; rc < nr; rc += g.ch) {
         int const chv = min(g.ch, nr - rc);
-        // decode: warp = staged row, lane = pixel
-        for (int rr = warp; rr < chv; rr += 8) {
-            int const y = min(max(r_lo + rc + rr, 0), in_h - 1);
-            uint8_t const* src_row = in + (size_t)y * stride;
-            float* dst_row = s_in + rr * in_elems;
-            for (int px = lane; px < px_per_row; px += 32) {
-                float* dst = dst_row + px * BPP;
-                if (px < nc) {
-                    int const x = min(max(c_lo + px, 0), in_w - 1);
-                    uint8_t const* src = src_row + (size_t)x * BPP;
-                    if (BPP == 4 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
-                        uint32_t const p = __ldg(reinterpret_cast<uint32_t const*>(src));
-                        dst[0] = s_dec[p & 255u];
-                        dst[1] = s_dec[(p >> 8) & 255u];
-                        dst[2] = s_dec[(p >> 16) & 255u];
-                        dst[3] = s_dec[p >> 24];
-                    } else {
+        if (use_pre) {
+            if (warp < chv) {
+                float* dst_row = s_in + warp * in_elems;
 #pragma unroll
-                        for (int c = 0; c < BPP; ++c) dst[c] = s_dec[__ldg(src + c)];
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < BPP; ++c) dst[c] = 0.0f;
+                for (int i = 0; i < kPre; ++i) {
+                    int const e = lane + 32 * i;
+                    if (e < row_bytes) dst_row[e] = s_dec[pre[i]];
                 }
+                for (int e = row_bytes + lane; e < in_elems; e += 32) dst_row[e] = 0.0f;
+            }
+        } else {
+            // decode: warp = staged row, lanes walk its bytes (32 consecutive bytes per load instruction)
+            for (int rr = warp; rr < chv; rr += 8) {
+                int const y = min(max(r_lo + rc + rr, 0), in_h - 1);
+                uint8_t const* src_row = in + (size_t)y * stride;
+                float* dst_row = s_in + rr * in_elems;
+                for (int e = lane; e < row_bytes; e += 32) {
+                    int const px = e / BPP, c = e - px * BPP;
+                    int const x = min(max(c_lo + px, 0), in_w - 1);
+                    dst_row[e] = s_dec[__ldg(src_row + (size_t)x * BPP + c)];
+                }
+                for (int e = row_bytes + lane; e < in_elems; e += 32) dst_row[e] = 0.0f;
             }
         }
         __syncthreads();
+        if (use_pre && rc + g.ch < nr) prefetch(rc + g.ch);
         if (hactive) {
-            for (int rr = 0; rr < chv; ++rr) {
-                float const* row = s_in + rr * in_elems + foff;
-                float acc = 0.0f;
+            int const r_end = min((grp + 1) * rows_per_group, chv);
+            int rr = grp * rows_per_group;
+            for (; rr + 1 < r_end; rr += 2) {  // two rows at once: two independent add chains
+                float const* row0 = s_in + rr * in_elems + foff;
+                float const* row1 = row0 + in_elems;
+                float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-                for (int k = 0; k < KT; ++k) acc = __fadd_rn(acc, __fmul_rn(row[k * BPP], w[k]));
-                s_hb[(rc + rr) * row_elems + tid] = acc;
+                for (int k = 0; k < KT; ++k) {
+                    a0 = __fadd_rn(a0, __fmul_rn(row0[k * BPP], w[k]));
+                    a1 = __fadd_rn(a1, __fmul_rn(row1[k * BPP], w[k]));
+                }
+                s_hb[(rc + rr) * row_elems + j] = a0;
+                s_hb[(rc + rr + 1) * row_elems + j] = a1;
+            }
+            if (rr < r_end) {
+                float const* row0 = s_in + rr * in_elems + foff;
+                float a0 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < KT; ++k) a0 = __fadd_rn(a0, __fmul_rn(row0[k * BPP], w[k]));
+                s_hb[(rc + rr) * row_elems + j] = a0;
             }
         }
         __syncthreads();
@@ -279,11 +318,11 @@ __global__ void __launch_bounds__(256) resize_tile_kernel(uint8_t const* __restr
     // vertical pass + encode: four neighbouring columns per thread
     int const quads = row_elems >> 2, valid_elems = tcv * BPP;
     for (int i = tid; i < trv * quads; i += 256) {
-        int const oyl = i / quads, j = (i - oyl * quads) * 4;
-        if (j >= valid_elems) continue;
+        int const oyl = i / quads, jj = (i - oyl * quads) * 4;
+        if (jj >= valid_elems) continue;
         int const rbase = __ldg(t.vfirst + oy0 + oyl) - r_lo;
         float const* vw = s_vw + oyl * t.vtaps;
-        float const* col = s_hb + rbase * row_elems + j;
+        float const* col = s_hb + rbase * row_elems + jj;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = 0; k < t.vtaps; ++k) {
             float4 const v = *reinterpret_cast<float4 const*>(col + k * row_elems);
@@ -295,14 +334,14 @@ __global__ void __launch_bounds__(256) resize_tile_kernel(uint8_t const* __restr
         }
         uint32_t const b0 = (uint32_t)srgb_encode(acc.x, s_thr), b1 = (uint32_t)srgb_encode(acc.y, s_thr);
         uint32_t const b2 = (uint32_t)srgb_encode(acc.z, s_thr), b3 = (uint32_t)srgb_encode(acc.w, s_thr);
-        uint8_t* dst = out + ((size_t)(oy0 + oyl) * out_w + ox0) * BPP + j;
-        if (j + 4 <= valid_elems && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        uint8_t* dst = out + ((size_t)(oy0 + oyl) * out_w + ox0) * BPP + jj;
+        if (jj + 4 <= valid_elems && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
             *reinterpret_cast<uint32_t*>(dst) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
         } else {
             uint32_t const b[4] = {b0, b1, b2, b3};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (j + e < valid_elems) dst[e] = (uint8_t)b[e];
+                if (jj + e < valid_elems) dst[e] = (uint8_t)b[e];
         }
     }
 }
@@ -470,9 +509,13 @@ __device__ __forceinline__ uint32_t pack_mask4(float const* v) {
 
 // Identity case: the resized extent equals the output extent (long side == 1024), so the second bilinear has weights
 // 1 / 0 and output pixel (y, x) is the thresholded 256 -> 1024 interpolation itself.  A thread owns 8 neighbouring
-// columns of an 8-row strip: the two low-resolution rows an output row blends change every 4 rows, and their
-// horizontal interpolation at the thread's columns (8 + 8 registers) is carried from row to row.  No shared memory, no
-// barriers: the 256 KiB plane stays in L1 / L2.
+// columns (two low-resolution cells) of an 8-row strip.  In the interior the half-pixel interpolation is periodic -- output
+// column 4j + b blends low-resolution columns (j-1, j) with weights (0.375, 0.625), (0.125, 0.875) for b = 0, 1 and (j, j+1)
+// with (0.875, 0.125), (0.625, 0.375) for b = 2, 3, exactly the values lerp_coord() produces -- and likewise for rows, so
+// interior threads use constants: 4 loads per low-resolution row, no coordinate arithmetic (the generic form spent 20
+// instructions per pixel, 74 % issue utilisation: profiles/r02a_summary.md).  Strips that touch the first / last two
+// columns or rows (where the source coordinate is clamped) take the generic path.  The two low-resolution rows an output
+// row blends change every 4 rows; their horizontal interpolation (8 + 8 registers) is carried from row to row.
 constexpr int kIdRows = 8;
 __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __restrict__ low_res, int64_t plane_stride,
                                                                  int const* __restrict__ plane_index, int w, int h,
@@ -484,6 +527,56 @@ __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __
     if (x0 >= w || ys >= h) return;
     float const* __restrict__ low = low_res + (plane_index ? plane_index[plane] : plane) * plane_stride;
     uint8_t* const plane_out = out_planes ? out_planes[plane] : out_contig + (size_t)plane * w * h;
+    uint8_t* dst = plane_out + (size_t)ys * w + x0;
+    bool const aligned = (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && (w & 7) == 0;
+    if (x0 >= 8 && x0 + 16 <= kImageSize && x0 + 8 <= w && ys >= 8 && ys + 16 <= kImageSize && ys + kIdRows <= h && aligned) {
+        // ---- interior: constant weights ----
+        int const j = x0 >> 2;  // low-resolution cell of column x0 (and j + 1 of column x0 + 4)
+        // rows ys .. ys+7 (ys a multiple of 8, i = ys / 4) blend low-resolution rows (i-1, i) for t = 0, 1; (i, i+1) for
+        // t = 2..5; (i+1, i+2) for t = 6, 7.  All 16 loads are issued before the first use: the kernel is otherwise bound
+        // by three dependent trips to L2 / HBM per thread.
+        int const i = ys >> 2;
+        float a[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a[r][c] = __ldg(low + (i - 1 + r) * kLowRes + j - 1 + c);
+        auto hrow = [&](float const (&q)[4], float (&o)[8]) {
+            o[0] = 0.375f * q[0] + 0.625f * q[1];
+            o[1] = 0.125f * q[0] + 0.875f * q[1];
+            o[2] = 0.875f * q[1] + 0.125f * q[2];
+            o[3] = 0.625f * q[1] + 0.375f * q[2];
+            o[4] = 0.375f * q[1] + 0.625f * q[2];
+            o[5] = 0.125f * q[1] + 0.875f * q[2];
+            o[6] = 0.875f * q[2] + 0.125f * q[3];
+            o[7] = 0.625f * q[2] + 0.375f * q[3];
+        };
+        float ha[8], hb[8];
+        hrow(a[0], ha);
+        hrow(a[1], hb);
+        auto emit = [&](int t, float l0, float l1) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = l0 * ha[e] + l1 * hb[e];
+            *reinterpret_cast<uint2*>(dst + (size_t)t * w) = make_uint2(pack_mask4(v), pack_mask4(v + 4));
+        };
+        emit(0, 0.375f, 0.625f);
+        emit(1, 0.125f, 0.875f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ha[e] = hb[e];
+        hrow(a[2], hb);
+        emit(2, 0.875f, 0.125f);
+        emit(3, 0.625f, 0.375f);
+        emit(4, 0.375f, 0.625f);
+        emit(5, 0.125f, 0.875f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ha[e] = hb[e];
+        hrow(a[3], hb);
+        emit(6, 0.875f, 0.125f);
+        emit(7, 0.625f, 0.375f);
+        return;
+    }
+    // ---- border strips: generic coordinates ----
     Lerp lx[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) lx[e] = lerp_coord(min(x0 + e, w - 1), 0.25f, kLowRes);
@@ -494,7 +587,6 @@ __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __
     };
     int c0 = -1, c1 = -1;
     float h0[8], h1[8];
-#pragma unroll
     for (int t = 0; t < kIdRows; ++t) {
         int const y = ys + t;
         if (y < h) {
@@ -520,17 +612,17 @@ __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = q.l0 * h0[e] + q.l1 * h1[e];
-            uint8_t* dst = plane_out + (size_t)y * w + x0;
-            if (x0 + 8 <= w && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-                *reinterpret_cast<uint2*>(dst) = make_uint2(pack_mask4(v), pack_mask4(v + 4));
+            uint8_t* d = plane_out + (size_t)y * w + x0;
+            if (x0 + 8 <= w && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+                *reinterpret_cast<uint2*>(d) = make_uint2(pack_mask4(v), pack_mask4(v + 4));
             } else {
-                for (int e = 0; e < 8 && x0 + e < w; ++e) dst[e] = v[e] > 0.f ? 255 : 0;
+                for (int e = 0; e < 8 && x0 + e < w; ++e) d[e] = v[e] > 0.f ? 255 : 0;
             }
         }
     }
 }
 
-// General case.  A block produces kRows complete output rows of one mask; every intermediate is computed once per
+// General case.  A block produces g.rows (32 .. 1, by shared-memory need) complete output rows of one mask; every intermediate is computed once per
 // block and kept in shared memory:
 //   1. the few low-resolution rows the block needs                                     s_low[n_low][256]
 //   2. their horizontal interpolation at the 1024 grid                                 s_h[n_low][1024]
@@ -541,9 +633,9 @@ struct PostGeom {
     int rw, rh, w, h;
     float sx, sy;
     int n_slots, n_low;  // upper bounds of the 1024-grid rows / low-resolution rows a block needs (host)
+    int rows;            // output rows per block
 };
 
-template <int kRows>
 __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __restrict__ low_res, int64_t plane_stride,
                                                              int const* __restrict__ plane_index, PostGeom g,
                                                              uint8_t* const* __restrict__ out_planes,
@@ -554,8 +646,8 @@ __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __rest
     float* const s_grid = s_h + g.n_low * kImageSize;
     int const tid = threadIdx.x;
     int const plane = blockIdx.y;
-    int const y0 = blockIdx.x * kRows;
-    int const rows_valid = min(kRows, g.h - y0);
+    int const y0 = blockIdx.x * g.rows;
+    int const rows_valid = min(g.rows, g.h - y0);
     float const* low = low_res + (plane_index ? plane_index[plane] : plane) * plane_stride;
     uint8_t* const plane_out = out_planes ? out_planes[plane] : out_contig + (size_t)plane * g.w * g.h;
 
@@ -590,14 +682,10 @@ __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __rest
         for (int xx = tid; xx < g.rw; xx += 256) s_grid[slot * kImageSize + xx] = q.l0 * r0[xx] + q.l1 * r1[xx];
     }
     __syncthreads();
-    // 4. second bilinear + threshold
-    Lerp ly[kRows];
-#pragma unroll
-    for (int t = 0; t < kRows; ++t) {
-        ly[t] = lerp_coord(min(y0 + t, g.h - 1), g.sy, g.rh);
-        ly[t].i0 -= g_base;
-        ly[t].i1 -= g_base;
-    }
+    // 4. second bilinear + threshold.  The row loop is NOT unrolled: its coordinates are block-uniform (uniform datapath),
+    // the two "row pair changed" branches are uniform, and the body stays small (the unrolled form was 3600 instructions,
+    // 22 per pixel, a third of them branches and predicate logic: profiles/r02a_summary.md).
+    bool const word_ok = (g.w & 3) == 0 && (reinterpret_cast<uintptr_t>(plane_out) & 3) == 0;
     for (int x0 = 4 * tid; x0 < g.w; x0 += 1024) {
         Lerp lx[4];
 #pragma unroll
@@ -609,37 +697,37 @@ __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __rest
         };
         int ca = -1, cb = -1;
         float ha[4], hb[4];
+        uint8_t* dst = plane_out + (size_t)y0 * g.w + x0;
+        bool const full = x0 + 4 <= g.w && word_ok;
+#pragma unroll 1
+        for (int t = 0; t < rows_valid; ++t, dst += g.w) {
+            Lerp const q = lerp_coord(y0 + t, g.sy, g.rh);
+            int const a = q.i0 - g_base, b = q.i1 - g_base;
+            if (a != ca) {
+                if (a == cb) {
 #pragma unroll
-        for (int t = 0; t < kRows; ++t) {
-            if (t < rows_valid) {
-                int const a = ly[t].i0, b = ly[t].i1;  // block-uniform
-                if (a != ca) {
-                    if (a == cb) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) ha[e] = hb[e];
-                    } else {
-                        hrow(a, ha);
-                    }
-                    ca = a;
-                }
-                if (b != cb) {
-                    if (b == ca) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) hb[e] = ha[e];
-                    } else {
-                        hrow(b, hb);
-                    }
-                    cb = b;
-                }
-                float v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = ly[t].l0 * ha[e] + ly[t].l1 * hb[e];
-                uint8_t* dst = plane_out + (size_t)(y0 + t) * g.w + x0;
-                if (x0 + 4 <= g.w && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
-                    *reinterpret_cast<uint32_t*>(dst) = pack_mask4(v);
+                    for (int e = 0; e < 4; ++e) ha[e] = hb[e];
                 } else {
-                    for (int e = 0; e < 4 && x0 + e < g.w; ++e) dst[e] = v[e] > 0.f ? 255 : 0;
+                    hrow(a, ha);
                 }
+                ca = a;
+            }
+            if (b != cb) {
+                if (b == ca) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) hb[e] = ha[e];
+                } else {
+                    hrow(b, hb);
+                }
+                cb = b;
+            }
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = q.l0 * ha[e] + q.l1 * hb[e];
+            if (full) {
+                *reinterpret_cast<uint32_t*>(dst) = pack_mask4(v);
+            } else {
+                for (int e = 0; e < 4 && x0 + e < g.w; ++e) dst[e] = v[e] > 0.f ? 255 : 0;
             }
         }
     }
@@ -681,14 +769,6 @@ template <typename K> void set_smem_limit(K kernel, int bytes) {
 
 constexpr int kPostSmemBudget = 72 * 1024;  // three blocks per SM
 
-template <int kRows>
-void launch_post_tile(cudaStream_t s, float const* low_res, int64_t plane_stride, int const* plane_index, int count,
-                      PostGeom const& g, int smem, uint8_t* const* out_planes, uint8_t* out_contig) {
-    set_smem_limit(mask_post_tile_kernel<kRows>, smem);
-    dim3 grid(ceil_div(g.h, kRows), count);
-    mask_post_tile_kernel<kRows><<<grid, 256, smem, s>>>(low_res, plane_stride, plane_index, g, out_planes, out_contig);
-}
-
 // shared-memory need of a kRows-row block; fills the exact upper bounds of the rows it may touch
 int post_plan(PostGeom& g, int rows) {
     // span of i1(last) - i0(first) + 1 over `n` consecutive destinations at source step `scale`: <= scale*(n-1) + 3
@@ -715,7 +795,7 @@ void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride
         return;
     }
     int rows = 0, smem = 0;
-    for (int r : {16, 8, 4, 2, 1}) {
+    for (int r : {32, 16, 8, 4, 2, 1}) {
         smem = post_plan(g, r);
         if (smem <= kPostSmemBudget) { rows = r; break; }
     }
@@ -726,20 +806,17 @@ void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride
         KERNEL_CHECK();
         return;
     }
-    switch (rows) {
-        case 16: launch_post_tile<16>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-        case 8: launch_post_tile<8>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-        case 4: launch_post_tile<4>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-        case 2: launch_post_tile<2>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-        default: launch_post_tile<1>(s, low_res, plane_stride, plane_index, count, g, smem, out_planes, out_contig); break;
-    }
+    g.rows = rows;
+    set_smem_limit(mask_post_tile_kernel, smem);
+    mask_post_tile_kernel<<<dim3(ceil_div(h, rows), count), 256, smem, s>>>(low_res, plane_stride, plane_index, g, out_planes, out_contig);
     KERNEL_CHECK();
 }
 
 // Tile shape for the single-kernel resize: the largest candidate whose shared-memory need fits the budget.
 ResizeTile plan_resize_tile(ResizeDeviceTables const& t, int bpp, int kt, int out_w, int out_h) {
-    static int const kRowsCand[] = {16, 8, 4, 2, 1};
-    int const tc_full = bpp == 3 ? 80 : 256 / bpp;  // 240 / 256 threads own an H-pass column
+    static int const kRowsCand[] = {32, 16, 8, 4, 2, 1};
+    // tall, narrow tiles: two row groups of tc * bpp H-pass columns fill the 256 threads (120 / 128 columns each)
+    int const tc_full = bpp == 3 ? 40 : 128 / bpp;
     ResizeTile best;
     for (int tc = tc_full; tc >= 8 && best.tr == 0; tc /= 2) {
         if ((tc * bpp) % 4 != 0) continue;

@@ -10,6 +10,8 @@
 
 #include "../profiler.hpp"
 
+#include <cstdlib>
+
 namespace dlimg {
 namespace dec {
 
@@ -120,6 +122,173 @@ __global__ void __launch_bounds__(kWarps * 32) t2i_flash_kernel(float const* __r
     }
 }
 
+// ---- tensor-core form ----------------------------------------------------------------------------------------------
+// The same partials from warp-level MMAs (mma.sync m16n8k16, fp16 operands, fp32 accumulators) -- the CUDA-core kernel
+// above spends ~100 instructions per key and lane (profiles/r02a_summary.md: 80-92 us per 64-prompt launch for 134 MB).
+// A warp owns 64 consecutive keys of its block's split and walks them in 4 steps of 16 keys, 4 heads at a time:
+//   S^T (16 keys x 8 tokens) = K_h (16 x 16 dims, A operand straight from global memory: a fragment register is two
+//         neighbouring dims of one key row) * Q_h^T (16 dims x 8 tokens: 7 + one zero row; B operand, resident registers)
+//   pass 1 takes the maximum of every (head, token) column over the warp's 64 keys; pass 2 recomputes S^T (the K rows
+//         come back from L1), p = 2^(s - max), and accumulates  O (8 tokens x 16 dims) += P (tokens x keys) * V_h:
+//         P is S^T transposed -- one movmatrix per 8 x 8 block of the accumulator fragment -- and V's B fragment
+//         (two KEYS of one dim per register) is the transposed natural row fragment, again by movmatrix.
+// With the final maximum known before pass 2 nothing is ever rescaled.  Scores are kept in log2 units (q carries
+// 0.25 * log2 e).  Output: the same per-(prompt, split) partials as above, merged by token_post_t2i.
+__device__ __forceinline__ void mma16816_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
+    uint32_t y;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 const v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t const*>(&v);
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+#if !defined(DLIMG_B200_ACT_BF16)
+constexpr int kKeysPerWarp = kImgTokens / (kT2iSplits * kWarps);  // 64
+static_assert(kKeysPerWarp == 64, "the tensor-core kernel walks 4 steps of 16 keys per warp");
+
+__global__ void __launch_bounds__(kWarps * 32, 2) t2i_mma_kernel(float const* __restrict__ q, act_t const* __restrict__ base,
+                                                              act_t const* const* __restrict__ ptrs, int64_t prompt_stride,
+                                                              int pitch, int v_off, float* __restrict__ part) {
+    __shared__ float sm_acc[kWarps][kTokens][128];
+    __shared__ float sm_m[kWarps][kTokens][kHeads];
+    __shared__ float sm_s[kWarps][kTokens][kHeads];
+    int const p = blockIdx.x, split = blockIdx.y;
+    int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int const g = lane >> 2, t = lane & 3;
+    act_t const* const Kb = (ptrs ? ptrs[p] : base + (size_t)p * prompt_stride) + (size_t)((split * kWarps + warp) * kKeysPerWarp) * pitch;
+    act_t const* const Vb = Kb + v_off;
+    float const kQScale = 0.25f * 1.4426950408889634f;  // 1 / sqrt(16) * log2 e
+    float const* qrow = q + ((size_t)p * kTokens + g) * 128;  // token g (g == 7: the zero padding row)
+
+#pragma unroll 1
+    for (int hg = 0; hg < 2; ++hg) {  // four heads at a time (register budget)
+        uint32_t qb[4][2];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            int const c = (hg * 4 + h) * 16 + 2 * t;
+            float2 const x0 = g < kTokens ? *reinterpret_cast<float2 const*>(qrow + c) : make_float2(0.f, 0.f);
+            float2 const x1 = g < kTokens ? *reinterpret_cast<float2 const*>(qrow + c + 8) : make_float2(0.f, 0.f);
+            qb[h][0] = pack_h2(x0.x * kQScale, x0.y * kQScale);
+            qb[h][1] = pack_h2(x1.x * kQScale, x1.y * kQScale);
+        }
+        auto scores = [&](int step, int h, float (&s)[4]) {  // S^T of 16 keys for head hg * 4 + h
+            act_t const* r0 = Kb + (size_t)(step * 16 + g) * pitch + (hg * 4 + h) * 16 + 2 * t;
+            act_t const* r1 = r0 + (size_t)8 * pitch;
+            uint32_t const a0 = __ldg(reinterpret_cast<uint32_t const*>(r0)), a1 = __ldg(reinterpret_cast<uint32_t const*>(r1));
+            uint32_t const a2 = __ldg(reinterpret_cast<uint32_t const*>(r0 + 8)), a3 = __ldg(reinterpret_cast<uint32_t const*>(r1 + 8));
+            s[0] = s[1] = s[2] = s[3] = 0.f;
+            mma16816_f16(s, a0, a1, a2, a3, qb[h][0], qb[h][1]);
+        };
+        // pass 1: column maxima (tokens 2t, 2t + 1) over the warp's keys
+        float mx[4][2];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) mx[h][0] = mx[h][1] = -INFINITY;
+#pragma unroll
+        for (int step = 0; step < 4; ++step)
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                float s[4];
+                scores(step, h, s);
+                mx[h][0] = fmaxf(mx[h][0], fmaxf(s[0], s[2]));
+                mx[h][1] = fmaxf(mx[h][1], fmaxf(s[1], s[3]));
+            }
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float m = mx[h][e];
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                mx[h][e] = m;
+            }
+        // pass 2: probabilities, sums, O += P V
+        float o[4][2][4], l[4][2];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            l[h][0] = l[h][1] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) o[h][j][0] = o[h][j][1] = o[h][j][2] = o[h][j][3] = 0.f;
+        }
+#pragma unroll
+        for (int step = 0; step < 4; ++step)
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                float s[4];
+                scores(step, h, s);
+                float const p0 = ex2f(s[0] - mx[h][0]), p1 = ex2f(s[1] - mx[h][1]);
+                float const p2 = ex2f(s[2] - mx[h][0]), p3 = ex2f(s[3] - mx[h][1]);
+                l[h][0] += p0 + p2;
+                l[h][1] += p1 + p3;
+                uint32_t const pa0 = movm_t(pack_h2(p0, p1));  // P[token g][keys 2t, 2t + 1]
+                uint32_t const pa2 = movm_t(pack_h2(p2, p3));  // P[token g][keys 8 + 2t, 9 + 2t]
+                act_t const* r0 = Vb + (size_t)(step * 16 + g) * pitch + (hg * 4 + h) * 16 + 2 * t;
+                act_t const* r1 = r0 + (size_t)8 * pitch;
+                uint32_t const v00 = movm_t(__ldg(reinterpret_cast<uint32_t const*>(r0)));      // keys 0-7,  dims 0-7
+                uint32_t const v10 = movm_t(__ldg(reinterpret_cast<uint32_t const*>(r1)));      // keys 8-15, dims 0-7
+                uint32_t const v01 = movm_t(__ldg(reinterpret_cast<uint32_t const*>(r0 + 8)));  // keys 0-7,  dims 8-15
+                uint32_t const v11 = movm_t(__ldg(reinterpret_cast<uint32_t const*>(r1 + 8)));  // keys 8-15, dims 8-15
+                mma16816_f16(o[h][0], pa0, 0u, pa2, 0u, v00, v10);
+                mma16816_f16(o[h][1], pa0, 0u, pa2, 0u, v01, v11);
+            }
+        // partials of this warp: accumulators (token g, dims 8 j + 2t, + 1), maxima / sums (tokens 2t, 2t + 1)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float s = l[h][e];
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 16);
+                int const tok = 2 * t + e;
+                if (g == 0 && tok < kTokens) {
+                    sm_m[warp][tok][hg * 4 + h] = mx[h][e] * 0.6931471805599453f;  // back to natural-log units
+                    sm_s[warp][tok][hg * 4 + h] = s;
+                }
+            }
+            if (g < kTokens) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    *reinterpret_cast<float2*>(&sm_acc[warp][g][(hg * 4 + h) * 16 + 8 * j + 2 * t]) = make_float2(o[h][j][0], o[h][j][1]);
+            }
+        }
+    }
+    __syncthreads();
+    // merge the 8 warps -> one partial per (prompt, split)
+    float* dst = part + ((size_t)p * kT2iSplits + split) * kTokens * kPartStride;
+    for (int idx = tid; idx < kTokens * 128; idx += kWarps * 32) {
+        int const tk = idx >> 7, d = idx & 127, h = d >> 4;
+        float M = sm_m[0][tk][h];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) M = fmaxf(M, sm_m[w][tk][h]);
+        float A = 0.f, S = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            float const e = __expf(sm_m[w][tk][h] - M);
+            A = fmaf(sm_acc[w][tk][d], e, A);
+            S = fmaf(sm_s[w][tk][h], e, S);
+        }
+        dst[tk * kPartStride + d] = A;
+        if ((d & 15) == 0) {
+            dst[tk * kPartStride + 128 + h] = M;
+            dst[tk * kPartStride + 136 + h] = S;
+        }
+    }
+}
+#endif
+
 __global__ void __launch_bounds__(128) t2i_combine_kernel(float const* __restrict__ part, float* __restrict__ out) {
     int const p = blockIdx.x, t = blockIdx.y, d = threadIdx.x, h = d >> 4;
     float const* src = part + ((size_t)p * kT2iSplits * kTokens + t) * kPartStride;
@@ -145,9 +314,16 @@ void token_to_image_attention(cudaStream_t s, float const* q, act_t const* base,
     static_assert(kImgTokens % (kT2iSplits * kWarps * kChunk) == 0, "key split must be even");
     {
         ProfScope prof(s, CAT_DEC_ATTN, 4.0 * P * kTokens * kImgTokens * 128, (double)P * kImgTokens * 128 * 4);
+#if defined(DLIMG_B200_ACT_BF16)
         t2i_flash_kernel<<<dim3(P, kT2iSplits), kWarps * 32, 0, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
+#else
+        static bool const cuda_core = std::getenv("DLIMG_B200_T2I_SIMT") != nullptr;  // cross-check: the CUDA-core form
+        if (cuda_core) t2i_flash_kernel<<<dim3(P, kT2iSplits), kWarps * 32, 0, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
+        else t2i_mma_kernel<<<dim3(P, kT2iSplits), kWarps * 32, 0, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
+#endif
         KERNEL_CHECK();
     }
+    if (!out) return;  // the partials are merged by token_post_t2i
     ProfScope prof(s, CAT_DEC_ATTN);
     t2i_combine_kernel<<<dim3(P, kTokens), 128, 0, s>>>(scratch, out);
     KERNEL_CHECK();

@@ -150,12 +150,25 @@ Norm load_norm(WeightFile const& wf, std::string const& p, int c) {
     return n;
 }
 
+Linear32T load_linear32t(WeightFile const& wf, std::string const& p, int n, int k) {
+    auto const& w = wf.get(p + ".weight", {n, k}).data;
+    std::vector<float> t((size_t)n * k);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < k; ++j) t[(size_t)j * n + i] = w[(size_t)i * k + j];
+    Linear32T l;
+    l.n = n;
+    l.k = k;
+    l.wt.upload(t);
+    l.b.upload(wf.get(p + ".bias", {n}).data);
+    return l;
+}
+
 AttnW load_attn(WeightFile const& wf, std::string const& p, int dim, int internal) {
     AttnW a;
-    a.q = load_linear32(wf, p + ".q_proj", internal, dim);
-    a.k = load_linear32(wf, p + ".k_proj", internal, dim);
-    a.v = load_linear32(wf, p + ".v_proj", internal, dim);
-    a.o = load_linear32(wf, p + ".out_proj", dim, internal);
+    a.q = load_linear32t(wf, p + ".q_proj", internal, dim);
+    a.k = load_linear32t(wf, p + ".k_proj", internal, dim);
+    a.v = load_linear32t(wf, p + ".v_proj", internal, dim);
+    a.o = load_linear32t(wf, p + ".out_proj", dim, internal);
     return a;
 }
 
@@ -326,10 +339,10 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
         std::string const p = D + "transformer.layers." + std::to_string(i);
         DecLayerW& l = dec_.layers[i];
         l.self_attn = load_attn(wf, p + ".self_attn", 256, 256);
-        l.t2i_q = load_linear32(wf, p + ".cross_attn_token_to_image.q_proj", 128, 256);
-        l.t2i_o = load_linear32(wf, p + ".cross_attn_token_to_image.out_proj", 256, 128);
-        l.i2t_k = load_linear32(wf, p + ".cross_attn_image_to_token.k_proj", 128, 256);
-        l.i2t_v = load_linear32(wf, p + ".cross_attn_image_to_token.v_proj", 128, 256);
+        l.t2i_q = load_linear32t(wf, p + ".cross_attn_token_to_image.q_proj", 128, 256);
+        l.t2i_o = load_linear32t(wf, p + ".cross_attn_token_to_image.out_proj", 256, 128);
+        l.i2t_k = load_linear32t(wf, p + ".cross_attn_image_to_token.k_proj", 128, 256);
+        l.i2t_v = load_linear32t(wf, p + ".cross_attn_image_to_token.v_proj", 128, 256);
         l.i2t_out = load_linear16(wf, p + ".cross_attn_image_to_token.out_proj", 256, 128);
         load_image_proj({{p + ".cross_attn_token_to_image.k_proj", true}, {p + ".cross_attn_token_to_image.v_proj", false},
                          {p + ".cross_attn_image_to_token.q_proj", true}},
@@ -343,8 +356,8 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
     }
     {
         std::string const p = D + "transformer.final_attn_token_to_image";
-        dec_.final_q = load_linear32(wf, p + ".q_proj", 128, 256);
-        dec_.final_o = load_linear32(wf, p + ".out_proj", 256, 128);
+        dec_.final_q = load_linear32t(wf, p + ".q_proj", 128, 256);
+        dec_.final_o = load_linear32t(wf, p + ".out_proj", 256, 128);
         load_image_proj({{p + ".k_proj", true}, {p + ".v_proj", false}}, dec_.kv_final, dec_.pos_kv_final);
     }
     dec_.norm_final = load_norm(wf, D + "transformer.norm_final_attn", 256);
@@ -404,9 +417,10 @@ EncoderWorkspace::EncoderWorkspace(int mb) : max_batch(mb) {
 DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
     size_t const P = (size_t)mp;
     param_block.allocate(DecoderParams::bytes(mp));
-    for (auto* b : {&tok0, &queries, &tq, &tk, &tv, &ta, &tmp}) b->allocate(P * 7 * 256);
+    for (auto* b : {&tok0, &queries, &tmp}) b->allocate(P * 7 * 256);
     t128a.allocate(P * 7 * 128);
     t128b.allocate(P * 7 * 128);
+    t128c.allocate(P * 7 * 128);
     hid.allocate(P * 7 * 2048);
     hyper.allocate(P * 4 * 32);
     iou.allocate(P * 4);
@@ -414,7 +428,6 @@ DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
     big.allocate(P * 4096 * 256);
     kvq.allocate(P * 4096 * 384);
     ao.allocate(P * 4096 * 128);
-    up2.allocate(P * 16384 * 128);
     low.allocate(P * 4 * 65536);
     plane_index.allocate(P * 3);
     iou_sel.allocate(P * 3);
@@ -616,20 +629,6 @@ void SamModel::lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, 
     dec::linear_small(s, x, xs, x2, xs, rows, l.k, l.w.get(), l.b.get(), l.n, relu, y, ys);
 }
 
-// Token self-attention block of the two-way transformer: queries <- LN(queries? + out_proj(attn(q, k, v)))
-void SamModel::attn_tokens(cudaStream_t s, DecoderWorkspace& ws, AttnW const& a, bool with_pe, bool residual, Norm const& n,
-                           int P) const {
-    int const R = P * dec::kTokens;
-    float const* pe = with_pe ? ws.tok0.get() : nullptr;
-    lin(s, ws.queries.get(), 256, pe, R, a.q, false, ws.tq.get(), 256);
-    lin(s, ws.queries.get(), 256, pe, R, a.k, false, ws.tk.get(), 256);
-    lin(s, ws.queries.get(), 256, nullptr, R, a.v, false, ws.tv.get(), 256);
-    dec::token_self_attention(s, ws.tq.get(), ws.tk.get(), ws.tv.get(), P, ws.ta.get());
-    lin(s, ws.ta.get(), 256, nullptr, R, a.o, false, ws.tmp.get(), 256);
-    dec::layernorm256(s, ws.tmp.get(), residual ? ws.queries.get() : nullptr, 0, R, n.g.get(), n.b.get(), nullptr, 0,
-                      ws.queries.get(), nullptr);
-}
-
 void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P) const {
     DLIMG_ASSERT(P >= 1 && P <= ws.max_prompts);
     DecoderParams const prm = DecoderWorkspace::layout(ws.param_block.get(), P);
@@ -639,45 +638,71 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P) const {
 
     dec::PromptParams pp{dec_.gaussian.get(), dec_.point_embed.get(), dec_.not_a_point.get(), dec_.iou_token.get(),
                          dec_.mask_tokens.get()};
-    dec::prompt_tokens(s, prm.coords, prm.labels, P, pp, ws.tok0.get());
-    CUDA_CHECK(cudaMemcpyAsync(ws.queries.get(), ws.tok0.get(), sizeof(float) * (size_t)R * 256, cudaMemcpyDeviceToDevice, s));
+    dec::prompt_tokens(s, prm.coords, prm.labels, P, pp, ws.tok0.get(), ws.queries.get());
 
     for (int li = 0; li < 2; ++li) {
         DecLayerW const& l = dec_.layers[li];
         bool const first = li == 0;
-        // (1) token self-attention (layer 0: no positional encoding, output replaces the queries)
-        attn_tokens(s, ws, l.self_attn, !first, !first, l.n1, P);
+        // (1) token self-attention (layer 0: no positional encoding, output replaces the queries) + LayerNorm + the
+        // query projection of (2), one kernel
+        {
+            dec::TokenAttnBlock a;
+            a.queries = ws.queries.get();
+            a.pe = ws.tok0.get();
+            a.wq_t = l.self_attn.q.wt.get(); a.bq = l.self_attn.q.b.get();
+            a.wk_t = l.self_attn.k.wt.get(); a.bk = l.self_attn.k.b.get();
+            a.wv_t = l.self_attn.v.wt.get(); a.bv = l.self_attn.v.b.get();
+            a.wo_t = l.self_attn.o.wt.get(); a.bo = l.self_attn.o.b.get();
+            a.gamma = l.n1.g.get(); a.beta = l.n1.b.get();
+            a.with_pe = first ? 0 : 1;
+            a.residual = first ? 0 : 1;
+            a.w_next_t = l.t2i_q.wt.get(); a.b_next = l.t2i_q.b.get();
+            a.out_next = ws.t128a.get();
+            dec::token_attn_block(s, a, P);
+        }
         // image-side projections [K | V | Q] of this layer from the image stream: layer 0's depend on the image only and
         // come with the embedding (per-prompt tables); layer 1's are one GEMM with the position terms added by its epilogue
         if (!first)
             gemm16(s, ws.keys.get(), IR, dec_.kvq[1], ws.kvq.get(), gemm::ACT_NONE, dec_.pos_kvq[1].get(), nullptr, false, 0, nullptr,
                    dec::kImgTokens);
-        // (2) tokens attend to the image
-        lin(s, ws.queries.get(), 256, ws.tok0.get(), R, l.t2i_q, false, ws.t128a.get(), 128);
+        // (2) tokens attend to the image (split-key partials), then merge + out projection + residual + LayerNorm
         dec::token_to_image_attention(s, ws.t128a.get(), ws.kvq.get(), first ? prm.kvq0 : nullptr, kvq_stride, 384, 128, P,
-                                      ws.t2i_scratch.get(), ws.t128b.get());
-        lin(s, ws.t128b.get(), 128, nullptr, R, l.t2i_o, false, ws.tmp.get(), 256);
-        dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, l.n2.g.get(), l.n2.b.get(), nullptr, 0, ws.queries.get(), nullptr);
-        // (3) token MLP
+                                      ws.t2i_scratch.get(), nullptr);
+        {
+            dec::TokenPostT2i t{ws.t2i_scratch.get(), ws.queries.get(), l.t2i_o.wt.get(), l.t2i_o.b.get(), l.n2.g.get(), l.n2.b.get()};
+            dec::token_post_t2i(s, t, P);
+        }
+        // (3) token MLP on the tensor cores (7 rows per prompt, 4 MB of weights read once per pass)
         lin(s, ws.queries.get(), 256, nullptr, R, l.lin1, true, ws.hid.get(), 2048);
         lin(s, ws.hid.get(), 2048, nullptr, R, l.lin2, false, ws.tmp.get(), 256);
-        dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, l.n3.g.get(), l.n3.b.get(), nullptr, 0, ws.queries.get(), nullptr);
+        // residual + LayerNorm + the token-side projections of (4) (and, after the last layer, of the final attention)
+        {
+            dec::TokenPostMlp m;
+            m.queries = ws.queries.get();
+            m.mlp_out = ws.tmp.get();
+            m.pe = ws.tok0.get();
+            m.gamma = l.n3.g.get(); m.beta = l.n3.b.get();
+            m.count = first ? 2 : 3;
+            m.w_t[0] = l.i2t_k.wt.get(); m.b[0] = l.i2t_k.b.get(); m.with_pe[0] = 1; m.out[0] = ws.t128a.get();
+            m.w_t[1] = l.i2t_v.wt.get(); m.b[1] = l.i2t_v.b.get(); m.with_pe[1] = 0; m.out[1] = ws.t128b.get();
+            m.w_t[2] = dec_.final_q.wt.get(); m.b[2] = dec_.final_q.b.get(); m.with_pe[2] = 1; m.out[2] = ws.t128c.get();
+            dec::token_post_mlp(s, m, P);
+        }
         // (4) image attends to the tokens: keys <- LN(keys + out_proj(attn)); Q is column block 2 of [K | V | Q]
-        lin(s, ws.queries.get(), 256, ws.tok0.get(), R, l.i2t_k, false, ws.t128a.get(), 128);
-        lin(s, ws.queries.get(), 256, nullptr, R, l.i2t_v, false, ws.t128b.get(), 128);
         dec::image_to_token_attention(s, ws.kvq.get(), first ? prm.kvq0 : nullptr, kvq_stride, 384, 256, ws.t128a.get(), ws.t128b.get(),
                                       P, ws.ao.get());
         gemm16(s, ws.ao.get(), IR, l.i2t_out, ws.big.get(), gemm::ACT_NONE, nullptr);
         dec::layernorm256_img(s, ws.big.get(), ws.keys.get(), first ? prm.keys0 : nullptr, P, l.n4.g.get(), l.n4.b.get(), ws.keys.get());
     }
-    // final token -> image attention
+    // final token -> image attention (its query projection came out of the last token_post_mlp)
     gemm16(s, ws.keys.get(), IR, dec_.kv_final, ws.kvq.get(), gemm::ACT_NONE, dec_.pos_kv_final.get(), nullptr, false, 0, nullptr,
            dec::kImgTokens);
-    lin(s, ws.queries.get(), 256, ws.tok0.get(), R, dec_.final_q, false, ws.t128a.get(), 128);
-    dec::token_to_image_attention(s, ws.t128a.get(), ws.kvq.get(), nullptr, kv_stride, 256, 128, P, ws.t2i_scratch.get(), ws.t128b.get());
-    lin(s, ws.t128b.get(), 128, nullptr, R, dec_.final_o, false, ws.tmp.get(), 256);
-    dec::layernorm256(s, ws.tmp.get(), ws.queries.get(), 0, R, dec_.norm_final.g.get(), dec_.norm_final.b.get(), nullptr, 0,
-                      ws.queries.get(), nullptr);
+    dec::token_to_image_attention(s, ws.t128c.get(), ws.kvq.get(), nullptr, kv_stride, 256, 128, P, ws.t2i_scratch.get(), nullptr);
+    {
+        dec::TokenPostT2i t{ws.t2i_scratch.get(), ws.queries.get(), dec_.final_o.wt.get(), dec_.final_o.b.get(), dec_.norm_final.g.get(),
+                            dec_.norm_final.b.get()};
+        dec::token_post_t2i(s, t, P);
+    }
 
     // IoU head on the iou token, hypernetwork MLPs on the four mask tokens: one kernel for the five 3-layer MLPs
     {
@@ -693,11 +718,28 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P) const {
         dec::token_mlp3(s, ws.queries.get(), P, h, ws.hyper.get(), ws.iou.get());
     }
 
-    // upscaling: two transposed 2x2/stride-2 convolutions as GEMMs in a blocked pixel layout
-    gemm16(s, ws.keys.get(), IR, dec_.up1, ws.big.get(), gemm::ACT_NONE, nullptr);
-    dec::layernorm64_gelu(s, ws.big.get(), IR * 4, dec_.up_ln.g.get(), dec_.up_ln.b.get());
-    gemm16(s, ws.big.get(), IR * 4, dec_.up2, ws.up2.get(), gemm::ACT_GELU, nullptr);
-    dec::mask_dot(s, ws.hyper.get(), ws.up2.get(), P, ws.low.get());
+    // upscaling: two transposed 2x2/stride-2 convolutions as GEMMs in a blocked pixel layout, with the LayerNorm2d + GELU
+    // between them and the final hypernetwork product folded into their epilogues (gemm.cuh Epilogue::fuse): the
+    // (P, 65536, 32) upscaled embedding is never written, only the (P, 4, 256, 256) logits
+    {
+        gemm::Epilogue e;
+        e.bias = dec_.up1.b.get();
+        e.act = gemm::ACT_GELU;
+        e.ldc = dec_.up1.n;
+        e.fuse = 1;
+        e.fuse_a = dec_.up_ln.g.get();
+        e.fuse_b = dec_.up_ln.b.get();
+        gemm::launch(s, false, gemm::Operand{ws.keys.get(), IR, 256, 256}, gemm::Operand{dec_.up1.w.get(), 256, 256, 256}, ws.big.get(), e,
+                     num_sms_);
+        gemm::Epilogue e2;
+        e2.bias = dec_.up2.b.get();
+        e2.act = gemm::ACT_GELU;
+        e2.ldc = dec_.up2.n;
+        e2.fuse = 2;
+        e2.fuse_a = ws.hyper.get();
+        e2.fuse_out = ws.low.get();
+        gemm::launch(s, false, gemm::Operand{ws.big.get(), IR * 4, 64, 64}, gemm::Operand{dec_.up2.w.get(), 128, 64, 64}, nullptr, e2, num_sms_);
+    }
 }
 
 }  // namespace dlimg

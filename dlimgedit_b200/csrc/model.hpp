@@ -104,11 +104,16 @@ struct EncoderW {
     Norm neck_ln2;
 };
 
-struct AttnW { Linear32 q, k, v, o; };  // token-side projections (fp32); the image-side ones live in DecoderW below
+struct Linear32T {  // fp32 weight TRANSPOSED to (K, N) + bias -- the fused token-side kernels (decoder_tokens.cu)
+    DeviceBuffer<float> wt;
+    DeviceBuffer<float> b;
+    int n = 0, k = 0;
+};
+struct AttnW { Linear32T q, k, v, o; };  // token-side projections (fp32); the image-side ones live in DecoderW below
 struct DecLayerW {
     AttnW self_attn;
-    Linear32 t2i_q, t2i_o;   // tokens -> image attention: query and output projections (token rows)
-    Linear32 i2t_k, i2t_v;   // image -> tokens attention: key / value projections (token rows)
+    Linear32T t2i_q, t2i_o;  // tokens -> image attention: query and output projections (token rows)
+    Linear32T i2t_k, i2t_v;  // image -> tokens attention: key / value projections (token rows)
     Linear16 i2t_out;        // (256, 128) output projection of image -> tokens attention (image rows, 16-bit)
     Norm n1, n2, n3, n4;
     Linear32 lin1, lin2;
@@ -116,7 +121,7 @@ struct DecLayerW {
 struct DecoderW {
     DeviceBuffer<float> gaussian, point_embed, not_a_point, no_mask, iou_token, mask_tokens;
     DecLayerW layers[2];
-    Linear32 final_q, final_o;
+    Linear32T final_q, final_o;
     Norm norm_final;
     // Image-side projections as 16-bit GEMM operands.  The projections that see `keys + pos` (attention keys of
     // tokens -> image, queries of image -> tokens) are split as keys W^T + (pos W^T): the second term does not depend on the
@@ -155,14 +160,13 @@ struct DecoderParams {
 struct DecoderWorkspace {
     int max_prompts = 0;
     DeviceBuffer<uint8_t> param_block;                       // DecoderParams::bytes(max_prompts), laid out per pass by layout()
-    DeviceBuffer<float> tok0, queries, tq, tk, tv, ta, tmp;  // (P,7,256)
-    DeviceBuffer<float> t128a, t128b;                        // (P,7,128)
+    DeviceBuffer<float> tok0, queries, tmp;                  // (P,7,256)
+    DeviceBuffer<float> t128a, t128b, t128c;                 // (P,7,128)
     DeviceBuffer<float> hid;                                 // (P,7,2048)
     DeviceBuffer<float> hyper, iou;                          // (P,4,32), (P,4)
     DeviceBuffer<act_t> keys, big;                           // (P,4096,256) image stream / GEMM output in front of a LayerNorm
     DeviceBuffer<act_t> kvq;                                 // (P,4096,384) [K | V | Q] of layer 1; (P,4096,256) [K | V] final
     DeviceBuffer<act_t> ao;                                  // (P,4096,128) image -> tokens attention output
-    DeviceBuffer<act_t> up2;                                 // (P,16384,128)
     DeviceBuffer<float> low;                                 // (P,4,256,256)
     DeviceBuffer<int> plane_index;                           // (P*3)
     DeviceBuffer<float> iou_sel;                             // (P*3)
@@ -207,8 +211,6 @@ class SamModel {
     void gemm32(cudaStream_t s, float const* a, int64_t rows, Linear32 const& l, float* out, int act) const;
     void lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, int rows, Linear32 const& l, bool relu, float* y,
              int64_t ys) const;
-    void attn_tokens(cudaStream_t s, DecoderWorkspace& ws, AttnW const& a, bool with_pe, bool residual, Norm const& n,
-                     int P) const;
 
     EncoderW enc_;
     DecoderW dec_;
