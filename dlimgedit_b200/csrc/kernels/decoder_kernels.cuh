@@ -55,6 +55,10 @@ void token_to_image_attention(cudaStream_t s, float const* q, act_t const* base,
 void image_to_token_attention(cudaStream_t s, act_t const* Q, act_t const* const* Qptrs, int64_t q_prompt_stride, int q_pitch,
                               int q_off, float const* kt, float const* vt, int P, act_t* out);
 
+// The same on tensor cores (mma.sync, t2i_attention.cu); DLIMG_B200_I2T_SIMT selects the CUDA-core form above.
+void image_to_token_attention_mma(cudaStream_t s, act_t const* Q, act_t const* const* Qptrs, int64_t q_prompt_stride, int q_pitch,
+                                  int q_off, float const* kt, float const* vt, int P, act_t* out);
+
 // fp32 -> 16-bit storage (load-time tables).
 void f32_to_act(cudaStream_t s, float const* in, int64_t n, act_t* out);
 
@@ -84,13 +88,13 @@ struct TokenMlp3 {
 };
 void token_mlp3(cudaStream_t s, float const* tokens, int P, TokenMlp3 const& heads, float* hyper, float* iou);
 
-// ---- fused token-side blocks (decoder_tokens.cu): one CTA per prompt, weights transposed to (K, N) ------------------------
+// ---- fused token-side blocks (decoder_tokens.cu): a 4-CTA cluster per prompt, weights as [K / 4][N][4] ----------------------
 // [+pe] -> q, k, v -> 8-head self-attention over the 7 tokens -> out projection -> [+residual] LayerNorm -> queries (in
 // place), then out_next (P, 7, 128) = (queries + pe) w_next^T + b_next: the query projection of tokens -> image attention.
 struct TokenAttnBlock {
     float* queries;       // (P, 7, 256) in / out
     float const* pe;      // (P, 7, 256) the prompt tokens (positional encoding of the token side)
-    float const *wq_t, *bq, *wk_t, *bk, *wv_t, *bv, *wo_t, *bo;  // (256, 256) transposed weights, (256) biases
+    float const *wq_t, *bq, *wk_t, *bk, *wv_t, *bv, *wo_t, *bo;  // (256, 256) weights as [K / 4][N][4], (256) biases
     float const *gamma, *beta;
     int with_pe, residual;  // layer 0: q = k = v = queries, output replaces them; later: q = k = queries + pe, residual
     float const *w_next_t, *b_next;  // (256, 128), (128)

@@ -15,8 +15,8 @@
 // next step needs from the other three CTAs -- the attention output, the LayerNorm row sums, the normalised rows --
 // travels through distributed shared memory (st.shared::cluster) followed by a cluster barrier.
 // The 7-row MLP (256 -> 2048 -> 256) stays on the tensor-core GEMM: its 4 MB of weights want to be read once per pass.
-// Weights are stored transposed (K, N) so that neighbouring threads read neighbouring output features of one k: coalesced
-// rows, each value used for the prompt's 7 rows.  fp32 FMA throughout; a prompt's result does not depend on which other
+// Weights are stored transposed and k-blocked, [K / 4][N][4], so that neighbouring threads read neighbouring output features
+// (coalesced 16-byte loads), each value used for the prompt's 7 rows.  fp32 FMA throughout; a prompt's result does not depend on which other
 // prompts share the pass.
 #include "decoder_kernels.cuh"
 
@@ -43,27 +43,33 @@ constexpr int kS128 = 128 / kCl;   // 32: ... of a 128-wide one
 // out_s[r][f] = bias[n0 + f] + sum_k xs[r][k] * Wt[k][n0 + f]   for r < 7, f < NOUT, with all 256 threads: thread
 // (part, f) sums its share of k, the 256 / NOUT partial sums meet in shared memory.
 // xs: shared [7][K]; Wt: global (K, N) row-major; scratch: shared [256 / NOUT][7][NOUT]; out_s: shared [7][NOUT].
-template <int NOUT>
-__device__ __forceinline__ void cta_proj(float const* xs, int K, float const* __restrict__ Wt, int N, int n0,
+template <int NOUT, int K>
+__device__ __forceinline__ void cta_proj(float const* xs, float const* __restrict__ Wt, int N, int n0,
                                          float const* __restrict__ bias, float* scratch, float* out_s) {
     constexpr int kParts = kThreads / NOUT;
+    constexpr int kPer = K / kParts;  // k values per thread: 64 (256 -> 64 wide), 32 (256 -> 32 wide, 128 -> 64 wide)
+    static_assert(kPer % 4 == 0 && kPer <= 64, "k slice per thread");
     int const f = threadIdx.x % NOUT, part = threadIdx.x / NOUT;
-    int const kper = K / kParts, k0 = part * kper;
+    int const k0 = part * kPer;
+    // Wt is stored as [K / 4][N][4]: the four k values of one output feature are one 16-byte load, so a thread's whole
+    // weight slice is 8 or 16 loads, all requested before the first use -- one trip to L2 per projection (with scalar
+    // loads ptxas kept a rolling window of ~20 of the 64 in flight: 15 cycles of scoreboard stall per issued instruction)
+    float4 w[kPer / 4];
+    float4 const* wp = reinterpret_cast<float4 const*>(Wt) + (size_t)(k0 / 4) * N + n0 + f;
+#pragma unroll
+    for (int k = 0; k < kPer / 4; ++k) w[k] = __ldg(wp + (size_t)k * N);
     float acc[kT];
 #pragma unroll
     for (int r = 0; r < kT; ++r) acc[r] = 0.f;
-    float const* w = Wt + (size_t)k0 * N + n0 + f;
-#pragma unroll 4
-    for (int k = 0; k < kper; k += 4) {
-        float const w0 = __ldg(w + (size_t)(k + 0) * N), w1 = __ldg(w + (size_t)(k + 1) * N);
-        float const w2 = __ldg(w + (size_t)(k + 2) * N), w3 = __ldg(w + (size_t)(k + 3) * N);
+#pragma unroll
+    for (int k = 0; k < kPer / 4; ++k) {
 #pragma unroll
         for (int r = 0; r < kT; ++r) {
-            float4 const x = *reinterpret_cast<float4 const*>(xs + r * K + k0 + k);
-            acc[r] = fmaf(x.x, w0, acc[r]);
-            acc[r] = fmaf(x.y, w1, acc[r]);
-            acc[r] = fmaf(x.z, w2, acc[r]);
-            acc[r] = fmaf(x.w, w3, acc[r]);
+            float4 const x = *reinterpret_cast<float4 const*>(xs + r * K + k0 + 4 * k);
+            acc[r] = fmaf(x.x, w[k].x, acc[r]);
+            acc[r] = fmaf(x.y, w[k].y, acc[r]);
+            acc[r] = fmaf(x.z, w[k].z, acc[r]);
+            acc[r] = fmaf(x.w, w[k].w, acc[r]);
         }
     }
 #pragma unroll
@@ -149,9 +155,9 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_at
     }
     __syncthreads();
     // q, k from queries (+ pe), v from queries: this CTA's 64 features = heads 2 * rank, 2 * rank + 1
-    cta_proj<kS256>(sm.xp, kDim, p.wq_t, kDim, n0, p.bq, sm.scratch, sm.q);
-    cta_proj<kS256>(sm.xp, kDim, p.wk_t, kDim, n0, p.bk, sm.scratch, sm.k);
-    cta_proj<kS256>(sm.xs, kDim, p.wv_t, kDim, n0, p.bv, sm.scratch, sm.v);
+    cta_proj<kS256, kDim>(sm.xp, p.wq_t, kDim, n0, p.bq, sm.scratch, sm.q);
+    cta_proj<kS256, kDim>(sm.xp, p.wk_t, kDim, n0, p.bk, sm.scratch, sm.k);
+    cta_proj<kS256, kDim>(sm.xs, p.wv_t, kDim, n0, p.bv, sm.scratch, sm.v);
     // scores of the two local heads: 2 x 7 x 7, head_dim 32, scale 1 / sqrt(32)
     if (n < 2 * kT * kT) {
         int const h = n / (kT * kT), t = (n / kT) % kT, u = n % kT;
@@ -195,7 +201,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_at
     __syncthreads();
     cluster_scatter_slice(cluster, sm.o, sm.full);  // every CTA needs all 256 features as the input of the out projection
     cluster.sync();
-    cta_proj<kS256>(sm.full, kDim, p.wo_t, kDim, n0, p.bo, sm.scratch, sm.o);
+    cta_proj<kS256, kDim>(sm.full, p.wo_t, kDim, n0, p.bo, sm.scratch, sm.o);
     if (p.residual) {
         for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] += sm.xs[(i / kS256) * kDim + n0 + (i % kS256)];
         __syncthreads();
@@ -212,7 +218,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_at
     cluster_scatter_slice(cluster, sm.o, sm.full);
     cluster.sync();
     // query projection of tokens -> image attention: (queries + pe) W^T + b, 256 -> 128; this CTA's 32 features
-    cta_proj<kS128>(sm.full, kDim, p.w_next_t, 128, rank * kS128, p.b_next, sm.scratch, sm.q);
+    cta_proj<kS128, kDim>(sm.full, p.w_next_t, 128, rank * kS128, p.b_next, sm.scratch, sm.q);
     for (int i = n; i < kT * kS128; i += kThreads)
         p.out_next[((size_t)prompt * kT + i / kS128) * 128 + rank * kS128 + (i % kS128)] = sm.q[i];
     cluster.sync();  // no CTA exits while another may still write into its shared memory
@@ -252,7 +258,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
     }
     __syncthreads();
     float* q_g = p.queries + (size_t)prompt * kT * kDim;
-    cta_proj<kS256>(sm.in_full, 128, p.wo_t, kDim, n0, p.bo, sm.scratch, sm.o);
+    cta_proj<kS256, 128>(sm.in_full, p.wo_t, kDim, n0, p.bo, sm.scratch, sm.o);
     for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] += q_g[(i / kS256) * kDim + n0 + (i % kS256)];
     __syncthreads();
     cluster_row_stats(cluster, sm.o, sm.ln_part, sm.stats);
@@ -290,7 +296,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
     }
     cluster.sync();
     for (int j = 0; j < p.count; ++j) {
-        cta_proj<kS128>(p.with_pe[j] ? sm.xp_full : sm.in_full, kDim, p.w_t[j], 128, rank * kS128, p.b[j], sm.scratch, sm.p32);
+        cta_proj<kS128, kDim>(p.with_pe[j] ? sm.xp_full : sm.in_full, p.w_t[j], 128, rank * kS128, p.b[j], sm.scratch, sm.p32);
         for (int i = n; i < kT * kS128; i += kThreads)
             p.out[j][((size_t)prompt * kT + i / kS128) * 128 + rank * kS128 + (i % kS128)] = sm.p32[i];
         __syncthreads();

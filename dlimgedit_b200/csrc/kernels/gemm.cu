@@ -46,6 +46,7 @@ struct EpiParams {
     float const* fuse_a;  // kFuse 1: LayerNorm2d gamma (64); kFuse 2: hypernetwork weights (prompts, 4, 32)
     float const* fuse_b;  // kFuse 1: LayerNorm2d beta (64)
     float* fuse_out;      // kFuse 2: low-resolution mask logits (prompts, 4, 256, 256)
+    void const* const* res_table;  // staged residual: base pointer of every group of res_mod output rows (kFuse 3, layer 0)
 };
 
 __device__ __forceinline__ void add_bias16(float (&v)[16], float const* bias, int col) {
@@ -227,6 +228,10 @@ struct SlabCtx {
 // kFuse (staged 16-bit GELU epilogues of the mask decoder's upscaling, one warp = one 64- / 32-column group of a row):
 //   1  the warp's 64 columns are one LayerNorm2d group (output_upscaling.1 on the (dy, dx) block of the first transposed
 //      convolution): statistics from a first pass over the accumulators, then normalise -> GELU -> store as usual.
+//   3  (with a staged residual, block_n == N == 256) LayerNorm over the whole 256-wide row of  acc + bias + residual:
+//      the pre-norm sums go to the staging area as usual and leave their row sums; the kernel exchanges those between
+//      the four warps of the row and ln_copy_out() normalises on the way to global memory (two-way transformer:
+//      keys <- LN(keys + out_proj(attention))).
 //   2  the warp's 32 columns are the 32 channels of one output pixel (ey, ex) of the second transposed convolution: after
 //      GELU they are dotted with the prompt's four hypernetwork vectors and ONLY the four mask logits are written
 //      (mask_decoder: masks = hyper_in @ upscaled_embedding) -- the upscaled tensor never reaches memory.
@@ -351,7 +356,7 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             }
             uint32_t const dst = cx.stage_base + stage_offset(kCnt, cx.lane, 2 * k);
             uint32_t const dst1 = cx.stage_base + stage_offset(kCnt, cx.lane, 2 * k + 1);
-            if (kRes && ep.residual) {
+            if (kRes && (ep.residual || ep.res_table)) {
                 // the residual piece of this tile is already in the staging area (cp.async, whole row segments); this
                 // lane adds its row's 16 values in fp32 and puts the rounded sums back in the same place
                 uint4 rs[2];
@@ -368,7 +373,7 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
                     }
                 }
             }
-            if (kRes && ep.stats_out) {  // LayerNorm row sums of what this GEMM writes (fp32 values, fixed order)
+            if (kRes && (kFuse == 3 || ep.stats_out)) {  // LayerNorm row sums of what this GEMM writes (fp32 values, fixed order)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     sum += v[i];
@@ -394,6 +399,10 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
 #pragma unroll
             for (int m = 0; m < 4; ++m) o[(int64_t)m * 65536] = dot[m];
         }
+        return;
+    }
+    if (kFuse == 3) {  // the rows are normalised on their way out, once the row sums of all four warps have met
+        __syncwarp();
         return;
     }
     if (kStaged && !kF32) {
@@ -427,6 +436,37 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
         }
         __syncwarp();  // the staging area is private to this warp
     }
+}
+
+// kFuse 3: the warp's 32 x 128-byte piece of pre-norm rows (staging area) -> (x - mean) * rstd * gamma + beta -> global,
+// whole row segments per store instruction.  mean / rstd: of this lane's row; the row a lane stores comes by shuffle.
+__device__ __forceinline__ void ln_copy_out(SlabCtx const& cx, float mean, float rstd, uint32_t gamma_s, uint32_t beta_s) {
+    constexpr int kCnt = 4, kCpr = 2 * kCnt, kRows = 32 / kCpr, kIters = 32 / kRows;  // 8 pieces per row, 4 rows per instruction
+    int const row0 = cx.lane / kCpr, chunk = cx.lane - row0 * kCpr;
+    int const col = cx.col0 + chunk * 8;
+    float g[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g[4 * i]), "=f"(g[4 * i + 1]), "=f"(g[4 * i + 2]), "=f"(g[4 * i + 3]) : "r"(gamma_s + (uint32_t)((col + 4 * i) * 4)));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[4 * i]), "=f"(b[4 * i + 1]), "=f"(b[4 * i + 2]), "=f"(b[4 * i + 3]) : "r"(beta_s + (uint32_t)((col + 4 * i) * 4)));
+    }
+    act_t* p = cx.out_seg + (int64_t)row0 * cx.ldc + chunk * 8;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+        int const rr = row0 + it * kRows;
+        float const mu = __shfl_sync(0xffffffffu, mean, rr), rs = __shfl_sync(0xffffffffu, rstd, rr);
+        uint4 x;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(cx.stage_base + stage_offset(kCnt, rr, chunk)));
+        act2_t* h = reinterpret_cast<act2_t*>(&x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 const f = act22f2(h[j]);
+            h[j] = f22act2((f.x - mu) * rs * g[2 * j] + b[2 * j], (f.y - mu) * rs * g[2 * j + 1] + b[2 * j + 1]);
+        }
+        if (rr < cx.rows_valid) *reinterpret_cast<uint4*>(p) = x;
+        p += (int64_t)kRows * cx.ldc;
+    }
+    __syncwarp();  // the staging area is private to this warp
 }
 
 // Implicit-GEMM 3x3 convolution (stride 1, zero padding 1) over a 16-bit NHWC tensor: the A operand of k-block
@@ -517,6 +557,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (bias_bytes) {  // weights: independent of the previous kernel
         for (int i = threadIdx.x; i < N; i += kNumThreads)
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * (uint32_t)i), "f"(ep.bias ? __ldg(ep.bias + i) : 0.f) : "memory");
+        if (kFuse == 3)  // LayerNorm gamma / beta behind the bias vector
+            for (int i = threadIdx.x; i < 2 * N; i += kNumThreads)
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * (uint32_t)(N + i)), "f"(__ldg((i < N ? ep.fuse_a : ep.fuse_b - N) + i)) : "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -619,13 +662,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // into its staging area with cp.async as whole row segments -- one tile ahead, right after the staging area has
         // been drained -- so neither the residual reads nor the output writes touch partial 128-byte lines.
         auto prefetch_residual = [&](int tile) {
-            if (s_cnt == 0 || !ep.residual) return;  // (the kernel also serves plain GEMMs that only want row sums)
+            if (s_cnt == 0 || (!ep.residual && !ep.res_table)) return;  // (the kernel also serves plain GEMMs that only want row sums)
             int const m0 = (tile / n_tiles) * kBlockM + quarter * 32;
             int const n0 = (tile % n_tiles) * block_n + s_first * 16;
             // res_mod: the residual is a (res_mod, N) table shared by every group of res_mod output rows (a multiple of
             // the tile height, so a tile never straddles two groups) -- the decoder's position terms
             int const r0 = ep.res_mod ? m0 % ep.res_mod : m0;
-            act_t const* seg = reinterpret_cast<act_t const*>(ep.residual) + (int64_t)r0 * ep.ldc + n0;
+            act_t const* seg = (ep.res_table ? reinterpret_cast<act_t const*>(ep.res_table[m0 / ep.res_mod])
+                                             : reinterpret_cast<act_t const*>(ep.residual)) + (int64_t)r0 * ep.ldc + n0;
             int const cpr = 2 * s_cnt, rows_it = 32 / cpr;  // 16-byte pieces per row, rows per instruction
             int const row0 = lane / cpr, chunk = lane - row0 * cpr;
             int const rows_valid = min(32, M - m0);
@@ -709,6 +753,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             if (kFuse == 2) {  // block_n == 128: every warp owns the 32 channels of one output pixel
                 epilogue_slabs<2, kStaged, kAct, kLn, kRes, kTF32 != 0, 2>(cx, ep, out, row_sum, row_sumsq);
+                continue;
+            }
+            if (kFuse == 3) {  // block_n == N == 256: LayerNorm of the whole row, statistics exchanged between its four warps
+                epilogue_slabs<4, kStaged, kAct, kLn, kRes, kTF32 != 0, 3>(cx, ep, out, row_sum, row_sumsq);
+                uint32_t const red = stage_out + (uint32_t)(staging_bytes - bias_bytes - 8192 + (local & 1) * 4096);
+                uint32_t const mine = red + (uint32_t)(((quarter * 4 + slab) * 32 + lane) * 8);
+                asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(mine), "f"(row_sum), "f"(row_sumsq) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+                float sx = 0.f, sq = 0.f;
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) {
+                    float a, b;
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)(((quarter * 4 + w4) * 32 + lane) * 8)));
+                    sx += a;
+                    sq += b;
+                }
+                float const mean = sx * (1.0f / 256.0f);
+                float const rstd = rsqrtf(fmaxf(sq * (1.0f / 256.0f) - mean * mean, 0.f) + ep.ln_eps);
+                ln_copy_out(cx, mean, rstd, bias_s + 4u * (uint32_t)N, bias_s + 8u * (uint32_t)N);
+                if (tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + (int)gridDim.x);
                 continue;
             }
             switch (s_cnt) {  // warp-uniform
@@ -1279,6 +1343,7 @@ EpiParams to_params(Epilogue const& e, int N) {
     p.fuse_a = e.fuse_a;
     p.fuse_b = e.fuse_b;
     p.fuse_out = e.fuse_out;
+    p.res_table = e.res_table;
     return p;
 }
 
@@ -1341,7 +1406,10 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     // Small problems (the decoder's token-side Linears, single-image encoder passes): narrower tiles put more SMs to
     // work and shorten the per-CTA k-loop.  The sum over K of an output element does not depend on the tile width, so
     // results are bit-identical; producers of row sums keep their width (the consumer counts the partial sums).
-    if (epi.fuse) {
+    if (epi.fuse == 3) {
+        DLIMG_ASSERT(!tf32 && !ci && ep.act == ACT_NONE && (ep.residual || ep.res_table) && !ep.ln_stats && !ep.stats_out && !ep.row_map && !ep.out_f32);
+        DLIMG_ASSERT(N == 256 && ep.bias && ep.fuse_a && ep.fuse_b && (!ep.res_table || ep.res_mod > 0));
+    } else if (epi.fuse) {
         DLIMG_ASSERT(!tf32 && !ci && ep.act == ACT_GELU && !ep.residual && !ep.ln_stats && !ep.stats_out && !ep.row_map && !ep.out_f32);
         DLIMG_ASSERT((epi.fuse == 1 && N == 256 && ep.fuse_a && ep.fuse_b) || (epi.fuse == 2 && N == 128 && M % 16384 == 0 && ep.fuse_a && ep.fuse_out));
     } else if (!ep.stats_out) {
@@ -1366,8 +1434,8 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
     // plain 16-bit outputs go through the coalescing (staged) epilogue; residual / scatter / fp32 outputs store directly
     static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch
     static bool const allow_staged_res = !std::getenv("DLIMG_B200_GEMM_DIRECT_RESIDUAL");  // A/B switch
-    bool const res_ok = !ep.residual || (allow_staged_res && ep.act == ACT_NONE && !ep.ln_stats);
-    if (ep.res_mod) DLIMG_ASSERT(ep.residual && ep.res_mod % kBlockM == 0 && M % ep.res_mod == 0);
+    bool const res_ok = !(ep.residual || ep.res_table) || (allow_staged_res && ep.act == ACT_NONE && !ep.ln_stats);
+    if (ep.res_mod) DLIMG_ASSERT((ep.residual || ep.res_table) && ep.res_mod % kBlockM == 0 && M % ep.res_mod == 0);
     static bool const allow_staged_f32 = !std::getenv("DLIMG_B200_GEMM_DIRECT_F32");  // A/B switch
     bool const staged_f32 = allow_staged && allow_staged_f32 && tf32 && ep.out_f32 && !ep.residual && !ep.row_map && !ep.stats_out &&
                             !ep.ln_stats && block_n >= 64 && N <= 2048;
@@ -1379,17 +1447,19 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
         fail("GEMM: the folded LayerNorm needs a plain 16-bit output (staged epilogue) and a bias");
     if (ep.stats_out && (ep.act != ACT_NONE || ep.row_map || ep.out_f32 || block_n < 64))
         fail("GEMM: row statistics are produced by the 16-bit epilogues without activation only");
-    int const bias_bytes = staged ? (int)round_up64((int64_t)N * 4, 1024) : 0;
-    SmemPlan const sp = plan_smem(block_n, staged, ep.stats_out != nullptr, bias_bytes, tf32);
+    int const bias_bytes = staged ? (int)round_up64((int64_t)N * 4 * (epi.fuse == 3 ? 3 : 1), 1024) : 0;  // fuse 3: + gamma, beta
+    SmemPlan const sp = plan_smem(block_n, staged, ep.stats_out != nullptr || epi.fuse == 3, bias_bytes, tf32);
     DLIMG_ASSERT(sp.stages >= 2);
     using Kernel = void (*)(CUtensorMap, CUtensorMap, int, int, int, int, int, int, int, void*, EpiParams, ConvParams);
     Kernel kernel;
     if (tf32) kernel = staged ? gemm_tc_kernel<1, true> : gemm_tc_kernel<1, false>;
     else if (!staged) kernel = gemm_tc_kernel<0, false>;
+    else if (epi.fuse == 3) kernel = gemm_tc_kernel<0, true, ACT_NONE, false, true, 3>;
     else if (ep.residual || ep.stats_out) kernel = gemm_tc_kernel<0, true, ACT_NONE, false, true>;
     else if (ep.ln_stats) kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, true> : gemm_tc_kernel<0, true, ACT_NONE, true>;
     else kernel = ep.act == ACT_GELU ? gemm_tc_kernel<0, true, ACT_GELU, false> : gemm_tc_kernel<0, true, ACT_NONE, false>;
-    if (epi.fuse) {
+    if (epi.fuse == 3) DLIMG_ASSERT(staged && block_n == 256);
+    if (epi.fuse == 1 || epi.fuse == 2) {
         DLIMG_ASSERT(staged);
         kernel = epi.fuse == 1 ? gemm_tc_kernel<0, true, ACT_GELU, false, false, 1> : gemm_tc_kernel<0, true, ACT_GELU, false, false, 2>;
     }

@@ -45,7 +45,11 @@ struct Epilogue {
     //   fuse = 1, N == 256: LayerNorm2d(64, eps 1e-6) over every 64-column group (gamma = fuse_a, beta = fuse_b) before the GELU
     //   fuse = 2, N == 128, M = prompts * 16384: the GELU'd 32-channel groups are dotted with the prompt's hypernetwork
     //             vectors fuse_a (prompts, 4, 32) and only the mask logits fuse_out (prompts, 4, 256, 256) are written
+    //   fuse = 3, N == 256, with a residual: out = LayerNorm(acc + bias + residual) over the whole row (gamma = fuse_a, beta =
+    //             fuse_b, eps = ln_eps).  The residual of output rows [g * res_mod, (g + 1) * res_mod) may come from its own
+    //             base pointer res_table[g] (device array) instead of `residual`
     int fuse = 0;
+    void const* const* res_table = nullptr;
     float const* fuse_a = nullptr;
     float const* fuse_b = nullptr;
     float* fuse_out = nullptr;

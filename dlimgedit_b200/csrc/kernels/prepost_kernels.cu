@@ -509,13 +509,13 @@ __device__ __forceinline__ uint32_t pack_mask4(float const* v) {
 
 // Identity case: the resized extent equals the output extent (long side == 1024), so the second bilinear has weights
 // 1 / 0 and output pixel (y, x) is the thresholded 256 -> 1024 interpolation itself.  A thread owns 8 neighbouring
-// columns (two low-resolution cells) of an 8-row strip.  In the interior the half-pixel interpolation is periodic -- output
-// column 4j + b blends low-resolution columns (j-1, j) with weights (0.375, 0.625), (0.125, 0.875) for b = 0, 1 and (j, j+1)
-// with (0.875, 0.125), (0.625, 0.375) for b = 2, 3, exactly the values lerp_coord() produces -- and likewise for rows, so
-// interior threads use constants: 4 loads per low-resolution row, no coordinate arithmetic (the generic form spent 20
-// instructions per pixel, 74 % issue utilisation: profiles/r02a_summary.md).  Strips that touch the first / last two
-// columns or rows (where the source coordinate is clamped) take the generic path.  The two low-resolution rows an output
-// row blends change every 4 rows; their horizontal interpolation (8 + 8 registers) is carried from row to row.
+// columns (two low-resolution cells) of an 8-row strip.  The half-pixel interpolation is periodic -- output column
+// 4j + b blends low-resolution columns (j-1, j) with weights (0.375, 0.625), (0.125, 0.875) for b = 0, 1 and (j, j+1) with
+// (0.875, 0.125), (0.625, 0.375) for b = 2, 3, exactly the values lerp_coord() produces, and likewise for rows -- so the
+// weights are constants: 16 loads per thread, all issued up front, no coordinate arithmetic.  The borders stay on the same
+// path (a separate border path made every warp that holds column 0 or 1016 run both: half of all warps): the clamped
+// source coordinate of the last two columns / rows is reproduced by clamping the LOAD index (0.875 a + 0.125 a, like the
+// generic form), that of the first two (weights exactly 1 and 0) by switching the two weights of those lanes.
 constexpr int kIdRows = 8;
 __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __restrict__ low_res, int64_t plane_stride,
                                                                  int const* __restrict__ plane_index, int w, int h,
@@ -528,98 +528,61 @@ __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __
     float const* __restrict__ low = low_res + (plane_index ? plane_index[plane] : plane) * plane_stride;
     uint8_t* const plane_out = out_planes ? out_planes[plane] : out_contig + (size_t)plane * w * h;
     uint8_t* dst = plane_out + (size_t)ys * w + x0;
-    bool const aligned = (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && (w & 7) == 0;
-    if (x0 >= 8 && x0 + 16 <= kImageSize && x0 + 8 <= w && ys >= 8 && ys + 16 <= kImageSize && ys + kIdRows <= h && aligned) {
-        // ---- interior: constant weights ----
-        int const j = x0 >> 2;  // low-resolution cell of column x0 (and j + 1 of column x0 + 4)
-        // rows ys .. ys+7 (ys a multiple of 8, i = ys / 4) blend low-resolution rows (i-1, i) for t = 0, 1; (i, i+1) for
-        // t = 2..5; (i+1, i+2) for t = 6, 7.  All 16 loads are issued before the first use: the kernel is otherwise bound
-        // by three dependent trips to L2 / HBM per thread.
-        int const i = ys >> 2;
-        float a[4][4];
+    bool const word_ok = x0 + 8 <= w && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && (w & 7) == 0;
+    int const rows_valid = min(kIdRows, h - ys);
+    int const j = x0 >> 2, i = ys >> 2;  // low-resolution cell of column x0 / row ys
+    float a[4][4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 4; ++r) {
+        float const* row = low + min(max(i - 1 + r, 0), kLowRes - 1) * kLowRes;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) a[r][c] = __ldg(low + (i - 1 + r) * kLowRes + j - 1 + c);
-        auto hrow = [&](float const (&q)[4], float (&o)[8]) {
-            o[0] = 0.375f * q[0] + 0.625f * q[1];
-            o[1] = 0.125f * q[0] + 0.875f * q[1];
-            o[2] = 0.875f * q[1] + 0.125f * q[2];
-            o[3] = 0.625f * q[1] + 0.375f * q[2];
-            o[4] = 0.375f * q[1] + 0.625f * q[2];
-            o[5] = 0.125f * q[1] + 0.875f * q[2];
-            o[6] = 0.875f * q[2] + 0.125f * q[3];
-            o[7] = 0.625f * q[2] + 0.375f * q[3];
-        };
-        float ha[8], hb[8];
-        hrow(a[0], ha);
-        hrow(a[1], hb);
-        auto emit = [&](int t, float l0, float l1) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = l0 * ha[e] + l1 * hb[e];
-            *reinterpret_cast<uint2*>(dst + (size_t)t * w) = make_uint2(pack_mask4(v), pack_mask4(v + 4));
-        };
-        emit(0, 0.375f, 0.625f);
-        emit(1, 0.125f, 0.875f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) ha[e] = hb[e];
-        hrow(a[2], hb);
-        emit(2, 0.875f, 0.125f);
-        emit(3, 0.625f, 0.375f);
-        emit(4, 0.375f, 0.625f);
-        emit(5, 0.125f, 0.875f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) ha[e] = hb[e];
-        hrow(a[3], hb);
-        emit(6, 0.875f, 0.125f);
-        emit(7, 0.625f, 0.375f);
-        return;
+        for (int c = 0; c < 4; ++c) a[r][c] = __ldg(row + min(max(j - 1 + c, 0), kLowRes - 1));
     }
-    // ---- border strips: generic coordinates ----
-    Lerp lx[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) lx[e] = lerp_coord(min(x0 + e, w - 1), 0.25f, kLowRes);
-    auto hrow = [&](int r, float (&o)[8]) {
-        float const* row = low + r * kLowRes;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = lx[e].l0 * __ldg(row + lx[e].i0) + lx[e].l1 * __ldg(row + lx[e].i1);
+    // columns 0, 1 and rows 0, 1: source coordinate clamped to 0 -> weights (1, 0) on (low[0], low[1]) = (0, 1) on the
+    // (clamped low[-1] = low[0], low[0]) pair loaded here
+    bool const left = x0 == 0, top = ys == 0;
+    float const xa0 = left ? 0.f : 0.375f, xb0 = left ? 1.f : 0.625f, xa1 = left ? 0.f : 0.125f, xb1 = left ? 1.f : 0.875f;
+    float const ya0 = top ? 0.f : 0.375f, yb0 = top ? 1.f : 0.625f, ya1 = top ? 0.f : 0.125f, yb1 = top ? 1.f : 0.875f;
+    auto hrow = [&](float const (&q)[4], float (&o)[8]) {
+        o[0] = xa0 * q[0] + xb0 * q[1];
+        o[1] = xa1 * q[0] + xb1 * q[1];
+        o[2] = 0.875f * q[1] + 0.125f * q[2];
+        o[3] = 0.625f * q[1] + 0.375f * q[2];
+        o[4] = 0.375f * q[1] + 0.625f * q[2];
+        o[5] = 0.125f * q[1] + 0.875f * q[2];
+        o[6] = 0.875f * q[2] + 0.125f * q[3];
+        o[7] = 0.625f * q[2] + 0.375f * q[3];
     };
-    int c0 = -1, c1 = -1;
-    float h0[8], h1[8];
-    for (int t = 0; t < kIdRows; ++t) {
-        int const y = ys + t;
-        if (y < h) {
-            Lerp const q = lerp_coord(y, 0.25f, kLowRes);
-            if (q.i0 != c0) {
-                if (q.i0 == c1) {
+    float ha[8], hb[8];
+    auto emit = [&](int t, float l0, float l1) {
+        if (t >= rows_valid) return;
+        float v[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) h0[e] = h1[e];
-                } else {
-                    hrow(q.i0, h0);
-                }
-                c0 = q.i0;
-            }
-            if (q.i1 != c1) {
-                if (q.i1 == c0) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) h1[e] = h0[e];
-                } else {
-                    hrow(q.i1, h1);
-                }
-                c1 = q.i1;
-            }
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = q.l0 * h0[e] + q.l1 * h1[e];
-            uint8_t* d = plane_out + (size_t)y * w + x0;
-            if (x0 + 8 <= w && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
-                *reinterpret_cast<uint2*>(d) = make_uint2(pack_mask4(v), pack_mask4(v + 4));
-            } else {
-                for (int e = 0; e < 8 && x0 + e < w; ++e) d[e] = v[e] > 0.f ? 255 : 0;
-            }
+        for (int e = 0; e < 8; ++e) v[e] = l0 * ha[e] + l1 * hb[e];
+        uint8_t* d = dst + (size_t)t * w;
+        if (word_ok) {
+            *reinterpret_cast<uint2*>(d) = make_uint2(pack_mask4(v), pack_mask4(v + 4));
+        } else {
+            for (int e = 0; e < 8 && x0 + e < w; ++e) d[e] = v[e] > 0.f ? 255 : 0;
         }
-    }
+    };
+    // rows ys .. ys+7 blend low-resolution rows (i-1, i) for t = 0, 1; (i, i+1) for t = 2..5; (i+1, i+2) for t = 6, 7
+    hrow(a[0], ha);
+    hrow(a[1], hb);
+    emit(0, ya0, yb0);
+    emit(1, ya1, yb1);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ha[e] = hb[e];
+    hrow(a[2], hb);
+    emit(2, 0.875f, 0.125f);
+    emit(3, 0.625f, 0.375f);
+    emit(4, 0.375f, 0.625f);
+    emit(5, 0.125f, 0.875f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ha[e] = hb[e];
+    hrow(a[3], hb);
+    emit(6, 0.875f, 0.125f);
+    emit(7, 0.625f, 0.375f);
 }
 
 // General case.  A block produces g.rows (32 .. 1, by shared-memory need) complete output rows of one mask; every intermediate is computed once per

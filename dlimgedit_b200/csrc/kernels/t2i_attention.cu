@@ -289,6 +289,74 @@ __global__ void __launch_bounds__(kWarps * 32, 2) t2i_mma_kernel(float const* __
 }
 #endif
 
+#if !defined(DLIMG_B200_ACT_BF16)
+// Image -> tokens attention on tensor cores: a warp owns 16 consecutive image tokens of one prompt and walks the 8 heads.
+//   S (16 image tokens x 8 tokens) = Q_h (16 x 16 dims: A fragments straight from the image stream in global memory)
+//                                    * K_h^T (16 dims x 8: B fragments of the prompt's token keys, shared memory)
+//   softmax over the 7 tokens of a row = over the four lanes of a quad (the padding column is masked),
+//   O (16 x 16 dims) = P (16 x 8, zero-extended to k = 16: the accumulator fragment of S IS the A fragment) * V_h
+//                      (B fragments prepared once per block: two TOKENS of one dim per register).
+// ~30 instructions per (16 image tokens, head) and lane instead of ~350 per (token, head) and thread on CUDA cores.
+__global__ void __launch_bounds__(256) i2t_mma_kernel(act_t const* __restrict__ Q, act_t const* const* __restrict__ Qptrs,
+                                                      int64_t q_prompt_stride, int q_pitch, int q_off,
+                                                      float const* __restrict__ kt, float const* __restrict__ vt,
+                                                      act_t* __restrict__ out) {
+    __shared__ uint32_t kb[kHeads][2][32];     // B fragments of K^T per head: [k-half][lane]
+    __shared__ uint32_t vb[kHeads][2][32];     // B fragments of V per head: [dim tile][lane] (k = tokens 0..7; 8..15 are zero)
+    int const p = blockIdx.y;
+    int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    float const kScale = 0.25f * 1.4426950408889634f;  // 1 / sqrt(16) * log2 e, carried by K
+    for (int i = tid; i < kHeads * 2 * 32; i += 256) {
+        int const h = i >> 6, half = (i >> 5) & 1, l = i & 31, gg = l >> 2, tt = l & 3;
+        // K^T fragment (k = dim, n = token gg): dims 2tt, 2tt+1 (+8 for the second half) of token gg (token 7 = padding)
+        float2 kv = make_float2(0.f, 0.f);
+        if (gg < kTokens) kv = *reinterpret_cast<float2 const*>(kt + ((size_t)p * kTokens + gg) * 128 + h * 16 + half * 8 + 2 * tt);
+        kb[h][half][l] = pack_h2(kv.x * kScale, kv.y * kScale);
+        // V fragment (k = token, n = dim gg of tile `half`): tokens 2tt, 2tt+1
+        int const d = h * 16 + half * 8 + gg;
+        float const v0 = 2 * tt < kTokens ? vt[((size_t)p * kTokens + 2 * tt) * 128 + d] : 0.f;
+        float const v1 = 2 * tt + 1 < kTokens ? vt[((size_t)p * kTokens + 2 * tt + 1) * 128 + d] : 0.f;
+        vb[h][half][l] = pack_h2(v0, v1);
+    }
+    __syncthreads();
+    int const tok0 = (blockIdx.x * 8 + warp) * 16;  // 8 warps x 16 image tokens per block
+    act_t const* qbase = (Qptrs ? Qptrs[p] : Q + (size_t)p * q_prompt_stride) + q_off;
+    act_t const* r0 = qbase + (size_t)(tok0 + g) * q_pitch + 2 * t;
+    act_t const* r1 = r0 + (size_t)8 * q_pitch;
+    act_t* o0 = out + ((size_t)p * kImgTokens + tok0 + g) * 128 + 2 * t;
+    act_t* o1 = o0 + (size_t)8 * 128;
+    bool const pad_col = t == 3;  // this lane's second column is token 7: the padding column
+#pragma unroll
+    for (int h = 0; h < kHeads; ++h) {
+        uint32_t const a0 = __ldg(reinterpret_cast<uint32_t const*>(r0 + h * 16)), a1 = __ldg(reinterpret_cast<uint32_t const*>(r1 + h * 16));
+        uint32_t const a2 = __ldg(reinterpret_cast<uint32_t const*>(r0 + h * 16 + 8)), a3 = __ldg(reinterpret_cast<uint32_t const*>(r1 + h * 16 + 8));
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816_f16(s, a0, a1, a2, a3, kb[h][0][lane], kb[h][1][lane]);
+        if (pad_col) s[1] = s[3] = -INFINITY;
+        float m0 = fmaxf(s[0], s[1]), m1 = fmaxf(s[2], s[3]);
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float const p0 = ex2f(s[0] - m0), p1 = ex2f(s[1] - m0), p2 = ex2f(s[2] - m1), p3 = ex2f(s[3] - m1);
+        float l0 = p0 + p1, l1 = p2 + p3;
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        float const i0 = 1.0f / l0, i1 = 1.0f / l1;
+        uint32_t const pa0 = pack_h2(p0 * i0, p1 * i0), pa1 = pack_h2(p2 * i1, p3 * i1);  // rows g / g + 8, k = tokens 2t, 2t + 1
+        float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816_f16(oa, pa0, pa1, 0u, 0u, vb[h][0][lane], 0u);  // dims 0-7 of the head
+        mma16816_f16(ob, pa0, pa1, 0u, 0u, vb[h][1][lane], 0u);  // dims 8-15
+        *reinterpret_cast<uint32_t*>(o0 + h * 16) = pack_h2(oa[0], oa[1]);
+        *reinterpret_cast<uint32_t*>(o1 + h * 16) = pack_h2(oa[2], oa[3]);
+        *reinterpret_cast<uint32_t*>(o0 + h * 16 + 8) = pack_h2(ob[0], ob[1]);
+        *reinterpret_cast<uint32_t*>(o1 + h * 16 + 8) = pack_h2(ob[2], ob[3]);
+    }
+}
+#endif
+
 __global__ void __launch_bounds__(128) t2i_combine_kernel(float const* __restrict__ part, float* __restrict__ out) {
     int const p = blockIdx.x, t = blockIdx.y, d = threadIdx.x, h = d >> 4;
     float const* src = part + ((size_t)p * kT2iSplits * kTokens + t) * kPartStride;
@@ -327,6 +395,22 @@ void token_to_image_attention(cudaStream_t s, float const* q, act_t const* base,
     ProfScope prof(s, CAT_DEC_ATTN);
     t2i_combine_kernel<<<dim3(P, kTokens), 128, 0, s>>>(scratch, out);
     KERNEL_CHECK();
+}
+
+void image_to_token_attention_mma(cudaStream_t s, act_t const* Q, act_t const* const* Qptrs, int64_t q_prompt_stride, int q_pitch,
+                                  int q_off, float const* kt, float const* vt, int P, act_t* out) {
+#if defined(DLIMG_B200_ACT_BF16)
+    image_to_token_attention(s, Q, Qptrs, q_prompt_stride, q_pitch, q_off, kt, vt, P, out);
+#else
+    static bool const cuda_core = std::getenv("DLIMG_B200_I2T_SIMT") != nullptr;  // cross-check: the CUDA-core form
+    if (cuda_core) {
+        image_to_token_attention(s, Q, Qptrs, q_prompt_stride, q_pitch, q_off, kt, vt, P, out);
+        return;
+    }
+    ProfScope prof(s, CAT_DEC_ATTN, 4.0 * P * kTokens * kImgTokens * 128, (double)P * kImgTokens * 128 * 4);
+    i2t_mma_kernel<<<dim3(kImgTokens / 128, P), 256, 0, s>>>(Q, Qptrs, q_prompt_stride, q_pitch, q_off, kt, vt, out);
+    KERNEL_CHECK();
+#endif
 }
 
 }  // namespace dec

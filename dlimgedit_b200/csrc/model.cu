@@ -152,9 +152,9 @@ Norm load_norm(WeightFile const& wf, std::string const& p, int c) {
 
 Linear32T load_linear32t(WeightFile const& wf, std::string const& p, int n, int k) {
     auto const& w = wf.get(p + ".weight", {n, k}).data;
-    std::vector<float> t((size_t)n * k);
+    std::vector<float> t((size_t)n * k);  // [k / 4][n][4]: see decoder_tokens.cu cta_proj
     for (int i = 0; i < n; ++i)
-        for (int j = 0; j < k; ++j) t[(size_t)j * n + i] = w[(size_t)i * k + j];
+        for (int j = 0; j < k; ++j) t[((size_t)(j / 4) * n + i) * 4 + (j % 4)] = w[(size_t)i * k + j];
     Linear32T l;
     l.n = n;
     l.k = k;
@@ -689,10 +689,27 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P) const {
             dec::token_post_mlp(s, m, P);
         }
         // (4) image attends to the tokens: keys <- LN(keys + out_proj(attn)); Q is column block 2 of [K | V | Q]
-        dec::image_to_token_attention(s, ws.kvq.get(), first ? prm.kvq0 : nullptr, kvq_stride, 384, 256, ws.t128a.get(), ws.t128b.get(),
-                                      P, ws.ao.get());
-        gemm16(s, ws.ao.get(), IR, l.i2t_out, ws.big.get(), gemm::ACT_NONE, nullptr);
-        dec::layernorm256_img(s, ws.big.get(), ws.keys.get(), first ? prm.keys0 : nullptr, P, l.n4.g.get(), l.n4.b.get(), ws.keys.get());
+        dec::image_to_token_attention_mma(s, ws.kvq.get(), first ? prm.kvq0 : nullptr, kvq_stride, 384, 256, ws.t128a.get(),
+                                          ws.t128b.get(), P, ws.ao.get());
+        {   // out projection + residual + LayerNorm in one GEMM (Epilogue::fuse = 3).  Layer 0 reads its residual, the image's
+            // own prompt-independent keys, through the per-prompt table and writes ws.keys; layer 1 updates ws.keys in place
+            // (a tile reads its residual rows into shared memory before it writes the same rows).
+            gemm::Epilogue e;
+            e.bias = l.i2t_out.b.get();
+            e.ldc = 256;
+            e.fuse = 3;
+            e.fuse_a = l.n4.g.get();
+            e.fuse_b = l.n4.b.get();
+            e.ln_eps = 1e-5f;
+            if (first) {
+                e.res_table = reinterpret_cast<void const* const*>(prm.keys0);
+                e.res_mod = dec::kImgTokens;
+            } else {
+                e.residual = ws.keys.get();
+            }
+            gemm::launch(s, false, gemm::Operand{ws.ao.get(), IR, 128, 128}, gemm::Operand{l.i2t_out.w.get(), 256, 128, 128}, ws.keys.get(), e,
+                         num_sms_);
+        }
     }
     // final token -> image attention (its query projection came out of the last token_post_mlp)
     gemm16(s, ws.keys.get(), IR, dec_.kv_final, ws.kvq.get(), gemm::ACT_NONE, dec_.pos_kv_final.get(), nullptr, false, 0, nullptr,

@@ -104,7 +104,7 @@ struct EncoderW {
     Norm neck_ln2;
 };
 
-struct Linear32T {  // fp32 weight TRANSPOSED to (K, N) + bias -- the fused token-side kernels (decoder_tokens.cu)
+struct Linear32T {  // fp32 weight transposed and k-blocked, [K / 4][N][4], + bias -- the fused token-side kernels (decoder_tokens.cu)
     DeviceBuffer<float> wt;
     DeviceBuffer<float> b;
     int n = 0, k = 0;

@@ -84,8 +84,10 @@ struct dlimg_Api {
     /* reference dlimgedit.cpp:77-79 (BiRefNet).  Out of scope for this engine: always dlimg_error. */
     dlimg_Result (*segment_objects)(dlimg_ImageView const*, uint8_t* out_mask, dlimg_Environment);
 
-    /* reference dlimgedit.cpp:81-90 (stb image I/O).  load_image: binary PPM/PGM only; save_image:
-     * PNG (stored deflate) for mask / rgb / rgba.  Off the hot path. */
+    /* reference dlimgedit.cpp:81-90 (stb image I/O).  load_image: PNG (8-bit grey / RGB / RGBA, non-interlaced),
+     * baseline JPEG (8-bit, Huffman; stb_image's IDCT / chroma upsampling / colour conversion restated) and binary
+     * PGM / PPM; pixels come from new[] (destroy_image).  save_image: PNG (stored deflate) for mask / rgb / rgba.
+     * Off the hot path. */
     dlimg_Result (*load_image)(char const*, int* out_extent, int* out_channels, uint8_t** out_pixels);
     dlimg_Result (*save_image)(dlimg_ImageView const*, char const*);
     uint8_t* (*create_image)(int w, int h, int channels);
@@ -129,19 +131,24 @@ struct dlimg_b200_Ext {
 
     /* Work submitted through the *_batch calls below goes to `cuda_stream` (a cudaStream_t; NULL =
      * the environment's own stream).  Batch calls are asynchronous with respect to the host unless
-     * stated otherwise; use `synchronize` or your own events on that stream. */
+     * stated otherwise; use `synchronize` or your own events on that stream.  Switching streams needs no
+     * synchronisation by the caller: everything already queued on the old stream is ordered in front of
+     * whatever is submitted to the new one (event dependency), because workspaces and embeddings are shared. */
     dlimg_Result (*set_stream)(dlimg_Environment, void* cuda_stream);
     dlimg_Result (*synchronize)(dlimg_Environment); /* the work stream and the library's two copy streams */
     dlimg_Result (*get_stats)(dlimg_Environment, dlimg_b200_Stats*);
 
-    /* Encode `count` images.  views[i].pixels is a HOST pointer when pixels_on_device == 0 (copied
-     * through pinned staging inside the call) or a DEVICE pointer otherwise.  All images of one call
-     * must share width, height, channels; stride may differ.  out[i] receives a new segmentation
-     * handle (destroy with dlimg_Api.destroy_segmentation). */
+    /* Encode `count` images.  views[i].pixels is a HOST pointer when pixels_on_device == 0 or a DEVICE
+     * pointer otherwise.  Host pixels are copied straight from the caller's memory on the library's upload
+     * stream (one copy per run of packed images that are contiguous in memory; truly asynchronous only from
+     * page-locked memory) and are free again when the call returns; the encoder itself keeps running.  All
+     * images of one call must share width, height, channels; stride may differ.  out[i] receives a new
+     * segmentation handle (destroy with dlimg_Api.destroy_segmentation). */
     dlimg_Result (*process_batch)(dlimg_Environment, dlimg_ImageView const* views, int count,
                                   int pixels_on_device, dlimg_Segmentation* out);
 
-    /* Answer `count` prompts; prompt i refers to segs[i] (handles may repeat).  multi == 0: one mask
+    /* Answer `count` prompts; prompt i refers to segs[i] (handles may repeat, and may belong to different
+     * images of any extent: up to $DLIMG_B200_MAX_PROMPTS prompts share one decoder pass).  multi == 0: one mask
      * per prompt (best of tokens 1..3 by predicted IoU, as the single-mask decoder graph does);
      * multi == 1: three masks per prompt (tokens 1..3).  masks_out[i] points at n*W_i*H_i bytes
      * (n = multi ? 3 : 1) on the device (masks_on_device == 1) or host (0: complete when the call returns;
