@@ -210,7 +210,8 @@ dlimg_Result dbg_gemm(void* stream, int tf32, int simt, void const* a, void cons
         CUDA_CHECK(cudaGetDevice(&dev));
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-        if (simt) gemm::launch_simt(static_cast<cudaStream_t>(stream), tf32 != 0, A, B, out, e);
+        if (simt >= 2) e.ksplit = simt;  // split-K on the tensor-core kernel: out holds `simt` partial results
+        if (simt == 1) gemm::launch_simt(static_cast<cudaStream_t>(stream), tf32 != 0, A, B, out, e);
         else gemm::launch(static_cast<cudaStream_t>(stream), tf32 != 0, A, B, out, e, prop.multiProcessorCount);
     });
 }

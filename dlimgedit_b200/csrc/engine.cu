@@ -1,5 +1,6 @@
 // engine.cu -- see engine.hpp.
 #include "engine.hpp"
+#include "kernels/mask_select.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -488,7 +489,7 @@ void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, boo
 // One decoder pass over P prompts, which may belong to different images: uploads the parameter block (coordinates,
 // labels, per-prompt image tables) in one copy and launches the pass -- a CUDA graph per P, since every address in it is
 // fixed (workspace, weights, parameter block) and only the block's contents change.
-void EnvironmentImpl::decode_chunk(SegmentationImpl* const* segs, dlimg_b200_Prompt const* prompts, int P, bool eager) {
+void EnvironmentImpl::decode_chunk(SegmentationImpl* const* segs, dlimg_b200_Prompt const* prompts, int P, bool eager, int mask_mode) {
     cudaStream_t const s = stream();
     SamModel& m = model();
     DecoderWorkspace& ws = decoder_ws(P);
@@ -511,10 +512,11 @@ void EnvironmentImpl::decode_chunk(SegmentationImpl* const* segs, dlimg_b200_Pro
     CUDA_CHECK(cudaMemcpyAsync(ws.param_block.get(), staging, bytes, cudaMemcpyHostToDevice, s));
     counters_.h2d_bytes += bytes;
     if (eager || !use_graphs_ || profiler_.enabled()) {
-        m.decode(s, ws, P);
+        m.decode(s, ws, P, mask_mode);
     } else {
-        auto it = decode_graphs_.find(P);
-        if (it == decode_graphs_.end()) it = decode_graphs_.emplace(P, capture(s, [&] { m.decode(s, ws, P); })).first;
+        int const key = P * 4 + mask_mode;
+        auto it = decode_graphs_.find(key);
+        if (it == decode_graphs_.end()) it = decode_graphs_.emplace(key, capture(s, [&] { m.decode(s, ws, P, mask_mode); })).first;
         CUDA_CHECK(cudaGraphLaunch(it->second.exec, s));
         count_launch(it->second.kernels);
     }
@@ -540,7 +542,7 @@ void EnvironmentImpl::compute_masks_batch(SegmentationImpl* const* segs, dlimg_b
     int const group_cap = on_device ? max_prompts_ : std::min(max_prompts_, kHostGroup);
     for (int i = 0; i < count; i += group_cap) {
         int const P = std::min(group_cap, count - i);
-        decode_chunk(segs + i, prompts + i, P, false);
+        decode_chunk(segs + i, prompts + i, P, false, multi ? MASKS_MULTI : MASKS_BEST);
         DecoderWorkspace& ws = *dec_ws_;
         int const planes = P * n;
         float* iou_dst = (on_device && ious_out) ? ious_out + (size_t)i * n : ws.iou_sel.get();
@@ -627,7 +629,7 @@ void EnvironmentImpl::low_res_logits(SegmentationImpl& seg, dlimg_b200_Prompt co
     Scope scope(*this);
     cudaStream_t const s = stream();
     SegmentationImpl* segs[1] = {&seg};
-    decode_chunk(segs, &prompt, 1, true);
+    decode_chunk(segs, &prompt, 1, true, MASKS_ALL);
     DecoderWorkspace& ws = *dec_ws_;
     CUDA_CHECK(cudaMemcpyAsync(logits_host, ws.low.get(), sizeof(float) * 4 * 65536, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(iou_host, ws.iou.get(), sizeof(float) * 4, cudaMemcpyDeviceToHost, s));

@@ -123,7 +123,7 @@ class EnvironmentImpl {
     struct ChunkOut { float* emb_nchw; act_t* keys0; act_t* kvq0; };
     void encode_chunk(enc::ImageDesc const* host_descs, int batch, prepost::LongestSide const& size, int channels, ChunkOut const& out,
                       Tap* tap);
-    void decode_chunk(SegmentationImpl* const* segs, dlimg_b200_Prompt const* prompts, int P, bool eager);
+    void decode_chunk(SegmentationImpl* const* segs, dlimg_b200_Prompt const* prompts, int P, bool eager, int mask_mode);
     void prepare_input(dlimg_ImageView const& view, uint8_t const* dev_pixels, int dev_stride, prepost::LongestSide const& size,
                        int slot, enc::ImageDesc& desc);
     void release_graphs();

@@ -1,5 +1,6 @@
 // decoder_kernels.cu -- see decoder_kernels.cuh.
 #include "decoder_kernels.cuh"
+#include "mask_select.cuh"
 #include "gelu.cuh"
 
 #include "../profiler.hpp"
@@ -404,42 +405,6 @@ __global__ void __launch_bounds__(256) mask_dot_kernel(float const* __restrict__
     for (int m = 0; m < 4; ++m) low[((size_t)p * 4 + m) * 65536 + pix] = acc[m];
 }
 
-// The five 3-layer token MLPs at the end of the decoder (IoU head on the iou token, one hypernetwork per mask token):
-// one CTA per (prompt, head) runs all three layers with the activations in shared memory, a warp per output feature
-// with coalesced weight rows.  Replaces 15 launches of 14-23 us each (tools/gpu_dec_launches.sh).
-__global__ void __launch_bounds__(256) token_mlp3_kernel(float const* __restrict__ tokens, TokenMlp3 heads,
-                                                         float* __restrict__ hyper, float* __restrict__ iou) {
-    __shared__ __align__(16) float xa[kDim], xb[kDim];
-    int const p = blockIdx.x, m = blockIdx.y;  // m = 0: IoU head (token 0), m = 1..4: hypernetwork of mask token m
-    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    xa[threadIdx.x] = tokens[((size_t)p * kTokens + m) * kDim + threadIdx.x];
-    __syncthreads();
-    auto layer = [&](float const* __restrict__ W, float const* __restrict__ b, int n_out, float const* x, float* y, bool relu,
-                     int64_t y_stride_dummy) {
-        (void)y_stride_dummy;
-        float4 const x0 = reinterpret_cast<float4 const*>(x)[lane * 2], x1 = reinterpret_cast<float4 const*>(x)[lane * 2 + 1];
-        for (int n = warp; n < n_out; n += 8) {
-            float4 const* w4 = reinterpret_cast<float4 const*>(W + (size_t)n * kDim) + lane * 2;
-            float4 const w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-            float a = x0.x * w0.x;
-            a = fmaf(x0.y, w0.y, a); a = fmaf(x0.z, w0.z, a); a = fmaf(x0.w, w0.w, a);
-            a = fmaf(x1.x, w1.x, a); a = fmaf(x1.y, w1.y, a); a = fmaf(x1.z, w1.z, a); a = fmaf(x1.w, w1.w, a);
-            a = warp_sum(a);
-            if (lane == 0) {
-                a += b[n];
-                y[n] = relu ? fmaxf(a, 0.f) : a;
-            }
-        }
-    };
-    layer(heads.w[m][0], heads.b[m][0], kDim, xa, xb, true, 0);
-    __syncthreads();
-    layer(heads.w[m][1], heads.b[m][1], kDim, xb, xa, true, 0);
-    __syncthreads();
-    int const n_out = m == 0 ? 4 : 32;
-    float* dst = m == 0 ? iou + (size_t)p * 4 : hyper + ((size_t)p * 4 + (m - 1)) * 32;
-    layer(heads.w[m][2], heads.b[m][2], n_out, xa, dst, false, 0);
-}
-
 __global__ void f32_to_act_kernel(float const* __restrict__ in, int64_t n, act_t* __restrict__ out) {
     int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = f2act(in[i]);
@@ -456,13 +421,7 @@ __global__ void select_masks_kernel(float const* __restrict__ iou, int P, int mu
             if (iou_out) iou_out[p * 3 + i] = s[1 + i];
         }
     } else {
-        // score = iou + (num_points - 2.5) * [1000, 0, 0, 0] with num_points == 2; first maximum wins
-        float best = s[0] + (2.0f - 2.5f) * 1000.0f;
-        int bi = 0;
-        for (int i = 1; i < 4; ++i) {
-            float const v = s[i] + (2.0f - 2.5f) * 0.0f;
-            if (v > best) { best = v; bi = i; }
-        }
+        int const bi = best_mask_index(s);  // mask_select.cuh
         plane_index[p] = p * 4 + bi;
         if (iou_out) iou_out[p] = s[bi];
     }
@@ -541,12 +500,6 @@ void mask_dot(cudaStream_t s, float const* hyper, act_t const* up2, int P, float
     ProfScope prof(s, CAT_DEC_MISC, 2.0 * P * 65536 * 128, (double)P * (16384.0 * 128 * 2 + 4 * 65536 * 4));
     dim3 grid(65536 / 256, P);
     mask_dot_kernel<<<grid, 256, 0, s>>>(hyper, up2, low);
-    KERNEL_CHECK();
-}
-
-void token_mlp3(cudaStream_t s, float const* tokens, int P, TokenMlp3 const& heads, float* hyper, float* iou) {
-    ProfScope prof(s, CAT_DEC_LINEAR);
-    token_mlp3_kernel<<<dim3((unsigned)P, 5), 256, 0, s>>>(tokens, heads, hyper, iou);
     KERNEL_CHECK();
 }
 

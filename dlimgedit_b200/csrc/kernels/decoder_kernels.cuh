@@ -82,7 +82,7 @@ void mask_dot(cudaStream_t s, float const* hyper, act_t const* up2, int P, float
 
 // IoU head (slot 0, on token 0, 256 -> 256 -> 256 -> 4) and the four hypernetwork MLPs (slots 1..4, on mask tokens 1..4,
 // 256 -> 256 -> 256 -> 32), ReLU between layers: tokens (P, 7, 256) -> iou (P, 4), hyper (P, 4, 32).
-struct TokenMlp3 {
+struct TokenMlp3 {  // weights as [K / 4][N][4] (Linear32T); decoder_tokens.cu
     float const* w[5][3];
     float const* b[5][3];
 };
@@ -112,11 +112,14 @@ struct TokenPostT2i {
 };
 void token_post_t2i(cudaStream_t s, TokenPostT2i const& p, int P);
 
-// queries <- LayerNorm(queries + mlp_out); then `count` (<= 3) projections 256 -> 128 of the new queries (+ pe if
+// queries <- LayerNorm(queries + mlp_bias + sum of the mlp_out partials); then `count` (<= 3) projections 256 -> 128 of the new queries (+ pe if
 // with_pe[j]) -> out[j] (P, 7, 128).
 struct TokenPostMlp {
     float* queries;
-    float const* mlp_out;
+    float const* mlp_out;        // mlp_parts split-K partial sums of the MLP's second Linear, mlp_part_stride floats apart ...
+    int mlp_parts;
+    int64_t mlp_part_stride;
+    float const* mlp_bias;       // ... and its bias (256)
     float const* pe;
     float const *gamma, *beta;
     int count;

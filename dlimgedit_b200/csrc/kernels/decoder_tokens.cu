@@ -269,7 +269,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
     cluster.sync();
 }
 
-// After the token MLP: queries <- LayerNorm(queries + mlp_out), then up to three 256 -> 128 projections of the new
+// After the token MLP: queries <- LayerNorm(queries + mlp_out) (mlp_out = bias + the split-K partial sums), then up to three 256 -> 128 projections of the new
 // queries (with or without the positional encoding added): keys / values of image -> tokens attention, and after the
 // last layer the queries of the final tokens -> image attention.
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_post_mlp_kernel(TokenPostMlp p) {
@@ -283,7 +283,9 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
     float const* pe_g = p.pe + (size_t)prompt * kT * kDim;
     for (int i = n; i < kT * kS256; i += kThreads) {
         int const g = (i / kS256) * kDim + n0 + (i % kS256);
-        sm.o[i] = q_g[g] + m_g[g];
+        float v = q_g[g] + __ldg(p.mlp_bias + n0 + (i % kS256));
+        for (int sp = 0; sp < p.mlp_parts; ++sp) v += m_g[(size_t)sp * p.mlp_part_stride + g];  // split-K partials, fixed order
+        sm.o[i] = v;
     }
     __syncthreads();
     cluster_row_stats(cluster, sm.o, sm.ln_part, sm.stats);
@@ -302,6 +304,53 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
         __syncthreads();
     }
     cluster.sync();
+}
+
+// IoU head and the four hypernetwork MLPs (256 -> 256 -> 256 -> 4 | 32, ReLU between): a cluster owns one MLP for SEVEN
+// PROMPTS (the 7 rows cta_proj works on are prompts here, token m of each), so the MLP's 0.5 MB of weights are pulled once
+// per seven prompts, a quarter per CTA, one trip to L2 per layer.  (The earlier kernel -- a CTA per (prompt, MLP), a warp
+// per output feature -- walked 32 dependent weight-row loads per layer: 34 us per 64-prompt pass.)
+struct Mlp3Smem {
+    float x[kT * kDim], y[kT * kDim];
+    float o[kT * kS256];
+    float scratch[kThreads * kT];
+};
+
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_mlp3_kernel(float const* __restrict__ tokens, TokenMlp3 heads,
+                                                                                       int P, float* __restrict__ hyper,
+                                                                                       float* __restrict__ iou) {
+    extern __shared__ __align__(16) uint8_t tok_smem[];
+    Mlp3Smem& sm = *reinterpret_cast<Mlp3Smem*>(tok_smem);
+    cg::cluster_group cluster = cg::this_cluster();
+    int const rank = (int)cluster.block_rank();
+    int const groups = (P + kT - 1) / kT;
+    int const cl = blockIdx.x / kCl, m = cl / groups, p0 = (cl % groups) * kT;  // m = 0: IoU head (token 0), 1..4: mask token m
+    int const n = threadIdx.x, n0 = rank * kS256;
+    for (int i = n; i < kT * kDim; i += kThreads) {
+        int const r = i / kDim;
+        sm.x[i] = p0 + r < P ? tokens[((size_t)(p0 + r) * kTokens + m) * kDim + (i % kDim)] : 0.f;
+    }
+    __syncthreads();
+    cta_proj<kS256, kDim>(sm.x, heads.w[m][0], kDim, n0, heads.b[m][0], sm.scratch, sm.o);
+    for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] = fmaxf(sm.o[i], 0.f);
+    __syncthreads();
+    cluster_scatter_slice(cluster, sm.o, sm.y);
+    cluster.sync();
+    cta_proj<kS256, kDim>(sm.y, heads.w[m][1], kDim, n0, heads.b[m][1], sm.scratch, sm.o);
+    for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] = fmaxf(sm.o[i], 0.f);
+    __syncthreads();
+    cluster_scatter_slice(cluster, sm.o, sm.x);  // every CTA is past its reads of x: they precede the barrier above
+    cluster.sync();
+    if (rank != 0) return;  // the narrow last layer is one CTA's work (nothing is written to the others any more)
+    if (m == 0) {
+        cta_proj<4, kDim>(sm.x, heads.w[0][2], 4, 0, heads.b[0][2], sm.scratch, sm.o);
+        for (int i = n; i < kT * 4; i += kThreads)
+            if (p0 + i / 4 < P) iou[(size_t)(p0 + i / 4) * 4 + (i % 4)] = sm.o[i];
+    } else {
+        cta_proj<32, kDim>(sm.x, heads.w[m][2], 32, 0, heads.b[m][2], sm.scratch, sm.o);
+        for (int i = n; i < kT * 32; i += kThreads)
+            if (p0 + i / 32 < P) hyper[((size_t)(p0 + i / 32) * 4 + (m - 1)) * 32 + (i % 32)] = sm.o[i];
+    }
 }
 
 template <typename K, typename P> void launch_cluster(K kernel, size_t smem, cudaStream_t s, int prompts, P const& params) {
@@ -335,6 +384,15 @@ void token_post_mlp(cudaStream_t s, TokenPostMlp const& p, int P) {
     DLIMG_ASSERT(p.count >= 1 && p.count <= 3);
     ProfScope prof(s, CAT_DEC_LINEAR, 2.0 * P * kT * kDim * 128 * p.count);
     launch_cluster(token_post_mlp_kernel, sizeof(PostSmem), s, P, p);
+    KERNEL_CHECK();
+}
+
+void token_mlp3(cudaStream_t s, float const* tokens, int P, TokenMlp3 const& heads, float* hyper, float* iou) {
+    ProfScope prof(s, CAT_DEC_LINEAR, 2.0 * P * (4.0 * (2 * kDim * kDim + 32 * kDim) + 2 * kDim * kDim + 4 * kDim));
+    static std::once_flag once;
+    std::call_once(once, [] { CUDA_CHECK(cudaFuncSetAttribute(token_mlp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Mlp3Smem))); });
+    int const groups = (P + kT - 1) / kT;
+    token_mlp3_kernel<<<5 * groups * kCl, kThreads, sizeof(Mlp3Smem), s>>>(tokens, heads, P, hyper, iou);
     KERNEL_CHECK();
 }
 

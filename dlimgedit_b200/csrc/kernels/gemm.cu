@@ -1,6 +1,7 @@
 // gemm.cu -- tcgen05 / TMEM / TMA GEMM for sm_100a (see gemm.cuh for the contract).
 #include "gemm.cuh"
 #include "gelu.cuh"
+#include "mask_select.cuh"
 #include "tcgen05.cuh"
 
 #include "../profiler.hpp"
@@ -44,10 +45,18 @@ struct EpiParams {
     int ldc;
     int res_mod;   // staged residual: residual row = output row % res_mod (0 = output row)
     float const* fuse_a;  // kFuse 1: LayerNorm2d gamma (64); kFuse 2: hypernetwork weights (prompts, 4, 32)
-    float const* fuse_b;  // kFuse 1: LayerNorm2d beta (64)
+    float const* fuse_b;  // kFuse 1: LayerNorm2d beta (64); kFuse 2, MASKS_BEST: predicted IoUs (prompts, 4)
+    int fuse_mode;        // kFuse 2: MaskMode
+    int ksplit;           // split-K: M holds ksplit * (rows of A rounded up to 128)
     float* fuse_out;      // kFuse 2: low-resolution mask logits (prompts, 4, 256, 256)
     void const* const* res_table;  // staged residual: base pointer of every group of res_mod output rows (kFuse 3, layer 0)
 };
+
+// d += a * b on both lanes of a packed fp32 pair (one FFMA2 on sm_100)
+__device__ __forceinline__ void ffma2(float2& d, float2 a, float2 b) {
+    uint64_t& dd = reinterpret_cast<uint64_t&>(d);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(reinterpret_cast<uint64_t const&>(a)), "l"(reinterpret_cast<uint64_t const&>(b)));
+}
 
 __device__ __forceinline__ void add_bias16(float (&v)[16], float const* bias, int col) {
     float4 const* b4 = reinterpret_cast<float4 const*>(bias + col);
@@ -239,7 +248,20 @@ template <int kCnt, bool kStaged, int kAct, bool kLn, bool kRes = false, bool kF
 __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams const& ep, void* out, float& sum, float& sumsq) {
     uint32_t r[2][16];
     float ln_mean = 0.f, ln_rstd = 1.f;
-    float dot[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 dot2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    float const* fuse2_hy = nullptr;  // kFuse 2: hypernetwork vectors of this row's prompt, first requested mask
+    int fuse2_first = 0, fuse2_count = 4;
+    if (kFuse == 2) {
+        int64_t const prompt = (cx.row0 + cx.lane) >> 14;  // 16384 blocked pixels per prompt: uniform over the warp
+        if (ep.fuse_mode == MASKS_MULTI) {
+            fuse2_first = 1;
+            fuse2_count = 3;
+        } else if (ep.fuse_mode == MASKS_BEST) {
+            fuse2_first = best_mask_index(ep.fuse_b + prompt * 4);
+            fuse2_count = 1;
+        }
+        fuse2_hy = ep.fuse_a + prompt * 128 + fuse2_first * 32;
+    }
     if (kFuse == 1) {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -337,19 +359,17 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
                 uint4 x[2];
                 activate_pack16(v, kAct, x);  // the same 16-bit values the unfused path stored
                 act2_t const* h = reinterpret_cast<act2_t const*>(x);
-                int64_t const prompt = (cx.row0 + cx.lane) >> 14;  // 16384 blocked pixels per prompt
-                float const* hy = ep.fuse_a + prompt * 128 + (c & 31);
+                float const* hy = fuse2_hy + (c & 31);
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
+                    if (m >= fuse2_count) break;
                     float4 const* h4 = reinterpret_cast<float4 const*>(hy + m * 32);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float4 const w = __ldg(h4 + i);
-                        float2 const a = act22f2(h[2 * i]), b = act22f2(h[2 * i + 1]);
-                        dot[m] = fmaf(a.x, w.x, dot[m]);
-                        dot[m] = fmaf(a.y, w.y, dot[m]);
-                        dot[m] = fmaf(b.x, w.z, dot[m]);
-                        dot[m] = fmaf(b.y, w.w, dot[m]);
+                        // two fp32 FMAs per instruction: even / odd channels accumulate separately
+                        ffma2(dot2[m], act22f2(h[2 * i]), make_float2(w.x, w.y));
+                        ffma2(dot2[m], act22f2(h[2 * i + 1]), make_float2(w.z, w.w));
                     }
                 }
                 continue;
@@ -395,9 +415,10 @@ __device__ __forceinline__ void epilogue_slabs(SlabCtx const& cx, EpiParams cons
             int64_t const prompt = row >> 14;
             int const rr = (int)(row & 16383), pix = rr >> 2, dy = (rr >> 1) & 1, dx = rr & 1, g = (cx.col0 >> 5) & 3;
             int const Y = 4 * (pix >> 6) + 2 * dy + (g >> 1), X = 4 * (pix & 63) + 2 * dx + (g & 1);
-            float* o = ep.fuse_out + (prompt * 4) * 65536 + Y * 256 + X;
+            float* o = ep.fuse_out + (prompt * 4 + fuse2_first) * 65536 + Y * 256 + X;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) o[(int64_t)m * 65536] = dot[m];
+            for (int m = 0; m < 4; ++m)
+                if (m < fuse2_count) o[(int64_t)m * 65536] = dot2[m].x + dot2[m].y;
         }
         return;
     }
@@ -530,9 +551,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
     int const elems_per_kb = kTF32 ? 32 : 64;
     int const elem_bytes = kTF32 ? 4 : 2;
-    int const num_kb = (K + elems_per_kb - 1) / elems_per_kb;
+    // split-K (EpiParams::ksplit > 1): M counts the rows of all partial outputs -- m-tile mt is rows (mt % m_tiles_a) * 128 of
+    // A and k-blocks [(mt / m_tiles_a) * num_kb, +num_kb); only the producer knows, the rest of the kernel sees a tall problem
+    int const num_kb = (K + elems_per_kb - 1) / elems_per_kb / ep.ksplit;
     int const n_tiles = N / block_n;
     int const m_tiles = (M + kBlockM - 1) / kBlockM;
+    int const m_tiles_a = m_tiles / ep.ksplit;
     int const total_tiles = m_tiles * n_tiles;
 
     if (warp == 0 && lane == 0) {
@@ -575,7 +599,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             uint32_t phase = 0;
             uint32_t const tx_bytes = stage_bytes;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int const m0 = (tile / n_tiles) * kBlockM;
+                int const mt_all = tile / n_tiles, kb0 = (mt_all / m_tiles_a) * num_kb;
+                int const m0 = (mt_all % m_tiles_a) * kBlockM;
                 int const n0 = (tile % n_tiles) * block_n;
                 int img = 0, y0 = 0;
                 if (conv.w > 0) {
@@ -590,9 +615,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         int const tap = kb / conv.cblocks, cb = kb - tap * conv.cblocks, ky = tap / 3, kx = tap - ky * 3;
                         tma_load_4d(a_stage(stage), &tma_a, full_bar(stage), cb * 64, kx - 1, y0 + ky - 1, img);
                     } else {
-                        tma_load_2d(a_stage(stage), &tma_a, full_bar(stage), kb * elems_per_kb, m0);
+                        tma_load_2d(a_stage(stage), &tma_a, full_bar(stage), (kb0 + kb) * elems_per_kb, m0);
                     }
-                    tma_load_2d(b_stage(stage), &tma_b, full_bar(stage), kb * elems_per_kb, n0);
+                    tma_load_2d(b_stage(stage), &tma_b, full_bar(stage), (kb0 + kb) * elems_per_kb, n0);
                     if (++stage == num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -607,7 +632,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             uint32_t const idesc = make_idesc(fmt, kBlockM, block_n);
             uint64_t const adesc0 = make_smem_desc(a_stage(0)), bdesc0 = make_smem_desc(b_stage(0));
             uint64_t const stage_step = (uint64_t)(stage_bytes >> 4);  // descriptor address field: 16-byte units
-            int const tail_bytes = (K - (num_kb - 1) * elems_per_kb) * elem_bytes;
+            int const tail_bytes = ep.ksplit > 1 ? elems_per_kb * elem_bytes : (K - (num_kb - 1) * elems_per_kb) * elem_bytes;
             int const tail_instr = (tail_bytes + 31) >> 5;
             int stage = 0;
             uint32_t phase = 0;
@@ -1342,6 +1367,8 @@ EpiParams to_params(Epilogue const& e, int N) {
     p.res_mod = e.res_mod;
     p.fuse_a = e.fuse_a;
     p.fuse_b = e.fuse_b;
+    p.fuse_mode = e.fuse_mode;
+    p.ksplit = e.ksplit > 1 ? e.ksplit : 1;
     p.fuse_out = e.fuse_out;
     p.res_table = e.res_table;
     return p;
@@ -1397,8 +1424,12 @@ void launch_conv3x3(cudaStream_t stream, void const* in, int batch, int H, int W
 namespace {
 void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const& b, void* out, Epilogue const& epi,
                  int num_sms, ConvInput const* ci) {
-    int const M = (int)a.rows, N = (int)b.rows, K = (int)a.cols;
+    int const ks = epi.ksplit > 1 ? epi.ksplit : 1;
+    int const M = ks > 1 ? (int)(split_rows(a.rows) * ks) : (int)a.rows, N = (int)b.rows, K = (int)a.cols;
     DLIMG_ASSERT(a.cols == b.cols);
+    if (ks > 1)  // whole k-blocks per split, plain fp32 outputs: the tall problem the epilogue sees has no other meaning
+        DLIMG_ASSERT(!ci && epi.out_f32 && !epi.fuse && !epi.residual && !epi.res_table && !epi.ln_stats && !epi.stats_out && !epi.row_map &&
+                     !epi.bias && K % (ks * (tf32 ? 32 : 64)) == 0);
     DLIMG_ASSERT(M > 0 && N > 0 && K > 0);
     int block_n = pick_block_n(N);
     if (block_n == 0) fail("GEMM: N must be a multiple of 16, got " + std::to_string(N));
@@ -1411,7 +1442,7 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
         DLIMG_ASSERT(N == 256 && ep.bias && ep.fuse_a && ep.fuse_b && (!ep.res_table || ep.res_mod > 0));
     } else if (epi.fuse) {
         DLIMG_ASSERT(!tf32 && !ci && ep.act == ACT_GELU && !ep.residual && !ep.ln_stats && !ep.stats_out && !ep.row_map && !ep.out_f32);
-        DLIMG_ASSERT((epi.fuse == 1 && N == 256 && ep.fuse_a && ep.fuse_b) || (epi.fuse == 2 && N == 128 && M % 16384 == 0 && ep.fuse_a && ep.fuse_out));
+        DLIMG_ASSERT((epi.fuse == 1 && N == 256 && ep.fuse_a && ep.fuse_b) || (epi.fuse == 2 && N == 128 && M % 16384 == 0 && ep.fuse_a && ep.fuse_out && (epi.fuse_mode != MASKS_BEST || ep.fuse_b)));
     } else if (!ep.stats_out) {
         int const tiles_m = ceil_div(M, kBlockM);
         while (block_n >= 128 && block_n % 32 == 0 && N % (block_n / 2) == 0 && 2 * tiles_m * (N / block_n) <= num_sms) block_n /= 2;
@@ -1427,7 +1458,7 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
                         : make_map(a, tf32, kBlockM);
     CUtensorMap mb = make_map(b, tf32, block_n);
     int const tiles = ceil_div(M, kBlockM) * (N / block_n);
-    ProfScope prof(stream, tf32 ? CAT_GEMM_TF32 : CAT_GEMM_BF16, 2.0 * M * N * K,
+    ProfScope prof(stream, tf32 ? CAT_GEMM_TF32 : CAT_GEMM_BF16, 2.0 * M * N * K / ks,
                    (double)(tf32 ? 4 : 2) * ((double)M * (ci ? ci->C : K) + (double)N * K) +
                        (double)(ep.out_f32 ? 4 : 2) * M * N * (ep.residual ? 2.0 : 1.0));
     int const grid = tiles < num_sms ? tiles : num_sms;
@@ -1518,7 +1549,7 @@ void launch_mlp_fused(cudaStream_t stream, void const* x, int64_t rows, int C, v
 void launch_simt(cudaStream_t stream, bool f32_operands, Operand const& a, Operand const& b, void* out,
                  Epilogue const& epi) {
     int const M = (int)a.rows, N = (int)b.rows, K = (int)a.cols;
-    DLIMG_ASSERT(a.cols == b.cols);
+    DLIMG_ASSERT(a.cols == b.cols && epi.ksplit <= 1);
     EpiParams ep = to_params(epi, N);
     ProfScope prof(stream, CAT_OTHER, 2.0 * M * N * K);
     dim3 grid(ceil_div(N, 32), ceil_div(M, 32)), block(32, 8);

@@ -44,11 +44,18 @@ struct Epilogue {
     // Fused tails of the mask decoder's upscaling (16-bit GELU epilogue; see epilogue_slabs in gemm.cu):
     //   fuse = 1, N == 256: LayerNorm2d(64, eps 1e-6) over every 64-column group (gamma = fuse_a, beta = fuse_b) before the GELU
     //   fuse = 2, N == 128, M = prompts * 16384: the GELU'd 32-channel groups are dotted with the prompt's hypernetwork
-    //             vectors fuse_a (prompts, 4, 32) and only the mask logits fuse_out (prompts, 4, 256, 256) are written
+    //             vectors fuse_a (prompts, 4, 32) and only the mask logits fuse_out (prompts, 4, 256, 256) are written.
+    //             fuse_mode (mask_select.cuh MaskMode): all four planes | planes 1..3 | only the plane the predicted IoUs
+    //             fuse_b (prompts, 4) select -- the other planes of fuse_out are then left untouched
     //   fuse = 3, N == 256, with a residual: out = LayerNorm(acc + bias + residual) over the whole row (gamma = fuse_a, beta =
     //             fuse_b, eps = ln_eps).  The residual of output rows [g * res_mod, (g + 1) * res_mod) may come from its own
     //             base pointer res_table[g] (device array) instead of `residual`
     int fuse = 0;
+    int fuse_mode = 0;
+    // Split-K for skinny problems (the decoder's 7-row-per-prompt 2048 -> 256 Linear: 16 tiles with a 64-step k-loop each):
+    // split s of ksplit sums k in [s K / ksplit, (s + 1) K / ksplit) into rows [s * Mpad, s * Mpad + M) of `out`, Mpad = M
+    // rounded up to 128 (split_rows()); the CONSUMER adds the ksplit partial sums in a fixed order.  fp32 outputs only.
+    int ksplit = 1;
     void const* const* res_table = nullptr;
     float const* fuse_a = nullptr;
     float const* fuse_b = nullptr;
@@ -92,6 +99,7 @@ void launch_conv3x3(cudaStream_t stream, void const* in, int batch, int H, int W
 // memory.  x (rows, C) 16-bit (also the residual; out may alias x), w1 (4C, C) with the LayerNorm folded in (gamma-scaled,
 // row-centred), b1 (4C) folded bias, ln_stats (rows) partial (sum, sum of squares) of x's rows, w2 (C, 4C), b2 (C);
 // stats_out (optional, rows): (sum, sum of squares) of the output rows.
+inline int64_t split_rows(int64_t M) { return (M + 127) / 128 * 128; }  // rows per split-K partial
 bool mlp_fused_supported(int C);
 void launch_mlp_fused(cudaStream_t stream, void const* x, int64_t rows, int C, void const* w1, float const* b1,
                       float2 const* ln_stats, float ln_eps, void const* w2, float const* b2, void* out, float2* stats_out,

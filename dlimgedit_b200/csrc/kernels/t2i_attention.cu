@@ -124,25 +124,11 @@ __global__ void __launch_bounds__(kWarps * 32) t2i_flash_kernel(float const* __r
 
 // ---- tensor-core form ----------------------------------------------------------------------------------------------
 // The same partials from warp-level MMAs (mma.sync m16n8k16, fp16 operands, fp32 accumulators) -- the CUDA-core kernel
-// above spends ~100 instructions per key and lane (profiles/r02a_summary.md: 80-92 us per 64-prompt launch for 134 MB).
-// A warp owns 64 consecutive keys of its block's split and walks them in 4 steps of 16 keys, 4 heads at a time:
-//   S^T (16 keys x 8 tokens) = K_h (16 x 16 dims, A operand straight from global memory: a fragment register is two
-//         neighbouring dims of one key row) * Q_h^T (16 dims x 8 tokens: 7 + one zero row; B operand, resident registers)
-//   pass 1 takes the maximum of every (head, token) column over the warp's 64 keys; pass 2 recomputes S^T (the K rows
-//         come back from L1), p = 2^(s - max), and accumulates  O (8 tokens x 16 dims) += P (tokens x keys) * V_h:
-//         P is S^T transposed -- one movmatrix per 8 x 8 block of the accumulator fragment -- and V's B fragment
-//         (two KEYS of one dim per register) is the transposed natural row fragment, again by movmatrix.
-// With the final maximum known before pass 2 nothing is ever rescaled.  Scores are kept in log2 units (q carries
-// 0.25 * log2 e).  Output: the same per-(prompt, split) partials as above, merged by token_post_t2i.
+// above spends ~100 instructions per key and lane (80-92 us per 64-prompt launch for 134 MB).
 __device__ __forceinline__ void mma16816_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
-    uint32_t y;
-    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
-    return y;
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 const v = __floats2half2_rn(a, b);
@@ -155,135 +141,125 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 #if !defined(DLIMG_B200_ACT_BF16)
-constexpr int kKeysPerWarp = kImgTokens / (kT2iSplits * kWarps);  // 64
-static_assert(kKeysPerWarp == 64, "the tensor-core kernel walks 4 steps of 16 keys per warp");
+constexpr int kTileKeys = 32;                    // keys per pipeline stage
+constexpr int kT2iStages = 3;
+constexpr int kTileBytes = kTileKeys * 512;      // [K tile: 32 rows x 256 B | V tile: 32 rows x 256 B]
+constexpr int kSplitKeys = kImgTokens / kT2iSplits;
+constexpr int kT2iSmem = kT2iStages * kTileBytes;  // 48 KB: four blocks per SM, so 64 prompts x 8 splits are one wave
+static_assert(kWarps == kHeads, "one warp per head");
+static_assert(kSplitKeys % kTileKeys == 0, "whole tiles per split");
 
-__global__ void __launch_bounds__(kWarps * 32, 2) t2i_mma_kernel(float const* __restrict__ q, act_t const* __restrict__ base,
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+
+// Second form of the tensor-core kernel (the first read its fragments straight from global memory with 4-byte loads and
+// was bound by L1 sector throughput, 76 %): a block owns one (prompt, split) = 512 keys and streams them through a
+// 3-stage cp.async ring of 32-key tiles -- whole 256-byte K and V rows, 16-byte chunks XOR-swizzled by the row -- and
+// each of the 8 warps owns one HEAD, so no cross-warp merge is needed.  Per tile and warp:
+//   S (tokens x 32 keys)  = Q_h (A: 7 tokens + zero rows, resident) * K_h^T (B: ldmatrix of the K rows)  -- 4 mma
+//   online softmax per tile (maximum over the quad, one rescale of the accumulators per tile), scores stay in registers
+//   O (tokens x 16 dims) += P (A: the accumulator fragment of S, packed to fp16) * V_h (B: ldmatrix.trans) -- 4 mma
+// No transposes, no second pass over K.  Scores are kept in log2 units (q carries 0.25 * log2 e).
+// Output: per-(prompt, split) partials, merged by token_post_t2i.
+__global__ void __launch_bounds__(kWarps * 32, 4) t2i_mma_kernel(float const* __restrict__ q, act_t const* __restrict__ base,
                                                               act_t const* const* __restrict__ ptrs, int64_t prompt_stride,
                                                               int pitch, int v_off, float* __restrict__ part) {
-    __shared__ float sm_acc[kWarps][kTokens][128];
-    __shared__ float sm_m[kWarps][kTokens][kHeads];
-    __shared__ float sm_s[kWarps][kTokens][kHeads];
+    extern __shared__ __align__(128) uint8_t t2i_smem[];
     int const p = blockIdx.x, split = blockIdx.y;
-    int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int const tid = threadIdx.x, h = tid >> 5, lane = tid & 31;
     int const g = lane >> 2, t = lane & 3;
-    act_t const* const Kb = (ptrs ? ptrs[p] : base + (size_t)p * prompt_stride) + (size_t)((split * kWarps + warp) * kKeysPerWarp) * pitch;
+    act_t const* const Kb = (ptrs ? ptrs[p] : base + (size_t)p * prompt_stride) + (size_t)(split * kSplitKeys) * pitch;
     act_t const* const Vb = Kb + v_off;
-    float const kQScale = 0.25f * 1.4426950408889634f;  // 1 / sqrt(16) * log2 e
-    float const* qrow = q + ((size_t)p * kTokens + g) * 128;  // token g (g == 7: the zero padding row)
+    uint32_t const smem_s = (uint32_t)__cvta_generic_to_shared(t2i_smem);
 
+    auto issue = [&](int tile) {  // 32 keys x (16 + 16) chunks of 16 bytes: 4 per thread
+        uint32_t const st = smem_s + (tile % kT2iStages) * kTileBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int const c = i * 256 + tid, kv = c >> 9, row = (c >> 4) & 31, ch = c & 15;
+            act_t const* src = (kv ? Vb : Kb) + (size_t)(tile * kTileKeys + row) * pitch + ch * 8;
+            uint32_t const dst = st + kv * (kTileKeys * 256) + row * 256 + ((ch ^ (row & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+    };
+    issue(0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    issue(1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    float const kQScale = 0.25f * 1.4426950408889634f;  // 1 / sqrt(16) * log2 e
+    uint32_t qa0 = 0u, qa2 = 0u;  // A fragment of Q_h: row g = token g (row 7 and rows 8-15 are zero)
+    if (g < kTokens) {
+        float const* qrow = q + ((size_t)p * kTokens + g) * 128 + h * 16 + 2 * t;
+        float2 const x0 = *reinterpret_cast<float2 const*>(qrow), x1 = *reinterpret_cast<float2 const*>(qrow + 8);
+        qa0 = pack_h2(x0.x * kQScale, x0.y * kQScale);
+        qa2 = pack_h2(x1.x * kQScale, x1.y * kQScale);
+    }
+    // ldmatrix.x4 lane addressing: matrices (keys 0-7 | 8-15) x (dims 0-7 | 8-15) of this head
+    int const lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lchunk = 2 * h + (lane >> 4);
+    float m = -INFINITY, l = 0.f;
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    constexpr int kTiles = kSplitKeys / kTileKeys;
 #pragma unroll 1
-    for (int hg = 0; hg < 2; ++hg) {  // four heads at a time (register budget)
-        uint32_t qb[4][2];
+    for (int tile = 0; tile < kTiles; ++tile) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();  // tile is visible; every warp is done with tile - 1, whose stage the next copy reuses
+        if (tile + 2 < kTiles) issue(tile + 2);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        uint32_t const st = smem_s + (tile % kT2iStages) * kTileBytes;
+        float sc[kTileKeys / 16][2][4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            int const c = (hg * 4 + h) * 16 + 2 * t;
-            float2 const x0 = g < kTokens ? *reinterpret_cast<float2 const*>(qrow + c) : make_float2(0.f, 0.f);
-            float2 const x1 = g < kTokens ? *reinterpret_cast<float2 const*>(qrow + c + 8) : make_float2(0.f, 0.f);
-            qb[h][0] = pack_h2(x0.x * kQScale, x0.y * kQScale);
-            qb[h][1] = pack_h2(x1.x * kQScale, x1.y * kQScale);
+        for (int step = 0; step < kTileKeys / 16; ++step) {
+            int const row = step * 16 + lrow;
+            uint32_t k0, k1, k2, k3;  // (keys 0-7, dims 0-7), (keys 8-15, dims 0-7), (keys 0-7, dims 8-15), (keys 8-15, dims 8-15)
+            ldsm_x4(st + row * 256 + ((lchunk ^ (row & 7)) << 4), k0, k1, k2, k3);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) sc[step][j][0] = sc[step][j][1] = sc[step][j][2] = sc[step][j][3] = 0.f;
+            mma16816_f16(sc[step][0], qa0, 0u, qa2, 0u, k0, k2);  // keys 0-7 of the step
+            mma16816_f16(sc[step][1], qa0, 0u, qa2, 0u, k1, k3);  // keys 8-15
         }
-        auto scores = [&](int step, int h, float (&s)[4]) {  // S^T of 16 keys for head hg * 4 + h
-            act_t const* r0 = Kb + (size_t)(step * 16 + g) * pitch + (hg * 4 + h) * 16 + 2 * t;
-            act_t const* r1 = r0 + (size_t)8 * pitch;
-            uint32_t const a0 = __ldg(reinterpret_cast<uint32_t const*>(r0)), a1 = __ldg(reinterpret_cast<uint32_t const*>(r1));
-            uint32_t const a2 = __ldg(reinterpret_cast<uint32_t const*>(r0 + 8)), a3 = __ldg(reinterpret_cast<uint32_t const*>(r1 + 8));
-            s[0] = s[1] = s[2] = s[3] = 0.f;
-            mma16816_f16(s, a0, a1, a2, a3, qb[h][0], qb[h][1]);
-        };
-        // pass 1: column maxima (tokens 2t, 2t + 1) over the warp's keys
-        float mx[4][2];
+        float mt = -INFINITY;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) mx[h][0] = mx[h][1] = -INFINITY;
+        for (int step = 0; step < kTileKeys / 16; ++step)
 #pragma unroll
-        for (int step = 0; step < 4; ++step)
+            for (int j = 0; j < 2; ++j) mt = fmaxf(mt, fmaxf(sc[step][j][0], sc[step][j][1]));
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 1));
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 2));
+        float const m_new = fmaxf(m, mt);
+        float const alpha = ex2f(m - m_new);  // first tile: 2^(-inf) = 0
+        m = m_new;
+        l *= alpha;
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                float s[4];
-                scores(step, h, s);
-                mx[h][0] = fmaxf(mx[h][0], fmaxf(s[0], s[2]));
-                mx[h][1] = fmaxf(mx[h][1], fmaxf(s[1], s[3]));
-            }
-#pragma unroll
-        for (int h = 0; h < 4; ++h)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                float m = mx[h][e];
-                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                mx[h][e] = m;
-            }
-        // pass 2: probabilities, sums, O += P V
-        float o[4][2][4], l[4][2];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            l[h][0] = l[h][1] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) o[h][j][0] = o[h][j][1] = o[h][j][2] = o[h][j][3] = 0.f;
+        for (int j = 0; j < 2; ++j) {
+            o[j][0] *= alpha;
+            o[j][1] *= alpha;
         }
 #pragma unroll
-        for (int step = 0; step < 4; ++step)
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                float s[4];
-                scores(step, h, s);
-                float const p0 = ex2f(s[0] - mx[h][0]), p1 = ex2f(s[1] - mx[h][1]);
-                float const p2 = ex2f(s[2] - mx[h][0]), p3 = ex2f(s[3] - mx[h][1]);
-                l[h][0] += p0 + p2;
-                l[h][1] += p1 + p3;
-                uint32_t const pa0 = movm_t(pack_h2(p0, p1));  // P[token g][keys 2t, 2t + 1]
-                uint32_t const pa2 = movm_t(pack_h2(p2, p3));  // P[token g][keys 8 + 2t, 9 + 2t]
-                act_t const* r0 = Vb + (size_t)(step * 16 + g) * pitch + (hg * 4 + h) * 16 + 2 * t;
-                act_t const* r1 = r0 + (size_t)8 * pitch;
-                uint32_t const v00 = movm_t(__ldg(reinterpret_cast<uint32_t const*>(r0)));      // keys 0-7,  dims 0-7
-                uint32_t const v10 = movm_t(__ldg(reinterpret_cast<uint32_t const*>(r1)));      // keys 8-15, dims 0-7
-                uint32_t const v01 = movm_t(__ldg(reinterpret_cast<uint32_t const*>(r0 + 8)));  // keys 0-7,  dims 8-15
-                uint32_t const v11 = movm_t(__ldg(reinterpret_cast<uint32_t const*>(r1 + 8)));  // keys 8-15, dims 8-15
-                mma16816_f16(o[h][0], pa0, 0u, pa2, 0u, v00, v10);
-                mma16816_f16(o[h][1], pa0, 0u, pa2, 0u, v01, v11);
-            }
-        // partials of this warp: accumulators (token g, dims 8 j + 2t, + 1), maxima / sums (tokens 2t, 2t + 1)
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                float s = l[h][e];
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s += __shfl_xor_sync(0xffffffffu, s, 8);
-                s += __shfl_xor_sync(0xffffffffu, s, 16);
-                int const tok = 2 * t + e;
-                if (g == 0 && tok < kTokens) {
-                    sm_m[warp][tok][hg * 4 + h] = mx[h][e] * 0.6931471805599453f;  // back to natural-log units
-                    sm_s[warp][tok][hg * 4 + h] = s;
-                }
-            }
-            if (g < kTokens) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    *reinterpret_cast<float2*>(&sm_acc[warp][g][(hg * 4 + h) * 16 + 8 * j + 2 * t]) = make_float2(o[h][j][0], o[h][j][1]);
-            }
+        for (int step = 0; step < kTileKeys / 16; ++step) {
+            float const p0 = ex2f(sc[step][0][0] - m), p1 = ex2f(sc[step][0][1] - m);
+            float const p2 = ex2f(sc[step][1][0] - m), p3 = ex2f(sc[step][1][1] - m);
+            l += (p0 + p1) + (p2 + p3);
+            uint32_t const pa0 = pack_h2(p0, p1), pa2 = pack_h2(p2, p3);  // P[token g][keys 2t, 2t + 1 | 8 + 2t, 9 + 2t]
+            int const row = step * 16 + lrow;
+            uint32_t v00, v10, v01, v11;  // B fragments of V: (keys 0-7 | 8-15) x (dims 0-7 | 8-15), two KEYS per register
+            ldsm_x4_t(st + kTileKeys * 256 + row * 256 + ((lchunk ^ (row & 7)) << 4), v00, v10, v01, v11);
+            mma16816_f16(o[0], pa0, 0u, pa2, 0u, v00, v10);
+            mma16816_f16(o[1], pa0, 0u, pa2, 0u, v01, v11);
         }
     }
-    __syncthreads();
-    // merge the 8 warps -> one partial per (prompt, split)
-    float* dst = part + ((size_t)p * kT2iSplits + split) * kTokens * kPartStride;
-    for (int idx = tid; idx < kTokens * 128; idx += kWarps * 32) {
-        int const tk = idx >> 7, d = idx & 127, h = d >> 4;
-        float M = sm_m[0][tk][h];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    if (g < kTokens) {
+        float* dst = part + (((size_t)p * kT2iSplits + split) * kTokens + g) * kPartStride;
 #pragma unroll
-        for (int w = 1; w < kWarps; ++w) M = fmaxf(M, sm_m[w][tk][h]);
-        float A = 0.f, S = 0.f;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            float const e = __expf(sm_m[w][tk][h] - M);
-            A = fmaf(sm_acc[w][tk][d], e, A);
-            S = fmaf(sm_s[w][tk][h], e, S);
-        }
-        dst[tk * kPartStride + d] = A;
-        if ((d & 15) == 0) {
-            dst[tk * kPartStride + 128 + h] = M;
-            dst[tk * kPartStride + 136 + h] = S;
+        for (int j = 0; j < 2; ++j) *reinterpret_cast<float2*>(dst + h * 16 + 8 * j + 2 * t) = make_float2(o[j][0], o[j][1]);
+        if (t == 0) {
+            dst[128 + h] = m * 0.6931471805599453f;  // back to natural-log units
+            dst[136 + h] = l;
         }
     }
 }
@@ -291,7 +267,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) t2i_mma_kernel(float const* __
 
 #if !defined(DLIMG_B200_ACT_BF16)
 // Image -> tokens attention on tensor cores: a warp owns 16 consecutive image tokens of one prompt and walks the 8 heads.
-//   S (16 image tokens x 8 tokens) = Q_h (16 x 16 dims: A fragments straight from the image stream in global memory)
+//   S (16 image tokens x 8 tokens) = Q_h (16 x 16 dims: A fragments by ldmatrix from the warp's staged tile)
 //                                    * K_h^T (16 dims x 8: B fragments of the prompt's token keys, shared memory)
 //   softmax over the 7 tokens of a row = over the four lanes of a quad (the padding column is masked),
 //   O (16 x 16 dims) = P (16 x 8, zero-extended to k = 16: the accumulator fragment of S IS the A fragment) * V_h
@@ -303,6 +279,7 @@ __global__ void __launch_bounds__(256) i2t_mma_kernel(act_t const* __restrict__ 
                                                       act_t* __restrict__ out) {
     __shared__ uint32_t kb[kHeads][2][32];     // B fragments of K^T per head: [k-half][lane]
     __shared__ uint32_t vb[kHeads][2][32];     // B fragments of V per head: [dim tile][lane] (k = tokens 0..7; 8..15 are zero)
+    __shared__ __align__(16) uint8_t tile[8][16 * 256];  // per warp: the Q tile, then the output tile
     int const p = blockIdx.y;
     int const tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     float const kScale = 0.25f * 1.4426950408889634f;  // 1 / sqrt(16) * log2 e, carried by K
@@ -321,15 +298,35 @@ __global__ void __launch_bounds__(256) i2t_mma_kernel(act_t const* __restrict__ 
     __syncthreads();
     int const tok0 = (blockIdx.x * 8 + warp) * 16;  // 8 warps x 16 image tokens per block
     act_t const* qbase = (Qptrs ? Qptrs[p] : Q + (size_t)p * q_prompt_stride) + q_off;
-    act_t const* r0 = qbase + (size_t)(tok0 + g) * q_pitch + 2 * t;
-    act_t const* r1 = r0 + (size_t)8 * q_pitch;
-    act_t* o0 = out + ((size_t)p * kImgTokens + tok0 + g) * 128 + 2 * t;
-    act_t* o1 = o0 + (size_t)8 * 128;
+    // The warp's Q tile (16 tokens x 128 dims, 4 KB) goes through shared memory: 16-byte loads of whole rows (fully used
+    // sectors; fragment-shaped 4-byte loads kept L1 at 81 % of its sector rate), stored with the 16-byte chunk index
+    // XOR-swizzled by the row so that ldmatrix and the fragment-shaped output stores are conflict free.  The outputs of a
+    // head overwrite the chunks its Q fragments came from; the tile leaves again as whole rows.
+    uint8_t* const tw = tile[warp];
+    {
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int const c = i * 32 + lane, row = c >> 4, ch = c & 15;
+            v[i] = __ldg(reinterpret_cast<uint4 const*>(qbase + (size_t)(tok0 + row) * q_pitch) + ch);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int const c = i * 32 + lane, row = c >> 4, ch = c & 15;
+            *reinterpret_cast<uint4*>(tw + row * 256 + ((ch ^ (row & 7)) << 4)) = v[i];
+        }
+    }
+    __syncwarp();
+    int const lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = lane >> 4;  // ldmatrix.x4: matrices (rows 0-7 | 8-15) x (dims 0-7 | 8-15)
+    uint32_t const tw_s = (uint32_t)__cvta_generic_to_shared(tw);
     bool const pad_col = t == 3;  // this lane's second column is token 7: the padding column
 #pragma unroll
     for (int h = 0; h < kHeads; ++h) {
-        uint32_t const a0 = __ldg(reinterpret_cast<uint32_t const*>(r0 + h * 16)), a1 = __ldg(reinterpret_cast<uint32_t const*>(r1 + h * 16));
-        uint32_t const a2 = __ldg(reinterpret_cast<uint32_t const*>(r0 + h * 16 + 8)), a3 = __ldg(reinterpret_cast<uint32_t const*>(r1 + h * 16 + 8));
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(tw_s + lrow * 256 + (((2 * h + lhalf) ^ (lrow & 7)) << 4))
+                     : "memory");
         float s[4] = {0.f, 0.f, 0.f, 0.f};
         mma16816_f16(s, a0, a1, a2, a3, kb[h][0][lane], kb[h][1][lane]);
         if (pad_col) s[1] = s[3] = -INFINITY;
@@ -349,10 +346,19 @@ __global__ void __launch_bounds__(256) i2t_mma_kernel(act_t const* __restrict__ 
         float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
         mma16816_f16(oa, pa0, pa1, 0u, 0u, vb[h][0][lane], 0u);  // dims 0-7 of the head
         mma16816_f16(ob, pa0, pa1, 0u, 0u, vb[h][1][lane], 0u);  // dims 8-15
-        *reinterpret_cast<uint32_t*>(o0 + h * 16) = pack_h2(oa[0], oa[1]);
-        *reinterpret_cast<uint32_t*>(o1 + h * 16) = pack_h2(oa[2], oa[3]);
-        *reinterpret_cast<uint32_t*>(o0 + h * 16 + 8) = pack_h2(ob[0], ob[1]);
-        *reinterpret_cast<uint32_t*>(o1 + h * 16 + 8) = pack_h2(ob[2], ob[3]);
+        uint8_t* const c0 = tw + (((2 * h) ^ g) << 4) + 4 * t;      // dims 0-7: chunk 2h (rows g and g + 8 swizzle alike)
+        uint8_t* const c1 = tw + (((2 * h + 1) ^ g) << 4) + 4 * t;  // dims 8-15
+        *reinterpret_cast<uint32_t*>(c0 + g * 256) = pack_h2(oa[0], oa[1]);
+        *reinterpret_cast<uint32_t*>(c0 + (g + 8) * 256) = pack_h2(oa[2], oa[3]);
+        *reinterpret_cast<uint32_t*>(c1 + g * 256) = pack_h2(ob[0], ob[1]);
+        *reinterpret_cast<uint32_t*>(c1 + (g + 8) * 256) = pack_h2(ob[2], ob[3]);
+    }
+    __syncwarp();
+    act_t* const obase = out + ((size_t)p * kImgTokens + tok0) * 128;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int const c = i * 32 + lane, row = c >> 4, ch = c & 15;
+        reinterpret_cast<uint4*>(obase + (size_t)row * 128)[ch] = *reinterpret_cast<uint4 const*>(tw + row * 256 + ((ch ^ (row & 7)) << 4));
     }
 }
 #endif
@@ -387,7 +393,7 @@ void token_to_image_attention(cudaStream_t s, float const* q, act_t const* base,
 #else
         static bool const cuda_core = std::getenv("DLIMG_B200_T2I_SIMT") != nullptr;  // cross-check: the CUDA-core form
         if (cuda_core) t2i_flash_kernel<<<dim3(P, kT2iSplits), kWarps * 32, 0, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
-        else t2i_mma_kernel<<<dim3(P, kT2iSplits), kWarps * 32, 0, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
+        else t2i_mma_kernel<<<dim3(P, kT2iSplits), kWarps * 32, kT2iSmem, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
 #endif
         KERNEL_CHECK();
     }

@@ -391,13 +391,13 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
     }
     for (int m = 0; m < 4; ++m) {
         std::string const p = D + "output_hypernetworks_mlps." + std::to_string(m) + ".layers.";
-        dec_.hyper[m][0] = load_linear32(wf, p + "0", 256, 256);
-        dec_.hyper[m][1] = load_linear32(wf, p + "1", 256, 256);
-        dec_.hyper[m][2] = load_linear32(wf, p + "2", 32, 256);
+        dec_.hyper[m][0] = load_linear32t(wf, p + "0", 256, 256);
+        dec_.hyper[m][1] = load_linear32t(wf, p + "1", 256, 256);
+        dec_.hyper[m][2] = load_linear32t(wf, p + "2", 32, 256);
     }
-    dec_.iou[0] = load_linear32(wf, D + "iou_prediction_head.layers.0", 256, 256);
-    dec_.iou[1] = load_linear32(wf, D + "iou_prediction_head.layers.1", 256, 256);
-    dec_.iou[2] = load_linear32(wf, D + "iou_prediction_head.layers.2", 4, 256);
+    dec_.iou[0] = load_linear32t(wf, D + "iou_prediction_head.layers.0", 256, 256);
+    dec_.iou[1] = load_linear32t(wf, D + "iou_prediction_head.layers.1", 256, 256);
+    dec_.iou[2] = load_linear32t(wf, D + "iou_prediction_head.layers.2", 4, 256);
 
     CUDA_CHECK(cudaDeviceSynchronize());
 }
@@ -417,7 +417,8 @@ EncoderWorkspace::EncoderWorkspace(int mb) : max_batch(mb) {
 DecoderWorkspace::DecoderWorkspace(int mp) : max_prompts(mp) {
     size_t const P = (size_t)mp;
     param_block.allocate(DecoderParams::bytes(mp));
-    for (auto* b : {&tok0, &queries, &tmp}) b->allocate(P * 7 * 256);
+    for (auto* b : {&tok0, &queries}) b->allocate(P * 7 * 256);
+    tmp.allocate((size_t)kMlpSplit * gemm::split_rows(P * 7) * 256);  // split-K partials of the token MLP's second Linear
     t128a.allocate(P * 7 * 128);
     t128b.allocate(P * 7 * 128);
     t128c.allocate(P * 7 * 128);
@@ -629,7 +630,7 @@ void SamModel::lin(cudaStream_t s, float const* x, int64_t xs, float const* x2, 
     dec::linear_small(s, x, xs, x2, xs, rows, l.k, l.w.get(), l.b.get(), l.n, relu, y, ys);
 }
 
-void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P) const {
+void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P, int mask_mode) const {
     DLIMG_ASSERT(P >= 1 && P <= ws.max_prompts);
     DecoderParams const prm = DecoderWorkspace::layout(ws.param_block.get(), P);
     int const R = P * dec::kTokens;
@@ -674,12 +675,22 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P) const {
         }
         // (3) token MLP on the tensor cores (7 rows per prompt, 4 MB of weights read once per pass)
         lin(s, ws.queries.get(), 256, nullptr, R, l.lin1, true, ws.hid.get(), 2048);
-        lin(s, ws.hid.get(), 2048, nullptr, R, l.lin2, false, ws.tmp.get(), 256);
+        {   // second Linear (K = 2048) split over k: 16 output tiles with a 64-step k-loop each left 130 SMs idle for 22 us
+            gemm::Epilogue e;
+            e.out_f32 = 1;
+            e.ldc = 256;
+            e.ksplit = kMlpSplit;
+            gemm::launch(s, true, gemm::Operand{ws.hid.get(), R, 2048, 2048}, gemm::Operand{l.lin2.w.get(), 256, 2048, 2048}, ws.tmp.get(), e,
+                         num_sms_);
+        }
         // residual + LayerNorm + the token-side projections of (4) (and, after the last layer, of the final attention)
         {
             dec::TokenPostMlp m;
             m.queries = ws.queries.get();
             m.mlp_out = ws.tmp.get();
+            m.mlp_parts = kMlpSplit;
+            m.mlp_part_stride = gemm::split_rows(R) * 256;
+            m.mlp_bias = l.lin2.b.get();
             m.pe = ws.tok0.get();
             m.gamma = l.n3.g.get(); m.beta = l.n3.b.get();
             m.count = first ? 2 : 3;
@@ -725,10 +736,10 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P) const {
     {
         dec::TokenMlp3 h;
         for (int l = 0; l < 3; ++l) {
-            h.w[0][l] = dec_.iou[l].w.get();
+            h.w[0][l] = dec_.iou[l].wt.get();
             h.b[0][l] = dec_.iou[l].b.get();
             for (int m = 0; m < 4; ++m) {
-                h.w[1 + m][l] = dec_.hyper[m][l].w.get();
+                h.w[1 + m][l] = dec_.hyper[m][l].wt.get();
                 h.b[1 + m][l] = dec_.hyper[m][l].b.get();
             }
         }
@@ -754,6 +765,8 @@ void SamModel::decode(cudaStream_t s, DecoderWorkspace& ws, int P) const {
         e2.ldc = dec_.up2.n;
         e2.fuse = 2;
         e2.fuse_a = ws.hyper.get();
+        e2.fuse_b = ws.iou.get();
+        e2.fuse_mode = mask_mode;
         e2.fuse_out = ws.low.get();
         gemm::launch(s, false, gemm::Operand{ws.big.get(), IR * 4, 64, 64}, gemm::Operand{dec_.up2.w.get(), 128, 64, 64}, nullptr, e2, num_sms_);
     }

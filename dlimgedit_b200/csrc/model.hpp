@@ -104,6 +104,8 @@ struct EncoderW {
     Norm neck_ln2;
 };
 
+constexpr int kMlpSplit = 8;  // k-splits of the decoder token MLP's 2048 -> 256 Linear (gemm.cuh Epilogue::ksplit)
+
 struct Linear32T {  // fp32 weight transposed and k-blocked, [K / 4][N][4], + bias -- the fused token-side kernels (decoder_tokens.cu)
     DeviceBuffer<float> wt;
     DeviceBuffer<float> b;
@@ -134,8 +136,8 @@ struct DecoderW {
     Linear16 up1;  // (256 = (dy,dx,co), 256)
     Norm up_ln;    // LayerNorm2d(64)
     Linear16 up2;  // (128 = (ey,ex,c2), 64)
-    Linear32 hyper[4][3];
-    Linear32 iou[3];
+    Linear32T hyper[4][3];
+    Linear32T iou[3];
 };
 
 // ---- workspaces -------------------------------------------------------------------------------
@@ -160,7 +162,8 @@ struct DecoderParams {
 struct DecoderWorkspace {
     int max_prompts = 0;
     DeviceBuffer<uint8_t> param_block;                       // DecoderParams::bytes(max_prompts), laid out per pass by layout()
-    DeviceBuffer<float> tok0, queries, tmp;                  // (P,7,256)
+    DeviceBuffer<float> tok0, queries;                       // (P,7,256)
+    DeviceBuffer<float> tmp;                                 // split-K partials of the token MLP output
     DeviceBuffer<float> t128a, t128b, t128c;                 // (P,7,128)
     DeviceBuffer<float> hid;                                 // (P,7,2048)
     DeviceBuffer<float> hyper, iou;                          // (P,4,32), (P,4)
@@ -200,7 +203,9 @@ class SamModel {
 
     // Runs the prompt encoder + mask decoder for P prompts whose parameter block (DecoderWorkspace::layout(ws.param_block, P))
     // has been filled by the engine.  Results: ws.low (P, 4, 256, 256) logits and ws.iou (P, 4).
-    void decode(cudaStream_t s, DecoderWorkspace& ws, int P) const;
+    // mask_mode (kernels/mask_select.cuh MaskMode): which planes of ws.low the pass writes -- all four, masks 1..3, or only
+    // the plane the predicted IoUs select (single-mask calls: a quarter of the hypernetwork products and logit writes)
+    void decode(cudaStream_t s, DecoderWorkspace& ws, int P, int mask_mode = 0) const;
 
     static StageCfg stage(int i);  // i = 1..3
 

@@ -21,8 +21,9 @@ def gather_scores(local: np.ndarray, n_images: int, rank: int, world: int) -> np
     import torch.distributed as dist
     per_rank = -(-n_images // world)
     P = local.shape[1] if local.ndim == 2 else 0
+    on_gpu = world > 1 and dist.get_backend() == "nccl"  # NCCL moves device tensors only
     if world > 1:
-        P_t = torch.tensor([P])
+        P_t = torch.tensor([P], device="cuda" if on_gpu else "cpu")
         dist.all_reduce(P_t, op=dist.ReduceOp.MAX)
         P = int(P_t.item())
     buf = torch.zeros(per_rank, P)
@@ -30,7 +31,7 @@ def gather_scores(local: np.ndarray, n_images: int, rank: int, world: int) -> np
         buf[: local.shape[0]] = torch.from_numpy(local)
     if world == 1:
         return buf[:n_images].numpy()
-    if dist.get_backend() == "nccl":
+    if on_gpu:
         buf = buf.cuda()
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)

@@ -19,7 +19,8 @@ typedef struct dlimg_b200_Debug {
      * folded LayerNorm; B must hold gamma-scaled weights with centred rows, then out = rstd * (A B^T) + bias (see
      * csrc/kernels/gemm.cuh): ln_parts == 0 -> per-row (mean, rstd) pairs [M][2]; ln_parts >= 1 -> [M][ln_parts]
      * partial (sum, sum of squares) of the rows of A.  stats_out (optional): [M][N / block_n][2], the same partial
-     * sums of the rows this GEMM writes. */
+     * sums of the rows this GEMM writes.  simt: 0 = tcgen05 kernel, 1 = CUDA-core cross-check kernel, k >= 2 = tcgen05
+     * kernel with split-K over k parts: out is [k][M rounded up to 128][N] fp32 partial sums (no bias). */
     dlimg_Result (*gemm)(void* stream, int tf32, int simt, void const* a, void const* b, int M, int N, int K,
                          float const* bias, void const* residual, int const* row_map, int act, int out_f32, void* out,
                          float const* ln_stats, int ln_parts, float* stats_out);

@@ -97,6 +97,25 @@ def test_tf32_gemm(M, N, K):
     assert torch.allclose(simt.double(), ref, atol=1e-4, rtol=1e-4)
 
 
+@pytest.mark.parametrize("M,N,K,ks", [(448, 256, 2048, 8), (7, 256, 2048, 8), (1792, 256, 2048, 8), (130, 64, 512, 4)])
+def test_tf32_gemm_split_k(M, N, K, ks):
+    """Split-K (the decoder token MLP's 2048 -> 256 Linear): `ks` partial results in row blocks of M rounded up to 128."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    mpad = (M + 127) // 128 * 128
+    out = torch.full((ks * mpad, N), float("nan"), device="cuda")
+    gemm(a, b, out_f32=True, simt=ks, out=out)
+    parts = out.view(ks, mpad, N)
+    assert torch.isfinite(parts[:, :M]).all()
+    kk = K // ks
+    for s in range(ks):  # every part is the product over its own k range
+        ref = a[:, s * kk:(s + 1) * kk].double() @ b[:, s * kk:(s + 1) * kk].double().t()
+        assert float((parts[s, :M].double() - ref).abs().max()) < 5e-3
+    whole = gemm(a, b, out_f32=True)
+    assert float((parts[:, :M].sum(0) - whole).abs().max()) < 1e-3
+
+
 def test_gemm_back_to_back_is_deterministic():
     g = torch.Generator(device="cuda").manual_seed(3)
     a = torch.randn(65536, 64, device="cuda", generator=g).to(act_dtype())
