@@ -203,6 +203,7 @@ struct ResizeTile {
     int tr = 0, tc = 0;          // output rows / columns per block; tc * bpp <= 256 and a multiple of 4
     int nr_max = 0, nc_max = 0;  // most input rows / columns any tile needs (exact, from the axis plans)
     int ch = 8;                  // input rows decoded per pass (one per warp)
+    int raw_pitch = 0;           // bytes per row of the raw (cp.async) staging buffers
     int smem_bytes = 0;
 };
 
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) resize_tile_kernel(uint8_t const* __restr
     extern __shared__ __align__(16) float rs_smem[];
     int const row_elems = g.tc * BPP;            // H-pass outputs per input row
     int const px_per_row = g.nc_max + KT;        // staged pixels per input row (tail zero-filled: taps >= htaps read it)
-    int const in_elems = px_per_row * BPP;
+    int const in_elems = (px_per_row * BPP + 32 + 3) & ~3;  // floats per staged row (+32: the streaming path's alignment slack)
     float* const s_dec = rs_smem;
     float* const s_thr = s_dec + 256;
     float* const s_vw = s_thr + 256;
@@ -243,36 +244,52 @@ __global__ void __launch_bounds__(256) resize_tile_kernel(uint8_t const* __restr
     }
     bool const interior = c_lo >= 0 && c_hi < in_w;  // no horizontal clamping in this tile: staged bytes are contiguous
     int const row_bytes = nc * BPP;
-    // The bytes of the NEXT chunk's rows are fetched into registers before the H-pass of the current chunk and decoded
-    // after it: the trip to L2 / HBM hides behind the filter arithmetic (without it the kernel sat at 30 % issue
-    // utilisation, half of its stalls on these loads: profiles/r02a_summary.md).  One staged row per warp (g.ch == 8).
-    constexpr int kPre = 24;
-    bool const use_pre = interior && g.ch == 8 && row_bytes <= 32 * kPre;
-    uint8_t pre[kPre];
-    auto prefetch = [&](int rc) {
+    // Interior tiles of 16-byte aligned images stream their input rows with cp.async, one chunk (8 rows, one per warp) ahead
+    // of the chunk being filtered: whole 16-byte granules from the aligned address below the tile's first byte into a raw
+    // byte buffer (double-buffered), decoded from there four bytes per shared-memory load.  The trip to L2 / HBM no longer
+    // sits in front of every chunk (byte loads straight from global memory left the kernel at 30 % issue utilisation, half
+    // of its stalls on them), and the copy holds no registers.  Reading up to 15 bytes past the tile's last byte stays
+    // inside the image unless the tile touches the last row: those tiles, clamped ones and unaligned images decode with
+    // plain loads.
+    int const byte_lo = c_lo * BPP, a_lo = byte_lo & ~15, d0 = byte_lo - a_lo;
+    int const raw_len = (d0 + row_bytes + 15) & ~15;
+    bool const use_async = interior && g.ch == 8 && ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)stride) & 15) == 0 &&
+                           (a_lo + raw_len <= in_w * BPP || r_hi < in_h - 1);
+    uint8_t* const s_raw = reinterpret_cast<uint8_t*>(s_in + g.ch * in_elems);  // [2][ch][raw_pitch]
+    auto issue = [&](int rc, int buf) {
         if (warp < min(g.ch, nr - rc)) {
             int const y = min(max(r_lo + rc + warp, 0), in_h - 1);
-            uint8_t const* src = in + (size_t)y * stride + (size_t)c_lo * BPP;
-#pragma unroll
-            for (int i = 0; i < kPre; ++i) {
-                int const e = lane + 32 * i;
-                pre[i] = e < row_bytes ? __ldg(src + e) : (uint8_t)0;
-            }
+            uint8_t const* src = in + (size_t)y * stride + a_lo;
+            uint32_t const dst = (uint32_t)__cvta_generic_to_shared(s_raw + (size_t)(buf * g.ch + warp) * g.raw_pitch);
+            for (int o = lane * 16; o < raw_len; o += 512)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (use_pre) prefetch(0);
+    if (use_async) issue(0, 0);
+    // the zero tail behind every staged row (taps >= htaps read it) is written once: decoding never touches it.  The
+    // streaming path decodes whole raw rows -- staged element e sits at index d0 + e, the raw bytes around the tile's own are
+    // image bytes too (finite values under zero weights) -- so every shared-memory store is an aligned 16-byte one.
+    int const e_shift = use_async ? d0 : 0;
+    for (int rr = warp; rr < g.ch; rr += 8)
+        for (int e = (use_async ? raw_len : row_bytes) + lane; e < in_elems; e += 32) s_in[rr * in_elems + e] = 0.0f;
     __syncthreads();
-    for (int rc = 0; rc < nr; rc += g.ch) {
+    int chunk = 0;
+    for (int rc = 0; rc < nr; rc += g.ch, ++chunk) {
         int const chv = min(g.ch, nr - rc);
-        if (use_pre) {
+        if (use_async) {
+            bool const more = rc + g.ch < nr;
+            if (more) issue(rc + g.ch, (chunk + 1) & 1);
+            if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();  // (a warp decodes the row it copied itself, but the H-pass below must be done with s_in)
             if (warp < chv) {
-                float* dst_row = s_in + warp * in_elems;
-#pragma unroll
-                for (int i = 0; i < kPre; ++i) {
-                    int const e = lane + 32 * i;
-                    if (e < row_bytes) dst_row[e] = s_dec[pre[i]];
+                uint32_t const* raw = reinterpret_cast<uint32_t const*>(s_raw + (size_t)((chunk & 1) * g.ch + warp) * g.raw_pitch);
+                float4* dst_row = reinterpret_cast<float4*>(s_in + warp * in_elems);
+                for (int wi = lane; wi < (raw_len >> 2); wi += 32) {
+                    uint32_t const v = raw[wi];
+                    dst_row[wi] = make_float4(s_dec[v & 255u], s_dec[(v >> 8) & 255u], s_dec[(v >> 16) & 255u], s_dec[v >> 24]);
                 }
-                for (int e = row_bytes + lane; e < in_elems; e += 32) dst_row[e] = 0.0f;
             }
         } else {
             // decode: warp = staged row, lanes walk its bytes (32 consecutive bytes per load instruction)
@@ -285,16 +302,33 @@ __global__ void __launch_bounds__(256) resize_tile_kernel(uint8_t const* __restr
                     int const x = min(max(c_lo + px, 0), in_w - 1);
                     dst_row[e] = s_dec[__ldg(src_row + (size_t)x * BPP + c)];
                 }
-                for (int e = row_bytes + lane; e < in_elems; e += 32) dst_row[e] = 0.0f;
             }
         }
         __syncthreads();
-        if (use_pre && rc + g.ch < nr) prefetch(rc + g.ch);
         if (hactive) {
             int const r_end = min((grp + 1) * rows_per_group, chv);
             int rr = grp * rows_per_group;
-            for (; rr + 1 < r_end; rr += 2) {  // two rows at once: two independent add chains
-                float const* row0 = s_in + rr * in_elems + foff;
+            for (; rr + 3 < r_end; rr += 4) {  // four rows at once: four independent add chains hide the shared-memory latency
+                float const* row0 = s_in + rr * in_elems + foff + e_shift;
+                float const* row1 = row0 + in_elems;
+                float const* row2 = row1 + in_elems;
+                float const* row3 = row2 + in_elems;
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                    a0 = __fadd_rn(a0, __fmul_rn(row0[k * BPP], w[k]));
+                    a1 = __fadd_rn(a1, __fmul_rn(row1[k * BPP], w[k]));
+                    a2 = __fadd_rn(a2, __fmul_rn(row2[k * BPP], w[k]));
+                    a3 = __fadd_rn(a3, __fmul_rn(row3[k * BPP], w[k]));
+                }
+                float* hb = s_hb + (rc + rr) * row_elems + j;
+                hb[0] = a0;
+                hb[row_elems] = a1;
+                hb[2 * row_elems] = a2;
+                hb[3 * row_elems] = a3;
+            }
+            for (; rr + 1 < r_end; rr += 2) {  // two rows at once
+                float const* row0 = s_in + rr * in_elems + foff + e_shift;
                 float const* row1 = row0 + in_elems;
                 float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
@@ -306,15 +340,16 @@ __global__ void __launch_bounds__(256) resize_tile_kernel(uint8_t const* __restr
                 s_hb[(rc + rr + 1) * row_elems + j] = a1;
             }
             if (rr < r_end) {
-                float const* row0 = s_in + rr * in_elems + foff;
+                float const* row0 = s_in + rr * in_elems + foff + e_shift;
                 float a0 = 0.0f;
 #pragma unroll
                 for (int k = 0; k < KT; ++k) a0 = __fadd_rn(a0, __fmul_rn(row0[k * BPP], w[k]));
                 s_hb[(rc + rr) * row_elems + j] = a0;
             }
         }
-        __syncthreads();
+        if (!use_async) __syncthreads();  // (the streaming path meets at the barrier in front of its next decode)
     }
+    __syncthreads();
     // vertical pass + encode: four neighbouring columns per thread
     int const quads = row_elems >> 2, valid_elems = tcv * BPP;
     for (int i = tid; i < trv * quads; i += 256) {
@@ -502,9 +537,16 @@ __global__ void __launch_bounds__(256) mask_post_kernel(float const* __restrict_
 // neighbouring output bytes per row, keeps the horizontally interpolated source rows it needs in registers across the
 // output rows of its strip, and writes whole 32- / 64-bit words (128 / 256 contiguous bytes per warp instruction).
 
-__device__ __forceinline__ uint32_t pack_mask4(float const* v) {
-    return (v[0] > 0.f ? 0x000000ffu : 0u) | (v[1] > 0.f ? 0x0000ff00u : 0u) | (v[2] > 0.f ? 0x00ff0000u : 0u) |
-           (v[3] > 0.f ? 0xff000000u : 0u);
+// Four mask bytes (v > 0 ? 255 : 0) from four values that were computed with weights scaled by kSignScale = 2^100: the
+// scaling is exact (power of two) and makes every positive result a NORMAL float, whose bit pattern read as a signed
+// integer is >= 2^23; zero stays 0 and negative values are negative integers, so an unsigned-saturating 8-bit pack of the
+// raw bits is the threshold -- two instructions per four pixels instead of 4 FSETP + 4 SEL + 3 PRMT.
+constexpr float kSignScale = 1.2676506002282294e30f;  // 2^100
+__device__ __forceinline__ uint32_t pack_sign4(float const* v) {
+    uint32_t hi, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(__float_as_int(v[3])), "r"(__float_as_int(v[2])), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(__float_as_int(v[1])), "r"(__float_as_int(v[0])), "r"(hi));
+    return d;
 }
 
 // Identity case: the resized extent equals the output extent (long side == 1024), so the second bilinear has weights
@@ -558,10 +600,10 @@ __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __
         if (t >= rows_valid) return;
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = l0 * ha[e] + l1 * hb[e];
+        for (int e = 0; e < 8; ++e) v[e] = (l0 * kSignScale) * ha[e] + (l1 * kSignScale) * hb[e];  // exact scaling: pack_sign4
         uint8_t* d = dst + (size_t)t * w;
         if (word_ok) {
-            *reinterpret_cast<uint2*>(d) = make_uint2(pack_mask4(v), pack_mask4(v + 4));
+            *reinterpret_cast<uint2*>(d) = make_uint2(pack_sign4(v), pack_sign4(v + 4));
         } else {
             for (int e = 0; e < 8 && x0 + e < w; ++e) d[e] = v[e] > 0.f ? 255 : 0;
         }
@@ -585,28 +627,35 @@ __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __
     emit(7, 0.625f, 0.375f);
 }
 
-// General case.  A block produces g.rows (32 .. 1, by shared-memory need) complete output rows of one mask; every intermediate is computed once per
-// block and kept in shared memory:
+// General case.  A block produces g.rows (32 .. 1, by shared-memory need) complete output rows of one mask; every
+// intermediate is computed once per block and kept in shared memory:
 //   1. the few low-resolution rows the block needs                                     s_low[n_low][256]
 //   2. their horizontal interpolation at the 1024 grid                                 s_h[n_low][1024]
-//   3. the vertical interpolation = the 1024-grid rows the block needs                 s_grid[n_slots][1024]
-//   4. output pixels: a thread owns 4 neighbouring columns; the second bilinear's horizontal half for the two grid rows
-//      of an output row is carried in registers from row to row (when enlarging, several output rows share the pair).
+//   3. the vertical interpolation = the 1024-grid rows the block needs                 s_grid[n_slots][1024 + pad]
+//      (column rw repeats column rw - 1, so the right neighbour of a sample is always at +4 bytes: no second index)
+//   4. output pixels: a thread owns PX neighbouring columns (4 / 8 / 16 by output width: wide outputs amortise the per-row
+//      bookkeeping over more pixels and store 16 bytes at once); the second bilinear's horizontal half for the two grid
+//      rows of an output row is carried in registers from row to row (when enlarging, several output rows share the
+//      pair), and each output row's (grid row pair, weight) comes from a small table built once per block instead of
+//      being recomputed by every thread (at PX = 4 the coordinate arithmetic was a third of the 15 instructions per pixel).
 struct PostGeom {
     int rw, rh, w, h;
     float sx, sy;
     int n_slots, n_low;  // upper bounds of the 1024-grid rows / low-resolution rows a block needs (host)
     int rows;            // output rows per block
 };
+constexpr int kGridPitch = kImageSize + 4;  // floats per s_grid row (one repeated column + alignment)
 
-__global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __restrict__ low_res, int64_t plane_stride,
-                                                             int const* __restrict__ plane_index, PostGeom g,
-                                                             uint8_t* const* __restrict__ out_planes,
-                                                             uint8_t* __restrict__ out_contig) {
+template <int PX>
+__global__ void __launch_bounds__(256, PX >= 16 ? 2 : 3) mask_post_tile_kernel(float const* __restrict__ low_res, int64_t plane_stride,
+                                                                               int const* __restrict__ plane_index, PostGeom g,
+                                                                               uint8_t* const* __restrict__ out_planes,
+                                                                               uint8_t* __restrict__ out_contig) {
     extern __shared__ __align__(16) uint8_t post_smem[];
     float* const s_low = reinterpret_cast<float*>(post_smem);
     float* const s_h = s_low + g.n_low * kLowRes;
     float* const s_grid = s_h + g.n_low * kImageSize;
+    int4* const s_row = reinterpret_cast<int4*>(s_grid + g.n_slots * kGridPitch);  // per output row: slot a, slot b, weight of b
     int const tid = threadIdx.x;
     int const plane = blockIdx.y;
     int const y0 = blockIdx.x * g.rows;
@@ -627,49 +676,85 @@ __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __rest
         float4* dst = reinterpret_cast<float4*>(s_low);
         for (int i = tid; i < n_low * (kLowRes / 4); i += 256) dst[i] = __ldg(src + i);
     }
+    if (tid < rows_valid) {
+        Lerp const q = lerp_coord(y0 + tid, g.sy, g.rh);
+        s_row[tid] = make_int4(q.i0 - g_base, q.i1 - g_base, __float_as_int(q.l1), 0);
+    }
     __syncthreads();
-    // 2. horizontal interpolation of those rows at grid columns 0 .. rw-1
-    for (int xx = tid; xx < g.rw; xx += 256) {
-        Lerp const lx = lerp_coord(xx, 0.25f, kLowRes);
+    // 2. horizontal interpolation of those rows at grid columns 0 .. rw-1: a thread owns four neighbouring columns (their
+    // sample coordinates are computed once, the results leave as one 16-byte store per low-resolution row)
+    if (4 * tid < g.rw) {
+        Lerp lx[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) lx[e] = lerp_coord(min(4 * tid + e, kImageSize - 1), 0.25f, kLowRes);
         for (int j = 0; j < n_low; ++j) {
             float const* r = s_low + j * kLowRes;
-            s_h[j * kImageSize + xx] = lx.l0 * r[lx.i0] + lx.l1 * r[lx.i1];
+            float4 o;
+            o.x = lx[0].l0 * r[lx[0].i0] + lx[0].l1 * r[lx[0].i1];
+            o.y = lx[1].l0 * r[lx[1].i0] + lx[1].l1 * r[lx[1].i1];
+            o.z = lx[2].l0 * r[lx[2].i0] + lx[2].l1 * r[lx[2].i1];
+            o.w = lx[3].l0 * r[lx[3].i0] + lx[3].l1 * r[lx[3].i1];
+            *reinterpret_cast<float4*>(s_h + j * kImageSize + 4 * tid) = o;
         }
     }
     __syncthreads();
-    // 3. the 1024-grid rows
-    for (int slot = 0; slot < n_slots; ++slot) {
-        Lerp const q = lerp_coord(g_base + slot, 0.25f, kLowRes);
-        float const* r0 = s_h + (q.i0 - l_base) * kImageSize;
-        float const* r1 = s_h + (q.i1 - l_base) * kImageSize;
-        for (int xx = tid; xx < g.rw; xx += 256) s_grid[slot * kImageSize + xx] = q.l0 * r0[xx] + q.l1 * r1[xx];
+    // 3. the 1024-grid rows, four columns per thread (columns past rw - 1 are computed but never read, except the copy
+    // of column rw - 1 written behind it)
+    if (4 * tid < g.rw) {
+        for (int slot = 0; slot < n_slots; ++slot) {
+            Lerp const q = lerp_coord(g_base + slot, 0.25f, kLowRes);
+            float4 const a = *reinterpret_cast<float4 const*>(s_h + (q.i0 - l_base) * kImageSize + 4 * tid);
+            float4 const b = *reinterpret_cast<float4 const*>(s_h + (q.i1 - l_base) * kImageSize + 4 * tid);
+            float4 o;
+            o.x = q.l0 * a.x + q.l1 * b.x;
+            o.y = q.l0 * a.y + q.l1 * b.y;
+            o.z = q.l0 * a.z + q.l1 * b.z;
+            o.w = q.l0 * a.w + q.l1 * b.w;
+            float* dst = s_grid + slot * kGridPitch + 4 * tid;
+            *reinterpret_cast<float4*>(dst) = o;
+            int const last = g.rw - 1 - 4 * tid;  // position of column rw - 1 among this thread's four
+            if (last >= 0 && last < 4) dst[last + 1] = last == 0 ? o.x : last == 1 ? o.y : last == 2 ? o.z : o.w;
+        }
     }
     __syncthreads();
-    // 4. second bilinear + threshold.  The row loop is NOT unrolled: its coordinates are block-uniform (uniform datapath),
-    // the two "row pair changed" branches are uniform, and the body stays small (the unrolled form was 3600 instructions,
-    // 22 per pixel, a third of them branches and predicate logic: profiles/r02a_summary.md).
+    // 4. second bilinear + threshold.  The row loop is NOT unrolled over rows (the unrolled form was 3600 instructions, a
+    // third of them branches and predicate logic: profiles/r02a_summary.md); the "row pair changed" branches are uniform.
     bool const word_ok = (g.w & 3) == 0 && (reinterpret_cast<uintptr_t>(plane_out) & 3) == 0;
-    for (int x0 = 4 * tid; x0 < g.w; x0 += 1024) {
-        Lerp lx[4];
+    bool const vec_ok = PX == 16 && (g.w & 15) == 0 && (reinterpret_cast<uintptr_t>(plane_out) & 15) == 0;
+    uint32_t const grid_s = (uint32_t)__cvta_generic_to_shared(s_grid);
+    for (int x0 = PX * tid; x0 < g.w; x0 += 256 * PX) {
+        uint32_t off[PX];  // byte offset of the left sample inside a grid row
+        float l1[PX];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) lx[e] = lerp_coord(min(x0 + e, g.w - 1), g.sx, g.rw);
-        auto hrow = [&](int slot, float (&o)[4]) {
-            float const* r = s_grid + slot * kImageSize;
+        for (int e = 0; e < PX; ++e) {
+            Lerp const lx = lerp_coord(min(x0 + e, g.w - 1), g.sx, g.rw);
+            off[e] = grid_s + 4u * (uint32_t)lx.i0;
+            l1[e] = lx.l1;
+        }
+        auto hrow = [&](int slot, float (&o)[PX]) {
+            uint32_t const row_off = (uint32_t)slot * (kGridPitch * 4);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = lx[e].l0 * r[lx[e].i0] + lx[e].l1 * r[lx[e].i1];
+            for (int e = 0; e < PX; ++e) {
+                float r0, r1;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r0) : "r"(off[e] + row_off));
+                asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(r1) : "r"(off[e] + row_off));
+                o[e] = (1.0f - l1[e]) * r0 + l1[e] * r1;
+            }
         };
         int ca = -1, cb = -1;
-        float ha[4], hb[4];
+        float ha[PX], hb[PX];
         uint8_t* dst = plane_out + (size_t)y0 * g.w + x0;
-        bool const full = x0 + 4 <= g.w && word_ok;
+        bool const full = x0 + PX <= g.w;
 #pragma unroll 1
         for (int t = 0; t < rows_valid; ++t, dst += g.w) {
-            Lerp const q = lerp_coord(y0 + t, g.sy, g.rh);
-            int const a = q.i0 - g_base, b = q.i1 - g_base;
+            int4 const q = s_row[t];
+            int const a = q.x, b = q.y;
+            float const q1u = __int_as_float(q.z);
+            float const q0 = (1.0f - q1u) * kSignScale, q1 = q1u * kSignScale;  // exact: see pack_sign4
             if (a != ca) {
                 if (a == cb) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) ha[e] = hb[e];
+                    for (int e = 0; e < PX; ++e) ha[e] = hb[e];
                 } else {
                     hrow(a, ha);
                 }
@@ -678,19 +763,25 @@ __global__ void __launch_bounds__(256) mask_post_tile_kernel(float const* __rest
             if (b != cb) {
                 if (b == ca) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) hb[e] = ha[e];
+                    for (int e = 0; e < PX; ++e) hb[e] = ha[e];
                 } else {
                     hrow(b, hb);
                 }
                 cb = b;
             }
-            float v[4];
+            float v[PX];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = q.l0 * ha[e] + q.l1 * hb[e];
-            if (full) {
-                *reinterpret_cast<uint32_t*>(dst) = pack_mask4(v);
+            for (int e = 0; e < PX; ++e) v[e] = q0 * ha[e] + q1 * hb[e];
+            if (full && vec_ok) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_sign4(v), pack_sign4(v + 4), pack_sign4(v + (PX > 8 ? 8 : 0)),
+                                                            pack_sign4(v + (PX > 8 ? 12 : 0)));
+            } else if (full && word_ok) {
+#pragma unroll
+                for (int e = 0; e < PX; e += 4) *reinterpret_cast<uint32_t*>(dst + e) = pack_sign4(v + e);
             } else {
-                for (int e = 0; e < 4 && x0 + e < g.w; ++e) dst[e] = v[e] > 0.f ? 255 : 0;
+#pragma unroll
+                for (int e = 0; e < PX; ++e)  // (fully unrolled: a dynamic index would put v[] in local memory)
+                    if (x0 + e < g.w) dst[e] = v[e] > 0.f ? 255 : 0;
             }
         }
     }
@@ -738,7 +829,7 @@ int post_plan(PostGeom& g, int rows) {
     auto span = [](float scale, int n, int limit) { return std::min(limit, (int)std::ceil((double)scale * (n - 1)) + 3); };
     g.n_slots = span(g.sy, rows, g.rh);
     g.n_low = span(0.25f, g.n_slots, kLowRes);
-    return g.n_low * (kLowRes + kImageSize) * 4 + g.n_slots * kImageSize * 4;
+    return g.n_low * (kLowRes + kImageSize) * 4 + g.n_slots * kGridPitch * 4 + rows * 16;
 }
 
 void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride, int const* plane_index, int count, int rw,
@@ -758,9 +849,11 @@ void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride
         return;
     }
     int rows = 0, smem = 0;
+    // wide outputs run the 16-column kernel, whose registers allow two blocks per SM anyway: give them taller blocks
+    int const budget = w > 2048 ? 100 * 1024 : kPostSmemBudget;
     for (int r : {32, 16, 8, 4, 2, 1}) {
         smem = post_plan(g, r);
-        if (smem <= kPostSmemBudget) { rows = r; break; }
+        if (smem <= budget) { rows = r; break; }
     }
     if (rows == 0) {  // cannot happen for rh <= 1024 (one row needs 3 + 3 source rows); kept as a guard
         DLIMG_ASSERT(h <= 65535);
@@ -770,14 +863,23 @@ void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride
         return;
     }
     g.rows = rows;
-    set_smem_limit(mask_post_tile_kernel, smem);
-    mask_post_tile_kernel<<<dim3(ceil_div(h, rows), count), 256, smem, s>>>(low_res, plane_stride, plane_index, g, out_planes, out_contig);
+    auto go = [&](auto kernel) {
+        set_smem_limit(kernel, smem);
+        kernel<<<dim3(ceil_div(h, rows), count), 256, smem, s>>>(low_res, plane_stride, plane_index, g, out_planes, out_contig);
+    };
+    if (w > 2048) go(mask_post_tile_kernel<16>);      // 256 threads x 16 columns cover a 4K row in one pass
+    else if (w > 1024) go(mask_post_tile_kernel<8>);
+    else go(mask_post_tile_kernel<4>);
     KERNEL_CHECK();
 }
 
 // Tile shape for the single-kernel resize: the largest candidate whose shared-memory need fits the budget.
 ResizeTile plan_resize_tile(ResizeDeviceTables const& t, int bpp, int kt, int out_w, int out_h) {
     static int const kRowsCand[] = {32, 16, 8, 4, 2, 1};
+    static int64_t const budget = [] {  // tile height vs blocks per SM (development switch)
+        char const* e = std::getenv("DLIMG_B200_RESIZE_SMEM_KB");
+        return (int64_t)std::min(std::max(e ? std::atoi(e) : 64, 16), 200) * 1024;
+    }();
     // tall, narrow tiles: two row groups of tc * bpp H-pass columns fill the 256 threads (120 / 128 columns each)
     int const tc_full = bpp == 3 ? 40 : 128 / bpp;
     ResizeTile best;
@@ -792,9 +894,11 @@ ResizeTile plan_resize_tile(ResizeDeviceTables const& t, int bpp, int kt, int ou
             for (int ox0 = 0; ox0 < out_w; ox0 += tc)
                 g.nc_max = std::max(g.nc_max, t.hfirst_host[std::min(ox0 + tc, out_w) - 1] + t.htaps - t.hfirst_host[ox0]);
             g.ch = 8;
-            int64_t const floats = 512 + ((tr * t.vtaps + 3) & ~3) + (int64_t)g.nr_max * tc * bpp + (int64_t)g.ch * (g.nc_max + kt) * bpp;
-            if (floats * 4 <= 100 * 1024) {
-                g.smem_bytes = (int)(floats * 4);
+            int64_t const floats = 512 + ((tr * t.vtaps + 3) & ~3) + (int64_t)g.nr_max * tc * bpp + (int64_t)g.ch * (((g.nc_max + kt) * bpp + 32 + 3) & ~3);
+            g.raw_pitch = (g.nc_max * bpp + 15 + 15) & ~15;
+            int64_t const bytes = floats * 4 + 2 * (int64_t)g.ch * g.raw_pitch;
+            if (bytes <= budget) {
+                g.smem_bytes = (int)bytes;
                 best = g;
                 break;
             }

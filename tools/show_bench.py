@@ -1,5 +1,5 @@
 import json, sys
-d = json.load(open(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/bench.json'))
+d = json.loads([l for l in open(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/bench.json').read().splitlines() if l.startswith('{')][-1])  # NCCL prints its version first
 print("value", round(d["value"], 1), "img/s  ms/step", round(d["ms_per_step"], 3), " e2e", round(d["e2e"]["value"], 1), "ms", round(d["e2e"]["ms_per_step"], 2))
 print("launches", d["gpu_launches"], d["clocks"])
 r = d["roofline"]
