@@ -1,6 +1,9 @@
 """Builds libdlimgedit.so (C++ host + sm_100a CUDA kernels) in-tree with nvcc.
 
-    python -m dlimgedit_b200._build [--force] [--verbose]
+    python -m dlimgedit_b200._build [--force] [--verbose] [--dev]
+
+--dev compiles the development switches and their alternative kernels in (-DDLIMG_B200_DEV, csrc/common.hpp); a change of the
+flag rebuilds everything.
 
 The library is linked against the static CUDA runtime only: no cuBLAS / cuDNN / onnxruntime.
 """
@@ -54,16 +57,20 @@ def _headers():
     return out
 
 
-def _compile(src: str, obj: str, verbose: bool):
-    cmd = [NVCC] + COMMON + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
+def _compile(src: str, obj: str, verbose: bool, dev: bool = False):
+    cmd = [NVCC] + COMMON + (["-DDLIMG_B200_DEV"] if dev else []) + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
     return r.stderr
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
     os.makedirs(os.path.join(OBJ_DIR, "kernels"), exist_ok=True)
+    flavour = os.path.join(OBJ_DIR, "flavour")
+    want = "dev" if dev else "release"
+    if not os.path.exists(flavour) or open(flavour).read() != want:
+        force = True
     newest_header = max(os.path.getmtime(h) for h in _headers())
     jobs = []
     objs = []
@@ -76,7 +83,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             jobs.append((src, obj))
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
-            for log in ex.map(lambda j: _compile(j[0], j[1], verbose), jobs):
+            for log in ex.map(lambda j: _compile(j[0], j[1], verbose, dev), jobs):
                 if verbose and log:
                     print(log)
     if jobs or not os.path.exists(LIB_PATH):
@@ -88,8 +95,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(soname) or os.path.getmtime(soname) < os.path.getmtime(LIB_PATH):
         import shutil
         shutil.copy2(LIB_PATH, soname)
+    with open(flavour, "w") as f:
+        f.write(want)
     return LIB_PATH
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, dev="--dev" in sys.argv))

@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -19,6 +20,24 @@ class Error : public std::runtime_error {
 };
 
 [[noreturn]] inline void fail(std::string const& msg) { throw Error(msg); }
+
+// Development switches.  The library keeps a few alternative code paths to cross-check a fused kernel against its unfused
+// form or to A/B a design (DLIMG_B200_UNFUSED_PATCH, DLIMG_B200_T2I_SIMT, ...).  In a release build they are compiled out:
+// dev_switch() is a constant false, so the branches fold away, and the kernels that only they reach sit under
+// `#if DLIMG_B200_ALT`.  `python -m dlimgedit_b200._build --dev` (-DDLIMG_B200_DEV) and the bf16 build (which runs the
+// unfused forms) compile them in.
+#if defined(DLIMG_B200_DEV) || defined(DLIMG_B200_ACT_BF16)
+#define DLIMG_B200_ALT 1
+inline bool dev_switch(char const* name) { return std::getenv(name) != nullptr; }
+inline int dev_int(char const* name, int def) {
+    char const* v = std::getenv(name);
+    return v ? std::atoi(v) : def;
+}
+#else
+#define DLIMG_B200_ALT 0
+constexpr bool dev_switch(char const*) { return false; }
+constexpr int dev_int(char const*, int def) { return def; }
+#endif
 
 // Same contract as the reference's ASSERT (assert.hpp:17-28): report on stderr and throw.
 #define DLIMG_ASSERT(cond)                                                                           \

@@ -14,8 +14,7 @@ thread_local EnvCounters* tl_counters = nullptr;
 
 bool pdl_enabled(int family) {
     static unsigned const mask = [] {
-        char const* e = std::getenv("DLIMG_B200_PDL_MASK");
-        return e ? (unsigned)std::strtoul(e, nullptr, 0) : 0u;  // measured: no gain inside the CUDA graph (profiles/r01f)
+        return (unsigned)dev_int("DLIMG_B200_PDL_MASK", 0);  // development switch; measured: no gain inside the CUDA graph (profiles/r01f)
     }();
     return (mask >> family) & 1u;
 }

@@ -108,41 +108,7 @@ __global__ void __launch_bounds__(kLinWarps * 32) linear_small_kernel(float cons
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) token_self_attention_kernel(float const* __restrict__ q, float const* __restrict__ k,
-                                                                   float const* __restrict__ v, float* __restrict__ out) {
-    int const p = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    size_t const base = (size_t)p * kTokens * kDim + h * 32 + lane;
-    float kk[kTokens], vv[kTokens];
-#pragma unroll
-    for (int u = 0; u < kTokens; ++u) {
-        kk[u] = k[base + u * kDim];
-        vv[u] = v[base + u * kDim];
-    }
-    float const scale = 0.17677669529663687f;  // 1/sqrt(32)
-#pragma unroll
-    for (int t = 0; t < kTokens; ++t) {
-        float const qv = q[base + t * kDim];
-        float s[kTokens];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int u = 0; u < kTokens; ++u) {
-            s[u] = warp_sum(qv * kk[u]) * scale;
-            mx = fmaxf(mx, s[u]);
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int u = 0; u < kTokens; ++u) {
-            s[u] = expf(s[u] - mx);
-            sum += s[u];
-        }
-        float o = 0.f;
-#pragma unroll
-        for (int u = 0; u < kTokens; ++u) o = fmaf(s[u] / sum, vv[u], o);
-        out[base + t * kDim] = o;
-    }
-}
-
+#if DLIMG_B200_ALT  // CUDA-core form, kept as the cross-check of i2t_mma_kernel (DLIMG_B200_I2T_SIMT)
 // ---------------------------------------------------------------------------------------------
 // Image -> token attention core, one thread per (image token, head).  Q rows are 16-bit (the [K|V|Q] projection of the
 // image stream, row pitch q_pitch elements); the 7 token keys / values of the prompt sit in shared memory as
@@ -226,184 +192,7 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(act_t const* __restr
     o4[0] = ov[0];
     o4[1] = ov[1];
 }
-
-// keys <- LayerNorm_256(x + res) on the 16-bit image stream (eps 1e-5, fp32 statistics): one warp per row, 16-byte
-// loads.  The residual of prompt p is res_ptrs[p] (layer 0: the image's own prompt-independent keys) or
-// res + p * 4096 * 256.  In-place (out == res) is allowed: a row is read and written by the same lane.
-__global__ void __launch_bounds__(256) layernorm256_img_kernel(act_t const* __restrict__ x, act_t const* res,
-                                                               act_t const* const* __restrict__ res_ptrs, int64_t rows,
-                                                               float const* __restrict__ gamma, float const* __restrict__ beta,
-                                                               act_t* out) {
-    int64_t const row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    int const lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    int64_t const p = row / kImgTokens, tok = row - p * kImgTokens;
-    act_t const* r = (res_ptrs ? res_ptrs[p] : res + p * kImgTokens * kDim) + tok * kDim;
-    uint4 const xa = __ldg(reinterpret_cast<uint4 const*>(x + row * kDim) + lane);
-    uint4 const ra = *(reinterpret_cast<uint4 const*>(r) + lane);
-    act2_t const* xh = reinterpret_cast<act2_t const*>(&xa);
-    act2_t const* rh = reinterpret_cast<act2_t const*>(&ra);
-    float v[8];
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float2 const a = act22f2(xh[j]), b = act22f2(rh[j]);
-        v[2 * j] = a.x + b.x;
-        v[2 * j + 1] = a.y + b.y;
-        sum += v[2 * j] + v[2 * j + 1];
-    }
-    float const mean = warp_sum(sum) * (1.0f / kDim);
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float const d = v[i] - mean;
-        var = fmaf(d, d, var);
-    }
-    float const rstd = rsqrtf(warp_sum(var) * (1.0f / kDim) + 1e-5f);
-    float4 const g0 = __ldg(reinterpret_cast<float4 const*>(gamma) + 2 * lane), g1 = __ldg(reinterpret_cast<float4 const*>(gamma) + 2 * lane + 1);
-    float4 const b0 = __ldg(reinterpret_cast<float4 const*>(beta) + 2 * lane), b1 = __ldg(reinterpret_cast<float4 const*>(beta) + 2 * lane + 1);
-    float const gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    float const bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    uint4 ov;
-    act2_t* oh = reinterpret_cast<act2_t*>(&ov);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        oh[j] = f22act2((v[2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j], (v[2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]);
-    *(reinterpret_cast<uint4*>(out + row * kDim) + lane) = ov;
-}
-
-// ---------------------------------------------------------------------------------------------
-// `res` and `out` may alias (in-place residual update), so neither is __restrict__.
-__global__ void __launch_bounds__(256) layernorm256_kernel(float const* x, float const* res, int64_t res_mod, int64_t rows,
-                                                           float const* __restrict__ gamma, float const* __restrict__ beta,
-                                                           float const* __restrict__ pos, int64_t pos_mod, float* out,
-                                                           float* out2) {
-    int64_t const row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    int const lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    float v[8];
-    {
-        float4 const a = reinterpret_cast<float4 const*>(x + row * kDim)[lane];
-        float4 const b = reinterpret_cast<float4 const*>(x + row * kDim)[32 + lane];
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    }
-    if (res) {
-        float const* r = res + (row % res_mod) * kDim;
-        float4 const a = reinterpret_cast<float4 const*>(r)[lane];
-        float4 const b = reinterpret_cast<float4 const*>(r)[32 + lane];
-        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sum += v[i];
-    float const mean = warp_sum(sum) * (1.0f / kDim);
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float const d = v[i] - mean;
-        var = fmaf(d, d, var);
-    }
-    float const rstd = rsqrtf(warp_sum(var) * (1.0f / kDim) + 1e-5f);
-    float y[8];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        float4 const g = reinterpret_cast<float4 const*>(gamma)[half * 32 + lane];
-        float4 const bt = reinterpret_cast<float4 const*>(beta)[half * 32 + lane];
-        y[4 * half + 0] = (v[4 * half + 0] - mean) * rstd * g.x + bt.x;
-        y[4 * half + 1] = (v[4 * half + 1] - mean) * rstd * g.y + bt.y;
-        y[4 * half + 2] = (v[4 * half + 2] - mean) * rstd * g.z + bt.z;
-        y[4 * half + 3] = (v[4 * half + 3] - mean) * rstd * g.w + bt.w;
-        reinterpret_cast<float4*>(out + row * kDim)[half * 32 + lane] =
-            make_float4(y[4 * half], y[4 * half + 1], y[4 * half + 2], y[4 * half + 3]);
-    }
-    if (out2) {
-        float const* q = pos + (row % pos_mod) * kDim;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float4 const a = reinterpret_cast<float4 const*>(q)[half * 32 + lane];
-            reinterpret_cast<float4*>(out2 + row * kDim)[half * 32 + lane] =
-                make_float4(y[4 * half] + a.x, y[4 * half + 1] + a.y, y[4 * half + 2] + a.z, y[4 * half + 3] + a.w);
-        }
-    }
-}
-
-// In-place LayerNorm2d over groups of 64 channels (eps 1e-6) + exact GELU on 16-bit rows of 64: eight lanes per row
-// (16 bytes each), four rows per warp.
-__global__ void __launch_bounds__(256) layernorm64_gelu_kernel(act_t* __restrict__ x, int64_t rows,
-                                                               float const* __restrict__ gamma,
-                                                               float const* __restrict__ beta) {
-    int64_t const row = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 + ((threadIdx.x & 31) >> 3);
-    int const l8 = threadIdx.x & 7;
-    bool const ok = row < rows;
-    uint4 xa = make_uint4(0, 0, 0, 0);
-    if (ok) xa = *(reinterpret_cast<uint4 const*>(x + row * 64) + l8);
-    act2_t const* xh = reinterpret_cast<act2_t const*>(&xa);
-    float v[8];
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float2 const a = act22f2(xh[j]);
-        v[2 * j] = a.x;
-        v[2 * j + 1] = a.y;
-        sum += a.x + a.y;
-    }
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    float const mean = sum * (1.0f / 64.0f);
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float const d = v[i] - mean;
-        var = fmaf(d, d, var);
-    }
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    float const rstd = rsqrtf(var * (1.0f / 64.0f) + 1e-6f);
-    float4 const g0 = __ldg(reinterpret_cast<float4 const*>(gamma) + 2 * l8), g1 = __ldg(reinterpret_cast<float4 const*>(gamma) + 2 * l8 + 1);
-    float4 const b0 = __ldg(reinterpret_cast<float4 const*>(beta) + 2 * l8), b1 = __ldg(reinterpret_cast<float4 const*>(beta) + 2 * l8 + 1);
-    float const gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    float const bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    uint4 ov;
-    act2_t* oh = reinterpret_cast<act2_t*>(&ov);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        oh[j] = f22act2(gelu_erf((v[2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j]),
-                        gelu_erf((v[2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]));
-    if (ok) *(reinterpret_cast<uint4*>(x + row * 64) + l8) = ov;
-}
-
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mask_dot_kernel(float const* __restrict__ hyper, act_t const* __restrict__ up2,
-                                                       float* __restrict__ low) {
-    __shared__ float hs[4 * 32];
-    int const p = blockIdx.y;
-    if (threadIdx.x < 128) hs[threadIdx.x] = hyper[(size_t)p * 128 + threadIdx.x];
-    __syncthreads();
-    int const pix = blockIdx.x * blockDim.x + threadIdx.x;  // Y*256 + X
-    int const Y = pix >> 8, X = pix & 255;
-    int const y = Y >> 2, dy = (Y >> 1) & 1, ey = Y & 1;
-    int const x = X >> 2, dx = (X >> 1) & 1, ex = X & 1;
-    size_t const row = ((size_t)(y * 64 + x) * 4 + dy * 2 + dx);
-    uint4 const* u4 = reinterpret_cast<uint4 const*>(up2 + ((size_t)p * 16384 + row) * 128 + (ey * 2 + ex) * 32);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint4 const u = __ldg(u4 + c);
-        act2_t const* uh = reinterpret_cast<act2_t const*>(&u);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 const f = act22f2(uh[j]);
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                float const* hm = hs + m * 32 + c * 8 + 2 * j;
-                acc[m] = fmaf(f.x, hm[0], acc[m]);
-                acc[m] = fmaf(f.y, hm[1], acc[m]);
-            }
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m) low[((size_t)p * 4 + m) * 65536 + pix] = acc[m];
-}
+#endif
 
 __global__ void f32_to_act_kernel(float const* __restrict__ in, int64_t n, act_t* __restrict__ out) {
     int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -458,12 +247,7 @@ void linear_small(cudaStream_t s, float const* x, int64_t x_stride, float const*
     KERNEL_CHECK();
 }
 
-void token_self_attention(cudaStream_t s, float const* q, float const* k, float const* v, int P, float* out) {
-    ProfScope prof(s, CAT_DEC_ATTN);
-    token_self_attention_kernel<<<P, 256, 0, s>>>(q, k, v, out);
-    KERNEL_CHECK();
-}
-
+#if DLIMG_B200_ALT
 void image_to_token_attention(cudaStream_t s, act_t const* Q, act_t const* const* Qptrs, int64_t q_prompt_stride, int q_pitch,
                               int q_off, float const* kt, float const* vt, int P, act_t* out) {
     ProfScope prof(s, CAT_DEC_ATTN, 4.0 * P * kTokens * kImgTokens * 128, (double)P * kImgTokens * 128 * 4);
@@ -471,37 +255,7 @@ void image_to_token_attention(cudaStream_t s, act_t const* Q, act_t const* const
     i2t_attention_kernel<<<grid, 256, 0, s>>>(Q, Qptrs, q_prompt_stride, q_pitch, q_off, kt, vt, out);
     KERNEL_CHECK();
 }
-
-void layernorm256_img(cudaStream_t s, act_t const* x, act_t const* res, act_t const* const* res_ptrs, int P, float const* gamma,
-                      float const* beta, act_t* out) {
-    int64_t const rows = (int64_t)P * kImgTokens;
-    ProfScope prof(s, CAT_DEC_NORM, 0, (double)rows * kDim * 6);
-    layernorm256_img_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, s>>>(x, res, res_ptrs, rows, gamma, beta, out);
-    KERNEL_CHECK();
-}
-
-void layernorm256(cudaStream_t s, float const* x, float const* res, int64_t res_mod, int64_t rows, float const* gamma,
-                  float const* beta, float const* pos, int64_t pos_mod, float* out, float* out2) {
-    ProfScope prof(s, CAT_DEC_NORM);
-    if (res_mod <= 0) res_mod = rows;
-    if (pos_mod <= 0) pos_mod = rows;
-    layernorm256_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, s>>>(x, res, res_mod, rows, gamma, beta, pos, pos_mod, out,
-                                                                     out2);
-    KERNEL_CHECK();
-}
-
-void layernorm64_gelu(cudaStream_t s, act_t* x, int64_t rows, float const* gamma, float const* beta) {
-    ProfScope prof(s, CAT_DEC_NORM, 0, (double)rows * 64 * 4);
-    layernorm64_gelu_kernel<<<(unsigned)ceil_div64(rows, 32), 256, 0, s>>>(x, rows, gamma, beta);
-    KERNEL_CHECK();
-}
-
-void mask_dot(cudaStream_t s, float const* hyper, act_t const* up2, int P, float* low) {
-    ProfScope prof(s, CAT_DEC_MISC, 2.0 * P * 65536 * 128, (double)P * (16384.0 * 128 * 2 + 4 * 65536 * 4));
-    dim3 grid(65536 / 256, P);
-    mask_dot_kernel<<<grid, 256, 0, s>>>(hyper, up2, low);
-    KERNEL_CHECK();
-}
+#endif
 
 void f32_to_act(cudaStream_t s, float const* in, int64_t n, act_t* out) {
     ProfScope prof(s, CAT_DEC_MISC);

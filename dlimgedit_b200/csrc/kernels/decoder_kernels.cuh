@@ -37,9 +37,6 @@ void dense_pe(cudaStream_t s, float const* gaussian, float* pos);
 void linear_small(cudaStream_t s, float const* x, int64_t x_stride, float const* x2, int64_t x2_stride, int rows, int K,
                   float const* W, float const* b, int N, bool relu, float* y, int64_t y_stride);
 
-// Token self-attention: q, k, v (P, 7, 256) already projected; 8 heads x 32 -> out (P, 7, 256).
-void token_self_attention(cudaStream_t s, float const* q, float const* k, float const* v, int P, float* out);
-
 // Token -> image attention core: q (P, 7, 128) fp32; K and V rows of the image stream in 16 bits: row i of prompt p at
 // base_p + i * pitch (K) and base_p + v_off + i * pitch (V), where base_p = ptrs[p] (per-prompt tables, layer 0: the
 // image's prompt-independent projections) or base + p * prompt_stride; 8 heads x 16 -> out (P, 7, 128) fp32.
@@ -52,8 +49,10 @@ void token_to_image_attention(cudaStream_t s, float const* q, act_t const* base,
 
 // Image -> token attention core: Q rows (16-bit, 128 wide) of prompt p at Qp + q_off + i * q_pitch, Qp = Qptrs[p] or
 // Q + p * q_prompt_stride; kt, vt (P, 7, 128) fp32 -> out (P, 4096, 128) 16-bit.
+#if DLIMG_B200_ALT  // CUDA-core cross-check form (development builds)
 void image_to_token_attention(cudaStream_t s, act_t const* Q, act_t const* const* Qptrs, int64_t q_prompt_stride, int q_pitch,
                               int q_off, float const* kt, float const* vt, int P, act_t* out);
+#endif
 
 // The same on tensor cores (mma.sync, t2i_attention.cu); DLIMG_B200_I2T_SIMT selects the CUDA-core form above.
 void image_to_token_attention_mma(cudaStream_t s, act_t const* Q, act_t const* const* Qptrs, int64_t q_prompt_stride, int q_pitch,
@@ -61,24 +60,6 @@ void image_to_token_attention_mma(cudaStream_t s, act_t const* Q, act_t const* c
 
 // fp32 -> 16-bit storage (load-time tables).
 void f32_to_act(cudaStream_t s, float const* in, int64_t n, act_t* out);
-
-// Image stream: out = LayerNorm_256(x + res) (eps 1e-5) on 16-bit rows, P * 4096 of them; the residual rows of prompt p
-// are res_ptrs[p] (4096, 256) or res + p * 4096 * 256.  out == res is allowed.
-void layernorm256_img(cudaStream_t s, act_t const* x, act_t const* res, act_t const* const* res_ptrs, int P, float const* gamma,
-                      float const* beta, act_t* out);
-
-// out = LayerNorm_256(x + res) (eps 1e-5); optionally out2 = out + pos.  res row = row % res_mod, pos row =
-// row % pos_mod.  res / pos / out2 may be null.  In-place (out == x) is allowed.
-void layernorm256(cudaStream_t s, float const* x, float const* res, int64_t res_mod, int64_t rows, float const* gamma,
-                  float const* beta, float const* pos, int64_t pos_mod, float* out, float* out2);
-
-// In-place LayerNorm2d over groups of 64 channels (eps 1e-6) followed by exact GELU; 16-bit rows of 64.
-void layernorm64_gelu(cudaStream_t s, act_t* x, int64_t rows, float const* gamma, float const* beta);
-
-// low[p, m, Y, X] = sum_c hyper[p, m, c] * up2[p, blocked(Y, X), c]  (m = 0..3), where up2 (16-bit) is the blocked
-// output of the two transposed convolutions: row ((y*64+x)*4 + dy*2+dx), col (ey*2+ex)*32 + c, with
-// Y = 4y + 2dy + ey, X = 4x + 2dx + ex.
-void mask_dot(cudaStream_t s, float const* hyper, act_t const* up2, int P, float* low);
 
 // IoU head (slot 0, on token 0, 256 -> 256 -> 256 -> 4) and the four hypernetwork MLPs (slots 1..4, on mask tokens 1..4,
 // 256 -> 256 -> 256 -> 32), ReLU between layers: tokens (P, 7, 256) -> iou (P, 4), hyper (P, 4, 32).

@@ -30,6 +30,7 @@ __device__ __forceinline__ uint4 pack8(float const (&f)[8]) {
     return v;
 }
 
+#if DLIMG_B200_ALT  // unfused PatchEmbed conv1 and im2col: cross-check forms of patch_embed.cu / the implicit-GEMM neck conv
 // ---------------------------------------------------------------------------------------------
 struct Conv1Params {
     int w, h, bpp;
@@ -124,6 +125,8 @@ __global__ void im2col3x3_kernel(act_t const* __restrict__ in, int H, int W, int
         v = reinterpret_cast<uint4 const*>(in)[(((int64_t)b * H + iy) * W + ix) * C8 + c8];
     reinterpret_cast<uint4*>(out)[t] = v;  // t == (r*9 + tap)*C8 + c8
 }
+
+#endif  // DLIMG_B200_ALT
 
 // ---------------------------------------------------------------------------------------------
 // Depthwise 3x3.  Each thread produces kTX horizontally adjacent outputs for 8 channels: the filter taps are
@@ -631,6 +634,7 @@ __global__ void act_to_f32_kernel(act_t const* __restrict__ in, int64_t n, float
 
 }  // namespace
 
+#if DLIMG_B200_ALT
 // ---------------------------------------------------------------------------------------------
 void conv1_preprocess(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h, int channels,
                       float const* weight, float const* bias, act_t* out) {
@@ -654,13 +658,15 @@ void im2col3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, 
     KERNEL_CHECK();
 }
 
+#endif  // DLIMG_B200_ALT
+
 namespace {
 template <int kStride, int kC8>
 void launch_dwconv(cudaStream_t s, dim3 grid, act_t const* in, int H, int W, int Ho, int Wo, int xgroups, float const* weight,
                    act_t const* weight16, float const* bias, bool gelu, act_t* out) {
     constexpr int kTX = 4;
 #if !defined(DLIMG_B200_ACT_BF16)
-    static bool const acc32 = std::getenv("DLIMG_B200_DW_ACC32") != nullptr;  // A/B switch for parity experiments
+    static bool const acc32 = dev_switch("DLIMG_B200_DW_ACC32");  // A/B switch for parity experiments
     if (weight16 && !acc32) {
         launch_pdl(PDL_DWCONV, dwconv3x3_kernel<kStride, kTX, kC8, DwAccH2<kTX>, act_t>, grid, dim3(256), 0, s, in, H, W, Ho, Wo, xgroups, weight16, bias, gelu ? 1 : 0, out);
         return;

@@ -24,8 +24,10 @@ struct ImageDesc {
 // PatchEmbed conv 3x3 s2 p1 (3->32, BN folded) + GELU.  Reads the u8 image once, writes bf16
 // (B, 512, 512, 32).  `w`,`h` is the valid (already <= 1024) extent; weight layout [27][32] (tap-major,
 // tap = (ky*3+kx)*3+ci), bias [32].
+#if DLIMG_B200_ALT  // development / bf16 builds only (common.hpp)
 void conv1_preprocess(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h, int channels,
                       float const* weight, float const* bias, act_t* out);
+#endif
 
 // The whole PatchEmbed in one kernel (patch_embed.cu): preprocess + conv1 + GELU + conv2 -> out (B, 256, 256, 64).
 // w1_frag: conv1 weights from patch_embed_w1_fragments(); w2_map: TMA descriptor of the conv2 weights as a K-major
@@ -43,7 +45,9 @@ void mbconv_tail(cudaStream_t s, CUtensorMap const& expanded_map, int batch, act
                  CUtensorMap const& w3_map, float const* b3, act_t const* shortcut, act_t* out, int num_sms);
 
 // im2col for 3x3 / pad 1 convolutions on NHWC bf16: out[(b,oy,ox)][(ky,kx,c)] (K = 9*C).
+#if DLIMG_B200_ALT
 void im2col3x3(cudaStream_t s, act_t const* in, int batch, int H, int W, int C, int stride, act_t* out);
+#endif
 
 // Depthwise 3x3 / pad 1, NHWC 16-bit, fp32 weights [9][C] + bias [C] (BN folded), optional GELU.  weight16 (optional):
 // the same filter in act_t; with fp16 storage the GELU'd convolutions then run in packed-half arithmetic.

@@ -1463,11 +1463,11 @@ void launch_impl(cudaStream_t stream, bool tf32, Operand const& a, Operand const
                        (double)(ep.out_f32 ? 4 : 2) * M * N * (ep.residual ? 2.0 : 1.0));
     int const grid = tiles < num_sms ? tiles : num_sms;
     // plain 16-bit outputs go through the coalescing (staged) epilogue; residual / scatter / fp32 outputs store directly
-    static bool const allow_staged = !std::getenv("DLIMG_B200_GEMM_DIRECT");  // A/B switch
-    static bool const allow_staged_res = !std::getenv("DLIMG_B200_GEMM_DIRECT_RESIDUAL");  // A/B switch
+    static bool const allow_staged = !dev_switch("DLIMG_B200_GEMM_DIRECT");  // A/B switch
+    static bool const allow_staged_res = !dev_switch("DLIMG_B200_GEMM_DIRECT_RESIDUAL");  // A/B switch
     bool const res_ok = !(ep.residual || ep.res_table) || (allow_staged_res && ep.act == ACT_NONE && !ep.ln_stats);
     if (ep.res_mod) DLIMG_ASSERT((ep.residual || ep.res_table) && ep.res_mod % kBlockM == 0 && M % ep.res_mod == 0);
-    static bool const allow_staged_f32 = !std::getenv("DLIMG_B200_GEMM_DIRECT_F32");  // A/B switch
+    static bool const allow_staged_f32 = !dev_switch("DLIMG_B200_GEMM_DIRECT_F32");  // A/B switch
     bool const staged_f32 = allow_staged && allow_staged_f32 && tf32 && ep.out_f32 && !ep.residual && !ep.row_map && !ep.stats_out &&
                             !ep.ln_stats && block_n >= 64 && N <= 2048;
     bool const staged = staged_f32 ||

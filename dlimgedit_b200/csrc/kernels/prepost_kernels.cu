@@ -876,10 +876,9 @@ void launch_mask_post(cudaStream_t s, float const* low_res, int64_t plane_stride
 // Tile shape for the single-kernel resize: the largest candidate whose shared-memory need fits the budget.
 ResizeTile plan_resize_tile(ResizeDeviceTables const& t, int bpp, int kt, int out_w, int out_h) {
     static int const kRowsCand[] = {32, 16, 8, 4, 2, 1};
-    static int64_t const budget = [] {  // tile height vs blocks per SM (development switch)
-        char const* e = std::getenv("DLIMG_B200_RESIZE_SMEM_KB");
-        return (int64_t)std::min(std::max(e ? std::atoi(e) : 64, 16), 200) * 1024;
-    }();
+    // tile height vs blocks per SM: 64 KB = 16-row tiles at 4K -> 1024, three blocks per SM (100 KB: 156 us, 48 KB: 114 / 129 us
+    // for RGB / BGRA against 122 / 109 us, profiles/r02_summary.md)
+    static int64_t const budget = (int64_t)std::min(std::max(dev_int("DLIMG_B200_RESIZE_SMEM_KB", 64), 16), 200) * 1024;
     // tall, narrow tiles: two row groups of tc * bpp H-pass columns fill the 256 threads (120 / 128 columns each)
     int const tc_full = bpp == 3 ? 40 : 128 / bpp;
     ResizeTile best;

@@ -27,6 +27,7 @@ __device__ __forceinline__ float4 load4(act_t const* p) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+#if DLIMG_B200_ALT  // CUDA-core form: the bf16 build and the cross-check of t2i_mma_kernel
 __global__ void __launch_bounds__(kWarps * 32) t2i_flash_kernel(float const* __restrict__ q, act_t const* __restrict__ base,
                                                                 act_t const* const* __restrict__ ptrs, int64_t prompt_stride,
                                                                 int pitch, int v_off, float* __restrict__ part) {
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(kWarps * 32) t2i_flash_kernel(float const* __r
         }
     }
 }
+#endif
 
 // ---- tensor-core form ----------------------------------------------------------------------------------------------
 // The same partials from warp-level MMAs (mma.sync m16n8k16, fp16 operands, fp32 accumulators) -- the CUDA-core kernel
@@ -391,9 +393,12 @@ void token_to_image_attention(cudaStream_t s, float const* q, act_t const* base,
 #if defined(DLIMG_B200_ACT_BF16)
         t2i_flash_kernel<<<dim3(P, kT2iSplits), kWarps * 32, 0, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
 #else
-        static bool const cuda_core = std::getenv("DLIMG_B200_T2I_SIMT") != nullptr;  // cross-check: the CUDA-core form
+#if DLIMG_B200_ALT
+        static bool const cuda_core = dev_switch("DLIMG_B200_T2I_SIMT");  // cross-check: the CUDA-core form
         if (cuda_core) t2i_flash_kernel<<<dim3(P, kT2iSplits), kWarps * 32, 0, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
-        else t2i_mma_kernel<<<dim3(P, kT2iSplits), kWarps * 32, kT2iSmem, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
+        else
+#endif
+            t2i_mma_kernel<<<dim3(P, kT2iSplits), kWarps * 32, kT2iSmem, s>>>(q, base, ptrs, prompt_stride, pitch, v_off, scratch);
 #endif
         KERNEL_CHECK();
     }
@@ -408,11 +413,13 @@ void image_to_token_attention_mma(cudaStream_t s, act_t const* Q, act_t const* c
 #if defined(DLIMG_B200_ACT_BF16)
     image_to_token_attention(s, Q, Qptrs, q_prompt_stride, q_pitch, q_off, kt, vt, P, out);
 #else
-    static bool const cuda_core = std::getenv("DLIMG_B200_I2T_SIMT") != nullptr;  // cross-check: the CUDA-core form
+#if DLIMG_B200_ALT
+    static bool const cuda_core = dev_switch("DLIMG_B200_I2T_SIMT");  // cross-check: the CUDA-core form
     if (cuda_core) {
         image_to_token_attention(s, Q, Qptrs, q_prompt_stride, q_pitch, q_off, kt, vt, P, out);
         return;
     }
+#endif
     ProfScope prof(s, CAT_DEC_ATTN, 4.0 * P * kTokens * kImgTokens * 128, (double)P * kImgTokens * 128 * 4);
     i2t_mma_kernel<<<dim3(kImgTokens / 128, P), 256, 0, s>>>(Q, Qptrs, q_prompt_stride, q_pitch, q_off, kt, vt, out);
     KERNEL_CHECK();

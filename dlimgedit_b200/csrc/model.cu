@@ -405,11 +405,13 @@ SamModel::SamModel(std::string const& weight_path, int num_sms) : num_sms_(num_s
 // ---------------------------------------------------------------------------------------------
 EncoderWorkspace::EncoderWorkspace(int mb) : max_batch(mb) {
     size_t const B = (size_t)mb;
+#if DLIMG_B200_ALT  // conv1 activation and im2col matrix of the unfused PatchEmbed / neck (17 + 38 MB per image)
     c1.allocate(B * 512 * 512 * 32);
     col.allocate(B * 65536 * 288);
+#endif
     xa.allocate(B * 65536 * 64);
     xb.allocate(B * 65536 * 64);
-    for (auto& b : big) b.allocate(B * 65536 * 256);
+    for (auto& b : big) b.allocate(B * 65536 * 256);  // expanded MBConv / qkv / attention-output sized scratch
     stats.allocate(B * 16384);
     stats_parts.allocate(B * 16384 * 2);
 }
@@ -487,14 +489,19 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
     // form: conv1, im2col, GEMM -- used to cross-check the fused kernel)
     act_t* x = ws.xa.get();
     act_t* y = ws.xb.get();
-    static bool const unfused_patch = kActBf16 || std::getenv("DLIMG_B200_UNFUSED_PATCH") != nullptr;
+#if DLIMG_B200_ALT
+    static bool const unfused_patch = kActBf16 || dev_switch("DLIMG_B200_UNFUSED_PATCH");
     if (unfused_patch) {
         enc::conv1_preprocess(s, images, batch, w, h, channels, enc_.conv1_w.get(), enc_.conv1_b.get(), ws.c1.get());
         tap_act(s, tap, "conv1", ws.c1.get(), (size_t)B * 512 * 512 * 32);
         enc::im2col3x3(s, ws.c1.get(), batch, 512, 512, 32, 2, ws.col.get());
         gemm16(s, ws.col.get(), B * 65536, enc_.conv2, x, ACT_NONE, nullptr);
-    } else {
+    } else
+#endif
+    {
         bool const want_c1 = tap && tap->name && std::strcmp(tap->name, "conv1") == 0;
+        // the (B, 512, 512, 32) conv1 activation only exists for this debug tap (eager path): 17 MB per image on demand
+        if (want_c1 && !ws.c1.get()) ws.c1.allocate((size_t)ws.max_batch * 512 * 512 * 32);
         enc::patch_embed(s, images, batch, w, h, channels, enc_.conv1_frag.get(), enc_.conv1_b.get(), enc_.conv2_map,
                          enc_.conv2.b.get(), x, want_c1 ? ws.c1.get() : nullptr, num_sms_);
         tap_act(s, tap, "conv1", ws.c1.get(), (size_t)B * 512 * 512 * 32);
@@ -503,7 +510,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
 
     // layer 0: MBConv x2: 1x1 expand + GELU (GEMM), then depthwise 3x3 + GELU + 1x1 project + shortcut + GELU in one
     // kernel (DLIMG_B200_UNFUSED_MBCONV=1 keeps the depthwise kernel + project GEMM, used to cross-check)
-    static bool const unfused_mbconv = kActBf16 || std::getenv("DLIMG_B200_UNFUSED_MBCONV") != nullptr;
+    static bool const unfused_mbconv = kActBf16 || dev_switch("DLIMG_B200_UNFUSED_MBCONV");
     for (int i = 0; i < 2; ++i) {
         MBConvW const& m = enc_.mb[i];
         gemm16(s, x, B * 65536, m.conv1, ws.big[0].get(), ACT_GELU, nullptr);
@@ -519,7 +526,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         tap_act(s, tap, i == 0 ? "mb0" : "mb1", x, (size_t)B * 65536 * 64);
     }
 
-    static bool const merge_stats = !kActBf16 && std::getenv("DLIMG_B200_LN_STATS_KERNEL") == nullptr;  // A/B switch
+    static bool const merge_stats = !kActBf16 && !dev_switch("DLIMG_B200_LN_STATS_KERNEL");  // A/B switch
     // conv3 of a PatchMerging block also leaves the LayerNorm row sums of its output for the qkv GEMM of the stage's
     // first block (same form as the fc2 / fused-MLP epilogues of the later blocks)
     auto merge = [&](MergeW const& m, int res, char const* name) {
@@ -541,8 +548,8 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
         int const rows = (int)(B * L);
         float2* stats = ws.stats.get();
         int const fc2_parts = C / gemm::pick_block_n(C);  // N tiles of fc2 = partial sums per row
-        static bool const fused_mlp = std::getenv("DLIMG_B200_UNFUSED_MLP") == nullptr;
-        static bool const lc_tma = !kActBf16 && std::getenv("DLIMG_B200_LOCAL_CONV_REG") == nullptr;  // A/B switch
+        static bool const fused_mlp = !dev_switch("DLIMG_B200_UNFUSED_MLP");
+        static bool const lc_tma = !kActBf16 && !dev_switch("DLIMG_B200_LOCAL_CONV_REG");  // A/B switch
         for (int i = 0; i < c.depth; ++i) {
             BlockW const& b = enc_.blocks[st - 1][(size_t)i];
             std::string const tn = "s" + std::to_string(st) + "b" + std::to_string(i);
@@ -594,11 +601,14 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
     enc::layernorm_rows(s, ws.big[0].get(), (int)(B * 4096), 256, nullptr, enc_.neck_ln1.g.get(), enc_.neck_ln1.b.get(), 1e-6f,
                         ws.big[1].get(), false);
     tap_act(s, tap, "neck1", ws.big[1].get(), (size_t)B * 4096 * 256);
-    static bool const neck_im2col = kActBf16 || std::getenv("DLIMG_B200_NECK_IM2COL") != nullptr;  // A/B switch
+#if DLIMG_B200_ALT
+    static bool const neck_im2col = kActBf16 || dev_switch("DLIMG_B200_NECK_IM2COL");  // A/B switch
     if (neck_im2col) {
         enc::im2col3x3(s, ws.big[1].get(), batch, 64, 64, 256, 1, ws.col.get());
         gemm16(s, ws.col.get(), B * 4096, enc_.neck2, ws.big[0].get(), ACT_NONE, nullptr);
-    } else {  // implicit GEMM: shifted 4D TMA boxes of the NHWC activation are the A operand
+    } else
+#endif
+    {  // implicit GEMM: shifted 4D TMA boxes of the NHWC activation are the A operand
         gemm::Epilogue e;
         e.bias = enc_.neck2.b.get();
         e.ldc = enc_.neck2.n;

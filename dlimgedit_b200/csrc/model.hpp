@@ -143,7 +143,8 @@ struct DecoderW {
 // ---- workspaces -------------------------------------------------------------------------------
 struct EncoderWorkspace {
     int max_batch = 0;
-    DeviceBuffer<act_t> c1, col, xa, xb, big[4];
+    DeviceBuffer<act_t> c1, col;       // development builds / the conv1 debug tap only
+    DeviceBuffer<act_t> xa, xb, big[3];
     DeviceBuffer<float2> stats;    // (max_batch * 16384): per-token LayerNorm (mean, rstd) of the current block input
     DeviceBuffer<float2> stats_parts;  // (max_batch * 16384 * 2): partial (sum, sum of squares) written by fc2's epilogue
     explicit EncoderWorkspace(int max_batch);
