@@ -549,6 +549,21 @@ __device__ __forceinline__ uint32_t pack_sign4(float const* v) {
     return d;
 }
 
+// Packed fp32 pairs (one instruction for two lanes of arithmetic; per-lane rounding identical to the scalar forms the
+// compiler emitted for  l0 * a + l1 * b:  t = l1 * b  rounded,  result = fma(l0, a, t)).
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d)) : "l"(reinterpret_cast<uint64_t const&>(a)), "l"(reinterpret_cast<uint64_t const&>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<uint64_t const&>(a)), "l"(reinterpret_cast<uint64_t const&>(b)), "l"(reinterpret_cast<uint64_t const&>(c)));
+    return d;
+}
+
 // Identity case: the resized extent equals the output extent (long side == 1024), so the second bilinear has weights
 // 1 / 0 and output pixel (y, x) is the thresholded 256 -> 1024 interpolation itself.  A thread owns 8 neighbouring
 // columns (two low-resolution cells) of an 8-row strip.  The half-pixel interpolation is periodic -- output column
@@ -585,27 +600,32 @@ __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __
     bool const left = x0 == 0, top = ys == 0;
     float const xa0 = left ? 0.f : 0.375f, xb0 = left ? 1.f : 0.625f, xa1 = left ? 0.f : 0.125f, xb1 = left ? 1.f : 0.875f;
     float const ya0 = top ? 0.f : 0.375f, yb0 = top ? 1.f : 0.625f, ya1 = top ? 0.f : 0.125f, yb1 = top ? 1.f : 0.875f;
-    auto hrow = [&](float const (&q)[4], float (&o)[8]) {
-        o[0] = xa0 * q[0] + xb0 * q[1];
-        o[1] = xa1 * q[0] + xb1 * q[1];
-        o[2] = 0.875f * q[1] + 0.125f * q[2];
-        o[3] = 0.625f * q[1] + 0.375f * q[2];
-        o[4] = 0.375f * q[1] + 0.625f * q[2];
-        o[5] = 0.125f * q[1] + 0.875f * q[2];
-        o[6] = 0.875f * q[2] + 0.125f * q[3];
-        o[7] = 0.625f * q[2] + 0.375f * q[3];
+    // two neighbouring columns per instruction (mul2 / fma2): o = wa * q[j] + wb * q[j + 1] with per-column weights
+    float2 const wa01 = make_float2(xa0, xa1), wb01 = make_float2(xb0, xb1);
+    float2 const wa23 = make_float2(0.875f, 0.625f), wb23 = make_float2(0.125f, 0.375f);
+    float2 const wa45 = make_float2(0.375f, 0.125f), wb45 = make_float2(0.625f, 0.875f);
+    auto hrow = [&](float const (&q)[4], float2 (&o)[4]) {
+        float2 const q0 = make_float2(q[0], q[0]), q1 = make_float2(q[1], q[1]), q2 = make_float2(q[2], q[2]), q3 = make_float2(q[3], q[3]);
+        o[0] = fma2(wa01, q0, mul2(wb01, q1));
+        o[1] = fma2(wa23, q1, mul2(wb23, q2));
+        o[2] = fma2(wa45, q1, mul2(wb45, q2));
+        o[3] = fma2(wa23, q2, mul2(wb23, q3));
     };
-    float ha[8], hb[8];
+    float2 ha[4], hb[4];
     auto emit = [&](int t, float l0, float l1) {
         if (t >= rows_valid) return;
-        float v[8];
+        float2 const l0p = make_float2(l0 * kSignScale, l0 * kSignScale), l1p = make_float2(l1 * kSignScale, l1 * kSignScale);  // exact scaling: pack_sign4
+        float2 v2[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (l0 * kSignScale) * ha[e] + (l1 * kSignScale) * hb[e];  // exact scaling: pack_sign4
+        for (int e = 0; e < 4; ++e) v2[e] = fma2(l0p, ha[e], mul2(l1p, hb[e]));
+        float const* v = reinterpret_cast<float const*>(v2);
         uint8_t* d = dst + (size_t)t * w;
         if (word_ok) {
             *reinterpret_cast<uint2*>(d) = make_uint2(pack_sign4(v), pack_sign4(v + 4));
         } else {
-            for (int e = 0; e < 8 && x0 + e < w; ++e) d[e] = v[e] > 0.f ? 255 : 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (x0 + e < w) d[e] = v[e] > 0.f ? 255 : 0;
         }
     };
     // rows ys .. ys+7 blend low-resolution rows (i-1, i) for t = 0, 1; (i, i+1) for t = 2..5; (i+1, i+2) for t = 6, 7
@@ -614,14 +634,14 @@ __global__ void __launch_bounds__(256) mask_post_identity_kernel(float const* __
     emit(0, ya0, yb0);
     emit(1, ya1, yb1);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) ha[e] = hb[e];
+    for (int e = 0; e < 4; ++e) ha[e] = hb[e];
     hrow(a[2], hb);
     emit(2, 0.875f, 0.125f);
     emit(3, 0.625f, 0.375f);
     emit(4, 0.375f, 0.625f);
     emit(5, 0.125f, 0.875f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) ha[e] = hb[e];
+    for (int e = 0; e < 4; ++e) ha[e] = hb[e];
     hrow(a[3], hb);
     emit(6, 0.875f, 0.125f);
     emit(7, 0.625f, 0.375f);
@@ -731,18 +751,21 @@ __global__ void __launch_bounds__(256, PX >= 16 ? 2 : 3) mask_post_tile_kernel(f
             off[e] = grid_s + 4u * (uint32_t)lx.i0;
             l1[e] = lx.l1;
         }
-        auto hrow = [&](int slot, float (&o)[PX]) {
+        auto hrow = [&](int slot, float2 (&o)[PX / 2]) {
             uint32_t const row_off = (uint32_t)slot * (kGridPitch * 4);
 #pragma unroll
-            for (int e = 0; e < PX; ++e) {
-                float r0, r1;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r0) : "r"(off[e] + row_off));
-                asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(r1) : "r"(off[e] + row_off));
-                o[e] = (1.0f - l1[e]) * r0 + l1[e] * r1;
+            for (int e = 0; e < PX; e += 2) {
+                float2 r0, r1;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r0.x) : "r"(off[e] + row_off));
+                asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(r1.x) : "r"(off[e] + row_off));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r0.y) : "r"(off[e + 1] + row_off));
+                asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(r1.y) : "r"(off[e + 1] + row_off));
+                float2 const w1 = make_float2(l1[e], l1[e + 1]), w0 = make_float2(1.0f - l1[e], 1.0f - l1[e + 1]);
+                o[e / 2] = fma2(w0, r0, mul2(w1, r1));
             }
         };
         int ca = -1, cb = -1;
-        float ha[PX], hb[PX];
+        float2 ha[PX / 2], hb[PX / 2];
         uint8_t* dst = plane_out + (size_t)y0 * g.w + x0;
         bool const full = x0 + PX <= g.w;
 #pragma unroll 1
@@ -754,7 +777,7 @@ __global__ void __launch_bounds__(256, PX >= 16 ? 2 : 3) mask_post_tile_kernel(f
             if (a != ca) {
                 if (a == cb) {
 #pragma unroll
-                    for (int e = 0; e < PX; ++e) ha[e] = hb[e];
+                    for (int e = 0; e < PX / 2; ++e) ha[e] = hb[e];
                 } else {
                     hrow(a, ha);
                 }
@@ -763,15 +786,17 @@ __global__ void __launch_bounds__(256, PX >= 16 ? 2 : 3) mask_post_tile_kernel(f
             if (b != cb) {
                 if (b == ca) {
 #pragma unroll
-                    for (int e = 0; e < PX; ++e) hb[e] = ha[e];
+                    for (int e = 0; e < PX / 2; ++e) hb[e] = ha[e];
                 } else {
                     hrow(b, hb);
                 }
                 cb = b;
             }
-            float v[PX];
+            float2 v2[PX / 2];
+            float2 const q0p = make_float2(q0, q0), q1p = make_float2(q1, q1);
 #pragma unroll
-            for (int e = 0; e < PX; ++e) v[e] = q0 * ha[e] + q1 * hb[e];
+            for (int e = 0; e < PX / 2; ++e) v2[e] = fma2(q0p, ha[e], mul2(q1p, hb[e]));
+            float const* v = reinterpret_cast<float const*>(v2);
             if (full && vec_ok) {
                 *reinterpret_cast<uint4*>(dst) = make_uint4(pack_sign4(v), pack_sign4(v + 4), pack_sign4(v + (PX > 8 ? 8 : 0)),
                                                             pack_sign4(v + (PX > 8 ? 12 : 0)));
