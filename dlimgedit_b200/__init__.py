@@ -137,6 +137,7 @@ class _Ext(ctypes.Structure):
         ("profile_enable", _F(_R, _H, ctypes.c_int)),
         ("profile_read", _F(_R, _H, ctypes.POINTER(_ProfileEntry), ctypes.c_int, c_i32p)),
         ("get_embedding_async", _F(_R, _H, c_f32p)),
+        ("get_embedding_f16_async", _F(_R, _H, ctypes.c_void_p)),
     ]
 
 
@@ -414,6 +415,11 @@ class Segmentation:
         """Queues the embedding read into `out` (page-locked, 256*64*64 float32); complete after Environment.synchronize()."""
         assert out.dtype == np.float32 and out.size == 256 * 64 * 64 and out.flags["C_CONTIGUOUS"]
         _check(ext().get_embedding_async(self._h, out.ctypes.data_as(c_f32p)))
+
+    def embedding_f16_async(self, out: np.ndarray) -> None:
+        """The same as half precision: `out` is page-locked, 256*64*64 float16; complete after Environment.synchronize()."""
+        assert out.dtype == np.float16 and out.size == 256 * 64 * 64 and out.flags["C_CONTIGUOUS"]
+        _check(ext().get_embedding_f16_async(self._h, out.ctypes.data))
 
     def low_res_logits(self, prompt) -> Tuple[np.ndarray, np.ndarray]:
         logits = np.empty((4, 256, 256), np.float32)

@@ -148,6 +148,10 @@ dlimg_Result ext_get_embedding_async(dlimg_Segmentation seg, float* out_host) {
     return try_([=] { to_impl(seg).embedding_nchw_async(out_host); });
 }
 
+dlimg_Result ext_get_embedding_f16_async(dlimg_Segmentation seg, uint16_t* out_host) {
+    return try_([=] { to_impl(seg).embedding_nchw_f16_async(out_host); });
+}
+
 dlimg_Result ext_get_low_res_logits(dlimg_Segmentation seg, dlimg_b200_Prompt const* prompt, float* logits, float* iou) {
     return try_([=] { to_impl(seg).environment().low_res_logits(to_impl(seg), *prompt, logits, iou); });
 }
@@ -352,7 +356,7 @@ DLIMG_B200_EXPORT dlimg_Api const* dlimg_init(void) {
 DLIMG_B200_EXPORT dlimg_b200_Ext const* dlimg_b200_ext_init(void) {
     using namespace dlimg;
     ext_.struct_size = sizeof(dlimg_b200_Ext);
-    ext_.abi_version = 2;
+    ext_.abi_version = 3;
     ext_.set_stream = ext_set_stream;
     ext_.synchronize = ext_synchronize;
     ext_.get_stats = ext_get_stats;
@@ -367,6 +371,7 @@ DLIMG_B200_EXPORT dlimg_b200_Ext const* dlimg_b200_ext_init(void) {
     ext_.profile_enable = ext_profile_enable;
     ext_.profile_read = ext_profile_read;
     ext_.get_embedding_async = ext_get_embedding_async;
+    ext_.get_embedding_f16_async = ext_get_embedding_f16_async;
     return &ext_;
 }
 

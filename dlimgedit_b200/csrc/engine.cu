@@ -746,6 +746,26 @@ void SegmentationImpl::embedding_nchw_async(float* out_host) {
     env_.counters_.d2h_bytes += kEmbFloats * sizeof(float);
 }
 
+void SegmentationImpl::embedding_nchw_f16_async(uint16_t* out_host) {
+#if defined(DLIMG_B200_ACT_BF16)
+    (void)out_host;
+    fail("get_embedding_f16_async: this build stores bf16");
+#else
+    std::lock_guard<std::mutex> lock(env_.mutex());
+    EnvironmentImpl::Scope scope(env_);
+    if (!encoded()) fail("segmentation handle holds no processed image");
+    cudaStream_t const cs = env_.copy_out_;
+    CUDA_CHECK(cudaStreamWaitEvent(cs, store_->ready(), 0));
+    void* tmp = nullptr;  // stream-ordered scratch: conversion, copy and free are all queued on the copy-out stream
+    CUDA_CHECK(cudaMallocAsync(&tmp, kEmbFloats * sizeof(act_t), cs));
+    dec::f32_to_act(cs, emb_nchw_, (int64_t)kEmbFloats, static_cast<act_t*>(tmp));
+    CUDA_CHECK(cudaMemcpyAsync(out_host, tmp, kEmbFloats * sizeof(act_t), cudaMemcpyDeviceToHost, cs));
+    CUDA_CHECK(cudaFreeAsync(tmp, cs));
+    store_->mark_read(cs);
+    env_.counters_.d2h_bytes += kEmbFloats * sizeof(act_t);
+#endif
+}
+
 void SegmentationImpl::embedding_nchw(float* out_host) {
     embedding_nchw_async(out_host);
     CUDA_CHECK(cudaStreamSynchronize(env_.copy_out_));

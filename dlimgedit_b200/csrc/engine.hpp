@@ -182,6 +182,7 @@ class SegmentationImpl {
     void compute_mask(int const* point, int const* region, uint8_t** out_masks, float* out_accuracy);  // :131-174
     void embedding_nchw(float* out_host);        // blocking
     void embedding_nchw_async(float* out_host);  // returns at once; complete after EnvironmentImpl::synchronize()
+    void embedding_nchw_f16_async(uint16_t* out_host);  // the same as fp16 (converted on the copy-out stream)
 
     int width() const { return size_.orig_w; }
     int height() const { return size_.orig_h; }

@@ -193,6 +193,11 @@ struct dlimg_b200_Ext {
      * process_batch, whose host->device upload runs on a third stream).  out_host should be page-locked and must
      * stay valid until `synchronize` returns. */
     dlimg_Result (*get_embedding_async)(dlimg_Segmentation, float* out_host);
+
+    /* abi_version >= 3.  The same, as IEEE half precision: 256*64*64 uint16 values, half the bytes over PCIe (the
+     * embedding is converted on the device on its way out).  For callers that keep embeddings on the host and are bound
+     * by the download -- eight ranks on one host share its copy bandwidth. */
+    dlimg_Result (*get_embedding_f16_async)(dlimg_Segmentation, uint16_t* out_host);
 };
 
 DLIMG_B200_EXPORT struct dlimg_b200_Ext const* dlimg_b200_ext_init(void);

@@ -100,6 +100,10 @@ inline void get_embedding(Segmentation const& seg, float* out_host) { throw_on_e
 inline void get_embedding_async(Segmentation const& seg, float* out_host) {
     throw_on_error(ext().get_embedding_async(seg.handle(), out_host));
 }
+// half-precision download (256*64*64 uint16 values): complete after synchronize()
+inline void get_embedding_f16_async(Segmentation const& seg, uint16_t* out_host) {
+    throw_on_error(ext().get_embedding_f16_async(seg.handle(), out_host));
+}
 
 }  // namespace b200
 }  // namespace dlimg

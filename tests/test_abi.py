@@ -52,7 +52,7 @@ def test_table_layout_matches_reference_abi():
     api = dl.api()
     for name, _ in dl._Api._fields_:
         assert ctypes.cast(getattr(api, name), ctypes.c_void_p).value, name
-    assert dl.ext().abi_version == 2
+    assert dl.ext().abi_version == 3
 
 
 def test_backend_support_without_gpu():

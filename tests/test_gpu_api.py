@@ -108,6 +108,17 @@ def test_async_embedding_read_matches_blocking(env):
     assert not np.array_equal(outs[0].numpy(), outs[1].numpy())
 
 
+def test_half_precision_embedding_download(env):
+    """get_embedding_f16_async: the fp32 embedding rounded to IEEE half on the device, half the PCIe bytes."""
+    import torch
+    from conftest import synthetic_image
+    seg = env.process_batch([dl.ImageView(synthetic_image(1024, 1024, 4, seed=31), channels=dl.Channels.rgba)])[0]
+    h = torch.empty(1, 256, 64, 64, dtype=torch.float16).pin_memory()
+    seg.embedding_f16_async(h.numpy())
+    env.synchronize()
+    assert np.array_equal(h.numpy(), seg.embedding().astype(np.float16))  # round-to-nearest-even on both sides
+
+
 def test_async_host_masks_match_blocking(env):
     """masks_on_device = 2: host masks whose downloads overlap the following calls; complete after synchronize()."""
     import torch
