@@ -39,8 +39,9 @@ void patch_embed(cudaStream_t s, ImageDesc const* imgs, int batch, int w, int h,
 void patch_embed_w1_fragments(float const* w27x32, uint32_t* out512);
 
 // Second half of an MBConv block in one kernel (mbconv_tail.cu): depthwise 3x3 + GELU on the (B, 256, 256, 256) expanded
-// tensor (given as a TMA descriptor from gemm::make_tensor_map_nhwc, box 128 ch x 18 x 10), then 1x1 conv 256 -> 64 +
+// tensor (given as a TMA descriptor from gemm::make_tensor_map_nhwc, box mbconv_tail_unit_channels() ch x 18 x 10), then 1x1 conv 256 -> 64 +
 // shortcut + GELU.  w3_map: K-major (64, 256) project weights, box 64 rows.
+int mbconv_tail_unit_channels();  // channels of the TMA box of `expanded_map`: 64 (128 in a development A/B run)
 void mbconv_tail(cudaStream_t s, CUtensorMap const& expanded_map, int batch, act_t const* dw_w16, float const* dw_b,
                  CUtensorMap const& w3_map, float const* b3, act_t const* shortcut, act_t* out, int num_sms);
 

@@ -518,7 +518,7 @@ void SamModel::encode(cudaStream_t s, EncoderWorkspace& ws, enc::ImageDesc const
             enc::dwconv3x3(s, ws.big[0].get(), batch, 256, 256, 256, 1, m.conv2.w.get(), m.conv2.w16.get(), m.conv2.b.get(), true, ws.big[1].get());
             gemm16(s, ws.big[1].get(), B * 65536, m.conv3, y, ACT_GELU, x);
         } else {
-            CUtensorMap const in_map = gemm::make_tensor_map_nhwc(ws.big[0].get(), batch, 256, 256, 256, 128, 18, 10);
+            CUtensorMap const in_map = gemm::make_tensor_map_nhwc(ws.big[0].get(), batch, 256, 256, 256, enc::mbconv_tail_unit_channels(), 18, 10);
             CUtensorMap const w3_map = gemm::make_tensor_map(gemm::Operand{m.conv3.w.get(), 64, 256, 256}, false, 64);
             enc::mbconv_tail(s, in_map, batch, m.conv2.w16.get(), m.conv2.b.get(), w3_map, m.conv3.b.get(), x, y, num_sms_);
         }
