@@ -45,14 +45,13 @@ struct LcCfg {
     static constexpr int kSmemW = kSmemBar + 64;              // filter [9][C] fp32 + bias [C], C known at run time
 };
 
-__device__ __forceinline__ void unpack8h(uint4 const& v, float (&f)[8]) {
-    act2_t const* h = reinterpret_cast<act2_t const*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float2 const t = act22f2(h[i]);
-        f[2 * i] = t.x;
-        f[2 * i + 1] = t.y;
-    }
+// d = a * b + c on both lanes of a packed fp32 pair: one FFMA2, per-lane result identical to fmaf
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<uint64_t const&>(a)), "l"(reinterpret_cast<uint64_t const&>(b)), "l"(reinterpret_cast<uint64_t const&>(c)));
+    return d;
 }
 
 template <int kC8>
@@ -119,13 +118,13 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
         locate(u, b, oy0, ox0, pt);
         int const buf = u % kInBufs;
         float const* const w = wsm + (pt * kC8 + c8) * 4;  // tap k: halves at w + k * C and w + k * C + C / 2
-        float acc[4][8];
+        float2 acc2[4][4];  // [pixel][channel pair]: fp32 accumulation on packed pairs (FFMA2: half the FMA instructions)
         {
             float4 const b0 = *reinterpret_cast<float4 const*>(w + 9 * C), b1 = *reinterpret_cast<float4 const*>(w + 9 * C + (C >> 1));
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-                acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
-                acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+                acc2[o][0] = make_float2(b0.x, b0.y); acc2[o][1] = make_float2(b0.z, b0.w);
+                acc2[o][2] = make_float2(b1.x, b1.y); acc2[o][3] = make_float2(b1.z, b1.w);
             }
         }
         mbar_wait(bar + 8 * buf, ((uint32_t)(u / kInBufs)) & 1u);
@@ -151,18 +150,18 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
             }
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
-                float f[8];
-                unpack8h(v[c], f);
+                act2_t const* h = reinterpret_cast<act2_t const*>(&v[c]);
+                float2 const f0 = act22f2(h[0]), f1 = act22f2(h[1]), f2 = act22f2(h[2]), f3 = act22f2(h[3]);
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     int const o = c - kx;
                     if (o < 0 || o >= 4) continue;
                     float const* wk = w + (ky * 3 + kx) * C;
                     float4 const w0 = *reinterpret_cast<float4 const*>(wk), w1 = *reinterpret_cast<float4 const*>(wk + (C >> 1));
-                    acc[o][0] = fmaf(f[0], w0.x, acc[o][0]); acc[o][1] = fmaf(f[1], w0.y, acc[o][1]);
-                    acc[o][2] = fmaf(f[2], w0.z, acc[o][2]); acc[o][3] = fmaf(f[3], w0.w, acc[o][3]);
-                    acc[o][4] = fmaf(f[4], w1.x, acc[o][4]); acc[o][5] = fmaf(f[5], w1.y, acc[o][5]);
-                    acc[o][6] = fmaf(f[6], w1.z, acc[o][6]); acc[o][7] = fmaf(f[7], w1.w, acc[o][7]);
+                    acc2[o][0] = fma2(f0, make_float2(w0.x, w0.y), acc2[o][0]);
+                    acc2[o][1] = fma2(f1, make_float2(w0.z, w0.w), acc2[o][1]);
+                    acc2[o][2] = fma2(f2, make_float2(w1.x, w1.y), acc2[o][2]);
+                    acc2[o][3] = fma2(f3, make_float2(w1.z, w1.w), acc2[o][3]);
                 }
             }
         }
@@ -173,17 +172,18 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
         float2* const mypart = part + (u & 1) * (kTH * kTW * L::kPartPitch) + ((ty * kTW + xg * 4) * L::kPartPitch + c8);
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
+            float const* acc_o = reinterpret_cast<float const*>(acc2[o]);
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                s1 += acc[o][i];
-                s2 = fmaf(acc[o][i], acc[o][i], s2);
+                s1 += acc_o[i];
+                s2 = fmaf(acc_o[i], acc_o[i], s2);
             }
             mypart[o * L::kPartPitch] = make_float2(s1, s2);
             uint4 ov;
             act2_t* oh = reinterpret_cast<act2_t*>(&ov);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) oh[i] = f22act2(acc[o][2 * i], acc[o][2 * i + 1]);
+            for (int i = 0; i < 4; ++i) oh[i] = f22act2(acc2[o][i].x, acc2[o][i].y);
             orow[(size_t)o * (C / 8)] = ov;
         }
         // the partial sums of this row pair's 32 pixels are visible to its first warp
