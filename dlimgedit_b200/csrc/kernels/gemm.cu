@@ -686,31 +686,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // kRes (staged kernels with a 16-bit residual): the warp's 32 x (s_cnt * 32 B) piece of the residual is copied
         // into its staging area with cp.async as whole row segments -- one tile ahead, right after the staging area has
         // been drained -- so neither the residual reads nor the output writes touch partial 128-byte lines.
-        auto prefetch_residual = [&](int tile) {
+        // Tile coordinates are stepped, not divided: tile -> tile + gridDim.x is (mt + g_mt, nt + g_nt) with one carry.  The
+        // divisions by the run-time n_tiles (and lane / cpr below) were ~100 of the ~290 instructions a warp spends per tile
+        // in the folded-LayerNorm GEMM (profiles/r02_summary.md section 6).
+        int const g_mt = (int)gridDim.x / n_tiles, g_nt = (int)gridDim.x - g_mt * n_tiles;
+        auto step = [&](int& mt, int& nt) {
+            mt += g_mt;
+            nt += g_nt;
+            if (nt >= n_tiles) {
+                nt -= n_tiles;
+                ++mt;
+            }
+        };
+        int const res_cpr = 2 * s_cnt, res_rows_it = s_cnt ? 32 / res_cpr : 0;  // 16-byte pieces per row, rows per instruction
+        int const res_row0 = s_cnt ? lane / res_cpr : 0, res_chunk = lane - res_row0 * res_cpr;
+        auto prefetch_residual = [&](int mt, int nt) {
             if (s_cnt == 0 || (!ep.residual && !ep.res_table)) return;  // (the kernel also serves plain GEMMs that only want row sums)
-            int const m0 = (tile / n_tiles) * kBlockM + quarter * 32;
-            int const n0 = (tile % n_tiles) * block_n + s_first * 16;
+            int const m0 = mt * kBlockM + quarter * 32;
+            int const n0 = nt * block_n + s_first * 16;
             // res_mod: the residual is a (res_mod, N) table shared by every group of res_mod output rows (a multiple of
             // the tile height, so a tile never straddles two groups) -- the decoder's position terms
             int const r0 = ep.res_mod ? m0 % ep.res_mod : m0;
             act_t const* seg = (ep.res_table ? reinterpret_cast<act_t const*>(ep.res_table[m0 / ep.res_mod])
                                              : reinterpret_cast<act_t const*>(ep.residual)) + (int64_t)r0 * ep.ldc + n0;
-            int const cpr = 2 * s_cnt, rows_it = 32 / cpr;  // 16-byte pieces per row, rows per instruction
-            int const row0 = lane / cpr, chunk = lane - row0 * cpr;
             int const rows_valid = min(32, M - m0);
-            if (row0 < rows_it) {
-                for (int rr = row0; rr < rows_valid; rr += rows_it) {
-                    uint32_t const dst = my_stage + stage_offset(s_cnt, rr, chunk);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(seg + (int64_t)rr * ep.ldc + chunk * 8) : "memory");
+            if (res_row0 < res_rows_it) {
+                for (int rr = res_row0; rr < rows_valid; rr += res_rows_it) {
+                    uint32_t const dst = my_stage + stage_offset(s_cnt, rr, res_chunk);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(seg + (int64_t)rr * ep.ldc + res_chunk * 8) : "memory");
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        if (kRes && (int)blockIdx.x < total_tiles) prefetch_residual(blockIdx.x);
+        int cur_mt = (int)blockIdx.x / n_tiles, cur_nt = (int)blockIdx.x - cur_mt * n_tiles;  // coordinates of `tile` in the loop below
+        if (kRes && (int)blockIdx.x < total_tiles) prefetch_residual(cur_mt, cur_nt);
         // folded LayerNorm: (mean, rstd) of this lane's row (ln_parts == 0) or its (sum, sum of squares), the partial
         // sums of the producing kernel added in a fixed order
-        auto load_ln = [&](int tile) {
-            int const row = (tile / n_tiles) * kBlockM + quarter * 32 + lane;
+        auto load_ln = [&](int mt) {
+            int const row = mt * kBlockM + quarter * 32 + lane;
             float2 r = make_float2(0.f, 1.f);
             if (row < M) {
                 if (ep.ln_parts == 0) {
@@ -728,13 +741,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             return r;
         };
         float2 ln_next = make_float2(0.f, 1.f);
-        if (kStaged && kLn && (int)blockIdx.x < total_tiles) ln_next = load_ln(blockIdx.x);
+        if (kStaged && kLn && (int)blockIdx.x < total_tiles) ln_next = load_ln(cur_mt);
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int const acc = local & 1;
             uint32_t const acc_phase = (uint32_t)(local >> 1) & 1u;
-            int const m0 = (tile / n_tiles) * kBlockM;
-            int const n0 = (tile % n_tiles) * block_n;
+            int const m0 = cur_mt * kBlockM;
+            int const n0 = cur_nt * block_n;
+            int const this_nt = cur_nt;
+            step(cur_mt, cur_nt);  // from here on: the coordinates of the next tile of this CTA
+            bool const has_next = tile + (int)gridDim.x < total_tiles;
             int64_t orow = -1;
             float rstd = 1.f;  // folded LayerNorm: 1/std of this thread's row
             if (!kStaged) {
@@ -748,7 +764,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     float const inv_k = 1.0f / (float)K, mean = ln_next.x * inv_k;
                     rstd = rsqrtf(fmaxf(fmaf(-mean, mean, ln_next.y * inv_k), 0.f) + ep.ln_eps);
                 }
-                if (tile + (int)gridDim.x < total_tiles) ln_next = load_ln(tile + (int)gridDim.x);
+                if (has_next) ln_next = load_ln(cur_mt);
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -797,7 +813,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 float const mean = sx * (1.0f / 256.0f);
                 float const rstd = rsqrtf(fmaxf(sq * (1.0f / 256.0f) - mean * mean, 0.f) + ep.ln_eps);
                 ln_copy_out(cx, mean, rstd, bias_s + 4u * (uint32_t)N, bias_s + 8u * (uint32_t)N);
-                if (tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + (int)gridDim.x);
+                if (has_next) prefetch_residual(cur_mt, cur_nt);
                 continue;
             }
             switch (s_cnt) {  // warp-uniform
@@ -811,7 +827,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (lane == 0) mbar_arrive(tempty_bar(acc));
                     break;
             }
-            if (kRes && tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + (int)gridDim.x);
+            if (kRes && has_next) prefetch_residual(cur_mt, cur_nt);
             if ((!kStaged || kRes) && ep.stats_out) {
                 // row statistics of this tile: the four warps of a lane quarter hold pieces of the same 32 rows
                 uint32_t const red = stage_out + (uint32_t)(staging_bytes - bias_bytes - 8192 + (local & 1) * 4096);
@@ -828,7 +844,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         sx += a;
                         sq += b;
                     }
-                    ep.stats_out[(int64_t)row * n_tiles + (tile % n_tiles)] = make_float2(sx, sq);
+                    ep.stats_out[(int64_t)row * n_tiles + this_nt] = make_float2(sx, sq);
                 }
                 // the other buffer is used by the next tile; a warp can only reach the tile after that once every warp
                 // of its quarter (including the reader above) has passed the next tile's barrier
