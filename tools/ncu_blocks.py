@@ -15,7 +15,14 @@ for r in csv.reader(out.splitlines()):
         tables.append(cur)
     elif cur is not None:
         cur["rows"].append(r)
-t = tables[2 * want + 1]
+# one or two tables per launch (the second repeats the kernel name): take the last table of the wanted launch
+groups = []
+for tb in tables:
+    if groups and groups[-1][-1]["name"] == tb["name"] and len(groups[-1]) < 2:
+        groups[-1].append(tb)
+    else:
+        groups.append([tb])
+t = groups[want][-1]
 h = t["rows"][0]
 ie, src, sa = h.index("Instructions Executed"), h.index("Source"), h.index("# Samples")
 body = t["rows"][1:]

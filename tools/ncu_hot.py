@@ -14,7 +14,13 @@ for r in csv.reader(out.splitlines()):
         tables.append(cur)
     elif cur is not None:
         cur["rows"].append(r)
-t = tables[2 * want + (1 if "src" in sys.argv[3:] else 0)]  # two tables per launch: SASS, then source lines
+groups = []
+for tb in tables:  # one or two tables per launch (the second repeats the kernel name)
+    if groups and groups[-1][-1]["name"] == tb["name"] and len(groups[-1]) < 2:
+        groups[-1].append(tb)
+    else:
+        groups.append([tb])
+t = groups[want][-1 if "src" in sys.argv[3:] else 0]
 h = t["rows"][0]
 si, src = h.index("# Samples"), h.index("Source")
 body = [r for r in t["rows"][1:] if len(r) > si]
