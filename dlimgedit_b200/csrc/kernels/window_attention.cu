@@ -78,8 +78,8 @@ struct Cfg {
 // One chunk of kCnt key blocks (8 keys each) of the online softmax for one (head, query tile).
 template <int kCnt, bool kFirst, bool kBiasInSmem>
 __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4], uint32_t k_addr, uint32_t v_addr, int row_bytes,
-                                             uint32_t bias_addr, float4 const* __restrict__ bias_gl, float (&m)[2], float (&l)[2],
-                                             float (&o)[4][4]) {
+                                             uint32_t bias_addr, float4 const* __restrict__ bias_gl, float (&m)[2], float (&l)[4],
+                                             float (&o)[4][4], uint32_t ones_b) {
     float const kScale = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
     float s[kCnt][4];
     float cm0 = -INFINITY, cm1 = -INFINITY;
@@ -134,8 +134,8 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
         float const a0 = ex2((m[0] - n0) * (kBiasInSmem ? 1.0f : kScale)), a1 = ex2((m[1] - n1) * (kBiasInSmem ? 1.0f : kScale));
         m[0] = n0;
         m[1] = n1;
-        l[0] *= a0;
-        l[1] *= a1;
+        l[0] *= a0;  // (accumulator fragment of the ones column: rows g / g + 8 in elements 0 / 2 of the lanes with t == 0)
+        l[2] *= a1;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
             o[d][0] *= a0; o[d][1] *= a0;
@@ -156,8 +156,6 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
             s[j][2] = ex2(fmaf(s[j][2], kScale, e1));
             s[j][3] = ex2(fmaf(s[j][3], kScale, e1));
         }
-        l[0] += s[j][0] + s[j][1];
-        l[1] += s[j][2] + s[j][3];
     }
     // O += P V, 16 keys per step; an odd trailing key block pairs with zeros
 #pragma unroll
@@ -177,6 +175,9 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
         ldsm_x4_t(va + 32u, b0, b1, b2, b3);  // dims 16-23, 24-31
         mma16816(o[2], a0, a1, a2, a3, b0, b1);
         mma16816(o[3], a0, a1, a2, a3, b2, b3);
+        // row sums of P from the tensor core as well: a fifth B tile whose column 0 is all ones (the sums of the ROUNDED
+        // probabilities, i.e. exactly what the other four products were normalised with; four FADDs per key block less)
+        mma16816(l, a0, a1, a2, a3, ones_b, ones_b);
     }
 }
 
@@ -265,27 +266,25 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
         uint32_t aq[2][4];
         ldsm_x4(tile + q_off, aq[0][0], aq[0][1], aq[0][2], aq[0][3]);
         ldsm_x4(tile + q_off + 32u, aq[1][0], aq[1][1], aq[1][2], aq[1][3]);
-        float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+        float m[2] = {-INFINITY, -INFINITY}, l[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t const ones_b = g == 0 ? (kActBf16 ? 0x3f803f80u : 0x3c003c00u) : 0u;  // B fragment (k = keys 2t, 2t + 1; n = g): column 0 = 1.0
         float o[4][4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
         if constexpr (C::NK8 <= 8) {
-            attend_chunk<C::NK8, true, C::kBiasInSmem>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o);
+            attend_chunk<C::NK8, true, C::kBiasInSmem>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
         } else {
             static_assert(C::NK8 <= 8 || C::NK8 == 25, "chunk schedule written for 196-token windows");
             // 25 key blocks in chunks of 4 (+1): with the bias table in global memory the kernel runs two CTAs per SM
             // at 72 registers, and a 4-block chunk (16 score registers) is what fits without spilling
-            attend_chunk<4, true, C::kBiasInSmem>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o);
+            attend_chunk<4, true, C::kBiasInSmem>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
 #pragma unroll
             for (int c0 = 4; c0 < 24; c0 += 4)
-                attend_chunk<4, false, C::kBiasInSmem>(c0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o);
-            attend_chunk<1, false, C::kBiasInSmem>(24, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o);
+                attend_chunk<4, false, C::kBiasInSmem>(c0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
+            attend_chunk<1, false, C::kBiasInSmem>(24, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
         }
-        l[0] += __shfl_xor_sync(0xffffffffu, l[0], 1);
-        l[0] += __shfl_xor_sync(0xffffffffu, l[0], 2);
-        l[1] += __shfl_xor_sync(0xffffffffu, l[1], 1);
-        l[1] += __shfl_xor_sync(0xffffffffu, l[1], 2);
-        float const inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+        // the sums sit in the t == 0 lane of every quad
+        float const inv0 = 1.0f / __shfl_sync(0xffffffffu, l[0], lane & ~3), inv1 = 1.0f / __shfl_sync(0xffffffffu, l[2], lane & ~3);
         // O (16-bit) goes into this task's own Q slot of the tile; the CTA then writes whole token rows
         uint32_t const o_addr = tile + (uint32_t)((qt * 16 + g) * C::kRowBytes + (hh * 96 + 2 * t) * 2);
 #pragma unroll

@@ -133,7 +133,9 @@ struct dlimg_b200_Ext {
      * the environment's own stream).  Batch calls are asynchronous with respect to the host unless
      * stated otherwise; use `synchronize` or your own events on that stream.  Switching streams needs no
      * synchronisation by the caller: everything already queued on the old stream is ordered in front of
-     * whatever is submitted to the new one (event dependency), because workspaces and embeddings are shared. */
+     * whatever is submitted to the new one (event dependency), because workspaces and embeddings are shared.
+     * DEVICE buffers passed to any call below are read and written on that stream: the environment's own stream is
+     * non-blocking, so a caller that fills them on another stream shares it here or synchronises first. */
     dlimg_Result (*set_stream)(dlimg_Environment, void* cuda_stream);
     dlimg_Result (*synchronize)(dlimg_Environment); /* the work stream and the library's two copy streams */
     dlimg_Result (*get_stats)(dlimg_Environment, dlimg_b200_Stats*);

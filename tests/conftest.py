@@ -52,6 +52,11 @@ def model_dir(tmp_path_factory):
 def env(model_dir):
     import dlimgedit_b200 as dl
     e = dl.Environment(dl.Options(dl.Backend.gpu, model_dir))
+    # The tests hand the library device tensors that torch has just filled on ITS stream; the library's own stream is
+    # non-blocking, so without this a kernel could run before (or under) a pending torch.zeros / .cuda() of its operands
+    # (seen once as ~2000 cleared mask pixels).  Same contract as for any caller: share a stream or synchronize.
+    import torch
+    e.set_stream(torch.cuda.current_stream().cuda_stream)
     yield e
     e.close()
 
