@@ -84,7 +84,13 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []   # (arrival time, text)
+        self.t_mark = None
+
+    def mark(self):
+        """The timed region starts now: samples that arrived earlier (warm-up) are dropped, unless nothing else came."""
+        self.t_mark = time.time()
+        return self
 
     def start(self):
         try:
@@ -97,7 +103,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -106,7 +112,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        lines = [l for t, l in self.lines if self.t_mark is None or t >= self.t_mark]
+        if not lines and self.lines:  # a very short region between two samples: the one taken just before it
+            lines = [self.lines[-1][1]]
+        for l in lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -274,11 +283,12 @@ def run_ours(args):
     def step_dev(i):
         keep.append(env.process_batch(dev_views(i % n_sets)))
 
+    clocks = ClockSampler(local_rank).start()  # (started before the warm-up: nvidia-smi needs ~0.3 s to deliver its first line)
     for i in range(W):
         step_dev(i)
     torch.cuda.synchronize()
     keep.clear()
-    clocks = ClockSampler(local_rank).start()
+    clocks.mark()
     launches0 = env.stats()["kernel_launches"]
     ms = timed(step_dev, K)
     launches = env.stats()["kernel_launches"] - launches0

@@ -214,19 +214,34 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
     // fixed stride, so the per-copy work is one small constant division and an address add.
     constexpr int kLoadTok = C::kThreads / C::kCPT;  // tokens moved per sweep of the CTA
     int const ld_part = tid % C::kCPT, ld_tok0 = tid / C::kCPT;
-    auto load_item = [&](int win, int buf) {
-        int const b = win / (nw * nw), wr = win % (nw * nw);
-        int const y0 = (wr / nw) * kWS, x0 = (wr % nw) * kWS;
-        act_t const* const src0 = qkv + ((size_t)(b * res + y0) * res + x0) * ld + hg * kHG * 96 + ld_part * 8;
+    // Window coordinates are stepped from item to item (win -> win + w_stride is (b, wy, wx) plus a constant triple with two
+    // carries) and windows that lie inside the image skip the per-token bounds tests: the four run-time divisions and the
+    // tests were a quarter (14 x 14 windows) to a half (7 x 7) of the kernel's instructions (profiles/r02_summary.md section 6).
+    struct WinPos {
+        int b, wy, wx;
+    };
+    int const nw2 = nw * nw;
+    WinPos const wstep{w_stride / nw2, (w_stride % nw2) / nw, w_stride % nw};
+    auto advance = [&](WinPos& p) {
+        p.wx += wstep.wx;
+        if (p.wx >= nw) { p.wx -= nw; ++p.wy; }
+        p.wy += wstep.wy;
+        if (p.wy >= nw) { p.wy -= nw; ++p.b; }
+        p.b += wstep.b;
+    };
+    auto load_item = [&](WinPos const& p, int buf) {
+        int const y0 = p.wy * kWS, x0 = p.wx * kWS;
+        act_t const* const src0 = qkv + ((size_t)(p.b * res + y0) * res + x0) * ld + hg * kHG * 96 + ld_part * 8;
         uint32_t const dst0 = tile0_s + (uint32_t)(buf * C::kTileBytes + ld_part * 16);
+        bool const inside = y0 + kWS <= res && x0 + kWS <= res;  // block-uniform
         if (ld_tok0 < kLoadTok) {
 #pragma unroll
             for (int tok = ld_tok0, i = 0; i < (C::n + kLoadTok - 1) / kLoadTok; ++i, tok += kLoadTok) {
                 if (tok < C::n) {
                     int const iy = tok / kWS, ix = tok - iy * kWS;
                     uint32_t const dst = dst0 + (uint32_t)(tok * C::kRowBytes);
-                    if (y0 + iy < res && x0 + ix < res) {
-                        act_t const* src = src0 + (size_t)(iy * res + ix) * ld;
+                    if (inside || (y0 + iy < res && x0 + ix < res)) {
+                        act_t const* src = src0 + (iy * res + ix) * ld;  // (element offsets inside one window fit 32 bits)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                     } else {
                         uint4 const v = __ldg(reinterpret_cast<uint4 const*>(pad_qkv + hg * kHG * 96 + ld_part * 8));
@@ -251,11 +266,13 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
                                   ((hh * C::NQ + qt) * C::NK8) * 32 + lane;  // (fp32 fragments: one float4 per lane and key block)
 
     int it = 0;
-    if (w_first < total_windows) load_item(w_first, 0);
-    for (int win = w_first; win < total_windows; win += w_stride, ++it) {
+    WinPos cur{w_first / nw2, (w_first % nw2) / nw, w_first % nw}, nxt = cur;
+    if (w_first < total_windows) load_item(cur, 0);
+    for (int win = w_first; win < total_windows; win += w_stride, ++it, cur = nxt) {
         int const buf = it & 1;
+        advance(nxt);
         if (win + w_stride < total_windows) {
-            load_item(win + w_stride, buf ^ 1);
+            load_item(nxt, buf ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -295,19 +312,19 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
         __syncthreads();  // all heads' outputs of this window are in the tile
 
         if (st_tok0 < kStoreTok) {
-            int const b = win / (nw * nw), wr = win % (nw * nw);
-            int const y0 = (wr / nw) * kWS, x0 = (wr % nw) * kWS;
+            int const y0 = cur.wy * kWS, x0 = cur.wx * kWS;
             int const Cout = heads * 32;
-            act_t* const dst0 = out + ((size_t)(b * res + y0) * res + x0) * Cout + hg * kHG * 32 + st_part * 8;
+            bool const inside = y0 + kWS <= res && x0 + kWS <= res;
+            act_t* const dst0 = out + ((size_t)(cur.b * res + y0) * res + x0) * Cout + hg * kHG * 32 + st_part * 8;
             uint32_t const src0 = tile + (uint32_t)(((st_part >> 2) * 96 + (st_part & 3) * 8) * 2);
 #pragma unroll
             for (int tok = st_tok0, i = 0; i < (C::n + kStoreTok - 1) / kStoreTok; ++i, tok += kStoreTok) {
                 if (tok < C::n) {
                     int const iy = tok / kWS, ix = tok - iy * kWS;
-                    if (y0 + iy < res && x0 + ix < res) {
+                    if (inside || (y0 + iy < res && x0 + ix < res)) {
                         uint4 v;
                         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src0 + (uint32_t)(tok * C::kRowBytes)));
-                        *reinterpret_cast<uint4*>(dst0 + (size_t)(iy * res + ix) * Cout) = v;
+                        *reinterpret_cast<uint4*>(dst0 + (iy * res + ix) * Cout) = v;
                     }
                 }
             }
