@@ -113,9 +113,34 @@ local_conv_kernel(const __grid_constant__ CUtensorMap in_map, float const* __res
 
     int const c8 = tid % kC8, xg = (tid / kC8) & 3, ty = tid / (kC8 * 4);
     int const grp = tid / L::kGroup, gtid = tid - grp * L::kGroup;  // row pair and index within it
+    // unit coordinates of the main loop are stepped (unit += gridDim.x is a constant (image, tile row, tile column, part)
+    // quadruple with carries): every thread needs them, and locate() is four run-time divisions
+    int const tiles_y = tiles_per_img / tiles_x;
+    int sb, sty, stx, spt;
+    {
+        int const g = (int)gridDim.x, gt = g / parts;
+        spt = g - gt * parts;
+        sb = gt / tiles_per_img;
+        int const r = gt - sb * tiles_per_img;
+        sty = r / tiles_x;
+        stx = r - sty * tiles_x;
+    }
+    int cb, cty, ctx, cpt;
+    {
+        int oy0, ox0;
+        locate(0, cb, oy0, ox0, cpt);
+        cty = oy0 / kTH;
+        ctx = ox0 / kTW;
+    }
     for (int u = 0; u < my_units; ++u) {
-        int b, oy0, ox0, pt;
-        locate(u, b, oy0, ox0, pt);
+        int const b = cb, oy0 = cty * kTH, ox0 = ctx * kTW, pt = cpt;
+        cpt += spt;
+        if (cpt >= parts) { cpt -= parts; ++ctx; }
+        ctx += stx;
+        if (ctx >= tiles_x) { ctx -= tiles_x; ++cty; }
+        cty += sty;
+        if (cty >= tiles_y) { cty -= tiles_y; ++cb; }
+        cb += sb;
         int const buf = u % kInBufs;
         float const* const w = wsm + (pt * kC8 + c8) * 4;  // tap k: halves at w + k * C and w + k * C + C / 2
         float2 acc2[4][4];  // [pixel][channel pair]: fp32 accumulation on packed pairs (FFMA2: half the FMA instructions)
