@@ -722,26 +722,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (kRes && (int)blockIdx.x < total_tiles) prefetch_residual(cur_mt, cur_nt);
         // folded LayerNorm: (mean, rstd) of this lane's row (ln_parts == 0) or its (sum, sum of squares), the partial
         // sums of the producing kernel added in a fixed order
+        // The statistics of the NEXT tile's rows are requested one tile ahead and only touched when that tile starts: the
+        // loads return raw (up to kLnRaw partial pairs per row, summed in a fixed order at use).  Summing inside the
+        // prefetch made it wait for its own loads -- a quarter of the stall samples of the qkv GEMMs sat on that add.
+        constexpr int kLnRaw = 4;
+        struct LnRaw {
+            float2 v[kLnRaw];
+        };
         auto load_ln = [&](int mt) {
             int const row = mt * kBlockM + quarter * 32 + lane;
-            float2 r = make_float2(0.f, 1.f);
+            LnRaw r;
+#pragma unroll
+            for (int pp = 0; pp < kLnRaw; ++pp) r.v[pp] = make_float2(0.f, pp == 0 && ep.ln_parts == 0 ? 1.f : 0.f);
             if (row < M) {
                 if (ep.ln_parts == 0) {
-                    r = __ldg(ep.ln_stats + row);
-                } else {
+                    r.v[0] = __ldg(ep.ln_stats + row);
+                } else if (ep.ln_parts <= kLnRaw) {
+#pragma unroll
+                    for (int pp = 0; pp < kLnRaw; ++pp)
+                        if (pp < ep.ln_parts) r.v[pp] = __ldg(ep.ln_stats + (int64_t)row * ep.ln_parts + pp);
+                } else {  // many partial sums: added here (this path waits for its loads)
                     float sx = 0.f, sq = 0.f;
                     for (int pp = 0; pp < ep.ln_parts; ++pp) {
                         float2 const pv = __ldg(ep.ln_stats + (int64_t)row * ep.ln_parts + pp);
                         sx += pv.x;
                         sq += pv.y;
                     }
-                    r = make_float2(sx, sq);
+                    r.v[0] = make_float2(sx, sq);
                 }
             }
             return r;
         };
-        float2 ln_next = make_float2(0.f, 1.f);
-        if (kStaged && kLn && (int)blockIdx.x < total_tiles) ln_next = load_ln(cur_mt);
+        auto ln_sum = [&](LnRaw const& r) {  // fixed order: ((p0 + p1) + p2) + p3, zeros for the unused slots
+            float sx = r.v[0].x, sq = r.v[0].y;
+#pragma unroll
+            for (int pp = 1; pp < kLnRaw; ++pp) {
+                sx += r.v[pp].x;
+                sq += r.v[pp].y;
+            }
+            return make_float2(sx, sq);
+        };
+        LnRaw ln_raw;
+#pragma unroll
+        for (int pp = 0; pp < kLnRaw; ++pp) ln_raw.v[pp] = make_float2(0.f, pp == 0 ? 1.f : 0.f);
+        if (kStaged && kLn && (int)blockIdx.x < total_tiles) ln_raw = load_ln(cur_mt);
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int const acc = local & 1;
@@ -758,13 +782,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 if (row < M) orow = ep.row_map ? (int64_t)__ldg(ep.row_map + row) : (int64_t)row;
             } else if (kLn) {
                 // the row statistics were fetched one tile ahead (their latency used to sit in front of every tile)
+                float2 const ln_cur = ln_sum(ln_raw);
                 if (ep.ln_parts == 0) {
-                    rstd = ln_next.y;
+                    rstd = ln_cur.y;
                 } else {
-                    float const inv_k = 1.0f / (float)K, mean = ln_next.x * inv_k;
-                    rstd = rsqrtf(fmaxf(fmaf(-mean, mean, ln_next.y * inv_k), 0.f) + ep.ln_eps);
+                    float const inv_k = 1.0f / (float)K, mean = ln_cur.x * inv_k;
+                    rstd = rsqrtf(fmaxf(fmaf(-mean, mean, ln_cur.y * inv_k), 0.f) + ep.ln_eps);
                 }
-                if (has_next) ln_next = load_ln(cur_mt);
+                if (has_next) ln_raw = load_ln(cur_mt);
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
