@@ -127,6 +127,30 @@ def test_batched_prompts_equal_single_calls(env, seg_case):
         assert np.array_equal(m3[2][k], single[k][0]) and abs(i3[2, k] - single[k][1]) < 1e-6
 
 
+def test_mask_modes_agree(env, seg_case):
+    """One decoder, three ways to ask: all four logit planes (get_low_res_logits), the selected plane (compute_mask) and planes
+    1..3 (compute_masks) come from the same fused epilogue with a different MaskMode -- post-processing the planes of the first
+    by hand must give the masks of the other two, and the selection must follow the exported graph's rule (two prompt points:
+    mask 0 is penalised by 500, the best of the rest wins)."""
+    _, seg, _, _ = seg_case
+    for p in (PROMPTS[0], PROMPTS[2], PROMPTS[5]):
+        logits, iou4 = seg.low_res_logits(p)
+        score = iou4 + (2 - 2.5) * np.array([1000.0, 0, 0, 0], np.float32)
+        best = int(np.argmax(score))
+        assert best in (1, 2, 3)
+        d_low = torch.from_numpy(logits).cuda().contiguous()
+        out = torch.zeros(4, 1200, 1800, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        assert dl.ext().mask_postprocess(env.handle(), d_low.data_ptr(), 4, 1800, 1200, out.data_ptr()) == 0
+        env.synchronize()
+        planes = out.cpu().numpy()
+        assert np.array_equal(planes[best], seg.compute_mask(p))
+        multi = seg.compute_masks(p)
+        for k in range(3):
+            assert np.array_equal(planes[1 + k], multi[k][0])
+            assert abs(multi[k][1] - float(iou4[1 + k])) < 1e-6
+
+
 def test_device_resident_masks(env, seg_case):
     _, seg, _, _ = seg_case
     prompts = [PROMPTS[0], PROMPTS[4]]
