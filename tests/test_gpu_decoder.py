@@ -133,7 +133,7 @@ def test_mask_modes_agree(env, seg_case):
     by hand must give the masks of the other two, and the selection must follow the exported graph's rule (two prompt points:
     mask 0 is penalised by 500, the best of the rest wins)."""
     _, seg, _, _ = seg_case
-    for p in (PROMPTS[0], PROMPTS[2], PROMPTS[5]):
+    for p in (PROMPTS[0], PROMPTS[1], PROMPTS[2]):  # compute_masks takes points only, like the reference
         logits, iou4 = seg.low_res_logits(p)
         score = iou4 + (2 - 2.5) * np.array([1000.0, 0, 0, 0], np.float32)
         best = int(np.argmax(score))
