@@ -43,21 +43,33 @@ constexpr int kS128 = 128 / kCl;   // 32: ... of a 128-wide one
 // out_s[r][f] = bias[n0 + f] + sum_k xs[r][k] * Wt[k][n0 + f]   for r < 7, f < NOUT, with all 256 threads: thread
 // (part, f) sums its share of k, the 256 / NOUT partial sums meet in shared memory.
 // xs: shared [7][K]; Wt: global (K, N) row-major; scratch: shared [256 / NOUT][7][NOUT]; out_s: shared [7][NOUT].
+// The projection comes in two halves so that a kernel can request the weight slice of its NEXT projection before it
+// reduces the current one (and the first slice before it even loads its inputs): the slice lives in registers only between
+// proj_load and proj_run's FMA loop, so one slice is live at a time and the trips to L2 overlap the reductions, the
+// attention core and the cluster barriers instead of standing in front of every projection.
 template <int NOUT, int K>
-__device__ __forceinline__ void cta_proj(float const* xs, float const* __restrict__ Wt, int N, int n0,
-                                         float const* __restrict__ bias, float* scratch, float* out_s) {
-    constexpr int kParts = kThreads / NOUT;
-    constexpr int kPer = K / kParts;  // k values per thread: 64 (256 -> 64 wide), 32 (256 -> 32 wide, 128 -> 64 wide)
+struct ProjW {
+    static constexpr int kParts = kThreads / NOUT;
+    static constexpr int kPer = K / kParts;  // k values per thread: 64 (256 -> 64 wide), 32 (256 -> 32 wide, 128 -> 64 wide)
     static_assert(kPer % 4 == 0 && kPer <= 64, "k slice per thread");
+    float4 w[kPer / 4];
+};
+// Wt is stored as [K / 4][N][4]: the four k values of one output feature are one 16-byte load, so a thread's whole
+// weight slice is 1 .. 16 loads, all requested at once (with scalar loads ptxas kept a rolling window of ~20 of the 64 in
+// flight: 15 cycles of scoreboard stall per issued instruction)
+template <int NOUT, int K>
+__device__ __forceinline__ void proj_load(ProjW<NOUT, K>& pw, float const* __restrict__ Wt, int N, int n0) {
+    int const f = threadIdx.x % NOUT, part = threadIdx.x / NOUT;
+    float4 const* wp = reinterpret_cast<float4 const*>(Wt) + (size_t)(part * ProjW<NOUT, K>::kPer / 4) * N + n0 + f;
+#pragma unroll
+    for (int k = 0; k < ProjW<NOUT, K>::kPer / 4; ++k) pw.w[k] = __ldg(wp + (size_t)k * N);
+}
+// partial sums of this thread's k slice -> scratch
+template <int NOUT, int K>
+__device__ __forceinline__ void proj_fma(ProjW<NOUT, K> const& pw, float const* xs, float* scratch) {
+    constexpr int kPer = ProjW<NOUT, K>::kPer;
     int const f = threadIdx.x % NOUT, part = threadIdx.x / NOUT;
     int const k0 = part * kPer;
-    // Wt is stored as [K / 4][N][4]: the four k values of one output feature are one 16-byte load, so a thread's whole
-    // weight slice is 8 or 16 loads, all requested before the first use -- one trip to L2 per projection (with scalar
-    // loads ptxas kept a rolling window of ~20 of the 64 in flight: 15 cycles of scoreboard stall per issued instruction)
-    float4 w[kPer / 4];
-    float4 const* wp = reinterpret_cast<float4 const*>(Wt) + (size_t)(k0 / 4) * N + n0 + f;
-#pragma unroll
-    for (int k = 0; k < kPer / 4; ++k) w[k] = __ldg(wp + (size_t)k * N);
     float acc[kT];
 #pragma unroll
     for (int r = 0; r < kT; ++r) acc[r] = 0.f;
@@ -66,14 +78,19 @@ __device__ __forceinline__ void cta_proj(float const* xs, float const* __restric
 #pragma unroll
         for (int r = 0; r < kT; ++r) {
             float4 const x = *reinterpret_cast<float4 const*>(xs + r * K + k0 + 4 * k);
-            acc[r] = fmaf(x.x, w[k].x, acc[r]);
-            acc[r] = fmaf(x.y, w[k].y, acc[r]);
-            acc[r] = fmaf(x.z, w[k].z, acc[r]);
-            acc[r] = fmaf(x.w, w[k].w, acc[r]);
+            acc[r] = fmaf(x.x, pw.w[k].x, acc[r]);
+            acc[r] = fmaf(x.y, pw.w[k].y, acc[r]);
+            acc[r] = fmaf(x.z, pw.w[k].z, acc[r]);
+            acc[r] = fmaf(x.w, pw.w[k].w, acc[r]);
         }
     }
 #pragma unroll
     for (int r = 0; r < kT; ++r) scratch[(part * kT + r) * NOUT + f] = acc[r];
+}
+// bias + the partial sums, in a fixed order -> out_s; barriers on both sides
+template <int NOUT, int K>
+__device__ __forceinline__ void proj_reduce(int n0, float const* __restrict__ bias, float const* scratch, float* out_s) {
+    constexpr int kParts = ProjW<NOUT, K>::kParts;
     __syncthreads();
     for (int i = threadIdx.x; i < kT * NOUT; i += kThreads) {
         int const ff = i % NOUT;
@@ -83,6 +100,14 @@ __device__ __forceinline__ void cta_proj(float const* xs, float const* __restric
         out_s[i] = s;
     }
     __syncthreads();
+}
+template <int NOUT, int K>
+__device__ __forceinline__ void cta_proj(float const* xs, float const* __restrict__ Wt, int N, int n0,
+                                         float const* __restrict__ bias, float* scratch, float* out_s) {
+    ProjW<NOUT, K> pw;
+    proj_load(pw, Wt, N, n0);
+    proj_fma(pw, xs, scratch);
+    proj_reduce<NOUT, K>(n0, bias, scratch, out_s);
 }
 
 // LayerNorm over 256 features that are spread over the cluster: this CTA holds v[r][f] for its 64 features (shared [7][64]).
@@ -147,6 +172,8 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_at
     int const n0 = rank * kS256;
     float* q_g = p.queries + (size_t)prompt * kT * kDim;
     float const* pe_g = p.pe + (size_t)prompt * kT * kDim;
+    ProjW<kS256, kDim> pw;  // one weight slice in flight or in use at a time (see proj_load)
+    proj_load(pw, p.wq_t, kDim, n0);
 #pragma unroll
     for (int r = 0; r < kT; ++r) {
         float const x = q_g[r * kDim + n], e = pe_g[r * kDim + n];
@@ -155,9 +182,15 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_at
     }
     __syncthreads();
     // q, k from queries (+ pe), v from queries: this CTA's 64 features = heads 2 * rank, 2 * rank + 1
-    cta_proj<kS256, kDim>(sm.xp, p.wq_t, kDim, n0, p.bq, sm.scratch, sm.q);
-    cta_proj<kS256, kDim>(sm.xp, p.wk_t, kDim, n0, p.bk, sm.scratch, sm.k);
-    cta_proj<kS256, kDim>(sm.xs, p.wv_t, kDim, n0, p.bv, sm.scratch, sm.v);
+    proj_fma(pw, sm.xp, sm.scratch);
+    proj_load(pw, p.wk_t, kDim, n0);
+    proj_reduce<kS256, kDim>(n0, p.bq, sm.scratch, sm.q);
+    proj_fma(pw, sm.xp, sm.scratch);
+    proj_load(pw, p.wv_t, kDim, n0);
+    proj_reduce<kS256, kDim>(n0, p.bk, sm.scratch, sm.k);
+    proj_fma(pw, sm.xs, sm.scratch);
+    proj_load(pw, p.wo_t, kDim, n0);  // in flight during the attention core and the cluster exchange
+    proj_reduce<kS256, kDim>(n0, p.bv, sm.scratch, sm.v);
     // scores of the two local heads: 2 x 7 x 7, head_dim 32, scale 1 / sqrt(32)
     if (n < 2 * kT * kT) {
         int const h = n / (kT * kT), t = (n / kT) % kT, u = n % kT;
@@ -201,7 +234,10 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_at
     __syncthreads();
     cluster_scatter_slice(cluster, sm.o, sm.full);  // every CTA needs all 256 features as the input of the out projection
     cluster.sync();
-    cta_proj<kS256, kDim>(sm.full, p.wo_t, kDim, n0, p.bo, sm.scratch, sm.o);
+    proj_fma(pw, sm.full, sm.scratch);
+    ProjW<kS128, kDim> pw_next;
+    proj_load(pw_next, p.w_next_t, 128, rank * kS128);  // in flight during the LayerNorm and its two cluster barriers
+    proj_reduce<kS256, kDim>(n0, p.bo, sm.scratch, sm.o);
     if (p.residual) {
         for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] += sm.xs[(i / kS256) * kDim + n0 + (i % kS256)];
         __syncthreads();
@@ -218,7 +254,8 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_at
     cluster_scatter_slice(cluster, sm.o, sm.full);
     cluster.sync();
     // query projection of tokens -> image attention: (queries + pe) W^T + b, 256 -> 128; this CTA's 32 features
-    cta_proj<kS128, kDim>(sm.full, p.w_next_t, 128, rank * kS128, p.b_next, sm.scratch, sm.q);
+    proj_fma(pw_next, sm.full, sm.scratch);
+    proj_reduce<kS128, kDim>(rank * kS128, p.b_next, sm.scratch, sm.q);
     for (int i = n; i < kT * kS128; i += kThreads)
         p.out_next[((size_t)prompt * kT + i / kS128) * 128 + rank * kS128 + (i % kS128)] = sm.q[i];
     cluster.sync();  // no CTA exits while another may still write into its shared memory
@@ -240,26 +277,50 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
     int const rank = (int)cluster.block_rank();
     int const prompt = blockIdx.x / kCl, n = threadIdx.x, n0 = rank * kS256;
     constexpr int kPart = 128 + 16;
-    for (int i = n; i < kT * 128; i += kThreads) {  // (every CTA merges all 7 x 128 values: they are its GEMM input)
-        int const t = i >> 7, d = i & 127, h = d >> 4;
+    ProjW<kS256, 128> pw;
+    proj_load(pw, p.wo_t, kDim, n0);  // under the merge of the attention partials
+    // every CTA needs all 7 x 128 merged values (they are its GEMM input): each merges the 32 dims of its own two heads --
+    // one element per thread, one round of loads -- and delivers them to all four through distributed shared memory
+    if (n < kT * 32) {
+        int const t = n >> 5, d = rank * 32 + (n & 31), h = d >> 4;
         float const* src = p.partials + ((size_t)prompt * kT2iSplits * kT + t) * kPart;
         size_t const split_stride = (size_t)kT * kPart;
+        float mx[kT2iSplits], ac[kT2iSplits], su[kT2iSplits];
+#pragma unroll
+        for (int sp = 0; sp < kT2iSplits; ++sp) {
+            mx[sp] = src[sp * split_stride + 128 + h];
+            ac[sp] = src[sp * split_stride + d];
+            su[sp] = src[sp * split_stride + 136 + h];
+        }
         float M = -INFINITY;
 #pragma unroll
-        for (int sp = 0; sp < kT2iSplits; ++sp) M = fmaxf(M, src[sp * split_stride + 128 + h]);
+        for (int sp = 0; sp < kT2iSplits; ++sp) M = fmaxf(M, mx[sp]);
         float A = 0.f, S = 0.f;
 #pragma unroll
         for (int sp = 0; sp < kT2iSplits; ++sp) {
-            float const e = __expf(src[sp * split_stride + 128 + h] - M);
-            A = fmaf(src[sp * split_stride + d], e, A);
-            S = fmaf(src[sp * split_stride + 136 + h], e, S);
+            float const e = __expf(mx[sp] - M);
+            A = fmaf(ac[sp], e, A);
+            S = fmaf(su[sp], e, S);
         }
-        sm.in_full[i] = A / S;
+        float const o = A / S;
+#pragma unroll
+        for (int c = 0; c < kCl; ++c) cluster.map_shared_rank(sm.in_full, c)[t * 128 + d] = o;
     }
-    __syncthreads();
+    cluster.sync();
     float* q_g = p.queries + (size_t)prompt * kT * kDim;
-    cta_proj<kS256, 128>(sm.in_full, p.wo_t, kDim, n0, p.bo, sm.scratch, sm.o);
-    for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] += q_g[(i / kS256) * kDim + n0 + (i % kS256)];
+    float res[2];  // this thread's residual values, requested before the projection
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        int const i = n + j * kThreads;
+        res[j] = i < kT * kS256 ? q_g[(i / kS256) * kDim + n0 + (i % kS256)] : 0.f;
+    }
+    proj_fma(pw, sm.in_full, sm.scratch);
+    proj_reduce<kS256, 128>(n0, p.bo, sm.scratch, sm.o);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        int const i = n + j * kThreads;
+        if (i < kT * kS256) sm.o[i] += res[j];
+    }
     __syncthreads();
     cluster_row_stats(cluster, sm.o, sm.ln_part, sm.stats);
     for (int i = n; i < kT * kS256; i += kThreads) {
@@ -281,6 +342,8 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
     float* q_g = p.queries + (size_t)prompt * kT * kDim;
     float const* m_g = p.mlp_out + (size_t)prompt * kT * kDim;
     float const* pe_g = p.pe + (size_t)prompt * kT * kDim;
+    ProjW<kS128, kDim> pw;
+    proj_load(pw, p.w_t[0], 128, rank * kS128);  // under the residual sum, the LayerNorm and its cluster barriers
     for (int i = n; i < kT * kS256; i += kThreads) {
         int const g = (i / kS256) * kDim + n0 + (i % kS256);
         float v = q_g[g] + __ldg(p.mlp_bias + n0 + (i % kS256));
@@ -298,7 +361,9 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
     }
     cluster.sync();
     for (int j = 0; j < p.count; ++j) {
-        cta_proj<kS128, kDim>(p.with_pe[j] ? sm.xp_full : sm.in_full, p.w_t[j], 128, rank * kS128, p.b[j], sm.scratch, sm.p32);
+        proj_fma(pw, p.with_pe[j] ? sm.xp_full : sm.in_full, sm.scratch);
+        if (j + 1 < p.count) proj_load(pw, p.w_t[j + 1], 128, rank * kS128);
+        proj_reduce<kS128, kDim>(rank * kS128, p.b[j], sm.scratch, sm.p32);
         for (int i = n; i < kT * kS128; i += kThreads)
             p.out[j][((size_t)prompt * kT + i / kS128) * 128 + rank * kS128 + (i % kS128)] = sm.p32[i];
         __syncthreads();
@@ -326,17 +391,22 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_ml
     int const groups = (P + kT - 1) / kT;
     int const cl = blockIdx.x / kCl, m = cl / groups, p0 = (cl % groups) * kT;  // m = 0: IoU head (token 0), 1..4: mask token m
     int const n = threadIdx.x, n0 = rank * kS256;
+    ProjW<kS256, kDim> pw;
+    proj_load(pw, heads.w[m][0], kDim, n0);
     for (int i = n; i < kT * kDim; i += kThreads) {
         int const r = i / kDim;
         sm.x[i] = p0 + r < P ? tokens[((size_t)(p0 + r) * kTokens + m) * kDim + (i % kDim)] : 0.f;
     }
     __syncthreads();
-    cta_proj<kS256, kDim>(sm.x, heads.w[m][0], kDim, n0, heads.b[m][0], sm.scratch, sm.o);
+    proj_fma(pw, sm.x, sm.scratch);
+    proj_load(pw, heads.w[m][1], kDim, n0);  // under the reduction, the exchange and the cluster barrier
+    proj_reduce<kS256, kDim>(n0, heads.b[m][0], sm.scratch, sm.o);
     for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] = fmaxf(sm.o[i], 0.f);
     __syncthreads();
     cluster_scatter_slice(cluster, sm.o, sm.y);
     cluster.sync();
-    cta_proj<kS256, kDim>(sm.y, heads.w[m][1], kDim, n0, heads.b[m][1], sm.scratch, sm.o);
+    proj_fma(pw, sm.y, sm.scratch);
+    proj_reduce<kS256, kDim>(n0, heads.b[m][1], sm.scratch, sm.o);
     for (int i = n; i < kT * kS256; i += kThreads) sm.o[i] = fmaxf(sm.o[i], 0.f);
     __syncthreads();
     cluster_scatter_slice(cluster, sm.o, sm.x);  // every CTA is past its reads of x: they precede the barrier above
