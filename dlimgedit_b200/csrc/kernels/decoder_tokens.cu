@@ -250,15 +250,15 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_at
         sm.o[i] = y + pe_g[r * kDim + c];  // input of the following query projection
     }
     __syncthreads();
-    cluster.sync();  // (every CTA is past its out projection: `full` may be overwritten)
-    cluster_scatter_slice(cluster, sm.o, sm.full);
-    cluster.sync();
+    // gathered into `xp`, which every CTA stopped reading at its k projection (all are past the barrier behind the attention
+    // exchange): `full` is still being read by slower CTAs' out projections, and a buffer of its own saves a cluster barrier
+    cluster_scatter_slice(cluster, sm.o, sm.xp);
+    cluster.sync();  // the last remote access of the kernel lies before this barrier: CTAs may exit independently afterwards
     // query projection of tokens -> image attention: (queries + pe) W^T + b, 256 -> 128; this CTA's 32 features
-    proj_fma(pw_next, sm.full, sm.scratch);
+    proj_fma(pw_next, sm.xp, sm.scratch);
     proj_reduce<kS128, kDim>(rank * kS128, p.b_next, sm.scratch, sm.q);
     for (int i = n; i < kT * kS128; i += kThreads)
         p.out_next[((size_t)prompt * kT + i / kS128) * 128 + rank * kS128 + (i % kS128)] = sm.q[i];
-    cluster.sync();  // no CTA exits while another may still write into its shared memory
 }
 
 struct PostSmem {
@@ -327,7 +327,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
         int const r = i / kS256, c = n0 + (i % kS256);
         q_g[r * kDim + c] = (sm.o[i] - sm.stats[2 * r]) * sm.stats[2 * r + 1] * __ldg(p.gamma + c) + __ldg(p.beta + c);
     }
-    cluster.sync();
+    // (no closing cluster barrier: the last remote access is in front of the barrier inside cluster_row_stats)
 }
 
 // After the token MLP: queries <- LayerNorm(queries + mlp_out) (mlp_out = bias + the split-K partial sums), then up to three 256 -> 128 projections of the new
@@ -344,10 +344,16 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
     float const* pe_g = p.pe + (size_t)prompt * kT * kDim;
     ProjW<kS128, kDim> pw;
     proj_load(pw, p.w_t[0], 128, rank * kS128);  // under the residual sum, the LayerNorm and its cluster barriers
+    constexpr int kMaxParts = 8;  // split-K partials summed from registers (all loads of a row in flight at once)
     for (int i = n; i < kT * kS256; i += kThreads) {
         int const g = (i / kS256) * kDim + n0 + (i % kS256);
+        float part[kMaxParts];
+#pragma unroll
+        for (int sp = 0; sp < kMaxParts; ++sp) part[sp] = sp < p.mlp_parts ? m_g[(size_t)sp * p.mlp_part_stride + g] : 0.f;
         float v = q_g[g] + __ldg(p.mlp_bias + n0 + (i % kS256));
-        for (int sp = 0; sp < p.mlp_parts; ++sp) v += m_g[(size_t)sp * p.mlp_part_stride + g];  // split-K partials, fixed order
+#pragma unroll
+        for (int sp = 0; sp < kMaxParts; ++sp) v += part[sp];  // fixed order; unused slots add zero
+        for (int sp = kMaxParts; sp < p.mlp_parts; ++sp) v += m_g[(size_t)sp * p.mlp_part_stride + g];
         sm.o[i] = v;
     }
     __syncthreads();
@@ -368,7 +374,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads) token_po
             p.out[j][((size_t)prompt * kT + i / kS128) * 128 + rank * kS128 + (i % kS128)] = sm.p32[i];
         __syncthreads();
     }
-    cluster.sync();
+    // (no closing cluster barrier: the projections above touch local shared memory only)
 }
 
 // IoU head and the four hypernetwork MLPs (256 -> 256 -> 256 -> 4 | 32, ReLU between): a cluster owns one MLP for SEVEN
