@@ -754,14 +754,20 @@ void SegmentationImpl::embedding_nchw_f16_async(uint16_t* out_host) {
     std::lock_guard<std::mutex> lock(env_.mutex());
     EnvironmentImpl::Scope scope(env_);
     if (!encoded()) fail("segmentation handle holds no processed image");
-    cudaStream_t const cs = env_.copy_out_;
-    CUDA_CHECK(cudaStreamWaitEvent(cs, store_->ready(), 0));
-    void* tmp = nullptr;  // stream-ordered scratch: conversion, copy and free are all queued on the copy-out stream
-    CUDA_CHECK(cudaMallocAsync(&tmp, kEmbFloats * sizeof(act_t), cs));
-    dec::f32_to_act(cs, emb_nchw_, (int64_t)kEmbFloats, static_cast<act_t*>(tmp));
-    CUDA_CHECK(cudaMemcpyAsync(out_host, tmp, kEmbFloats * sizeof(act_t), cudaMemcpyDeviceToHost, cs));
-    CUDA_CHECK(cudaFreeAsync(tmp, cs));
-    store_->mark_read(cs);
+    // The conversion runs on the WORK stream, in order behind the encoder (on the copy-out stream it had to squeeze onto SMs
+    // that the next pass's persistent kernels occupy, and the downloads behind it stalled unpredictably); the copy follows on
+    // the copy-out stream.  The 16-bit shadow belongs to the handle: allocated and freed on the work stream, so the pool hands
+    // the same blocks round (an allocation on one stream and its release on another is only recycled after a synchronisation).
+    cudaStream_t const ws = env_.stream(), cs = env_.copy_out_;
+    CUDA_CHECK(cudaStreamWaitEvent(ws, store_->ready(), 0));
+    if (!f16_shadow_) f16_shadow_ = std::make_unique<StreamBuffer>(kEmbFloats * sizeof(act_t), ws);
+    act_t* const shadow = reinterpret_cast<act_t*>(f16_shadow_->bytes());
+    dec::f32_to_act(ws, emb_nchw_, (int64_t)kEmbFloats, shadow);
+    CUDA_CHECK(cudaEventRecord(f16_shadow_->ready(), ws));
+    store_->mark_used(ws);
+    CUDA_CHECK(cudaStreamWaitEvent(cs, f16_shadow_->ready(), 0));
+    CUDA_CHECK(cudaMemcpyAsync(out_host, shadow, kEmbFloats * sizeof(act_t), cudaMemcpyDeviceToHost, cs));
+    f16_shadow_->mark_read(cs);
     env_.counters_.d2h_bytes += kEmbFloats * sizeof(act_t);
 #endif
 }

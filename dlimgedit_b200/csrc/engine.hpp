@@ -182,7 +182,7 @@ class SegmentationImpl {
     void compute_mask(int const* point, int const* region, uint8_t** out_masks, float* out_accuracy);  // :131-174
     void embedding_nchw(float* out_host);        // blocking
     void embedding_nchw_async(float* out_host);  // returns at once; complete after EnvironmentImpl::synchronize()
-    void embedding_nchw_f16_async(uint16_t* out_host);  // the same as fp16 (converted on the copy-out stream)
+    void embedding_nchw_f16_async(uint16_t* out_host);  // the same as fp16 (converted on the work stream into a per-handle shadow)
 
     int width() const { return size_.orig_w; }
     int height() const { return size_.orig_h; }
@@ -197,6 +197,7 @@ class SegmentationImpl {
     float* emb_nchw_ = nullptr;            // (256, 4096) fp32: the reference's `image_embeddings` layout
     act_t* keys0_ = nullptr;               // (4096, 256) 16-bit: embedding + no_mask_embed, the decoder's layer-0 image stream
     act_t* kvq0_ = nullptr;                // (4096, 384) 16-bit: its layer-0 [K | V | Q] projections
+    std::unique_ptr<StreamBuffer> f16_shadow_;  // (256, 4096) fp16 copy of emb_nchw_, made by the first get_embedding_f16_async
 };
 
 }  // namespace dlimg
