@@ -558,15 +558,12 @@ def run_ours(args):
     # ---------------- config 1: single-call latency through the 13-slot table, real image ----------------
     latency = None
     if "latency" in sections and rank == 0:
-        import ctypes
         truck = os.path.join(ROOT, "tests", "golden", "truck.jpg")
-        a = dl.api()
-        e2 = (ctypes.c_int * 2)(); chn = ctypes.c_int(); px = ctypes.c_void_p()
-        assert a.load_image(truck.encode(), e2, ctypes.byref(chn), ctypes.byref(px)) == 0, a.last_error()  # the library's own JPEG reader
-        tw, th = e2[0], e2[1]
-        img = np.ctypeslib.as_array(ctypes.cast(px, ctypes.POINTER(ctypes.c_uint8)), shape=(th, tw, chn.value)).copy()
-        a.destroy_image(px)
-        view = dl.ImageView(img, channels=dl.Channels.rgb)
+        # like the reference's C++ wrapper: the input is an Image of the library (Image::load -> load_image, the library's own
+        # JPEG reader) and the masks are Images it creates (create_image) -- page-locked while the environment lives
+        timg = dl.Image.load(truck)
+        view = timg.view()
+        view_pageable = dl.ImageView(timg.pixels.copy(), channels=dl.Channels.rgb)  # a caller's own (pageable) pixels
 
         def wall(fn, n):
             fn()  # first call (graph capture / allocations) is reported separately by the caller when wanted
@@ -578,6 +575,14 @@ def run_ours(args):
                 ts.append((time.perf_counter() - t0) * 1e3)
             return {"median_ms": statistics.median(ts), "min_ms": min(ts), "n": n}
 
+        import ctypes
+        plain_mask = np.empty((timg.extent().height, timg.extent().width), np.uint8)
+
+        def raw_mask(seg, x, y):  # the slot itself, writing into the caller's own (pageable) buffer
+            ptrs = (ctypes.c_void_p * 3)(plain_mask.ctypes.data, None, None)
+            acc = (ctypes.c_float * 3)()
+            assert dl.api().get_segmentation_mask(seg._h, (ctypes.c_int * 2)(x, y), None, ptrs, acc) == 0
+
         env.synchronize()
         t0 = time.perf_counter()
         s0 = dl.Segmentation.process(view, env)
@@ -585,13 +590,16 @@ def run_ours(args):
         first_ms = (time.perf_counter() - t0) * 1e3
         segs_l = []
         lat = {"image": "tests/golden/truck.jpg (reference test/input/truck.jpg, 1800x1200 RGB, decoded by the library's load_image)",
-               "api": "dlimg_Api 13-slot table: process_image_for_segmentation / get_segmentation_mask (blocking, host buffers)",
+               "api": "dlimg_Api 13-slot table: process_image_for_segmentation / get_segmentation_mask (blocking, host buffers "
+                      "from load_image / create_image as in dlimgedit.impl.hpp; *_pageable: the caller's own numpy pixels)",
                "process_first_call_ms": first_ms,
                # Segmentation::process returns once the pixels are consumed (the encoder keeps running); the reference's call
                # returns with the embedding computed, so the latency that compares is "call + synchronize"
                "process": wall(lambda: (segs_l.append(dl.Segmentation.process(view, env)), env.synchronize()), 10),
+               "process_pageable": wall(lambda: (segs_l.append(dl.Segmentation.process(view_pageable, env)), env.synchronize()), 10),
                "process_call_returns_ms": wall(lambda: segs_l.append(dl.Segmentation.process(view, env)), 5)["median_ms"],
                "compute_mask_point_486_722": wall(lambda: s0.compute_mask(dl.Point(486, 722)), 20),  # test_segmentation.cpp:139
+               "compute_mask_point_486_722_pageable": wall(lambda: raw_mask(s0, 486, 722), 20),
                "compute_mask_point_220_355": wall(lambda: s0.compute_mask(dl.Point(220, 355)), 20),  # README.md:29
                "compute_mask_region": wall(lambda: s0.compute_mask(dl.Region(dl.Point(180, 110), dl.Point(505, 330))), 20),
                "compute_masks_point": wall(lambda: s0.compute_masks(dl.Point(486, 722)), 20),

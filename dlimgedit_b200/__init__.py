@@ -164,6 +164,7 @@ class _Debug(ctypes.Structure):
                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)),
         ("local_conv", _F(_R, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int)),
+        ("image_pool_stats", _F(None, ctypes.POINTER(ctypes.c_uint64))),
     ]
 
 
@@ -242,6 +243,59 @@ class ImageView:
 
     def to_c(self) -> _ImageView:
         return _ImageView(self.extent.width, self.extent.height, int(self.channels), self.stride, self._addr)
+
+
+class Image:
+    """Image that owns packed pixels handed out by the library (dlimgedit.hpp:48-82; dlimgedit.impl.hpp:44-66: the
+    constructor takes them from `create_image`, `load` from `load_image`, the destructor gives them back through
+    `destroy_image`).  While a GPU environment is alive these buffers are page-locked (csrc/image_pool.hpp), so passing
+    an Image to `Segmentation.process` / receiving one from `compute_mask` moves over PCIe without pageable staging.
+    `pixels` is a numpy view (H, W, C) -- or (H, W) for masks -- that keeps the Image alive."""
+
+    def __init__(self, extent: Extent, channels: Channels = Channels.rgba, _pixels: int = 0):
+        self._extent = extent
+        self._channels = Channels(channels)
+        addr = _pixels or api().create_image(extent.width, extent.height, count(self._channels))
+        if not addr:
+            raise Exception("create_image failed")
+        self._addr = addr
+        n = count(self._channels)
+        shape = (extent.height, extent.width) if n == 1 else (extent.height, extent.width, n)
+        buf = (ctypes.c_uint8 * (extent.width * extent.height * n)).from_address(addr)
+        # the ctypes buffer owns the pixels: they go back to the library when the Image AND every numpy view of it are gone
+        # (no reference cycle, so that happens at once and a cached page-locked block is re-used by the next call)
+        buf._release = weakref.finalize(buf, api().destroy_image, addr)
+        self._pixels = np.frombuffer(buf, np.uint8).reshape(shape)
+
+    def extent(self) -> Extent:
+        return self._extent
+
+    def channels(self) -> Channels:
+        return self._channels
+
+    @property
+    def pixels(self) -> np.ndarray:
+        return self._pixels
+
+    def size(self) -> int:
+        return self._extent.width * self._extent.height * count(self._channels)
+
+    def view(self) -> "ImageView":
+        return ImageView(self._pixels, self._extent, self._channels)
+
+    @staticmethod
+    def load(filepath) -> "Image":
+        e = (ctypes.c_int * 2)()
+        ch = ctypes.c_int()
+        px = ctypes.c_void_p()
+        _check(api().load_image(os.fspath(filepath).encode(), e, ctypes.byref(ch), ctypes.byref(px)))
+        return Image(Extent(e[0], e[1]), Channels(ch.value), _pixels=px.value)
+
+    @staticmethod
+    def save(img, filepath) -> None:
+        view = img.view() if isinstance(img, Image) else img
+        c = view.to_c()
+        _check(api().save_image(ctypes.byref(c), os.fspath(filepath).encode()))
 
 
 class Options:  # dlimgedit.hpp:91-96
@@ -380,8 +434,9 @@ class Segmentation:
         return Extent(e[0], e[1])
 
     def _mask_call(self, point, region, n_masks):
+        # like dlimgedit.impl.hpp:146-168: the results are Images of the library (page-locked while the environment lives)
         e = self.extent()
-        masks = [np.empty((e.height, e.width), np.uint8) for _ in range(n_masks)]
+        masks = [Image(e, Channels.mask).pixels for _ in range(n_masks)]
         ptrs = (ctypes.c_void_p * 3)(*[m.ctypes.data for m in masks] + [None] * (3 - n_masks))
         ious = (ctypes.c_float * 3)(0.0, 0.0, 0.0)
         pt = (ctypes.c_int * 2)(point.x, point.y) if point is not None else None

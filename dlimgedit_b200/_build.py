@@ -25,6 +25,7 @@ SOURCES = [
     "model.cu",
     "weights.cpp",
     "image_io.cpp",
+    "image_pool.cpp",
     "profiler.cpp",
     "kernels/gemm.cu",
     "kernels/encoder_kernels.cu",

@@ -5,6 +5,7 @@
 #include "../../include/dlimg_b200_debug.h"
 #include "engine.hpp"
 #include "image_io.hpp"
+#include "image_pool.hpp"
 #include "kernels/gemm.cuh"
 #include "profiler.hpp"
 
@@ -83,10 +84,18 @@ dlimg_Result save_image_api(dlimg_ImageView const* img, char const* filepath) {
     return try_([=] { save_image(*img, filepath); });
 }
 
-// Pixels handed out by this library (create_image, load_image) all come from new[] so destroy_image's
-// delete[] is always matched (the reference mixes malloc and delete[]).
-uint8_t* create_image(int w, int h, int channels) { return new uint8_t[(size_t)w * h * channels]; }
-void destroy_image(uint8_t const* pixels) { delete[] pixels; }
+// Pixels handed out by this library (create_image, load_image) all come from image_alloc, so destroy_image's
+// image_free is always matched (the reference mixes malloc and delete[]).  While a GPU environment is
+// alive these buffers are page-locked and recycled by size (image_pool.hpp).
+uint8_t* create_image(int w, int h, int channels) {
+    if (w <= 0 || h <= 0 || channels <= 0) return nullptr;
+    try {
+        return image_alloc((size_t)w * h * channels);
+    } catch (std::exception const&) {
+        return nullptr;
+    }
+}
+void destroy_image(uint8_t const* pixels) { image_free(pixels); }
 
 char const* last_error() { return last_error_.c_str(); }
 
@@ -293,6 +302,15 @@ dlimg_Result dbg_local_conv(void* stream, void const* in, int batch, int H, int 
     });
 }
 
+void dbg_image_pool_stats(uint64_t* out5) {
+    ImagePoolStats const st = image_pool_stats();
+    out5[0] = st.pinned_in_use;
+    out5[1] = st.pinned_cached;
+    out5[2] = st.pinned_allocs;
+    out5[3] = st.reuses;
+    out5[4] = st.plain_allocs;
+}
+
 dlimg_Result dbg_conv3x3(void* stream, void const* in, int batch, int H, int W, int C, void const* weight, float const* bias, int N,
                          void* out) {
     return try_([=] {
@@ -390,6 +408,7 @@ DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void) {
     debug_.mlp_fused = dbg_mlp_fused;
     debug_.conv3x3 = dbg_conv3x3;
     debug_.local_conv = dbg_local_conv;
+    debug_.image_pool_stats = dbg_image_pool_stats;
     return &debug_;
 }
 

@@ -1,5 +1,6 @@
 // engine.cu -- see engine.hpp.
 #include "engine.hpp"
+#include "image_pool.hpp"
 #include "kernels/mask_select.cuh"
 
 #include <algorithm>
@@ -185,6 +186,7 @@ EnvironmentImpl::EnvironmentImpl(dlimg_Options const& opts) {
     auto const& t = prepost::srgb_tables();
     srgb_decode_.upload(std::vector<float>(t.decode, t.decode + 256));
     srgb_threshold_.upload(std::vector<float>(t.encode_threshold, t.encode_threshold + 256));
+    image_pool_attach(device_);  // (last: nothing above may throw after it) façade images are page-locked from now on
 }
 
 void EnvironmentImpl::release_graphs() {
@@ -197,6 +199,7 @@ void EnvironmentImpl::release_graphs() {
 EnvironmentImpl::~EnvironmentImpl() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
+    image_pool_detach();
     release_graphs();
     if (own_stream_) cudaStreamDestroy(own_stream_);
     if (copy_in_) cudaStreamDestroy(copy_in_);

@@ -1,5 +1,6 @@
 // image_io.cpp -- see image_io.hpp.  Minimal PNG / baseline-JPEG / PNM codec written for this library (no stb).
 #include "image_io.hpp"
+#include "image_pool.hpp"
 
 #include <algorithm>
 #include <cstdio>
@@ -221,7 +222,7 @@ uint8_t* load_png(std::vector<uint8_t> const& file, char const* path, int* exten
     size_t const expect = (row + 1) * (size_t)h;
     std::vector<uint8_t> raw = inflate(idat.data(), idat.size(), expect);
     if (raw.size() < expect) fail(std::string("Failed to load image ") + path + ": PNG data too short");
-    uint8_t* px = new uint8_t[row * h];
+    uint8_t* px = image_alloc(row * h);
     for (uint32_t y = 0; y < h; ++y) {
         uint8_t const* src = &raw[(row + 1) * y];
         uint8_t* dst = px + row * y;
@@ -237,7 +238,7 @@ uint8_t* load_png(std::vector<uint8_t> const& file, char const* path, int* exten
             case 2: v += b; break;
             case 3: v += (a + b) >> 1; break;
             case 4: v += paeth(a, b, c); break;
-            default: delete[] px; fail(std::string("Failed to load image ") + path + ": bad PNG filter");
+            default: image_free(px); fail(std::string("Failed to load image ") + path + ": bad PNG filter");
             }
             dst[x] = (uint8_t)v;
         }
@@ -272,7 +273,7 @@ uint8_t* load_pnm(std::vector<uint8_t> const& file, char const* path, int* exten
     if (maxv != 255 || w <= 0 || h <= 0 || (uint32_t)w > kMaxImageDim || (uint32_t)h > kMaxImageDim ||
         (uint64_t)w * h * ch > kMaxImageBytes || pos + (size_t)w * h * ch > file.size())
         fail(std::string("Failed to load image ") + path + ": unsupported PNM variant");
-    uint8_t* px = new uint8_t[(size_t)w * h * ch];
+    uint8_t* px = image_alloc((size_t)w * h * ch);
     std::memcpy(px, &file[pos], (size_t)w * h * ch);
     extent[0] = w;
     extent[1] = h;
@@ -632,7 +633,7 @@ uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* exte
         }
     // planes -> interleaved pixels
     int const nc = (int)comps.size();
-    uint8_t* px = new uint8_t[(size_t)W * H * (nc == 1 ? 1 : 3)];
+    uint8_t* px = image_alloc((size_t)W * H * (nc == 1 ? 1 : 3));
     if (nc == 1) {
         for (int y = 0; y < H; ++y) std::memcpy(px + (size_t)y * W, &comps[0].data[(size_t)y * comps[0].w2], (size_t)W);
         extent[0] = W; extent[1] = H; *channels = 1;
@@ -645,7 +646,7 @@ uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* exte
         up[k].hs = hmax / c.h;
         up[k].vs = vmax / c.v;
         if (!((up[k].hs == 1 || up[k].hs == 2) && (up[k].vs == 1 || up[k].vs == 2))) {
-            delete[] px;
+            image_free(px);
             bad("unsupported chroma subsampling");
         }
         up[k].ystep = up[k].vs >> 1;

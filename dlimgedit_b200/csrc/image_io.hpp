@@ -8,7 +8,7 @@
 
 namespace dlimg {
 
-// Returns pixels allocated with new[] (released by dlimg_Api::destroy_image).
+// Returns pixels from image_alloc (image_pool.hpp; released by dlimg_Api::destroy_image -> image_free).
 uint8_t* load_image(char const* filepath, int* out_extent, int* out_channels);
 void save_image(dlimg_ImageView const& img, char const* filepath);
 

@@ -76,7 +76,17 @@ struct Cfg {
 };
 
 // One chunk of kCnt key blocks (8 keys each) of the online softmax for one (head, query tile).
-template <int kCnt, bool kFirst, bool kBiasInSmem>
+//
+// kMode 0: the running row maxima follow every chunk (the accumulators are rescaled each time).
+// kMode 1: LAZY maxima.  The reference point m of a row only moves when some score of the chunk exceeds it by more than
+//          kLazyGrowth (in log2 units); until then the probabilities are taken relative to the old m and may reach
+//          2^kLazyGrowth, which a 16-bit float holds with the same relative precision, and the final division by the row
+//          sum (accumulated from the same rounded values) is unchanged.  The test is per lane plus one warp vote, so the
+//          common chunk drops the quad reductions, two exponentials and the 18 accumulator multiplications.
+// (ex2.approx.f16x2 was tried for the exponentials: ptxas lowers it to two MUFU.EX2.F16 plus a PRMT on sm_100a, so it
+// saves no XU cycles and costs instructions.)
+constexpr float kLazyGrowth = 8.0f;
+template <int kCnt, bool kFirst, bool kBiasInSmem, int kMode>
 __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4], uint32_t k_addr, uint32_t v_addr, int row_bytes,
                                              uint32_t bias_addr, float4 const* __restrict__ bias_gl, float (&m)[2], float (&l)[4],
                                              float (&o)[4][4], uint32_t ones_b) {
@@ -122,51 +132,53 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
             cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
         }
     }
-    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
-    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
-    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
-    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
-    if (kFirst) {
-        m[0] = cm0;
-        m[1] = cm1;
-    } else {  // every chunk holds at least one unmasked key, so the running maxima are finite from chunk 0 on
-        float const n0 = fmaxf(m[0], cm0), n1 = fmaxf(m[1], cm1);
-        float const a0 = ex2((m[0] - n0) * (kBiasInSmem ? 1.0f : kScale)), a1 = ex2((m[1] - n1) * (kBiasInSmem ? 1.0f : kScale));
-        m[0] = n0;
-        m[1] = n1;
-        l[0] *= a0;  // (accumulator fragment of the ones column: rows g / g + 8 in elements 0 / 2 of the lanes with t == 0)
-        l[2] *= a1;
+    bool moved = true;
+    if (!kFirst && kMode >= 1) {  // (scores of the global-bias path are still unscaled: the growth bound is divided by the scale)
+        float const bound = kBiasInSmem ? kLazyGrowth : kLazyGrowth / kScale;
+        moved = __any_sync(0xffffffffu, cm0 > m[0] + bound || cm1 > m[1] + bound);
+    }
+    if (moved) {
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+        if (kFirst) {
+            m[0] = cm0;
+            m[1] = cm1;
+        } else {  // every chunk holds at least one unmasked key, so the running maxima are finite from chunk 0 on
+            float const n0 = fmaxf(m[0], cm0), n1 = fmaxf(m[1], cm1);
+            float const a0 = ex2((m[0] - n0) * (kBiasInSmem ? 1.0f : kScale)), a1 = ex2((m[1] - n1) * (kBiasInSmem ? 1.0f : kScale));
+            m[0] = n0;
+            m[1] = n1;
+            l[0] *= a0;  // (accumulator fragment of the ones column: rows g / g + 8 in elements 0 / 2 of the lanes with t == 0)
+            l[2] *= a1;
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            o[d][0] *= a0; o[d][1] *= a0;
-            o[d][2] *= a1; o[d][3] *= a1;
+            for (int d = 0; d < 4; ++d) {
+                o[d][0] *= a0; o[d][1] *= a0;
+                o[d][2] *= a1; o[d][3] *= a1;
+            }
         }
     }
     float const e0 = -m[0] * kScale, e1 = -m[1] * kScale;  // (global-bias path: scores are still unscaled)
+    uint32_t p[kCnt + 1][2];  // probabilities as packed pairs: [j][0] = row g, [j][1] = row g + 8 (keys 2t, 2t + 1 of block j)
+    p[kCnt][0] = p[kCnt][1] = 0u;
 #pragma unroll
     for (int j = 0; j < kCnt; ++j) {
+        float x0, x1, x2, x3;
         if (kBiasInSmem) {
-            s[j][0] = ex2(s[j][0] - m[0]);
-            s[j][1] = ex2(s[j][1] - m[0]);
-            s[j][2] = ex2(s[j][2] - m[1]);
-            s[j][3] = ex2(s[j][3] - m[1]);
+            x0 = s[j][0] - m[0]; x1 = s[j][1] - m[0];
+            x2 = s[j][2] - m[1]; x3 = s[j][3] - m[1];
         } else {
-            s[j][0] = ex2(fmaf(s[j][0], kScale, e0));
-            s[j][1] = ex2(fmaf(s[j][1], kScale, e0));
-            s[j][2] = ex2(fmaf(s[j][2], kScale, e1));
-            s[j][3] = ex2(fmaf(s[j][3], kScale, e1));
+            x0 = fmaf(s[j][0], kScale, e0); x1 = fmaf(s[j][1], kScale, e0);
+            x2 = fmaf(s[j][2], kScale, e1); x3 = fmaf(s[j][3], kScale, e1);
         }
+        p[j][0] = pack2(ex2(x0), ex2(x1));
+        p[j][1] = pack2(ex2(x2), ex2(x3));
     }
     // O += P V, 16 keys per step; an odd trailing key block pairs with zeros
 #pragma unroll
     for (int kb = 0; kb < (kCnt + 1) / 2; ++kb) {
-        uint32_t const a0 = pack2(s[2 * kb][0], s[2 * kb][1]);
-        uint32_t const a1 = pack2(s[2 * kb][2], s[2 * kb][3]);
-        uint32_t a2 = 0u, a3 = 0u;
-        if (2 * kb + 1 < kCnt) {
-            a2 = pack2(s[2 * kb + 1][0], s[2 * kb + 1][1]);
-            a3 = pack2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
-        }
+        uint32_t const a0 = p[2 * kb][0], a1 = p[2 * kb][1], a2 = p[2 * kb + 1][0], a3 = p[2 * kb + 1][1];
         uint32_t const va = v_addr + (uint32_t)((nb0 + 2 * kb) * 8 * row_bytes);
         uint32_t b0, b1, b2, b3;
         ldsm_x4_t(va, b0, b1, b2, b3);  // dims 0-7 (keys 0-7, 8-15), dims 8-15
@@ -181,7 +193,7 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
     }
 }
 
-template <int kWS, int kHG>
+template <int kWS, int kHG, int kMode>
 __global__ void __launch_bounds__(Cfg<kWS, kHG>::kThreads, Cfg<kWS, kHG>::kMinBlocks)
 window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int heads, act_t const* __restrict__ pad_qkv,
                          __half const* __restrict__ bias_frag, act_t* __restrict__ out) {
@@ -289,16 +301,16 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
 #pragma unroll
         for (int d = 0; d < 4; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
         if constexpr (C::NK8 <= 8) {
-            attend_chunk<C::NK8, true, C::kBiasInSmem>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
+            attend_chunk<C::NK8, true, C::kBiasInSmem, kMode>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
         } else {
             static_assert(C::NK8 <= 8 || C::NK8 == 25, "chunk schedule written for 196-token windows");
             // 25 key blocks in chunks of 4 (+1): with the bias table in global memory the kernel runs two CTAs per SM
             // at 72 registers, and a 4-block chunk (16 score registers) is what fits without spilling
-            attend_chunk<4, true, C::kBiasInSmem>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
+            attend_chunk<4, true, C::kBiasInSmem, kMode>(0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
 #pragma unroll
             for (int c0 = 4; c0 < 24; c0 += 4)
-                attend_chunk<4, false, C::kBiasInSmem>(c0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
-            attend_chunk<1, false, C::kBiasInSmem>(24, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
+                attend_chunk<4, false, C::kBiasInSmem, kMode>(c0, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
+            attend_chunk<1, false, C::kBiasInSmem, kMode>(24, aq, tile + k_off, tile + v_off, C::kRowBytes, bias_addr, bias_gl, m, l, o, ones_b);
         }
         // the sums sit in the t == 0 lane of every quad
         float const inv0 = 1.0f / __shfl_sync(0xffffffffu, l[0], lane & ~3), inv1 = 1.0f / __shfl_sync(0xffffffffu, l[2], lane & ~3);
@@ -333,13 +345,13 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
     }
 }
 
-template <int kWS, int kHG>
-void launch_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int heads, act_t const* pad_qkv,
-                      __half const* bias_frag, act_t* out, int num_sms) {
+template <int kWS, int kHG, int kMode>
+void launch_attention_mode(cudaStream_t s, act_t const* qkv, int batch, int res, int heads, act_t const* pad_qkv,
+                           __half const* bias_frag, act_t* out, int num_sms) {
     using C = Cfg<kWS, kHG>;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(window_attention_kernel2<kWS, kHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        CUDA_CHECK(cudaFuncSetAttribute(window_attention_kernel2<kWS, kHG, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         attr_set = true;
     }
     int const n_groups = heads / kHG;
@@ -347,9 +359,21 @@ void launch_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int 
     int const items = batch * nw * nw * n_groups;
     int grid = (num_sms * C::kMinBlocks / n_groups) * n_groups;
     if (grid > items) grid = items;
-    launch_pdl(PDL_ATTENTION, window_attention_kernel2<kWS, kHG>, dim3(grid), dim3(C::kThreads), (size_t)C::kSmemBytes, s, qkv, batch, res, heads, pad_qkv,
-               bias_frag, out);
+    launch_pdl(PDL_ATTENTION, window_attention_kernel2<kWS, kHG, kMode>, dim3(grid), dim3(C::kThreads), (size_t)C::kSmemBytes, s, qkv, batch, res, heads,
+               pad_qkv, bias_frag, out);
     KERNEL_CHECK();
+}
+
+constexpr int kSoftmaxMode = 1;  // attend_chunk's kMode of the release build
+
+template <int kWS, int kHG>
+void launch_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int heads, act_t const* pad_qkv,
+                      __half const* bias_frag, act_t* out, int num_sms) {
+#if DLIMG_B200_ALT
+    int const mode = dev_int("DLIMG_B200_WA_MODE", kSoftmaxMode);  // development A/B of the softmax variants
+    if (mode == 0) return launch_attention_mode<kWS, kHG, 0>(s, qkv, batch, res, heads, pad_qkv, bias_frag, out, num_sms);
+#endif
+    launch_attention_mode<kWS, kHG, kSoftmaxMode>(s, qkv, batch, res, heads, pad_qkv, bias_frag, out, num_sms);
 }
 
 }  // namespace

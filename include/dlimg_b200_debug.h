@@ -58,6 +58,10 @@ typedef struct dlimg_b200_Debug {
      * tma != 0: the TMA halo-tile kernel (H % 8 == 0, W % 16 == 0, C in {128, 160, 320}); 0: the register-tiled kernel. */
     dlimg_Result (*local_conv)(void* stream, void const* in, int batch, int H, int W, int C, float const* weight,
                                float const* bias, void* out, float* stats, int tma);
+    /* Storage behind create_image / load_image / destroy_image (csrc/image_pool.hpp): out[0] page-locked bytes in use,
+     * out[1] page-locked bytes cached for re-use, out[2] page-locked allocations made, out[3] re-uses of a cached block,
+     * out[4] plain (pageable) allocations. */
+    void (*image_pool_stats)(uint64_t* out5);
 } dlimg_b200_Debug;
 
 DLIMG_B200_EXPORT dlimg_b200_Debug const* dlimg_b200_debug_init(void);

@@ -219,3 +219,27 @@ def test_load_image_rejects_hostile_png_headers(tmp_path):
     pnm = tmp_path / "overflow.ppm"
     pnm.write_bytes(b"P6 99999999999 99999999999 255\n" + bytes(12))
     assert a.load_image(str(pnm).encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 1
+
+
+def test_image_class_owns_library_pixels(tmp_path):
+    """dlimg::Image mirror (dlimgedit.hpp:48-82): pixels come from create_image / load_image and go back through
+    destroy_image when the Image and its numpy views are gone.  Without an environment the storage is plain memory."""
+    st = (ctypes.c_uint64 * 5)()
+    dl.debug().image_pool_stats(st)
+    plain0 = st[4]
+    img = dl.Image(dl.Extent(320, 200), dl.Channels.rgb)
+    assert img.pixels.shape == (200, 320, 3) and img.size() == 320 * 200 * 3
+    img.pixels[:] = np.arange(320 * 3, dtype=np.uint8).reshape(1, 320, 3)
+    dl.Image.save(img, tmp_path / "img.png")
+    back = dl.Image.load(tmp_path / "img.png")
+    assert (back.extent().width, back.extent().height, back.channels()) == (320, 200, dl.Channels.rgb)
+    assert np.array_equal(back.pixels, img.pixels)
+    rows = img.pixels[5:7]
+    del img  # a view keeps the pixels alive
+    assert rows[0, 1, 2] == 5
+    mask = dl.Image(dl.Extent(7, 5), dl.Channels.mask)
+    assert mask.pixels.shape == (5, 7)
+    dl.debug().image_pool_stats(st)
+    assert st[4] >= plain0 + 3 and st[0] == 0  # nothing is page-locked while no GPU environment exists
+    assert dl.api().create_image(0, 4, 4) is None
+    dl.api().destroy_image(None)

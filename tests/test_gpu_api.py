@@ -140,3 +140,62 @@ def test_async_host_masks_match_blocking(env):
             assert np.array_equal(a.numpy(), b)
         assert np.array_equal(hi.numpy(), ref_ious)
     seg.close()
+
+
+def _pool():
+    st = (ctypes.c_uint64 * 5)()
+    dl.debug().image_pool_stats(st)
+    return dict(in_use=st[0], cached=st[1], pinned_allocs=st[2], reuses=st[3], plain=st[4])
+
+
+def test_library_images_are_page_locked_and_recycled(env):
+    """create_image / load_image hand out page-locked blocks while an environment lives (csrc/image_pool.hpp), destroy_image
+    caches them by size; results through them equal the results through plain numpy buffers."""
+    import os
+    import torch
+    truck = os.path.join(os.path.dirname(__file__), "golden", "truck.jpg")
+    before = _pool()
+    img = dl.Image.load(truck)
+    mid = _pool()
+    assert mid["in_use"] - before["in_use"] >= img.size()          # the loader's buffer is a pool block
+    assert mid["pinned_allocs"] + mid["reuses"] == before["pinned_allocs"] + before["reuses"] + 1
+    assert torch.from_numpy(img.pixels).is_pinned()                  # and CUDA agrees that it is page-locked
+    seg_a = dl.Segmentation.process(img.view(), env)
+    seg_b = dl.Segmentation.process(dl.ImageView(img.pixels.copy(), channels=dl.Channels.rgb), env)  # pageable copy
+    assert np.array_equal(seg_a.embedding(), seg_b.embedding())
+    m1 = seg_a.compute_mask(dl.Point(486, 722))                      # an Image of the library, like dlimgedit.impl.hpp:146
+    assert torch.from_numpy(m1).is_pinned() and m1.shape == (1200, 1800)
+    plain = np.empty((1200, 1800), np.uint8)
+    ptrs = (ctypes.c_void_p * 3)(plain.ctypes.data, None, None)
+    acc = (ctypes.c_float * 3)()
+    assert dl.api().get_segmentation_mask(seg_b._h, (ctypes.c_int * 2)(486, 722), None, ptrs, acc) == 0
+    assert np.array_equal(m1, plain)
+    # release -> cached -> re-used by the next request of the same size
+    keep = m1.copy()
+    del m1
+    a = _pool()
+    m2 = seg_a.compute_mask(dl.Point(486, 722))
+    b = _pool()
+    assert b["reuses"] == a["reuses"] + 1 and b["pinned_allocs"] == a["pinned_allocs"]
+    assert np.array_equal(m2, keep)
+    small = dl.Image(dl.Extent(16, 16), dl.Channels.rgba)             # below the pinning threshold: plain memory
+    assert _pool()["plain"] == b["plain"] + 1
+    del small, m2, img
+    seg_a.close()
+    seg_b.close()
+    assert _pool()["in_use"] == before["in_use"]
+
+
+def test_images_outlive_their_environment(model_dir):
+    """Blocks still in use when the last environment goes are released later without one; the cache is dropped with it."""
+    base = _pool()
+    e = dl.Environment(dl.Options(dl.Backend.gpu, model_dir))
+    img = dl.Image(dl.Extent(512, 512), dl.Channels.rgba)
+    tmp = dl.Image(dl.Extent(512, 256), dl.Channels.rgba)
+    del tmp
+    img.pixels[:] = 3
+    e.close()
+    assert int(img.pixels.sum()) == 3 * 512 * 512 * 4
+    del img
+    after = _pool()
+    assert after["in_use"] == base["in_use"]

@@ -150,14 +150,19 @@ def test_batch_equals_single(env, case):
     assert not np.array_equal(e[0], e[1])
 
 
-@pytest.mark.parametrize("batch,res,ws,heads", [(1, 128, 7, 4), (2, 64, 14, 5), (3, 64, 7, 10), (1, 20, 14, 5), (2, 9, 7, 4)])
-def test_window_attention_kernel(batch, res, ws, heads):
+@pytest.mark.parametrize("batch,res,ws,heads,gain", [(1, 128, 7, 4, 1.0), (2, 64, 14, 5, 1.0), (3, 64, 7, 10, 1.0), (1, 20, 14, 5, 1.0),
+                                                     (2, 9, 7, 4, 1.0), (2, 64, 14, 5, 2.0), (1, 28, 14, 5, 3.5)])
+def test_window_attention_kernel(batch, res, ws, heads, gain):
     """Tensor-core windowed attention on the un-partitioned grid (partition, zero-padding tokens, un-partition inside
-    the kernel) vs the CUDA-core kernel on explicitly partitioned windows vs a plain PyTorch fp32 reference."""
+    the kernel) vs the CUDA-core kernel on explicitly partitioned windows vs a plain PyTorch fp32 reference.  gain > 1
+    spreads the scores (std gain^2 in nats) so that the running maxima of the 14 x 14 kernel's lazy online softmax move in
+    some chunks and stay in others (both branches of attend_chunk)."""
     from gpu_util import act_dtype
     n = ws * ws
     g = torch.Generator(device="cuda").manual_seed(res * 31 + ws + heads)
-    qkv = torch.randn(batch, res, res, heads * 96, device="cuda", generator=g).to(act_dtype())
+    qkv = torch.randn(batch, res, res, heads * 96, device="cuda", generator=g)
+    qkv.view(batch, res, res, heads, 96)[..., :64] *= gain  # q and k
+    qkv = qkv.to(act_dtype())
     pad = torch.randn(heads * 96, device="cuda", generator=g).to(act_dtype())
     bias = torch.randn(heads, n, n, device="cuda", generator=g)
     out = torch.zeros(batch * res * res, heads * 32, device="cuda", dtype=act_dtype())
