@@ -3,6 +3,7 @@
 #include "image_pool.hpp"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -285,7 +286,8 @@ uint8_t* load_pnm(std::vector<uint8_t> const& file, char const* path, int* exten
 // The reference's load_image is stbi_load (image.cpp:11-23), which reads JPEG; test/input/truck.jpg is the one real
 // fixture of the reference.  Restated from the published stb_image algorithm so that pixels come out the way the
 // reference sees them: integer IDCT with 12-bit constants, "hv_2" triangle-filter chroma upsampling, 20-bit fixed-point
-// YCbCr -> RGB.  Progressive and arithmetic-coded files are refused.
+// YCbCr -> RGB.  Sequential (SOF0 / SOF1) and progressive (SOF2) Huffman files, interleaved or one scan per component, with
+// restart intervals; lossless, hierarchical and arithmetic-coded files are refused.
 struct JpegHuff {
     uint8_t size[257];
     uint16_t code[256];
@@ -445,7 +447,8 @@ struct JpegComp {
     int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
     int w2 = 0, h2 = 0;  // padded plane extent
     int dc_pred = 0;
-    std::vector<uint8_t> data;
+    std::vector<short> coef;    // DCT coefficients, 64 per block, blocks in raster order over the padded plane
+    std::vector<uint8_t> data;  // samples
 };
 
 // one row of chroma at full horizontal resolution from the two nearest source rows (3/4 near + 1/4 far vertically,
@@ -483,33 +486,211 @@ void resample_h2(uint8_t* out, uint8_t const* in, int w) {  // stbi__resample_ro
 }
 
 uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* extent, int* channels) {
-    static uint8_t const zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
-                                       41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
-                                       30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    static uint8_t const zigzag[64 + 15] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                            41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                            30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63,
+                                            // (a corrupt run may step past 63: those land on the last coefficient)
+                                            63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
     auto bad = [&](char const* why) { fail(std::string("Failed to load image ") + path + ": " + why); };
     uint16_t quant[4][64] = {};
     JpegHuff dc[4], ac[4];
     bool have_dc[4] = {}, have_ac[4] = {};
     std::vector<JpegComp> comps;
     int W = 0, H = 0, restart = 0, hmax = 1, vmax = 1;
-    bool adobe_transform_rgb = false, jfif = false;
+    bool adobe_transform_rgb = false, progressive = false, any_scan = false;
     size_t pos = 2;
     auto u16 = [&](size_t at) {
         if (at + 2 > file.size()) bad("truncated JPEG");
         return (int)((file[at] << 8) | file[at + 1]);
     };
-    bool scan_found = false;
-    while (!scan_found) {
-        while (pos < file.size() && file[pos] != 0xFF) ++pos;
-        while (pos < file.size() && file[pos] == 0xFF) ++pos;
-        if (pos >= file.size()) bad("no scan in JPEG");
-        int const marker = file[pos++];
+    int mcux = 0, mcuy = 0;
+
+    // One scan (T.81 B.2.3 / G.1): entropy-coded data from file[pos] into the coefficient planes.  Sequential files put whole
+    // (dequantised) blocks there; progressive ones build the coefficients up over several scans -- the first DC scan, DC
+    // refinement bits, AC bands and their refinements (spectral selection ss..se, successive approximation ah / al) --
+    // and are dequantised when the image is complete.  Scans of ONE component walk that component's own blocks in raster
+    // order (not the padded MCU grid).
+    auto decode_scan = [&](std::vector<JpegComp*> const& sc, int ss, int se, int ah, int al) {
+        JpegBits br{file.data(), file.size(), pos};
+        int eob_run = 0;
+        for (JpegComp* c : sc) c->dc_pred = 0;
+        auto getbit = [&]() {
+            if (br.cnt < 1) br.fill();
+            int const b = (int)(br.buf >> 31);
+            br.buf <<= 1;
+            --br.cnt;
+            return b;
+        };
+        auto getbits = [&](int n) {
+            if (n == 0) return 0;
+            if (br.cnt < n) br.fill();
+            int const v = (int)(br.buf >> (32 - n));
+            br.buf <<= n;
+            br.cnt -= n;
+            return v;
+        };
+        auto sequential_block = [&](JpegComp& c, short* blk) {
+            int const t = br.decode(dc[c.td]);
+            if (t > 15) bad("bad DC code");
+            c.dc_pred += br.receive_extend(t);
+            blk[0] = (short)(c.dc_pred * quant[c.tq][0]);
+            for (int k = 1; k < 64;) {
+                int const rs = br.decode(ac[c.ta]);
+                int const s = rs & 15, r = rs >> 4;
+                if (s == 0) {
+                    if (rs != 0xF0) break;  // end of block
+                    k += 16;
+                } else {
+                    k += r;
+                    if (k > 63) bad("bad AC run");
+                    int const z = zigzag[k++];
+                    blk[z] = (short)(br.receive_extend(s) * quant[c.tq][z]);
+                }
+            }
+        };
+        auto progressive_dc = [&](JpegComp& c, short* blk) {
+            if (ah == 0) {  // first pass: the difference, scaled by the point transform
+                int const t = br.decode(dc[c.td]);
+                if (t > 15) bad("bad DC code");
+                c.dc_pred += br.receive_extend(t);
+                blk[0] = (short)(c.dc_pred * (1 << al));
+            } else if (getbit()) {  // refinement: one more bit of precision
+                blk[0] = (short)(blk[0] + (1 << al));
+            }
+        };
+        auto progressive_ac = [&](JpegComp& c, short* blk) {
+            JpegHuff const& h = ac[c.ta];
+            if (ah == 0) {  // first pass over the band ss..se
+                if (eob_run) {
+                    --eob_run;
+                    return;
+                }
+                int k = ss;
+                do {
+                    int const rs = br.decode(h);
+                    int const s = rs & 15, r = rs >> 4;
+                    if (s == 0) {
+                        if (r < 15) {  // end of band for this and the next eob_run blocks
+                            eob_run = 1 << r;
+                            if (r) eob_run += getbits(r);
+                            --eob_run;
+                            break;
+                        }
+                        k += 16;
+                    } else {
+                        k += r;
+                        int const z = zigzag[k++];
+                        blk[z] = (short)(br.receive_extend(s) * (1 << al));
+                    }
+                } while (k <= se);
+                return;
+            }
+            // refinement pass: a correction bit for every coefficient that is already non-zero, new +-1 coefficients in between
+            short const bit = (short)(1 << al);
+            auto refine = [&](short* p) {
+                if (getbit() && (*p & bit) == 0) *p = (short)(*p > 0 ? *p + bit : *p - bit);
+            };
+            if (eob_run) {
+                --eob_run;
+                for (int k = ss; k <= se; ++k) {
+                    short* p = &blk[zigzag[k]];
+                    if (*p != 0) refine(p);
+                }
+                return;
+            }
+            int k = ss;
+            do {
+                int const rs = br.decode(h);
+                int s = rs & 15, r = rs >> 4;
+                if (s == 0) {
+                    if (r < 15) {
+                        eob_run = (1 << r) - 1;
+                        if (r) eob_run += getbits(r);
+                        r = 64;  // run to the end of the band
+                    }  // else: sixteen zero coefficients (only zeros count)
+                } else {
+                    if (s != 1) bad("bad refinement code");
+                    s = getbit() ? bit : -bit;
+                }
+                while (k <= se) {
+                    short* p = &blk[zigzag[k++]];
+                    if (*p != 0) {
+                        refine(p);
+                    } else {
+                        if (r == 0) {
+                            *p = (short)s;
+                            break;
+                        }
+                        --r;
+                    }
+                }
+            } while (k <= se);
+        };
+        auto block = [&](JpegComp& c, int bx, int by) {
+            short* blk = &c.coef[((size_t)by * (size_t)(c.w2 / 8) + (size_t)bx) * 64];
+            if (!progressive) sequential_block(c, blk);
+            else if (ss == 0) progressive_dc(c, blk);
+            else progressive_ac(c, blk);
+        };
+        int todo = restart ? restart : 0x7fffffff;
+        auto after_unit = [&]() {
+            if (--todo > 0) return;
+            // restart interval: byte-align, expect RSTn, reset the predictors and the end-of-band run
+            br.reset();
+            size_t q = br.pos;
+            while (q + 1 < file.size() && !(file[q] == 0xFF && file[q + 1] >= 0xD0 && file[q + 1] <= 0xD7)) {
+                if (file[q] == 0xFF && file[q + 1] != 0 && file[q + 1] != 0xFF) break;  // another marker: the scan is over
+                ++q;
+            }
+            if (q + 1 < file.size() && file[q + 1] >= 0xD0 && file[q + 1] <= 0xD7) br.pos = q + 2;
+            for (JpegComp* c : sc) c->dc_pred = 0;
+            eob_run = 0;
+            todo = restart;
+        };
+        if (sc.size() == 1) {
+            JpegComp& c = *sc[0];
+            int const bw = ((W * c.h + hmax - 1) / hmax + 7) >> 3, bh = ((H * c.v + vmax - 1) / vmax + 7) >> 3;
+            for (int by = 0; by < bh; ++by)
+                for (int bx = 0; bx < bw; ++bx) {
+                    block(c, bx, by);
+                    after_unit();
+                }
+        } else {
+            for (int my = 0; my < mcuy; ++my)
+                for (int mx = 0; mx < mcux; ++mx) {
+                    for (JpegComp* c : sc)
+                        for (int by = 0; by < c->v; ++by)
+                            for (int bx = 0; bx < c->h; ++bx) block(*c, mx * c->h + bx, my * c->v + by);
+                    after_unit();
+                }
+        }
+        pos = br.pos;
+    };
+
+    bool done = false;
+    while (!done) {
+        // next marker: 0xFF, any number of fill 0xFF, a non-zero code (0xFF 0x00 is a stuffed data byte left over from a scan)
+        int marker = 0;
+        while (marker == 0) {
+            while (pos < file.size() && file[pos] != 0xFF) ++pos;
+            while (pos < file.size() && file[pos] == 0xFF) ++pos;
+            if (pos >= file.size()) {
+                if (!any_scan) bad("no scan in JPEG");
+                marker = 0xD9;  // the end-of-image marker is missing: decode what was read
+                break;
+            }
+            marker = file[pos++];
+        }
         if (marker == 0xD8 || marker == 0x01 || (marker >= 0xD0 && marker <= 0xD7)) continue;
-        if (marker == 0xD9) bad("no scan in JPEG");
+        if (marker == 0xD9) {
+            if (!any_scan) bad("no scan in JPEG");
+            break;
+        }
         int const len = u16(pos);
         if (len < 2 || pos + (size_t)len > file.size()) bad("truncated JPEG segment");
         uint8_t const* d = &file[pos + 2];
         int const n = len - 2;
+        pos += (size_t)len;
         switch (marker) {
         case 0xDB:  // quantisation tables
             for (int i = 0; i < n;) {
@@ -519,7 +700,7 @@ uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* exte
                 i += 1 + 64 * (pq + 1);
             }
             break;
-        case 0xC4:  // Huffman tables
+        case 0xC4:  // Huffman tables (progressive files redefine them between scans)
             for (int i = 0; i < n;) {
                 if (i + 17 > n) bad("bad DHT");
                 int const tc = d[i] >> 4, th = d[i] & 15;
@@ -531,13 +712,15 @@ uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* exte
                 i += 17 + total;
             }
             break;
-        case 0xC0: case 0xC1: {  // baseline / extended sequential, Huffman
+        case 0xC0: case 0xC1: case 0xC2: {  // baseline / extended sequential / progressive, Huffman
+            if (!comps.empty()) bad("more than one frame header");
+            progressive = marker == 0xC2;
             if (n < 6 || d[0] != 8) bad("only 8-bit JPEG is supported");
             H = (d[1] << 8) | d[2];
             W = (d[3] << 8) | d[4];
             int const nc = d[5];
             if (W <= 0 || H <= 0 || (nc != 1 && nc != 3) || n < 6 + 3 * nc) bad("unsupported JPEG frame");
-            if ((uint64_t)W * H * 3 > kMaxImageBytes) bad("image too large");
+            if ((uint32_t)W > kMaxImageDim || (uint32_t)H > kMaxImageDim || (uint64_t)W * H * 3 > kMaxImageBytes) bad("image too large");
             comps.resize((size_t)nc);
             for (int i = 0; i < nc; ++i) {
                 comps[(size_t)i].id = d[6 + 3 * i];
@@ -549,88 +732,71 @@ uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* exte
                 hmax = std::max(hmax, comps[(size_t)i].h);
                 vmax = std::max(vmax, comps[(size_t)i].v);
             }
+            // coefficient planes, each padded to whole MCUs
+            mcux = (W + 8 * hmax - 1) / (8 * hmax);
+            mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+            for (auto& c : comps) {
+                c.w2 = mcux * c.h * 8;
+                c.h2 = mcuy * c.v * 8;
+                c.coef.assign((size_t)c.w2 * c.h2, 0);
+            }
             break;
         }
-        case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
-            bad("only baseline (sequential Huffman) JPEG is supported");
+        case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
+            bad("only Huffman-coded sequential and progressive JPEG is supported (no lossless, hierarchical or arithmetic coding)");
             break;
         case 0xDD: restart = n >= 2 ? ((d[0] << 8) | d[1]) : 0; break;
-        case 0xE0: jfif = n >= 5 && !std::memcmp(d, "JFIF", 5); break;
         case 0xEE: if (n >= 12 && !std::memcmp(d, "Adobe", 5)) adobe_transform_rgb = d[11] == 0; break;
         case 0xDA: {
             if (comps.empty()) bad("scan before frame header");
-            int const ns = d[0];
-            if (ns != (int)comps.size() || n < 1 + 2 * ns + 3) bad("only single-scan (interleaved) JPEG is supported");
+            int const ns = n >= 1 ? d[0] : 0;
+            if (ns < 1 || ns > (int)comps.size() || n < 1 + 2 * ns + 3) bad("bad scan header");
+            std::vector<JpegComp*> sc;
             for (int i = 0; i < ns; ++i) {
                 int const cid = d[1 + 2 * i];
                 JpegComp* c = nullptr;
                 for (auto& cc : comps)
                     if (cc.id == cid) c = &cc;
-                if (!c) bad("bad scan component");
+                if (!c || std::find(sc.begin(), sc.end(), c) != sc.end()) bad("bad scan component");
                 c->td = d[2 + 2 * i] >> 4;
                 c->ta = d[2 + 2 * i] & 15;
-                if (c->td > 3 || c->ta > 3 || !have_dc[c->td] || !have_ac[c->ta]) bad("missing Huffman table");
+                if (c->td > 3 || c->ta > 3) bad("bad Huffman table index");
+                sc.push_back(c);
             }
-            scan_found = true;
+            int ss = d[1 + 2 * ns], se = d[2 + 2 * ns];
+            int const ah = d[3 + 2 * ns] >> 4, al = d[3 + 2 * ns] & 15;
+            if (progressive) {
+                if (ss > 63 || se > 63 || ss > se || ah > 13 || al > 13) bad("bad progressive scan parameters");
+                if (ss == 0 && se != 0) bad("bad progressive scan parameters");   // DC and AC never share a scan
+                if (ss > 0 && ns != 1) bad("bad progressive scan parameters");    // AC scans hold one component
+            } else {
+                if (ss != 0 || ah != 0 || al != 0) bad("bad sequential scan parameters");
+                se = 63;
+            }
+            for (JpegComp* c : sc) {
+                bool const need_dc = !progressive || (ss == 0 && ah == 0), need_ac = !progressive || ss > 0;
+                if ((need_dc && !have_dc[c->td]) || (need_ac && !have_ac[c->ta])) bad("missing Huffman table");
+            }
+            decode_scan(sc, ss, se, ah, al);
+            any_scan = true;
             break;
         }
         default: break;  // APPn, COM, ...
         }
-        pos += (size_t)len;
     }
-    (void)jfif;
-    // entropy-coded segment -> component planes (each padded to whole MCUs)
-    int const mcu_w = 8 * hmax, mcu_h = 8 * vmax;
-    int const mcux = (W + mcu_w - 1) / mcu_w, mcuy = (H + mcu_h - 1) / mcu_h;
+    // coefficients -> samples
     for (auto& c : comps) {
-        c.w2 = mcux * c.h * 8;
-        c.h2 = mcuy * c.v * 8;
         c.data.assign((size_t)c.w2 * c.h2, 0);
+        int const bw = c.w2 / 8, bh = c.h2 / 8;
+        for (int by = 0; by < bh; ++by)
+            for (int bx = 0; bx < bw; ++bx) {
+                short* blk = &c.coef[((size_t)by * bw + bx) * 64];
+                if (progressive)
+                    for (int k = 0; k < 64; ++k) blk[k] = (short)(blk[k] * quant[c.tq][k]);
+                jpeg_idct_block(&c.data[(size_t)(by * 8) * c.w2 + (size_t)bx * 8], c.w2, blk);
+            }
+        std::vector<short>().swap(c.coef);
     }
-    JpegBits br{file.data(), file.size(), pos};
-    int todo = restart ? restart : 0x7fffffff;
-    auto decode_block = [&](JpegComp& c, short (&blk)[64]) {
-        std::memset(blk, 0, sizeof(blk));
-        int const t = br.decode(dc[c.td]);
-        if (t > 15) bad("bad DC code");
-        int const diff = br.receive_extend(t);
-        c.dc_pred += diff;
-        blk[0] = (short)(c.dc_pred * quant[c.tq][0]);
-        for (int k = 1; k < 64;) {
-            int const rs = br.decode(ac[c.ta]);
-            int const s = rs & 15, r = rs >> 4;
-            if (s == 0) {
-                if (rs != 0xF0) break;  // end of block
-                k += 16;
-            } else {
-                k += r;
-                if (k > 63) bad("bad AC run");
-                int const z = zigzag[k++];
-                blk[z] = (short)(br.receive_extend(s) * quant[c.tq][z]);
-            }
-        }
-    };
-    for (int my = 0; my < mcuy; ++my)
-        for (int mx = 0; mx < mcux; ++mx) {
-            for (auto& c : comps)
-                for (int by = 0; by < c.v; ++by)
-                    for (int bx = 0; bx < c.h; ++bx) {
-                        short blk[64];
-                        decode_block(c, blk);
-                        jpeg_idct_block(&c.data[(size_t)((my * c.v + by) * 8) * c.w2 + (size_t)(mx * c.h + bx) * 8], c.w2, blk);
-                    }
-            if (--todo <= 0) {  // restart interval: byte-align, expect RSTn, reset the predictors
-                br.reset();
-                size_t q = br.pos;
-                while (q + 1 < file.size() && !(file[q] == 0xFF && file[q + 1] >= 0xD0 && file[q + 1] <= 0xD7)) {
-                    if (file[q] == 0xFF && file[q + 1] == 0xD9) break;
-                    ++q;
-                }
-                if (q + 1 < file.size() && file[q + 1] != 0xD9) br.pos = q + 2;
-                for (auto& c : comps) c.dc_pred = 0;
-                todo = restart;
-            }
-        }
     // planes -> interleaved pixels
     int const nc = (int)comps.size();
     uint8_t* px = image_alloc((size_t)W * H * (nc == 1 ? 1 : 3));
@@ -702,6 +868,264 @@ uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* exte
     return px;
 }
 
+// ---- BMP and TGA (the reference's load_image documents "PNG, JPEG, BMP, TGA", dlimgedit.hpp:59) -----------------
+// Restated from the published stb_image behaviour the reference sees: BMP with 1 / 4 / 8-bit palettes, 16-bit (5-5-5 or
+// bit fields), 24-bit and 32-bit pixels (bit fields or plain, where an all-zero alpha channel reads as opaque), bottom-up
+// or top-down, no RLE; TGA of types 1 / 2 / 3 and their run-length forms 9 / 10 / 11 with 8, 15 / 16, 24 or 32 bits per
+// pixel and either vertical origin.  Output channels: 3, or 4 when the file carries alpha, or 1 for 8-bit grey TGA.
+int high_bit(uint32_t z) {
+    int n = 0;
+    if (z == 0) return -1;
+    if (z >= 0x10000) { n += 16; z >>= 16; }
+    if (z >= 0x00100) { n += 8; z >>= 8; }
+    if (z >= 0x00010) { n += 4; z >>= 4; }
+    if (z >= 0x00004) { n += 2; z >>= 2; }
+    if (z >= 0x00002) { n += 1; }
+    return n;
+}
+int bit_count(uint32_t a) {
+    int n = 0;
+    for (; a; a &= a - 1) ++n;
+    return n;
+}
+// a field of `bits` bits at `shift` -> 8 bits by replicating the bit pattern
+int shift_signed(uint32_t v, int shift, int bits) {
+    static uint32_t const mul_table[9] = {0, 0xff, 0x55, 0x49, 0x11, 0x21, 0x41, 0x81, 0x01};
+    static uint32_t const shift_table[9] = {0, 0, 0, 1, 0, 2, 4, 6, 0};
+    if (shift < 0) v <<= -shift;
+    else v >>= shift;
+    v >>= (8 - bits);
+    return (int)((v * mul_table[bits]) >> shift_table[bits]);
+}
+
+uint8_t* load_bmp(std::vector<uint8_t> const& file, char const* path, int* extent, int* channels) {
+    auto bad = [&](char const* why) { fail(std::string("Failed to load image ") + path + ": " + why); };
+    auto le16 = [&](size_t at) -> uint32_t {
+        if (at + 2 > file.size()) bad("truncated BMP");
+        return (uint32_t)file[at] | ((uint32_t)file[at + 1] << 8);
+    };
+    auto le32 = [&](size_t at) -> uint32_t { return le16(at) | (le16(at + 2) << 16); };
+    uint32_t const offset = le32(10), hsz = le32(14);
+    if (hsz != 12 && hsz != 40 && hsz != 56 && hsz != 108 && hsz != 124) bad("unknown BMP header");
+    int w, h, bpp;
+    uint32_t compress = 0, mr = 0, mg = 0, mb = 0, ma = 0;
+    bool all_a_check = false;
+    if (hsz == 12) {
+        w = (int)le16(18);
+        h = (int)le16(20);
+        if (le16(22) != 1) bad("bad BMP");
+        bpp = (int)le16(24);
+    } else {
+        w = (int)le32(18);
+        h = (int)le32(22);
+        if (le16(26) != 1) bad("bad BMP");
+        bpp = (int)le16(28);
+        compress = le32(30);
+        if (compress == 1 || compress == 2) bad("run-length encoded BMP is not supported");
+        if (compress >= 4) bad("BMP with embedded JPEG / PNG is not supported");
+        if (compress == 3 && bpp != 16 && bpp != 32) bad("bad BMP");
+        if (hsz == 40 || hsz == 56) {
+            if (bpp == 16 || bpp == 32) {
+                if (compress == 0) {
+                    if (bpp == 32) { mr = 0xffu << 16; mg = 0xffu << 8; mb = 0xffu; ma = 0xffu << 24; all_a_check = true; }
+                    else { mr = 31u << 10; mg = 31u << 5; mb = 31u; }
+                } else {  // bit fields behind the 40-byte header (56-byte headers hold them inside)
+                    mr = le32(54); mg = le32(58); mb = le32(62);
+                    if (hsz == 56) ma = le32(66);
+                    if (mr == mg && mg == mb) bad("bad BMP");
+                }
+            }
+        } else {  // V4 / V5 headers always carry the masks
+            mr = le32(54); mg = le32(58); mb = le32(62); ma = le32(66);
+            if (compress != 3 && (bpp == 16 || bpp == 32)) {
+                if (bpp == 32) { mr = 0xffu << 16; mg = 0xffu << 8; mb = 0xffu; ma = 0xffu << 24; all_a_check = true; }
+                else { mr = 31u << 10; mg = 31u << 5; mb = 31u; ma = 0; }
+            }
+        }
+    }
+    bool const flip = h > 0;  // positive height: rows are stored bottom-up
+    if (h < 0) h = -h;
+    if (h == INT32_MIN || w <= 0 || h <= 0 || (uint32_t)w > kMaxImageDim || (uint32_t)h > kMaxImageDim) bad("bad BMP extent");
+    if (bpp != 1 && bpp != 4 && bpp != 8 && bpp != 16 && bpp != 24 && bpp != 32) bad("unsupported BMP bit depth");
+    int const out_ch = ma ? 4 : 3;
+    if ((uint64_t)w * h * out_ch > kMaxImageBytes) bad("image too large");
+    int psize = 0;
+    if (bpp < 16) {
+        if (hsz == 12) psize = ((int)offset - 14 - 12) / 3;
+        else psize = ((int)offset - 14 - (int)hsz) >> 2;
+        if (psize <= 0 || psize > 256) bad("bad BMP palette");
+    }
+    size_t const row_in = (((size_t)w * bpp + 31) / 32) * 4;
+    if ((size_t)offset + row_in * (size_t)h > file.size()) bad("truncated BMP");
+    uint8_t* px = image_alloc((size_t)w * h * out_ch);
+    if (bpp < 16) {
+        uint8_t pal[256][3] = {};
+        size_t pp = 14 + hsz;
+        for (int i = 0; i < psize; ++i) {
+            if (pp + 3 > file.size()) { image_free(px); bad("truncated BMP"); }
+            pal[i][2] = file[pp]; pal[i][1] = file[pp + 1]; pal[i][0] = file[pp + 2];
+            pp += hsz == 12 ? 3 : 4;
+        }
+        for (int y = 0; y < h; ++y) {
+            uint8_t const* src = &file[offset + row_in * (size_t)y];
+            uint8_t* dst = px + (size_t)(flip ? h - 1 - y : y) * w * 3;
+            for (int x = 0; x < w; ++x) {
+                int v;
+                if (bpp == 8) v = src[x];
+                else if (bpp == 4) v = (src[x >> 1] >> ((x & 1) ? 0 : 4)) & 15;
+                else v = (src[x >> 3] >> (7 - (x & 7))) & 1;
+                dst[3 * x] = pal[v][0]; dst[3 * x + 1] = pal[v][1]; dst[3 * x + 2] = pal[v][2];
+            }
+        }
+    } else {
+        int rshift = 0, gshift = 0, bshift = 0, ashift = 0, rcount = 0, gcount = 0, bcount = 0, acount = 0;
+        bool const easy24 = bpp == 24, easy32 = bpp == 32 && mb == 0xffu && mg == 0xff00u && mr == 0x00ff0000u && ma == 0xff000000u;
+        if (!easy24 && !easy32) {
+            if (!mr || !mg || !mb) { image_free(px); bad("bad BMP masks"); }
+            rshift = high_bit(mr) - 7; rcount = bit_count(mr);
+            gshift = high_bit(mg) - 7; gcount = bit_count(mg);
+            bshift = high_bit(mb) - 7; bcount = bit_count(mb);
+            ashift = high_bit(ma) - 7; acount = bit_count(ma);
+            if (rcount > 8 || gcount > 8 || bcount > 8 || acount > 8) { image_free(px); bad("bad BMP masks"); }
+        }
+        uint32_t all_a = 0;
+        for (int y = 0; y < h; ++y) {
+            uint8_t const* src = &file[offset + row_in * (size_t)y];
+            uint8_t* dst = px + (size_t)(flip ? h - 1 - y : y) * w * out_ch;
+            for (int x = 0; x < w; ++x) {
+                if (easy24 || easy32) {
+                    uint8_t const* s = src + (size_t)x * (bpp / 8);
+                    dst[0] = s[2]; dst[1] = s[1]; dst[2] = s[0];
+                    if (out_ch == 4) { dst[3] = easy32 ? s[3] : 255; all_a |= dst[3]; }
+                } else {
+                    uint32_t const v = bpp == 16 ? ((uint32_t)src[2 * x] | ((uint32_t)src[2 * x + 1] << 8))
+                                                 : ((uint32_t)src[4 * x] | ((uint32_t)src[4 * x + 1] << 8) | ((uint32_t)src[4 * x + 2] << 16) | ((uint32_t)src[4 * x + 3] << 24));
+                    dst[0] = (uint8_t)shift_signed(v & mr, rshift, rcount);
+                    dst[1] = (uint8_t)shift_signed(v & mg, gshift, gcount);
+                    dst[2] = (uint8_t)shift_signed(v & mb, bshift, bcount);
+                    if (out_ch == 4) { dst[3] = ma ? (uint8_t)shift_signed(v & ma, ashift, acount) : 255; all_a |= dst[3]; }
+                }
+                dst += out_ch;
+            }
+        }
+        if (out_ch == 4 && all_a_check && all_a == 0)  // plain 32-bit files usually leave the fourth byte at zero: opaque
+            for (size_t i = 3; i < (size_t)w * h * 4; i += 4) px[i] = 255;
+    }
+    extent[0] = w; extent[1] = h; *channels = out_ch;
+    return px;
+}
+
+bool looks_like_tga(std::vector<uint8_t> const& f) {
+    if (f.size() < 18) return false;
+    int const cmap = f[1], type = f[2], bpp = f[16];
+    if (cmap > 1) return false;
+    if (cmap == 1) {
+        if (type != 1 && type != 9) return false;
+        int const pb = f[7];
+        if (pb != 8 && pb != 15 && pb != 16 && pb != 24 && pb != 32) return false;
+    } else if (type != 2 && type != 3 && type != 10 && type != 11) {
+        return false;
+    }
+    if ((f[12] | (f[13] << 8)) < 1 || (f[14] | (f[15] << 8)) < 1) return false;
+    if (cmap == 1 && bpp != 8 && bpp != 16) return false;
+    return bpp == 8 || bpp == 15 || bpp == 16 || bpp == 24 || bpp == 32;
+}
+
+uint8_t* load_tga(std::vector<uint8_t> const& file, char const* path, int* extent, int* channels) {
+    auto bad = [&](char const* why) { fail(std::string("Failed to load image ") + path + ": " + why); };
+    int const id_len = file[0], indexed = file[1];
+    int type = file[2];
+    int const pal_start = file[3] | (file[4] << 8), pal_len = file[5] | (file[6] << 8), pal_bits = file[7];
+    int const w = file[12] | (file[13] << 8), h = file[14] | (file[15] << 8), bpp = file[16];
+    bool const top_down = (file[17] >> 5) & 1;
+    bool const rle = type >= 8;
+    if (rle) type -= 8;
+    auto comp_of = [&](int bits, bool grey) {
+        switch (bits) {
+        case 8: return 1;
+        case 15: case 16: return grey ? 2 : 3;
+        case 24: return 3;
+        case 32: return 4;
+        default: return 0;
+        }
+    };
+    int const comp = indexed ? comp_of(pal_bits, false) : comp_of(bpp, type == 3);
+    if (comp == 0) bad("bad TGA pixel format");
+    if (comp == 2) bad("16-bit grey + alpha TGA has no counterpart among the image channel orders");
+    if (indexed && bpp != 8 && bpp != 16) bad("bad TGA index size");
+    bool const rgb16 = !indexed ? (bpp == 15 || bpp == 16) : (pal_bits == 15 || pal_bits == 16);
+    size_t pos = 18 + (size_t)id_len;
+    auto need = [&](size_t n) {
+        if (pos + n > file.size()) bad("truncated TGA");
+    };
+    auto put_pixel = [&](uint8_t const* raw, uint8_t* out) {  // one stored pixel (file order) -> output order
+        if (rgb16) {
+            int const v = raw[0] | (raw[1] << 8);
+            out[0] = (uint8_t)((((v >> 10) & 31) * 255) / 31);
+            out[1] = (uint8_t)((((v >> 5) & 31) * 255) / 31);
+            out[2] = (uint8_t)(((v & 31) * 255) / 31);
+        } else if (comp == 1) {
+            out[0] = raw[0];
+        } else {
+            out[0] = raw[2]; out[1] = raw[1]; out[2] = raw[0];
+            if (comp == 4) out[3] = raw[3];
+        }
+    };
+    int const pal_entry = indexed ? (pal_bits + 7) / 8 : 0;
+    std::vector<uint8_t> palette;
+    if (indexed) {
+        if (pal_len == 0) bad("bad TGA palette");
+        need((size_t)pal_len * pal_entry);
+        palette.assign(file.begin() + (long)pos, file.begin() + (long)(pos + (size_t)pal_len * pal_entry));
+        pos += (size_t)pal_len * pal_entry;
+    }
+    (void)pal_start;  // (entries are addressed from zero, like the reference's reader does)
+    if ((uint64_t)w * h * comp > kMaxImageBytes) bad("image too large");
+    uint8_t* px = image_alloc((size_t)w * h * comp);
+    int const stored = indexed ? bpp / 8 : (bpp + 7) / 8;
+    uint8_t raw[4] = {};
+    uint8_t cur[4] = {};
+    int rle_count = 0;
+    bool rle_repeat = false, have = false;
+    try {
+        for (size_t i = 0; i < (size_t)w * h; ++i) {
+            bool read_next = true;
+            if (rle) {
+                if (rle_count == 0) {
+                    need(1);
+                    int const cmd = file[pos++];
+                    rle_count = 1 + (cmd & 127);
+                    rle_repeat = (cmd >> 7) != 0;
+                    have = false;
+                } else if (rle_repeat && have) {
+                    read_next = false;
+                }
+            }
+            if (read_next) {
+                need((size_t)stored);
+                if (indexed) {
+                    int idx = stored == 1 ? file[pos] : (file[pos] | (file[pos + 1] << 8));
+                    if (idx >= pal_len) idx = 0;
+                    std::memcpy(raw, &palette[(size_t)idx * pal_entry], (size_t)pal_entry);
+                } else {
+                    std::memcpy(raw, &file[pos], (size_t)stored);
+                }
+                pos += (size_t)stored;
+                put_pixel(raw, cur);
+                have = true;
+            }
+            size_t const y = i / (size_t)w, x = i % (size_t)w;
+            std::memcpy(px + ((top_down ? y : (size_t)h - 1 - y) * (size_t)w + x) * comp, cur, (size_t)comp);
+            if (rle) --rle_count;
+        }
+    } catch (...) {
+        image_free(px);
+        throw;
+    }
+    extent[0] = w; extent[1] = h; *channels = comp;
+    return px;
+}
+
 void chunk(std::vector<uint8_t>& out, char const* type, std::vector<uint8_t> const& data) {
     put_be32(out, (uint32_t)data.size());
     size_t const start = out.size();
@@ -718,7 +1142,9 @@ uint8_t* load_image(char const* filepath, int* out_extent, int* out_channels) {
     if (file.size() > 8 && !std::memcmp(file.data(), png_sig, 8)) return load_png(file, filepath, out_extent, out_channels);
     if (file.size() > 2 && file[0] == 'P' && (file[1] == '5' || file[1] == '6')) return load_pnm(file, filepath, out_extent, out_channels);
     if (file.size() > 4 && file[0] == 0xFF && file[1] == 0xD8) return load_jpeg(file, filepath, out_extent, out_channels);
-    fail(std::string("Failed to load image ") + filepath + ": unsupported format (PNG, baseline JPEG and binary PGM/PPM are supported)");
+    if (file.size() > 26 && file[0] == 'B' && file[1] == 'M') return load_bmp(file, filepath, out_extent, out_channels);
+    if (looks_like_tga(file)) return load_tga(file, filepath, out_extent, out_channels);  // (no signature: tested last)
+    fail(std::string("Failed to load image ") + filepath + ": unsupported format (PNG, JPEG, BMP, TGA and binary PGM/PPM are supported)");
 }
 
 // reference image.cpp:25-35: mask / rgb / rgba only, rows written packed (the reference also ignores stride)

@@ -149,7 +149,7 @@ def test_srgb_tables_match_oracle():
         assert L.ref_linear_to_srgb8(float(np.nextafter(t, np.float32(-1)))) == i - 1
 
 
-def test_load_image_reads_baseline_jpeg(tmp_path):
+def test_load_image_reads_jpeg(tmp_path):
     """reference image.cpp:11-23 loads JPEG through stb_image; the library's own decoder restates stb's integer IDCT,
     hv_2 chroma upsampling and fixed-point YCbCr -> RGB.  Checked against libjpeg-turbo (PIL): the two decoders may
     differ by a few LSB (different IDCT rounding / upsampling rounding), not more."""
@@ -182,10 +182,86 @@ def test_load_image_reads_baseline_jpeg(tmp_path):
         ref = np.asarray(Image.open(f).convert(mode)).reshape(97, 131, n)
         d = np.abs(got.astype(int) - ref.astype(int))
         assert n == (3 if mode == "RGB" else 1) and d.max() <= 6 and d.mean() < 0.6, (name, d.max(), d.mean())
-    prog = str(tmp_path / "progressive.jpg")
-    Image.fromarray(pic).save(prog, progressive=True)
-    assert a.load_image(prog.encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 1
-    assert b"baseline" in a.last_error()
+    # progressive files (spectral selection + successive approximation, one component per AC scan) hold the same
+    # coefficients as their sequential twins, so they must decode to exactly the same pixels
+    for name, kw, src in (("444", dict(subsampling=0), pic), ("422", dict(subsampling=1), pic), ("420", dict(subsampling=2), pic),
+                          ("grey", {}, pic[..., 0])):
+        for q in (35, 92):
+            fb, fp = str(tmp_path / f"{name}_{q}_b.jpg"), str(tmp_path / f"{name}_{q}_p.jpg")
+            Image.fromarray(src).save(fb, quality=q, **kw)
+            Image.fromarray(src).save(fp, quality=q, progressive=True, **kw)
+            assert open(fp, "rb").read().count(b"\xff\xc2") >= 1  # really SOF2
+            base, prog = dl.Image.load(fb), dl.Image.load(fp)
+            assert np.array_equal(base.pixels, prog.pixels), (name, q)
+    rst = str(tmp_path / "restart.jpg")
+    try:
+        Image.fromarray(pic).save(rst, quality=80, progressive=True, restart_marker_blocks=3)
+        has_rst = b"\xff\xdd" in open(rst, "rb").read()
+    except TypeError:
+        has_rst = False
+    if has_rst:
+        plain = str(tmp_path / "norestart.jpg")
+        Image.fromarray(pic).save(plain, quality=80, progressive=True)
+        assert np.array_equal(dl.Image.load(rst).pixels, dl.Image.load(plain).pixels)
+    lossless = bytearray(open(str(tmp_path / "444.jpg"), "rb").read())
+    lossless[lossless.index(b"\xff\xc0") + 1] = 0xC9  # pretend: arithmetic-coded frame
+    (tmp_path / "arith.jpg").write_bytes(bytes(lossless))
+    assert a.load_image(str(tmp_path / "arith.jpg").encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 1
+    assert b"arithmetic" in a.last_error()
+
+
+def test_load_image_reads_bmp_and_tga(tmp_path):
+    """dlimgedit.hpp:59: "Supported formats are PNG, JPEG, BMP, TGA" (stb_image behind image.cpp:11-23).  Files written by
+    PIL; decoded pixels must equal the source exactly (these formats are lossless)."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    pic = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    pic[5:15] = pic[4]
+    pic[:, 10:30] = pic[:, 9:10]  # runs for the RLE forms
+    rgba = np.dstack([pic, rng.integers(1, 256, (37, 53), dtype=np.uint8)])
+    pal = Image.fromarray(pic).quantize(64)
+    pal_rgb = np.asarray(pal.convert("RGB"))
+    grey = pic[..., 0]
+    cases = [("24.bmp", Image.fromarray(pic), {}, pic), ("32.bmp", Image.fromarray(rgba), {}, rgba),
+             ("p8.bmp", pal, {}, pal_rgb), ("l8.bmp", Image.fromarray(grey), {}, np.dstack([grey] * 3)),
+             ("1.bmp", Image.fromarray(grey > 127), {}, np.dstack([(grey > 127).astype(np.uint8) * 255] * 3)),
+             ("24.tga", Image.fromarray(pic), {}, pic), ("24r.tga", Image.fromarray(pic), dict(compression="tga_rle"), pic),
+             ("32.tga", Image.fromarray(rgba), {}, rgba), ("32r.tga", Image.fromarray(rgba), dict(compression="tga_rle"), rgba),
+             ("l.tga", Image.fromarray(grey), {}, grey), ("lr.tga", Image.fromarray(grey), dict(compression="tga_rle"), grey),
+             ("p.tga", pal, {}, pal_rgb), ("pr.tga", pal, dict(compression="tga_rle"), pal_rgb),
+             ("top.tga", Image.fromarray(pic), dict(orientation=1), pic)]
+    for name, img, kw, want in cases:
+        f = tmp_path / name
+        img.save(f, **kw)
+        got = dl.Image.load(f)
+        assert got.pixels.shape == want.shape, (name, got.pixels.shape)
+        assert np.array_equal(got.pixels, want), name
+    # 16-bit 5-5-5 BMP: bit patterns are replicated to 8 bits; a 32-bit file whose fourth byte is zero everywhere is opaque
+    import struct
+    w, h = 5, 3
+    v = rng.integers(0, 1 << 15, (h, w), dtype=np.uint16)
+    rows = b"".join(v[h - 1 - y].astype("<u2").tobytes() + b"\0" * ((4 - (2 * w) % 4) % 4) for y in range(h))
+    hdr = b"BM" + struct.pack("<IHHI", 54 + len(rows), 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, w, h, 1, 16, 0, len(rows), 0, 0, 0, 0)
+    (tmp_path / "555.bmp").write_bytes(hdr + rows)
+    got = dl.Image.load(tmp_path / "555.bmp").pixels
+    def rep(x):
+        return (x << 3) | (x >> 2)
+    want = np.dstack([rep((v >> 10) & 31), rep((v >> 5) & 31), rep(v & 31)]).astype(np.uint8)
+    assert np.array_equal(got, want)
+    bgr0 = np.dstack([pic[:h, :w, ::-1], np.zeros((h, w), np.uint8)])
+    rows = b"".join(bgr0[h - 1 - y].tobytes() for y in range(h))
+    hdr = b"BM" + struct.pack("<IHHI", 54 + len(rows), 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, w, -h, 1, 32, 0, len(rows), 0, 0, 0, 0)
+    (tmp_path / "x32.bmp").write_bytes(hdr + b"".join(bgr0[y].tobytes() for y in range(h)))  # negative height: top-down
+    got = dl.Image.load(tmp_path / "x32.bmp").pixels
+    assert got.shape == (h, w, 4) and np.array_equal(got[..., :3], pic[:h, :w]) and (got[..., 3] == 255).all()
+    a = dl.api()
+    ext = (ctypes.c_int * 2)()
+    ch = ctypes.c_int()
+    px = ctypes.c_void_p()
+    (tmp_path / "cut.bmp").write_bytes(open(tmp_path / "24.bmp", "rb").read()[:200])
+    assert a.load_image(str(tmp_path / "cut.bmp").encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 1 and b"truncated" in a.last_error()
+    (tmp_path / "cut.tga").write_bytes(open(tmp_path / "24r.tga", "rb").read()[:100])
+    assert a.load_image(str(tmp_path / "cut.tga").encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 1 and b"truncated" in a.last_error()
 
 
 def test_load_image_rejects_hostile_png_headers(tmp_path):
