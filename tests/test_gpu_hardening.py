@@ -179,3 +179,39 @@ def test_counters_and_profile_are_per_environment(env, model_dir):
         assert env.stats()["kernel_launches"] == before  # the other environment's launches are not counted here
     finally:
         other.close()
+
+
+def test_many_handles_leave_no_device_or_pinned_memory_behind(env):
+    """The reference's usage pattern is a long-lived Environment with one short-lived Segmentation per opened image
+    (README.md:20-33).  After a warm-up the device pool and the page-locked image pool must be stable over many
+    process -> compute_mask -> destroy cycles of differently sized images."""
+    import ctypes
+    import torch
+    sizes = [(300, 500, 3), (640, 480, 4), (1024, 1024, 4), (720, 1280, 3)]
+    imgs = [synthetic_image(h, w, c, seed=20 + i) for i, (h, w, c) in enumerate(sizes)]
+
+    def cycle(i):
+        img = imgs[i % len(imgs)]
+        ch = dl.Channels.rgb if img.shape[2] == 3 else dl.Channels.rgba
+        seg = dl.Segmentation.process(dl.ImageView(img, channels=ch), env)
+        m = seg.compute_mask(dl.Point(img.shape[1] // 2, img.shape[0] // 2))
+        assert m.shape == img.shape[:2]
+        seg.close()
+
+    def pool_in_use():
+        st = (ctypes.c_uint64 * 5)()
+        dl.debug().image_pool_stats(st)
+        return st[0]
+
+    for i in range(8):
+        cycle(i)
+    env.synchronize()
+    torch.cuda.synchronize()
+    free0, pinned0 = torch.cuda.mem_get_info()[0], pool_in_use()
+    for i in range(120):
+        cycle(i)
+    env.synchronize()
+    torch.cuda.synchronize()
+    free1, pinned1 = torch.cuda.mem_get_info()[0], pool_in_use()
+    assert free0 - free1 < (64 << 20), (free0, free1)  # device memory: nothing accumulates
+    assert pinned1 == pinned0                          # every mask buffer went back to the pool
