@@ -452,7 +452,15 @@ void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, boo
                            views[start + i + run].pixels == v.pixels + image_bytes * (size_t)run)
                         ++run;
                 if (packed) {
-                    CUDA_CHECK(cudaMemcpyAsync(dst, v.pixels, image_bytes * (size_t)run, cudaMemcpyHostToDevice, copy_in_));
+                    cudaError_t const merged = cudaMemcpyAsync(dst, v.pixels, image_bytes * (size_t)run, cudaMemcpyHostToDevice, copy_in_);
+                    if (merged == cudaErrorInvalidValue && run > 1) {  // separate page-locked allocations that happen to be neighbours
+                        cudaGetLastError();
+                        for (int r = 0; r < run; ++r)
+                            CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)r * image_bytes, v.pixels + (size_t)r * image_bytes, image_bytes,
+                                                       cudaMemcpyHostToDevice, copy_in_));
+                    } else {
+                        CUDA_CHECK(merged);
+                    }
                 } else {
                     CUDA_CHECK(cudaMemcpy2DAsync(dst, row_bytes, v.pixels, (size_t)v.stride, row_bytes, (size_t)v.height,
                                                  cudaMemcpyHostToDevice, copy_in_));
@@ -611,7 +619,20 @@ void EnvironmentImpl::compute_masks_batch(SegmentationImpl* const* segs, dlimg_b
                     run_bytes += (size_t)sg->width() * sg->height();
                     ++k1;
                 }
-                CUDA_CHECK(cudaMemcpyAsync(host_dst, staging_dev + first_off, run_bytes, cudaMemcpyDeviceToHost, copy_out_));
+                cudaError_t const merged = cudaMemcpyAsync(host_dst, staging_dev + first_off, run_bytes, cudaMemcpyDeviceToHost, copy_out_);
+                if (merged == cudaErrorInvalidValue && k1 - k > 1) {
+                    // neighbouring buffers that are SEPARATE page-locked allocations: one copy may not span them
+                    cudaGetLastError();
+                    size_t off = 0;
+                    for (int kk = k; kk < k1; ++kk) {
+                        SegmentationImpl const* sg = segs[i + kk / n];
+                        size_t const bytes = (size_t)sg->width() * sg->height();
+                        CUDA_CHECK(cudaMemcpyAsync(host_dst + off, staging_dev + first_off + off, bytes, cudaMemcpyDeviceToHost, copy_out_));
+                        off += bytes;
+                    }
+                } else {
+                    CUDA_CHECK(merged);
+                }
                 k = k1;
             }
             counters_.d2h_bytes += total_bytes;

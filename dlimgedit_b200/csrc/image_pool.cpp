@@ -29,10 +29,10 @@ Pool& pool() {
     return *p;
 }
 
-size_t rounded(size_t bytes) {
-    size_t const unit = bytes >= ((size_t)1 << 20) ? (size_t)1 << 20 : kMinPinned;
-    return (bytes + unit - 1) / unit * unit;
-}
+// Block size of a request: whole 64 KiB units and always at least one byte more than asked for, so that two blocks that
+// happen to be neighbours in the address space never look like ONE contiguous run of images to the engine (it merges
+// the copies of buffers that follow each other exactly, and a copy must not span two page-locked allocations).
+size_t rounded(size_t bytes) { return (bytes / kMinPinned + 1) * kMinPinned; }
 
 // cudaHostAlloc / cudaFreeHost initialise the CALLING thread's current device; the caller of create_image may never have
 // touched CUDA, so the calls run with the environment's device current and leave the thread as they found it.

@@ -199,3 +199,49 @@ def test_images_outlive_their_environment(model_dir):
     del img
     after = _pool()
     assert after["in_use"] == base["in_use"]
+
+
+def test_neighbouring_page_locked_buffers_are_not_copied_as_one(env):
+    """The engine merges the copies of host buffers that follow each other exactly; two SEPARATE page-locked regions
+    that happen to be neighbours cannot be spanned by one cudaMemcpyAsync (cudaErrorInvalidValue), so the merged copy
+    falls back to one copy per buffer.  Seen with three 1 MiB masks from three neighbouring cudaHostAlloc blocks."""
+    import torch
+    rt = torch.cuda.cudart()
+    n = 1024 * 1024
+    raw = np.empty(4 * n + 4096, np.uint8)
+    off = (-raw.ctypes.data) % 4096
+    base = raw[off:off + 4 * n]
+    parts = [base[k * n:(k + 1) * n] for k in range(4)]
+    registered = []
+    try:
+        for p in parts:  # four separate registrations, back to back in the address space
+            assert int(rt.cudaHostRegister(p.ctypes.data, n, 0)) == 0
+            registered.append(p.ctypes.data)
+        rng = np.random.default_rng(5)
+        img = synthetic_image(1024, 1024, 4, seed=31)
+        # input side: two images in neighbouring registrations go through process_batch as one packed run
+        parts[0][:] = 0
+        two = [parts[2].reshape(512, 512, 4), parts[3].reshape(512, 512, 4)]
+        two[0][:] = img[:512, :512]
+        two[1][:] = img[512:, 512:]
+        segs2 = env.process_batch([dl.ImageView(t, channels=dl.Channels.rgba) for t in two])
+        env.synchronize()
+        for t, s2 in zip(two, segs2):
+            alone = dl.Segmentation.process(dl.ImageView(t.copy(), channels=dl.Channels.rgba), env)
+            assert np.array_equal(s2.embedding(), alone.embedding())
+            alone.close()
+            s2.close()
+        # output side: masks of consecutive prompts into neighbouring registrations
+        seg = dl.Segmentation.process(dl.ImageView(img, channels=dl.Channels.rgba), env)
+        prompts = [dl.Point(int(rng.integers(0, 1024)), int(rng.integers(0, 1024))) for _ in range(2)]
+        ref, _ = env.compute_masks_batch([seg] * 2, prompts, multi=False)
+        outs = [parts[0].reshape(1, 1024, 1024), parts[1].reshape(1, 1024, 1024)]
+        ious = np.empty((2, 1), np.float32)
+        env.compute_masks_batch([seg] * 2, prompts, multi=False, host_out=outs, host_ious=ious)
+        for a, b in zip(outs, ref):
+            assert np.array_equal(a, b)
+        seg.close()
+    finally:
+        env.synchronize()
+        for addr in registered:
+            rt.cudaHostUnregister(addr)
