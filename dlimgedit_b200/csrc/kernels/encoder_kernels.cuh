@@ -89,12 +89,11 @@ void layernorm_stats(cudaStream_t s, act_t const* in, int rows, int C, float eps
 // attention_bias_fragments().
 void window_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int ws, int heads, act_t const* pad_qkv,
                       uint16_t const* bias_frag, act_t* out, int num_sms);
-// Size of the fragment-ordered bias table in uint16 slots (two per fp32 value).
+// Number of fp16 values of the fragment-ordered bias table.
 size_t attention_bias_fragment_count(int heads, int ws);
-// dense (heads, n, n) fp32 -> fp32 [head][query tile (16)][key block (8)][lane (32)][4], values divided by the qk scale
-// (they initialise the accumulators of Q K^T); for lane = 4*g + t the four values are (row g, col 2t), (g, 2t+1),
-// (g+8, 2t), (g+8, 2t+1) of the 16 x 8 block; key columns beyond n hold -inf (which masks them in the softmax), query
-// rows beyond n hold 0.
+// dense (heads, n, n) fp32 -> fp16 [head][query tile (16)][key block (8)][lane (32)][4], values scaled by log2(e); for
+// lane = 4*g + t the four values are (row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1) of the 16 x 8 block; key columns
+// beyond n hold -inf (which masks them in the softmax), query rows beyond n hold 0.
 void attention_bias_fragments(float const* dense, int heads, int ws, uint16_t* out);
 // CUDA-core reference of the attention core on already partitioned windows, dense (heads, n, n) fp32 bias; qkv
 // (windows*n, heads*96) -> out (windows*n, heads*32).  Cross-check in tests.

@@ -8,10 +8,10 @@
 // rows of padding tokens ever exist in HBM.
 //
 // CTAs are persistent over (window, head group) items with a fixed head group, so the relative-position bias of
-// those heads is staged once (7x7 windows; fp32, in mma accumulator-fragment order, divided by the qk scale so that it
-// is the initial accumulator of Q K^T) and the next item's tokens stream in (double buffer) while the current one is
-// computed.  One warp per (head, 16-query tile): S = Q K^T with mma.sync m16n8k16 fed by ldmatrix, online softmax over
-// chunks of 32 keys in registers (exp2; lazy running maxima, see attend_chunk), P
+// those heads is staged once (7x7 windows: fp16, already in mma accumulator-fragment order and scaled by log2 e; 14x14: fp32
+// fragments read through the read-only path as the initial accumulators of Q K^T) and the next item's tokens stream in
+// (double buffer) while the current one is computed.  One warp per (head, 16-query tile): S = Q K^T with mma.sync
+// m16n8k16 fed by ldmatrix, online softmax over chunks of 32 keys in registers (exp2; lazy running maxima, attend_chunk), P
 // re-used in place as the A operand of O += P V (V through ldmatrix.trans, no transposed copy).  These windows are far
 // below a 128-row tcgen05 tile and the attention core is 3-19 % of a stage's MACs, so the warp-level
 // MMA is the right tool; the kernel is bound by instruction issue, which is what this structure minimises.
@@ -66,11 +66,10 @@ struct Cfg {
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kRowBytes = kHG * 192 + 16;  // [q|k|v] of kHG heads + 16 B: rows land in distinct bank groups
     static constexpr int kTileBytes = NKP * kRowBytes;
-    static constexpr int kBiasBytes = kHG * NQ * NK8 * 32 * 16;  // fp32 accumulator fragments: one float4 per lane and key block
-    // 7x7 windows: the table of a head group (56 / 70 KB) is staged in shared memory once per CTA.  14x14 windows: the 163 KB
-    // of a head would cap the SM at ONE 13-warp CTA, and the kernel is latency bound; the table stays in global memory
-    // instead (read-only path, L1 / L2 resident) so that two CTAs fit.
-    static constexpr bool kBiasInSmem = kBiasBytes <= 80 * 1024;
+    static constexpr int kBiasBytes = kHG * NQ * NK8 * 32 * 8;
+    // 14x14 windows: the 83 KB bias table of a head would cap the SM at ONE 13-warp CTA, and the kernel is latency
+    // bound; the table stays in global memory instead (read-only path, L1 / L2 resident) so that two CTAs fit.
+    static constexpr bool kBiasInSmem = kBiasBytes <= 48 * 1024;
     static constexpr int kSmemBias = kBiasInSmem ? kBiasBytes : 0;
     static constexpr int kSmemBytes = kSmemBias + 2 * kTileBytes;
     static constexpr int kMinBlocks = kBiasInSmem ? 1 : 2;
@@ -85,40 +84,62 @@ struct Cfg {
 //          2^kLazyGrowth, which a 16-bit float holds with the same relative precision, and the final division by the row
 //          sum (accumulated from the same rounded values) is unchanged.  The test is per lane plus one warp vote, so the
 //          common chunk drops the quad reductions, two exponentials and the 18 accumulator multiplications.
-// (Two ways of taking work off the XU pipe were measured and dropped: every fourth exponential as a degree-3 polynomial on
-// the FMA pipe -- 1.44 ms per step against 1.39, the kernel is short of issue slots, not of MUFU throughput -- and
-// ex2.approx.f16x2 for the exponentials: ptxas lowers it to two MUFU.EX2.F16 plus a PRMT on sm_100a, so it
-// saves no XU cycles and costs instructions.)
+// Measured and dropped: (a) every fourth exponential as a degree-3 polynomial on the FMA pipe -- 1.44 ms of attention per step
+// against 1.39, the kernel is short of issue slots and L1 data-pipe cycles, not of MUFU throughput; (b) ex2.approx.f16x2:
+// ptxas lowers it to two MUFU.EX2.F16 plus a PRMT on sm_100a, no XU cycles saved; (c) fp32 accumulator-initialising bias
+// fragments in shared memory for the 7x7 windows as well: 48 instructions fewer per item, but twice the shared-memory
+// wavefronts for the table -- 392 us against 374 us per pass for the 128-wide stage; (d) a 16-bit table for the 14x14 windows
+// (half the L2 -> L1 traffic of the bias, four conversions more per key block): 1.369 against 1.376 ms, not worth the precision.
 constexpr float kLazyGrowth = 8.0f;
 template <int kCnt, bool kFirst, bool kBiasInSmem, int kMode>
 __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4], uint32_t k_addr, uint32_t v_addr, int row_bytes,
-                                             uint32_t bias_addr, float4 const* __restrict__ bias_gl, float (&m)[2], float (&l)[4],
+                                             uint32_t bias_addr, uint8_t const* __restrict__ bias_gl, float (&m)[2], float (&l)[4],
                                              float (&o)[4][4], uint32_t ones_b) {
     float const kScale = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e)
     float s[kCnt][4];
     float cm0 = -INFINITY, cm1 = -INFINITY;
-    // bias fragments (fp32, divided by the qk scale) are the initial accumulators of the MMA: s = q.k + bias / scale, and the
-    // scale * log2 e moves into the exponent below -- eight instructions fewer per key block than converting and adding a
-    // 16-bit bias.  They come from shared memory (7x7 windows) or through the read-only path (14x14).
+    if (kBiasInSmem) {
+        // bias fragments (fp16, pre-multiplied by log2 e) in shared memory: s = q.k * scale * log2 e + bias
 #pragma unroll
-    for (int j = 0; j < kCnt; ++j) {
-        float4 bw;
-        if (kBiasInSmem) {
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bw.x), "=f"(bw.y), "=f"(bw.z), "=f"(bw.w) : "r"(bias_addr + (uint32_t)((nb0 + j) * 512)));
-        } else {
-            bw = __ldg(bias_gl + (nb0 + j) * 32);
+        for (int j = 0; j < kCnt; ++j) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(k_addr + (uint32_t)((nb0 + j) * 8 * row_bytes), b0, b1, b2, b3);
+            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+            mma16816(s[j], aq[0][0], aq[0][1], aq[0][2], aq[0][3], b0, b1);
+            mma16816(s[j], aq[1][0], aq[1][1], aq[1][2], aq[1][3], b2, b3);
         }
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(k_addr + (uint32_t)((nb0 + j) * 8 * row_bytes), b0, b1, b2, b3);
-        s[j][0] = bw.x; s[j][1] = bw.y; s[j][2] = bw.z; s[j][3] = bw.w;
-        mma16816(s[j], aq[0][0], aq[0][1], aq[0][2], aq[0][3], b0, b1);
-        mma16816(s[j], aq[1][0], aq[1][1], aq[1][2], aq[1][3], b2, b3);
-        cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
-        cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+#pragma unroll
+        for (int j = 0; j < kCnt; ++j) {
+            uint32_t w0, w1;
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(bias_addr + (uint32_t)((nb0 + j) * 256)));
+            float2 const f0 = __half22float2(*reinterpret_cast<__half2 const*>(&w0));
+            float2 const f1 = __half22float2(*reinterpret_cast<__half2 const*>(&w1));
+            s[j][0] = fmaf(s[j][0], kScale, f0.x);
+            s[j][1] = fmaf(s[j][1], kScale, f0.y);
+            s[j][2] = fmaf(s[j][2], kScale, f1.x);
+            s[j][3] = fmaf(s[j][3], kScale, f1.y);
+            cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
+            cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+        }
+    } else {
+        // bias fragments (fp32, divided by the qk scale) from global memory are the initial accumulators of the MMA:
+        // s = q.k + bias / scale, and the scale * log2 e moves into the exponent below -- eight instructions fewer per
+        // key block than converting and adding an fp16 bias
+#pragma unroll
+        for (int j = 0; j < kCnt; ++j) {
+            float4 const bw = __ldg(reinterpret_cast<float4 const*>(bias_gl) + (nb0 + j) * 32);
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(k_addr + (uint32_t)((nb0 + j) * 8 * row_bytes), b0, b1, b2, b3);
+            s[j][0] = bw.x; s[j][1] = bw.y; s[j][2] = bw.z; s[j][3] = bw.w;
+            mma16816(s[j], aq[0][0], aq[0][1], aq[0][2], aq[0][3], b0, b1);
+            mma16816(s[j], aq[1][0], aq[1][1], aq[1][2], aq[1][3], b2, b3);
+            cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
+            cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+        }
     }
     bool moved = true;
-    if (!kFirst && kMode >= 1) {  // (the scores are still unscaled: the growth bound is divided by the scale)
-        float const bound = kLazyGrowth / kScale;
+    if (!kFirst && (kMode & 1)) {  // (scores of the global-bias path are still unscaled: the growth bound is divided by the scale)
+        float const bound = kBiasInSmem ? kLazyGrowth : kLazyGrowth / kScale;
         moved = __any_sync(0xffffffffu, cm0 > m[0] + bound || cm1 > m[1] + bound);
     }
     if (moved) {
@@ -131,7 +152,7 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
             m[1] = cm1;
         } else {  // every chunk holds at least one unmasked key, so the running maxima are finite from chunk 0 on
             float const n0 = fmaxf(m[0], cm0), n1 = fmaxf(m[1], cm1);
-            float const a0 = ex2((m[0] - n0) * kScale), a1 = ex2((m[1] - n1) * kScale);
+            float const a0 = ex2((m[0] - n0) * (kBiasInSmem ? 1.0f : kScale)), a1 = ex2((m[1] - n1) * (kBiasInSmem ? 1.0f : kScale));
             m[0] = n0;
             m[1] = n1;
             l[0] *= a0;  // (accumulator fragment of the ones column: rows g / g + 8 in elements 0 / 2 of the lanes with t == 0)
@@ -143,13 +164,19 @@ __device__ __forceinline__ void attend_chunk(int nb0, uint32_t const (&aq)[2][4]
             }
         }
     }
-    float const e0 = -m[0] * kScale, e1 = -m[1] * kScale;  // (the scores are still unscaled)
+    float const e0 = -m[0] * kScale, e1 = -m[1] * kScale;  // (global-bias path: scores are still unscaled)
     uint32_t p[kCnt + 1][2];  // probabilities as packed pairs: [j][0] = row g, [j][1] = row g + 8 (keys 2t, 2t + 1 of block j)
     p[kCnt][0] = p[kCnt][1] = 0u;
 #pragma unroll
     for (int j = 0; j < kCnt; ++j) {
-        float const x0 = fmaf(s[j][0], kScale, e0), x1 = fmaf(s[j][1], kScale, e0);
-        float const x2 = fmaf(s[j][2], kScale, e1), x3 = fmaf(s[j][3], kScale, e1);
+        float x0, x1, x2, x3;
+        if (kBiasInSmem) {
+            x0 = s[j][0] - m[0]; x1 = s[j][1] - m[0];
+            x2 = s[j][2] - m[1]; x3 = s[j][3] - m[1];
+        } else {
+            x0 = fmaf(s[j][0], kScale, e0); x1 = fmaf(s[j][1], kScale, e0);
+            x2 = fmaf(s[j][2], kScale, e1); x3 = fmaf(s[j][3], kScale, e1);
+        }
         p[j][0] = pack2(ex2(x0), ex2(x1));
         p[j][1] = pack2(ex2(x2), ex2(x3));
     }
@@ -251,9 +278,10 @@ window_attention_kernel2(act_t const* __restrict__ qkv, int batch, int res, int 
     uint32_t const q_off = (uint32_t)((qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * C::kRowBytes + (hh * 96 + ((lane >> 4) & 1) * 8) * 2);
     uint32_t const k_off = (uint32_t)((lane & 7) * C::kRowBytes + (hh * 96 + 32 + (lane >> 3) * 8) * 2);
     uint32_t const v_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * C::kRowBytes + (hh * 96 + 64 + ((lane >> 4) & 1) * 8) * 2);
-    uint32_t const bias_addr = bias_s + (uint32_t)((((hh * C::NQ + qt) * C::NK8) * 32 + lane) * 16);
-    float4 const* const bias_gl = reinterpret_cast<float4 const*>(bias_frag) + (size_t)hg * (C::kBiasBytes / 16) +
-                                  ((hh * C::NQ + qt) * C::NK8) * 32 + lane;  // (one float4 per lane and key block)
+    uint32_t const bias_addr = bias_s + (uint32_t)((((hh * C::NQ + qt) * C::NK8) * 32 + lane) * 8);
+    // (14x14, fp32 fragments: one float4 per lane and key block)
+    uint8_t const* const bias_gl = reinterpret_cast<uint8_t const*>(bias_frag) +
+                                   ((size_t)hg * (C::kBiasBytes / 8) + ((hh * C::NQ + qt) * C::NK8) * 32 + lane) * 16;
 
     int it = 0;
     WinPos cur{w_first / nw2, (w_first % nw2) / nw, w_first % nw}, nxt = cur;
@@ -348,12 +376,18 @@ void launch_attention_mode(cudaStream_t s, act_t const* qkv, int batch, int res,
 
 constexpr int kSoftmaxMode = 1;  // attend_chunk's kMode of the release build
 
+int softmax_mode() {
+    static int const mode = dev_int("DLIMG_B200_WA_MODE", kSoftmaxMode);  // development A/B of the variants
+    return mode;
+}
+
 template <int kWS, int kHG>
 void launch_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int heads, act_t const* pad_qkv,
                       __half const* bias_frag, act_t* out, int num_sms) {
 #if DLIMG_B200_ALT
-    int const mode = dev_int("DLIMG_B200_WA_MODE", kSoftmaxMode);  // development A/B of the softmax variants
+    int const mode = softmax_mode();
     if (mode == 0) return launch_attention_mode<kWS, kHG, 0>(s, qkv, batch, res, heads, pad_qkv, bias_frag, out, num_sms);
+    if (mode == 1) return launch_attention_mode<kWS, kHG, 1>(s, qkv, batch, res, heads, pad_qkv, bias_frag, out, num_sms);
 #endif
     launch_attention_mode<kWS, kHG, kSoftmaxMode>(s, qkv, batch, res, heads, pad_qkv, bias_frag, out, num_sms);
 }
@@ -365,16 +399,19 @@ int attention_head_group(int ws, int heads) {
     return heads % 5 == 0 ? 5 : (heads % 4 == 0 ? 4 : 0);
 }
 
-// fp32 fragments in mma accumulator order, divided by the qk scale (they initialise the accumulators of Q K^T); two uint16
-// slots per value.  Key columns beyond the window are -inf (masked).
+// 7 x 7 windows: fp16 fragments pre-multiplied by log2 e (they live in shared memory).  14 x 14 windows: fp32 fragments
+// divided by the qk scale (read from global memory straight into the MMA accumulators), two uint16 slots per value.
+static bool bias_fragments_fp32(int ws) { return !Cfg<14, 1>::kBiasInSmem && ws == 14; }
+
 size_t attention_bias_fragment_count(int heads, int ws) {
     int const n = ws * ws, nq = (n + 15) / 16, nk8 = (n + 7) / 8;
-    return (size_t)heads * nq * nk8 * 32 * 4 * 2;
+    return (size_t)heads * nq * nk8 * 32 * 4 * (bias_fragments_fp32(ws) ? 2 : 1);
 }
 
 void attention_bias_fragments(float const* dense, int heads, int ws, uint16_t* out) {
     int const n = ws * ws, nq = (n + 15) / 16, nk8 = (n + 7) / 8;
-    float* const dst = reinterpret_cast<float*>(out);
+    float const log2e = 1.4426950408889634f;
+    bool const f32 = bias_fragments_fp32(ws);
     size_t i = 0;
     for (int h = 0; h < heads; ++h)
         for (int qt = 0; qt < nq; ++qt)
@@ -385,8 +422,15 @@ void attention_bias_fragments(float const* dense, int heads, int ws, uint16_t* o
                         int const c = nb * 8 + 2 * (lane & 3) + (e & 1);
                         float v = 0.f;
                         if (c >= n) v = -INFINITY;  // key padding of the tile: masked
-                        else if (r < n) v = dense[((size_t)h * n + r) * n + c] * 5.656854249492381f;  // / 32^-0.5
-                        dst[i++] = v;
+                        else if (r < n) v = dense[((size_t)h * n + r) * n + c];
+                        if (f32) {
+                            if (c < n) v *= 5.656854249492381f;  // / 32^-0.5
+                            reinterpret_cast<float*>(out)[i++] = v;
+                        } else {
+                            if (c < n) v *= log2e;
+                            __half const hv = __float2half_rn(v);
+                            out[i++] = *reinterpret_cast<uint16_t const*>(&hv);
+                        }
                     }
 }
 

@@ -82,7 +82,7 @@ struct BlockW {
     // mean / rstd are applied in the GEMM epilogue), see gemm.cuh Epilogue::ln_stats
     Linear16 qkv, proj;
     DeviceBuffer<act_t> qkv_pad;        // (3C): qkv of a zero-padding token = projection of LN(0) = beta
-    DeviceBuffer<uint16_t> attn_bias;   // fragment-ordered relative-position bias (attention_bias_fragments: fp32 values in uint16 pairs)
+    DeviceBuffer<uint16_t> attn_bias;   // fp16 fragment-ordered relative-position bias (attention_bias_fragments)
     DwConv local_conv;
     Linear16 fc1, fc2;
 };
