@@ -28,6 +28,7 @@ constexpr size_t kEmbFloats = (size_t)dec::kImgTokens * kEmbedDim;              
 constexpr size_t kKeysElems = (size_t)dec::kImgTokens * 256, kKvqElems = (size_t)dec::kImgTokens * 384;
 // per image in a chunk's store: [fp32 embedding | 16-bit keys0 | 16-bit kvq0], every part 256-byte aligned
 constexpr size_t kStoreBytesPerImage = kEmbFloats * 4 + (kKeysElems + kKvqElems) * sizeof(act_t);
+constexpr size_t kShadowBytesPerImage = kEmbFloats * sizeof(act_t);  // 16-bit copy of the embedding behind a chunk's store
 
 int env_int(char const* name, int def, int lo, int hi) {
     char const* v = std::getenv(name);
@@ -93,6 +94,7 @@ StreamBuffer::~StreamBuffer() {
     if (ready_) cudaEventDestroy(ready_);
     if (last_read_) cudaEventDestroy(last_read_);
     if (last_use_) cudaEventDestroy(last_use_);
+    if (f16_ready) cudaEventDestroy(f16_ready);
 }
 void StreamBuffer::mark_read(cudaStream_t copy_stream) {
     std::lock_guard<std::mutex> lock(mutex_);
@@ -431,7 +433,8 @@ void EnvironmentImpl::process_batch(dlimg_ImageView const* views, int count, boo
         int const B = std::min(max_batch_, count - start);
         // one allocation per chunk: per image the fp32 NCHW embedding (what get_embedding returns: the reference's
         // `image_embeddings`) and the decoder's 16-bit prompt-independent inputs
-        auto store = std::make_shared<StreamBuffer>(kStoreBytesPerImage * (size_t)B, s);
+        auto store = std::make_shared<StreamBuffer>((kStoreBytesPerImage + kShadowBytesPerImage) * (size_t)B, s);
+        store->images = B;
         float* const emb_nchw = reinterpret_cast<float*>(store->bytes());
         act_t* const keys0 = reinterpret_cast<act_t*>(store->bytes() + kEmbFloats * 4 * (size_t)B);
         act_t* const kvq0 = keys0 + kKeysElems * (size_t)B;
@@ -779,19 +782,26 @@ void SegmentationImpl::embedding_nchw_f16_async(uint16_t* out_host) {
     EnvironmentImpl::Scope scope(env_);
     if (!encoded()) fail("segmentation handle holds no processed image");
     // The conversion runs on the WORK stream, in order behind the encoder (on the copy-out stream it had to squeeze onto SMs
-    // that the next pass's persistent kernels occupy, and the downloads behind it stalled unpredictably); the copy follows on
-    // the copy-out stream.  The 16-bit shadow belongs to the handle: allocated and freed on the work stream, so the pool hands
-    // the same blocks round (an allocation on one stream and its release on another is only recycled after a synchronisation).
+    // that the next pass's persistent kernels occupy, and the downloads behind it stalled unpredictably), ONCE for all images
+    // of the chunk into the 16-bit region behind the chunk's store: one launch per chunk instead of one per image, and no
+    // per-handle allocation (a fresh 2 MiB block per new handle made the memory pool grow in the middle of a pipelined run).
+    // The copy follows on the copy-out stream.
     cudaStream_t const ws = env_.stream(), cs = env_.copy_out_;
-    CUDA_CHECK(cudaStreamWaitEvent(ws, store_->ready(), 0));
-    if (!f16_shadow_) f16_shadow_ = std::make_unique<StreamBuffer>(kEmbFloats * sizeof(act_t), ws);
-    act_t* const shadow = reinterpret_cast<act_t*>(f16_shadow_->bytes());
-    dec::f32_to_act(ws, emb_nchw_, (int64_t)kEmbFloats, shadow);
-    CUDA_CHECK(cudaEventRecord(f16_shadow_->ready(), ws));
-    store_->mark_used(ws);
-    CUDA_CHECK(cudaStreamWaitEvent(cs, f16_shadow_->ready(), 0));
-    CUDA_CHECK(cudaMemcpyAsync(out_host, shadow, kEmbFloats * sizeof(act_t), cudaMemcpyDeviceToHost, cs));
-    f16_shadow_->mark_read(cs);
+    StreamBuffer& st = *store_;
+    float const* const emb_base = reinterpret_cast<float const*>(st.bytes());
+    act_t* const shadow_base = reinterpret_cast<act_t*>(st.bytes() + kStoreBytesPerImage * (size_t)st.images);
+    if (!st.f16_done) {
+        CUDA_CHECK(cudaStreamWaitEvent(ws, st.ready(), 0));
+        if (!st.f16_ready) CUDA_CHECK(cudaEventCreateWithFlags(&st.f16_ready, cudaEventDisableTiming));
+        dec::f32_to_act(ws, emb_base, (int64_t)kEmbFloats * st.images, shadow_base);
+        CUDA_CHECK(cudaEventRecord(st.f16_ready, ws));
+        st.mark_used(ws);
+        st.f16_done = true;
+    }
+    size_t const index = (size_t)(emb_nchw_ - emb_base) / kEmbFloats;
+    CUDA_CHECK(cudaStreamWaitEvent(cs, st.f16_ready, 0));
+    CUDA_CHECK(cudaMemcpyAsync(out_host, shadow_base + index * kEmbFloats, kEmbFloats * sizeof(act_t), cudaMemcpyDeviceToHost, cs));
+    st.mark_read(cs);
     env_.counters_.d2h_bytes += kEmbFloats * sizeof(act_t);
 #endif
 }

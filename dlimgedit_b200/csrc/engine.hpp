@@ -43,6 +43,12 @@ class StreamBuffer {
     cudaEvent_t ready() const { return ready_; }
     void mark_read(cudaStream_t copy_stream);
     void mark_used(cudaStream_t work_stream);
+    // Embedding stores only (guarded by the environment's mutex): number of images in the chunk, and the state of the 16-bit
+    // copy of their embeddings that sits behind them -- converted once for the whole chunk by the first
+    // get_embedding_f16_async of any of its images, `f16_ready` recorded behind that conversion.
+    int images = 0;
+    bool f16_done = false;
+    cudaEvent_t f16_ready = nullptr;
 
   private:
     void* ptr_ = nullptr;
@@ -182,7 +188,7 @@ class SegmentationImpl {
     void compute_mask(int const* point, int const* region, uint8_t** out_masks, float* out_accuracy);  // :131-174
     void embedding_nchw(float* out_host);        // blocking
     void embedding_nchw_async(float* out_host);  // returns at once; complete after EnvironmentImpl::synchronize()
-    void embedding_nchw_f16_async(uint16_t* out_host);  // the same as fp16 (converted on the work stream into a per-handle shadow)
+    void embedding_nchw_f16_async(uint16_t* out_host);  // the same as fp16 (the chunk's embeddings are converted once, on the work stream)
 
     int width() const { return size_.orig_w; }
     int height() const { return size_.orig_h; }
@@ -197,7 +203,6 @@ class SegmentationImpl {
     float* emb_nchw_ = nullptr;            // (256, 4096) fp32: the reference's `image_embeddings` layout
     act_t* keys0_ = nullptr;               // (4096, 256) 16-bit: embedding + no_mask_embed, the decoder's layer-0 image stream
     act_t* kvq0_ = nullptr;                // (4096, 384) 16-bit: its layer-0 [K | V | Q] projections
-    std::unique_ptr<StreamBuffer> f16_shadow_;  // (256, 4096) fp16 copy of emb_nchw_, made by the first get_embedding_f16_async
 };
 
 }  // namespace dlimg

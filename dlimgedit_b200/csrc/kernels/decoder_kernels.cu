@@ -199,6 +199,20 @@ __global__ void f32_to_act_kernel(float const* __restrict__ in, int64_t n, act_t
     if (i < n) out[i] = f2act(in[i]);
 }
 
+// eight values per thread: two 16-byte loads, one 16-byte store (n % 8 == 0, both pointers 16-byte aligned)
+__global__ void f32_to_act8_kernel(float4 const* __restrict__ in, int64_t n8, uint4* __restrict__ out) {
+    int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    float4 const a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
+    act2_t const p0 = f22act2(a.x, a.y), p1 = f22act2(a.z, a.w), p2 = f22act2(b.x, b.y), p3 = f22act2(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t const*>(&p0);
+    o.y = *reinterpret_cast<uint32_t const*>(&p1);
+    o.z = *reinterpret_cast<uint32_t const*>(&p2);
+    o.w = *reinterpret_cast<uint32_t const*>(&p3);
+    out[i] = o;
+}
+
 __global__ void select_masks_kernel(float const* __restrict__ iou, int P, int multi, int* __restrict__ plane_index,
                                     float* __restrict__ iou_out) {
     int const p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,7 +273,10 @@ void image_to_token_attention(cudaStream_t s, act_t const* Q, act_t const* const
 
 void f32_to_act(cudaStream_t s, float const* in, int64_t n, act_t* out) {
     ProfScope prof(s, CAT_DEC_MISC);
-    f32_to_act_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(in, n, out);
+    if (n % 8 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+        f32_to_act8_kernel<<<(unsigned)ceil_div64(n / 8, 256), 256, 0, s>>>(reinterpret_cast<float4 const*>(in), n / 8, reinterpret_cast<uint4*>(out));
+    else
+        f32_to_act_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(in, n, out);
     KERNEL_CHECK();
 }
 
