@@ -72,7 +72,7 @@ struct Cfg {
     static constexpr bool kBiasInSmem = kBiasBytes <= 48 * 1024;
     static constexpr int kSmemBias = kBiasInSmem ? kBiasBytes : 0;
     static constexpr int kSmemBytes = kSmemBias + 2 * kTileBytes;
-    static constexpr int kMinBlocks = kBiasInSmem ? 1 : 2;
+    static constexpr int kMinBlocks = !kBiasInSmem ? 2 : (kHG > 2 ? 1 : (kHG == 2 ? 2 : 4));
     static constexpr int kCPT = kHG * 12;        // 16-byte chunks per token
 };
 
@@ -394,11 +394,6 @@ void launch_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int 
 
 }  // namespace
 
-int attention_head_group(int ws, int heads) {
-    if (ws == 14) return 1;
-    return heads % 5 == 0 ? 5 : (heads % 4 == 0 ? 4 : 0);
-}
-
 // 7 x 7 windows: fp16 fragments pre-multiplied by log2 e (they live in shared memory).  14 x 14 windows: fp32 fragments
 // divided by the qk scale (read from global memory straight into the MMA accumulators), two uint16 slots per value.
 static bool bias_fragments_fp32(int ws) { return !Cfg<14, 1>::kBiasInSmem && ws == 14; }
@@ -439,8 +434,16 @@ void window_attention(cudaStream_t s, act_t const* qkv, int batch, int res, int 
     int const nw = (res + ws - 1) / ws, n = ws * ws;
     ProfScope prof(s, CAT_WIN_ATTN, 4.0 * batch * nw * nw * heads * n * n * 32, (double)batch * res * res * heads * 128 * 2);
     __half const* bf = reinterpret_cast<__half const*>(bias_frag);
-    if (ws == 7 && heads % 5 == 0) launch_attention<7, 5>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
-    else if (ws == 7 && heads % 4 == 0) launch_attention<7, 4>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
+    // 7x7 windows: ONE head per CTA, four CTAs of four warps per SM.  A CTA meets at two CTA-wide barriers per item (tokens
+    // landed / outputs complete), and with all the heads of a window in one 16- or 20-warp CTA the SM idled through every
+    // load and store phase: 1.378 ms of attention per step with 4 / 5 heads per CTA, 1.262 with two, 1.246 with one.
+#if DLIMG_B200_ALT
+    int const hg = dev_int("DLIMG_B200_WA_HG", 1);  // development A/B of the grouping
+    if (ws == 7 && hg == 5 && heads % 5 == 0) return launch_attention<7, 5>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
+    if (ws == 7 && hg == 4 && heads % 4 == 0) return launch_attention<7, 4>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
+    if (ws == 7 && hg == 2 && heads % 2 == 0) return launch_attention<7, 2>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
+#endif
+    if (ws == 7) launch_attention<7, 1>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
     else if (ws == 14) launch_attention<14, 1>(s, qkv, batch, res, heads, pad_qkv, bf, out, num_sms);
     else fail("window_attention: unsupported (window, heads) = (" + std::to_string(ws) + ", " + std::to_string(heads) + ")");
 }
