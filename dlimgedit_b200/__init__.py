@@ -289,6 +289,9 @@ class Image:
         ch = ctypes.c_int()
         px = ctypes.c_void_p()
         _check(api().load_image(os.fspath(filepath).encode(), e, ctypes.byref(ch), ctypes.byref(px)))
+        if ch.value not in (1, 3, 4):  # grey + alpha files: the reference casts the count to a Channels value that does not exist
+            api().destroy_image(px)
+            raise Exception(f"Failed to load image {os.fspath(filepath)}: {ch.value} channels have no Channels value")
         return Image(Extent(e[0], e[1]), Channels(ch.value), _pixels=px.value)
 
     @staticmethod

@@ -193,60 +193,161 @@ int paeth(int a, int b, int c) {
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
+// PNG as stb_image's 8-bit loader sees it (the reference's stbi_load, image.cpp:11-23): every colour type and bit depth,
+// palettes, tRNS transparency (an extra alpha channel), Adam7 interlacing; 16-bit samples keep their high byte, 1 / 2 / 4-bit
+// grey is scaled to 0..255.  Channels out: grey 1 (2 with alpha or tRNS), RGB / palette 3 (4 with alpha or tRNS).
 uint8_t* load_png(std::vector<uint8_t> const& file, char const* path, int* extent, int* channels) {
+    auto bad = [&](char const* why) { fail(std::string("Failed to load image ") + path + ": " + why); };
     size_t pos = 8;
     uint32_t w = 0, h = 0;
     int depth = 0, color = 0, interlace = 0;
+    bool have_ihdr = false, have_trns = false;
+    uint8_t palette[256][4];
+    int pal_len = 0;
+    uint16_t key[3] = {0, 0, 0};  // tRNS colour key of grey / RGB images (file precision)
     std::vector<uint8_t> idat;
     while (pos + 12 <= file.size()) {
         uint32_t const len = be32(&file[pos]);
         char const* type = reinterpret_cast<char const*>(&file[pos + 4]);
-        if (pos + 12 + len > file.size()) fail(std::string("Failed to load image ") + path + ": truncated PNG");
+        if (len > file.size() || pos + 12 + len > file.size()) bad("truncated PNG");
         uint8_t const* d = &file[pos + 8];
         if (!std::memcmp(type, "IHDR", 4)) {
-            if (len != 13) fail(std::string("Failed to load image ") + path + ": malformed PNG header");
+            if (len != 13 || have_ihdr) bad("malformed PNG header");
+            have_ihdr = true;
             w = be32(d); h = be32(d + 4); depth = d[8]; color = d[9]; interlace = d[12];
+            if (d[10] != 0 || d[11] != 0 || interlace > 1) bad("malformed PNG header");
+        } else if (!std::memcmp(type, "PLTE", 4)) {
+            if (!have_ihdr || len > 256 * 3 || len % 3) bad("bad PNG palette");
+            pal_len = (int)(len / 3);
+            for (int i = 0; i < pal_len; ++i) {
+                palette[i][0] = d[3 * i]; palette[i][1] = d[3 * i + 1]; palette[i][2] = d[3 * i + 2]; palette[i][3] = 255;
+            }
+        } else if (!std::memcmp(type, "tRNS", 4)) {
+            if (!have_ihdr || !idat.empty()) bad("misplaced tRNS chunk");
+            if (color == 3) {
+                if (pal_len == 0 || len > (uint32_t)pal_len) bad("bad tRNS chunk");
+                for (uint32_t i = 0; i < len; ++i) palette[i][3] = d[i];
+            } else if (color == 0 || color == 2) {
+                uint32_t const n = color == 0 ? 1 : 3;
+                if (len != 2 * n) bad("bad tRNS chunk");
+                for (uint32_t i = 0; i < n; ++i) key[i] = (uint16_t)((d[2 * i] << 8) | d[2 * i + 1]);
+            } else {
+                bad("tRNS chunk in an image with an alpha channel");
+            }
+            have_trns = true;
         } else if (!std::memcmp(type, "IDAT", 4)) {
+            if (!have_ihdr) bad("malformed PNG");
             idat.insert(idat.end(), d, d + len);
         } else if (!std::memcmp(type, "IEND", 4)) {
             break;
         }
-        pos += 12 + len;
+        pos += 12 + (size_t)len;
     }
-    int const ch = color == 0 ? 1 : color == 2 ? 3 : color == 6 ? 4 : 0;
-    if (!w || !h || depth != 8 || !ch || interlace)
-        fail(std::string("Failed to load image ") + path + ": only 8-bit grey/RGB/RGBA non-interlaced PNG is supported");
+    int const samples = color == 0 ? 1 : color == 2 ? 3 : color == 3 ? 1 : color == 4 ? 2 : color == 6 ? 4 : 0;
+    bool const depth_ok = color == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                          : color == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8)
+                                       : (depth == 8 || depth == 16);
+    if (!have_ihdr || !w || !h || !samples || !depth_ok) bad("unsupported PNG colour type / bit depth");
+    if (color == 3 && pal_len == 0) bad("PNG palette missing");
+    int const out_ch = color == 3 ? (have_trns ? 4 : 3) : samples + ((have_trns && (color == 0 || color == 2)) ? 1 : 0);
     // sizes in 64 bits, bounded before anything is allocated (a 2^31 x 2^31 header must not wrap to a small buffer)
-    if (w > kMaxImageDim || h > kMaxImageDim || (uint64_t)w * h * (uint64_t)ch > kMaxImageBytes)
-        fail(std::string("Failed to load image ") + path + ": image too large");
-    size_t const row = (size_t)w * ch;
-    size_t const expect = (row + 1) * (size_t)h;
-    std::vector<uint8_t> raw = inflate(idat.data(), idat.size(), expect);
-    if (raw.size() < expect) fail(std::string("Failed to load image ") + path + ": PNG data too short");
-    uint8_t* px = image_alloc(row * h);
-    for (uint32_t y = 0; y < h; ++y) {
-        uint8_t const* src = &raw[(row + 1) * y];
-        uint8_t* dst = px + row * y;
-        uint8_t const* up = y ? dst - row : nullptr;
-        int const ft = src[0];
-        ++src;
-        for (size_t x = 0; x < row; ++x) {
-            int const a = x >= (size_t)ch ? dst[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
-            int v = src[x];
-            switch (ft) {
-            case 0: break;
-            case 1: v += a; break;
-            case 2: v += b; break;
-            case 3: v += (a + b) >> 1; break;
-            case 4: v += paeth(a, b, c); break;
-            default: image_free(px); fail(std::string("Failed to load image ") + path + ": bad PNG filter");
-            }
-            dst[x] = (uint8_t)v;
+    if (w > kMaxImageDim || h > kMaxImageDim || (uint64_t)w * h * (uint64_t)std::max(out_ch, samples * (depth / 8 ? depth / 8 : 1)) > kMaxImageBytes)
+        bad("image too large");
+    int const px_bits = depth * samples;
+    int const fbpp = std::max(1, px_bits / 8);  // distance of the "left" byte for the filters
+    // the seven Adam7 passes (or the one pass of a plain image): origin, spacing, extent
+    static int const xorig[7] = {0, 4, 0, 2, 0, 1, 0}, yorig[7] = {0, 0, 4, 0, 2, 0, 1};
+    static int const xspc[7] = {8, 8, 4, 4, 2, 2, 1}, yspc[7] = {8, 8, 8, 4, 4, 2, 2};
+    struct Pass { uint32_t x0, y0, dx, dy, pw, ph; size_t row; };
+    std::vector<Pass> passes;
+    size_t expect = 0;
+    if (!interlace) {
+        passes.push_back(Pass{0, 0, 1, 1, w, h, ((size_t)w * px_bits + 7) / 8});
+    } else {
+        for (int p = 0; p < 7; ++p) {
+            uint32_t const pw = (w + (uint32_t)xspc[p] - 1 - (uint32_t)xorig[p]) / (uint32_t)xspc[p];
+            uint32_t const ph = (h + (uint32_t)yspc[p] - 1 - (uint32_t)yorig[p]) / (uint32_t)yspc[p];
+            if ((uint32_t)xorig[p] >= w || (uint32_t)yorig[p] >= h || !pw || !ph) continue;
+            passes.push_back(Pass{(uint32_t)xorig[p], (uint32_t)yorig[p], (uint32_t)xspc[p], (uint32_t)yspc[p], pw, ph, ((size_t)pw * px_bits + 7) / 8});
         }
+    }
+    for (Pass const& p : passes) expect += (p.row + 1) * (size_t)p.ph;
+    std::vector<uint8_t> raw = inflate(idat.data(), idat.size(), expect);
+    if (raw.size() < expect) bad("PNG data too short");
+
+    uint8_t* px = image_alloc((size_t)w * h * out_ch);
+    static int const depth_scale[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
+    std::vector<uint8_t> prev, cur, line;  // unfiltered scanlines of the pass; one scanline as 8-bit samples
+    size_t at = 0;
+    try {
+        for (Pass const& p : passes) {
+            prev.assign(p.row, 0);
+            cur.assign(p.row, 0);
+            line.assign((size_t)p.pw * samples * (depth == 16 ? 2 : 1), 0);
+            for (uint32_t y = 0; y < p.ph; ++y) {
+                int const ft = raw[at++];
+                uint8_t const* src = &raw[at];
+                at += p.row;
+                for (size_t x = 0; x < p.row; ++x) {
+                    int const a = x >= (size_t)fbpp ? cur[x - fbpp] : 0, b = prev[x], c = x >= (size_t)fbpp ? prev[x - fbpp] : 0;
+                    int v = src[x];
+                    switch (ft) {
+                    case 0: break;
+                    case 1: v += a; break;
+                    case 2: v += b; break;
+                    case 3: v += (a + b) >> 1; break;
+                    case 4: v += paeth(a, b, c); break;
+                    default: bad("bad PNG filter");
+                    }
+                    cur[x] = (uint8_t)v;
+                }
+                // scanline -> samples (16-bit ones stay two bytes until the colour key has been compared)
+                if (depth >= 8) {
+                    std::memcpy(line.data(), cur.data(), line.size());
+                } else {
+                    int const mask = (1 << depth) - 1, scale = color == 0 ? depth_scale[depth] : 1;
+                    for (size_t i = 0; i < (size_t)p.pw; ++i) {
+                        size_t const bit = i * (size_t)depth;
+                        int const v = (cur[bit >> 3] >> (8 - depth - (int)(bit & 7))) & mask;
+                        line[i] = (uint8_t)(v * scale);
+                    }
+                }
+                uint8_t* dst_row = px + ((size_t)(p.y0 + y * p.dy) * w) * out_ch;
+                for (uint32_t i = 0; i < p.pw; ++i) {
+                    uint8_t* o = dst_row + (size_t)(p.x0 + i * p.dx) * out_ch;
+                    if (color == 3) {
+                        int const idx = line[i];
+                        if (idx >= pal_len) bad("PNG palette index out of range");
+                        o[0] = palette[idx][0]; o[1] = palette[idx][1]; o[2] = palette[idx][2];
+                        if (out_ch == 4) o[3] = palette[idx][3];
+                    } else if (depth == 16) {
+                        uint8_t const* s16 = &line[(size_t)i * samples * 2];
+                        bool is_key = have_trns;
+                        for (int k = 0; k < samples; ++k) {
+                            o[k] = s16[2 * k];  // the high byte
+                            if (have_trns && (uint16_t)((s16[2 * k] << 8) | s16[2 * k + 1]) != key[k]) is_key = false;
+                        }
+                        if (out_ch > samples) o[samples] = is_key ? 0 : 255;
+                    } else {
+                        uint8_t const* s8 = &line[(size_t)i * samples];
+                        bool is_key = have_trns;
+                        for (int k = 0; k < samples; ++k) {
+                            o[k] = s8[k];
+                            if (have_trns && s8[k] != (uint8_t)((key[k] & 255) * (color == 0 ? depth_scale[depth] : 1))) is_key = false;
+                        }
+                        if (out_ch > samples) o[samples] = is_key ? 0 : 255;
+                    }
+                }
+                prev.swap(cur);
+            }
+        }
+    } catch (...) {
+        image_free(px);
+        throw;
     }
     extent[0] = (int)w;
     extent[1] = (int)h;
-    *channels = ch;
+    *channels = out_ch;
     return px;
 }
 

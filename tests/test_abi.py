@@ -319,3 +319,84 @@ def test_image_class_owns_library_pixels(tmp_path):
     assert st[4] >= plain0 + 3 and st[0] == 0  # nothing is page-locked while no GPU environment exists
     assert dl.api().create_image(0, 4, 4) is None
     dl.api().destroy_image(None)
+
+
+def _raw_load(path):
+    a = dl.api()
+    e = (ctypes.c_int * 2)()
+    ch = ctypes.c_int()
+    px = ctypes.c_void_p()
+    assert a.load_image(str(path).encode(), e, ctypes.byref(ch), ctypes.byref(px)) == 0, a.last_error()
+    arr = np.ctypeslib.as_array(ctypes.cast(px, ctypes.POINTER(ctypes.c_uint8)), shape=(e[1], e[0], ch.value)).copy()
+    a.destroy_image(px)
+    return arr
+
+
+def test_load_image_reads_every_png_flavour(tmp_path):
+    """stb_image (behind the reference's load_image) reads every PNG colour type and bit depth, palettes, tRNS and Adam7
+    interlacing; 16-bit samples keep their high byte, sub-byte grey is scaled to 0..255, tRNS adds an alpha channel."""
+    import struct
+    import warnings
+    import zlib
+    from PIL import Image
+    rng = np.random.default_rng(1)
+    pic = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    pic[5:15] = pic[4]
+    rgba = np.dstack([pic, rng.integers(0, 256, (37, 53), dtype=np.uint8)])
+    grey = pic[..., 0]
+
+    def check(name, img, want, **kw):
+        img.save(tmp_path / name, **kw)
+        got = _raw_load(tmp_path / name)
+        want = want.reshape(want.shape[0], want.shape[1], -1)
+        assert got.shape == want.shape and np.array_equal(got, want), name
+
+    for colours, bits in ((37, 8), (13, 4), (4, 2), (2, 1)):  # palettes at every index width
+        pal = Image.fromarray(pic).quantize(colours)
+        check(f"p{bits}.png", pal, np.asarray(pal.convert("RGB")), bits=bits)
+    palt = Image.fromarray(pic).quantize(20)
+    palt.save(tmp_path / "pt.png", transparency=3)          # palette + tRNS -> 4 channels
+    assert np.array_equal(_raw_load(tmp_path / "pt.png"), np.asarray(Image.open(tmp_path / "pt.png").convert("RGBA")))
+    one = Image.fromarray(grey > 127)
+    check("1.png", one, np.asarray(one).astype(np.uint8) * 255)  # 1-bit grey is scaled to 0 / 255
+    check("l.png", Image.fromarray(grey), grey)
+    check("la.png", Image.fromarray(np.dstack([grey, pic[..., 1]]), "LA"), np.dstack([grey, pic[..., 1]]))  # 2 channels, as stb reports
+    with pytest.raises(dl.Exception, match="2 channels"):
+        dl.Image.load(tmp_path / "la.png")                  # ... which the façade's Channels enum cannot name
+    check("rgb.png", Image.fromarray(pic), pic)
+    check("rgba.png", Image.fromarray(rgba), rgba)
+    g16 = rng.integers(0, 65536, (37, 53), dtype=np.uint16)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        check("g16.png", Image.fromarray(g16, "I;16"), (g16 >> 8).astype(np.uint8))  # 16-bit: the high byte
+    Image.fromarray(grey).save(tmp_path / "lk.png", transparency=int(grey[0, 0]))     # grey + colour key -> grey + alpha
+    assert np.array_equal(_raw_load(tmp_path / "lk.png"), np.dstack([grey, np.where(grey == grey[0, 0], 0, 255).astype(np.uint8)]))
+    Image.fromarray(pic).save(tmp_path / "rk.png", transparency=tuple(int(v) for v in pic[0, 0]))
+    alpha = np.where((pic == pic[0, 0]).all(-1), 0, 255).astype(np.uint8)
+    assert np.array_equal(_raw_load(tmp_path / "rk.png"), np.dstack([pic, alpha]))
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+
+    def adam7(arr, colour):  # PIL writes no interlaced files: the seven passes by hand, filter type 0
+        h, w = arr.shape[:2]
+        s = arr.reshape(h, w, -1)
+        raw = b""
+        for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+            sub = s[y0::dy, x0::dx]
+            if sub.size:
+                raw += b"".join(b"\x00" + row.tobytes() for row in sub)
+        ihdr = struct.pack(">IIBBBBB", w, h, 8, colour, 0, 0, 1)
+        return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+
+    for name, arr, colour in (("i_rgb.png", pic, 2), ("i_small.png", pic[:3, :5].copy(), 2), ("i_rgba.png", rgba, 6), ("i_grey.png", grey[:9, :2].copy(), 0)):
+        (tmp_path / name).write_bytes(adam7(arr, colour))
+        assert np.array_equal(_raw_load(tmp_path / name), arr.reshape(arr.shape[0], arr.shape[1], -1)), name
+    a = dl.api()
+    ext = (ctypes.c_int * 2)()
+    ch = ctypes.c_int()
+    px = ctypes.c_void_p()
+    bad = bytearray(adam7(pic, 2))
+    bad[24] = 3  # bit depth 3 does not exist
+    (tmp_path / "bad_depth.png").write_bytes(bytes(bad))
+    assert a.load_image(str(tmp_path / "bad_depth.png").encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 1
