@@ -464,10 +464,11 @@ struct JpegBits {
 };
 
 inline uint8_t jclamp(int x) { return (uint8_t)((unsigned)x > 255 ? (x < 0 ? 0 : 255) : x); }
+inline uint8_t jclamp(int64_t x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
 
-#define DLIMG_F2F(x) ((int)(((x) * 4096 + 0.5)))
+#define DLIMG_F2F(x) ((int64_t)(((x) * 4096 + 0.5)))
 #define DLIMG_IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)        \
-    int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;   \
+    int64_t t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3; \
     p2 = s2;                                                  \
     p3 = s6;                                                  \
     p1 = (p2 + p3) * DLIMG_F2F(0.5411961f);                   \
@@ -503,12 +504,14 @@ inline uint8_t jclamp(int x) { return (uint8_t)((unsigned)x > 255 ? (x < 0 ? 0 :
     t1 += p2 + p4;                                            \
     t0 += p1 + p3;
 
+// (64-bit intermediates: the arithmetic is stb_image's, but a corrupt stream can carry coefficients whose products leave 32
+// bits, which is undefined behaviour for the int the published code uses; results are identical whenever that one is defined)
 void jpeg_idct_block(uint8_t* out, int out_stride, short const data[64]) {
-    int val[64], *v = val;
+    int64_t val[64], *v = val;
     short const* d = data;
     for (int i = 0; i < 8; ++i, ++d, ++v) {  // columns
         if (d[8] == 0 && d[16] == 0 && d[24] == 0 && d[32] == 0 && d[40] == 0 && d[48] == 0 && d[56] == 0) {
-            int const dcterm = d[0] * 4;
+            int64_t const dcterm = (int64_t)d[0] * 4;
             v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dcterm;
         } else {
             DLIMG_IDCT_1D(d[0], d[8], d[16], d[24], d[32], d[40], d[48], d[56])
@@ -634,6 +637,7 @@ uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* exte
             int const t = br.decode(dc[c.td]);
             if (t > 15) bad("bad DC code");
             c.dc_pred += br.receive_extend(t);
+            if (c.dc_pred < -32768 || c.dc_pred > 32767) bad("bad DC delta");  // (a valid predictor has 12 bits; keeps the sums in range)
             blk[0] = (short)(c.dc_pred * quant[c.tq][0]);
             for (int k = 1; k < 64;) {
                 int const rs = br.decode(ac[c.ta]);
@@ -654,6 +658,7 @@ uint8_t* load_jpeg(std::vector<uint8_t> const& file, char const* path, int* exte
                 int const t = br.decode(dc[c.td]);
                 if (t > 15) bad("bad DC code");
                 c.dc_pred += br.receive_extend(t);
+                if (c.dc_pred < -32768 || c.dc_pred > 32767) bad("bad DC delta");
                 blk[0] = (short)(c.dc_pred * (1 << al));
             } else if (getbit()) {  // refinement: one more bit of precision
                 blk[0] = (short)(blk[0] + (1 << al));
