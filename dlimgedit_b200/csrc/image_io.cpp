@@ -1240,6 +1240,117 @@ void chunk(std::vector<uint8_t>& out, char const* type, std::vector<uint8_t> con
     put_be32(out, crc32(&out[start], out.size() - start));
 }
 
+// zlib stream for the PNG writer: deflate with the FIXED Huffman code (RFC 1951 3.2.6) over a greedy LZ77 match search
+// (hash of three bytes, chains of up to 24 candidates, 32 KiB window) -- the same class of encoder as the stb_image_write
+// the reference saves with; masks shrink from megabytes to kilobytes.  Off the hot path.
+struct BitWriter {
+    std::vector<uint8_t>& out;
+    uint32_t acc = 0;
+    int n = 0;
+    void bits(uint32_t v, int count) {  // LSB first
+        acc |= v << n;
+        n += count;
+        while (n >= 8) {
+            out.push_back((uint8_t)(acc & 0xFF));
+            acc >>= 8;
+            n -= 8;
+        }
+    }
+    void code(uint32_t c, int count) {  // Huffman codes go out MSB first
+        uint32_t r = 0;
+        for (int i = 0; i < count; ++i) r |= ((c >> i) & 1u) << (count - 1 - i);
+        bits(r, count);
+    }
+    void flush() {
+        if (n > 0) bits(0, 8 - n);
+    }
+};
+
+std::vector<uint8_t> zlib_compress(std::vector<uint8_t> const& raw) {
+    static uint16_t const lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static uint8_t const lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static uint16_t const dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static uint8_t const dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    std::vector<uint8_t> z;
+    z.reserve(raw.size() / 4 + 64);
+    z.push_back(0x78);
+    z.push_back(0x5E);  // 32 KiB window, "fast" level; (0x785E) % 31 == 0
+    BitWriter bw{z};
+    bw.bits(1, 1);  // final block
+    bw.bits(1, 2);  // fixed Huffman codes
+    auto literal = [&](int v) {
+        if (v < 144) bw.code(0x30 + (uint32_t)v, 8);
+        else bw.code(0x190 + (uint32_t)(v - 144), 9);
+    };
+    auto length_distance = [&](int len, int dist) {
+        int lc = 28;
+        while (lbase[lc] > len) --lc;
+        int const sym = 257 + lc;
+        if (sym < 280) bw.code((uint32_t)(sym - 256), 7);
+        else bw.code(0xC0 + (uint32_t)(sym - 280), 8);
+        if (lext[lc]) bw.bits((uint32_t)(len - lbase[lc]), lext[lc]);
+        int dc = 29;
+        while (dbase[dc] > dist) --dc;
+        bw.code((uint32_t)dc, 5);
+        if (dext[dc]) bw.bits((uint32_t)(dist - dbase[dc]), dext[dc]);
+    };
+    constexpr int kHashBits = 15, kWindow = 32768, kMaxChain = 24;
+    std::vector<int32_t> head((size_t)1 << kHashBits, -1), prev(raw.size(), -1);
+    size_t const n = raw.size();
+    auto hash3 = [&](size_t i) { return (uint32_t)(((raw[i] << 16) | (raw[i + 1] << 8) | raw[i + 2]) * 2654435761u) >> (32 - kHashBits); };
+    auto insert = [&](size_t i) {
+        if (i + 2 < n) {
+            uint32_t const h = hash3(i);
+            prev[i] = head[h];
+            head[h] = (int32_t)i;
+        }
+    };
+    size_t i = 0;
+    while (i < n) {
+        int best_len = 0, best_dist = 0;
+        if (i + 2 < n) {
+            int32_t cand = head[hash3(i)];
+            int const max_len = (int)std::min<size_t>(258, n - i);
+            for (int chain = 0; cand >= 0 && chain < kMaxChain && i - (size_t)cand <= (size_t)kWindow; ++chain, cand = prev[(size_t)cand]) {
+                if (raw[(size_t)cand + (size_t)best_len] != raw[i + (size_t)best_len]) continue;  // cannot beat the best so far
+                int len = 0;
+                while (len < max_len && raw[(size_t)cand + (size_t)len] == raw[i + (size_t)len]) ++len;
+                if (len > best_len) {
+                    best_len = len;
+                    best_dist = (int)(i - (size_t)cand);
+                    if (len == max_len) break;
+                }
+            }
+        }
+        if (best_len >= 3) {
+            length_distance(best_len, best_dist);
+            for (int k = 0; k < best_len; ++k) insert(i + (size_t)k);
+            i += (size_t)best_len;
+        } else {
+            literal(raw[i]);
+            insert(i);
+            ++i;
+        }
+    }
+    bw.code(0, 7);  // end of block
+    bw.flush();
+    if (z.size() > raw.size() + raw.size() / 65535 * 5 + 16) {
+        // incompressible data (the fixed code spends nine bits on bytes >= 144): stored blocks instead
+        z.resize(2);
+        size_t pos = 0;
+        do {
+            size_t const len = std::min<size_t>(65535, raw.size() - pos);
+            z.push_back(pos + len == raw.size() ? 1 : 0);
+            z.push_back((uint8_t)(len & 0xFF)); z.push_back((uint8_t)(len >> 8));
+            z.push_back((uint8_t)(~len & 0xFF)); z.push_back((uint8_t)((~len >> 8) & 0xFF));
+            z.insert(z.end(), raw.begin() + (long)pos, raw.begin() + (long)(pos + len));
+            pos += len;
+        } while (pos < raw.size());
+    }
+    put_be32(z, adler32(raw.data(), raw.size()));
+    return z;
+}
+
 }  // namespace
 
 uint8_t* load_image(char const* filepath, int* out_extent, int* out_channels) {
@@ -1257,28 +1368,40 @@ uint8_t* load_image(char const* filepath, int* out_extent, int* out_channels) {
 void save_image(dlimg_ImageView const& img, char const* filepath) {
     if (!(img.channels == CH_MASK || img.channels == CH_RGB || img.channels == CH_RGBA))
         fail("Unsupported channel order [" + std::to_string(img.channels) + "]");
+    if (img.width <= 0 || img.height <= 0 || !img.pixels) fail(std::string("Failed to save image ") + filepath);
     int const comp = bytes_per_pixel(img.channels);
     size_t const row = (size_t)img.width * comp;
+    // scanlines with the PNG filter (none / sub / up / average / Paeth) that leaves the smallest sum of magnitudes
     std::vector<uint8_t> raw;
-    raw.reserve((row + 1) * img.height);
+    raw.reserve((row + 1) * (size_t)img.height);
+    std::vector<uint8_t> cand[5];
+    for (auto& c : cand) c.resize(row);
+    std::vector<uint8_t> const zeros(row, 0);
     for (int y = 0; y < img.height; ++y) {
-        raw.push_back(0);  // filter type none
         uint8_t const* src = img.pixels + (size_t)y * row;
-        raw.insert(raw.end(), src, src + row);
+        uint8_t const* up = y ? src - row : zeros.data();
+        for (size_t x = 0; x < row; ++x) {
+            int const a = x >= (size_t)comp ? src[x - (size_t)comp] : 0, b = up[x], c = x >= (size_t)comp ? up[x - (size_t)comp] : 0;
+            cand[0][x] = src[x];
+            cand[1][x] = (uint8_t)(src[x] - a);
+            cand[2][x] = (uint8_t)(src[x] - b);
+            cand[3][x] = (uint8_t)(src[x] - ((a + b) >> 1));
+            cand[4][x] = (uint8_t)(src[x] - paeth(a, b, c));
+        }
+        int best = 0;
+        uint64_t best_cost = UINT64_MAX;
+        for (int f = 0; f < 5; ++f) {
+            uint64_t cost = 0;
+            for (size_t x = 0; x < row; ++x) cost += (uint64_t)std::abs((int)(int8_t)cand[f][x]);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = f;
+            }
+        }
+        raw.push_back((uint8_t)best);
+        raw.insert(raw.end(), cand[best].begin(), cand[best].end());
     }
-    std::vector<uint8_t> z;
-    z.push_back(0x78);
-    z.push_back(0x01);
-    size_t pos = 0;
-    do {  // stored deflate blocks (no compression: the mask path is not size sensitive)
-        size_t const n = std::min<size_t>(65535, raw.size() - pos);
-        z.push_back(pos + n == raw.size() ? 1 : 0);
-        z.push_back((uint8_t)(n & 0xFF)); z.push_back((uint8_t)(n >> 8));
-        z.push_back((uint8_t)(~n & 0xFF)); z.push_back((uint8_t)((~n >> 8) & 0xFF));
-        z.insert(z.end(), raw.begin() + (long)pos, raw.begin() + (long)(pos + n));
-        pos += n;
-    } while (pos < raw.size());
-    put_be32(z, adler32(raw.data(), raw.size()));
+    std::vector<uint8_t> const z = zlib_compress(raw);
 
     std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     std::vector<uint8_t> ihdr;

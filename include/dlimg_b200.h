@@ -87,9 +87,9 @@ struct dlimg_Api {
     /* reference dlimgedit.cpp:81-90 (stb image I/O).  load_image: PNG (every colour type and bit depth, palettes, tRNS, Adam7; 16-bit samples keep the high byte),
      * JPEG (8-bit, Huffman, sequential or progressive; stb_image's IDCT / chroma upsampling / colour conversion
      * restated), BMP (palettes, 16 / 24 / 32 bits, bit fields; no RLE), TGA (types 1 / 2 / 3 and their run-length
-     * forms) and binary PGM / PPM; arithmetic-coded / lossless JPEG are refused.  save_image: PNG
-     * (stored deflate) for mask / rgb / rgba.  Pixel buffers of load_image / create_image are released with
-     * destroy_image; while a GPU environment is alive they are page-locked and recycled by size, so process /
+     * forms) and binary PGM / PPM; arithmetic-coded / lossless JPEG are refused.  save_image: PNG (filtered
+     * scanlines, fixed-Huffman deflate) for mask / rgb / rgba.  Pixel buffers of load_image / create_image are released
+     * with destroy_image; while a GPU environment is alive they are page-locked and recycled by size, so process /
      * get_segmentation_mask on them copy over PCIe without pageable staging (csrc/image_pool.hpp). */
     dlimg_Result (*load_image)(char const*, int* out_extent, int* out_channels, uint8_t** out_pixels);
     dlimg_Result (*save_image)(dlimg_ImageView const*, char const*);

@@ -400,3 +400,30 @@ def test_load_image_reads_every_png_flavour(tmp_path):
     bad[24] = 3  # bit depth 3 does not exist
     (tmp_path / "bad_depth.png").write_bytes(bytes(bad))
     assert a.load_image(str(tmp_path / "bad_depth.png").encode(), ext, ctypes.byref(ch), ctypes.byref(px)) == 1
+
+
+def test_save_image_writes_compressed_png(tmp_path):
+    """save_image (reference image.cpp:25-35 -> stbi_write_png): filtered scanlines in a fixed-Huffman deflate stream.
+    Any PNG reader must get the pixels back; a mask shrinks by two orders of magnitude; noise falls back to stored blocks."""
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    yy, xx = np.mgrid[0:600, 0:900]
+    mask = (((xx - 450) ** 2 + (yy - 300) ** 2 < 200 ** 2) * 255).astype(np.uint8)
+    photo = np.clip(np.stack([127 + 100 * np.sin(xx / 37.0), 127 + 100 * np.cos(yy / 23.0), (xx + yy) % 256], -1)
+                    + rng.normal(0, 3, (600, 900, 3)), 0, 255).astype(np.uint8)
+    cases = [("mask.png", mask, dl.Channels.mask), ("photo.png", photo, dl.Channels.rgb),
+             ("rgba.png", np.dstack([photo[:100, :150], mask[:100, :150]]), dl.Channels.rgba),
+             ("noise.png", rng.integers(0, 256, (97, 131, 3), dtype=np.uint8), dl.Channels.rgb),
+             ("one.png", np.array([[9]], np.uint8), dl.Channels.mask), ("flat.png", np.full((5, 300, 3), 7, np.uint8), dl.Channels.rgb)]
+    sizes = {}
+    for name, arr, ch in cases:
+        img = dl.Image(dl.Extent(arr.shape[1], arr.shape[0]), ch)
+        img.pixels[:] = arr
+        dl.Image.save(img, tmp_path / name)
+        assert np.array_equal(np.asarray(Image.open(tmp_path / name)), arr), name      # libpng reads it
+        assert np.array_equal(dl.Image.load(tmp_path / name).pixels, arr), name        # and so does the library
+        sizes[name] = (tmp_path / name).stat().st_size
+    assert sizes["mask.png"] < mask.size // 50
+    assert sizes["photo.png"] < photo.size * 0.9
+    assert sizes["noise.png"] < 97 * 131 * 3 + 300       # stored blocks: no worse than raw + framing
+    assert sizes["flat.png"] < 200
