@@ -10,9 +10,11 @@ algorithm that `script/export_models.py:21-43` exports, anchored on the referenc
   * constant mask input / has_mask=0   reference src/segmentation.cpp:43-45
 
 Self-consistency gates (tests/test_oracle_model.py): learnable-parameter count == 10,130,092 with the
-published split (prompt encoder 6,220 / mask decoder 4,058,340), and the decoder half agrees with
-`transformers.models.sam` (an independent restatement of the same published algorithm) given copied
-weights.
+published split (prompt encoder 6,220 / mask decoder 4,058,340), and everything but the TinyViT trunk agrees
+with `transformers.models.sam` (an independent restatement of the same published algorithm) given copied
+weights: mask decoder, prompt assembly + dense positional grid, mask post-processing + threshold, the
+resized-extent rule and the normalise + pad preprocessing.  The TinyViT-5M trunk has no independent
+implementation in this image (no timm): it is pinned by the parameter split and its shapes only.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this module.  The product path (dlimgedit_b200/csrc) never does.
