@@ -201,3 +201,14 @@ def test_image_tensor_and_preprocessing_match_transformers_sam(oracle_sam):
     assert np.all(ours[:, :, 683:, :] == 0) and np.all(theirs[:, :, 683:, :] == 0)
     bgra = np.dstack([rgb[..., ::-1], rng.integers(0, 256, (683, 1024), dtype=np.uint8)])
     assert np.array_equal(P.create_image_tensor(bgra, 5), t)   # Channels::bgra (dlimgedit.hpp:29): same planes, alpha dropped
+
+
+@pytest.mark.parametrize("ws", [7, 14])
+def test_attention_bias_index_table_matches_levit(ws):
+    """TinyViT's attention takes its relative-position bias table from LeViT (first-seen ordering of (|dy|, |dx|) offsets over
+    itertools.product pairs); `transformers`' LevitAttention builds the same table independently."""
+    from transformers.models.levit.modeling_levit import LevitAttention
+    att = LevitAttention(hidden_sizes=32, key_dim=8, num_attention_heads=2, attention_ratio=1, resolution=ws)
+    idx, n_off = R.attention_bias_idxs(ws)
+    assert n_off == att.attention_biases.shape[1] == ws * ws
+    assert torch.equal(idx, att.attention_bias_idxs)
