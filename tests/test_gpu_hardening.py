@@ -199,6 +199,8 @@ def test_many_handles_leave_no_device_or_pinned_memory_behind(env):
         seg.close()
 
     def pool_in_use():
+        import gc
+        gc.collect()  # (library buffers that only a reference cycle of an earlier test keeps alive are released first)
         st = (ctypes.c_uint64 * 5)()
         dl.debug().image_pool_stats(st)
         return st[0]
