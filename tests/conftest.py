@@ -48,13 +48,41 @@ def model_dir(tmp_path_factory):
     return str(d)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _device_fills_complete_before_use():
+    """The tests hand the library device buffers that torch has just filled (torch.zeros(..., device="cuda") for outputs) on
+    torch's stream -- in a pytest process the legacy default stream, whose handle 0 the C ABI reads as "the environment's own
+    stream".  That stream is non-blocking, so a library kernel could run before or UNDER the pending fill (seen once as ~2000
+    cleared mask pixels in test_gpu_prepost).  Same contract as for any caller -- share a stream or synchronize -- and the
+    tests synchronize: device fills return only when they have completed.  (Host-to-device copies of pageable tensors,
+    `.cuda()`, are complete on return anyway; the debug-table kernels run on the legacy stream itself.)"""
+    if not _has_gpu():
+        yield
+        return
+    import torch
+    originals = {name: getattr(torch, name) for name in ("zeros", "ones", "full", "zeros_like", "ones_like", "full_like")}
+
+    def synchronous(fn):
+        def wrapped(*args, **kwargs):
+            t = fn(*args, **kwargs)
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                torch.cuda.synchronize()
+            return t
+        return wrapped
+
+    for name, fn in originals.items():
+        setattr(torch, name, synchronous(fn))
+    yield
+    for name, fn in originals.items():
+        setattr(torch, name, fn)
+
+
 @pytest.fixture(scope="session")
 def env(model_dir):
     import dlimgedit_b200 as dl
     e = dl.Environment(dl.Options(dl.Backend.gpu, model_dir))
-    # The tests hand the library device tensors that torch has just filled on ITS stream; the library's own stream is
-    # non-blocking, so without this a kernel could run before (or under) a pending torch.zeros / .cuda() of its operands
-    # (seen once as ~2000 cleared mask pixels).  Same contract as for any caller: share a stream or synchronize.
+    # (torch's current stream in a pytest process is the legacy default stream, handle 0 = "the environment's own stream" for
+    # the C ABI: the library works on its own non-blocking stream in these tests; see _device_fills_complete_before_use)
     import torch
     e.set_stream(torch.cuda.current_stream().cuda_stream)
     yield e
