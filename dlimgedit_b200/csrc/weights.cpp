@@ -1,6 +1,7 @@
 // weights.cpp -- see weights.hpp.
 #include "weights.hpp"
 
+#include <cstdint>
 #include <cstring>
 #include <fstream>
 
@@ -24,20 +25,35 @@ WeightFile WeightFile::load(std::string const& path) {
     uint32_t const version = read_pod<uint32_t>(f);
     if (version != 1) fail("Unsupported weight container version " + std::to_string(version));
     uint32_t const count = read_pod<uint32_t>(f);
+    // every size in the header is checked against the size of the file before anything is allocated for it
+    f.seekg(0, std::ios::end);
+    uint64_t const file_size = (uint64_t)f.tellg();
+    f.seekg(16, std::ios::beg);
+    constexpr uint64_t kMinRecord = 2 + 1 + 8 + 8;  // name length, rank, offset, element count
+    if ((uint64_t)count * kMinRecord > file_size) fail("Corrupt weight container: tensor count exceeds the file: " + path);
     struct Rec { std::string name; std::vector<int64_t> shape; uint64_t offset, numel; };
     std::vector<Rec> recs(count);
     for (auto& r : recs) {
         uint16_t const len = read_pod<uint16_t>(f);
+        if ((uint64_t)f.tellg() + len > file_size) fail("Corrupt weight container: truncated tensor name");
         r.name.resize(len);
         f.read(&r.name[0], len);
+        if (!f) fail("Unexpected end of weight file");
         uint8_t const ndim = read_pod<uint8_t>(f);
+        if (ndim > 8) fail("Corrupt weight container: rank " + std::to_string(ndim) + " of " + r.name);
         r.shape.resize(ndim);
         for (auto& d : r.shape) d = read_pod<uint32_t>(f);
         r.offset = read_pod<uint64_t>(f);
         r.numel = read_pod<uint64_t>(f);
         uint64_t n = 1;
-        for (auto d : r.shape) n *= (uint64_t)d;
-        if (n != r.numel) fail("Corrupt weight container: shape/numel mismatch for " + r.name);
+        bool overflow = false;
+        for (auto d : r.shape) {
+            if (d != 0 && n > UINT64_MAX / (uint64_t)d) overflow = true;
+            n *= (uint64_t)d;
+        }
+        if (overflow || n != r.numel) fail("Corrupt weight container: shape/numel mismatch for " + r.name);
+        if (r.numel > file_size / sizeof(float) || r.offset > file_size || r.offset + r.numel * sizeof(float) > file_size)
+            fail("Corrupt weight container: payload of " + r.name + " lies outside the file");
     }
     std::streamoff const payload = f.tellg();
     WeightFile wf;
@@ -46,6 +62,7 @@ WeightFile WeightFile::load(std::string const& path) {
         HostTensor t;
         t.shape = r.shape;
         t.data.resize(r.numel);
+        if ((uint64_t)payload + r.offset + r.numel * sizeof(float) > file_size) fail("Corrupt weight container: payload truncated at " + r.name);
         f.seekg(payload + (std::streamoff)r.offset);
         f.read(reinterpret_cast<char*>(t.data.data()), (std::streamsize)(r.numel * sizeof(float)));
         if (!f) fail("Corrupt weight container: payload truncated at " + r.name);
